@@ -1,0 +1,205 @@
+/* pf_b200.h — C ABI of libpf_b200.so: the B200 (sm_100a) kernels behind PocketFlow's
+ * compression-aware training step.
+ *
+ * The reference (Tencent/PocketFlow) has no FFI: its de-facto operator boundary is the set of
+ * private learner methods that emit TensorFlow op chains.  Each entry point below replaces one
+ * such chain; the comment above it cites the reference file:line it stands in for.
+ *
+ * Conventions:
+ *   - every function returns int: 0 = ok, <0 = pf_status, >0 = cudaError_t;
+ *     pf_last_error() returns a thread-local human-readable message for the last failure.
+ *   - the caller owns every buffer (inputs, outputs, workspaces, descriptor tables); kernels
+ *     never allocate.  Pointers named *_dev are device pointers; `stream` is a cudaStream_t
+ *     passed as void* (0 = legacy default stream).
+ *   - all calls are asynchronous with respect to the host (enqueue only) unless stated.
+ *   - fp32 everywhere ("u32"/"u8" where noted); tensors are dense, NHWC activations,
+ *     HWIO ([kh,kw,cin,cout]) kernels — the TF layouts the reference uses.
+ *   - there is NO CPU fallback anywhere in this library.
+ */
+#ifndef PF_B200_H_
+#define PF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PF_B200_ABI_VERSION 1
+
+typedef enum pf_status {
+  PF_OK = 0,
+  PF_ERR_INVALID_ARG = -1,  /* bad size / null pointer / unsupported mode (Python raises ValueError) */
+  PF_ERR_UNSUPPORTED = -2,  /* shape outside what the kernel implements                              */
+  PF_ERR_NO_DEVICE = -3,    /* no CUDA device / driver                                              */
+  PF_ERR_NCCL = -4,         /* NCCL missing or returned an error                                    */
+  PF_ERR_INTERNAL = -5
+} pf_status;
+
+int pf_abi_version(void);
+const char* pf_last_error(void);
+/* Number of kernel launches this library has enqueued in this process (bench.py "gpu_launches"). */
+int64_t pf_launch_count(void);
+void pf_launch_count_reset(void);
+/* Device query helper: SM count of the current device (148 on B200). */
+int pf_sm_count(int* out);
+
+/* ---------------------------------------------------------------------------------------------
+ * Ordered-uint encoding of float min/max slots.  enc(f) is monotone in f, so atomicMin/atomicMax
+ * on uint32 implement float min/max.  A min slot starts at 0xFFFFFFFF, a max slot at 0.
+ *   enc(f) = bits(f) ^ (bits(f) >> 31 ? 0xFFFFFFFF : 0x80000000)
+ * ------------------------------------------------------------------------------------------- */
+
+/* ---------------------------------------------------------------------------------------------
+ * a1  Weight fake-quantization, multi-tensor (one launch pair for every layer).
+ *     Replaces UniformQuantization.__uniform_quantize(mode='weight') + __scale + __inv_scale +
+ *     __channel_bucket / __split_bucket — learners/uniform_quantization/utils.py:163-289.
+ *
+ *     Every tensor is described by one pf_uq_seg.  Bucket id of flat element i is (i % ncols):
+ *       per-layer  (use_buckets=False): ncols = 1,              padded = numel
+ *       'channel'  (reshape [-1,cout], reduce axis 0): ncols = cout, padded = numel
+ *       'split'    (pad with copies of the LAST element to a multiple of bucket_size, reshape
+ *                   [bucket_size,-1], reduce axis 0): ncols = padded/bucket_size; elements
+ *                   i in [numel,padded) read src[numel-1]   (utils.py:247-274: strided buckets)
+ *     qw = alpha*(rint((w-beta)/alpha*k)/k)+beta, alpha=(max-min)+1e-10f, beta=min,
+ *     k=float(2^bits-1); round-half-even; every op individually rounded (no FMA contraction).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct pf_uq_seg {
+  const float* src;   /* device; 16-byte aligned                                  */
+  float* dst;         /* device; 16-byte aligned; may equal src                   */
+  int64_t numel;      /* < 2^31                                                    */
+  int64_t padded;     /* >= numel; multiple of ncols                               */
+  int32_t ncols;      /* number of buckets of this tensor                          */
+  int32_t bucket0;    /* first slot of this tensor in mn_enc/mx_enc (multiple of 4)*/
+  int32_t bits;       /* 1..32                                                     */
+  int32_t reserved;
+} pf_uq_seg;
+
+/* One unit of CTA work.  kind 0: flat chunk [start, start+count) of seg (elementwise kernels and
+ * per-layer min/max).  kind 1: column tile for bucketed min/max: columns [c0, c0+ncol_tile),
+ * rows [start, start+count) of the [padded/ncols, ncols] view. */
+typedef struct pf_work {
+  int32_t seg;
+  int32_t kind;
+  int64_t start;
+  int32_t count;
+  int32_t c0;
+  int32_t ncol_tile;
+  int32_t reserved;
+} pf_work;
+
+/* Phase 1: per-bucket min/max into ordered-uint slots (caller pre-fills mn_enc with 0xFF bytes and
+ * mx_enc with 0 — pf_fill_u32 does both).  work table = pf_uq_plan_minmax (host side, Python). */
+int pf_uq_weight_minmax(const pf_uq_seg* segs_dev, const pf_work* work_dev, int n_work,
+                        uint32_t* mn_enc_dev, uint32_t* mx_enc_dev, void* stream);
+/* Phase 2: quantize.  work table: kind-0 chunks.  (The second read of the weights is an L2 hit:
+ * all weights of ResNet-50 are 94 MB < 126 MB L2.) */
+int pf_uq_weight_quant(const pf_uq_seg* segs_dev, const pf_work* work_dev, int n_work,
+                       const uint32_t* mn_enc_dev, const uint32_t* mx_enc_dev, void* stream);
+/* a3  STE backward of the weight quantizer as a stand-alone op, in place on the gradient:
+ *     g <- (((g*alpha)/k)*k)/alpha   (gradient_override_map Round->Identity, utils.py:185-186;
+ *     min/max under stop_gradient, :224-225).  segs[i].src/dst point at the gradient. */
+int pf_uq_weight_ste_bwd(const pf_uq_seg* segs_dev, const pf_work* work_dev, int n_work,
+                         const uint32_t* mn_enc_dev, const uint32_t* mx_enc_dev, void* stream);
+
+/* a2  Activation fake-quantization (per-TENSOR min/max, utils.py:51-79, 215-231).
+ *     minmax: accumulates into minmax_enc_dev[0] (min) / [1] (max) (pre-filled 0xFFFFFFFF / 0).
+ *     quant : y = Q(x) with the scalar range; src may equal dst. */
+int pf_uq_act_minmax(const float* x_dev, int64_t n, uint32_t* minmax_enc_dev, void* stream);
+int pf_uq_act_quant(const float* x_dev, float* y_dev, int64_t n, const uint32_t* minmax_enc_dev,
+                    int bits, void* stream);
+
+int pf_fill_u32(uint32_t* p_dev, int64_t n, uint32_t value, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a5  Magnitude-threshold mask build, multi-tensor.
+ *     Replaces WeightSparseLearner.__build_masks — learners/weight_sparsification/learner.py:260-294:
+ *        bkup = where(mask > 0.5, w, bkup); thr = percentile(|bkup|, 100*s) ('nearest': the
+ *        element at index rank_desc of the DESCENDING sort); mask = float(|bkup| > thr);
+ *        w = bkup*mask.
+ *     The order statistic is found exactly by a 4-pass radix select on the IEEE bit pattern of
+ *     |bkup| (no sort, no approximation) so masks are bit-exact.
+ *     ranks_desc_dev[i] = clip(int32(rint((n-1)*(1-q/100))),0,n-1), computed on the host in
+ *     float64 exactly as tf.contrib.distributions.percentile does.
+ *     workspace_dev: n_seg * PF_WS_WORKSPACE_U32_PER_SEG uint32 (zeroed by the call).
+ *     thr_out_dev (optional, n_seg floats) receives each tensor's threshold.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct pf_ws_seg {
+  float* w;
+  float* bkup;
+  float* mask;
+  int64_t numel;
+} pf_ws_seg;
+#define PF_WS_WORKSPACE_U32_PER_SEG (256 + 8)
+
+int pf_ws_mask_build(const pf_ws_seg* segs_dev, int n_seg, const pf_work* work_dev, int n_work,
+                     const int64_t* ranks_desc_dev, uint32_t* workspace_dev, float* thr_out_dev,
+                     void* stream);
+
+/* Exact k-th order statistic of plain values (not |.|), multi-tensor, used by the codebook
+ * quantile initialisation (learners/nonuniform_quantization/utils.py:349-366).  Query q reads
+ * segs[qseg[q]].bkup (numel floats) and returns the element at descending index ranks_desc[q]. */
+int pf_select_desc(const pf_ws_seg* segs_dev, const int32_t* qseg_dev, int n_query,
+                   const pf_work* work_dev, int n_work, /* work[].seg indexes QUERIES */
+                   const int64_t* ranks_desc_dev, uint32_t* workspace_dev, float* out_dev,
+                   void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a6/a9  Fused optimizer steps over flat fp32 ranges.
+ *   momentum: replaces __calc_grads_pruned (weight_sparsification/learner.py:314-332) +
+ *     MomentumOptimizer.apply_gradients (:201,:212), with the Horovod average
+ *     (utils/multi_gpu_wrapper.py:82-89) and the l2_loss gradient folded in:
+ *        gt = g*grad_scale + wd*w ; gt *= mask (if mask) ; acc = acc*mom + gt ; w -= lr*acc
+ *   adam: TF-1.x ApplyAdam (uniform_quantization/learner.py:244):
+ *        gt as above (no mask); alpha = lr*sqrt(1-b2p)/(1-b1p);
+ *        m += (gt-m)*(1-b1); v += (gt*gt-v)*(1-b2); w -= (m*alpha)/(sqrt(v)+eps)
+ *   lr/b1p/b2p are read from device scalars (hp_dev) so the step is CUDA-graph replayable:
+ *     momentum: hp_dev[0]=lr ; adam: hp_dev[0]=lr, [1]=beta1_power, [2]=beta2_power.
+ * ------------------------------------------------------------------------------------------- */
+int pf_momentum_step(float* w_dev, float* acc_dev, const float* g_dev, const float* mask_dev,
+                     int64_t n, const float* hp_dev, float momentum, float wd, float grad_scale,
+                     void* stream);
+int pf_adam_step(float* w_dev, float* m_dev, float* v_dev, const float* g_dev, int64_t n,
+                 const float* hp_dev, float beta1, float beta2, float eps, float wd,
+                 float grad_scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a7/a8  Losses.
+ *   pf_softmax_ce_fwd_bwd replaces tf.losses.softmax_cross_entropy(onehot, logits)
+ *     (nets/resnet_at_cifar10.py:104) and DistillationHelper.calc_loss
+ *     (learners/distillation_helper.py:86-103) in one pass over the N x K logits:
+ *        hard = mean_n CE(labels_n, s_n)
+ *        dst  = w_dst * mean_n CE(softmax(t_n/T), s_n/T)        (teacher_dev may be NULL)
+ *        dlogits = d(hard+dst)/ds ; correct_n = [argmax labels == argmax s]
+ *     out_dev[0]=hard, [1]=dst, [2]=accuracy (top-1), [3]=top-5 accuracy.
+ *     row_ws_dev: 4*N floats of scratch.  Deterministic (fixed-order final reduction).
+ *   pf_l2_loss: out_dev[0] = scale * sum(v^2)/2 over a flat range (tf.nn.l2_loss summed by add_n,
+ *     nets/resnet_at_cifar10.py:105-107).  partial_ws_dev: PF_L2_PARTIALS floats.
+ * ------------------------------------------------------------------------------------------- */
+int pf_softmax_ce_fwd_bwd(const float* logits_dev, const float* labels_dev,
+                          const float* teacher_dev, int n, int k, float tempr, float w_dst,
+                          float* dlogits_dev, float* out_dev, float* row_ws_dev, void* stream);
+#define PF_L2_PARTIALS 1024
+int pf_l2_loss(const float* v_dev, int64_t n, float scale, int accumulate, float* out_dev,
+               float* partial_ws_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a11 Codebook (non-uniform) weight quantization, multi-tensor, per-layer range.
+ *     Replaces NonUniformQuantization.__nonuni_quantize / __build_norm_quant_point —
+ *     learners/nonuniform_quantization/utils.py:168-194, 284-307:
+ *        xn=(w-beta)/alpha; idx=argmin_j|xn-c_j| (first index on ties);
+ *        q=c[idx]*sign(xn+1e-6); out=alpha*q+beta.
+ *     Uses pf_uq_seg (ncols must be 1; bits = log2(#centroids) <= 8) and the min/max slots of
+ *     pf_uq_weight_minmax.  clusters_dev: per seg 2^bits floats at offset seg*256.
+ *     idx_out_dev (optional): uint8 centroid index per element, laid out like the weights
+ *     (idx_base_dev[seg] = byte offset of the tensor), for the codebook gradient.
+ * ------------------------------------------------------------------------------------------- */
+int pf_nuq_weight_quant(const pf_uq_seg* segs_dev, const pf_work* work_dev, int n_work,
+                        const uint32_t* mn_enc_dev, const uint32_t* mx_enc_dev,
+                        const float* clusters_dev, uint8_t* idx_out_dev,
+                        const int64_t* idx_base_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PF_B200_H_ */

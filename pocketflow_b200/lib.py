@@ -1,0 +1,72 @@
+"""ctypes binding of libpf_b200.so (the C ABI declared in include/pf_b200.h).
+
+There is NO fallback: if the shared library is missing or fails to load, importing any
+compute entry point raises immediately (north star: "no CPU fallback").  Build it with
+``python -c "import __graft_entry__ as g; g.build()"`` or ``make -C pocketflow_b200/csrc``.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libpf_b200.so')
+
+c_i32, c_i64, c_f32, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
+
+# name -> (restype, argtypes); mirrors include/pf_b200.h one to one
+SIGNATURES = {
+    'pf_abi_version': (c_i32, []),
+    'pf_last_error': (ctypes.c_char_p, []),
+    'pf_launch_count': (c_i64, []),
+    'pf_launch_count_reset': (None, []),
+    'pf_sm_count': (c_i32, [ctypes.POINTER(c_i32)]),
+    'pf_fill_u32': (c_i32, [c_vp, c_i64, ctypes.c_uint32, c_vp]),
+    'pf_uq_weight_minmax': (c_i32, [c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]),
+    'pf_uq_weight_quant': (c_i32, [c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]),
+    'pf_uq_weight_ste_bwd': (c_i32, [c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]),
+    'pf_uq_act_minmax': (c_i32, [c_vp, c_i64, c_vp, c_vp]),
+    'pf_uq_act_quant': (c_i32, [c_vp, c_vp, c_i64, c_vp, c_i32, c_vp]),
+    'pf_ws_mask_build': (c_i32, [c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    'pf_select_desc': (c_i32, [c_vp, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    'pf_momentum_step': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_f32, c_f32, c_f32, c_vp]),
+    'pf_adam_step': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_f32, c_f32, c_f32, c_f32, c_f32, c_vp]),
+    'pf_softmax_ce_fwd_bwd': (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_f32, c_f32, c_vp, c_vp, c_vp, c_vp]),
+    'pf_l2_loss': (c_i32, [c_vp, c_i64, c_f32, c_i32, c_vp, c_vp, c_vp]),
+    'pf_nuq_weight_quant': (c_i32, [c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+}
+
+_lib = None
+
+
+class PFLibraryMissing(RuntimeError):
+    pass
+
+
+def load():
+    """Load libpf_b200.so once; raise loudly when it is absent (no CPU path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PFLibraryMissing(
+            'libpf_b200.so not found at %s — build it first (__graft_entry__.build()); '
+            'pocketflow_b200 has no CPU fallback' % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError = header/library mismatch: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    if lib.pf_abi_version() != 1:
+        raise RuntimeError('libpf_b200.so ABI version mismatch')
+    _lib = lib
+    return lib
+
+
+def check(status, what):
+    """0 = ok; <0 argument errors -> ValueError (the run scripts' `except ValueError` contract,
+    nets/resnet_at_cifar10_run.py:64-66); >0 cudaError_t -> RuntimeError."""
+    if status == 0:
+        return
+    msg = load().pf_last_error().decode('utf-8', 'replace')
+    if status in (-1, -2):
+        raise ValueError('%s: %s' % (what, msg))
+    raise RuntimeError('%s failed with status %d: %s' % (what, status, msg))

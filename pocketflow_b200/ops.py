@@ -1,0 +1,410 @@
+"""Host-side operator layer over the C ABI (include/pf_b200.h).
+
+Holds PyTorch CUDA tensors (device memory, streams) and calls libpf_b200.so through ctypes.  Each
+class/function names the reference op chain it replaces.  Pure host logic (bucket layouts, work
+tables, percentile ranks) lives in functions that need no GPU, so it is unit-tested on CPU.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import lib as _lib
+
+UQ_SEG = np.dtype([('src', 'u8'), ('dst', 'u8'), ('numel', 'i8'), ('padded', 'i8'),
+                   ('ncols', 'i4'), ('bucket0', 'i4'), ('bits', 'i4'), ('reserved', 'i4')])
+WORK = np.dtype([('seg', 'i4'), ('kind', 'i4'), ('start', 'i8'), ('count', 'i4'),
+                 ('c0', 'i4'), ('ncol_tile', 'i4'), ('reserved', 'i4')])
+WS_SEG = np.dtype([('w', 'u8'), ('bkup', 'u8'), ('mask', 'u8'), ('numel', 'i8')])
+assert UQ_SEG.itemsize == 48 and WORK.itemsize == 32 and WS_SEG.itemsize == 32
+
+CHUNK = 8192            # elements per CTA work item of the elementwise multi-tensor kernels
+WS_WORKSPACE_U32 = 264  # PF_WS_WORKSPACE_U32_PER_SEG
+L2_PARTIALS = 1024      # PF_L2_PARTIALS
+
+
+# ----------------------------------------------------------------------------- host-only helpers
+def uq_bucket_layout(shape, use_buckets, bucket_type, bucket_size):
+    """(ncols, padded) of a weight tensor: bucket id of flat element i is i % ncols.
+
+    Mirrors __channel_bucket / __split_bucket (learners/uniform_quantization/utils.py:247-289)."""
+    numel = int(np.prod(shape))
+    if not use_buckets:
+        return 1, numel
+    if bucket_type == 'channel':
+        return int(shape[-1]), numel
+    if bucket_type == 'split':
+        if bucket_size <= 0:
+            raise ValueError('Bucket size must be a postive integer')
+        multiple, rest = divmod(numel, bucket_size)
+        if rest:
+            multiple += 1
+        return multiple, multiple * bucket_size
+    raise ValueError("Unrecognized bucket type, must be 'weight' or 'channel'.")
+
+
+def flat_works(numels, chunk=CHUNK):
+    """kind-0 work items: chunks [start, start+count) of each tensor (start % 4 == 0)."""
+    rows = []
+    for s, n in enumerate(numels):
+        for start in range(0, int(n), chunk):
+            rows.append((s, 0, start, min(chunk, int(n) - start), 0, 0, 0))
+    return np.array(rows, dtype=WORK) if rows else np.zeros(0, dtype=WORK)
+
+
+def minmax_works(segs):
+    """Work table of pf_uq_weight_minmax: flat chunks for per-layer ranges, column tiles x row
+    ranges of the [padded/ncols, ncols] view for bucketed ranges."""
+    rows = []
+    for s, seg in enumerate(segs):
+        ncols, numel, padded = int(seg['ncols']), int(seg['numel']), int(seg['padded'])
+        if ncols == 1:
+            for start in range(0, numel, CHUNK):
+                rows.append((s, 0, start, min(CHUNK, numel - start), 0, 0, 0))
+            continue
+        tile = min(ncols, 1024 if ncols % 4 == 0 else 256)
+        nrows = padded // ncols
+        rows_per = max(64, (2 * CHUNK) // tile)
+        for c0 in range(0, ncols, tile):
+            tc = min(tile, ncols - c0)
+            for r0 in range(0, nrows, rows_per):
+                rows.append((s, 1, r0, min(rows_per, nrows - r0), c0, tc, 0))
+    return np.array(rows, dtype=WORK) if rows else np.zeros(0, dtype=WORK)
+
+
+def percentile_rank_desc(n, q):
+    """Index into the descending sort gathered by tf.contrib.distributions.percentile
+    (interpolation='nearest'): clip(int32(rint((n-1)*(1-q/100))), 0, n-1) in float64."""
+    idx = int(np.rint((float(n) - 1.0) * (1.0 - float(q) / 100.0)))
+    return min(max(idx, 0), n - 1)
+
+
+def ws_rank_desc(n, prune_ratio):
+    """Rank used by WeightSparseLearner.__build_masks: q = float32(ratio)*100 in float32
+    (learners/weight_sparsification/learner.py:284)."""
+    return percentile_rank_desc(n, np.float32(np.float32(prune_ratio) * np.float32(100.0)))
+
+
+def decode_ordered(u):
+    """numpy inverse of the ordered-uint float encoding used by the min/max slots."""
+    u = np.asarray(u).astype(np.uint32)
+    bits = np.where(u & 0x80000000, u & 0x7FFFFFFF, ~u).astype(np.uint32)
+    return bits.view(np.float32)
+
+
+# ----------------------------------------------------------------------------- device plumbing
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _upload(arr, device):
+    return torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).copy()).to(device)
+
+
+def _check_f32(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise ValueError('expected a contiguous float32 CUDA tensor')
+        if t.data_ptr() % 16:
+            raise ValueError('tensor storage must be 16-byte aligned')
+
+
+def launch_count():
+    return int(_lib.load().pf_launch_count())
+
+
+def launch_count_reset():
+    _lib.load().pf_launch_count_reset()
+
+
+# ----------------------------------------------------------------------------- a1/a3 weights
+class UniformWeightQuantizer:
+    """Multi-tensor weight fake-quantizer: ONE min/max launch + ONE quantize launch for all layers.
+
+    Stands in for UniformQuantization.insert_quant_op_for_weights' per-layer
+    __uniform_quantize(mode='weight') (learners/uniform_quantization/utils.py:81-113, 163-199)."""
+
+    def __init__(self, srcs, dsts, bits, use_buckets=False, bucket_type='channel', bucket_size=256):
+        self.L = _lib.load()
+        if len(srcs) != len(dsts):
+            raise ValueError('srcs/dsts length mismatch')
+        _check_f32(*srcs)
+        _check_f32(*dsts)
+        if bucket_size < 0:
+            raise ValueError('Bucket size must be a postive integer')
+        if bucket_type not in ('split', 'channel'):
+            raise ValueError("Unrecognized bucket type, must be 'weight' or 'channel'.")
+        self.srcs, self.dsts = list(srcs), list(dsts)
+        self.device = srcs[0].device if srcs else torch.device('cuda')
+        segs = np.zeros(len(srcs), dtype=UQ_SEG)
+        b0 = 0
+        for i, (s, d) in enumerate(zip(srcs, dsts)):
+            ncols, padded = uq_bucket_layout(tuple(s.shape), use_buckets, bucket_type, bucket_size)
+            segs[i] = (s.data_ptr(), d.data_ptr(), s.numel(), padded, ncols, b0, 8, 0)
+            b0 += (ncols + 3) // 4 * 4
+        self.segs = segs
+        self.n_buckets = max(b0, 4)
+        self.bucket_counts = [int(s['ncols']) for s in segs]
+        self.mn = torch.empty(self.n_buckets, dtype=torch.int32, device=self.device)
+        self.mx = torch.empty(self.n_buckets, dtype=torch.int32, device=self.device)
+        self.work_mm = minmax_works(segs)
+        self.work_q = flat_works([int(s['numel']) for s in segs])
+        self.work_mm_dev = _upload(self.work_mm, self.device)
+        self.work_q_dev = _upload(self.work_q, self.device)
+        self.grad_segs_dev = None
+        self.set_bits(bits)
+
+    def set_bits(self, bits):
+        bits = [int(b) for b in (bits if hasattr(bits, '__len__') else [bits] * len(self.srcs))]
+        if len(bits) != len(self.srcs):
+            raise ValueError('one bit-width per tensor expected')
+        if any(b < 1 or b > 32 for b in bits):
+            raise ValueError('bit-widths must be in [1, 32]')
+        self.bits = bits
+        self.segs['bits'] = bits
+        self.segs_dev = _upload(self.segs, self.device)
+        self.grad_segs_dev = None
+
+    def reset_ranges(self):
+        st = _stream()
+        _lib.check(self.L.pf_fill_u32(_p(self.mn), self.n_buckets, 0xFFFFFFFF, st), 'pf_fill_u32')
+        _lib.check(self.L.pf_fill_u32(_p(self.mx), self.n_buckets, 0, st), 'pf_fill_u32')
+
+    def minmax(self):
+        self.reset_ranges()
+        _lib.check(self.L.pf_uq_weight_minmax(_p(self.segs_dev), _p(self.work_mm_dev), len(self.work_mm),
+                                              _p(self.mn), _p(self.mx), _stream()), 'pf_uq_weight_minmax')
+
+    def quantize(self):
+        _lib.check(self.L.pf_uq_weight_quant(_p(self.segs_dev), _p(self.work_q_dev), len(self.work_q),
+                                             _p(self.mn), _p(self.mx), _stream()), 'pf_uq_weight_quant')
+
+    def forward(self):
+        if not self.srcs:
+            return
+        self.minmax()
+        self.quantize()
+
+    def ste_backward_(self, grads):
+        """In-place STE chain on the gradients w.r.t. the quantized weights (a3)."""
+        _check_f32(*grads)
+        if self.grad_segs_dev is None or self._grad_ptrs != [g.data_ptr() for g in grads]:
+            gs = self.segs.copy()
+            gs['src'] = [g.data_ptr() for g in grads]
+            gs['dst'] = gs['src']
+            self.grad_segs_dev = _upload(gs, self.device)
+            self._grad_ptrs = [g.data_ptr() for g in grads]
+        _lib.check(self.L.pf_uq_weight_ste_bwd(_p(self.grad_segs_dev), _p(self.work_q_dev), len(self.work_q),
+                                               _p(self.mn), _p(self.mx), _stream()), 'pf_uq_weight_ste_bwd')
+
+    def ranges(self):
+        """Per tensor (min, max) arrays decoded from the slots (host copy; tests/diagnostics)."""
+        mn = decode_ordered(self.mn.cpu().numpy().view(np.uint32))
+        mx = decode_ordered(self.mx.cpu().numpy().view(np.uint32))
+        out = []
+        for s in self.segs:
+            b0, nc = int(s['bucket0']), int(s['ncols'])
+            out.append((mn[b0:b0 + nc].copy(), mx[b0:b0 + nc].copy()))
+        return out
+
+    def bucket_storage_bits(self):
+        """2*32 bits per bucket (utils.py:299-306)."""
+        return sum(self.bucket_counts) * 32 * 2
+
+
+# ----------------------------------------------------------------------------- a2 activations
+def act_range_reset(minmax):
+    L = _lib.load()
+    st = _stream()
+    _lib.check(L.pf_fill_u32(_p(minmax), 1, 0xFFFFFFFF, st), 'pf_fill_u32')
+    _lib.check(L.pf_fill_u32(ctypes.c_void_p(minmax.data_ptr() + 4), 1, 0, st), 'pf_fill_u32')
+
+
+def act_minmax(x, minmax):
+    """Accumulate the per-tensor range of x into minmax (int32[2], ordered-uint)."""
+    _check_f32(x)
+    _lib.check(_lib.load().pf_uq_act_minmax(_p(x), x.numel(), _p(minmax), _stream()), 'pf_uq_act_minmax')
+
+
+def act_quant(x, y, minmax, bits):
+    _check_f32(x, y)
+    if not 1 <= int(bits) <= 32:
+        raise ValueError('bit-widths must be in [1, 32]')
+    _lib.check(_lib.load().pf_uq_act_quant(_p(x), _p(y), x.numel(), _p(minmax), int(bits), _stream()),
+               'pf_uq_act_quant')
+
+
+def act_fake_quant(x, bits, out=None, minmax=None):
+    """Q(x) with per-tensor range — __uniform_quantize(mode='activation') (utils.py:51-79)."""
+    if out is None:
+        out = torch.empty_like(x)
+    if minmax is None:
+        minmax = torch.empty(2, dtype=torch.int32, device=x.device)
+    act_range_reset(minmax)
+    act_minmax(x, minmax)
+    act_quant(x, out, minmax, bits)
+    return out
+
+
+# ----------------------------------------------------------------------------- a5 masks
+class MaskBuilder:
+    """Multi-tensor magnitude-mask build — WeightSparseLearner.__build_masks
+    (learners/weight_sparsification/learner.py:260-294)."""
+
+    def __init__(self, ws, bkups, masks):
+        self.L = _lib.load()
+        _check_f32(*ws)
+        _check_f32(*bkups)
+        _check_f32(*masks)
+        self.ws, self.bkups, self.masks = list(ws), list(bkups), list(masks)
+        self.device = ws[0].device
+        segs = np.zeros(len(ws), dtype=WS_SEG)
+        for i, (w, b, m) in enumerate(zip(ws, bkups, masks)):
+            if not (w.numel() == b.numel() == m.numel()):
+                raise ValueError('w/bkup/mask size mismatch')
+            segs[i] = (w.data_ptr(), b.data_ptr(), m.data_ptr(), w.numel())
+        self.segs = segs
+        self.segs_dev = _upload(segs, self.device)
+        self.work = flat_works([w.numel() for w in ws])
+        self.work_dev = _upload(self.work, self.device)
+        self.workspace = torch.zeros(len(ws) * WS_WORKSPACE_U32, dtype=torch.int32, device=self.device)
+        self.thr = torch.zeros(len(ws), dtype=torch.float32, device=self.device)
+        self.ranks = torch.zeros(len(ws), dtype=torch.int64, device=self.device)
+
+    def build(self, prune_ratios):
+        """prune_ratios: one (dynamic) float32 ratio per tensor."""
+        ranks = [ws_rank_desc(w.numel(), r) for w, r in zip(self.ws, prune_ratios)]
+        self.ranks.copy_(torch.tensor(ranks, dtype=torch.int64), non_blocking=False)
+        _lib.check(self.L.pf_ws_mask_build(_p(self.segs_dev), len(self.ws), _p(self.work_dev), len(self.work),
+                                           _p(self.ranks), _p(self.workspace), _p(self.thr), _stream()),
+                   'pf_ws_mask_build')
+        return ranks
+
+
+def select_desc(tensors, queries):
+    """Exact order statistics: queries = [(tensor_index, rank_desc)], returns a float32 CUDA tensor.
+    Used by the codebook quantile init (learners/nonuniform_quantization/utils.py:349-366)."""
+    L = _lib.load()
+    _check_f32(*tensors)
+    dev = tensors[0].device
+    segs = np.zeros(len(tensors), dtype=WS_SEG)
+    for i, t in enumerate(tensors):
+        segs[i] = (0, t.data_ptr(), 0, t.numel())
+    qseg = np.array([q[0] for q in queries], dtype=np.int32)
+    ranks = torch.tensor([int(q[1]) for q in queries], dtype=torch.int64, device=dev)
+    work = flat_works([tensors[q[0]].numel() for q in queries])
+    ws = torch.zeros(len(queries) * WS_WORKSPACE_U32, dtype=torch.int32, device=dev)
+    out = torch.empty(len(queries), dtype=torch.float32, device=dev)
+    segs_dev, qseg_dev, work_dev = _upload(segs, dev), _upload(qseg, dev), _upload(work, dev)
+    _lib.check(L.pf_select_desc(_p(segs_dev), _p(qseg_dev), len(queries), _p(work_dev), len(work),
+                                _p(ranks), _p(ws), _p(out), _stream()), 'pf_select_desc')
+    torch.cuda.current_stream().synchronize()   # tables above go out of scope
+    return out
+
+
+# ----------------------------------------------------------------------------- a6/a9 optimizers
+def momentum_step(w, acc, g, mask, hp, momentum, wd=0.0, grad_scale=1.0):
+    """g*mask + MomentumOptimizer.apply_gradients on a flat range
+    (learners/weight_sparsification/learner.py:201-212, 314-332).  hp[0] = lr (device)."""
+    _check_f32(w, acc, g, mask, hp)
+    _lib.check(_lib.load().pf_momentum_step(_p(w), _p(acc), _p(g), _p(mask), w.numel(), _p(hp),
+                                            float(momentum), float(wd), float(grad_scale), _stream()),
+               'pf_momentum_step')
+
+
+def adam_step(w, m, v, g, hp, beta1=0.9, beta2=0.999, eps=1e-8, wd=0.0, grad_scale=1.0):
+    """tf.train.AdamOptimizer step on a flat range (uniform_quantization/learner.py:244).
+    hp = [lr, beta1_power, beta2_power] (device)."""
+    _check_f32(w, m, v, g, hp)
+    _lib.check(_lib.load().pf_adam_step(_p(w), _p(m), _p(v), _p(g), w.numel(), _p(hp), float(beta1),
+                                        float(beta2), float(eps), float(wd), float(grad_scale), _stream()),
+               'pf_adam_step')
+
+
+# ----------------------------------------------------------------------------- a7/a8 losses
+def softmax_ce(logits, labels, teacher=None, tempr=4.0, w_dst=4.0, dlogits=None, out=None, row_ws=None):
+    """hard CE (+ distillation CE) forward and d/dlogits.  Returns (out[4], dlogits):
+    out = [hard, dst, top-1 accuracy, top-5 accuracy]."""
+    _check_f32(logits, labels, teacher)
+    n, k = logits.shape
+    if labels.shape != logits.shape or (teacher is not None and teacher.shape != logits.shape):
+        raise ValueError('labels/teacher must match logits shape')
+    if dlogits is None:
+        dlogits = torch.empty_like(logits)
+    if out is None:
+        out = torch.empty(4, dtype=torch.float32, device=logits.device)
+    if row_ws is None:
+        row_ws = torch.empty(4 * n, dtype=torch.float32, device=logits.device)
+    _lib.check(_lib.load().pf_softmax_ce_fwd_bwd(_p(logits), _p(labels), _p(teacher), n, k, float(tempr),
+                                                 float(w_dst), _p(dlogits), _p(out), _p(row_ws), _stream()),
+               'pf_softmax_ce_fwd_bwd')
+    return out, dlogits
+
+
+def l2_loss(v, scale, out, partial_ws, accumulate=False):
+    """out[0] (+)= scale * sum(v^2)/2 — tf.nn.l2_loss terms (nets/resnet_at_cifar10.py:105-107)."""
+    _check_f32(v, out, partial_ws)
+    _lib.check(_lib.load().pf_l2_loss(_p(v), v.numel(), float(scale), int(bool(accumulate)), _p(out),
+                                      _p(partial_ws), _stream()), 'pf_l2_loss')
+
+
+# ----------------------------------------------------------------------------- a11 codebooks
+class CodebookWeightQuantizer:
+    """Multi-tensor codebook quantizer, per-layer range —
+    NonUniformQuantization.__nonuni_quantize (learners/nonuniform_quantization/utils.py:168-194)."""
+
+    def __init__(self, srcs, dsts, bits, keep_index=False):
+        self.L = _lib.load()
+        _check_f32(*srcs)
+        _check_f32(*dsts)
+        self.uq = UniformWeightQuantizer(srcs, dsts, bits)       # per-layer ranges + tables
+        if any(b > 8 for b in self.uq.bits):
+            raise ValueError('codebook bit-widths must be <= 8')
+        self.srcs, self.dsts = list(srcs), list(dsts)
+        self.device = self.uq.device
+        self.clusters = torch.zeros(len(srcs), 256, dtype=torch.float32, device=self.device)
+        self.idx = None
+        if keep_index:
+            offs, tot = [], 0
+            for s in srcs:
+                offs.append(tot)
+                tot += (s.numel() + 15) // 16 * 16
+            self.idx = torch.zeros(tot, dtype=torch.uint8, device=self.device)
+            self.idx_base = torch.tensor(offs, dtype=torch.int64, device=self.device)
+            self.idx_offsets = offs
+
+    def quantile_init(self):
+        """clusters_j = percentile(x_n, (j+1)*100/(k+1)) (utils.py:349-366).  x -> x_n is monotone
+        non-decreasing in fp32, so the order statistic is selected on the raw weights (exact radix
+        select) and normalised afterwards with the same fp32 ops."""
+        self.uq.minmax()
+        queries = []
+        for i, s in enumerate(self.srcs):
+            k = 1 << self.uq.bits[i]
+            for j in range(k):
+                queries.append((i, percentile_rank_desc(s.numel(), (j + 1) * 100 / (k + 1))))
+        vals = select_desc(self.srcs, queries).cpu().numpy()
+        rng = self.uq.ranges()
+        c = np.zeros((len(self.srcs), 256), np.float32)
+        pos = 0
+        for i in range(len(self.srcs)):
+            k = 1 << self.uq.bits[i]
+            mn, mx = rng[i][0][0], rng[i][1][0]
+            alpha = np.float32(np.float32(mx - mn) + np.float32(1e-10))
+            c[i, :k] = ((vals[pos:pos + k] - mn).astype(np.float32) / alpha).astype(np.float32)
+            pos += k
+        self.clusters.copy_(torch.from_numpy(c))
+
+    def forward(self):
+        self.uq.minmax()
+        _lib.check(self.L.pf_nuq_weight_quant(_p(self.uq.segs_dev), _p(self.uq.work_q_dev), len(self.uq.work_q),
+                                              _p(self.uq.mn), _p(self.uq.mx), _p(self.clusters),
+                                              _p(self.idx), _p(self.idx_base) if self.idx is not None else None,
+                                              _stream()), 'pf_nuq_weight_quant')

@@ -1,0 +1,139 @@
+"""CPU-side tests: the C-ABI library loads and exports every symbol include/pf_b200.h declares,
+argument errors follow the error convention without touching a GPU, host-side planning logic is
+right, and the oracle still reproduces the committed golden vectors."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import pf_oracle as O
+from pocketflow_b200 import lib, ops
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+F32 = np.float32
+
+
+def header_symbols():
+    out = []
+    for fn in sorted(os.listdir(os.path.join(ROOT, 'include'))):
+        src = open(os.path.join(ROOT, 'include', fn)).read()
+        src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+        out += re.findall(r'\b(pf_[a-z0-9_]+)\s*\(', src)
+    return sorted(set(out))
+
+
+def test_library_exports_every_declared_symbol():
+    L = lib.load()
+    syms = header_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(L, s), 'libpf_b200.so does not export %s' % s
+    assert set(lib.SIGNATURES) == set(syms), set(lib.SIGNATURES) ^ set(syms)
+    assert L.pf_abi_version() == 1
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(lib, '_lib', None)
+    monkeypatch.setattr(lib, 'LIB_PATH', '/nonexistent/libpf_b200.so')
+    with pytest.raises(lib.PFLibraryMissing):
+        lib.load()
+
+
+def test_argument_errors_map_to_valueerror():
+    L = lib.load()
+    st = L.pf_uq_act_quant(None, None, -1, None, 8, None)
+    assert st == -1
+    with pytest.raises(ValueError):
+        lib.check(st, 'pf_uq_act_quant')
+    assert b'n < 0' in L.pf_last_error()
+    assert L.pf_uq_act_quant(None, None, 16, None, 0, None) == -1       # bits out of range
+    assert L.pf_softmax_ce_fwd_bwd(None, None, None, 0, 10, 4.0, 4.0, None, None, None, None) == -1
+    assert L.pf_uq_weight_quant(None, None, 0, None, None, None) == 0   # empty work = no-op
+    assert L.pf_momentum_step(None, None, None, None, 0, None, 0.9, 0.0, 1.0, None) == 0
+    with pytest.raises(RuntimeError):
+        lib.check(700, 'x')
+
+
+def test_struct_layouts_match_header():
+    assert ops.UQ_SEG.itemsize == 48 and ops.UQ_SEG.fields['ncols'][1] == 32
+    assert ops.WORK.itemsize == 32 and ops.WORK.fields['start'][1] == 8
+    assert ops.WS_SEG.itemsize == 32
+
+
+def test_bucket_layouts():
+    assert ops.uq_bucket_layout((3, 3, 64, 128), False, 'channel', 256) == (1, 73728)
+    assert ops.uq_bucket_layout((3, 3, 64, 128), True, 'channel', 256) == (128, 73728)
+    assert ops.uq_bucket_layout((3, 3, 64, 128), True, 'split', 256) == (288, 73728)
+    assert ops.uq_bucket_layout((10,), True, 'split', 4) == (3, 12)
+    with pytest.raises(ValueError):
+        ops.uq_bucket_layout((4, 4), True, 'bogus', 4)
+
+
+@pytest.mark.parametrize('numels', [[1], [8192], [8193, 5], [100000, 7, 0, 16384]])
+def test_flat_works_cover_exactly(numels):
+    w = ops.flat_works(numels)
+    for s, n in enumerate(numels):
+        mine = w[w['seg'] == s]
+        covered = np.zeros(n, np.int32)
+        for r in mine:
+            assert r['start'] % 4 == 0 and r['kind'] == 0
+            covered[r['start']:r['start'] + r['count']] += 1
+        assert np.all(covered == 1)
+
+
+def test_minmax_works_cover_exactly():
+    segs = np.zeros(4, dtype=ops.UQ_SEG)
+    segs[0] = (0, 0, 3 * 3 * 64 * 64, 3 * 3 * 64 * 64, 64, 0, 8, 0)       # channel
+    segs[1] = (0, 0, 2048 * 1001, 2048 * 1001, 1001, 64, 8, 0)           # ncols % 4 != 0
+    segs[2] = (0, 0, 1000, 1024, 4, 1068, 8, 0)                           # split, padded
+    segs[3] = (0, 0, 50000, 50000, 1, 1072, 8, 0)                         # per-layer
+    w = ops.minmax_works(segs)
+    for s in range(3):
+        nc = int(segs[s]['ncols'])
+        nr = int(segs[s]['padded']) // nc
+        cov = np.zeros((nr, nc), np.int32)
+        for r in w[w['seg'] == s]:
+            assert r['kind'] == 1 and (nc % 4 or (r['c0'] % 4 == 0 and r['ncol_tile'] % 4 == 0))
+            assert r['ncol_tile'] <= 1024
+            cov[r['start']:r['start'] + r['count'], r['c0']:r['c0'] + r['ncol_tile']] += 1
+        assert np.all(cov == 1)
+    assert np.all(w[w['seg'] == 3]['kind'] == 0)
+
+
+def test_percentile_rank_matches_oracle():
+    for n in (1, 2, 10, 777, 2359296):
+        for r in (0.0, 0.1, 0.25, 0.5, 0.75, 0.999, 1.0):
+            assert ops.ws_rank_desc(n, r) == O.ws_mask_rank(n, r)
+        for q in (0.0, 5.88, 50.0, 94.1, 100.0):
+            assert ops.percentile_rank_desc(n, q) == O.percentile_index(n, q)
+
+
+def test_ordered_encoding_roundtrip():
+    f = np.array([0.0, -0.0, 1.5, -1.5, 3e38, -3e38, 1e-40, -1e-40, np.inf, -np.inf], F32)
+    u = f.view(np.uint32)
+    enc = np.where(u & 0x80000000, ~u, u | 0x80000000).astype(np.uint32)
+    assert np.array_equal(ops.decode_ordered(enc).view(np.uint32), u)
+    keep = np.array([i for i in range(len(f)) if i != 1])       # -0.0 == 0.0 for argsort, enc(-0) < enc(+0)
+    order = keep[np.argsort(f[keep], kind='stable')]
+    assert np.all(np.diff(enc[order].astype(np.int64)) > 0)
+
+
+def test_oracle_reproduces_golden():
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'hotpath_v1.npz'))
+    for i in range(6):
+        w = g['w%d' % i]
+        for bits in (2, 4, 8):
+            assert np.array_equal(O.uniform_quantize(w, bits), g['w%d_layer_b%d' % (i, bits)])
+            assert np.array_equal(O.uniform_quantize(w, bits, use_buckets=True, bucket_type='channel'),
+                                  g['w%d_channel_b%d' % (i, bits)])
+            assert np.array_equal(O.uniform_quantize(w, bits, use_buckets=True, bucket_type='split', bucket_size=16),
+                                  g['w%d_split_b%d' % (i, bits)])
+    assert np.array_equal(O.uniform_quantize(g['act'], 8, mode='activation'), g['act_b8'])
+    for r in (0.0, 0.3, 0.5, 0.9):
+        v2, b2, m2, thr = O.ws_build_mask(g['ws_w'], g['ws_bkup'], g['ws_mask'], r)
+        tag = 'ws_r%02d' % int(r * 100)
+        assert np.array_equal(m2, g[tag + '_mask']) and np.array_equal(v2, g[tag + '_w'])
+    qx, c, idx = O.nonuniform_quantize(g['nuq_w'], 4)
+    assert np.array_equal(qx, g['nuq_q']) and np.array_equal(c, g['nuq_c'])
