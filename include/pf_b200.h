@@ -89,18 +89,23 @@ typedef struct pf_work {
 } pf_work;
 
 /* Phase 1: per-bucket min/max into ordered-uint slots (caller pre-fills mn_enc with 0xFF bytes and
- * mx_enc with 0 — pf_fill_u32 does both).  work table = pf_uq_plan_minmax (host side, Python). */
+ * mx_enc with 0 — pf_fill_u32 does both).  work table = kind-0 chunks (per-layer) / kind-1 tiles. */
 int pf_uq_weight_minmax(const pf_uq_seg* segs_dev, const pf_work* work_dev, int n_work,
                         uint32_t* mn_enc_dev, uint32_t* mx_enc_dev, void* stream);
+/* Phase 1b: scales_dev[0..n) = alpha = (max-min)+1e-10f, [n..2n) = beta = min, [2n..3n) = RN(1/alpha)
+ * (n = n_buckets, a multiple of 4).  The reciprocal feeds an exact (correctly rounded) division by
+ * residual correction, so results stay bit-identical to true fp32 division. */
+int pf_uq_weight_scales(const uint32_t* mn_enc_dev, const uint32_t* mx_enc_dev, int n_buckets,
+                        float* scales_dev, void* stream);
 /* Phase 2: quantize.  work table: kind-0 chunks.  (The second read of the weights is an L2 hit:
  * all weights of ResNet-50 are 94 MB < 126 MB L2.) */
 int pf_uq_weight_quant(const pf_uq_seg* segs_dev, const pf_work* work_dev, int n_work,
-                       const uint32_t* mn_enc_dev, const uint32_t* mx_enc_dev, void* stream);
+                       const float* scales_dev, int n_buckets, void* stream);
 /* a3  STE backward of the weight quantizer as a stand-alone op, in place on the gradient:
  *     g <- (((g*alpha)/k)*k)/alpha   (gradient_override_map Round->Identity, utils.py:185-186;
  *     min/max under stop_gradient, :224-225).  segs[i].src/dst point at the gradient. */
 int pf_uq_weight_ste_bwd(const pf_uq_seg* segs_dev, const pf_work* work_dev, int n_work,
-                         const uint32_t* mn_enc_dev, const uint32_t* mx_enc_dev, void* stream);
+                         const float* scales_dev, int n_buckets, void* stream);
 
 /* a2  Activation fake-quantization (per-TENSOR min/max, utils.py:51-79, 215-231).
  *     minmax: accumulates into minmax_enc_dev[0] (min) / [1] (max) (pre-filled 0xFFFFFFFF / 0).
@@ -110,6 +115,8 @@ int pf_uq_act_quant(const float* x_dev, float* y_dev, int64_t n, const uint32_t*
                     int bits, void* stream);
 
 int pf_fill_u32(uint32_t* p_dev, int64_t n, uint32_t value, void* stream);
+/* (min,max) ordered-uint pairs <- (0xFFFFFFFF, 0): one launch resets every activation range slot. */
+int pf_minmax_reset(uint32_t* pairs_dev, int64_t n_pairs, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a5  Magnitude-threshold mask build, multi-tensor.
@@ -189,15 +196,84 @@ int pf_l2_loss(const float* v_dev, int64_t n, float scale, int accumulate, float
  *     learners/nonuniform_quantization/utils.py:168-194, 284-307:
  *        xn=(w-beta)/alpha; idx=argmin_j|xn-c_j| (first index on ties);
  *        q=c[idx]*sign(xn+1e-6); out=alpha*q+beta.
- *     Uses pf_uq_seg (ncols must be 1; bits = log2(#centroids) <= 8) and the min/max slots of
- *     pf_uq_weight_minmax.  clusters_dev: per seg 2^bits floats at offset seg*256.
+ *     Uses pf_uq_seg (ncols must be 1; bits = log2(#centroids) <= 8) and the scales of
+ *     pf_uq_weight_minmax + pf_uq_weight_scales.  clusters_dev: per seg 2^bits floats at offset seg*256.
  *     idx_out_dev (optional): uint8 centroid index per element, laid out like the weights
  *     (idx_base_dev[seg] = byte offset of the tensor), for the codebook gradient.
  * ------------------------------------------------------------------------------------------- */
 int pf_nuq_weight_quant(const pf_uq_seg* segs_dev, const pf_work* work_dev, int n_work,
-                        const uint32_t* mn_enc_dev, const uint32_t* mx_enc_dev,
+                        const float* scales_dev, int n_buckets,
                         const float* clusters_dev, uint8_t* idx_out_dev,
                         const int64_t* idx_base_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a4  Convolution / dense layers, exact-fp32 CUDA-core path (pf_conv.cu).
+ *     Replaces tf.nn.conv2d / tf.matmul re-created on the quantized weight
+ *     (learners/uniform_quantization/utils.py:88-113) and their autodiff (learner.py:247).
+ *     x: NHWC [n,h,w,c]; w: HWIO [r,s,c,k]; y: NHWC [n,p,q,k]; pad_t/pad_l = leading padding
+ *     (TF 'SAME': pad_total//2; fixed_padding: (k-1)//2 — utils/external/resnet_model.py:71-103).
+ *     A dense layer is the h=w=r=s=1 case.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct pf_conv_desc {
+  int32_t n, h, w, c;      /* input  */
+  int32_t k, r, s;         /* filters, kernel height/width */
+  int32_t p, q;            /* output height/width */
+  int32_t stride_h, stride_w, pad_t, pad_l;
+} pf_conv_desc;            /* HOST struct, passed by pointer */
+#define PF_CONV_WGRAD_MAX_SPLITS 64
+#define PF_BN_MAX_SPLITS 1024
+
+/* y = conv(x, w) (+ bias[k]) (relu if relu != 0) */
+int pf_conv2d_fwd(const pf_conv_desc* d, const float* x_dev, const float* w_dev, const float* bias_dev,
+                  int relu, float* y_dev, void* stream);
+/* dx (+)= conv_transpose(dy, w).  wt_ws_dev: r*s*c*k floats of scratch (per-tap transposed weight). */
+int pf_conv2d_dgrad(const pf_conv_desc* d, const float* dy_dev, const float* w_dev, float* wt_ws_dev,
+                    int accumulate, float* dx_dev, void* stream);
+/* dw = x (*) dy, split-K with a fixed-order reduction (deterministic).
+ * ws_dev: pf_conv2d_wgrad_workspace_bytes(d) bytes. */
+int64_t pf_conv2d_wgrad_workspace_bytes(const pf_conv_desc* d);
+int pf_conv2d_wgrad(const pf_conv_desc* d, const float* x_dev, const float* dy_dev, float* ws_dev,
+                    float* dw_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a13 The HBM-bound layers between the convolutions (pf_nn.cu); tensors viewed as [m, c], c % 4 == 0.
+ *     tf.layers.batch_normalization(momentum, eps, fused) — utils/external/resnet_model.py:55-62:
+ *       stats : batch mean / biased variance / rstd (+ moving-stat update, unbiased moving variance);
+ *               ws_dev: 3*c*PF_BN_MAX_SPLITS floats.
+ *       apply : y = act(((x-mean)*rstd)*gamma+beta), act 0 none / 1 relu / 2 relu6; when
+ *               minmax_enc_dev != NULL also accumulates the per-tensor min/max of y for the
+ *               activation quantizer (utils.py:51-79) — the reference's two extra reduction passes.
+ *       bwd   : dgamma, dbeta, dx (+)= through act and training-mode BN; ws_dev as for stats.
+ * ------------------------------------------------------------------------------------------- */
+int pf_bn_train_stats(const float* x_dev, int64_t m, int c, float eps, float momentum, float* mean_dev,
+                      float* var_dev, float* rstd_dev, float* moving_mean_dev, float* moving_var_dev,
+                      float* ws_dev, void* stream);
+int pf_bn_eval_prepare(const float* moving_var_dev, int c, float eps, float* rstd_dev, void* stream);
+int pf_bn_apply(const float* x_dev, int64_t m, int c, const float* mean_dev, const float* rstd_dev,
+                const float* gamma_dev, const float* beta_dev, int act, float* y_dev,
+                uint32_t* minmax_enc_dev, void* stream);
+int pf_bn_bwd(const float* dy_dev, const float* x_dev, int64_t m, int c, const float* mean_dev,
+              const float* rstd_dev, const float* gamma_dev, const float* beta_dev, int act,
+              float* dgamma_dev, float* dbeta_dev, float* dx_dev, int accumulate, float* ws_dev,
+              void* stream);
+/* out (+)= a (+ b): residual add (resnet_model.py:199,314) / gradient fan-out; b_dev may be NULL */
+int pf_add(const float* a_dev, const float* b_dev, int64_t n, int accumulate, float* out_dev, void* stream);
+/* dx (+)= dy * [y > 0] (and [y < 6] for act == 2) */
+int pf_relu_bwd(const float* dy_dev, const float* y_dev, int64_t n, int act, int accumulate, float* dx_dev,
+                void* stream);
+/* out[c] = sum_m a[m][c] (bias gradient) */
+int pf_colsum(const float* a_dev, int64_t m, int c, float* out_dev, void* stream);
+/* max pooling (kernel r x s, strides, leading pads from the descriptor; k unused) and its gradient
+ * (the first maximum of a window in row-major order receives the gradient, like TF's MaxPoolGrad) */
+int pf_maxpool_fwd(const pf_conv_desc* d, const float* x_dev, float* y_dev, void* stream);
+int pf_maxpool_bwd(const pf_conv_desc* d, const float* dy_dev, const float* x_dev, const float* y_dev,
+                   int accumulate, float* dx_dev, void* stream);
+/* tf.reduce_mean over H,W (resnet_model.py:547-548) */
+int pf_global_avgpool_fwd(const float* x_dev, int n, int hw, int c, float* y_dev, void* stream);
+int pf_global_avgpool_bwd(const float* dy_dev, int n, int hw, int c, int accumulate, float* dx_dev, void* stream);
+/* row softmax and its backward (nets/lenet_at_cifar10.py:66) */
+int pf_softmax_fwd(const float* x_dev, int n, int k, float* y_dev, void* stream);
+int pf_softmax_bwd(const float* dy_dev, const float* y_dev, int n, int k, float* dx_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -41,6 +41,22 @@ __global__ void pf_fill_u32_kernel(uint32_t* p, int64_t n, uint32_t v) {
   for (; i < n; i += stride) p[i] = v;
 }
 
+__global__ void pf_minmax_reset_kernel(uint32_t* p, int64_t n_pairs) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_pairs) {
+    p[2 * i] = 0xFFFFFFFFu;
+    p[2 * i + 1] = 0u;
+  }
+}
+
+int pf_minmax_reset(uint32_t* pairs_dev, int64_t n_pairs, void* stream) {
+  PF_REQUIRE(n_pairs >= 0 && (pairs_dev != nullptr || n_pairs == 0), "pf_minmax_reset: bad arguments");
+  if (n_pairs == 0) return PF_OK;
+  pf_minmax_reset_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pairs_dev, n_pairs);
+  PF_CHECK_LAUNCH("pf_minmax_reset");
+  return PF_OK;
+}
+
 int pf_fill_u32(uint32_t* p_dev, int64_t n, uint32_t value, void* stream) {
   PF_REQUIRE(n >= 0 && (p_dev != nullptr || n == 0), "pf_fill_u32: bad arguments");
   if (n == 0) return PF_OK;

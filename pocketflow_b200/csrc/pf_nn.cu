@@ -1,0 +1,628 @@
+// pf_nn.cu — the HBM-bound layers around the convolutions: batch-norm
+// (training statistics, apply(+ReLU/ReLU6)(+activation range), backward), max/mean pooling,
+// residual add, ReLU backward, bias gradient.  NHWC fp32; every tensor is viewed as [M, C].
+//
+// Reference semantics: tf.layers.batch_normalization(momentum .997, eps 1e-5, fused)
+// (/root/reference/utils/external/resnet_model.py:55-62), tf.nn.relu (:144), max_pooling2d 3x3 s2
+// SAME (:521-525), reduce_mean over H,W (:547-548), residual add (:199,:314).
+// B200 design: one pass computes the batch statistics (shifted sums, fp64 combine), one pass applies
+// BN+ReLU AND accumulates the per-tensor min/max the activation quantizer needs
+// (uniform_quantization/utils.py:51-79), so the separate reduce_max/reduce_min passes of the
+// reference disappear.
+#include "pf_common.cuh"
+
+namespace {
+
+constexpr int NT = 256;
+constexpr int kColTile = 256;  // columns per CTA (64 float4 lanes)
+
+// ------------------------------------------------------------------ column-reduction scaffolding
+struct ColTile {
+  int c0, tc, nvec, nty, tx, ty;
+  __device__ ColTile(int C) {
+    c0 = blockIdx.x * kColTile;
+    tc = min(kColTile, C - c0);
+    nvec = tc >> 2;
+    nty = NT / nvec;
+    tx = threadIdx.x % nvec;
+    ty = threadIdx.x / nvec;
+  }
+};
+
+// BN statistics partials: per (split, channel): K (shift), s1 = sum(x-K), s2 = sum((x-K)^2)
+__global__ void __launch_bounds__(NT)
+bn_stats_partial_kernel(const float* __restrict__ x, int M, int C, int rows_per_split,
+                        float* __restrict__ part /* [splits][3][C] */) {
+  __shared__ float sh[2][NT * 4];
+  const ColTile t(C);
+  const int r0 = blockIdx.y * rows_per_split;
+  const int r1 = min(M, r0 + rows_per_split);
+  const int col = t.c0 + t.tx * 4;
+  float4 K = make_float4(0.f, 0.f, 0.f, 0.f), s1 = K, s2 = K;
+  if (t.ty < t.nty) {
+    K = __ldg(reinterpret_cast<const float4*>(x + (size_t)r0 * C + col));
+    for (int r = r0 + t.ty; r < r1; r += t.nty) {
+      const float4 v = pf_ld_stream(x + (size_t)r * C + col);
+      const float dx = v.x - K.x, dy = v.y - K.y, dz = v.z - K.z, dw = v.w - K.w;
+      s1.x += dx; s1.y += dy; s1.z += dz; s1.w += dw;
+      s2.x = fmaf(dx, dx, s2.x); s2.y = fmaf(dy, dy, s2.y); s2.z = fmaf(dz, dz, s2.z); s2.w = fmaf(dw, dw, s2.w);
+    }
+    float* a = &sh[0][(t.ty * t.nvec + t.tx) * 4];
+    float* b = &sh[1][(t.ty * t.nvec + t.tx) * 4];
+    a[0] = s1.x; a[1] = s1.y; a[2] = s1.z; a[3] = s1.w;
+    b[0] = s2.x; b[1] = s2.y; b[2] = s2.z; b[3] = s2.w;
+  }
+  __syncthreads();
+  // fixed-order combine over ty: deterministic
+  for (int c = threadIdx.x; c < t.tc; c += NT) {
+    float a = 0.f, b = 0.f;
+    for (int y = 0; y < t.nty; ++y) {
+      a += sh[0][(y * t.nvec + (c >> 2)) * 4 + (c & 3)];
+      b += sh[1][(y * t.nvec + (c >> 2)) * 4 + (c & 3)];
+    }
+    float* p = part + (size_t)blockIdx.y * 3 * C;
+    p[t.c0 + c] = __ldg(x + (size_t)r0 * C + t.c0 + c);
+    p[C + t.c0 + c] = a;
+    p[2 * C + t.c0 + c] = b;
+  }
+}
+
+// Combine the partials (Chan et al.) in fp64; emit mean, biased var, rstd; update moving stats.
+__global__ void __launch_bounds__(NT)
+bn_stats_final_kernel(const float* __restrict__ part, int M, int C, int splits, int rows_per_split,
+                      float eps, float momentum, float* __restrict__ mean, float* __restrict__ var,
+                      float* __restrict__ rstd, float* __restrict__ mov_mean, float* __restrict__ mov_var) {
+  const int c = blockIdx.x * NT + threadIdx.x;
+  if (c >= C) return;
+  double n_acc = 0.0, mean_acc = 0.0, m2_acc = 0.0;
+  for (int s = 0; s < splits; ++s) {
+    const int r0 = s * rows_per_split;
+    const double n = (double)(min(M, r0 + rows_per_split) - r0);
+    const float* p = part + (size_t)s * 3 * C;
+    const double K = p[c], s1 = p[C + c], s2 = p[2 * C + c];
+    const double mu = K + s1 / n;
+    const double m2 = s2 - s1 * s1 / n;
+    const double nt = n_acc + n;
+    const double delta = mu - mean_acc;
+    mean_acc += delta * n / nt;
+    m2_acc += m2 + delta * delta * n_acc * n / nt;
+    n_acc = nt;
+  }
+  const float mu = (float)mean_acc;
+  const float v = (float)(m2_acc / n_acc);
+  mean[c] = mu;
+  var[c] = v;
+  rstd[c] = __frsqrt_rn(__fadd_rn(v, eps));
+  if (mov_mean) {
+    // moving = moving*momentum + batch*(1-momentum); the moving variance uses the unbiased estimate
+    const float om = __fsub_rn(1.f, momentum);
+    const float vu = n_acc > 1.0 ? (float)(m2_acc / (n_acc - 1.0)) : v;
+    mov_mean[c] = __fadd_rn(__fmul_rn(mov_mean[c], momentum), __fmul_rn(mu, om));
+    mov_var[c] = __fadd_rn(__fmul_rn(mov_var[c], momentum), __fmul_rn(vu, om));
+  }
+}
+
+__global__ void __launch_bounds__(NT)
+bn_eval_prepare_kernel(const float* __restrict__ mov_var, int C, float eps, float* __restrict__ rstd) {
+  const int c = blockIdx.x * NT + threadIdx.x;
+  if (c < C) rstd[c] = __frsqrt_rn(__fadd_rn(mov_var[c], eps));
+}
+
+__device__ __forceinline__ float bn_act(float x, float mu, float rs, float ga, float be, int act) {
+  // ((x - mean) * rstd) * gamma + beta, each op rounded once
+  float y = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(x, mu), rs), ga), be);
+  if (act >= 1) y = fmaxf(y, 0.f);
+  if (act == 2) y = fminf(y, 6.f);
+  return y;
+}
+
+// y = act(bn(x)); optionally accumulates the per-tensor min/max of y (ordered-uint slots)
+__global__ void __launch_bounds__(NT)
+bn_apply_kernel(const float* __restrict__ x, int64_t total, int C, const float* __restrict__ mean,
+                const float* __restrict__ rstd, const float* __restrict__ gamma,
+                const float* __restrict__ beta, int act, float* __restrict__ y,
+                uint32_t* __restrict__ minmax_enc) {
+  __shared__ float s_mn[NT / 32], s_mx[NT / 32];
+  const int64_t nvec = total >> 2;
+  const int64_t stride = (int64_t)gridDim.x * NT;
+  int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x;
+  uint32_t c = (uint32_t)((i << 2) % (uint32_t)C);
+  const uint32_t step = (uint32_t)((stride << 2) % (uint32_t)C);
+  float mn = INFINITY, mx = -INFINITY;
+  for (; i < nvec; i += stride) {
+    float4 v = pf_ld_stream(x + (i << 2));
+    const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + c));
+    const float4 rs = __ldg(reinterpret_cast<const float4*>(rstd + c));
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
+    v.x = bn_act(v.x, mu.x, rs.x, ga.x, be.x, act);
+    v.y = bn_act(v.y, mu.y, rs.y, ga.y, be.y, act);
+    v.z = bn_act(v.z, mu.z, rs.z, ga.z, be.z, act);
+    v.w = bn_act(v.w, mu.w, rs.w, ga.w, be.w, act);
+    pf_st_stream(y + (i << 2), v);
+    mn = fminf(fminf(mn, v.x), fminf(v.y, fminf(v.z, v.w)));
+    mx = fmaxf(fmaxf(mx, v.x), fmaxf(v.y, fmaxf(v.z, v.w)));
+    c += step;
+    if (c >= (uint32_t)C) c -= (uint32_t)C;
+  }
+  if (minmax_enc) {
+    mn = pf_warp_min(mn);
+    mx = pf_warp_max(mx);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { s_mn[wid] = mn; s_mx[wid] = mx; }
+    __syncthreads();
+    if (wid == 0) {
+      mn = lane < NT / 32 ? s_mn[lane] : INFINITY;
+      mx = lane < NT / 32 ? s_mx[lane] : -INFINITY;
+      mn = pf_warp_min(mn);
+      mx = pf_warp_max(mx);
+      if (lane == 0 && mn <= mx) {
+        atomicMin(minmax_enc, pf_enc(mn));
+        atomicMax(minmax_enc + 1, pf_enc(mx));
+      }
+    }
+  }
+}
+
+// BN backward, phase 1: per channel sum(dz) and sum(dz * xhat), dz = dy masked by the activation.
+__global__ void __launch_bounds__(NT)
+bn_bwd_partial_kernel(const float* __restrict__ dy, const float* __restrict__ x, int M, int C,
+                      int rows_per_split, const float* __restrict__ mean, const float* __restrict__ rstd,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, int act,
+                      float* __restrict__ part /* [splits][2][C] */) {
+  __shared__ float sh[2][NT * 4];
+  const ColTile t(C);
+  const int r0 = blockIdx.y * rows_per_split;
+  const int r1 = min(M, r0 + rows_per_split);
+  const int col = t.c0 + t.tx * 4;
+  float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+  if (t.ty < t.nty) {
+    const float4 mu4 = __ldg(reinterpret_cast<const float4*>(mean + col));
+    const float4 rs4 = __ldg(reinterpret_cast<const float4*>(rstd + col));
+    const float4 ga4 = __ldg(reinterpret_cast<const float4*>(gamma + col));
+    const float4 be4 = __ldg(reinterpret_cast<const float4*>(beta + col));
+    const float mu[4] = {mu4.x, mu4.y, mu4.z, mu4.w}, rs[4] = {rs4.x, rs4.y, rs4.z, rs4.w};
+    const float ga[4] = {ga4.x, ga4.y, ga4.z, ga4.w}, be[4] = {be4.x, be4.y, be4.z, be4.w};
+    for (int r = r0 + t.ty; r < r1; r += t.nty) {
+      const float4 d4 = pf_ld_stream(dy + (size_t)r * C + col);
+      const float4 x4 = pf_ld_stream(x + (size_t)r * C + col);
+      const float d[4] = {d4.x, d4.y, d4.z, d4.w}, xv[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float xh = __fmul_rn(__fsub_rn(xv[j], mu[j]), rs[j]);
+        float dz = d[j];
+        if (act) {
+          const float z = __fadd_rn(__fmul_rn(xh, ga[j]), be[j]);
+          if (!(z > 0.f) || (act == 2 && !(z < 6.f))) dz = 0.f;
+        }
+        a[j] += dz;
+        b[j] = fmaf(dz, xh, b[j]);
+      }
+    }
+    float* pa = &sh[0][(t.ty * t.nvec + t.tx) * 4];
+    float* pb = &sh[1][(t.ty * t.nvec + t.tx) * 4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { pa[j] = a[j]; pb[j] = b[j]; }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < t.tc; c += NT) {
+    float sa = 0.f, sb = 0.f;
+    for (int y = 0; y < t.nty; ++y) {
+      sa += sh[0][(y * t.nvec + (c >> 2)) * 4 + (c & 3)];
+      sb += sh[1][(y * t.nvec + (c >> 2)) * 4 + (c & 3)];
+    }
+    float* p = part + (size_t)blockIdx.y * 2 * C;
+    p[t.c0 + c] = sa;
+    p[C + t.c0 + c] = sb;
+  }
+}
+
+__global__ void __launch_bounds__(NT)
+bn_bwd_final_kernel(const float* __restrict__ part, int C, int splits, float* __restrict__ dgamma,
+                    float* __restrict__ dbeta) {
+  const int c = blockIdx.x * NT + threadIdx.x;
+  if (c >= C) return;
+  double sa = 0.0, sb = 0.0;
+  for (int s = 0; s < splits; ++s) {
+    sa += part[(size_t)s * 2 * C + c];
+    sb += part[(size_t)s * 2 * C + C + c];
+  }
+  dbeta[c] = (float)sa;
+  dgamma[c] = (float)sb;
+}
+
+// phase 2: dx = gamma*rstd*(dz - dbeta/M - xhat*dgamma/M)   (training-mode BN)
+__global__ void __launch_bounds__(NT)
+bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, int64_t total, int C,
+                    float inv_m, const float* __restrict__ mean, const float* __restrict__ rstd,
+                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                    const float* __restrict__ dgamma, const float* __restrict__ dbeta, int act,
+                    int accumulate, float* __restrict__ dx) {
+  const int64_t nvec = total >> 2;
+  const int64_t stride = (int64_t)gridDim.x * NT;
+  int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x;
+  uint32_t c = (uint32_t)((i << 2) % (uint32_t)C);
+  const uint32_t step = (uint32_t)((stride << 2) % (uint32_t)C);
+  for (; i < nvec; i += stride) {
+    const float4 d4 = pf_ld_stream(dy + (i << 2));
+    const float4 x4 = pf_ld_stream(x + (i << 2));
+    const float4 mu4 = __ldg(reinterpret_cast<const float4*>(mean + c));
+    const float4 rs4 = __ldg(reinterpret_cast<const float4*>(rstd + c));
+    const float4 ga4 = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float4 be4 = __ldg(reinterpret_cast<const float4*>(beta + c));
+    const float4 dg4 = __ldg(reinterpret_cast<const float4*>(dgamma + c));
+    const float4 db4 = __ldg(reinterpret_cast<const float4*>(dbeta + c));
+    const float d[4] = {d4.x, d4.y, d4.z, d4.w}, xv[4] = {x4.x, x4.y, x4.z, x4.w};
+    const float mu[4] = {mu4.x, mu4.y, mu4.z, mu4.w}, rs[4] = {rs4.x, rs4.y, rs4.z, rs4.w};
+    const float ga[4] = {ga4.x, ga4.y, ga4.z, ga4.w}, be[4] = {be4.x, be4.y, be4.z, be4.w};
+    const float dg[4] = {dg4.x, dg4.y, dg4.z, dg4.w}, db[4] = {db4.x, db4.y, db4.z, db4.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float xh = __fmul_rn(__fsub_rn(xv[j], mu[j]), rs[j]);
+      float dz = d[j];
+      if (act) {
+        const float z = __fadd_rn(__fmul_rn(xh, ga[j]), be[j]);
+        if (!(z > 0.f) || (act == 2 && !(z < 6.f))) dz = 0.f;
+      }
+      o[j] = ga[j] * rs[j] * (dz - db[j] * inv_m - xh * dg[j] * inv_m);
+    }
+    float4 r = make_float4(o[0], o[1], o[2], o[3]);
+    if (accumulate) {
+      const float4 old = *reinterpret_cast<const float4*>(dx + (i << 2));
+      r.x += old.x; r.y += old.y; r.z += old.z; r.w += old.w;
+    }
+    pf_st_stream(dx + (i << 2), r);
+    c += step;
+    if (c >= (uint32_t)C) c -= (uint32_t)C;
+  }
+}
+
+// ------------------------------------------------------------------ elementwise helpers
+// out = a + b (residual add) ; or out (+)= a  when b == nullptr (gradient fan-out)
+__global__ void __launch_bounds__(NT)
+add_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n, int accumulate,
+           float* __restrict__ out) {
+  const int64_t nvec = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * NT;
+  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < nvec; i += stride) {
+    float4 v = pf_ld4(a + (i << 2));
+    if (b) {
+      const float4 w = pf_ld4(b + (i << 2));
+      v.x = __fadd_rn(v.x, w.x); v.y = __fadd_rn(v.y, w.y); v.z = __fadd_rn(v.z, w.z); v.w = __fadd_rn(v.w, w.w);
+    }
+    if (accumulate) {
+      const float4 o = pf_ld4(out + (i << 2));
+      v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+    }
+    pf_st_stream(out + (i << 2), v);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t j = (nvec << 2) + threadIdx.x;
+    float v = a[j] + (b ? b[j] : 0.f);
+    out[j] = accumulate ? out[j] + v : v;
+  }
+}
+
+// dx (+)= dy * [y > 0] (and [y < 6] for relu6)
+__global__ void __launch_bounds__(NT)
+relu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, int64_t n, int act,
+                int accumulate, float* __restrict__ dx) {
+  const int64_t stride = (int64_t)gridDim.x * NT;
+  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < n; i += stride) {
+    const float yy = y[i];
+    float v = (yy > 0.f && (act != 2 || yy < 6.f)) ? dy[i] : 0.f;
+    dx[i] = accumulate ? dx[i] + v : v;
+  }
+}
+
+// out[c] = sum_m a[m][c]   (bias gradient); fixed order per column -> deterministic
+__global__ void __launch_bounds__(NT)
+colsum_kernel(const float* __restrict__ a, int M, int C, float* __restrict__ out) {
+  __shared__ float sh[NT];
+  const int c = blockIdx.x;
+  float s = 0.f;
+  for (int m = threadIdx.x; m < M; m += NT) s += a[(size_t)m * C + c];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = NT / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[c] = sh[0];
+}
+
+// ------------------------------------------------------------------ pooling
+__global__ void __launch_bounds__(NT)
+maxpool_fwd_kernel(const float* __restrict__ x, int N, int H, int W, int C, int P, int Q, int kh, int kw,
+                   int sh, int sw, int pt, int pl, float* __restrict__ y) {
+  const int64_t total = (int64_t)N * P * Q * C;
+  const int64_t stride = (int64_t)gridDim.x * NT;
+  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < total; i += stride) {
+    const int c = (int)(i % C);
+    int64_t t = i / C;
+    const int ow = (int)(t % Q); t /= Q;
+    const int oh = (int)(t % P);
+    const int n = (int)(t / P);
+    float m = -INFINITY;
+    for (int r = 0; r < kh; ++r) {
+      const int ih = oh * sh - pt + r;
+      if (ih < 0 || ih >= H) continue;
+      for (int q = 0; q < kw; ++q) {
+        const int iw = ow * sw - pl + q;
+        if (iw < 0 || iw >= W) continue;
+        m = fmaxf(m, __ldg(x + (((size_t)n * H + ih) * W + iw) * C + c));
+      }
+    }
+    y[i] = m;
+  }
+}
+
+// dx[n,ih,iw,c] (+)= sum over windows containing (ih,iw) whose FIRST argmax (row-major scan, like
+// TF's MaxPoolGrad) is (ih,iw).  Gather form: no atomics, deterministic.
+__global__ void __launch_bounds__(NT)
+maxpool_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ y,
+                   int N, int H, int W, int C, int P, int Q, int kh, int kw, int sh, int sw, int pt,
+                   int pl, int accumulate, float* __restrict__ dx) {
+  const int64_t total = (int64_t)N * H * W * C;
+  const int64_t stride = (int64_t)gridDim.x * NT;
+  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < total; i += stride) {
+    const int c = (int)(i % C);
+    int64_t t = i / C;
+    const int iw = (int)(t % W); t /= W;
+    const int ih = (int)(t % H);
+    const int n = (int)(t / H);
+    const float xv = x[i];
+    float g = 0.f;
+    const int oh_lo = max(0, (ih + pt - kh + sh) / sh), oh_hi = min(P - 1, (ih + pt) / sh);
+    const int ow_lo = max(0, (iw + pl - kw + sw) / sw), ow_hi = min(Q - 1, (iw + pl) / sw);
+    for (int oh = oh_lo; oh <= oh_hi; ++oh) {
+      for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+        const size_t o = (((size_t)n * P + oh) * Q + ow) * C + c;
+        if (__ldg(y + o) != xv) continue;
+        // is (ih,iw) the first position of this window that attains the max?
+        bool first = true;
+        for (int r = 0; r < kh && first; ++r) {
+          const int yy = oh * sh - pt + r;
+          if (yy < 0 || yy >= H) continue;
+          for (int q = 0; q < kw; ++q) {
+            const int xx = ow * sw - pl + q;
+            if (xx < 0 || xx >= W) continue;
+            if (yy == ih && xx == iw) { r = kh; break; }
+            if (__ldg(x + (((size_t)n * H + yy) * W + xx) * C + c) == xv) { first = false; break; }
+          }
+        }
+        if (first) g += __ldg(dy + o);
+      }
+    }
+    dx[i] = accumulate ? dx[i] + g : g;
+  }
+}
+
+// y[n][c] = mean over HW ; one CTA per (n, 64-channel tile)
+__global__ void __launch_bounds__(NT)
+gap_fwd_kernel(const float* __restrict__ x, int HW, int C, float* __restrict__ y) {
+  __shared__ float sh[NT];
+  const int n = blockIdx.y;
+  const int cl = threadIdx.x & 63, part = threadIdx.x >> 6;  // 64 channels x 4 row-lanes
+  const int c = blockIdx.x * 64 + cl;
+  float s = 0.f;
+  if (c < C)
+    for (int p = part; p < HW; p += 4) s += __ldg(x + ((size_t)n * HW + p) * C + c);
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  if (part == 0 && c < C) {
+    const float tot = (sh[cl] + sh[64 + cl]) + (sh[128 + cl] + sh[192 + cl]);
+    y[(size_t)n * C + c] = __fdiv_rn(tot, (float)HW);
+  }
+}
+
+__global__ void __launch_bounds__(NT)
+gap_bwd_kernel(const float* __restrict__ dy, int64_t total, int HW, int C, int accumulate,
+               float* __restrict__ dx) {
+  const int64_t stride = (int64_t)gridDim.x * NT;
+  const float inv = 1.f / (float)HW;
+  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < total; i += stride) {
+    const int c = (int)(i % C);
+    const int64_t n = i / ((int64_t)HW * C);
+    const float g = __ldg(dy + n * C + c) * inv;
+    dx[i] = accumulate ? dx[i] + g : g;
+  }
+}
+
+// row softmax (LeNet ends in tf.nn.softmax, nets/lenet_at_cifar10.py:66) and its backward
+__global__ void __launch_bounds__(NT)
+softmax_fwd_kernel(const float* __restrict__ x, int n, int k, float* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const float* r = x + (size_t)row * k;
+  float m = -INFINITY;
+  for (int j = lane; j < k; j += 32) m = fmaxf(m, r[j]);
+  m = pf_warp_max(m);
+  float s = 0.f;
+  for (int j = lane; j < k; j += 32) s += expf(r[j] - m);
+  s = pf_warp_sum(s);
+  for (int j = lane; j < k; j += 32) y[(size_t)row * k + j] = __fdiv_rn(expf(r[j] - m), s);
+}
+__global__ void __launch_bounds__(NT)
+softmax_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, int n, int k,
+                   float* __restrict__ dx) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  float dot = 0.f;
+  for (int j = lane; j < k; j += 32) dot += dy[(size_t)row * k + j] * y[(size_t)row * k + j];
+  dot = pf_warp_sum(dot);
+  for (int j = lane; j < k; j += 32) {
+    const size_t o = (size_t)row * k + j;
+    dx[o] = (dy[o] - dot) * y[o];
+  }
+}
+
+inline unsigned ew_grid(int64_t work_items) {
+  int64_t want = (work_items + NT - 1) / NT;
+  const int64_t cap = (int64_t)PF_NUM_SMS * 8;
+  if (want < 1) want = 1;
+  return (unsigned)(want < cap ? want : cap);
+}
+
+inline int bn_splits(int M, int C, int* rows_per_split) {
+  const int col_tiles = (C + kColTile - 1) / kColTile;
+  int splits = (2 * PF_NUM_SMS + col_tiles - 1) / col_tiles;
+  const int max_by_rows = (M + 63) / 64;
+  if (splits > max_by_rows) splits = max_by_rows;
+  if (splits > PF_BN_MAX_SPLITS) splits = PF_BN_MAX_SPLITS;
+  if (splits < 1) splits = 1;
+  int rps = (M + splits - 1) / splits;
+  *rows_per_split = rps;
+  return (M + rps - 1) / rps;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pf_bn_train_stats(const float* x_dev, int64_t m, int c, float eps, float momentum, float* mean_dev,
+                      float* var_dev, float* rstd_dev, float* moving_mean_dev, float* moving_var_dev,
+                      float* ws_dev, void* stream) {
+  PF_REQUIRE(m > 0 && c > 0 && m < (1ll << 31), "pf_bn_train_stats: bad shape");
+  PF_REQUIRE((c & 3) == 0, "pf_bn_train_stats: C must be a multiple of 4 (got %d)", c);
+  PF_REQUIRE(x_dev && mean_dev && var_dev && rstd_dev && ws_dev, "pf_bn_train_stats: null pointer");
+  PF_REQUIRE((moving_mean_dev == nullptr) == (moving_var_dev == nullptr), "pf_bn_train_stats: moving stats come in pairs");
+  int rps;
+  const int splits = bn_splits((int)m, c, &rps);
+  dim3 grid((c + kColTile - 1) / kColTile, splits);
+  cudaStream_t st = (cudaStream_t)stream;
+  bn_stats_partial_kernel<<<grid, NT, 0, st>>>(x_dev, (int)m, c, rps, ws_dev);
+  PF_CHECK_LAUNCH("pf_bn_train_stats/partial");
+  bn_stats_final_kernel<<<(c + NT - 1) / NT, NT, 0, st>>>(ws_dev, (int)m, c, splits, rps, eps, momentum, mean_dev,
+                                                         var_dev, rstd_dev, moving_mean_dev, moving_var_dev);
+  PF_CHECK_LAUNCH("pf_bn_train_stats/final");
+  return PF_OK;
+}
+
+int pf_bn_eval_prepare(const float* moving_var_dev, int c, float eps, float* rstd_dev, void* stream) {
+  PF_REQUIRE(c > 0 && moving_var_dev && rstd_dev, "pf_bn_eval_prepare: bad arguments");
+  bn_eval_prepare_kernel<<<(c + NT - 1) / NT, NT, 0, (cudaStream_t)stream>>>(moving_var_dev, c, eps, rstd_dev);
+  PF_CHECK_LAUNCH("pf_bn_eval_prepare");
+  return PF_OK;
+}
+
+int pf_bn_apply(const float* x_dev, int64_t m, int c, const float* mean_dev, const float* rstd_dev,
+                const float* gamma_dev, const float* beta_dev, int act, float* y_dev,
+                uint32_t* minmax_enc_dev, void* stream) {
+  PF_REQUIRE(m > 0 && c > 0 && (c & 3) == 0, "pf_bn_apply: bad shape (C must be a multiple of 4)");
+  PF_REQUIRE(act >= 0 && act <= 2, "pf_bn_apply: act must be 0 (none), 1 (relu) or 2 (relu6)");
+  PF_REQUIRE(x_dev && mean_dev && rstd_dev && gamma_dev && beta_dev && y_dev, "pf_bn_apply: null pointer");
+  const int64_t total = m * c;
+  bn_apply_kernel<<<ew_grid(total >> 2), NT, 0, (cudaStream_t)stream>>>(x_dev, total, c, mean_dev, rstd_dev, gamma_dev,
+                                                                     beta_dev, act, y_dev, minmax_enc_dev);
+  PF_CHECK_LAUNCH("pf_bn_apply");
+  return PF_OK;
+}
+
+int pf_bn_bwd(const float* dy_dev, const float* x_dev, int64_t m, int c, const float* mean_dev,
+              const float* rstd_dev, const float* gamma_dev, const float* beta_dev, int act,
+              float* dgamma_dev, float* dbeta_dev, float* dx_dev, int accumulate, float* ws_dev,
+              void* stream) {
+  PF_REQUIRE(m > 0 && c > 0 && (c & 3) == 0 && m < (1ll << 31), "pf_bn_bwd: bad shape (C must be a multiple of 4)");
+  PF_REQUIRE(dy_dev && x_dev && mean_dev && rstd_dev && gamma_dev && beta_dev && dgamma_dev && dbeta_dev &&
+                 dx_dev && ws_dev, "pf_bn_bwd: null pointer");
+  int rps;
+  const int splits = bn_splits((int)m, c, &rps);
+  dim3 grid((c + kColTile - 1) / kColTile, splits);
+  cudaStream_t st = (cudaStream_t)stream;
+  bn_bwd_partial_kernel<<<grid, NT, 0, st>>>(dy_dev, x_dev, (int)m, c, rps, mean_dev, rstd_dev, gamma_dev, beta_dev,
+                                            act, ws_dev);
+  PF_CHECK_LAUNCH("pf_bn_bwd/partial");
+  bn_bwd_final_kernel<<<(c + NT - 1) / NT, NT, 0, st>>>(ws_dev, c, splits, dgamma_dev, dbeta_dev);
+  PF_CHECK_LAUNCH("pf_bn_bwd/final");
+  const int64_t total = m * c;
+  bn_bwd_apply_kernel<<<ew_grid(total >> 2), NT, 0, st>>>(dy_dev, x_dev, total, c, 1.f / (float)m, mean_dev, rstd_dev,
+                                                        gamma_dev, beta_dev, dgamma_dev, dbeta_dev, act, accumulate,
+                                                        dx_dev);
+  PF_CHECK_LAUNCH("pf_bn_bwd/apply");
+  return PF_OK;
+}
+
+int pf_add(const float* a_dev, const float* b_dev, int64_t n, int accumulate, float* out_dev, void* stream) {
+  PF_REQUIRE(n >= 0, "pf_add: n < 0");
+  if (n == 0) return PF_OK;
+  PF_REQUIRE(a_dev && out_dev, "pf_add: null pointer");
+  PF_REQUIRE((((uintptr_t)a_dev | (uintptr_t)b_dev | (uintptr_t)out_dev) & 15) == 0, "pf_add: 16-byte alignment required");
+  add_kernel<<<ew_grid(n >> 2), NT, 0, (cudaStream_t)stream>>>(a_dev, b_dev, n, accumulate, out_dev);
+  PF_CHECK_LAUNCH("pf_add");
+  return PF_OK;
+}
+
+int pf_relu_bwd(const float* dy_dev, const float* y_dev, int64_t n, int act, int accumulate, float* dx_dev,
+                void* stream) {
+  PF_REQUIRE(n >= 0 && (act == 1 || act == 2), "pf_relu_bwd: bad arguments");
+  if (n == 0) return PF_OK;
+  PF_REQUIRE(dy_dev && y_dev && dx_dev, "pf_relu_bwd: null pointer");
+  relu_bwd_kernel<<<ew_grid(n), NT, 0, (cudaStream_t)stream>>>(dy_dev, y_dev, n, act, accumulate, dx_dev);
+  PF_CHECK_LAUNCH("pf_relu_bwd");
+  return PF_OK;
+}
+
+int pf_colsum(const float* a_dev, int64_t m, int c, float* out_dev, void* stream) {
+  PF_REQUIRE(m > 0 && c > 0 && m < (1ll << 31) && a_dev && out_dev, "pf_colsum: bad arguments");
+  colsum_kernel<<<c, NT, 0, (cudaStream_t)stream>>>(a_dev, (int)m, c, out_dev);
+  PF_CHECK_LAUNCH("pf_colsum");
+  return PF_OK;
+}
+
+int pf_maxpool_fwd(const pf_conv_desc* d, const float* x_dev, float* y_dev, void* stream) {
+  PF_REQUIRE(d && x_dev && y_dev && d->n > 0 && d->c > 0 && d->p > 0 && d->q > 0, "pf_maxpool_fwd: bad arguments");
+  const int64_t total = (int64_t)d->n * d->p * d->q * d->c;
+  maxpool_fwd_kernel<<<ew_grid(total), NT, 0, (cudaStream_t)stream>>>(x_dev, d->n, d->h, d->w, d->c, d->p, d->q, d->r,
+                                                                     d->s, d->stride_h, d->stride_w, d->pad_t,
+                                                                     d->pad_l, y_dev);
+  PF_CHECK_LAUNCH("pf_maxpool_fwd");
+  return PF_OK;
+}
+
+int pf_maxpool_bwd(const pf_conv_desc* d, const float* dy_dev, const float* x_dev, const float* y_dev,
+                   int accumulate, float* dx_dev, void* stream) {
+  PF_REQUIRE(d && dy_dev && x_dev && y_dev && dx_dev && d->n > 0 && d->c > 0, "pf_maxpool_bwd: bad arguments");
+  const int64_t total = (int64_t)d->n * d->h * d->w * d->c;
+  maxpool_bwd_kernel<<<ew_grid(total), NT, 0, (cudaStream_t)stream>>>(dy_dev, x_dev, y_dev, d->n, d->h, d->w, d->c,
+                                                                     d->p, d->q, d->r, d->s, d->stride_h,
+                                                                     d->stride_w, d->pad_t, d->pad_l, accumulate,
+                                                                     dx_dev);
+  PF_CHECK_LAUNCH("pf_maxpool_bwd");
+  return PF_OK;
+}
+
+int pf_global_avgpool_fwd(const float* x_dev, int n, int hw, int c, float* y_dev, void* stream) {
+  PF_REQUIRE(n > 0 && hw > 0 && c > 0 && x_dev && y_dev, "pf_global_avgpool_fwd: bad arguments");
+  dim3 grid((c + 63) / 64, n);
+  gap_fwd_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(x_dev, hw, c, y_dev);
+  PF_CHECK_LAUNCH("pf_global_avgpool_fwd");
+  return PF_OK;
+}
+
+int pf_global_avgpool_bwd(const float* dy_dev, int n, int hw, int c, int accumulate, float* dx_dev, void* stream) {
+  PF_REQUIRE(n > 0 && hw > 0 && c > 0 && dy_dev && dx_dev, "pf_global_avgpool_bwd: bad arguments");
+  const int64_t total = (int64_t)n * hw * c;
+  gap_bwd_kernel<<<ew_grid(total), NT, 0, (cudaStream_t)stream>>>(dy_dev, total, hw, c, accumulate, dx_dev);
+  PF_CHECK_LAUNCH("pf_global_avgpool_bwd");
+  return PF_OK;
+}
+
+int pf_softmax_fwd(const float* x_dev, int n, int k, float* y_dev, void* stream) {
+  PF_REQUIRE(n > 0 && k > 0 && x_dev && y_dev, "pf_softmax_fwd: bad arguments");
+  softmax_fwd_kernel<<<(n + 7) / 8, NT, 0, (cudaStream_t)stream>>>(x_dev, n, k, y_dev);
+  PF_CHECK_LAUNCH("pf_softmax_fwd");
+  return PF_OK;
+}
+
+int pf_softmax_bwd(const float* dy_dev, const float* y_dev, int n, int k, float* dx_dev, void* stream) {
+  PF_REQUIRE(n > 0 && k > 0 && dy_dev && y_dev && dx_dev, "pf_softmax_bwd: bad arguments");
+  softmax_bwd_kernel<<<(n + 7) / 8, NT, 0, (cudaStream_t)stream>>>(dy_dev, y_dev, n, k, dx_dev);
+  PF_CHECK_LAUNCH("pf_softmax_bwd");
+  return PF_OK;
+}
+
+}  // extern "C"

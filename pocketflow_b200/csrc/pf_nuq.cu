@@ -11,9 +11,9 @@
 namespace {
 constexpr int kThreads = 256;
 
-__device__ __forceinline__ float nuq_one(float w, float alpha, float beta, const float* __restrict__ c,
-                                         int nc, uint8_t* idx_out) {
-  const float xn = __fdiv_rn(__fsub_rn(w, beta), alpha);
+__device__ __forceinline__ float nuq_one(float w, float alpha, float beta, float ralpha,
+                                         const float* __restrict__ c, int nc, uint8_t* idx_out) {
+  const float xn = pf_div_r(__fsub_rn(w, beta), alpha, ralpha);
   float best = fabsf(__fsub_rn(xn, c[0]));
   int bi = 0;
   for (int j = 1; j < nc; ++j) {
@@ -31,7 +31,7 @@ __device__ __forceinline__ float nuq_one(float w, float alpha, float beta, const
 
 __global__ void __launch_bounds__(kThreads)
 nuq_quant_kernel(const pf_uq_seg* __restrict__ segs, const pf_work* __restrict__ work,
-                 const uint32_t* __restrict__ mn_enc, const uint32_t* __restrict__ mx_enc,
+                 const float* __restrict__ scales, int n_buckets,
                  const float* __restrict__ clusters, uint8_t* __restrict__ idx_out,
                  const int64_t* __restrict__ idx_base) {
   __shared__ float sc[256];
@@ -40,22 +40,22 @@ nuq_quant_kernel(const pf_uq_seg* __restrict__ segs, const pf_work* __restrict__
   const int nc = 1 << s.bits;
   if ((int)threadIdx.x < nc) sc[threadIdx.x] = __ldg(clusters + (size_t)w.seg * 256 + threadIdx.x);
   __syncthreads();
-  const float mn = pf_dec(__ldg(mn_enc + s.bucket0)), mx = pf_dec(__ldg(mx_enc + s.bucket0));
-  const float alpha = __fadd_rn(__fsub_rn(mx, mn), 1e-10f);
+  const float alpha = __ldg(scales + s.bucket0), mn = __ldg(scales + n_buckets + s.bucket0);
+  const float ra = __ldg(scales + 2 * n_buckets + s.bucket0);
   uint8_t* io = idx_out ? idx_out + idx_base[w.seg] : nullptr;
   const int64_t end = w.start + w.count;
   for (int64_t i = w.start + (int64_t)threadIdx.x * 4; i < end; i += kThreads * 4) {
     if (i + 3 < end) {
       float4 v = pf_ld4(s.src + i);
       uint8_t id[4];
-      v.x = nuq_one(v.x, alpha, mn, sc, nc, io ? &id[0] : nullptr);
-      v.y = nuq_one(v.y, alpha, mn, sc, nc, io ? &id[1] : nullptr);
-      v.z = nuq_one(v.z, alpha, mn, sc, nc, io ? &id[2] : nullptr);
-      v.w = nuq_one(v.w, alpha, mn, sc, nc, io ? &id[3] : nullptr);
+      v.x = nuq_one(v.x, alpha, mn, ra, sc, nc, io ? &id[0] : nullptr);
+      v.y = nuq_one(v.y, alpha, mn, ra, sc, nc, io ? &id[1] : nullptr);
+      v.z = nuq_one(v.z, alpha, mn, ra, sc, nc, io ? &id[2] : nullptr);
+      v.w = nuq_one(v.w, alpha, mn, ra, sc, nc, io ? &id[3] : nullptr);
       pf_st_stream(s.dst + i, v);
       if (io) *reinterpret_cast<uchar4*>(io + i) = make_uchar4(id[0], id[1], id[2], id[3]);
     } else {
-      for (int64_t j = i; j < end; ++j) s.dst[j] = nuq_one(s.src[j], alpha, mn, sc, nc, io ? io + j : nullptr);
+      for (int64_t j = i; j < end; ++j) s.dst[j] = nuq_one(s.src[j], alpha, mn, ra, sc, nc, io ? io + j : nullptr);
     }
   }
 }
@@ -64,17 +64,17 @@ nuq_quant_kernel(const pf_uq_seg* __restrict__ segs, const pf_work* __restrict__
 extern "C" {
 
 int pf_nuq_weight_quant(const pf_uq_seg* segs_dev, const pf_work* work_dev, int n_work,
-                        const uint32_t* mn_enc_dev, const uint32_t* mx_enc_dev,
+                        const float* scales_dev, int n_buckets,
                         const float* clusters_dev, uint8_t* idx_out_dev,
                         const int64_t* idx_base_dev, void* stream) {
   PF_REQUIRE(n_work >= 0, "pf_nuq_weight_quant: n_work < 0");
   if (n_work == 0) return PF_OK;
-  PF_REQUIRE(segs_dev && work_dev && mn_enc_dev && mx_enc_dev && clusters_dev,
+  PF_REQUIRE(segs_dev && work_dev && scales_dev && clusters_dev,
              "pf_nuq_weight_quant: null pointer");
   PF_REQUIRE((idx_out_dev == nullptr) == (idx_base_dev == nullptr),
              "pf_nuq_weight_quant: idx_out and idx_base must be given together");
   nuq_quant_kernel<<<n_work, kThreads, 0, (cudaStream_t)stream>>>(
-      segs_dev, work_dev, mn_enc_dev, mx_enc_dev, clusters_dev, idx_out_dev, idx_base_dev);
+      segs_dev, work_dev, scales_dev, n_buckets, clusters_dev, idx_out_dev, idx_base_dev);
   PF_CHECK_LAUNCH("pf_nuq_weight_quant");
   return PF_OK;
 }

@@ -137,38 +137,52 @@ uq_weight_minmax_kernel(const pf_uq_seg* __restrict__ segs, const pf_work* __res
 // ------------------------------------------------------------------ weight quantize / STE backward
 enum { kModeQuant = 0, kModeSteBwd = 1 };
 
-template <int MODE>
-__device__ __forceinline__ float apply_one(float x, float mn, float mx, float k) {
+// per bucket: alpha = (max-min)+1e-10, beta = min, ralpha = RN(1/alpha)  ->  scales[3][n_buckets]
+__global__ void __launch_bounds__(kThreads)
+uq_scales_kernel(const uint32_t* __restrict__ mn_enc, const uint32_t* __restrict__ mx_enc, int n,
+                 float* __restrict__ scales) {
+  const int i = blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  const float mn = pf_dec(mn_enc[i]), mx = pf_dec(mx_enc[i]);
   const float alpha = __fadd_rn(__fsub_rn(mx, mn), 1e-10f);
-  if (MODE == kModeQuant) return pf_fake_quant(x, alpha, mn, k);
+  scales[i] = alpha;
+  scales[n + i] = mn;
+  scales[2 * n + i] = __frcp_rn(alpha);
+}
+
+template <int MODE>
+__device__ __forceinline__ float apply_one(float x, float alpha, float beta, float ralpha, float k, float rk) {
+  if (MODE == kModeQuant) return pf_fake_quant(x, alpha, beta, k, ralpha, rk);
   // STE: Mul(alpha) -> RealDiv(k) -> Mul(k) -> RealDiv(alpha) gradients, in that order
-  return __fdiv_rn(__fmul_rn(__fdiv_rn(__fmul_rn(x, alpha), k), k), alpha);
+  return pf_div_r(__fmul_rn(pf_div_r(__fmul_rn(x, alpha), k, rk), k), alpha, ralpha);
 }
 
 template <int MODE>
 __global__ void __launch_bounds__(kThreads)
 uq_weight_apply_kernel(const pf_uq_seg* __restrict__ segs, const pf_work* __restrict__ work,
-                       const uint32_t* __restrict__ mn_enc, const uint32_t* __restrict__ mx_enc) {
+                       const float* __restrict__ scales, int n_buckets) {
   const pf_work w = work[blockIdx.x];
   const pf_uq_seg s = segs[w.seg];
   const float k = pf_uq_kf(s.bits);
+  const float rk = __frcp_rn(k);
   const int64_t end = w.start + w.count;
   const uint32_t ncols = (uint32_t)s.ncols;
-  const uint32_t* __restrict__ mnp = mn_enc + s.bucket0;
-  const uint32_t* __restrict__ mxp = mx_enc + s.bucket0;
+  const float* __restrict__ pa = scales + s.bucket0;
+  const float* __restrict__ pb = scales + n_buckets + s.bucket0;
+  const float* __restrict__ pr = scales + 2 * n_buckets + s.bucket0;
   int64_t i = w.start + (int64_t)threadIdx.x * 4;
   if (ncols == 1) {
-    const float mn = pf_dec(__ldg(mnp)), mx = pf_dec(__ldg(mxp));
+    const float al = __ldg(pa), be = __ldg(pb), ra = __ldg(pr);
     for (; i < end; i += kThreads * 4) {
       if (i + 3 < end) {
         float4 v = pf_ld4(s.src + i);
-        v.x = apply_one<MODE>(v.x, mn, mx, k);
-        v.y = apply_one<MODE>(v.y, mn, mx, k);
-        v.z = apply_one<MODE>(v.z, mn, mx, k);
-        v.w = apply_one<MODE>(v.w, mn, mx, k);
+        v.x = apply_one<MODE>(v.x, al, be, ra, k, rk);
+        v.y = apply_one<MODE>(v.y, al, be, ra, k, rk);
+        v.z = apply_one<MODE>(v.z, al, be, ra, k, rk);
+        v.w = apply_one<MODE>(v.w, al, be, ra, k, rk);
         pf_st_stream(s.dst + i, v);
       } else {
-        for (int64_t j = i; j < end; ++j) s.dst[j] = apply_one<MODE>(s.src[j], mn, mx, k);
+        for (int64_t j = i; j < end; ++j) s.dst[j] = apply_one<MODE>(s.src[j], al, be, ra, k, rk);
       }
     }
     return;
@@ -180,17 +194,18 @@ uq_weight_apply_kernel(const pf_uq_seg* __restrict__ segs, const pf_work* __rest
   for (; i < end; i += kThreads * 4) {
     if (aligned && i + 3 < end) {
       float4 v = pf_ld4(s.src + i);
-      const uint4 a = __ldg(reinterpret_cast<const uint4*>(mnp + c));
-      const uint4 b = __ldg(reinterpret_cast<const uint4*>(mxp + c));
-      v.x = apply_one<MODE>(v.x, pf_dec(a.x), pf_dec(b.x), k);
-      v.y = apply_one<MODE>(v.y, pf_dec(a.y), pf_dec(b.y), k);
-      v.z = apply_one<MODE>(v.z, pf_dec(a.z), pf_dec(b.z), k);
-      v.w = apply_one<MODE>(v.w, pf_dec(a.w), pf_dec(b.w), k);
+      const float4 a = __ldg(reinterpret_cast<const float4*>(pa + c));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(pb + c));
+      const float4 r = __ldg(reinterpret_cast<const float4*>(pr + c));
+      v.x = apply_one<MODE>(v.x, a.x, b.x, r.x, k, rk);
+      v.y = apply_one<MODE>(v.y, a.y, b.y, r.y, k, rk);
+      v.z = apply_one<MODE>(v.z, a.z, b.z, r.z, k, rk);
+      v.w = apply_one<MODE>(v.w, a.w, b.w, r.w, k, rk);
       pf_st_stream(s.dst + i, v);
     } else {
       for (int j = 0; j < 4 && i + j < end; ++j) {
         const uint32_t cj = (c + j) % ncols;
-        s.dst[i + j] = apply_one<MODE>(s.src[i + j], pf_dec(__ldg(mnp + cj)), pf_dec(__ldg(mxp + cj)), k);
+        s.dst[i + j] = apply_one<MODE>(s.src[i + j], __ldg(pa + cj), __ldg(pb + cj), __ldg(pr + cj), k, rk);
       }
     }
     c += step;
@@ -236,6 +251,7 @@ uq_act_quant_kernel(const float* x, float* y, int64_t n, const uint32_t* __restr
   const float mn = pf_dec(__ldg(minmax_enc)), mx = pf_dec(__ldg(minmax_enc + 1));
   const float alpha = __fadd_rn(__fsub_rn(mx, mn), 1e-10f);
   const float k = pf_uq_kf(bits);
+  const float ra = __frcp_rn(alpha), rk = __frcp_rn(k);
   const int64_t nvec = n >> 2;
   const int64_t stride = (int64_t)gridDim.x * kThreads;
   int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
@@ -245,24 +261,24 @@ uq_act_quant_kernel(const float* x, float* y, int64_t n, const uint32_t* __restr
     for (int u = 0; u < kActUnroll; ++u) v[u] = pf_ld4(x + ((i + u * stride) << 2));
 #pragma unroll
     for (int u = 0; u < kActUnroll; ++u) {
-      v[u].x = pf_fake_quant(v[u].x, alpha, mn, k);
-      v[u].y = pf_fake_quant(v[u].y, alpha, mn, k);
-      v[u].z = pf_fake_quant(v[u].z, alpha, mn, k);
-      v[u].w = pf_fake_quant(v[u].w, alpha, mn, k);
+      v[u].x = pf_fake_quant(v[u].x, alpha, mn, k, ra, rk);
+      v[u].y = pf_fake_quant(v[u].y, alpha, mn, k, ra, rk);
+      v[u].z = pf_fake_quant(v[u].z, alpha, mn, k, ra, rk);
+      v[u].w = pf_fake_quant(v[u].w, alpha, mn, k, ra, rk);
       pf_st_stream(y + ((i + u * stride) << 2), v[u]);
     }
   }
   for (; i < nvec; i += stride) {
     float4 v = pf_ld4(x + (i << 2));
-    v.x = pf_fake_quant(v.x, alpha, mn, k);
-    v.y = pf_fake_quant(v.y, alpha, mn, k);
-    v.z = pf_fake_quant(v.z, alpha, mn, k);
-    v.w = pf_fake_quant(v.w, alpha, mn, k);
+    v.x = pf_fake_quant(v.x, alpha, mn, k, ra, rk);
+    v.y = pf_fake_quant(v.y, alpha, mn, k, ra, rk);
+    v.z = pf_fake_quant(v.z, alpha, mn, k, ra, rk);
+    v.w = pf_fake_quant(v.w, alpha, mn, k, ra, rk);
     pf_st_stream(y + (i << 2), v);
   }
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
     const int64_t j = (nvec << 2) + threadIdx.x;
-    y[j] = pf_fake_quant(x[j], alpha, mn, k);
+    y[j] = pf_fake_quant(x[j], alpha, mn, k, ra, rk);
   }
 }
 
@@ -289,24 +305,37 @@ int pf_uq_weight_minmax(const pf_uq_seg* segs_dev, const pf_work* work_dev, int 
   return PF_OK;
 }
 
+int pf_uq_weight_scales(const uint32_t* mn_enc_dev, const uint32_t* mx_enc_dev, int n_buckets,
+                        float* scales_dev, void* stream) {
+  PF_REQUIRE(n_buckets >= 0, "pf_uq_weight_scales: n_buckets < 0");
+  if (n_buckets == 0) return PF_OK;
+  PF_REQUIRE(mn_enc_dev && mx_enc_dev && scales_dev, "pf_uq_weight_scales: null pointer");
+  PF_REQUIRE((n_buckets & 3) == 0 && ((uintptr_t)scales_dev & 15) == 0,
+             "pf_uq_weight_scales: n_buckets must be a multiple of 4 and scales 16-byte aligned");
+  uq_scales_kernel<<<(n_buckets + kThreads - 1) / kThreads, kThreads, 0, (cudaStream_t)stream>>>(
+      mn_enc_dev, mx_enc_dev, n_buckets, scales_dev);
+  PF_CHECK_LAUNCH("pf_uq_weight_scales");
+  return PF_OK;
+}
+
 int pf_uq_weight_quant(const pf_uq_seg* segs_dev, const pf_work* work_dev, int n_work,
-                       const uint32_t* mn_enc_dev, const uint32_t* mx_enc_dev, void* stream) {
+                       const float* scales_dev, int n_buckets, void* stream) {
   PF_REQUIRE(n_work >= 0, "pf_uq_weight_quant: n_work < 0");
   if (n_work == 0) return PF_OK;
-  PF_REQUIRE(segs_dev && work_dev && mn_enc_dev && mx_enc_dev, "pf_uq_weight_quant: null pointer");
+  PF_REQUIRE(segs_dev && work_dev && scales_dev, "pf_uq_weight_quant: null pointer");
   uq_weight_apply_kernel<kModeQuant><<<n_work, kThreads, 0, (cudaStream_t)stream>>>(
-      segs_dev, work_dev, mn_enc_dev, mx_enc_dev);
+      segs_dev, work_dev, scales_dev, n_buckets);
   PF_CHECK_LAUNCH("pf_uq_weight_quant");
   return PF_OK;
 }
 
 int pf_uq_weight_ste_bwd(const pf_uq_seg* segs_dev, const pf_work* work_dev, int n_work,
-                         const uint32_t* mn_enc_dev, const uint32_t* mx_enc_dev, void* stream) {
+                         const float* scales_dev, int n_buckets, void* stream) {
   PF_REQUIRE(n_work >= 0, "pf_uq_weight_ste_bwd: n_work < 0");
   if (n_work == 0) return PF_OK;
-  PF_REQUIRE(segs_dev && work_dev && mn_enc_dev && mx_enc_dev, "pf_uq_weight_ste_bwd: null pointer");
+  PF_REQUIRE(segs_dev && work_dev && scales_dev, "pf_uq_weight_ste_bwd: null pointer");
   uq_weight_apply_kernel<kModeSteBwd><<<n_work, kThreads, 0, (cudaStream_t)stream>>>(
-      segs_dev, work_dev, mn_enc_dev, mx_enc_dev);
+      segs_dev, work_dev, scales_dev, n_buckets);
   PF_CHECK_LAUNCH("pf_uq_weight_ste_bwd");
   return PF_OK;
 }

@@ -1,0 +1,78 @@
+"""Abstract class for datasets (/root/reference/datasets/abstract_dataset.py:34-111).
+
+`build()` returns an iterator whose `get_next()` yields the symbolic (images, labels) placeholders
+of the current graph — what tf.data's `iterator.get_next()` returns in the reference — and whose
+`next_batch()` produces the host mini-batch (pinned memory) that the learner copies into them
+every step.  Multi-GPU training shards the stream by rank (reference: file-level sharding, :80-81)."""
+from abc import ABC
+
+import numpy as np
+import torch
+
+from .. import graph as G
+from ..flags import FLAGS, DEFINE_string, DEFINE_integer
+from ..utils.multi_gpu_wrapper import MultiGpuWrapper as mgw
+
+DEFINE_string('data_disk', 'local', 'data disk\'s location (\'local\' | \'hdfs\')')
+DEFINE_string('data_hdfs_host', None, 'HDFS host for data files')
+DEFINE_string('data_dir_local', None, 'data directory - local (None: synthetic batches)')
+DEFINE_string('data_dir_hdfs', None, 'data directory - HDFS')
+DEFINE_integer('cycle_length', 4, '# of datasets to interleave from in parallel')
+DEFINE_integer('nb_threads', 8, '# of threads for preprocessing the dataset')
+DEFINE_integer('buffer_size', 1024, '# of elements to be buffered when prefetching')
+DEFINE_integer('prefetch_size', 8, '# of mini-batches to be buffered when prefetching')
+
+
+class BatchIterator(object):
+    def __init__(self, batch_size, image_shape, nb_classes, generator):
+        self.batch_size, self.image_shape, self.nb_classes = batch_size, tuple(image_shape), nb_classes
+        self.generator = generator
+        self.images, self.labels = None, None
+        pin = torch.cuda.is_available()
+        self.host_images = torch.empty((batch_size,) + self.image_shape, dtype=torch.float32, pin_memory=pin)
+        self.host_labels = torch.empty((batch_size, nb_classes), dtype=torch.float32, pin_memory=pin)
+
+    def get_next(self):
+        """Symbolic (images, labels) of the current default graph."""
+        self.images = G.placeholder((self.batch_size,) + self.image_shape, 'images')
+        self.labels = G.placeholder((self.batch_size, self.nb_classes), 'labels')
+        self.images.iterator = self
+        return self.images, self.labels
+
+    def next_batch(self):
+        """Fill the pinned host buffers with the next mini-batch and return them."""
+        img, lab = self.generator(self.batch_size)
+        self.host_images.copy_(torch.from_numpy(img))
+        self.host_labels.copy_(torch.from_numpy(lab))
+        return self.host_images, self.host_labels
+
+
+class AbstractDataset(ABC):
+    def __init__(self, is_train):
+        self.is_train = is_train
+        self.batch_size = None
+        self.image_shape = None
+        self.nb_classes = None
+        self.enbl_shard = (is_train and FLAGS.enbl_multi_gpu)
+
+    def _generator(self):
+        """Synthetic stream shaped like the real data: standardised images
+        ~ N(0,1), uniformly random one-hot labels.  Seeds: images 1234, labels 1235 (+rank when
+        sharded, so every rank sees its own slice of the global batch)."""
+        rank = mgw.rank() if self.enbl_shard else 0
+        rng_i = np.random.default_rng(1234 + 7919 * rank + (0 if self.is_train else 1))
+        rng_l = np.random.default_rng(1235 + 7919 * rank + (0 if self.is_train else 1))
+        shape, k = self.image_shape, self.nb_classes
+
+        def gen(b):
+            img = rng_i.standard_normal(size=(b,) + tuple(shape), dtype=np.float32)
+            lab = np.zeros((b, k), np.float32)
+            lab[np.arange(b), rng_l.integers(0, k, size=b)] = 1.0
+            return img, lab
+        return gen
+
+    def build(self, enbl_trn_val_split=False):
+        it = BatchIterator(self.batch_size, self.image_shape, self.nb_classes, self._generator())
+        if self.is_train and enbl_trn_val_split:
+            return it, BatchIterator(self.batch_size, self.image_shape, self.nb_classes, self._generator())
+        return it

@@ -1,0 +1,580 @@
+"""Executor: lowers a `graph.Graph` to launches of libpf_b200.so kernels (forward, backward,
+gradient reduction, optimizer) and replays them through a CUDA graph.
+
+This is the stand-in for `sess.run(train_op)` into TensorFlow's executor
+(/root/reference/learners/uniform_quantization/learner.py:114-152): one call = one training step
+on one GPU.  State layout (B200, 180 GB HBM): all trainable parameters, their gradients and the
+optimizer slots live in FLAT fp32 buffers so that (a) the data-parallel gradient reduction is one
+collective over one buffer and (b) the optimizer / mask / weight-decay work is a
+handful of launches instead of ~110 per step.
+"""
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import graph as G
+from . import ops
+
+F32 = np.float32
+MATMUL_TYPES = ('Conv2D', 'MatMul', 'DepthwiseConv2dNative')
+ACT_TYPES = {'Relu': 1, 'Relu6': 2}
+
+
+def _align4(n):
+    return (n + 3) // 4 * 4
+
+
+class ParamStore:
+    """Flat storage for the trainable variables of one model scope (+ separate non-trainable store).
+
+    Order: maskable variables first, then by weight-decay coefficient, so that the optimizer runs
+    over at most a few contiguous ranges."""
+
+    def __init__(self, variables, device, wd_of=None, maskable=None, seed=1):
+        self.device = device
+        wd_of = wd_of or {}
+        maskable = set(maskable or [])
+        train = [v for v in variables if v.trainable]
+        other = [v for v in variables if not v.trainable]
+        key = lambda v: (0 if v in maskable else 1, -float(wd_of.get(v, 0.0)))
+        order = sorted(range(len(train)), key=lambda i: (key(train[i]), i))
+        self.train_vars = [train[i] for i in order]
+        self.other_vars = other
+        self.offset, self.ranges = {}, []      # ranges: (start, end, masked, wd)
+        pos = 0
+        cur = None
+        for v in self.train_vars:
+            k = (v in maskable, float(wd_of.get(v, 0.0)))
+            if cur is None or cur[2:] != k:
+                if cur is not None:
+                    self.ranges.append((cur[0], pos, cur[2], cur[3]))
+                cur = (pos, None) + k
+            self.offset[v] = pos
+            pos += _align4(v.numel)
+        if cur is not None:
+            self.ranges.append((cur[0], pos, cur[2], cur[3]))
+        self.n_train = max(pos, 4)
+        self.n_masked = max([e for (s, e, m, w) in self.ranges if m] + [0])
+        opos = 0
+        for v in other:
+            self.offset[v] = opos
+            opos += _align4(v.numel)
+        self.n_other = max(opos, 4)
+        self.P = torch.zeros(self.n_train, dtype=torch.float32, device=device)
+        self.O = torch.zeros(self.n_other, dtype=torch.float32, device=device)
+        self.init(seed)
+
+    def init(self, seed):
+        rng = np.random.default_rng(seed)
+        hp = np.zeros(self.n_train, F32)
+        for v in sorted(self.train_vars, key=lambda v: v.name):
+            hp[self.offset[v]:self.offset[v] + v.numel] = v.initializer(rng, v.shape).reshape(-1)
+        ho = np.zeros(self.n_other, F32)
+        for v in self.other_vars:
+            ho[self.offset[v]:self.offset[v] + v.numel] = v.initializer(rng, v.shape).reshape(-1)
+        self.P.copy_(torch.from_numpy(hp))
+        self.O.copy_(torch.from_numpy(ho))
+
+    def view(self, v, flat=None):
+        buf = flat if flat is not None else (self.P if v.trainable else self.O)
+        o = self.offset[v]
+        return buf[o:o + v.numel].view(v.shape)
+
+    def state_dict(self):
+        d = OrderedDict()
+        for v in self.train_vars + self.other_vars:
+            d[v.name] = self.view(v).detach().cpu().numpy().copy()
+        return d
+
+    def load_state_dict(self, d, strict=True):
+        for v in self.train_vars + self.other_vars:
+            if v.name in d:
+                self.view(v).copy_(torch.from_numpy(np.asarray(d[v.name], F32).reshape(v.shape)))
+            elif strict:
+                raise KeyError('missing variable in checkpoint: ' + v.name)
+
+
+class Executor:
+    """Forward (+ backward + update) of one graph on one GPU."""
+
+    def __init__(self, graph, images, logits, device, store=None, train=True, loss=None, labels=None,
+                 optimizer=None, weight_quant=None, act_quant=None, maskable=None, teacher=None,
+                 seed=1, exact_ste=True, grad_scale=1.0, scope=None):
+        self.g, self.device, self.train = graph, device, train
+        self.images, self.logits_t, self.labels_t = images, logits, labels
+        self.loss, self.teacher = loss, teacher
+        self.optimizer = optimizer or {}
+        self.exact_ste, self.grad_scale = exact_ste, float(grad_scale)
+        self.ops = self._reachable_ops(logits)
+        variables = []
+        for op in self.ops:
+            for v in op.vars.values():
+                if v not in variables:
+                    variables.append(v)
+        self.variables = variables
+        wd_of = dict(loss.l2) if loss is not None else {}
+        self.wd_of = wd_of
+        self.maskable = [v for v in (maskable or []) if v in variables]
+        self.store = store or ParamStore(variables, device, wd_of, self.maskable, seed)
+        self.weight_quant, self.act_quant = weight_quant, act_quant
+        self.prof = None
+        self._plan()
+        self._graph = None
+        self.step_count = 0
+
+    # ------------------------------------------------------------------ planning
+    def _reachable_ops(self, out):
+        seen, order = set(), []
+
+        def visit(t):
+            if t.op in seen:
+                return
+            seen.add(t.op)
+            for i in t.op.inputs:
+                visit(i)
+            order.append(t.op)
+        import sys
+        sys.setrecursionlimit(max(10000, sys.getrecursionlimit()))
+        visit(out)
+        pos = {op: i for i, op in enumerate(self.g.ops)}
+        return sorted(order, key=lambda o: pos[o])
+
+    def _consumers(self, t):
+        return [c for c in t.consumers if c in self._opset]
+
+    def _plan(self):
+        dev = self.device
+        self._opset = set(self.ops)
+        st = self.store
+        E = lambda shape: torch.empty(shape, dtype=torch.float32, device=dev)
+        self.buf, self.alias = {}, {}
+        self.fused_act, self.fused_into = {}, {}
+        # ---- fusion: BN -> Relu/Relu6 and Conv/MatMul(bias) -> Relu with a single consumer
+        for op in self.ops:
+            if op.type in ACT_TYPES:
+                src = op.inputs[0].op
+                if src.type in ('FusedBatchNorm', 'Conv2D', 'MatMul') and len(self._consumers(src.output)) == 1:
+                    if src.type == 'FusedBatchNorm' or op.type == 'Relu':
+                        self.fused_act[src] = ACT_TYPES[op.type]
+                        self.fused_into[op] = src
+                        continue
+                raise NotImplementedError('activation %s is not preceded by a fusable producer' % op.name)
+        # ---- quantization marks
+        self.wq_ops = list(self.weight_quant['ops']) if self.weight_quant else []
+        self.aq_ops = list(self.act_quant['ops']) if self.act_quant else []
+        self.aq_index = {op: i for i, op in enumerate(self.aq_ops)}
+        self.aq_slots = torch.zeros(max(len(self.aq_ops), 1), 2, dtype=torch.int32, device=dev)
+        self.aq_out = {}           # relu op -> out-of-place quantized buffer (producer is not BN)
+        # quantized weights live in a flat buffer with the same offsets as the parameters
+        self.QW = torch.zeros(st.n_train, dtype=torch.float32, device=dev) if self.wq_ops else None
+        self.wq = None
+        if self.wq_ops:
+            kvars = [op.vars['kernel'] for op in self.wq_ops]
+            srcs = [st.view(v) for v in kvars]
+            dsts = [st.view(v, self.QW) for v in kvars]
+            wq = self.weight_quant
+            if wq.get('kind', 'uniform') == 'uniform':
+                self.wq = ops.UniformWeightQuantizer(srcs, dsts, wq['bits'], wq.get('use_buckets', False),
+                                                     wq.get('bucket_type', 'channel'), wq.get('bucket_size', 256))
+            else:
+                self.wq = ops.CodebookWeightQuantizer(srcs, dsts, wq['bits'])
+        self.qvars = {op: op.vars['kernel'] for op in self.wq_ops}
+        # ---- tensors
+        for op in self.ops:
+            t = op.output
+            if op.type == 'Placeholder':
+                self.buf[t] = E(t.shape)
+                self.buf[t].zero_()
+            elif op.type in ('Reshape', 'Identity'):
+                self.alias[t] = op.inputs[0]
+            elif op in self.fused_into:
+                self.alias[t] = op.inputs[0]
+            else:
+                self.buf[t] = E(t.shape)
+            if op in self.aq_index and self.fused_into.get(op) is not None and \
+                    self.fused_into[op].type != 'FusedBatchNorm':
+                self.aq_out[op] = E(t.shape)
+        # ---- per-op scratch
+        self.bn = {}
+        max_ws, max_wt, max_bnws = 4, 4, 4
+        self.desc = {}
+        for op in self.ops:
+            if op.type == 'FusedBatchNorm':
+                c = op.output.shape[-1]
+                self.bn[op] = dict(mean=E((c,)), var=E((c,)), rstd=E((c,)))
+                max_bnws = max(max_bnws, 3 * c * ops.BN_MAX_SPLITS)
+            if op.type in ('Conv2D', 'MatMul'):
+                x, y = op.inputs[0], op.output
+                if op.type == 'Conv2D':
+                    n, h, w, c = x.shape
+                    _, p, q, k = y.shape
+                    (kh, kw), (sh, sw), (pt, pl) = op.attrs['ksize'], op.attrs['strides'], op.attrs['pad']
+                    d = ops.conv_desc(n, h, w, c, k, kh, kw, p, q, sh, sw, pt, pl)
+                else:
+                    n, c = x.shape
+                    k = y.shape[1]
+                    d = ops.conv_desc(n, 1, 1, c, k, 1, 1, 1, 1, 1, 1, 0, 0)
+                self.desc[op] = d
+                if self.train:
+                    max_ws = max(max_ws, ops.conv2d_wgrad_workspace_floats(d))
+                    max_wt = max(max_wt, op.vars['kernel'].numel)
+            if op.type == 'MaxPool':
+                x, y = op.inputs[0], op.output
+                n, h, w, c = x.shape
+                _, p, q, _ = y.shape
+                (kh, kw), (sh, sw), (pt, pl) = op.attrs['ksize'], op.attrs['strides'], op.attrs['pad']
+                self.desc[op] = ops.conv_desc(n, h, w, c, c, kh, kw, p, q, sh, sw, pt, pl)
+        if self.labels_t is not None and self.labels_t not in self.buf:
+            self.buf[self.labels_t] = torch.zeros(self.labels_t.shape, dtype=torch.float32, device=dev)
+        self.bn_ws = E((max_bnws,))
+        n_rows = self.logits_t.shape[0]
+        self.loss_out = torch.zeros(8, dtype=torch.float32, device=dev)
+        self.row_ws = E((4 * n_rows,))
+        if self.train:
+            self.G = torch.zeros(st.n_train, dtype=torch.float32, device=dev)
+            self.S1 = torch.zeros(st.n_train, dtype=torch.float32, device=dev)
+            self.S2 = torch.zeros(st.n_train, dtype=torch.float32, device=dev) \
+                if self.optimizer.get('kind') == 'adam' else None
+            self.hp = torch.zeros(4, dtype=torch.float32, device=dev)
+            self.hp_host = torch.zeros(4, dtype=torch.float32).pin_memory() if dev.type == 'cuda' else torch.zeros(4)
+            self.wgrad_ws = E((max_ws,))
+            self.wt_ws = E((max_wt,))
+            self.l2_out = torch.zeros(4, dtype=torch.float32, device=dev)
+            self.l2_ws = E((ops.L2_PARTIALS,))
+            self.gbuf, self.galias = {}, {}
+            self.relu_scratch = {}
+            for op in self.ops:
+                t = op.output
+                if op.type == 'Placeholder':
+                    continue
+                if t in self.alias:
+                    self.galias[t] = self.alias[t]
+                else:
+                    self.gbuf[t] = E(t.shape)
+                if op.type in ('Conv2D', 'MatMul') and op in self.fused_act:
+                    self.relu_scratch[op] = E(t.shape)
+            if self.maskable:
+                self.MASK = torch.ones(st.n_masked, dtype=torch.float32, device=dev)
+                self.BKUP = st.P[:st.n_masked].clone()
+                mv = self.maskable
+                self.mask_builder = ops.MaskBuilder([st.view(v) for v in mv],
+                                                    [st.view(v, self.BKUP) for v in mv],
+                                                    [st.view(v, self.MASK) for v in mv])
+            else:
+                self.MASK = None
+            if self.exact_ste and self.wq is not None and isinstance(self.wq, ops.UniformWeightQuantizer):
+                self._ste_grads = [st.view(v, self.G) for v in [op.vars['kernel'] for op in self.wq_ops]]
+            else:
+                self._ste_grads = None
+            self.beta1_power = F32(self.optimizer.get('beta1', 0.9))
+            self.beta2_power = F32(self.optimizer.get('beta2', 0.999))
+
+    # ------------------------------------------------------------------ profiling (bench.py roofline)
+    class _Timed:
+        def __init__(self, ex, cat):
+            self.ex, self.cat = ex, cat
+
+        def __enter__(self):
+            if self.ex.prof is not None:
+                self.a = torch.cuda.Event(enable_timing=True)
+                self.a.record()
+
+        def __exit__(self, *exc):
+            if self.ex.prof is not None:
+                b = torch.cuda.Event(enable_timing=True)
+                b.record()
+                self.ex.prof.setdefault(self.cat, []).append((self.a, b))
+
+    def timed(self, cat):
+        return Executor._Timed(self, cat)
+
+    def profile_step(self, lr, allreduce=None):
+        """One EAGER step with every launch group bracketed by CUDA events on the launching stream.
+        Returns {category: milliseconds}.  (Not the timed region: the benchmark replays a CUDA graph.)"""
+        self.prof = {}
+        if self.teacher is not None:
+            self.teacher.prof = self.prof
+        self.set_hyper(lr)
+        self.device_step(allreduce)
+        torch.cuda.synchronize()
+        out = {k: sum(a.elapsed_time(b) for a, b in v) for k, v in self.prof.items()}
+        self.prof = None
+        if self.teacher is not None:
+            self.teacher.prof = None
+        self.advance_optimizer_state()
+        return out
+
+    # ------------------------------------------------------------------ helpers
+    def T(self, t):
+        """Buffer that holds tensor t as seen by its consumers."""
+        while t in self.alias:
+            op = t.op
+            if op in self.aq_out:
+                return self.aq_out[op].view(t.shape)
+            t = self.alias[t]
+        b = self.buf[t]
+        return b if b.shape == t.shape else b.view(t.shape)
+
+    def raw(self, t):
+        while t in self.alias:
+            t = self.alias[t]
+        return self.buf[t]
+
+    def gkey(self, t):
+        while t in self.galias:
+            t = self.galias[t]
+        return t
+
+    def grad_target(self, t):
+        """(buffer, accumulate) for writing a contribution to dL/dt."""
+        k = self.gkey(t)
+        acc = k in self._gwritten
+        self._gwritten.add(k)
+        return self.gbuf[k], acc
+
+    def grad_of(self, t):
+        k = self.gkey(t)
+        return self.gbuf[k] if k in self._gwritten else None
+
+    def kernel_of(self, op):
+        v = op.vars['kernel']
+        if op in self.qvars:
+            return self.store.view(v, self.QW)
+        return self.store.view(v)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, training=None):
+        st = self.store
+        training = self.train if training is None else training
+        if self.aq_ops:
+            ops.minmax_reset(self.aq_slots)
+        if self.wq is not None:
+            with self.timed('weight_quant'):
+                self.wq.forward()
+        for op in self.ops:
+            ty = op.type
+            if ty in ('Placeholder', 'Reshape', 'Identity'):
+                continue
+            if ty in ('Conv2D', 'MatMul'):
+                bias = st.view(op.vars['bias']) if 'bias' in op.vars else None
+                with self.timed('conv_fwd'):
+                    ops.conv2d_fwd(self.desc[op], self.T(op.inputs[0]), self.kernel_of(op), bias,
+                                   op in self.fused_act, self.buf[op.output])
+            elif ty == 'FusedBatchNorm':
+                x, y = self.T(op.inputs[0]), self.buf[op.output]
+                c = y.shape[-1]
+                m = y.numel() // c
+                b = self.bn[op]
+                gamma, beta = st.view(op.vars['gamma']), st.view(op.vars['beta'])
+                mm, mv = st.view(op.vars['moving_mean']), st.view(op.vars['moving_variance'])
+                act = self.fused_act.get(op, 0)
+                relu_op = self._consumers(op.output)[0] if act else None
+                slot = self.aq_slots[self.aq_index[relu_op]] if relu_op in self.aq_index else None
+                with self.timed('bn_fwd'):
+                    if op.attrs['training'] and training:
+                        ops.bn_train_stats(x, m, c, op.attrs['epsilon'], op.attrs['momentum'], b['mean'], b['var'],
+                                           b['rstd'], mm, mv, self.bn_ws)
+                        ops.bn_apply(x, m, c, b['mean'], b['rstd'], gamma, beta, act, y, slot)
+                    else:
+                        ops.bn_eval_prepare(mv, c, op.attrs['epsilon'], b['rstd'])
+                        ops.bn_apply(x, m, c, mm, b['rstd'], gamma, beta, act, y, slot)
+                if slot is not None:
+                    with self.timed('act_quant'):
+                        ops.act_quant(y, y, slot, self.act_quant['bits'][self.aq_index[relu_op]])
+            elif ty in ACT_TYPES:
+                src = self.fused_into[op]
+                if op in self.aq_index and src.type != 'FusedBatchNorm':
+                    y = self.buf[src.output]
+                    slot = self.aq_slots[self.aq_index[op]]
+                    with self.timed('act_quant'):
+                        ops.act_minmax(y, slot)
+                        ops.act_quant(y, self.aq_out[op], slot, self.act_quant['bits'][self.aq_index[op]])
+            elif ty == 'MaxPool':
+                ops.maxpool_fwd(self.desc[op], self.T(op.inputs[0]), self.buf[op.output])
+            elif ty == 'Mean':
+                x = op.inputs[0]
+                n, h, w, c = x.shape
+                ops.global_avgpool_fwd(self.T(x), n, h * w, c, self.buf[op.output])
+            elif ty == 'Add':
+                ops.add(self.T(op.inputs[0]), self.T(op.inputs[1]), self.buf[op.output])
+            elif ty == 'Softmax':
+                ops.softmax_fwd(self.T(op.inputs[0]), self.buf[op.output])
+            else:
+                raise NotImplementedError('op type %s' % ty)
+        return self.T(self.logits_t)
+
+    # ------------------------------------------------------------------ loss + backward
+    def loss_and_backward(self):
+        st = self.store
+        L = self.loss
+        self._gwritten = set()
+        labels = self.T(self.labels_t)
+        ce_logits = L.ce[1]
+        teacher_logits, w_dst, T_dst = None, 0.0, 1.0
+        if L.dst is not None:
+            teacher_logits = self.teacher.T(self.teacher.logits_t)
+            w_dst, T_dst = L.dst[2], L.dst[3]
+        gl, _ = self.grad_target(ce_logits)
+        ops.softmax_ce(self.T(ce_logits), labels, teacher_logits, T_dst, w_dst, gl.view(ce_logits.shape),
+                       self.loss_out[:4], self.row_ws)
+        for op in reversed(self.ops):
+            ty = op.type
+            if ty == 'Placeholder':
+                continue
+            gy = self.grad_of(op.output)
+            if gy is None:
+                continue
+            if ty in ('Reshape', 'Identity') or op in self.fused_into:
+                continue                                   # gradient buffer is shared with the input
+            if ty in ('Conv2D', 'MatMul'):
+                d = self.desc[op]
+                x_t = op.inputs[0]
+                y = self.buf[op.output]
+                m, k = y.numel() // y.shape[-1], y.shape[-1]
+                if op in self.fused_act:
+                    dz = self.relu_scratch[op]
+                    ops.relu_bwd(gy, y, dz, self.fused_act[op])
+                    gy = dz
+                if 'bias' in op.vars:
+                    ops.colsum(gy, m, k, st.view(op.vars['bias'], self.G))
+                with self.timed('conv_wgrad'):
+                    ops.conv2d_wgrad(d, self.T(x_t), gy, self.wgrad_ws, st.view(op.vars['kernel'], self.G))
+                if x_t.op.type != 'Placeholder':
+                    gx, acc = self.grad_target(x_t)
+                    with self.timed('conv_dgrad'):
+                        ops.conv2d_dgrad(d, gy, self.kernel_of(op), self.wt_ws, acc, gx)
+            elif ty == 'FusedBatchNorm':
+                x_t = op.inputs[0]
+                y = self.buf[op.output]
+                c = y.shape[-1]
+                m = y.numel() // c
+                b = self.bn[op]
+                gx, acc = self.grad_target(x_t)
+                with self.timed('bn_bwd'):
+                    ops.bn_bwd(gy, self.T(x_t), m, c, b['mean'], b['rstd'], st.view(op.vars['gamma']),
+                               st.view(op.vars['beta']), self.fused_act.get(op, 0),
+                               st.view(op.vars['gamma'], self.G), st.view(op.vars['beta'], self.G), gx, acc,
+                               self.bn_ws)
+            elif ty == 'MaxPool':
+                x_t = op.inputs[0]
+                gx, acc = self.grad_target(x_t)
+                ops.maxpool_bwd(self.desc[op], gy, self.T(x_t), self.buf[op.output], gx, acc)
+            elif ty == 'Mean':
+                x_t = op.inputs[0]
+                n, h, w, c = x_t.shape
+                gx, acc = self.grad_target(x_t)
+                ops.global_avgpool_bwd(gy, n, h * w, c, gx, acc)
+            elif ty == 'Add':
+                for x_t in op.inputs:
+                    gx, acc = self.grad_target(x_t)
+                    ops.add(gy, None, gx, acc)
+            elif ty == 'Softmax':
+                x_t = op.inputs[0]
+                gx, acc = self.grad_target(x_t)
+                assert not acc
+                ops.softmax_bwd(gy, self.buf[op.output], gx)
+            else:
+                raise NotImplementedError('backward of %s' % ty)
+        if self._ste_grads is not None:
+            self.wq.ste_backward_(self._ste_grads)
+
+    def forward_eval_loss(self):
+        """Evaluation pass: BN in inference mode, quantizers active, losses/metrics only."""
+        if self.teacher is not None:
+            self.teacher.forward()
+        self.forward(training=False)
+        L = self.loss
+        teacher_logits, w_dst, T_dst = None, 0.0, 1.0
+        if L.dst is not None:
+            teacher_logits = self.teacher.T(self.teacher.logits_t)
+            w_dst, T_dst = L.dst[2], L.dst[3]
+        scratch = self.gbuf[self.gkey(L.ce[1])]
+        ops.softmax_ce(self.T(L.ce[1]), self.T(self.labels_t), teacher_logits, T_dst, w_dst,
+                       scratch.view(L.ce[1].shape), self.loss_out[:4], self.row_ws)
+        self.l2_value()
+
+    def l2_value(self):
+        first = True
+        for (s, e, masked, wd) in self.store.ranges:
+            if wd != 0.0:
+                ops.l2_loss(self.store.P[s:e], wd, self.l2_out, self.l2_ws, accumulate=not first)
+                first = False
+        if first:
+            self.l2_out.zero_()
+
+    def apply_gradients(self):
+        st, o = self.store, self.optimizer
+        for (s, e, masked, wd) in st.ranges:
+            if e <= s:
+                continue
+            if o['kind'] == 'momentum':
+                mask = self.MASK[s:e] if (masked and self.MASK is not None) else None
+                ops.momentum_step(st.P[s:e], self.S1[s:e], self.G[s:e], mask, self.hp, o.get('momentum', 0.9), wd,
+                                  self.grad_scale)
+            else:
+                ops.adam_step(st.P[s:e], self.S1[s:e], self.S2[s:e], self.G[s:e], self.hp, o.get('beta1', 0.9),
+                              o.get('beta2', 0.999), o.get('eps', 1e-8), wd, self.grad_scale)
+
+    # ------------------------------------------------------------------ one training step
+    def device_step(self, allreduce=None):
+        """Everything that runs on the GPU for one step (CUDA-graph capturable)."""
+        if self.teacher is not None:
+            self.teacher.forward()
+        self.forward()
+        self.loss_and_backward()
+        if allreduce is not None:
+            with self.timed('allreduce'):
+                allreduce(self.G)
+        with self.timed('optimizer'):
+            self.l2_value()
+            self.apply_gradients()
+
+    def set_hyper(self, lr):
+        self.hp_host[0] = float(lr)
+        self.hp_host[1] = float(self.beta1_power)
+        self.hp_host[2] = float(self.beta2_power)
+        self.hp.copy_(self.hp_host, non_blocking=True)
+
+    def advance_optimizer_state(self):
+        if self.optimizer.get('kind') == 'adam':
+            self.beta1_power = F32(self.beta1_power * F32(self.optimizer.get('beta1', 0.9)))
+            self.beta2_power = F32(self.beta2_power * F32(self.optimizer.get('beta2', 0.999)))
+        self.step_count += 1
+
+    def reset_optimizer_slots(self):
+        """tf.variables_initializer(optimizer.variables()) — run after every mask update
+        (weight_sparsification/learner.py:128,217)."""
+        self.S1.zero_()
+        if self.S2 is not None:
+            self.S2.zero_()
+
+    def capture(self, allreduce=None):
+        """Capture device_step into a CUDA graph (after one eager warm-up on a side stream)."""
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self.device_step(allreduce)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self.device_step(allreduce)
+        return self._graph
+
+    def run_step(self, lr, allreduce=None):
+        self.set_hyper(lr)
+        if self._graph is not None:
+            self._graph.replay()
+        else:
+            self.device_step(allreduce)
+        self.advance_optimizer_state()
+
+    def fetch_losses(self):
+        """(hard CE, distillation, l2, total, top1, top5) of the last step — one small D2H read."""
+        o = torch.cat([self.loss_out[:4], self.l2_out[:1]]).cpu().numpy()
+        hard, dst, top1, top5, l2 = [F32(x) for x in o]
+        total = F32(F32(hard + l2) + dst)
+        return dict(model_loss=F32(hard + l2), dst_loss=dst, l2=l2, ce=hard, loss=total, acc_top1=top1,
+                    acc_top5=top5)

@@ -1,0 +1,138 @@
+"""Abstract class for learners — the plugin surface of the reference
+(/root/reference/learners/abstract_learner.py:32-158), without TensorFlow."""
+from abc import ABC
+from abc import abstractmethod
+import glob
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import torch
+
+from ..flags import FLAGS, DEFINE_string, DEFINE_integer, DEFINE_boolean
+from ..utils.misc_utils import auto_barrier as auto_barrier_impl
+from ..utils.misc_utils import is_primary_worker as is_primary_worker_impl
+from ..utils.multi_gpu_wrapper import MultiGpuWrapper as mgw
+
+DEFINE_string('model_http_url', None, 'HTTP/HTTPS url for remote model files')
+DEFINE_integer('summ_step', 100, 'summarizaton step size')
+DEFINE_integer('save_step', 10000, 'model saving step size')
+DEFINE_string('save_path', './models/model.ckpt', 'model\'s save path')
+DEFINE_string('save_path_eval', './models_eval/model.ckpt', 'model\'s save path for evaluation')
+DEFINE_boolean('enbl_dst', False, 'enable the distillation loss for training')
+DEFINE_boolean('enbl_warm_start', False, 'enable warm start for training')
+
+
+def latest_checkpoint(ckpt_dir):
+    """tf.train.latest_checkpoint for the .npz checkpoints this build writes."""
+    files = sorted(glob.glob(os.path.join(ckpt_dir, '*.npz')), key=os.path.getmtime)
+    return files[-1] if files else None
+
+
+def save_checkpoint(path, state, step=None):
+    os.makedirs(os.path.dirname(path) or '.', exist_ok=True)
+    fn = path + ('-%d' % step if step is not None else '') + '.npz'
+    np.savez(fn, **{k.replace('/', '|'): v for k, v in state.items()})
+    return fn
+
+
+def load_checkpoint(fn):
+    d = np.load(fn)
+    return {k.replace('|', '/'): d[k] for k in d.files}
+
+
+class AbstractLearner(ABC):  # pylint: disable=too-many-instance-attributes
+    """A learner takes a ModelHelper (data pipeline + model definition) and performs training or
+    evaluation with its specific algorithm (abstract_learner.py:41-54)."""
+
+    def __init__(self, sm_writer, model_helper):
+        self.sm_writer = sm_writer
+        self.data_scope = 'data'
+        self.model_scope = 'model'
+
+        # one process per GPU; torch.distributed replaces Horovod + mpi4py (abstract_learner.py:68-74)
+        if FLAGS.enbl_multi_gpu:
+            mgw.init()
+            self.mpi_comm = mgw
+        else:
+            self.mpi_comm = None
+        if torch.cuda.is_available():
+            self.device = torch.device('cuda', mgw.local_rank() if FLAGS.enbl_multi_gpu else 0)
+            torch.cuda.set_device(self.device)
+        else:
+            self.device = torch.device('cpu')
+
+        self.build_dataset_train = model_helper.build_dataset_train
+        self.build_dataset_eval = model_helper.build_dataset_eval
+        self.forward_train = model_helper.forward_train
+        self.forward_eval = model_helper.forward_eval
+        self.calc_loss = model_helper.calc_loss
+        self.setup_lrn_rate = model_helper.setup_lrn_rate
+        self.warm_start = model_helper.warm_start
+        self.dump_n_eval = model_helper.dump_n_eval
+        self.model_name = model_helper.model_name
+        self.dataset_name = model_helper.dataset_name
+        self.forward_w_labels = model_helper.forward_w_labels
+
+        self.ckpt_file = 'models_%s_at_%s.tar.gz' % (self.model_name, self.dataset_name)
+        self.graph_train = None
+
+    @abstractmethod
+    def train(self):
+        """Train a model and periodically produce checkpoint files."""
+
+    @abstractmethod
+    def evaluate(self):
+        """Restore a model from the latest checkpoint files and then evaluate it."""
+
+    def download_model(self):
+        """Download remote model files and then uncompress (abstract_learner.py:105-125)."""
+        if latest_checkpoint(os.path.dirname(FLAGS.save_path)) is not None:
+            return
+        if FLAGS.model_http_url is None:
+            raise ValueError('local model files do not exist and <model_http_url> is not set')
+        subprocess.call(['wget', os.path.join(FLAGS.model_http_url, self.ckpt_file)])
+        if os.path.exists(self.ckpt_file):
+            if os.path.isdir(os.path.dirname(FLAGS.save_path)):
+                shutil.rmtree(os.path.dirname(FLAGS.save_path))
+            subprocess.call(['tar', '-xvf', self.ckpt_file])
+        else:
+            raise FileNotFoundError(
+                'pre-trained model not avaialable: {} / {}'.format(self.model_name, self.dataset_name))
+
+    def auto_barrier(self):
+        auto_barrier_impl(self.mpi_comm)
+
+    @classmethod
+    def is_primary_worker(cls, scope='global'):
+        return is_primary_worker_impl(scope)
+
+    @property
+    def vars(self):
+        """List of all global variables of the model scope."""
+        return [v for v in self.graph_train.variables.values() if v.name.startswith(self.model_scope + '/')]
+
+    @property
+    def trainable_vars(self):
+        return [v for v in self.vars if v.trainable]
+
+    @property
+    def update_ops(self):
+        """BN moving-statistic updates: fused into the BN statistics kernel here."""
+        return []
+
+    # ------------------------------------------------------------------ shared step plumbing
+    def feed(self, executor, iterator):
+        """Host -> device copy of the next mini-batch from pinned memory (the only per-step H2D)."""
+        images, labels = iterator.next_batch()
+        executor.buf[iterator.images].copy_(images, non_blocking=True)
+        executor.buf[iterator.labels].copy_(labels, non_blocking=True)
+        return images.numel() * 4 + labels.numel() * 4
+
+    def grad_allreduce(self):
+        """The one collective of the data-parallel step (replaces DistributedOptimizer,
+        utils/multi_gpu_wrapper.py:82-89)."""
+        if FLAGS.enbl_multi_gpu and mgw.size() > 1:
+            return mgw.allreduce_flat_
+        return None

@@ -1,0 +1,137 @@
+"""Non-Uniform Quantization Learner (/root/reference/learners/nonuniform_quantization/learner.py:33-520),
+'weights' optimisation mode: a 2^b-entry codebook per layer, quantile-initialised AFTER the weights
+are in place (learner.py:127-129), frozen; weights trained with Adam through the STE."""
+from timeit import default_timer as timer
+
+import numpy as np
+
+from ... import graph as G
+from ...engine import Executor
+from ...flags import FLAGS, DEFINE_integer, DEFINE_boolean, DEFINE_string
+from ...utils.multi_gpu_wrapper import MultiGpuWrapper as mgw
+from ...utils.lrn_rate_utils import piecewise_constant
+from ..abstract_learner import AbstractLearner, save_checkpoint
+from ..distillation_helper import DistillationHelper
+from .utils import NonUniformQuantization
+
+DEFINE_string('nuql_opt_mode', 'weights', 'the variables to optimize: [clusters, weights, both]')
+DEFINE_string('nuql_init_style', 'quantile', 'the initialization of quantization points: [quantile, uniform]')
+DEFINE_integer('nuql_weight_bits', 4, 'Number of bits to use for quantizing weights')
+DEFINE_integer('nuql_activation_bits', 32, 'Number of bits to use for quantizing activations')
+DEFINE_boolean('nuql_use_buckets', False, 'Use bucketing or not')
+DEFINE_integer('nuql_bucket_size', 256, 'Number of bucket size')
+DEFINE_string('nuql_bucket_type', 'split', 'bucket type: [split, channel]')
+DEFINE_integer('nuql_quant_epochs', 60, 'To be determined by datasets')
+DEFINE_boolean('nuql_quantize_all_layers', False, 'If False, leaving first and last layers unquantized')
+DEFINE_boolean('nuql_enbl_rl_agent', False, 'enable the RL agent')
+DEFINE_string('nuql_save_quant_model_path', './nuql_quant_models/model.ckpt', 'dir to save quantization model')
+
+
+def setup_bnds_decay_rates(model_name, dataset_name):
+    """learner.py:52-73; the lenet crash is patched like in the uniform learner."""
+    batch_size = FLAGS.batch_size if not FLAGS.enbl_multi_gpu else FLAGS.batch_size * mgw.size()
+    nb_batches_per_epoch = int(FLAGS.nb_smpls_train / batch_size)
+    mgw_size = int(mgw.size()) if FLAGS.enbl_multi_gpu else 1
+    init_lr = FLAGS.lrn_rate_init * FLAGS.batch_size * mgw_size / FLAGS.batch_size_norm \
+        if FLAGS.enbl_multi_gpu else FLAGS.lrn_rate_init
+    if dataset_name == 'cifar_10':
+        bnds = [nb_batches_per_epoch * 15, nb_batches_per_epoch * 40]
+        decay_rates = [1e-3, 1e-4, 1e-5]
+    elif dataset_name == 'ilsvrc_12':
+        if model_name.startswith('resnet'):
+            bnds = [nb_batches_per_epoch * 5, nb_batches_per_epoch * 20]
+            decay_rates = [5e-4, 5e-5, 5e-6]
+        else:
+            bnds = [nb_batches_per_epoch * 5, nb_batches_per_epoch * 30]
+            decay_rates = [1e-4, 1e-5, 1e-6]
+    else:
+        raise ValueError('Unrecognized dataset name')
+    finetune_steps = nb_batches_per_epoch * FLAGS.nuql_quant_epochs
+    init_lr = init_lr if FLAGS.enbl_warm_start else FLAGS.lrn_rate_init
+    return init_lr, bnds, decay_rates, finetune_steps
+
+
+class NonUniformQuantLearner(AbstractLearner):
+    # pylint: disable=too-many-instance-attributes
+    def __init__(self, sm_writer, model_helper):
+        super(NonUniformQuantLearner, self).__init__(sm_writer, model_helper)
+        if FLAGS.nuql_opt_mode != 'weights':
+            raise NotImplementedError("nuql_opt_mode '%s' (codebook gradients) is a next-tier row; "
+                                      "'weights' is built" % FLAGS.nuql_opt_mode)
+        if FLAGS.enbl_dst:
+            self.helper_dst = DistillationHelper(sm_writer, model_helper, self.mpi_comm)
+        self.statistics = {}
+        self.__build_train()
+
+    def train(self, nb_iters=None):
+        total = self.finetune_steps if nb_iters is None else nb_iters
+        ex = self.sess_train
+        if FLAGS.enbl_multi_gpu:
+            mgw.broadcast_global_variables([ex.store.P, ex.store.O])
+        time_prev = timer()
+        for idx_iter in range(total):
+            self.train_step()
+            if (idx_iter + 1) % FLAGS.summ_step == 0 and self.is_primary_worker():
+                r = ex.fetch_losses()
+                speed = FLAGS.batch_size * FLAGS.summ_step / (timer() - time_prev) * (mgw.size() if FLAGS.enbl_multi_gpu else 1)
+                print('iter #%d: lr = %e | model_loss = %.4f | loss = %.4f | acc_top1 = %.4f | speed = %.2f pics / sec'
+                      % (idx_iter + 1, self.lrn_rate(idx_iter), r['model_loss'], r['loss'], r['acc_top1'], speed))
+                time_prev = timer()
+        if self.is_primary_worker():
+            print('quantized model saved to ' + save_checkpoint(FLAGS.nuql_save_quant_model_path,
+                                                                ex.store.state_dict(), ex.step_count))
+
+    def train_step(self):
+        ex = self.sess_train
+        self.h2d_bytes = self.feed(ex, self.iterator_train)
+        ex.run_step(self.lrn_rate(ex.step_count), self.grad_allreduce())
+
+    def evaluate(self, nb_iters=1):
+        ex = self.sess_train
+        out = []
+        for _ in range(nb_iters):
+            self.feed(ex, self.iterator_train)
+            ex.forward_eval_loss()
+            out.append(ex.fetch_losses()['loss'])
+        return float(np.mean(out))
+
+    def cluster_init(self):
+        """ops['cluster_init'] (learner.py:127-129, 297-298): run AFTER the weights are restored."""
+        self.sess_train.wq.quantile_init()
+
+    def __build_train(self):
+        self.graph_train = G.Graph()
+        with self.graph_train.as_default():
+            with G.variable_scope(self.data_scope):
+                self.iterator_train = self.build_dataset_train()
+                images, labels = self.iterator_train.get_next()
+            self.images, self.labels = images, labels
+            logits_dst = self.helper_dst.calc_logits(None, images) if FLAGS.enbl_dst else None
+            with G.variable_scope(self.model_scope):
+                logits = self.forward_train(images)
+                self.weights = [v for v in self.trainable_vars if 'kernel' in v.name or 'weight' in v.name]
+                if not FLAGS.nuql_quantize_all_layers:
+                    self.weights = self.weights[1:-1]
+                self.statistics['num_weights'] = [v.numel for v in self.weights]
+                nq = NonUniformQuantization(self.graph_train, FLAGS.nuql_bucket_size, FLAGS.nuql_use_buckets,
+                                            FLAGS.nuql_init_style, FLAGS.nuql_bucket_type)
+                matmul_ops = nq.search_matmul_op(FLAGS.nuql_quantize_all_layers)
+                act_ops = nq.search_activation_op()
+                nq.insert_quant_op_for_weights({op.name: FLAGS.nuql_weight_bits for op in matmul_ops})
+                nq.insert_quant_op_for_activations({op.name: FLAGS.nuql_activation_bits for op in act_ops})
+                loss, metrics = self.calc_loss(labels, logits, self.trainable_vars)
+                if FLAGS.enbl_dst:
+                    loss += self.helper_dst.calc_loss(logits, logits_dst)
+        init_lr, bnds, decay_rates, self.finetune_steps = setup_bnds_decay_rates(self.model_name, self.dataset_name)
+        self.lrn_rate = piecewise_constant(list(bnds), [init_lr * d for d in decay_rates])
+        world = mgw.size() if FLAGS.enbl_multi_gpu else 1
+        teacher = None
+        if FLAGS.enbl_dst:
+            teacher = Executor(self.graph_train, images, logits_dst, self.device, train=False, seed=2)
+            self.helper_dst.restore(teacher.store)
+        self.sess_train = Executor(self.graph_train, images, logits, self.device, train=True, loss=loss, labels=labels,
+                                   optimizer=dict(kind='adam'), weight_quant=nq.weight_quant_spec(),
+                                   act_quant=nq.act_quant_spec(), teacher=teacher, seed=1, grad_scale=1.0 / world)
+        if teacher is not None:
+            teacher.buf[images] = self.sess_train.buf[images]
+        self.cluster_init()

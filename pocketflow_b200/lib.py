@@ -20,9 +20,11 @@ SIGNATURES = {
     'pf_launch_count_reset': (None, []),
     'pf_sm_count': (c_i32, [ctypes.POINTER(c_i32)]),
     'pf_fill_u32': (c_i32, [c_vp, c_i64, ctypes.c_uint32, c_vp]),
+    'pf_minmax_reset': (c_i32, [c_vp, c_i64, c_vp]),
     'pf_uq_weight_minmax': (c_i32, [c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]),
-    'pf_uq_weight_quant': (c_i32, [c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]),
-    'pf_uq_weight_ste_bwd': (c_i32, [c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]),
+    'pf_uq_weight_scales': (c_i32, [c_vp, c_vp, c_i32, c_vp, c_vp]),
+    'pf_uq_weight_quant': (c_i32, [c_vp, c_vp, c_i32, c_vp, c_i32, c_vp]),
+    'pf_uq_weight_ste_bwd': (c_i32, [c_vp, c_vp, c_i32, c_vp, c_i32, c_vp]),
     'pf_uq_act_minmax': (c_i32, [c_vp, c_i64, c_vp, c_vp]),
     'pf_uq_act_quant': (c_i32, [c_vp, c_vp, c_i64, c_vp, c_i32, c_vp]),
     'pf_ws_mask_build': (c_i32, [c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
@@ -31,8 +33,32 @@ SIGNATURES = {
     'pf_adam_step': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_f32, c_f32, c_f32, c_f32, c_f32, c_vp]),
     'pf_softmax_ce_fwd_bwd': (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_f32, c_f32, c_vp, c_vp, c_vp, c_vp]),
     'pf_l2_loss': (c_i32, [c_vp, c_i64, c_f32, c_i32, c_vp, c_vp, c_vp]),
-    'pf_nuq_weight_quant': (c_i32, [c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'pf_nuq_weight_quant': (c_i32, [c_vp, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    'pf_conv2d_fwd': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
+    'pf_conv2d_dgrad': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
+    'pf_conv2d_wgrad_workspace_bytes': (c_i64, [c_vp]),
+    'pf_conv2d_wgrad': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'pf_bn_train_stats': (c_i32, [c_vp, c_i64, c_i32, c_f32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'pf_bn_eval_prepare': (c_i32, [c_vp, c_i32, c_f32, c_vp, c_vp]),
+    'pf_bn_apply': (c_i32, [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]),
+    'pf_bn_bwd': (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_i32,
+                          c_vp, c_vp]),
+    'pf_add': (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp]),
+    'pf_relu_bwd': (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp]),
+    'pf_colsum': (c_i32, [c_vp, c_i64, c_i32, c_vp, c_vp]),
+    'pf_maxpool_fwd': (c_i32, [c_vp, c_vp, c_vp, c_vp]),
+    'pf_maxpool_bwd': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
+    'pf_global_avgpool_fwd': (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    'pf_global_avgpool_bwd': (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    'pf_softmax_fwd': (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp]),
+    'pf_softmax_bwd': (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
 }
+
+
+class ConvDesc(ctypes.Structure):
+    """pf_conv_desc (host struct)."""
+    _fields_ = [(n, c_i32) for n in ('n', 'h', 'w', 'c', 'k', 'r', 's', 'p', 'q',
+                                     'stride_h', 'stride_w', 'pad_t', 'pad_l')]
 
 _lib = None
 

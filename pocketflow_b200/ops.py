@@ -154,6 +154,7 @@ class UniformWeightQuantizer:
         self.bucket_counts = [int(s['ncols']) for s in segs]
         self.mn = torch.empty(self.n_buckets, dtype=torch.int32, device=self.device)
         self.mx = torch.empty(self.n_buckets, dtype=torch.int32, device=self.device)
+        self.scales = torch.empty(3 * self.n_buckets, dtype=torch.float32, device=self.device)
         self.work_mm = minmax_works(segs)
         self.work_q = flat_works([int(s['numel']) for s in segs])
         self.work_mm_dev = _upload(self.work_mm, self.device)
@@ -181,10 +182,12 @@ class UniformWeightQuantizer:
         self.reset_ranges()
         _lib.check(self.L.pf_uq_weight_minmax(_p(self.segs_dev), _p(self.work_mm_dev), len(self.work_mm),
                                               _p(self.mn), _p(self.mx), _stream()), 'pf_uq_weight_minmax')
+        _lib.check(self.L.pf_uq_weight_scales(_p(self.mn), _p(self.mx), self.n_buckets, _p(self.scales), _stream()),
+                   'pf_uq_weight_scales')
 
     def quantize(self):
         _lib.check(self.L.pf_uq_weight_quant(_p(self.segs_dev), _p(self.work_q_dev), len(self.work_q),
-                                             _p(self.mn), _p(self.mx), _stream()), 'pf_uq_weight_quant')
+                                             _p(self.scales), self.n_buckets, _stream()), 'pf_uq_weight_quant')
 
     def forward(self):
         if not self.srcs:
@@ -202,7 +205,7 @@ class UniformWeightQuantizer:
             self.grad_segs_dev = _upload(gs, self.device)
             self._grad_ptrs = [g.data_ptr() for g in grads]
         _lib.check(self.L.pf_uq_weight_ste_bwd(_p(self.grad_segs_dev), _p(self.work_q_dev), len(self.work_q),
-                                               _p(self.mn), _p(self.mx), _stream()), 'pf_uq_weight_ste_bwd')
+                                               _p(self.scales), self.n_buckets, _stream()), 'pf_uq_weight_ste_bwd')
 
     def ranges(self):
         """Per tensor (min, max) arrays decoded from the slots (host copy; tests/diagnostics)."""
@@ -405,6 +408,97 @@ class CodebookWeightQuantizer:
     def forward(self):
         self.uq.minmax()
         _lib.check(self.L.pf_nuq_weight_quant(_p(self.uq.segs_dev), _p(self.uq.work_q_dev), len(self.uq.work_q),
-                                              _p(self.uq.mn), _p(self.uq.mx), _p(self.clusters),
+                                              _p(self.uq.scales), self.uq.n_buckets, _p(self.clusters),
                                               _p(self.idx), _p(self.idx_base) if self.idx is not None else None,
                                               _stream()), 'pf_nuq_weight_quant')
+
+
+# ----------------------------------------------------------------------------- a4 conv / a13 layers
+BN_MAX_SPLITS = 1024
+
+
+def conv_desc(n, h, w, c, k, r, s, p, q, sh, sw, pt, pl):
+    return _lib.ConvDesc(n, h, w, c, k, r, s, p, q, sh, sw, pt, pl)
+
+
+def conv2d_fwd(d, x, w, bias, relu, y):
+    _lib.check(_lib.load().pf_conv2d_fwd(ctypes.byref(d), _p(x), _p(w), _p(bias), int(bool(relu)), _p(y), _stream()),
+               'pf_conv2d_fwd')
+
+
+def conv2d_dgrad(d, dy, w, wt_ws, accumulate, dx):
+    _lib.check(_lib.load().pf_conv2d_dgrad(ctypes.byref(d), _p(dy), _p(w), _p(wt_ws), int(bool(accumulate)), _p(dx),
+                                           _stream()), 'pf_conv2d_dgrad')
+
+
+def conv2d_wgrad_workspace_floats(d):
+    return int(_lib.load().pf_conv2d_wgrad_workspace_bytes(ctypes.byref(d))) // 4
+
+
+def conv2d_wgrad(d, x, dy, ws, dw):
+    _lib.check(_lib.load().pf_conv2d_wgrad(ctypes.byref(d), _p(x), _p(dy), _p(ws), _p(dw), _stream()),
+               'pf_conv2d_wgrad')
+
+
+def bn_train_stats(x, m, c, eps, momentum, mean, var, rstd, mov_mean, mov_var, ws):
+    _lib.check(_lib.load().pf_bn_train_stats(_p(x), m, c, float(eps), float(momentum), _p(mean), _p(var), _p(rstd),
+                                             _p(mov_mean), _p(mov_var), _p(ws), _stream()), 'pf_bn_train_stats')
+
+
+def bn_eval_prepare(mov_var, c, eps, rstd):
+    _lib.check(_lib.load().pf_bn_eval_prepare(_p(mov_var), c, float(eps), _p(rstd), _stream()), 'pf_bn_eval_prepare')
+
+
+def bn_apply(x, m, c, mean, rstd, gamma, beta, act, y, minmax=None):
+    _lib.check(_lib.load().pf_bn_apply(_p(x), m, c, _p(mean), _p(rstd), _p(gamma), _p(beta), int(act), _p(y),
+                                       _p(minmax), _stream()), 'pf_bn_apply')
+
+
+def bn_bwd(dy, x, m, c, mean, rstd, gamma, beta, act, dgamma, dbeta, dx, accumulate, ws):
+    _lib.check(_lib.load().pf_bn_bwd(_p(dy), _p(x), m, c, _p(mean), _p(rstd), _p(gamma), _p(beta), int(act),
+                                     _p(dgamma), _p(dbeta), _p(dx), int(bool(accumulate)), _p(ws), _stream()),
+               'pf_bn_bwd')
+
+
+def add(a, b, out, accumulate=False):
+    _lib.check(_lib.load().pf_add(_p(a), _p(b), a.numel(), int(bool(accumulate)), _p(out), _stream()), 'pf_add')
+
+
+def relu_bwd(dy, y, dx, act=1, accumulate=False):
+    _lib.check(_lib.load().pf_relu_bwd(_p(dy), _p(y), y.numel(), int(act), int(bool(accumulate)), _p(dx), _stream()),
+               'pf_relu_bwd')
+
+
+def colsum(a, m, c, out):
+    _lib.check(_lib.load().pf_colsum(_p(a), m, c, _p(out), _stream()), 'pf_colsum')
+
+
+def maxpool_fwd(d, x, y):
+    _lib.check(_lib.load().pf_maxpool_fwd(ctypes.byref(d), _p(x), _p(y), _stream()), 'pf_maxpool_fwd')
+
+
+def maxpool_bwd(d, dy, x, y, dx, accumulate=False):
+    _lib.check(_lib.load().pf_maxpool_bwd(ctypes.byref(d), _p(dy), _p(x), _p(y), int(bool(accumulate)), _p(dx),
+                                          _stream()), 'pf_maxpool_bwd')
+
+
+def global_avgpool_fwd(x, n, hw, c, y):
+    _lib.check(_lib.load().pf_global_avgpool_fwd(_p(x), n, hw, c, _p(y), _stream()), 'pf_global_avgpool_fwd')
+
+
+def global_avgpool_bwd(dy, n, hw, c, dx, accumulate=False):
+    _lib.check(_lib.load().pf_global_avgpool_bwd(_p(dy), n, hw, c, int(bool(accumulate)), _p(dx), _stream()),
+               'pf_global_avgpool_bwd')
+
+
+def softmax_fwd(x, y):
+    _lib.check(_lib.load().pf_softmax_fwd(_p(x), x.shape[0], x.shape[1], _p(y), _stream()), 'pf_softmax_fwd')
+
+
+def softmax_bwd(dy, y, dx):
+    _lib.check(_lib.load().pf_softmax_bwd(_p(dy), _p(y), y.shape[0], y.shape[1], _p(dx), _stream()), 'pf_softmax_bwd')
+
+
+def minmax_reset(slots):
+    """slots: int32 [n, 2] -> every pair = (0xFFFFFFFF, 0)."""
+    _lib.check(_lib.load().pf_minmax_reset(_p(slots), slots.numel() // 2, _stream()), 'pf_minmax_reset')

@@ -50,7 +50,7 @@ def test_argument_errors_map_to_valueerror():
     assert b'n < 0' in L.pf_last_error()
     assert L.pf_uq_act_quant(None, None, 16, None, 0, None) == -1       # bits out of range
     assert L.pf_softmax_ce_fwd_bwd(None, None, None, 0, 10, 4.0, 4.0, None, None, None, None) == -1
-    assert L.pf_uq_weight_quant(None, None, 0, None, None, None) == 0   # empty work = no-op
+    assert L.pf_uq_weight_quant(None, None, 0, None, 0, None) == 0         # empty work = no-op
     assert L.pf_momentum_step(None, None, None, None, 0, None, 0.9, 0.0, 1.0, None) == 0
     with pytest.raises(RuntimeError):
         lib.check(700, 'x')

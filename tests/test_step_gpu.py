@@ -1,0 +1,184 @@
+"""Full-step parity: the learner-level CUDA step against the CPU oracle step (oracle/step_oracle.py)
+from identical state on the same batch.  Bar (north star): per-step losses and updated weights
+within 1e-5 relative fp32; quantized weights bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.step_oracle import StepOracle
+from oracle import pf_oracle as O
+from pocketflow_b200.flags import FLAGS
+
+pytestmark = pytest.mark.gpu
+F32 = np.float32
+
+
+def rel(a, b):
+    return abs(float(a) - float(b)) / max(abs(float(b)), 1e-30)
+
+
+def make_uq_learner(resnet_size=8, batch=16, w_bits=8, a_bits=8, dst=True, buckets=True):
+    FLAGS.reset()
+    from pocketflow_b200.nets import resnet_at_cifar10 as R
+    from pocketflow_b200.learners.uniform_quantization.learner import UniformQuantLearner
+    FLAGS.resnet_size, FLAGS.batch_size = resnet_size, batch
+    FLAGS.uql_weight_bits, FLAGS.uql_activation_bits = w_bits, a_bits
+    FLAGS.uql_use_buckets, FLAGS.uql_bucket_type = buckets, 'channel'
+    FLAGS.enbl_dst = dst
+    return UniformQuantLearner(None, R.ModelHelper())
+
+
+def oracle_for(learner):
+    ex = learner.sess_train
+    teacher = None
+    if ex.teacher is not None:
+        teacher = StepOracle(ex.teacher.ops, ex.teacher.logits_t, learner.images)
+    return StepOracle(ex.ops, ex.logits_t, learner.images, learner.labels, ex.loss,
+                      ex.weight_quant, ex.act_quant, teacher)
+
+
+def relu_mask_mismatches(ex, orc, state, img):
+    """# of ReLU outputs whose sign pattern differs between the CUDA forward and the oracle forward.
+    ReLU'(0) is a derivative discontinuity: one element whose pre-activation is within fp32
+    summation-order noise (1e-7) of zero flips the mask and moves every upstream gradient by ~1e-2 of
+    its max-norm, so gradient parity is only meaningful on batches where no such element exists."""
+    params = {k: torch.from_numpy(v.copy()) for k, v in state.items()}
+    val = orc.forward(params, torch.from_numpy(img), True)
+    bad = 0
+    for op in ex.ops:
+        if op.type in ('Relu', 'Relu6'):
+            a = ex.T(op.output).cpu().numpy() > 0
+            b = val[op.output.name].numpy() > 0
+            bad += int((a != b).sum())
+    return bad
+
+
+@pytest.mark.parametrize('dst,buckets', [(True, True), (False, False)])
+def test_uq_step_matches_oracle(dst, buckets):
+    """W8 (per-channel / per-layer), activations at the reference's default 32 bits (the quantizer
+    chain still runs): losses within 1e-5, quantized weights bit-exact, gradients and
+    updated weights within 1e-4 / 1e-5 from identical state."""
+    lrn = make_uq_learner(dst=dst, buckets=buckets, a_bits=32)
+    ex = lrn.sess_train
+    orc = oracle_for(lrn)
+    state = ex.store.state_dict()
+    tstate = ex.teacher.store.state_dict() if ex.teacher is not None else None
+    opt = dict(kind='adam', slots={})
+    b1p, b2p = F32(0.9), F32(0.999)
+    checked = 0
+    for step in range(6):
+        images, labels = lrn.iterator_train.next_batch()
+        img, lab = images.numpy().copy(), labels.numpy().copy()
+        ex.buf[lrn.images].copy_(images)
+        ex.buf[lrn.labels].copy_(labels)
+        lr = lrn.lrn_rate(step)
+        ex.run_step(lr)
+        got = ex.fetch_losses()
+        flips = relu_mask_mismatches(ex, orc, state, img)
+        ref, new_state, grads = orc.step(state, img, lab, opt, lr, teacher_state=tstate, beta_powers=(b1p, b2p))
+        b1p, b2p = F32(b1p * F32(0.9)), F32(b2p * F32(0.999))
+        for op, bits in zip(ex.wq_ops, ex.weight_quant['bits']):
+            v = op.vars['kernel']
+            qref = O.uniform_quantize(state[v.name], bits, use_buckets=buckets, bucket_type='channel')
+            assert np.array_equal(ex.store.view(v, ex.QW).cpu().numpy(), qref), v.name
+        for k in ('ce', 'l2', 'loss') + (('dst_loss',) if dst else ()):
+            assert rel(got[k], ref[k]) <= 1e-5, (step, k, got[k], ref[k])     # north-star tolerance
+        assert got['acc_top1'] == ref['acc_top1']
+        if flips == 0:
+            checked += 1
+            for v in ex.store.train_vars:
+                g_ref = grads[v.name]
+                err = np.abs(ex.store.view(v, ex.G).cpu().numpy() - g_ref).max() / (np.abs(g_ref).max() + 1e-12)
+                assert err <= 1e-4, (step, v.name, err)
+            # Adam's first steps move every weight by ~lr regardless of |g|: compare the UPDATE
+            for v in ex.store.train_vars:
+                d_gpu = ex.store.view(v).cpu().numpy() - state[v.name]
+                d_ref = new_state[v.name] - state[v.name]
+                assert np.abs(ex.store.view(v).cpu().numpy() - new_state[v.name]).max() <= \
+                    1e-5 * np.abs(new_state[v.name]).max() + 1e-9, v.name
+                del d_gpu, d_ref
+            for v in ex.store.other_vars:           # BN moving statistics
+                np.testing.assert_allclose(ex.store.view(v).cpu().numpy(), new_state[v.name], rtol=2e-5, atol=1e-7)
+        # step from the SAME state next time (state injected from the oracle, SURVEY §7 hard part 1)
+        ex.store.load_state_dict(new_state)
+        for v in ex.store.train_vars:
+            ex.store.view(v, ex.S1).copy_(torch.from_numpy(opt['slots'][v.name + '/m']))
+            ex.store.view(v, ex.S2).copy_(torch.from_numpy(opt['slots'][v.name + '/v']))
+        state = new_state
+        if checked >= 2:
+            break
+    assert checked >= 1, 'every batch had a ReLU element within fp32 noise of zero'
+
+
+def test_uq_w8a8_step_loss_parity():
+    """8-bit ACTIVATION quantization makes the loss itself discontinuous in the activations: a value
+    within 1e-7 of a rounding boundary lands on a different level (1/255 of the range) in any two
+    fp32 implementations.  Measured on this net at batch 16: ~6e-5 relative on the loss; the bar
+    here is 2e-4 (documented deviation from the 1e-5 that holds at the default 32-bit activations)."""
+    lrn = make_uq_learner(dst=True, buckets=True, a_bits=8)
+    ex = lrn.sess_train
+    orc = oracle_for(lrn)
+    state = ex.store.state_dict()
+    tstate = ex.teacher.store.state_dict()
+    images, labels = lrn.iterator_train.next_batch()
+    ex.buf[lrn.images].copy_(images)
+    ex.buf[lrn.labels].copy_(labels)
+    ex.run_step(lrn.lrn_rate(0))
+    got = ex.fetch_losses()
+    ref, _, _ = orc.step(state, images.numpy(), labels.numpy(), dict(kind='adam', slots={}), lrn.lrn_rate(0),
+                         teacher_state=tstate)
+    for k in ('ce', 'dst_loss', 'loss'):
+        assert rel(got[k], ref[k]) <= 2e-4, (k, got[k], ref[k])
+    assert rel(got['l2'], ref['l2']) <= 1e-6
+    for op, bits in zip(ex.wq_ops, ex.weight_quant['bits']):
+        v = op.vars['kernel']
+        assert np.array_equal(ex.store.view(v, ex.QW).cpu().numpy(),
+                              O.uniform_quantize(state[v.name], bits, use_buckets=True, bucket_type='channel'))
+
+
+def test_uq_step_cuda_graph_replay_matches_eager():
+    lrn = make_uq_learner(dst=True)
+    ex = lrn.sess_train
+    images, labels = lrn.iterator_train.next_batch()
+    ex.buf[lrn.images].copy_(images)
+    ex.buf[lrn.labels].copy_(labels)
+    P0, O0 = ex.store.P.clone(), ex.store.O.clone()
+    ex.run_step(1e-3)
+    eager = ex.fetch_losses()
+    P1 = ex.store.P.clone()
+    # rewind and replay through a captured graph
+    ex.store.P.copy_(P0); ex.store.O.copy_(O0); ex.S1.zero_(); ex.S2.zero_()
+    ex.beta1_power, ex.beta2_power = F32(0.9), F32(0.999)
+    ex.capture()
+    ex.store.P.copy_(P0); ex.store.O.copy_(O0); ex.S1.zero_(); ex.S2.zero_()
+    ex.run_step(1e-3)
+    replay = ex.fetch_losses()
+    assert replay['loss'] == eager['loss']
+    assert torch.equal(ex.store.P, P1)
+
+
+def test_lenet_uq_step_matches_oracle():
+    FLAGS.reset()
+    from pocketflow_b200.nets import lenet_at_cifar10 as Lnet
+    from pocketflow_b200.learners.uniform_quantization.learner import UniformQuantLearner
+    FLAGS.batch_size, FLAGS.uql_weight_bits, FLAGS.uql_activation_bits = 16, 8, 32
+    FLAGS.loss_w_dcy, FLAGS.lrn_rate_init = 5e-4, 1e-2
+    lrn = UniformQuantLearner(None, Lnet.ModelHelper())
+    ex = lrn.sess_train
+    assert [op.vars['kernel'].shape for op in ex.wq_ops] == [(5, 5, 32, 64), (1600, 256)]
+    orc = oracle_for(lrn)
+    state = ex.store.state_dict()
+    images, labels = lrn.iterator_train.next_batch()
+    ex.buf[lrn.images].copy_(images)
+    ex.buf[lrn.labels].copy_(labels)
+    ex.run_step(lrn.lrn_rate(0))
+    got = ex.fetch_losses()
+    ref, new_state, grads = orc.step(state, images.numpy(), labels.numpy(), dict(kind='adam', slots={}),
+                                     lrn.lrn_rate(0), beta_powers=(F32(0.9), F32(0.999)))
+    for k in ('ce', 'l2', 'loss'):
+        assert rel(got[k], ref[k]) <= 1e-5, (k, got[k], ref[k])
+    if relu_mask_mismatches(ex, orc, state, images.numpy()) == 0:
+        for v in ex.store.train_vars:
+            g_ref = grads[v.name]
+            err = np.abs(ex.store.view(v, ex.G).cpu().numpy() - g_ref).max() / (np.abs(g_ref).max() + 1e-12)
+            assert err <= 1e-4, (v.name, err)
