@@ -23,14 +23,16 @@ DEFINE_integer('buffer_size', 1024, '# of elements to be buffered when prefetchi
 DEFINE_integer('prefetch_size', 8, '# of mini-batches to be buffered when prefetching')
 
 
+POOL_SIZE = 8   # distinct synthetic mini-batches kept in pinned host memory
+
+
 class BatchIterator(object):
     def __init__(self, batch_size, image_shape, nb_classes, generator):
         self.batch_size, self.image_shape, self.nb_classes = batch_size, tuple(image_shape), nb_classes
         self.generator = generator
         self.images, self.labels = None, None
-        pin = torch.cuda.is_available()
-        self.host_images = torch.empty((batch_size,) + self.image_shape, dtype=torch.float32, pin_memory=pin)
-        self.host_labels = torch.empty((batch_size, nb_classes), dtype=torch.float32, pin_memory=pin)
+        self.pin = torch.cuda.is_available()
+        self.pool, self.pool_size, self.cursor = [], POOL_SIZE, 0
 
     def get_next(self):
         """Symbolic (images, labels) of the current default graph."""
@@ -40,11 +42,20 @@ class BatchIterator(object):
         return self.images, self.labels
 
     def next_batch(self):
-        """Fill the pinned host buffers with the next mini-batch and return them."""
-        img, lab = self.generator(self.batch_size)
-        self.host_images.copy_(torch.from_numpy(img))
-        self.host_labels.copy_(torch.from_numpy(lab))
-        return self.host_images, self.host_labels
+        """Next mini-batch as (images, labels) in pinned host memory.  The synthetic stream is a pool of
+        POOL_SIZE distinct pre-generated batches cycled in order (what tf.data's prefetch buffer holds
+        in the reference: decoding happens off the step's critical path, datasets/abstract_dataset.py:107)."""
+        if len(self.pool) < self.pool_size:
+            img, lab = self.generator(self.batch_size)
+            hi = torch.empty((self.batch_size,) + self.image_shape, dtype=torch.float32, pin_memory=self.pin)
+            hl = torch.empty((self.batch_size, self.nb_classes), dtype=torch.float32, pin_memory=self.pin)
+            hi.copy_(torch.from_numpy(img))
+            hl.copy_(torch.from_numpy(lab))
+            self.pool.append((hi, hl))
+            return hi, hl
+        out = self.pool[self.cursor % self.pool_size]
+        self.cursor += 1
+        return out
 
 
 class AbstractDataset(ABC):
