@@ -236,6 +236,34 @@ int pf_conv2d_wgrad(const pf_conv_desc* d, const float* x_dev, const float* dy_d
                     float* dw_dev, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * a4  Convolution forward / dgrad on the tcgen05 tensor cores (pf_conv_tc.cu), same semantics as
+ *     pf_conv2d_fwd / pf_conv2d_dgrad.  fp32 operands are split x = hi + lo (bf16 each) and each
+ *     k-slice issues hi*hi + hi*lo + lo*hi into one fp32 TMEM accumulator (error ~2^-17 relative).
+ *     Requires Cin % 16 == 0 and Cout % 16 == 0 (pf_conv2d_tc_supported).
+ *     Weights are pre-split and laid out K-major once per step by pf_conv2d_tc_prep_weight into
+ *     caller-owned bf16 buffers of pf_conv2d_tc_weight_elems(d, dgrad) elements each, which the caller
+ *     zero-fills ONCE at allocation (padding columns are never written).
+ * ------------------------------------------------------------------------------------------- */
+int pf_conv2d_tc_supported(const pf_conv_desc* d);
+int64_t pf_conv2d_tc_weight_elems(const pf_conv_desc* d, int dgrad);
+int pf_conv2d_tc_prep_weight(const pf_conv_desc* d, const float* w_dev, void* fwd_hi_dev, void* fwd_lo_dev,
+                             void* dgrad_hi_dev, void* dgrad_lo_dev, void* stream);
+int pf_conv2d_tc_fwd(const pf_conv_desc* d, const float* x_dev, const void* w_hi_dev, const void* w_lo_dev,
+                     const float* bias_dev, int relu, float* y_dev, void* stream);
+int pf_conv2d_tc_dgrad(const pf_conv_desc* d, const float* dy_dev, const void* wd_hi_dev, const void* wd_lo_dev,
+                       int accumulate, float* dx_dev, void* stream);
+/* dw = x (*) dy on the tensor cores (MN-major operands, split-K with a fixed-order reduction).
+ * Requires Cin % 16 == 0 and Cout % 64 == 0; ws_dev: pf_conv2d_tc_wgrad_workspace_bytes(d) bytes. */
+#define PF_CONV_TC_WGRAD_MAX_SPLITS 64
+int pf_conv2d_tc_wgrad_supported(const pf_conv_desc* d);
+int64_t pf_conv2d_tc_wgrad_workspace_bytes(const pf_conv_desc* d);
+int pf_conv2d_tc_wgrad(const pf_conv_desc* d, const float* x_dev, const float* dy_dev, float* ws_dev,
+                       float* dw_dev, void* stream);
+/* hardware probe used by tests/test_tc_gpu.py to pin the descriptor conventions (not a product op) */
+int pf_tc_probe(const void* a_dev, const void* b_dev, float* d_dev, int n, int k, int mode, uint32_t lbo_a,
+                uint32_t sbo_a, uint32_t lbo_b, uint32_t sbo_b, uint32_t kstep_a, uint32_t kstep_b, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * a13 The HBM-bound layers between the convolutions (pf_nn.cu); tensors viewed as [m, c], c % 4 == 0.
  *     tf.layers.batch_normalization(momentum, eps, fused) — utils/external/resnet_model.py:55-62:
  *       stats : batch mean / biased variance / rstd (+ moving-stat update, unbiased moving variance);

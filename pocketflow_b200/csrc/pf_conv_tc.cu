@@ -1,0 +1,606 @@
+// pf_conv_tc.cu — convolution forward / dgrad on the 5th-generation tensor cores (tcgen05 + TMEM).
+//
+// The one genuine dense contraction of the step (tf.nn.conv2d re-created on the
+// quantized weight, /root/reference/learners/uniform_quantization/utils.py:92-104, and its dgrad).
+// tcgen05 has no fp32 x fp32 MMA, and the parity bar is fp32 (1e-5 on losses), so operands are split
+//     x = hi + lo,  hi = bf16(x), lo = bf16(x - hi)         (representation error 2^-18)
+// and every k-slice issues three bf16 MMAs into ONE fp32 TMEM accumulator:
+//     D += A_hi*B_hi + A_hi*B_lo + A_lo*B_hi               (the lo*lo term, 2^-18 relative, is dropped)
+//
+// Implicit GEMM, both operands K-major:  D[M x N] = A[M x K] * B[N x K]^T
+//   fwd  : M = N*P*Q pixels, N = Cout, K = R*S*Cin;  A = im2col(x) gathered on the fly; B = w^T
+//   dgrad: M = N*H*W pixels, N = Cin,  K = R*S*Cout; A = gathered dy;                  B = w as [Cin][(r,s,cout)]
+// B is pre-split / pre-transposed once per step by pf_conv2d_tc_prep_weight (weights change every
+// step; 20 B per weight).  A rows are gathered from NHWC fp32 by 128 producer threads (one GEMM row
+// each: 64 contiguous channels of one tap = 256 B), split, and written to 128B-swizzled K-major smem
+// tiles; one elected thread issues the MMAs; accumulators live in TMEM; the producer warps then run
+// the epilogue (tcgen05.ld -> global NHWC fp32).  mbarrier ring of kStages smem stages.
+#include "pf_common.cuh"
+#include "pf_tc_common.cuh"
+
+namespace {
+using namespace pftc;
+
+constexpr int TM = 128;      // GEMM rows per CTA (= TMEM lanes)
+constexpr int BK = 64;       // bf16 elements per k-stage (= one 128-byte swizzled row)
+constexpr int kProducerThreads = 256;  // two threads per GEMM row: 8 x 16 B of A and 8 x 16 B of B each per stage
+constexpr int kThreads = 288;          // warps 0-7: producers + epilogue, warp 8: MMA issuer + TMEM alloc
+constexpr int kMaxStages = 4;
+
+struct TcGeom {
+  int N, H, W, C, K, R, S, P, Q, sh, sw, pt, pl;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void split4(const float4 v, uint2& hi, uint2& lo) {
+  const __nv_bfloat16 hx = __float2bfloat16_rn(v.x), hy = __float2bfloat16_rn(v.y);
+  const __nv_bfloat16 hz = __float2bfloat16_rn(v.z), hw = __float2bfloat16_rn(v.w);
+  hi.x = (uint32_t)__bfloat16_as_ushort(hx) | ((uint32_t)__bfloat16_as_ushort(hy) << 16);
+  hi.y = (uint32_t)__bfloat16_as_ushort(hz) | ((uint32_t)__bfloat16_as_ushort(hw) << 16);
+  lo.x = pack_bf16(v.x - __bfloat162float(hx), v.y - __bfloat162float(hy));
+  lo.y = pack_bf16(v.z - __bfloat162float(hz), v.w - __bfloat162float(hw));
+}
+
+// MODE 0 = fwd (gather x), 1 = dgrad (gather dy)
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const float* __restrict__ src, const __nv_bfloat16* __restrict__ b_hi,
+               const __nv_bfloat16* __restrict__ b_lo, float* __restrict__ out, TcGeom g, int M, int Ng,
+               int Kdim, int Kpad, int BN, int n_stages, int accumulate, const float* __restrict__ bias,
+               int relu) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t a_bytes = TM * 128, b_bytes = (uint32_t)BN * 128;
+  const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+  __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], accum_bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int m0 = blockIdx.x * TM, n0 = blockIdx.y * BN;
+  const int nk = Kpad / BK;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < BN) tmem_cols <<= 1;
+
+  if (tid == 0) {
+    for (int s = 0; s < n_stages; ++s) {
+      mbar_init(&full_bar[s], kProducerThreads);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(&tmem_base_s, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp < 8) {
+    // ======================= producers: two threads per GEMM row =======================
+    const int row = tid >> 1, half = tid & 1;
+    const int m = m0 + row;
+    const bool row_ok = m < M;
+    const int CC = (MODE == 0) ? g.C : g.K;  // channels of the gathered tensor
+    int pn = 0, y0 = 0, x0 = 0;
+    if (row_ok) {
+      const int hw = (MODE == 0) ? g.P * g.Q : g.H * g.W;
+      const int wq = (MODE == 0) ? g.Q : g.W;
+      pn = m / hw;
+      const int rem = m - pn * hw;
+      const int y = rem / wq, x = rem - y * wq;
+      if (MODE == 0) {
+        y0 = y * g.sh - g.pt;
+        x0 = x * g.sw - g.pl;
+      } else {
+        y0 = y + g.pt;
+        x0 = x + g.pl;
+      }
+    }
+    const int bn = n0 + row;             // this thread pair's B row (output channel / input channel)
+    const bool b_ok = row < BN && bn < Ng;
+    const uint32_t sw = (uint32_t)(row & 7);
+    const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+    for (int ks = 0; ks < nk; ++ks) {
+      const int s = ks % n_stages;
+      // ---- issue every global load of this stage first (16 independent 16-byte loads per thread)
+      float4 av[2][4];
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const int kk = ks * BK + (half * 2 + jj) * 16;   // 16 channels inside one filter tap (CC % 16 == 0)
+        const float* p = nullptr;
+        if (row_ok && kk < Kdim) {
+          const int tap = kk / CC, c = kk - tap * CC;
+          const int r = tap / g.S, q = tap - r * g.S;
+          if (MODE == 0) {
+            const int ih = y0 + r, iw = x0 + q;
+            if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) p = src + (((size_t)pn * g.H + ih) * g.W + iw) * g.C + c;
+          } else {
+            const int th = y0 - r, tw = x0 - q;
+            if (th >= 0 && tw >= 0) {
+              const int oh = th / g.sh, ow = tw / g.sw;
+              if (oh * g.sh == th && ow * g.sw == tw && oh < g.P && ow < g.Q)
+                p = src + (((size_t)pn * g.P + oh) * g.Q + ow) * g.K + c;
+            }
+          }
+        }
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+          av[jj][v] = p ? __ldg(reinterpret_cast<const float4*>(p) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      uint4 bh[4], bl[4];
+      {
+        const uint4* gh = reinterpret_cast<const uint4*>(b_hi + (size_t)bn * Kpad + (size_t)ks * BK) + half * 4;
+        const uint4* gl = reinterpret_cast<const uint4*>(b_lo + (size_t)bn * Kpad + (size_t)ks * BK) + half * 4;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          bh[c] = b_ok ? __ldg(gh + c) : z4;
+          bl[c] = b_ok ? __ldg(gl + c) : z4;
+        }
+      }
+      // ---- the smem slot must be free before it is overwritten (the wait overlaps the loads above)
+      mbar_wait(&empty_bar[s], (((uint32_t)(ks / n_stages)) & 1u) ^ 1u);
+      uint8_t* st = smem + (size_t)s * stage_bytes;
+      uint8_t* a_hi_row = st + row * 128;
+      uint8_t* a_lo_row = st + a_bytes + row * 128;
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        uint2 h[4], l[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) split4(av[jj][v], h[v], l[v]);
+        // 16 bf16 = two 16-byte chunks: chunk ids 2j, 2j+1, XOR-swizzled with (row & 7)
+        const int j = half * 2 + jj;
+        const uint32_t c0 = (((uint32_t)(2 * j)) ^ sw) << 4, c1 = (((uint32_t)(2 * j + 1)) ^ sw) << 4;
+        *reinterpret_cast<uint4*>(a_hi_row + c0) = make_uint4(h[0].x, h[0].y, h[1].x, h[1].y);
+        *reinterpret_cast<uint4*>(a_hi_row + c1) = make_uint4(h[2].x, h[2].y, h[3].x, h[3].y);
+        *reinterpret_cast<uint4*>(a_lo_row + c0) = make_uint4(l[0].x, l[0].y, l[1].x, l[1].y);
+        *reinterpret_cast<uint4*>(a_lo_row + c1) = make_uint4(l[2].x, l[2].y, l[3].x, l[3].y);
+      }
+      if (row < BN) {
+        uint8_t* b_hi_row = st + 2 * a_bytes + row * 128;
+        uint8_t* b_lo_row = b_hi_row + b_bytes;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t off = (((uint32_t)(half * 4 + c)) ^ sw) << 4;
+          *reinterpret_cast<uint4*>(b_hi_row + off) = bh[c];
+          *reinterpret_cast<uint4*>(b_lo_row + off) = bl[c];
+        }
+      }
+      fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
+      mbar_arrive(&full_bar[s]);
+    }
+    // ======================= epilogue: TMEM -> registers -> global =======================
+    // warp w owns TMEM lanes [32*(w%4), +32); warps 0-3 take the low half of the columns, 4-7 the high half
+    mbar_wait(&accum_bar, 0);
+    tc_fence_after();
+    const int erow = (warp & 3) * 32 + (tid & 31);
+    const int em = m0 + erow;
+    const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
+    const int cbeg = (BN >= 64) ? (warp >> 2) * (BN / 2) : 0;
+    const int cend = (BN >= 64) ? cbeg + BN / 2 : ((warp >> 2) == 0 ? BN : 0);
+    for (int c0 = cbeg; c0 < cend; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + lane_base + (uint32_t)c0, r);
+      if (em < M) {
+        float* o = out + (size_t)em * Ng + n0 + c0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (n0 + c0 + j + 3 < Ng && c0 + j + 3 < BN) {
+            float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                   __uint_as_float(r[j + 3]));
+            if (bias) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + j));
+              v.x = __fadd_rn(v.x, bb.x); v.y = __fadd_rn(v.y, bb.y); v.z = __fadd_rn(v.z, bb.z); v.w = __fadd_rn(v.w, bb.w);
+            }
+            if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            if (accumulate) {
+              const float4 old = *reinterpret_cast<const float4*>(o + j);
+              v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
+            }
+            *reinterpret_cast<float4*>(o + j) = v;
+          }
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // ======================= MMA issuer: one elected thread =======================
+    if ((tid & 31) == 0) {
+      const uint32_t idesc = make_idesc_bf16(TM, BN, 0, 0);
+      for (int ks = 0; ks < nk; ++ks) {
+        const int s = ks % n_stages;
+        mbar_wait(&full_bar[s], ((uint32_t)(ks / n_stages)) & 1u);
+        tc_fence_after();
+        const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t a_hi = base, a_lo = base + a_bytes, bh = base + 2 * a_bytes, bl = bh + b_bytes;
+#pragma unroll
+        for (int kk = 0; kk < BK / 16; ++kk) {
+          const uint64_t dah = make_smem_desc(a_hi + kk * 32, 16, 1024);
+          const uint64_t dal = make_smem_desc(a_lo + kk * 32, 16, 1024);
+          const uint64_t dbh = make_smem_desc(bh + kk * 32, 16, 1024);
+          const uint64_t dbl = make_smem_desc(bl + kk * 32, 16, 1024);
+          umma_bf16(tmem_base, dah, dbh, idesc, (ks > 0 || kk > 0) ? 1u : 0u);
+          umma_bf16(tmem_base, dah, dbl, idesc, 1u);
+          umma_bf16(tmem_base, dal, dbh, idesc, 1u);
+        }
+        umma_commit(&empty_bar[s]);   // frees the smem stage when these MMAs have completed
+      }
+      umma_commit(&accum_bar);        // accumulator complete
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// wgrad on tensor cores:  dW[kf][co] = sum_pix im2col(x)[pix][kf] * dy[pix][co]
+// GEMM with M = kf = (r,s,c) tile of 128, N = cout tile, K = pixels; BOTH operands are MN-major
+// (channels are the contiguous axis of NHWC): smem tiles are [k/8][mn/64][k%8] rows of 64 bf16
+// (128 B, SWIZZLE_128B), descriptor LBO = 1024 (next 64-wide MN block), SBO = (tile_mn/64)*1024
+// (next group of 8 pixels), one K=16 MMA step = 2*SBO — conventions pinned by tests/test_tc_gpu.py.
+// Split-K over pixel ranges (grid.z); partials go to a workspace and are reduced in fixed order.
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ partial,
+                     TcGeom g, int Mtot, int Npix, int pix_per_split, int BN, int n_stages) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t a_bytes = BK * TM * 2, b_bytes = (uint32_t)BK * BN * 2;   // one bf16 tile
+  const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+  __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], accum_bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int m0 = blockIdx.x * TM, n0 = blockIdx.y * BN;
+  const int pbeg = blockIdx.z * pix_per_split;
+  const int pend = min(Npix, pbeg + pix_per_split);
+  const int nk = (pend - pbeg + BK - 1) / BK;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < BN) tmem_cols <<= 1;
+  if (tid == 0) {
+    for (int s = 0; s < n_stages; ++s) {
+      mbar_init(&full_bar[s], kProducerThreads);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(&tmem_base_s, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int mbA = TM / 64, mbB = BN / 64;
+
+  if (warp < 8) {
+    // producers: thread t -> pixel (t / 4) of the stage, quarter (t % 4) of the MN extent
+    const int pl = tid >> 2, quarter = tid & 3;
+    // A: kf sub-chunks [m0 + 32*quarter + 16*jj, +16): tap / channel decode is stage-invariant
+    int a_r[2], a_q[2], a_c[2];
+    bool a_ok[2];
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+      const int kf = m0 + quarter * 32 + jj * 16;
+      a_ok[jj] = kf < Mtot;
+      const int tap = kf / g.C;
+      a_c[jj] = kf - tap * g.C;
+      a_r[jj] = tap / g.S;
+      a_q[jj] = tap - a_r[jj] * g.S;
+    }
+    // B: cout sub-range [n0 + (BN/4)*quarter, +BN/4): BN/16 float4 per thread (8 for BN = 128, 4 for BN = 64)
+    const int bvec = BN / 16;
+    const int bcol = quarter * (BN / 4);
+    for (int ks = 0; ks < nk; ++ks) {
+      const int s = ks % n_stages;
+      const int pix = pbeg + ks * BK + pl;
+      const bool pok = pix < pend;
+      int pn = 0, oh = 0, ow = 0;
+      if (pok) {
+        const int pq = g.P * g.Q;
+        pn = pix / pq;
+        const int rem = pix - pn * pq;
+        oh = rem / g.Q;
+        ow = rem - oh * g.Q;
+      }
+      float4 av[2][4], bv[8];
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const float* p = nullptr;
+        if (pok && a_ok[jj]) {
+          const int ih = oh * g.sh - g.pt + a_r[jj], iw = ow * g.sw - g.pl + a_q[jj];
+          if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) p = x + (((size_t)pn * g.H + ih) * g.W + iw) * g.C + a_c[jj];
+        }
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+          av[jj][v] = p ? __ldg(reinterpret_cast<const float4*>(p) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      {
+        const float* p = (pok && n0 + bcol < g.K) ? dy + (size_t)pix * g.K + n0 + bcol : nullptr;
+#pragma unroll
+        for (int v = 0; v < 8; ++v)
+          bv[v] = (p && v < bvec) ? __ldg(reinterpret_cast<const float4*>(p) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      mbar_wait(&empty_bar[s], (((uint32_t)(ks / n_stages)) & 1u) ^ 1u);
+      uint8_t* st = smem + (size_t)s * stage_bytes;
+      const uint32_t k8 = (uint32_t)(pl & 7), kb = (uint32_t)(pl >> 3);
+      // ---- A: element e = 32*quarter + 16*jj + 4*v .. of the 128-wide kf tile
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        uint2 h[4], l[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) split4(av[jj][v], h[v], l[v]);
+        const uint32_t e = (uint32_t)(quarter * 32 + jj * 16);
+        const uint32_t rowi = kb * (uint32_t)(mbA * 8) + (e >> 6) * 8 + k8;
+        const uint32_t ch = (e & 63) >> 3;   // first of two 16-byte chunks
+        uint8_t* hi = st + rowi * 128;
+        uint8_t* lo = hi + a_bytes;
+        *reinterpret_cast<uint4*>(hi + (((ch) ^ k8) << 4)) = make_uint4(h[0].x, h[0].y, h[1].x, h[1].y);
+        *reinterpret_cast<uint4*>(hi + (((ch + 1) ^ k8) << 4)) = make_uint4(h[2].x, h[2].y, h[3].x, h[3].y);
+        *reinterpret_cast<uint4*>(lo + (((ch) ^ k8) << 4)) = make_uint4(l[0].x, l[0].y, l[1].x, l[1].y);
+        *reinterpret_cast<uint4*>(lo + (((ch + 1) ^ k8) << 4)) = make_uint4(l[2].x, l[2].y, l[3].x, l[3].y);
+      }
+      // ---- B: element e = bcol + 4*v of the BN-wide cout tile; two float4 make one 16-byte bf16 chunk
+#pragma unroll
+      for (int v = 0; v < 8; v += 2) {
+        if (v < bvec) {
+          uint2 h0, l0, h1, l1;
+          split4(bv[v], h0, l0);
+          split4(bv[v + 1], h1, l1);
+          const uint32_t e = (uint32_t)(bcol + v * 4);
+          const uint32_t rowi = kb * (uint32_t)(mbB * 8) + (e >> 6) * 8 + k8;
+          const uint32_t ch = (e & 63) >> 3;
+          uint8_t* hi = st + 2 * a_bytes + rowi * 128;
+          uint8_t* lo = hi + b_bytes;
+          *reinterpret_cast<uint4*>(hi + ((ch ^ k8) << 4)) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+          *reinterpret_cast<uint4*>(lo + ((ch ^ k8) << 4)) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&full_bar[s]);
+    }
+    // ---- epilogue: D rows = kf, columns = cout -> partial[z][kf][cout]
+    mbar_wait(&accum_bar, 0);
+    tc_fence_after();
+    const int erow = (warp & 3) * 32 + (tid & 31);
+    const int em = m0 + erow;
+    const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
+    const int cbeg = (warp >> 2) * (BN / 2), cend = cbeg + BN / 2;
+    float* outp = partial + (size_t)blockIdx.z * Mtot * g.K;
+    for (int c0 = cbeg; c0 < cend; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + lane_base + (uint32_t)c0, r);
+      if (em < Mtot) {
+        float* o = outp + (size_t)em * g.K + n0 + c0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (n0 + c0 + j + 3 < g.K)
+            *reinterpret_cast<float4*>(o + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                            __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        }
+      }
+    }
+  } else if (warp == 8) {
+    if ((tid & 31) == 0) {
+      const uint32_t idesc = make_idesc_bf16(TM, BN, 1, 1);
+      const uint32_t sbo_a = (uint32_t)mbA * 1024u, sbo_b = (uint32_t)mbB * 1024u;
+      for (int ks = 0; ks < nk; ++ks) {
+        const int s = ks % n_stages;
+        mbar_wait(&full_bar[s], ((uint32_t)(ks / n_stages)) & 1u);
+        tc_fence_after();
+        const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t a_hi = base, a_lo = base + a_bytes, bh = base + 2 * a_bytes, bl = bh + b_bytes;
+#pragma unroll
+        for (int kk = 0; kk < BK / 16; ++kk) {
+          const uint64_t dah = make_smem_desc(a_hi + kk * 2 * sbo_a, 1024, sbo_a);
+          const uint64_t dal = make_smem_desc(a_lo + kk * 2 * sbo_a, 1024, sbo_a);
+          const uint64_t dbh = make_smem_desc(bh + kk * 2 * sbo_b, 1024, sbo_b);
+          const uint64_t dbl = make_smem_desc(bl + kk * 2 * sbo_b, 1024, sbo_b);
+          umma_bf16(tmem_base, dah, dbh, idesc, (ks > 0 || kk > 0) ? 1u : 0u);
+          umma_bf16(tmem_base, dah, dbl, idesc, 1u);
+          umma_bf16(tmem_base, dal, dbh, idesc, 1u);
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(&accum_bar);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+__global__ void __launch_bounds__(256)
+tc_splitk_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int64_t n, int splits) {
+  const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+  if (i >= n) return;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int z = 0; z < splits; ++z) {
+    const float4 v = *reinterpret_cast<const float4*>(partial + (size_t)z * n + i);
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  *reinterpret_cast<float4*>(out + i) = s;
+}
+
+inline int tc_wgrad_splits(const TcGeom& g, int BN, int* pix_per_split) {
+  const int Mtot = g.R * g.S * g.C, Npix = g.N * g.P * g.Q;
+  const int tiles = ((Mtot + TM - 1) / TM) * ((g.K + BN - 1) / BN);
+  int splits = (2 * PF_NUM_SMS + tiles - 1) / tiles;
+  const int max_by_k = (Npix + 8 * BK - 1) / (8 * BK);
+  if (splits > max_by_k) splits = max_by_k;
+  if (splits > PF_CONV_TC_WGRAD_MAX_SPLITS) splits = PF_CONV_TC_WGRAD_MAX_SPLITS;
+  if (splits < 1) splits = 1;
+  int pps = (Npix + splits - 1) / splits;
+  pps = (pps + BK - 1) / BK * BK;
+  *pix_per_split = pps;
+  return (Npix + pps - 1) / pps;
+}
+
+// ---- weight preparation: fp32 HWIO [R,S,C,K] -> split bf16, K-major for both passes
+//   fwd  : [K (cout)][Kpad_f],  k = (r*S + s)*C + c
+//   dgrad: [C (cin) ][Kpad_d],  k = (r*S + s)*K + co
+__global__ void __launch_bounds__(256)
+tc_prep_weight_kernel(const float* __restrict__ w, int RS, int C, int K, int kpad_f, int kpad_d,
+                      __nv_bfloat16* __restrict__ f_hi, __nv_bfloat16* __restrict__ f_lo,
+                      __nv_bfloat16* __restrict__ d_hi, __nv_bfloat16* __restrict__ d_lo) {
+  const int64_t total = (int64_t)RS * C * K;
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += stride) {
+    const int co = (int)(i % K);
+    const int64_t t = i / K;
+    const int c = (int)(t % C);
+    const int rs = (int)(t / C);
+    const float v = __ldg(w + i);
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    const size_t fo = (size_t)co * kpad_f + (size_t)rs * C + c;
+    f_hi[fo] = h;
+    f_lo[fo] = l;
+    if (d_hi) {
+      const size_t dof = (size_t)c * kpad_d + (size_t)rs * K + co;
+      d_hi[dof] = h;
+      d_lo[dof] = l;
+    }
+  }
+}
+
+int tc_geom(const pf_conv_desc* d, TcGeom* g, const char* who) {
+  PF_REQUIRE(d != nullptr, "%s: null descriptor", who);
+  PF_REQUIRE(d->n > 0 && d->h > 0 && d->w > 0 && d->c > 0 && d->k > 0 && d->r > 0 && d->s > 0 && d->p > 0 &&
+                 d->q > 0 && d->stride_h > 0 && d->stride_w > 0 && d->pad_t >= 0 && d->pad_l >= 0,
+             "%s: non-positive dimension in conv descriptor", who);
+  *g = TcGeom{d->n, d->h, d->w, d->c, d->k, d->r, d->s, d->p, d->q, d->stride_h, d->stride_w, d->pad_t, d->pad_l};
+  return PF_OK;
+}
+
+inline int pad64(int64_t k) { return (int)((k + 63) / 64 * 64); }
+
+template <int MODE>
+int launch_tc(const TcGeom& g, const float* src, const void* b_hi, const void* b_lo, float* out, int accumulate,
+              const float* bias, int relu, cudaStream_t st, const char* who) {
+  const int64_t M64 = (MODE == 0) ? (int64_t)g.N * g.P * g.Q : (int64_t)g.N * g.H * g.W;
+  PF_REQUIRE(M64 < (1ll << 31), "%s: too many rows", who);
+  const int M = (int)M64;
+  const int Ng = (MODE == 0) ? g.K : g.C;
+  const int Kdim = (MODE == 0) ? g.R * g.S * g.C : g.R * g.S * g.K;
+  const int Kpad = pad64(Kdim);
+  int BN = Ng >= 128 ? 128 : (Ng >= 64 ? 64 : (Ng >= 32 ? 32 : 16));
+  const int nk = Kpad / BK;
+  int stages = nk < 3 ? (nk < 2 ? 1 : 2) : 3;
+  if (BN <= 64 && nk >= 4) stages = 4;
+  const size_t smem = (size_t)stages * (2 * TM * 128 + 2 * BN * 128) + 1024;
+  auto kern = conv_tc_kernel<MODE>;
+  PF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  dim3 grid((M + TM - 1) / TM, (Ng + BN - 1) / BN);
+  kern<<<grid, kThreads, smem, st>>>(src, (const __nv_bfloat16*)b_hi, (const __nv_bfloat16*)b_lo, out, g, M, Ng,
+                                     Kdim, Kpad, BN, stages, accumulate, bias, relu);
+  PF_CHECK_LAUNCH(who);
+  return PF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pf_conv2d_tc_supported(const pf_conv_desc* d) {
+  if (!d) return 0;
+  return (d->c % 16 == 0) && (d->k % 16 == 0) && d->c >= 16 && d->k >= 16;
+}
+
+int64_t pf_conv2d_tc_weight_elems(const pf_conv_desc* d, int dgrad) {
+  if (!d) return 0;
+  if (dgrad) return (int64_t)d->c * pad64((int64_t)d->r * d->s * d->k);
+  return (int64_t)d->k * pad64((int64_t)d->r * d->s * d->c);
+}
+
+int pf_conv2d_tc_prep_weight(const pf_conv_desc* d, const float* w_dev, void* fwd_hi_dev, void* fwd_lo_dev,
+                             void* dgrad_hi_dev, void* dgrad_lo_dev, void* stream) {
+  TcGeom g;
+  int rc = tc_geom(d, &g, "pf_conv2d_tc_prep_weight");
+  if (rc) return rc;
+  PF_REQUIRE(w_dev && fwd_hi_dev && fwd_lo_dev, "pf_conv2d_tc_prep_weight: null pointer");
+  PF_REQUIRE((dgrad_hi_dev == nullptr) == (dgrad_lo_dev == nullptr), "pf_conv2d_tc_prep_weight: dgrad buffers come in pairs");
+  const int kpf = pad64((int64_t)g.R * g.S * g.C), kpd = pad64((int64_t)g.R * g.S * g.K);
+  cudaStream_t st = (cudaStream_t)stream;
+  // padding columns must be zero: the buffers are zero-filled once by the caller at allocation time
+  const int64_t total = (int64_t)g.R * g.S * g.C * g.K;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > PF_NUM_SMS * 8) blocks = PF_NUM_SMS * 8;
+  tc_prep_weight_kernel<<<(unsigned)blocks, 256, 0, st>>>(w_dev, g.R * g.S, g.C, g.K, kpf, kpd,
+                                                         (__nv_bfloat16*)fwd_hi_dev, (__nv_bfloat16*)fwd_lo_dev,
+                                                         (__nv_bfloat16*)dgrad_hi_dev, (__nv_bfloat16*)dgrad_lo_dev);
+  PF_CHECK_LAUNCH("pf_conv2d_tc_prep_weight");
+  return PF_OK;
+}
+
+int pf_conv2d_tc_fwd(const pf_conv_desc* d, const float* x_dev, const void* w_hi_dev, const void* w_lo_dev,
+                     const float* bias_dev, int relu, float* y_dev, void* stream) {
+  TcGeom g;
+  int rc = tc_geom(d, &g, "pf_conv2d_tc_fwd");
+  if (rc) return rc;
+  PF_REQUIRE(pf_conv2d_tc_supported(d), "pf_conv2d_tc_fwd: Cin and Cout must be multiples of 16");
+  PF_REQUIRE(x_dev && w_hi_dev && w_lo_dev && y_dev, "pf_conv2d_tc_fwd: null pointer");
+  PF_REQUIRE((((uintptr_t)x_dev | (uintptr_t)y_dev | (uintptr_t)w_hi_dev | (uintptr_t)w_lo_dev) & 15) == 0,
+             "pf_conv2d_tc_fwd: 16-byte alignment required");
+  return launch_tc<0>(g, x_dev, w_hi_dev, w_lo_dev, y_dev, 0, bias_dev, relu, (cudaStream_t)stream, "pf_conv2d_tc_fwd");
+}
+
+int pf_conv2d_tc_dgrad(const pf_conv_desc* d, const float* dy_dev, const void* wd_hi_dev, const void* wd_lo_dev,
+                       int accumulate, float* dx_dev, void* stream) {
+  TcGeom g;
+  int rc = tc_geom(d, &g, "pf_conv2d_tc_dgrad");
+  if (rc) return rc;
+  PF_REQUIRE(pf_conv2d_tc_supported(d), "pf_conv2d_tc_dgrad: Cin and Cout must be multiples of 16");
+  PF_REQUIRE(dy_dev && wd_hi_dev && wd_lo_dev && dx_dev, "pf_conv2d_tc_dgrad: null pointer");
+  PF_REQUIRE((((uintptr_t)dy_dev | (uintptr_t)dx_dev | (uintptr_t)wd_hi_dev | (uintptr_t)wd_lo_dev) & 15) == 0,
+             "pf_conv2d_tc_dgrad: 16-byte alignment required");
+  return launch_tc<1>(g, dy_dev, wd_hi_dev, wd_lo_dev, dx_dev, accumulate, nullptr, 0, (cudaStream_t)stream,
+                      "pf_conv2d_tc_dgrad");
+}
+
+int pf_conv2d_tc_wgrad_supported(const pf_conv_desc* d) {
+  if (!d) return 0;
+  return (d->c % 16 == 0) && (d->k % 64 == 0) && d->c >= 16;
+}
+
+int64_t pf_conv2d_tc_wgrad_workspace_bytes(const pf_conv_desc* d) {
+  TcGeom g;
+  if (!d || tc_geom(d, &g, "pf_conv2d_tc_wgrad_workspace_bytes")) return 0;
+  const int BN = g.K >= 128 ? 128 : 64;
+  int pps;
+  const int splits = tc_wgrad_splits(g, BN, &pps);
+  return (int64_t)splits * g.R * g.S * g.C * g.K * 4;
+}
+
+int pf_conv2d_tc_wgrad(const pf_conv_desc* d, const float* x_dev, const float* dy_dev, float* ws_dev,
+                       float* dw_dev, void* stream) {
+  TcGeom g;
+  int rc = tc_geom(d, &g, "pf_conv2d_tc_wgrad");
+  if (rc) return rc;
+  PF_REQUIRE(pf_conv2d_tc_wgrad_supported(d), "pf_conv2d_tc_wgrad: needs Cin %% 16 == 0 and Cout %% 64 == 0");
+  PF_REQUIRE(x_dev && dy_dev && ws_dev && dw_dev, "pf_conv2d_tc_wgrad: null pointer");
+  PF_REQUIRE((((uintptr_t)x_dev | (uintptr_t)dy_dev | (uintptr_t)ws_dev | (uintptr_t)dw_dev) & 15) == 0,
+             "pf_conv2d_tc_wgrad: 16-byte alignment required");
+  const int64_t np64 = (int64_t)g.N * g.P * g.Q;
+  PF_REQUIRE(np64 < (1ll << 31), "pf_conv2d_tc_wgrad: too many pixels");
+  const int Mtot = g.R * g.S * g.C, Npix = (int)np64;
+  const int BN = g.K >= 128 ? 128 : 64;
+  int pps;
+  const int splits = tc_wgrad_splits(g, BN, &pps);
+  const int nk = pps / BK;
+  const int stages = nk < 3 ? (nk < 2 ? 1 : 2) : 3;
+  const size_t smem = (size_t)stages * (2 * BK * TM * 2 + 2 * BK * BN * 2) + 1024;
+  PF_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  dim3 grid((Mtot + TM - 1) / TM, (g.K + BN - 1) / BN, splits);
+  cudaStream_t st = (cudaStream_t)stream;
+  conv_tc_wgrad_kernel<<<grid, kThreads, smem, st>>>(x_dev, dy_dev, splits == 1 ? dw_dev : ws_dev, g, Mtot, Npix,
+                                                    pps, BN, stages);
+  PF_CHECK_LAUNCH("pf_conv2d_tc_wgrad");
+  if (splits > 1) {
+    const int64_t n = (int64_t)Mtot * g.K;
+    tc_splitk_reduce_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(ws_dev, dw_dev, n, splits);
+    PF_CHECK_LAUNCH("pf_conv2d_tc_wgrad/reduce");
+  }
+  return PF_OK;
+}
+
+}  // extern "C"

@@ -41,6 +41,11 @@ class BatchIterator(object):
         self.images.iterator = self
         return self.images, self.labels
 
+    def prefill(self):
+        """Generate the whole pool now (keeps host-side synthesis out of timed regions)."""
+        while len(self.pool) < self.pool_size:
+            self.next_batch()
+
     def next_batch(self):
         """Next mini-batch as (images, labels) in pinned host memory.  The synthetic stream is a pool of
         POOL_SIZE distinct pre-generated batches cycled in order (what tf.data's prefetch buffer holds

@@ -101,12 +101,16 @@ class Executor:
 
     def __init__(self, graph, images, logits, device, store=None, train=True, loss=None, labels=None,
                  optimizer=None, weight_quant=None, act_quant=None, maskable=None, teacher=None,
-                 seed=1, exact_ste=True, grad_scale=1.0, scope=None):
+                 seed=1, exact_ste=True, grad_scale=1.0, scope=None, conv_path=None):
         self.g, self.device, self.train = graph, device, train
         self.images, self.logits_t, self.labels_t = images, logits, labels
         self.loss, self.teacher = loss, teacher
         self.optimizer = optimizer or {}
         self.exact_ste, self.grad_scale = exact_ste, float(grad_scale)
+        # 'tc': tcgen05 split-bf16 conv where the shape allows (Cin, Cout multiples of 16), exact-fp32
+        # CUDA-core kernels elsewhere; 'fp32': exact-fp32 everywhere (the on-device reference)
+        import os as _os
+        self.conv_path = conv_path or _os.environ.get('PF_CONV_PATH', 'tc')
         self.ops = self._reachable_ops(logits)
         variables = []
         for op in self.ops:
@@ -198,6 +202,8 @@ class Executor:
                 self.aq_out[op] = E(t.shape)
         # ---- per-op scratch
         self.bn = {}
+        self.tc = {}
+        self.tc_wgrad = set()
         max_ws, max_wt, max_bnws = 4, 4, 4
         self.desc = {}
         for op in self.ops:
@@ -217,7 +223,12 @@ class Executor:
                     k = y.shape[1]
                     d = ops.conv_desc(n, 1, 1, c, k, 1, 1, 1, 1, 1, 1, 0, 0)
                 self.desc[op] = d
+                if self.conv_path == 'tc' and ops.conv2d_tc_supported(d):
+                    self.tc[op] = ops.TcWeights(d, dev, need_dgrad=self.train and x.op.type != 'Placeholder')
                 if self.train:
+                    if op in self.tc and ops.conv2d_tc_wgrad_supported(d):
+                        self.tc_wgrad.add(op)
+                        max_ws = max(max_ws, ops.conv2d_tc_wgrad_workspace_floats(d))
                     max_ws = max(max_ws, ops.conv2d_wgrad_workspace_floats(d))
                     max_wt = max(max_wt, op.vars['kernel'].numel)
             if op.type == 'MaxPool':
@@ -359,9 +370,16 @@ class Executor:
                 continue
             if ty in ('Conv2D', 'MatMul'):
                 bias = st.view(op.vars['bias']) if 'bias' in op.vars else None
-                with self.timed('conv_fwd'):
-                    ops.conv2d_fwd(self.desc[op], self.T(op.inputs[0]), self.kernel_of(op), bias,
-                                   op in self.fused_act, self.buf[op.output])
+                if op in self.tc:
+                    with self.timed('conv_prep'):
+                        self.tc[op].prepare(self.kernel_of(op))
+                    with self.timed('conv_fwd'):
+                        ops.conv2d_tc_fwd(self.desc[op], self.T(op.inputs[0]), self.tc[op], bias,
+                                          op in self.fused_act, self.buf[op.output])
+                else:
+                    with self.timed('conv_fwd'):
+                        ops.conv2d_fwd(self.desc[op], self.T(op.inputs[0]), self.kernel_of(op), bias,
+                                       op in self.fused_act, self.buf[op.output])
             elif ty == 'FusedBatchNorm':
                 x, y = self.T(op.inputs[0]), self.buf[op.output]
                 c = y.shape[-1]
@@ -440,11 +458,17 @@ class Executor:
                 if 'bias' in op.vars:
                     ops.colsum(gy, m, k, st.view(op.vars['bias'], self.G))
                 with self.timed('conv_wgrad'):
-                    ops.conv2d_wgrad(d, self.T(x_t), gy, self.wgrad_ws, st.view(op.vars['kernel'], self.G))
+                    if op in self.tc_wgrad:
+                        ops.conv2d_tc_wgrad(d, self.T(x_t), gy, self.wgrad_ws, st.view(op.vars['kernel'], self.G))
+                    else:
+                        ops.conv2d_wgrad(d, self.T(x_t), gy, self.wgrad_ws, st.view(op.vars['kernel'], self.G))
                 if x_t.op.type != 'Placeholder':
                     gx, acc = self.grad_target(x_t)
                     with self.timed('conv_dgrad'):
-                        ops.conv2d_dgrad(d, gy, self.kernel_of(op), self.wt_ws, acc, gx)
+                        if op in self.tc:
+                            ops.conv2d_tc_dgrad(d, gy, self.tc[op], acc, gx)
+                        else:
+                            ops.conv2d_dgrad(d, gy, self.kernel_of(op), self.wt_ws, acc, gx)
             elif ty == 'FusedBatchNorm':
                 x_t = op.inputs[0]
                 y = self.buf[op.output]

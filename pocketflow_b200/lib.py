@@ -38,6 +38,15 @@ SIGNATURES = {
     'pf_conv2d_dgrad': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
     'pf_conv2d_wgrad_workspace_bytes': (c_i64, [c_vp]),
     'pf_conv2d_wgrad': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'pf_conv2d_tc_supported': (c_i32, [c_vp]),
+    'pf_conv2d_tc_weight_elems': (c_i64, [c_vp, c_i32]),
+    'pf_conv2d_tc_prep_weight': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'pf_conv2d_tc_fwd': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
+    'pf_conv2d_tc_dgrad': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
+    'pf_conv2d_tc_wgrad_supported': (c_i32, [c_vp]),
+    'pf_conv2d_tc_wgrad_workspace_bytes': (c_i64, [c_vp]),
+    'pf_conv2d_tc_wgrad': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'pf_tc_probe': (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32] + [ctypes.c_uint32] * 6 + [c_vp]),
     'pf_bn_train_stats': (c_i32, [c_vp, c_i64, c_i32, c_f32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'pf_bn_eval_prepare': (c_i32, [c_vp, c_i32, c_f32, c_vp, c_vp]),
     'pf_bn_apply': (c_i32, [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]),

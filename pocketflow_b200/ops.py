@@ -502,3 +502,52 @@ def softmax_bwd(dy, y, dx):
 def minmax_reset(slots):
     """slots: int32 [n, 2] -> every pair = (0xFFFFFFFF, 0)."""
     _lib.check(_lib.load().pf_minmax_reset(_p(slots), slots.numel() // 2, _stream()), 'pf_minmax_reset')
+
+
+# ----------------------------------------------------------------------------- a4 on tensor cores
+def conv2d_tc_supported(d):
+    return bool(_lib.load().pf_conv2d_tc_supported(ctypes.byref(d)))
+
+
+class TcWeights:
+    """Split-bf16, K-major copies of one conv kernel for the tcgen05 path (fwd and dgrad operands)."""
+
+    def __init__(self, d, device, need_dgrad=True):
+        L = _lib.load()
+        self.d = d
+        nf = int(L.pf_conv2d_tc_weight_elems(ctypes.byref(d), 0))
+        self.f_hi = torch.zeros(nf, dtype=torch.bfloat16, device=device)
+        self.f_lo = torch.zeros(nf, dtype=torch.bfloat16, device=device)
+        self.d_hi = self.d_lo = None
+        if need_dgrad:
+            nd = int(L.pf_conv2d_tc_weight_elems(ctypes.byref(d), 1))
+            self.d_hi = torch.zeros(nd, dtype=torch.bfloat16, device=device)
+            self.d_lo = torch.zeros(nd, dtype=torch.bfloat16, device=device)
+
+    def prepare(self, w):
+        _lib.check(_lib.load().pf_conv2d_tc_prep_weight(ctypes.byref(self.d), _p(w), _p(self.f_hi), _p(self.f_lo),
+                                                        _p(self.d_hi), _p(self.d_lo), _stream()),
+                   'pf_conv2d_tc_prep_weight')
+
+
+def conv2d_tc_fwd(d, x, tw, bias, relu, y):
+    _lib.check(_lib.load().pf_conv2d_tc_fwd(ctypes.byref(d), _p(x), _p(tw.f_hi), _p(tw.f_lo), _p(bias),
+                                            int(bool(relu)), _p(y), _stream()), 'pf_conv2d_tc_fwd')
+
+
+def conv2d_tc_dgrad(d, dy, tw, accumulate, dx):
+    _lib.check(_lib.load().pf_conv2d_tc_dgrad(ctypes.byref(d), _p(dy), _p(tw.d_hi), _p(tw.d_lo),
+                                              int(bool(accumulate)), _p(dx), _stream()), 'pf_conv2d_tc_dgrad')
+
+
+def conv2d_tc_wgrad_supported(d):
+    return bool(_lib.load().pf_conv2d_tc_wgrad_supported(ctypes.byref(d)))
+
+
+def conv2d_tc_wgrad_workspace_floats(d):
+    return int(_lib.load().pf_conv2d_tc_wgrad_workspace_bytes(ctypes.byref(d))) // 4
+
+
+def conv2d_tc_wgrad(d, x, dy, ws, dw):
+    _lib.check(_lib.load().pf_conv2d_tc_wgrad(ctypes.byref(d), _p(x), _p(dy), _p(ws), _p(dw), _stream()),
+               'pf_conv2d_tc_wgrad')

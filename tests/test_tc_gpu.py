@@ -1,0 +1,138 @@
+"""tcgen05 path: (1) the hardware probe pins the shared-memory / instruction descriptor conventions of
+pf_tc_common.cuh; (2) pf_conv2d_tc_fwd / pf_conv2d_tc_dgrad against a float64 reference and against the
+exact-fp32 CUDA-core kernels.  Tolerance: 2e-5 of the output scale (split-bf16: operands carry 16
+mantissa bits, the dropped lo*lo term is 2^-18 relative) — two orders tighter than TF32 would be."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from pocketflow_b200 import lib as _lib
+from pocketflow_b200 import ops
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def probe(mode, N, K, la, sa, lb, sb, ka, kb):
+    L = _lib.load()
+    torch.manual_seed(N + K + mode)
+    if mode == 0:
+        A, B = torch.randn(128, K, device=DEV).bfloat16(), torch.randn(N, K, device=DEV).bfloat16()
+        ref = A.float() @ B.float().t()
+    else:
+        A, B = torch.randn(K, 128, device=DEV).bfloat16(), torch.randn(K, N, device=DEV).bfloat16()
+        ref = A.float().t() @ B.float()
+    D = torch.zeros(128, N, device=DEV)
+    st = L.pf_tc_probe(A.data_ptr(), B.data_ptr(), D.data_ptr(), N, K, mode, la, sa, lb, sb, ka, kb, None)
+    torch.cuda.synchronize()
+    assert st == 0
+    return (D - ref).abs().max().item() / ref.abs().max().item()
+
+
+@pytest.mark.parametrize('N,K', [(128, 64), (128, 256), (64, 128), (256, 128), (32, 64)])
+def test_probe_k_major_sw128(N, K):
+    # K-major, SWIZZLE_128B: SBO = 1024 B (8 rows x 128 B), K=16 step = 32 B, LBO unused
+    assert probe(0, N, K, 16, 1024, 16, 1024, 32, 32) < 1e-5
+
+
+@pytest.mark.parametrize('N,K', [(128, 64), (128, 256), (64, 128), (256, 128)])
+def test_probe_mn_major_sw128(N, K):
+    # MN-major: LBO = stride between 64-element MN blocks, SBO = stride between 8-k groups, K=16 step = 2*SBO
+    mbA, mbB = 2, N // 64
+    assert probe(1, N, K, 1024, mbA * 1024, 1024, mbB * 1024, 2 * mbA * 1024, 2 * mbB * 1024) < 1e-5
+
+
+CASES = [
+    # n, h, w, c, k, r, s, stride, pad0, pad1
+    (4, 16, 16, 16, 32, 3, 3, 1, 1, 1),
+    (2, 17, 15, 16, 48, 3, 3, 2, 1, 1),
+    (2, 8, 8, 64, 256, 1, 1, 1, 0, 0),
+    (2, 9, 9, 32, 64, 1, 1, 2, 0, 0),
+    (3, 14, 14, 64, 64, 3, 3, 1, 1, 1),
+    (2, 12, 12, 128, 128, 3, 3, 2, 0, 1),
+    (2, 7, 7, 512, 2048, 1, 1, 1, 0, 0),
+    (1, 7, 7, 512, 512, 3, 3, 1, 1, 1),
+    (5, 10, 10, 32, 64, 5, 5, 1, 0, 0),
+    (2, 32, 32, 16, 16, 3, 3, 1, 1, 1),
+]
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_conv_tc_fwd_dgrad(case):
+    n, h, w, c, k, r, s, st, p0, p1 = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(n, h, w, c, generator=g)
+    wt = torch.randn(r, s, c, k, generator=g) * (2.0 / (r * s * c)) ** 0.5
+    bias = torch.randn(k, generator=g)
+    p = (h + p0 + p1 - r) // st + 1
+    q = (w + p0 + p1 - s) // st + 1
+    xd = x.double().permute(0, 3, 1, 2).requires_grad_(True)
+    wd = wt.double().permute(3, 2, 0, 1)
+    yd = F.conv2d(F.pad(xd, (p0, p1, p0, p1)), wd, stride=st)
+    dy = torch.randn(n, p, q, k, generator=g)
+    yd.backward(dy.double().permute(0, 3, 1, 2))
+    y_ref, dx_ref = yd.permute(0, 2, 3, 1).detach(), xd.grad.permute(0, 2, 3, 1)
+    d = ops.conv_desc(n, h, w, c, k, r, s, p, q, st, st, p0, p0)
+    assert ops.conv2d_tc_supported(d)
+    X, W, DY = x.to(DEV), wt.to(DEV).contiguous(), dy.to(DEV)
+    tw = ops.TcWeights(d, torch.device(DEV))
+    tw.prepare(W)
+    Y = torch.empty(n, p, q, k, device=DEV)
+    ops.conv2d_tc_fwd(d, X, tw, None, False, Y)
+    err = (Y.cpu().double() - y_ref).abs().max().item() / y_ref.abs().max().item()
+    assert err <= 2e-5, 'fwd err %.3e' % err
+    ops.conv2d_tc_fwd(d, X, tw, bias.to(DEV), True, Y)
+    ref2 = torch.relu(y_ref + bias.double())
+    assert (Y.cpu().double() - ref2).abs().max().item() <= 2e-5 * ref2.abs().max().item()
+    DX = torch.full((n, h, w, c), 3.0, device=DEV)
+    ops.conv2d_tc_dgrad(d, DY, tw, False, DX)
+    err = (DX.cpu().double() - dx_ref).abs().max().item() / dx_ref.abs().max().item()
+    assert err <= 2e-5, 'dgrad err %.3e' % err
+    ops.conv2d_tc_dgrad(d, DY, tw, True, DX)
+    assert (DX.cpu().double() - 2 * dx_ref).abs().max().item() <= 4e-5 * dx_ref.abs().max().item()
+    # against the exact-fp32 kernel: same answer to split-bf16 accuracy
+    Y32 = torch.empty_like(Y)
+    ops.conv2d_fwd(d, X, W, None, False, Y32)
+    ops.conv2d_tc_fwd(d, X, tw, None, False, Y)
+    assert (Y - Y32).abs().max().item() <= 2e-5 * Y32.abs().max().item()
+
+
+WG_CASES = [c for c in CASES if c[4] % 64 == 0] + [(8, 28, 28, 64, 128, 3, 3, 1, 1, 1), (16, 8, 8, 256, 64, 1, 1, 1, 0, 0),
+                                                   (3, 9, 9, 16, 192, 3, 3, 1, 1, 1)]
+
+
+@pytest.mark.parametrize('case', WG_CASES)
+def test_conv_tc_wgrad(case):
+    n, h, w, c, k, r, s, st, p0, p1 = case
+    g = torch.Generator().manual_seed(sum(case) + 1)
+    x = torch.randn(n, h, w, c, generator=g)
+    p = (h + p0 + p1 - r) // st + 1
+    q = (w + p0 + p1 - s) // st + 1
+    dy = torch.randn(n, p, q, k, generator=g)
+    xd = x.double().permute(0, 3, 1, 2)
+    wd = torch.zeros(k, c, r, s, dtype=torch.float64, requires_grad=True)
+    yd = F.conv2d(F.pad(xd, (p0, p1, p0, p1)), wd, stride=st)
+    yd.backward(dy.double().permute(0, 3, 1, 2))
+    dw_ref = wd.grad.permute(2, 3, 1, 0)
+    d = ops.conv_desc(n, h, w, c, k, r, s, p, q, st, st, p0, p0)
+    assert ops.conv2d_tc_wgrad_supported(d)
+    ws = torch.empty(max(ops.conv2d_tc_wgrad_workspace_floats(d), 4), device=DEV)
+    DW = torch.full((r, s, c, k), 5.0, device=DEV)
+    ops.conv2d_tc_wgrad(d, x.to(DEV), dy.to(DEV), ws, DW)
+    err = (DW.cpu().double() - dw_ref).abs().max().item() / dw_ref.abs().max().item()
+    assert err <= 2e-5, 'wgrad err %.3e' % err
+
+
+def test_conv_tc_rejects_unsupported_shapes():
+    d = ops.conv_desc(2, 8, 8, 3, 16, 3, 3, 6, 6, 1, 1, 0, 0)
+    assert not ops.conv2d_tc_supported(d)
+    x, y = torch.zeros(2, 8, 8, 3, device=DEV), torch.zeros(2, 6, 6, 16, device=DEV)
+    dummy = torch.zeros(1024, dtype=torch.bfloat16, device=DEV)
+
+    class T:
+        f_hi = f_lo = dummy
+    with pytest.raises(ValueError):
+        ops.conv2d_tc_fwd(d, x, T, None, False, y)
