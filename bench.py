@@ -250,6 +250,7 @@ def main():
         return
     if args.warmup < 3:
         args.warmup = 3
+    os.environ.setdefault('NCCL_DEBUG', 'WARN')      # keep NCCL's version banner off stdout (one JSON line)
     import torch
     import torch.distributed as dist
     from pocketflow_b200 import ops

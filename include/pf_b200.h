@@ -291,11 +291,13 @@ int pf_relu_bwd(const float* dy_dev, const float* y_dev, int64_t n, int act, int
                 void* stream);
 /* out[c] = sum_m a[m][c] (bias gradient) */
 int pf_colsum(const float* a_dev, int64_t m, int c, float* out_dev, void* stream);
-/* max pooling (kernel r x s, strides, leading pads from the descriptor; k unused) and its gradient
- * (the first maximum of a window in row-major order receives the gradient, like TF's MaxPoolGrad) */
-int pf_maxpool_fwd(const pf_conv_desc* d, const float* x_dev, float* y_dev, void* stream);
-int pf_maxpool_bwd(const pf_conv_desc* d, const float* dy_dev, const float* x_dev, const float* y_dev,
-                   int accumulate, float* dx_dev, void* stream);
+/* max pooling (kernel r x s, strides, leading pads from the descriptor; k unused; c % 4 == 0).  The
+ * forward records the window position of the FIRST maximum in row-major order (uint8 per output
+ * element; argmax_dev may be NULL for inference) and the backward routes each gradient there, like
+ * TF's MaxPoolGrad.  Gather form, deterministic. */
+int pf_maxpool_fwd(const pf_conv_desc* d, const float* x_dev, float* y_dev, uint8_t* argmax_dev, void* stream);
+int pf_maxpool_bwd(const pf_conv_desc* d, const float* dy_dev, const uint8_t* argmax_dev, int accumulate,
+                   float* dx_dev, void* stream);
 /* tf.reduce_mean over H,W (resnet_model.py:547-548) */
 int pf_global_avgpool_fwd(const float* x_dev, int n, int hw, int c, float* y_dev, void* stream);
 int pf_global_avgpool_bwd(const float* dy_dev, int n, int hw, int c, int accumulate, float* dx_dev, void* stream);

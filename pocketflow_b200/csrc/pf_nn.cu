@@ -333,69 +333,82 @@ colsum_kernel(const float* __restrict__ a, int M, int C, float* __restrict__ out
 }
 
 // ------------------------------------------------------------------ pooling
+// Forward also records, per output element, which window position (r*kw + q) holds the FIRST maximum
+// in row-major scan order (TF's MaxPoolGrad routes the gradient there); 255 = empty window.
 __global__ void __launch_bounds__(NT)
 maxpool_fwd_kernel(const float* __restrict__ x, int N, int H, int W, int C, int P, int Q, int kh, int kw,
-                   int sh, int sw, int pt, int pl, float* __restrict__ y) {
-  const int64_t total = (int64_t)N * P * Q * C;
+                   int sh, int sw, int pt, int pl, float* __restrict__ y, uint8_t* __restrict__ argmax) {
+  const int64_t total = (int64_t)N * P * Q * (C >> 2);
   const int64_t stride = (int64_t)gridDim.x * NT;
+  const int C4 = C >> 2;
   for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < total; i += stride) {
-    const int c = (int)(i % C);
-    int64_t t = i / C;
+    const int c = (int)(i % C4) << 2;
+    int64_t t = i / C4;
     const int ow = (int)(t % Q); t /= Q;
     const int oh = (int)(t % P);
     const int n = (int)(t / P);
-    float m = -INFINITY;
+    float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    int a[4] = {255, 255, 255, 255};
     for (int r = 0; r < kh; ++r) {
       const int ih = oh * sh - pt + r;
       if (ih < 0 || ih >= H) continue;
       for (int q = 0; q < kw; ++q) {
         const int iw = ow * sw - pl + q;
         if (iw < 0 || iw >= W) continue;
-        m = fmaxf(m, __ldg(x + (((size_t)n * H + ih) * W + iw) * C + c));
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + (((size_t)n * H + ih) * W + iw) * C + c));
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (vv[j] > m[j]) { m[j] = vv[j]; a[j] = r * kw + q; }
       }
     }
-    y[i] = m;
+    const size_t o = ((((size_t)n * P + oh) * Q + ow) * C + c);
+    *reinterpret_cast<float4*>(y + o) = make_float4(m[0], m[1], m[2], m[3]);
+    if (argmax) *reinterpret_cast<uchar4*>(argmax + o) = make_uchar4((uint8_t)a[0], (uint8_t)a[1], (uint8_t)a[2], (uint8_t)a[3]);
   }
 }
 
-// dx[n,ih,iw,c] (+)= sum over windows containing (ih,iw) whose FIRST argmax (row-major scan, like
-// TF's MaxPoolGrad) is (ih,iw).  Gather form: no atomics, deterministic.
+// dx[n,ih,iw,c] (+)= sum of dy over the windows whose recorded argmax is (ih,iw).  Gather form: no
+// atomics, deterministic; each input position belongs to at most ceil(kh/sh)*ceil(kw/sw) windows.
 __global__ void __launch_bounds__(NT)
-maxpool_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ y,
-                   int N, int H, int W, int C, int P, int Q, int kh, int kw, int sh, int sw, int pt,
-                   int pl, int accumulate, float* __restrict__ dx) {
-  const int64_t total = (int64_t)N * H * W * C;
+maxpool_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ argmax, int N, int H, int W, int C,
+                   int P, int Q, int kh, int kw, int sh, int sw, int pt, int pl, int accumulate,
+                   float* __restrict__ dx) {
+  const int C4 = C >> 2;
+  const int64_t total = (int64_t)N * H * W * C4;
   const int64_t stride = (int64_t)gridDim.x * NT;
   for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < total; i += stride) {
-    const int c = (int)(i % C);
-    int64_t t = i / C;
+    const int c = (int)(i % C4) << 2;
+    int64_t t = i / C4;
     const int iw = (int)(t % W); t /= W;
     const int ih = (int)(t % H);
     const int n = (int)(t / H);
-    const float xv = x[i];
-    float g = 0.f;
+    float g[4] = {0.f, 0.f, 0.f, 0.f};
     const int oh_lo = max(0, (ih + pt - kh + sh) / sh), oh_hi = min(P - 1, (ih + pt) / sh);
     const int ow_lo = max(0, (iw + pl - kw + sw) / sw), ow_hi = min(Q - 1, (iw + pl) / sw);
     for (int oh = oh_lo; oh <= oh_hi; ++oh) {
+      const int r = ih + pt - oh * sh;
       for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+        const int q = iw + pl - ow * sw;
+        const int code = r * kw + q;
         const size_t o = (((size_t)n * P + oh) * Q + ow) * C + c;
-        if (__ldg(y + o) != xv) continue;
-        // is (ih,iw) the first position of this window that attains the max?
-        bool first = true;
-        for (int r = 0; r < kh && first; ++r) {
-          const int yy = oh * sh - pt + r;
-          if (yy < 0 || yy >= H) continue;
-          for (int q = 0; q < kw; ++q) {
-            const int xx = ow * sw - pl + q;
-            if (xx < 0 || xx >= W) continue;
-            if (yy == ih && xx == iw) { r = kh; break; }
-            if (__ldg(x + (((size_t)n * H + yy) * W + xx) * C + c) == xv) { first = false; break; }
-          }
+        const uchar4 a = __ldg(reinterpret_cast<const uchar4*>(argmax + o));
+        if (a.x == code || a.y == code || a.z == code || a.w == code) {
+          const float4 d = __ldg(reinterpret_cast<const float4*>(dy + o));
+          if (a.x == code) g[0] += d.x;
+          if (a.y == code) g[1] += d.y;
+          if (a.z == code) g[2] += d.z;
+          if (a.w == code) g[3] += d.w;
         }
-        if (first) g += __ldg(dy + o);
       }
     }
-    dx[i] = accumulate ? dx[i] + g : g;
+    float4 o4 = make_float4(g[0], g[1], g[2], g[3]);
+    float* p = dx + (i << 2);
+    if (accumulate) {
+      const float4 old = *reinterpret_cast<const float4*>(p);
+      o4.x += old.x; o4.y += old.y; o4.z += old.z; o4.w += old.w;
+    }
+    *reinterpret_cast<float4*>(p) = o4;
   }
 }
 
@@ -573,21 +586,23 @@ int pf_colsum(const float* a_dev, int64_t m, int c, float* out_dev, void* stream
   return PF_OK;
 }
 
-int pf_maxpool_fwd(const pf_conv_desc* d, const float* x_dev, float* y_dev, void* stream) {
+int pf_maxpool_fwd(const pf_conv_desc* d, const float* x_dev, float* y_dev, uint8_t* argmax_dev, void* stream) {
   PF_REQUIRE(d && x_dev && y_dev && d->n > 0 && d->c > 0 && d->p > 0 && d->q > 0, "pf_maxpool_fwd: bad arguments");
-  const int64_t total = (int64_t)d->n * d->p * d->q * d->c;
+  PF_REQUIRE((d->c & 3) == 0 && d->r * d->s < 255, "pf_maxpool_fwd: C must be a multiple of 4 and the window < 255");
+  const int64_t total = (int64_t)d->n * d->p * d->q * (d->c >> 2);
   maxpool_fwd_kernel<<<ew_grid(total), NT, 0, (cudaStream_t)stream>>>(x_dev, d->n, d->h, d->w, d->c, d->p, d->q, d->r,
                                                                      d->s, d->stride_h, d->stride_w, d->pad_t,
-                                                                     d->pad_l, y_dev);
+                                                                     d->pad_l, y_dev, argmax_dev);
   PF_CHECK_LAUNCH("pf_maxpool_fwd");
   return PF_OK;
 }
 
-int pf_maxpool_bwd(const pf_conv_desc* d, const float* dy_dev, const float* x_dev, const float* y_dev,
-                   int accumulate, float* dx_dev, void* stream) {
-  PF_REQUIRE(d && dy_dev && x_dev && y_dev && dx_dev && d->n > 0 && d->c > 0, "pf_maxpool_bwd: bad arguments");
-  const int64_t total = (int64_t)d->n * d->h * d->w * d->c;
-  maxpool_bwd_kernel<<<ew_grid(total), NT, 0, (cudaStream_t)stream>>>(dy_dev, x_dev, y_dev, d->n, d->h, d->w, d->c,
+int pf_maxpool_bwd(const pf_conv_desc* d, const float* dy_dev, const uint8_t* argmax_dev, int accumulate,
+                   float* dx_dev, void* stream) {
+  PF_REQUIRE(d && dy_dev && argmax_dev && dx_dev && d->n > 0 && d->c > 0, "pf_maxpool_bwd: bad arguments");
+  PF_REQUIRE((d->c & 3) == 0, "pf_maxpool_bwd: C must be a multiple of 4");
+  const int64_t total = (int64_t)d->n * d->h * d->w * (d->c >> 2);
+  maxpool_bwd_kernel<<<ew_grid(total), NT, 0, (cudaStream_t)stream>>>(dy_dev, argmax_dev, d->n, d->h, d->w, d->c,
                                                                      d->p, d->q, d->r, d->s, d->stride_h,
                                                                      d->stride_w, d->pad_t, d->pad_l, accumulate,
                                                                      dx_dev);

@@ -204,6 +204,7 @@ class Executor:
         self.bn = {}
         self.tc = {}
         self.tc_wgrad = set()
+        self.pool_argmax = {}
         max_ws, max_wt, max_bnws = 4, 4, 4
         self.desc = {}
         for op in self.ops:
@@ -237,6 +238,8 @@ class Executor:
                 _, p, q, _ = y.shape
                 (kh, kw), (sh, sw), (pt, pl) = op.attrs['ksize'], op.attrs['strides'], op.attrs['pad']
                 self.desc[op] = ops.conv_desc(n, h, w, c, c, kh, kw, p, q, sh, sw, pt, pl)
+                if self.train:
+                    self.pool_argmax[op] = torch.empty(y.shape, dtype=torch.uint8, device=dev)
         if self.labels_t is not None and self.labels_t not in self.buf:
             self.buf[self.labels_t] = torch.zeros(self.labels_t.shape, dtype=torch.float32, device=dev)
         self.bn_ws = E((max_bnws,))
@@ -256,12 +259,32 @@ class Executor:
             self.l2_ws = E((ops.L2_PARTIALS,))
             self.gbuf, self.galias = {}, {}
             self.relu_scratch = {}
+            # d(out)/d(in) of a residual Add is the identity: an input consumed ONLY by the Add shares the
+            # Add output's gradient buffer (no copy kernel); multi-consumer inputs keep their own buffer
+            add_alias = {}
+            for op in self.ops:
+                if op.type == 'Add':
+                    for x_t in op.inputs:
+                        root = x_t
+                        while root in self.alias:
+                            root = self.alias[root]
+                        single = len(self._consumers(x_t)) == 1 and root.op.type not in ('Placeholder',)
+                        chain_single = True
+                        tt = x_t
+                        while tt in self.alias:
+                            tt = self.alias[tt]
+                            chain_single = chain_single and len(self._consumers(tt)) == 1
+                        if single and chain_single and root not in add_alias and root is not op.output:
+                            add_alias[root] = op.output
+                            break                              # at most one input per Add
             for op in self.ops:
                 t = op.output
                 if op.type == 'Placeholder':
                     continue
                 if t in self.alias:
                     self.galias[t] = self.alias[t]
+                elif t in add_alias:
+                    self.galias[t] = add_alias[t]
                 else:
                     self.gbuf[t] = E(t.shape)
                 if op.type in ('Conv2D', 'MatMul') and op in self.fused_act:
@@ -410,13 +433,16 @@ class Executor:
                         ops.act_minmax(y, slot)
                         ops.act_quant(y, self.aq_out[op], slot, self.act_quant['bits'][self.aq_index[op]])
             elif ty == 'MaxPool':
-                ops.maxpool_fwd(self.desc[op], self.T(op.inputs[0]), self.buf[op.output])
+                with self.timed('pool'):
+                    ops.maxpool_fwd(self.desc[op], self.T(op.inputs[0]), self.buf[op.output], self.pool_argmax.get(op))
             elif ty == 'Mean':
                 x = op.inputs[0]
                 n, h, w, c = x.shape
-                ops.global_avgpool_fwd(self.T(x), n, h * w, c, self.buf[op.output])
+                with self.timed('pool'):
+                    ops.global_avgpool_fwd(self.T(x), n, h * w, c, self.buf[op.output])
             elif ty == 'Add':
-                ops.add(self.T(op.inputs[0]), self.T(op.inputs[1]), self.buf[op.output])
+                with self.timed('add_fwd'):
+                    ops.add(self.T(op.inputs[0]), self.T(op.inputs[1]), self.buf[op.output])
             elif ty == 'Softmax':
                 ops.softmax_fwd(self.T(op.inputs[0]), self.buf[op.output])
             else:
@@ -484,16 +510,21 @@ class Executor:
             elif ty == 'MaxPool':
                 x_t = op.inputs[0]
                 gx, acc = self.grad_target(x_t)
-                ops.maxpool_bwd(self.desc[op], gy, self.T(x_t), self.buf[op.output], gx, acc)
+                with self.timed('pool'):
+                    ops.maxpool_bwd(self.desc[op], gy, self.pool_argmax[op], gx, acc)
             elif ty == 'Mean':
                 x_t = op.inputs[0]
                 n, h, w, c = x_t.shape
                 gx, acc = self.grad_target(x_t)
-                ops.global_avgpool_bwd(gy, n, h * w, c, gx, acc)
+                with self.timed('pool'):
+                    ops.global_avgpool_bwd(gy, n, h * w, c, gx, acc)
             elif ty == 'Add':
                 for x_t in op.inputs:
+                    if self.gkey(x_t) is self.gkey(op.output):
+                        continue                           # gradient buffer shared with the output (plan-time alias)
                     gx, acc = self.grad_target(x_t)
-                    ops.add(gy, None, gx, acc)
+                    with self.timed('add_bwd'):
+                        ops.add(gy, None, gx, acc)
             elif ty == 'Softmax':
                 x_t = op.inputs[0]
                 gx, acc = self.grad_target(x_t)

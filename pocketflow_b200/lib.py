@@ -55,8 +55,8 @@ SIGNATURES = {
     'pf_add': (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp]),
     'pf_relu_bwd': (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp]),
     'pf_colsum': (c_i32, [c_vp, c_i64, c_i32, c_vp, c_vp]),
-    'pf_maxpool_fwd': (c_i32, [c_vp, c_vp, c_vp, c_vp]),
-    'pf_maxpool_bwd': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
+    'pf_maxpool_fwd': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'pf_maxpool_bwd': (c_i32, [c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
     'pf_global_avgpool_fwd': (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
     'pf_global_avgpool_bwd': (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     'pf_softmax_fwd': (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp]),

@@ -473,12 +473,12 @@ def colsum(a, m, c, out):
     _lib.check(_lib.load().pf_colsum(_p(a), m, c, _p(out), _stream()), 'pf_colsum')
 
 
-def maxpool_fwd(d, x, y):
-    _lib.check(_lib.load().pf_maxpool_fwd(ctypes.byref(d), _p(x), _p(y), _stream()), 'pf_maxpool_fwd')
+def maxpool_fwd(d, x, y, argmax=None):
+    _lib.check(_lib.load().pf_maxpool_fwd(ctypes.byref(d), _p(x), _p(y), _p(argmax), _stream()), 'pf_maxpool_fwd')
 
 
-def maxpool_bwd(d, dy, x, y, dx, accumulate=False):
-    _lib.check(_lib.load().pf_maxpool_bwd(ctypes.byref(d), _p(dy), _p(x), _p(y), int(bool(accumulate)), _p(dx),
+def maxpool_bwd(d, dy, argmax, dx, accumulate=False):
+    _lib.check(_lib.load().pf_maxpool_bwd(ctypes.byref(d), _p(dy), _p(argmax), int(bool(accumulate)), _p(dx),
                                           _stream()), 'pf_maxpool_bwd')
 
 

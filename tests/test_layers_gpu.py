@@ -155,10 +155,11 @@ def test_maxpool(cfg):
     yd.backward(dy.double().permute(0, 3, 1, 2))
     d = ops.conv_desc(n, h, w, c, c, k, k, p, p, s, s, pt, pt)
     Y = torch.empty(n, p, p, c, device=DEV)
-    ops.maxpool_fwd(d, x.to(DEV), Y)
+    AM = torch.empty(n, p, p, c, dtype=torch.uint8, device=DEV)
+    ops.maxpool_fwd(d, x.to(DEV), Y, AM)
     close(Y, yd.permute(0, 2, 3, 1), 0.0)
     DX = torch.empty(n, h, w, c, device=DEV)
-    ops.maxpool_bwd(d, dy.to(DEV), x.to(DEV), Y, DX)
+    ops.maxpool_bwd(d, dy.to(DEV), AM, DX)
     close(DX, xd.grad.permute(0, 2, 3, 1), 1e-6)
 
 

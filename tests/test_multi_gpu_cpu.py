@@ -1,0 +1,117 @@
+"""Host-side logic of the data-parallel path on CPU: world_size-2 `gloo` process groups exercise the
+MultiGpuWrapper surface (utils/multi_gpu_wrapper.py here; /root/reference/utils/multi_gpu_wrapper.py:30-98),
+rank-sharded synthetic data, the one-flat-buffer gradient exchange with the Horovod average folded
+into grad_scale, and the batch-size dependent schedules."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import pf_oracle as O
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, fn, ret):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR='127.0.0.1',
+                      MASTER_PORT=str(port))
+    from pocketflow_b200.utils.multi_gpu_wrapper import MultiGpuWrapper as mgw
+    mgw.init(backend='gloo')
+    try:
+        ret[rank] = fn(rank, world, mgw)
+    finally:
+        dist.destroy_process_group()
+
+
+def run_ranks(fn, world=2):
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), fn, ret), nprocs=world, join=True)
+    return [ret[r] for r in range(world)]
+
+
+def _collectives(rank, world, mgw):
+    assert mgw.size() == world and mgw.rank() == rank and mgw.local_rank() == rank
+    flat = torch.arange(10, dtype=torch.float32) * (rank + 1)
+    mgw.allreduce_flat_(flat)
+    p = torch.full((5,), float(rank))
+    mgw.broadcast_global_variables([p], 0)
+    mgw.barrier()
+    return flat.numpy().tolist(), p.numpy().tolist()
+
+
+def test_allreduce_broadcast_barrier():
+    out = run_ranks(_collectives)
+    for flat, p in out:
+        assert flat == (np.arange(10) * 3.0).tolist()      # sum over ranks 1x + 2x
+        assert p == [0.0] * 5                               # rank 0's values everywhere
+
+
+def _dp_step(rank, world, mgw):
+    """Two replicas, different data, one flat all-reduce, optimizer with grad_scale = 1/world:
+    replicas stay bit-identical and equal the oracle's update with the averaged gradient."""
+    rng = np.random.RandomState(0)
+    w0 = rng.randn(64).astype(np.float32)
+    acc0 = np.zeros(64, np.float32)
+    g_all = [np.random.RandomState(100 + r).randn(64).astype(np.float32) for r in range(world)]
+    flat = torch.from_numpy(g_all[rank].copy())
+    mgw.allreduce_flat_(flat)
+    w1, a1 = O.momentum_step(w0, acc0, flat.numpy(), 0.1, 0.9, wd=1e-4, grad_scale=1.0 / world)
+    return w1.tolist(), (g_all[0] + g_all[1]).tolist(), flat.numpy().tolist()
+
+
+def test_data_parallel_update_is_replicated_and_averaged():
+    out = run_ranks(_dp_step)
+    assert out[0][0] == out[1][0]                           # replicas in sync, bit for bit
+    assert out[0][2] == out[0][1] == out[1][2]              # the collective is a plain sum
+    # grad_scale=1/2 of the sum == Horovod's average for power-of-two worlds (exact in fp32)
+    g_avg = (np.array(out[0][1], np.float32) / np.float32(2)).astype(np.float32)
+    w_ref, _ = O.momentum_step(np.random.RandomState(0).randn(64).astype(np.float32), np.zeros(64, np.float32),
+                               g_avg, 0.1, 0.9, wd=1e-4)
+    assert np.array_equal(np.array(out[0][0], np.float32), w_ref)
+
+
+def _sharded_data(rank, world, mgw):
+    from pocketflow_b200.flags import FLAGS
+    from pocketflow_b200.datasets.cifar10_dataset import Cifar10Dataset
+    from pocketflow_b200 import graph as G
+    FLAGS.reset()
+    FLAGS.enbl_multi_gpu, FLAGS.batch_size = True, 4
+    it = Cifar10Dataset(is_train=True).build()
+    img, lab = it.next_batch()
+    # schedules see the GLOBAL batch (nets/resnet_at_cifar10.py:120-122, utils/lrn_rate_utils.py:40)
+    from pocketflow_b200.nets import resnet_at_cifar10 as R
+    FLAGS.batch_size = 128
+    lr_fn, nb_iters = R.ModelHelper().setup_lrn_rate(None)
+    return float(img.sum()), lab.argmax(1).tolist(), lr_fn(0), nb_iters
+
+
+def test_rank_sharded_data_and_scaled_schedule():
+    out = run_ranks(_sharded_data)
+    assert out[0][0] != out[1][0] and out[0][1] != out[1][1]      # every rank draws its own slice
+    for _, _, lr0, nb in out:
+        assert abs(lr0 - 0.1 * 256 / 128) < 1e-12                  # LR x world (batch_size_norm 128)
+        assert nb == int(50000 * 250 / 256)                        # iterations / world
+
+
+def test_single_process_wrapper_defaults():
+    from pocketflow_b200.utils.multi_gpu_wrapper import MultiGpuWrapper as mgw
+    assert mgw.size() == 1 and mgw.rank() == 0
+    t = torch.ones(3)
+    assert mgw.allreduce_flat_(t) is t and t.tolist() == [1, 1, 1]
+    env = {k: os.environ.pop(k) for k in ('RANK',) if k in os.environ}
+    try:
+        with pytest.raises(NameError):
+            mgw.init()
+    finally:
+        os.environ.update(env)

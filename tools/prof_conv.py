@@ -1,0 +1,28 @@
+"""One tcgen05 conv launch per pass for ncu (tools/gpu_prof_conv.sh)."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pocketflow_b200 import ops  # noqa: E402
+
+SHAPES = {'s3': (256, 14, 14, 256, 256, 3, 3, 1, 1), 's1': (256, 56, 56, 64, 256, 1, 1, 1, 0),
+          's2': (256, 28, 28, 128, 128, 3, 3, 1, 1)}
+dev = torch.device('cuda:0')
+for name in sys.argv[1:]:
+    n, h, w, c, k, r, s, st, pd = SHAPES[name]
+    p = (h + 2 * pd - r) // st + 1
+    d = ops.conv_desc(n, h, w, c, k, r, s, p, p, st, st, pd, pd)
+    x = torch.randn(n, h, w, c, device=dev)
+    wt = torch.randn(r, s, c, k, device=dev) * 0.05
+    y = torch.empty(n, p, p, k, device=dev)
+    dy = torch.randn(n, p, p, k, device=dev)
+    dw = torch.empty_like(wt)
+    tw = ops.TcWeights(d, dev)
+    tw.prepare(wt)
+    ws = torch.empty(max(ops.conv2d_tc_wgrad_workspace_floats(d), 4), device=dev)
+    for _ in range(3):
+        ops.conv2d_tc_fwd(d, x, tw, None, False, y)
+        ops.conv2d_tc_wgrad(d, x, dy, ws, dw)
+    torch.cuda.synchronize()
