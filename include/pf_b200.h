@@ -248,8 +248,10 @@ int pf_conv2d_tc_supported(const pf_conv_desc* d);
 int64_t pf_conv2d_tc_weight_elems(const pf_conv_desc* d, int dgrad);
 int pf_conv2d_tc_prep_weight(const pf_conv_desc* d, const float* w_dev, void* fwd_hi_dev, void* fwd_lo_dev,
                              void* dgrad_hi_dev, void* dgrad_lo_dev, void* stream);
+/* y = conv(x, w) (+ bias) (relu) (+ residual_dev: the fused residual add of resnet_model.py:199,314;
+ * NULL = none) */
 int pf_conv2d_tc_fwd(const pf_conv_desc* d, const float* x_dev, const void* w_hi_dev, const void* w_lo_dev,
-                     const float* bias_dev, int relu, float* y_dev, void* stream);
+                     const float* bias_dev, int relu, const float* residual_dev, float* y_dev, void* stream);
 int pf_conv2d_tc_dgrad(const pf_conv_desc* d, const float* dy_dev, const void* wd_hi_dev, const void* wd_lo_dev,
                        int accumulate, float* dx_dev, void* stream);
 /* dw = x (*) dy on the tensor cores (MN-major operands, split-K with a fixed-order reduction).

@@ -44,13 +44,22 @@ __device__ __forceinline__ void split4(const float4 v, uint2& hi, uint2& lo) {
   lo.y = pack_bf16(v.z - __bfloat162float(hz), v.w - __bfloat162float(hw));
 }
 
-// MODE 0 = fwd (gather x), 1 = dgrad (gather dy)
-template <int MODE>
-__global__ void __launch_bounds__(kThreads, 1)
+// MODE 0 = fwd (gather x), 1 = dgrad (gather dy).
+// Producers (8 warps): 8 lanes cover one row's 64-channel chunk (256 contiguous bytes of NHWC fp32):
+// thread t owns bytes [32*(t&7), +32) of rows (t>>3) + 32*i, i < 4 — a warp load touches 4 rows x 256 B
+// of fully used lines (the first version's one-row-per-thread mapping saturated the L1 tag stage:
+// ncu l1tex 79 %, 32 tag lookups per load instruction).  8 channels -> one 16-byte bf16 chunk each for
+// the hi and the lo tile.  A is double-buffered in registers one k-stage ahead (ping-pong sets, no
+// copies); B (pre-split weights, no conversion) goes global -> shared with cp.async straight into the
+// swizzled tile, overlapping the A conversion.
+// NPW = producer warps: 8 (1 CTA/SM, A ping-pong in registers; large K) or 4 (2-3 CTAs/SM so that one CTA's
+// loads / epilogue overlap another's MMAs; the small-K, output-bound 1x1 layers of the early stages).
+template <int MODE, int NPW>
+__global__ void __launch_bounds__(NPW * 32 + 32, NPW == 8 ? 1 : 2)
 conv_tc_kernel(const float* __restrict__ src, const __nv_bfloat16* __restrict__ b_hi,
                const __nv_bfloat16* __restrict__ b_lo, float* __restrict__ out, TcGeom g, int M, int Ng,
                int Kdim, int Kpad, int BN, int n_stages, int accumulate, const float* __restrict__ bias,
-               int relu) {
+               int relu, const float* __restrict__ residual) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const uint32_t a_bytes = TM * 128, b_bytes = (uint32_t)BN * 128;
@@ -65,145 +74,192 @@ conv_tc_kernel(const float* __restrict__ src, const __nv_bfloat16* __restrict__ 
 
   if (tid == 0) {
     for (int s = 0; s < n_stages; ++s) {
-      mbar_init(&full_bar[s], kProducerThreads);
+      mbar_init(&full_bar[s], NPW * 32);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(&accum_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(&tmem_base_s, tmem_cols);
+  constexpr int kProd = NPW * 32;          // producer threads
+  constexpr int ROWS = TM * 8 / kProd;     // A rows per thread: 4 (NPW = 8) or 8 (NPW = 4)
+  constexpr int RSTEP = kProd / 8;         // row stride between a thread's rows: 32 or 16 (multiples of 8)
+  if (warp == NPW) tmem_alloc(&tmem_base_s, tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  if (warp < 8) {
-    // ======================= producers: two threads per GEMM row =======================
-    const int row = tid >> 1, half = tid & 1;
-    const int m = m0 + row;
-    const bool row_ok = m < M;
-    const int CC = (MODE == 0) ? g.C : g.K;  // channels of the gathered tensor
-    int pn = 0, y0 = 0, x0 = 0;
-    if (row_ok) {
+  if (warp < NPW) {
+    const int l8 = tid & 7, rgrp = tid >> 3;          // 32-byte slice of the row, row group
+    const int CC = (MODE == 0) ? g.C : g.K;           // channels of the gathered tensor
+    int pn[ROWS], yx[ROWS];                           // per row: image index (< 0: beyond M), packed (y0, x0)
+    {
       const int hw = (MODE == 0) ? g.P * g.Q : g.H * g.W;
       const int wq = (MODE == 0) ? g.Q : g.W;
-      pn = m / hw;
-      const int rem = m - pn * hw;
-      const int y = rem / wq, x = rem - y * wq;
-      if (MODE == 0) {
-        y0 = y * g.sh - g.pt;
-        x0 = x * g.sw - g.pl;
-      } else {
-        y0 = y + g.pt;
-        x0 = x + g.pl;
+#pragma unroll
+      for (int i = 0; i < ROWS; ++i) {
+        const int m = m0 + rgrp + RSTEP * i;
+        pn[i] = -1;
+        yx[i] = 0;
+        if (m < M) {
+          const int n_ = m / hw;
+          const int rem = m - n_ * hw;
+          const int y = rem / wq, x = rem - y * wq;
+          pn[i] = n_;
+          const int y0 = (MODE == 0) ? y * g.sh - g.pt : y + g.pt;
+          const int x0 = (MODE == 0) ? x * g.sw - g.pl : x + g.pl;
+          yx[i] = (int)(((uint32_t)(y0 + 32768) << 16) | (uint32_t)(x0 + 32768));
+        }
       }
     }
-    const int bn = n0 + row;             // this thread pair's B row (output channel / input channel)
-    const bool b_ok = row < BN && bn < Ng;
-    const uint32_t sw = (uint32_t)(row & 7);
-    const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
-    for (int ks = 0; ks < nk; ++ks) {
-      const int s = ks % n_stages;
-      // ---- issue every global load of this stage first (16 independent 16-byte loads per thread)
-      float4 av[2][4];
+    const bool unit_stride = g.sh == 1 && g.sw == 1;
+    const uint32_t sw = (uint32_t)(rgrp & 7);         // (row & 7) for every row of this thread (rows differ by 32)
+    const uint32_t chunk_off = (((uint32_t)l8) ^ sw) << 4;
+    auto issue_loads_a = [&](int ks, float4 (&av)[2 * ROWS]) {
+      const int kk = ks * BK + (l8 >> 1) * 16;        // this lane's 16-channel sub-chunk: inside one filter tap
+      const bool kok = kk < Kdim;
+      const int tap = kk / CC, c = kk - tap * CC + (l8 & 1) * 8;
+      const int r = tap / g.S, q = tap - r * g.S;
 #pragma unroll
-      for (int jj = 0; jj < 2; ++jj) {
-        const int kk = ks * BK + (half * 2 + jj) * 16;   // 16 channels inside one filter tap (CC % 16 == 0)
+      for (int i = 0; i < ROWS; ++i) {
         const float* p = nullptr;
-        if (row_ok && kk < Kdim) {
-          const int tap = kk / CC, c = kk - tap * CC;
-          const int r = tap / g.S, q = tap - r * g.S;
+        if (kok && pn[i] >= 0) {
+          const int y0 = (int)((uint32_t)yx[i] >> 16) - 32768, x0 = (int)((uint32_t)yx[i] & 0xFFFFu) - 32768;
           if (MODE == 0) {
             const int ih = y0 + r, iw = x0 + q;
-            if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) p = src + (((size_t)pn * g.H + ih) * g.W + iw) * g.C + c;
+            if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) p = src + (((size_t)pn[i] * g.H + ih) * g.W + iw) * g.C + c;
           } else {
             const int th = y0 - r, tw = x0 - q;
             if (th >= 0 && tw >= 0) {
-              const int oh = th / g.sh, ow = tw / g.sw;
-              if (oh * g.sh == th && ow * g.sw == tw && oh < g.P && ow < g.Q)
-                p = src + (((size_t)pn * g.P + oh) * g.Q + ow) * g.K + c;
+              if (unit_stride) {
+                if (th < g.P && tw < g.Q) p = src + (((size_t)pn[i] * g.P + th) * g.Q + tw) * g.K + c;
+              } else {
+                const int oh = th / g.sh, ow = tw / g.sw;
+                if (oh * g.sh == th && ow * g.sw == tw && oh < g.P && ow < g.Q)
+                  p = src + (((size_t)pn[i] * g.P + oh) * g.Q + ow) * g.K + c;
+              }
             }
           }
         }
-#pragma unroll
-        for (int v = 0; v < 4; ++v)
-          av[jj][v] = p ? __ldg(reinterpret_cast<const float4*>(p) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+        av[2 * i] = p ? __ldg(reinterpret_cast<const float4*>(p)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        av[2 * i + 1] = p ? __ldg(reinterpret_cast<const float4*>(p) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      uint4 bh[4], bl[4];
-      {
-        const uint4* gh = reinterpret_cast<const uint4*>(b_hi + (size_t)bn * Kpad + (size_t)ks * BK) + half * 4;
-        const uint4* gl = reinterpret_cast<const uint4*>(b_lo + (size_t)bn * Kpad + (size_t)ks * BK) + half * 4;
+    };
+    auto issue_b_async = [&](int ks, uint8_t* st) {
+      // rows rgrp + RSTEP*i of the BN x 128-byte tile, 16-byte chunk l8, hi and lo; zero-fill out-of-range rows
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          bh[c] = b_ok ? __ldg(gh + c) : z4;
-          bl[c] = b_ok ? __ldg(gl + c) : z4;
+      for (int i = 0; i < ROWS; ++i) {
+        const int br = rgrp + RSTEP * i;
+        if (br < BN) {
+          const bool ok = n0 + br < Ng;
+          const size_t off = (size_t)(ok ? n0 + br : 0) * Kpad + (size_t)ks * BK + l8 * 8;
+          const uint32_t dst = smem_u32(st + 2 * a_bytes + (size_t)br * 128 + chunk_off);
+          const uint32_t nbytes = ok ? 16u : 0u;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(b_hi + off), "r"(nbytes) : "memory");
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + b_bytes), "l"(b_lo + off), "r"(nbytes) : "memory");
         }
       }
-      // ---- the smem slot must be free before it is overwritten (the wait overlaps the loads above)
-      mbar_wait(&empty_bar[s], (((uint32_t)(ks / n_stages)) & 1u) ^ 1u);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto store_a = [&](uint8_t* st, const float4 (&av)[2 * ROWS]) {
+#pragma unroll
+      for (int i = 0; i < ROWS; ++i) {
+        uint2 h0, l0, h1, l1;
+        split4(av[2 * i], h0, l0);
+        split4(av[2 * i + 1], h1, l1);
+        uint8_t* rowp = st + (size_t)(rgrp + RSTEP * i) * 128 + chunk_off;
+        *reinterpret_cast<uint4*>(rowp) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+        *reinterpret_cast<uint4*>(rowp + a_bytes) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+      }
+    };
+    auto do_stage = [&](int ks, const float4 (&av)[2 * ROWS]) {
+      const int s = ks % n_stages;
+      mbar_wait(&empty_bar[s], (((uint32_t)(ks / n_stages)) & 1u) ^ 1u);   // slot free?
       uint8_t* st = smem + (size_t)s * stage_bytes;
-      uint8_t* a_hi_row = st + row * 128;
-      uint8_t* a_lo_row = st + a_bytes + row * 128;
-#pragma unroll
-      for (int jj = 0; jj < 2; ++jj) {
-        uint2 h[4], l[4];
-#pragma unroll
-        for (int v = 0; v < 4; ++v) split4(av[jj][v], h[v], l[v]);
-        // 16 bf16 = two 16-byte chunks: chunk ids 2j, 2j+1, XOR-swizzled with (row & 7)
-        const int j = half * 2 + jj;
-        const uint32_t c0 = (((uint32_t)(2 * j)) ^ sw) << 4, c1 = (((uint32_t)(2 * j + 1)) ^ sw) << 4;
-        *reinterpret_cast<uint4*>(a_hi_row + c0) = make_uint4(h[0].x, h[0].y, h[1].x, h[1].y);
-        *reinterpret_cast<uint4*>(a_hi_row + c1) = make_uint4(h[2].x, h[2].y, h[3].x, h[3].y);
-        *reinterpret_cast<uint4*>(a_lo_row + c0) = make_uint4(l[0].x, l[0].y, l[1].x, l[1].y);
-        *reinterpret_cast<uint4*>(a_lo_row + c1) = make_uint4(l[2].x, l[2].y, l[3].x, l[3].y);
-      }
-      if (row < BN) {
-        uint8_t* b_hi_row = st + 2 * a_bytes + row * 128;
-        uint8_t* b_lo_row = b_hi_row + b_bytes;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const uint32_t off = (((uint32_t)(half * 4 + c)) ^ sw) << 4;
-          *reinterpret_cast<uint4*>(b_hi_row + off) = bh[c];
-          *reinterpret_cast<uint4*>(b_lo_row + off) = bl[c];
+      issue_b_async(ks, st);
+      store_a(st, av);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      fence_proxy_async_smem();   // generic-proxy + cp.async writes -> visible to the tensor core (async proxy)
+      mbar_arrive(&full_bar[s]);
+    };
+    if (NPW == 8) {
+      float4 a0[2 * ROWS], a1[2 * ROWS];
+      issue_loads_a(0, a0);
+      for (int ks = 0; ks < nk; ks += 2) {
+        if (ks + 1 < nk) issue_loads_a(ks + 1, a1);
+        do_stage(ks, a0);
+        if (ks + 1 < nk) {
+          if (ks + 2 < nk) issue_loads_a(ks + 2, a0);
+          do_stage(ks + 1, a1);
         }
       }
-      fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
-      mbar_arrive(&full_bar[s]);
+    } else {
+      for (int ks = 0; ks < nk; ++ks) {
+        float4 a0[2 * ROWS];
+        issue_loads_a(ks, a0);
+        do_stage(ks, a0);
+      }
     }
-    // ======================= epilogue: TMEM -> registers -> global =======================
-    // warp w owns TMEM lanes [32*(w%4), +32); warps 0-3 take the low half of the columns, 4-7 the high half
+    // ======================= epilogue: TMEM -> registers -> smem -> coalesced global =======================
+    // warp w owns TMEM lanes [32*(w%4), +32); warps 0-3 take the low half of the columns, 4-7 the high half.
+    // The tile is staged row-major in the (now idle) stage memory so that global stores are full rows.
     mbar_wait(&accum_bar, 0);
     tc_fence_after();
-    const int erow = (warp & 3) * 32 + (tid & 31);
-    const int em = m0 + erow;
-    const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
-    const int cbeg = (BN >= 64) ? (warp >> 2) * (BN / 2) : 0;
-    const int cend = (BN >= 64) ? cbeg + BN / 2 : ((warp >> 2) == 0 ? BN : 0);
-    for (int c0 = cbeg; c0 < cend; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_base + lane_base + (uint32_t)c0, r);
-      if (em < M) {
-        float* o = out + (size_t)em * Ng + n0 + c0;
+    float* stile = reinterpret_cast<float*>(smem);
+    const int pitch = BN + 4;                       // +16 B: conflict-free 128-bit row writes
+    {
+      const int erow = (warp & 3) * 32 + (tid & 31);
+      const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
+      const int cbeg = (NPW == 8 && BN >= 64) ? (warp >> 2) * (BN / 2) : 0;
+      const int cend = (NPW == 8) ? ((BN >= 64) ? cbeg + BN / 2 : ((warp >> 2) == 0 ? BN : 0)) : BN;
+      for (int c0 = cbeg; c0 < cend; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + lane_base + (uint32_t)c0, r);
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          if (n0 + c0 + j + 3 < Ng && c0 + j + 3 < BN) {
-            float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                   __uint_as_float(r[j + 3]));
-            if (bias) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + j));
-              v.x = __fadd_rn(v.x, bb.x); v.y = __fadd_rn(v.y, bb.y); v.z = __fadd_rn(v.z, bb.z); v.w = __fadd_rn(v.w, bb.w);
-            }
-            if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-            if (accumulate) {
-              const float4 old = *reinterpret_cast<const float4*>(o + j);
-              v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
-            }
-            *reinterpret_cast<float4*>(o + j) = v;
+        for (int j = 0; j < 32; j += 4)
+          if (c0 + j < BN)
+            *reinterpret_cast<uint4*>(stile + (size_t)erow * pitch + c0 + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(NPW * 32) : "memory");   // the epilogue (= producer) warps only
+    {
+      // full rows to global, 4 independent 16-byte pieces per thread per round so that the residual /
+      // accumulate loads of a round are all in flight before the first one is consumed
+      const int vec_per_row = BN >> 2;
+      const int total = TM * vec_per_row;
+      const float* extra = residual ? residual : (accumulate ? out : nullptr);
+      for (int e0 = tid; e0 < total; e0 += 4 * kProd) {
+        float4 xv[4];
+        size_t goff[4];
+        int sidx[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = e0 + u * kProd;
+          const int rr = e / vec_per_row, cv = (e - rr * vec_per_row) << 2;
+          const int mm = m0 + rr, nn = n0 + cv;
+          ok[u] = e < total && mm < M && nn + 3 < Ng;
+          goff[u] = (size_t)mm * Ng + nn;
+          sidx[u] = rr * pitch + cv;
+          xv[u] = (ok[u] && extra) ? *reinterpret_cast<const float4*>(extra + goff[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (!ok[u]) continue;
+          float4 v = *reinterpret_cast<const float4*>(stile + sidx[u]);
+          if (bias) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + (goff[u] % (size_t)Ng)));
+            v.x = __fadd_rn(v.x, bb.x); v.y = __fadd_rn(v.y, bb.y); v.z = __fadd_rn(v.z, bb.z); v.w = __fadd_rn(v.w, bb.w);
           }
+          if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+          if (extra) {   // fused residual add (resnet_model.py:199,314) or dx += (gradient accumulation)
+            v.x = __fadd_rn(v.x, xv[u].x); v.y = __fadd_rn(v.y, xv[u].y); v.z = __fadd_rn(v.z, xv[u].z); v.w = __fadd_rn(v.w, xv[u].w);
+          }
+          *reinterpret_cast<float4*>(out + goff[u]) = v;
         }
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == NPW) {
     // ======================= MMA issuer: one elected thread =======================
     if ((tid & 31) == 0) {
       const uint32_t idesc = make_idesc_bf16(TM, BN, 0, 0);
@@ -230,7 +286,7 @@ conv_tc_kernel(const float* __restrict__ src, const __nv_bfloat16* __restrict__ 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem_base, tmem_cols);
+  if (warp == NPW) tmem_dealloc(tmem_base, tmem_cols);
 }
 
 
@@ -273,88 +329,69 @@ conv_tc_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, 
   const int mbA = TM / 64, mbB = BN / 64;
 
   if (warp < 8) {
-    // producers: thread t -> pixel (t / 4) of the stage, quarter (t % 4) of the MN extent
-    const int pl = tid >> 2, quarter = tid & 3;
-    // A: kf sub-chunks [m0 + 32*quarter + 16*jj, +16): tap / channel decode is stage-invariant
-    int a_r[2], a_q[2], a_c[2];
-    bool a_ok[2];
+    // producers: 16 lanes cover one pixel's 128-wide MN extent (512 contiguous bytes of NHWC fp32), thread t
+    // owns elements [8*(t&15), +8) of pixels (t>>4) + 16*i, i < 4, of BOTH operands: 8 fp32 -> one 16-byte
+    // bf16 chunk each for the hi and lo tiles.
+    const int l16 = tid & 15, pgrp = tid >> 4;
+    // A: kf = m0 + 8*l16 .. +7 lies inside one filter tap (C % 16 == 0): decode is stage-invariant
+    const int kf = m0 + l16 * 8;
+    const bool a_ok = kf < Mtot;
+    const int a_tap = kf / g.C, a_c = kf - a_tap * g.C;
+    const int a_r = a_tap / g.S, a_q = a_tap - a_r * g.S;
+    // B: couts n0 + 8*l16 .. +7
+    const int bco = n0 + l16 * 8;
+    const bool b_okc = l16 * 8 < BN && bco < g.K;
+    const uint32_t e = (uint32_t)(l16 * 8);                 // element offset inside the 128-wide tile
+    const uint32_t mblk = e >> 6, chunk = (e & 63) >> 3;
+    auto issue_loads = [&](int ks, float4 (&av)[8], float4 (&bv)[8]) {
 #pragma unroll
-    for (int jj = 0; jj < 2; ++jj) {
-      const int kf = m0 + quarter * 32 + jj * 16;
-      a_ok[jj] = kf < Mtot;
-      const int tap = kf / g.C;
-      a_c[jj] = kf - tap * g.C;
-      a_r[jj] = tap / g.S;
-      a_q[jj] = tap - a_r[jj] * g.S;
-    }
-    // B: cout sub-range [n0 + (BN/4)*quarter, +BN/4): BN/16 float4 per thread (8 for BN = 128, 4 for BN = 64)
-    const int bvec = BN / 16;
-    const int bcol = quarter * (BN / 4);
+      for (int i = 0; i < 4; ++i) {
+        const int pix = pbeg + ks * BK + pgrp + 16 * i;
+        const float* pa = nullptr;
+        const float* pb = nullptr;
+        if (pix < pend) {
+          const int pq = g.P * g.Q;
+          const int pn = pix / pq;
+          const int rem = pix - pn * pq;
+          const int oh = rem / g.Q, ow = rem - oh * g.Q;
+          if (a_ok) {
+            const int ih = oh * g.sh - g.pt + a_r, iw = ow * g.sw - g.pl + a_q;
+            if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) pa = x + (((size_t)pn * g.H + ih) * g.W + iw) * g.C + a_c;
+          }
+          if (b_okc) pb = dy + (size_t)pix * g.K + bco;
+        }
+        av[2 * i] = pa ? __ldg(reinterpret_cast<const float4*>(pa)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        av[2 * i + 1] = pa ? __ldg(reinterpret_cast<const float4*>(pa) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+        bv[2 * i] = pb ? __ldg(reinterpret_cast<const float4*>(pb)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        bv[2 * i + 1] = pb ? __ldg(reinterpret_cast<const float4*>(pb) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    auto store_stage = [&](int s, const float4 (&av)[8], const float4 (&bv)[8]) {
+      uint8_t* st = smem + (size_t)s * stage_bytes;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t k = (uint32_t)(pgrp + 16 * i), k8 = k & 7, kb = k >> 3;
+        uint2 h0, l0, h1, l1;
+        split4(av[2 * i], h0, l0);
+        split4(av[2 * i + 1], h1, l1);
+        uint8_t* hi = st + (size_t)(kb * (uint32_t)(mbA * 8) + mblk * 8 + k8) * 128 + ((chunk ^ k8) << 4);
+        *reinterpret_cast<uint4*>(hi) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+        *reinterpret_cast<uint4*>(hi + a_bytes) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+        if (l16 * 8 < BN) {
+          split4(bv[2 * i], h0, l0);
+          split4(bv[2 * i + 1], h1, l1);
+          uint8_t* bh = st + 2 * a_bytes + (size_t)(kb * (uint32_t)(mbB * 8) + mblk * 8 + k8) * 128 + ((chunk ^ k8) << 4);
+          *reinterpret_cast<uint4*>(bh) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+          *reinterpret_cast<uint4*>(bh + b_bytes) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+        }
+      }
+    };
     for (int ks = 0; ks < nk; ++ks) {
       const int s = ks % n_stages;
-      const int pix = pbeg + ks * BK + pl;
-      const bool pok = pix < pend;
-      int pn = 0, oh = 0, ow = 0;
-      if (pok) {
-        const int pq = g.P * g.Q;
-        pn = pix / pq;
-        const int rem = pix - pn * pq;
-        oh = rem / g.Q;
-        ow = rem - oh * g.Q;
-      }
-      float4 av[2][4], bv[8];
-#pragma unroll
-      for (int jj = 0; jj < 2; ++jj) {
-        const float* p = nullptr;
-        if (pok && a_ok[jj]) {
-          const int ih = oh * g.sh - g.pt + a_r[jj], iw = ow * g.sw - g.pl + a_q[jj];
-          if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) p = x + (((size_t)pn * g.H + ih) * g.W + iw) * g.C + a_c[jj];
-        }
-#pragma unroll
-        for (int v = 0; v < 4; ++v)
-          av[jj][v] = p ? __ldg(reinterpret_cast<const float4*>(p) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      {
-        const float* p = (pok && n0 + bcol < g.K) ? dy + (size_t)pix * g.K + n0 + bcol : nullptr;
-#pragma unroll
-        for (int v = 0; v < 8; ++v)
-          bv[v] = (p && v < bvec) ? __ldg(reinterpret_cast<const float4*>(p) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      float4 av[8], bv[8];
+      issue_loads(ks, av, bv);
       mbar_wait(&empty_bar[s], (((uint32_t)(ks / n_stages)) & 1u) ^ 1u);
-      uint8_t* st = smem + (size_t)s * stage_bytes;
-      const uint32_t k8 = (uint32_t)(pl & 7), kb = (uint32_t)(pl >> 3);
-      // ---- A: element e = 32*quarter + 16*jj + 4*v .. of the 128-wide kf tile
-#pragma unroll
-      for (int jj = 0; jj < 2; ++jj) {
-        uint2 h[4], l[4];
-#pragma unroll
-        for (int v = 0; v < 4; ++v) split4(av[jj][v], h[v], l[v]);
-        const uint32_t e = (uint32_t)(quarter * 32 + jj * 16);
-        const uint32_t rowi = kb * (uint32_t)(mbA * 8) + (e >> 6) * 8 + k8;
-        const uint32_t ch = (e & 63) >> 3;   // first of two 16-byte chunks
-        uint8_t* hi = st + rowi * 128;
-        uint8_t* lo = hi + a_bytes;
-        *reinterpret_cast<uint4*>(hi + (((ch) ^ k8) << 4)) = make_uint4(h[0].x, h[0].y, h[1].x, h[1].y);
-        *reinterpret_cast<uint4*>(hi + (((ch + 1) ^ k8) << 4)) = make_uint4(h[2].x, h[2].y, h[3].x, h[3].y);
-        *reinterpret_cast<uint4*>(lo + (((ch) ^ k8) << 4)) = make_uint4(l[0].x, l[0].y, l[1].x, l[1].y);
-        *reinterpret_cast<uint4*>(lo + (((ch + 1) ^ k8) << 4)) = make_uint4(l[2].x, l[2].y, l[3].x, l[3].y);
-      }
-      // ---- B: element e = bcol + 4*v of the BN-wide cout tile; two float4 make one 16-byte bf16 chunk
-#pragma unroll
-      for (int v = 0; v < 8; v += 2) {
-        if (v < bvec) {
-          uint2 h0, l0, h1, l1;
-          split4(bv[v], h0, l0);
-          split4(bv[v + 1], h1, l1);
-          const uint32_t e = (uint32_t)(bcol + v * 4);
-          const uint32_t rowi = kb * (uint32_t)(mbB * 8) + (e >> 6) * 8 + k8;
-          const uint32_t ch = (e & 63) >> 3;
-          uint8_t* hi = st + 2 * a_bytes + rowi * 128;
-          uint8_t* lo = hi + b_bytes;
-          *reinterpret_cast<uint4*>(hi + ((ch ^ k8) << 4)) = make_uint4(h0.x, h0.y, h1.x, h1.y);
-          *reinterpret_cast<uint4*>(lo + ((ch ^ k8) << 4)) = make_uint4(l0.x, l0.y, l1.x, l1.y);
-        }
-      }
+      store_stage(s, av, bv);
       fence_proxy_async_smem();
       mbar_arrive(&full_bar[s]);
     }
@@ -476,7 +513,7 @@ inline int pad64(int64_t k) { return (int)((k + 63) / 64 * 64); }
 
 template <int MODE>
 int launch_tc(const TcGeom& g, const float* src, const void* b_hi, const void* b_lo, float* out, int accumulate,
-              const float* bias, int relu, cudaStream_t st, const char* who) {
+              const float* bias, int relu, const float* residual, cudaStream_t st, const char* who) {
   const int64_t M64 = (MODE == 0) ? (int64_t)g.N * g.P * g.Q : (int64_t)g.N * g.H * g.W;
   PF_REQUIRE(M64 < (1ll << 31), "%s: too many rows", who);
   const int M = (int)M64;
@@ -487,12 +524,22 @@ int launch_tc(const TcGeom& g, const float* src, const void* b_hi, const void* b
   const int nk = Kpad / BK;
   int stages = nk < 3 ? (nk < 2 ? 1 : 2) : 3;
   if (BN <= 64 && nk >= 4) stages = 4;
-  const size_t smem = (size_t)stages * (2 * TM * 128 + 2 * BN * 128) + 1024;
-  auto kern = conv_tc_kernel<MODE>;
-  PF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  size_t smem = (size_t)stages * (2 * TM * 128 + 2 * BN * 128);
+  const size_t epi = (size_t)TM * (BN + 4) * 4;          // the epilogue stages the fp32 tile in the same memory
+  if (smem < epi) smem = epi;
+  smem += 1024;
   dim3 grid((M + TM - 1) / TM, (Ng + BN - 1) / BN);
-  kern<<<grid, kThreads, smem, st>>>(src, (const __nv_bfloat16*)b_hi, (const __nv_bfloat16*)b_lo, out, g, M, Ng,
-                                     Kdim, Kpad, BN, stages, accumulate, bias, relu);
+  if (nk <= 2) {
+    auto kern = conv_tc_kernel<MODE, 4>;
+    PF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    kern<<<grid, 4 * 32 + 32, smem, st>>>(src, (const __nv_bfloat16*)b_hi, (const __nv_bfloat16*)b_lo, out, g, M, Ng,
+                                          Kdim, Kpad, BN, stages, accumulate, bias, relu, residual);
+  } else {
+    auto kern = conv_tc_kernel<MODE, 8>;
+    PF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    kern<<<grid, 8 * 32 + 32, smem, st>>>(src, (const __nv_bfloat16*)b_hi, (const __nv_bfloat16*)b_lo, out, g, M, Ng,
+                                          Kdim, Kpad, BN, stages, accumulate, bias, relu, residual);
+  }
   PF_CHECK_LAUNCH(who);
   return PF_OK;
 }
@@ -533,7 +580,7 @@ int pf_conv2d_tc_prep_weight(const pf_conv_desc* d, const float* w_dev, void* fw
 }
 
 int pf_conv2d_tc_fwd(const pf_conv_desc* d, const float* x_dev, const void* w_hi_dev, const void* w_lo_dev,
-                     const float* bias_dev, int relu, float* y_dev, void* stream) {
+                     const float* bias_dev, int relu, const float* residual_dev, float* y_dev, void* stream) {
   TcGeom g;
   int rc = tc_geom(d, &g, "pf_conv2d_tc_fwd");
   if (rc) return rc;
@@ -541,7 +588,9 @@ int pf_conv2d_tc_fwd(const pf_conv_desc* d, const float* x_dev, const void* w_hi
   PF_REQUIRE(x_dev && w_hi_dev && w_lo_dev && y_dev, "pf_conv2d_tc_fwd: null pointer");
   PF_REQUIRE((((uintptr_t)x_dev | (uintptr_t)y_dev | (uintptr_t)w_hi_dev | (uintptr_t)w_lo_dev) & 15) == 0,
              "pf_conv2d_tc_fwd: 16-byte alignment required");
-  return launch_tc<0>(g, x_dev, w_hi_dev, w_lo_dev, y_dev, 0, bias_dev, relu, (cudaStream_t)stream, "pf_conv2d_tc_fwd");
+  PF_REQUIRE(((uintptr_t)residual_dev & 15) == 0, "pf_conv2d_tc_fwd: residual must be 16-byte aligned");
+  return launch_tc<0>(g, x_dev, w_hi_dev, w_lo_dev, y_dev, 0, bias_dev, relu, residual_dev, (cudaStream_t)stream,
+                      "pf_conv2d_tc_fwd");
 }
 
 int pf_conv2d_tc_dgrad(const pf_conv_desc* d, const float* dy_dev, const void* wd_hi_dev, const void* wd_lo_dev,
@@ -553,7 +602,7 @@ int pf_conv2d_tc_dgrad(const pf_conv_desc* d, const float* dy_dev, const void* w
   PF_REQUIRE(dy_dev && wd_hi_dev && wd_lo_dev && dx_dev, "pf_conv2d_tc_dgrad: null pointer");
   PF_REQUIRE((((uintptr_t)dy_dev | (uintptr_t)dx_dev | (uintptr_t)wd_hi_dev | (uintptr_t)wd_lo_dev) & 15) == 0,
              "pf_conv2d_tc_dgrad: 16-byte alignment required");
-  return launch_tc<1>(g, dy_dev, wd_hi_dev, wd_lo_dev, dx_dev, accumulate, nullptr, 0, (cudaStream_t)stream,
+  return launch_tc<1>(g, dy_dev, wd_hi_dev, wd_lo_dev, dx_dev, accumulate, nullptr, 0, nullptr, (cudaStream_t)stream,
                       "pf_conv2d_tc_dgrad");
 }
 

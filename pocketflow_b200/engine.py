@@ -240,6 +240,22 @@ class Executor:
                 self.desc[op] = ops.conv_desc(n, h, w, c, c, kh, kw, p, q, sh, sw, pt, pl)
                 if self.train:
                     self.pool_argmax[op] = torch.empty(y.shape, dtype=torch.uint8, device=dev)
+        # ---- residual Add fused into the epilogue of the tcgen05 conv that produces one of its inputs:
+        # the conv writes conv(x) + shortcut straight into the Add's buffer (one pass instead of three)
+        self.fused_add = {}        # conv op -> (add op, other input tensor)
+        self.add_fused = set()
+        for op in self.ops:
+            if op.type != 'Add':
+                continue
+            for i, x_t in enumerate(op.inputs):
+                src, other = x_t.op, op.inputs[1 - i]
+                if src.type == 'Conv2D' and src in self.tc and x_t not in self.alias and src not in self.fused_act \
+                        and 'bias' not in src.vars and len(self._consumers(x_t)) == 1 \
+                        and self.g.ops.index(other.op) < self.g.ops.index(src):
+                    self.fused_add[src] = (op, other)
+                    self.add_fused.add(op)
+                    self.buf[x_t] = self.buf[op.output]       # the conv output IS the add output
+                    break
         if self.labels_t is not None and self.labels_t not in self.buf:
             self.buf[self.labels_t] = torch.zeros(self.labels_t.shape, dtype=torch.float32, device=dev)
         self.bn_ws = E((max_bnws,))
@@ -396,9 +412,10 @@ class Executor:
                 if op in self.tc:
                     with self.timed('conv_prep'):
                         self.tc[op].prepare(self.kernel_of(op))
+                    res = self.T(self.fused_add[op][1]) if op in self.fused_add else None
                     with self.timed('conv_fwd'):
                         ops.conv2d_tc_fwd(self.desc[op], self.T(op.inputs[0]), self.tc[op], bias,
-                                          op in self.fused_act, self.buf[op.output])
+                                          op in self.fused_act, self.buf[op.output], res)
                 else:
                     with self.timed('conv_fwd'):
                         ops.conv2d_fwd(self.desc[op], self.T(op.inputs[0]), self.kernel_of(op), bias,
@@ -441,6 +458,8 @@ class Executor:
                 with self.timed('pool'):
                     ops.global_avgpool_fwd(self.T(x), n, h * w, c, self.buf[op.output])
             elif ty == 'Add':
+                if op in self.add_fused:
+                    continue                               # computed by the producing conv's epilogue
                 with self.timed('add_fwd'):
                     ops.add(self.T(op.inputs[0]), self.T(op.inputs[1]), self.buf[op.output])
             elif ty == 'Softmax':

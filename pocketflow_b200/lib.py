@@ -41,7 +41,7 @@ SIGNATURES = {
     'pf_conv2d_tc_supported': (c_i32, [c_vp]),
     'pf_conv2d_tc_weight_elems': (c_i64, [c_vp, c_i32]),
     'pf_conv2d_tc_prep_weight': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
-    'pf_conv2d_tc_fwd': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
+    'pf_conv2d_tc_fwd': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]),
     'pf_conv2d_tc_dgrad': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
     'pf_conv2d_tc_wgrad_supported': (c_i32, [c_vp]),
     'pf_conv2d_tc_wgrad_workspace_bytes': (c_i64, [c_vp]),

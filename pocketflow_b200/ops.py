@@ -530,9 +530,9 @@ class TcWeights:
                    'pf_conv2d_tc_prep_weight')
 
 
-def conv2d_tc_fwd(d, x, tw, bias, relu, y):
+def conv2d_tc_fwd(d, x, tw, bias, relu, y, residual=None):
     _lib.check(_lib.load().pf_conv2d_tc_fwd(ctypes.byref(d), _p(x), _p(tw.f_hi), _p(tw.f_lo), _p(bias),
-                                            int(bool(relu)), _p(y), _stream()), 'pf_conv2d_tc_fwd')
+                                            int(bool(relu)), _p(residual), _p(y), _stream()), 'pf_conv2d_tc_fwd')
 
 
 def conv2d_tc_dgrad(d, dy, tw, accumulate, dx):

@@ -87,6 +87,10 @@ def test_conv_tc_fwd_dgrad(case):
     ops.conv2d_tc_fwd(d, X, tw, bias.to(DEV), True, Y)
     ref2 = torch.relu(y_ref + bias.double())
     assert (Y.cpu().double() - ref2).abs().max().item() <= 2e-5 * ref2.abs().max().item()
+    res = torch.randn(n, p, q, k, generator=g)
+    ops.conv2d_tc_fwd(d, X, tw, None, False, Y, res.to(DEV))           # fused residual add
+    ref3 = y_ref + res.double()
+    assert (Y.cpu().double() - ref3).abs().max().item() <= 2e-5 * ref3.abs().max().item()
     DX = torch.full((n, h, w, c), 3.0, device=DEV)
     ops.conv2d_tc_dgrad(d, DY, tw, False, DX)
     err = (DX.cpu().double() - dx_ref).abs().max().item() / dx_ref.abs().max().item()
