@@ -223,6 +223,10 @@ typedef struct pf_conv_desc {
 #define PF_CONV_WGRAD_MAX_SPLITS 64
 #define PF_BN_MAX_SPLITS 1024
 
+/* cols[m][k] (m = output pixel, k = (r*S+s)*C + c, zero-padded to kpad columns): explicit im2col for
+ * first layers whose Cin (3) the tensor-core path cannot take; the conv then runs as a 1x1 conv over
+ * kpad channels. */
+int pf_im2col(const pf_conv_desc* d, const float* x_dev, int kpad, float* cols_dev, void* stream);
 /* y = conv(x, w) (+ bias[k]) (relu if relu != 0) */
 int pf_conv2d_fwd(const pf_conv_desc* d, const float* x_dev, const float* w_dev, const float* bias_dev,
                   int relu, float* y_dev, void* stream);

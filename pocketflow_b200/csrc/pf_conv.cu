@@ -299,6 +299,37 @@ hwio_to_hwoi_kernel(const float* __restrict__ w, float* __restrict__ wt, int RS,
   }
 }
 
+// cols[m][k] = x[n, oh*sh - pt + r, ow*sw - pl + s, c], k = (r*S + s)*C + c; zero for padding taps and
+// for k in [R*S*C, kpad).  Used to turn a conv whose Cin is not a multiple of 16 (the 7x7x3 / 5x5x3 /
+// 3x3x3 first layers) into a 1x1 conv over kpad channels that the tensor-core path accepts.
+__global__ void __launch_bounds__(256)
+im2col_kernel(const float* __restrict__ x, Geom g, int M, int K, int kpad, float* __restrict__ cols) {
+  const int kv = kpad >> 2;
+  const int64_t total = (int64_t)M * kv;
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += stride) {
+    const int m = (int)(i / kv);
+    const int k0 = (int)(i - (int64_t)m * kv) << 2;
+    const int pq = g.P * g.Q;
+    const int n = m / pq;
+    const int rem = m - n * pq;
+    const int oh = rem / g.Q, ow = rem - oh * g.Q;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + j;
+      v[j] = 0.f;
+      if (k < K) {
+        const int rs = k / g.C, c = k - rs * g.C;
+        const int r = rs / g.S, q = rs - r * g.S;
+        const int ih = oh * g.sh - g.pt + r, iw = ow * g.sw - g.pl + q;
+        if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) v[j] = __ldg(x + (((size_t)n * g.H + ih) * g.W + iw) * g.C + c);
+      }
+    }
+    *reinterpret_cast<float4*>(cols + (size_t)m * kpad + k0) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
 int check_geom(const pf_conv_desc* d, Geom* g, const char* who) {
   PF_REQUIRE(d != nullptr, "%s: null descriptor", who);
   PF_REQUIRE(d->n > 0 && d->h > 0 && d->w > 0 && d->c > 0 && d->k > 0 && d->r > 0 && d->s > 0 &&
@@ -317,6 +348,21 @@ inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 }  // namespace
 
 extern "C" {
+
+int pf_im2col(const pf_conv_desc* d, const float* x_dev, int kpad, float* cols_dev, void* stream) {
+  Geom g;
+  int rc = check_geom(d, &g, "pf_im2col");
+  if (rc) return rc;
+  const int K = g.R * g.S * g.C;
+  PF_REQUIRE(x_dev && cols_dev && kpad >= K && (kpad & 3) == 0 && ((uintptr_t)cols_dev & 15) == 0,
+             "pf_im2col: kpad must be a multiple of 4 >= R*S*C and cols 16-byte aligned");
+  const int M = g.N * g.P * g.Q;
+  int64_t blocks = ((int64_t)M * (kpad >> 2) + 255) / 256;
+  if (blocks > PF_NUM_SMS * 16) blocks = PF_NUM_SMS * 16;
+  im2col_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x_dev, g, M, K, kpad, cols_dev);
+  PF_CHECK_LAUNCH("pf_im2col");
+  return PF_OK;
+}
 
 int pf_conv2d_fwd(const pf_conv_desc* d, const float* x_dev, const float* w_dev, const float* bias_dev,
                   int relu, float* y_dev, void* stream) {

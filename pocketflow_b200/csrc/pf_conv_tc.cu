@@ -529,7 +529,7 @@ int launch_tc(const TcGeom& g, const float* src, const void* b_hi, const void* b
   if (smem < epi) smem = epi;
   smem += 1024;
   dim3 grid((M + TM - 1) / TM, (Ng + BN - 1) / BN);
-  if (nk <= 2) {
+  if (nk <= 1) {
     auto kern = conv_tc_kernel<MODE, 4>;
     PF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     kern<<<grid, 4 * 32 + 32, smem, st>>>(src, (const __nv_bfloat16*)b_hi, (const __nv_bfloat16*)b_lo, out, g, M, Ng,

@@ -204,6 +204,7 @@ class Executor:
         self.bn = {}
         self.tc = {}
         self.tc_wgrad = set()
+        self.im2col = {}
         self.pool_argmax = {}
         max_ws, max_wt, max_bnws = 4, 4, 4
         self.desc = {}
@@ -224,6 +225,21 @@ class Executor:
                     k = y.shape[1]
                     d = ops.conv_desc(n, 1, 1, c, k, 1, 1, 1, 1, 1, 1, 0, 0)
                 self.desc[op] = d
+                if self.conv_path == 'tc' and op.type == 'Conv2D' and not ops.conv2d_tc_supported(d) \
+                        and k % 16 == 0 and c % 16 != 0 and x.op.type == 'Placeholder':
+                    # first layer (Cin = 3): explicit im2col into kpad channels, then a 1x1 tensor-core conv
+                    kdim = kh * kw * c
+                    kpad = (kdim + 15) // 16 * 16
+                    d1 = ops.conv_desc(n, p, q, kpad, k, 1, 1, p, q, 1, 1, 0, 0)
+                    self.im2col[op] = dict(kdim=kdim, kpad=kpad, d1=d1, compute=True,
+                                           cols=E((n * p * q, kpad)),
+                                           wpad=torch.zeros(kpad * k, dtype=torch.float32, device=dev),
+                                           tw=ops.TcWeights(d1, dev, need_dgrad=False))
+                    if self.train:
+                        self.im2col[op]['dwpad'] = torch.zeros(kpad * k, dtype=torch.float32, device=dev)
+                        if ops.conv2d_tc_wgrad_supported(d1):
+                            max_ws = max(max_ws, ops.conv2d_tc_wgrad_workspace_floats(d1))
+                        max_ws = max(max_ws, ops.conv2d_wgrad_workspace_floats(d1))
                 if self.conv_path == 'tc' and ops.conv2d_tc_supported(d):
                     self.tc[op] = ops.TcWeights(d, dev, need_dgrad=self.train and x.op.type != 'Placeholder')
                 if self.train:
@@ -409,7 +425,18 @@ class Executor:
                 continue
             if ty in ('Conv2D', 'MatMul'):
                 bias = st.view(op.vars['bias']) if 'bias' in op.vars else None
-                if op in self.tc:
+                if op in self.im2col:
+                    im = self.im2col[op]
+                    wk = self.kernel_of(op)
+                    with self.timed('conv_prep'):
+                        if im['compute']:
+                            ops.im2col(self.desc[op], self.T(op.inputs[0]), im['kpad'], im['cols'])
+                        ops.add(wk.reshape(-1), None, im['wpad'][:wk.numel()])       # rows >= R*S*C stay zero
+                        im['tw'].prepare(im['wpad'])
+                    with self.timed('conv_fwd'):
+                        ops.conv2d_tc_fwd(im['d1'], im['cols'], im['tw'], bias, op in self.fused_act,
+                                          self.buf[op.output])
+                elif op in self.tc:
                     with self.timed('conv_prep'):
                         self.tc[op].prepare(self.kernel_of(op))
                     res = self.T(self.fused_add[op][1]) if op in self.fused_add else None
@@ -503,7 +530,15 @@ class Executor:
                 if 'bias' in op.vars:
                     ops.colsum(gy, m, k, st.view(op.vars['bias'], self.G))
                 with self.timed('conv_wgrad'):
-                    if op in self.tc_wgrad:
+                    if op in self.im2col:
+                        im = self.im2col[op]
+                        gk = st.view(op.vars['kernel'], self.G)
+                        if ops.conv2d_tc_wgrad_supported(im['d1']):
+                            ops.conv2d_tc_wgrad(im['d1'], im['cols'], gy, self.wgrad_ws, im['dwpad'])
+                        else:
+                            ops.conv2d_wgrad(im['d1'], im['cols'], gy, self.wgrad_ws, im['dwpad'])
+                        ops.add(im['dwpad'][:gk.numel()], None, gk.reshape(-1))
+                    elif op in self.tc_wgrad:
                         ops.conv2d_tc_wgrad(d, self.T(x_t), gy, self.wgrad_ws, st.view(op.vars['kernel'], self.G))
                     else:
                         ops.conv2d_wgrad(d, self.T(x_t), gy, self.wgrad_ws, st.view(op.vars['kernel'], self.G))
@@ -590,6 +625,16 @@ class Executor:
             else:
                 ops.adam_step(st.P[s:e], self.S1[s:e], self.S2[s:e], self.G[s:e], self.hp, o.get('beta1', 0.9),
                               o.get('beta2', 0.999), o.get('eps', 1e-8), wd, self.grad_scale)
+
+    def share_im2col_from(self, other):
+        """The teacher and the student read the same image batch: reuse the teacher's im2col of the first
+        layer (it runs first inside device_step) instead of recomputing it."""
+        for op, im in self.im2col.items():
+            for op2, im2 in other.im2col.items():
+                if op.inputs[0] is op2.inputs[0] and im['kpad'] == im2['kpad'] and im['cols'].shape == im2['cols'].shape \
+                        and all(op.attrs[a] == op2.attrs[a] for a in ('ksize', 'strides', 'pad')):
+                    im['cols'] = im2['cols']
+                    im['compute'] = False
 
     # ------------------------------------------------------------------ one training step
     def device_step(self, allreduce=None):

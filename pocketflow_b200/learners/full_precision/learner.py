@@ -78,3 +78,4 @@ class FullPrecLearner(AbstractLearner):  # pylint: disable=too-many-instance-att
                                    seed=1, grad_scale=1.0 / world)
         if teacher is not None:
             teacher.buf[images] = self.sess_train.buf[images]
+            self.sess_train.share_im2col_from(teacher)

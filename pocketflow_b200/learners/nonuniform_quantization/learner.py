@@ -134,4 +134,5 @@ class NonUniformQuantLearner(AbstractLearner):
                                    act_quant=nq.act_quant_spec(), teacher=teacher, seed=1, grad_scale=1.0 / world)
         if teacher is not None:
             teacher.buf[images] = self.sess_train.buf[images]
+            self.sess_train.share_im2col_from(teacher)
         self.cluster_init()

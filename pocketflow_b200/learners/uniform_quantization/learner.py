@@ -175,6 +175,7 @@ class UniformQuantLearner(AbstractLearner):
                                    teacher=teacher, seed=1, grad_scale=1.0 / world)
         if teacher is not None:
             teacher.buf[self.images] = self.sess_train.buf[self.images]
+            self.sess_train.share_im2col_from(teacher)
         self.sess_eval = self.sess_train
 
     @staticmethod

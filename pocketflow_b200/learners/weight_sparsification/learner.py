@@ -129,6 +129,7 @@ class WeightSparseLearner(AbstractLearner):  # pylint: disable=too-many-instance
                                    maskable=self.maskable_vars, teacher=teacher, seed=1, grad_scale=1.0 / world)
         if teacher is not None:
             teacher.buf[images] = self.sess_train.buf[images]
+            self.sess_train.share_im2col_from(teacher)
         self.masks = [self.sess_train.store.view(v, self.sess_train.MASK) for v in self.maskable_vars]
 
     def __calc_prune_ratio_dyn(self, prune_ratio_fnl, global_step):

@@ -421,6 +421,10 @@ def conv_desc(n, h, w, c, k, r, s, p, q, sh, sw, pt, pl):
     return _lib.ConvDesc(n, h, w, c, k, r, s, p, q, sh, sw, pt, pl)
 
 
+def im2col(d, x, kpad, cols):
+    _lib.check(_lib.load().pf_im2col(ctypes.byref(d), _p(x), int(kpad), _p(cols), _stream()), 'pf_im2col')
+
+
 def conv2d_fwd(d, x, w, bias, relu, y):
     _lib.check(_lib.load().pf_conv2d_fwd(ctypes.byref(d), _p(x), _p(w), _p(bias), int(bool(relu)), _p(y), _stream()),
                'pf_conv2d_fwd')
