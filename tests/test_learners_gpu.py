@@ -1,0 +1,139 @@
+"""Learner-level GPU tests through the plugin surface (create_learner / train_step / prune / evaluate):
+WeightSparseLearner (masks bit-exact vs the oracle inside a real training loop, pruned weights stay
+zero), NonUniformQuantLearner (codebook init + step loss vs the oracle), FullPrecLearner, checkpoints."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pf_oracle as O
+from oracle.step_oracle import StepOracle
+from pocketflow_b200.flags import FLAGS
+
+pytestmark = pytest.mark.gpu
+F32 = np.float32
+
+
+def rel(a, b):
+    return abs(float(a) - float(b)) / max(abs(float(b)), 1e-30)
+
+
+def make(learner, **flags):
+    FLAGS.reset()
+    from pocketflow_b200.nets import resnet_at_cifar10 as R
+    from pocketflow_b200.learners.learner_utils import create_learner
+    import pocketflow_b200.learners.weight_sparsification.learner  # noqa: F401  (flag definitions)
+    import pocketflow_b200.learners.nonuniform_quantization.learner  # noqa: F401
+    import pocketflow_b200.learners.uniform_quantization.learner  # noqa: F401
+    FLAGS.resnet_size, FLAGS.batch_size, FLAGS.learner = 8, 16, learner
+    for k, v in flags.items():
+        setattr(FLAGS, k, v)
+    return create_learner(None, R.ModelHelper())
+
+
+def test_create_learner_names():
+    from pocketflow_b200.learners.learner_utils import create_learner
+    FLAGS.reset()
+    FLAGS.learner = 'bogus'
+    with pytest.raises(ValueError):
+        create_learner(None, None)
+    FLAGS.learner = 'uniform-tf'
+    with pytest.raises(ValueError):
+        create_learner(None, None)
+
+
+def test_weight_sparse_learner_masks_bit_exact_in_training_loop():
+    lrn = make('weight-sparse', ws_prune_ratio=0.6, ws_prune_ratio_prtl='uniform', enbl_dst=False)
+    ex = lrn.sess_train
+    names = [v.name for v in lrn.maskable_vars]
+    assert len(names) == 11 and all('kernel' in n for n in names)       # 10 convs + dense of ResNet-8
+    lrn.nb_iters_train = 40                                             # t_b = 4, t_e = 20
+    ref_bkup = {v.name: ex.store.view(v).cpu().numpy().copy() for v in lrn.maskable_vars}
+    ref_mask = {n: np.ones_like(b) for n, b in ref_bkup.items()}
+    for it in range(24):
+        lrn.train_step()
+        if (it + 1) % 4 == 0:
+            w_now = {v.name: ex.store.view(v).cpu().numpy().copy() for v in lrn.maskable_vars}
+            ratios = lrn.prune()
+            step = ex.step_count
+            assert ratios[0] == O.ws_prune_ratio_dyn(step, 40, 0.6)
+            for v, r in zip(lrn.maskable_vars, ratios):
+                nv, nb, nm, thr = O.ws_build_mask(w_now[v.name], ref_bkup[v.name], ref_mask[v.name], r)
+                ref_bkup[v.name], ref_mask[v.name] = nb, nm
+                assert np.array_equal(ex.store.view(v, ex.MASK).cpu().numpy(), nm), (it, v.name)     # bit-exact
+                assert np.array_equal(ex.store.view(v, ex.BKUP).cpu().numpy(), nb)
+                assert np.array_equal(ex.store.view(v).cpu().numpy(), nv)
+            assert float(ex.S1.abs().max()) == 0.0                      # momentum slots re-initialised
+        else:
+            # between mask updates pruned weights stay exactly zero (gradient masked in the fused optimizer)
+            for v in lrn.maskable_vars:
+                w = ex.store.view(v).cpu().numpy()
+                assert np.all(w[ref_mask[v.name] == 0] == 0)
+    loss, pr = lrn.evaluate()
+    assert abs(pr - 0.6) < 0.01 and np.isfinite(loss)
+    assert O.calc_prune_ratio([ex.store.view(v).cpu().numpy() for v in lrn.maskable_vars]) == F32(pr)
+
+
+def test_weight_sparse_heurist_protocol():
+    lrn = make('weight-sparse', ws_prune_ratio=0.5, ws_prune_ratio_prtl='heurist')
+    n = np.array([v.numel for v in lrn.maskable_vars], dtype=np.float64)
+    r = np.array([x[1] for x in lrn.var_names_n_prune_ratios])
+    np.testing.assert_allclose(r, O.ws_heurist_ratios(n, 0.5), rtol=1e-12)
+    assert abs((r * n).sum() / n.sum() - 0.5) < 1e-12
+
+
+def test_nonuniform_learner_step_matches_oracle(monkeypatch):
+    monkeypatch.setenv('PF_CONV_PATH', 'fp32')
+    lrn = make('non-uniform', nuql_weight_bits=4, enbl_dst=True)
+    ex = lrn.sess_train
+    assert isinstance(ex.wq, __import__('pocketflow_b200.ops', fromlist=['x']).CodebookWeightQuantizer)
+    state, tstate = ex.store.state_dict(), ex.teacher.store.state_dict()
+    clusters = ex.wq.clusters.cpu().numpy()
+    teacher = StepOracle(ex.teacher.ops, ex.teacher.logits_t, lrn.images)
+    orc = StepOracle(ex.ops, ex.logits_t, lrn.images, lrn.labels, ex.loss, ex.weight_quant, ex.act_quant, teacher)
+    for i, op in enumerate(ex.wq_ops):
+        w = state[op.vars['kernel'].name]
+        _, c_ref, _ = O.nonuniform_quantize(w, 4)
+        assert np.array_equal(clusters[i, :16], c_ref)                  # quantile init: exact order statistics
+        orc.clusters[op.name] = clusters[i, :16]
+    images, labels = lrn.iterator_train.next_batch()
+    ex.buf[lrn.images].copy_(images)
+    ex.buf[lrn.labels].copy_(labels)
+    ex.run_step(lrn.lrn_rate(0))
+    got = ex.fetch_losses()
+    for i, op in enumerate(ex.wq_ops):
+        v = op.vars['kernel']
+        q_ref, _, _ = O.nonuniform_quantize(state[v.name], 4, clusters[i, :16])
+        assert np.array_equal(ex.store.view(v, ex.QW).cpu().numpy(), q_ref)
+    ref, _, _ = orc.step(state, images.numpy(), labels.numpy(), dict(kind='adam', slots={}), lrn.lrn_rate(0),
+                         teacher_state=tstate)
+    for k in ('ce', 'l2', 'dst_loss', 'loss'):
+        assert rel(got[k], ref[k]) <= 1e-5, (k, got[k], ref[k])
+
+
+def test_full_prec_learner_and_checkpoint_roundtrip(tmp_path):
+    lrn = make('full-prec', save_path=str(tmp_path / 'models' / 'model.ckpt'))
+    ex = lrn.sess_train
+    losses = []
+    for _ in range(8):
+        lrn.train_step()
+        losses.append(ex.fetch_losses()['loss'])
+    assert np.all(np.isfinite(losses))
+    from pocketflow_b200.learners.abstract_learner import save_checkpoint, load_checkpoint, latest_checkpoint
+    fn = save_checkpoint(FLAGS.save_path, ex.store.state_dict(), ex.step_count)
+    assert latest_checkpoint(os.path.dirname(FLAGS.save_path)) == fn
+    sd = load_checkpoint(fn)
+    before = ex.store.P.clone()
+    ex.store.P.zero_()
+    ex.store.load_state_dict(sd)
+    assert torch.equal(ex.store.P, before)
+    assert np.isfinite(lrn.evaluate())
+
+
+def test_uniform_learner_trains_and_evaluates():
+    lrn = make('uniform', uql_weight_bits=8, uql_use_buckets=True, enbl_dst=True, summ_step=5, save_step=10 ** 9,
+               uql_save_quant_model_path='/tmp/pf_uql_test/model.ckpt')
+    lrn.train(nb_iters=6)            # includes the CUDA-graph-free eager loop, logging, final save + evaluate
+    r = lrn.sess_train.fetch_losses()
+    assert np.isfinite(r['loss']) and lrn.sess_train.step_count == 6
