@@ -50,6 +50,8 @@ WORKLOADS = {
                                'ResNet-20 v2 / synthetic CIFAR-10, WeightSparseLearner 50% + distillation'),
     'resnet50_nuq4_dst_b256': ('resnet_at_ilsvrc12', 50, 'non-uniform', dict(batch_size=256, enbl_dst=True,
                                nuql_weight_bits=4), 'ResNet-50 v2 / synthetic 224x224x3, NonUniformQuantLearner 4-bit codebook + distillation'),
+    'mobilenet_cpg50_b256': ('mobilenet_at_ilsvrc12', 0, 'chn-pruned-gpu', dict(batch_size=256, cpg_prune_ratio=0.5),
+                             'MobileNet-v1 / synthetic 224x224x3, ChannelPrunedGpuLearner masked step at 0.5 channel ratio'),
     'lenet_uq8_b128': ('lenet_at_cifar10', 0, 'uniform', dict(batch_size=128, uql_weight_bits=8),
                        'LeNet-5 / synthetic CIFAR-10, UniformQuantLearner 8-bit (configs[0], plumbing)'),
 }
@@ -68,6 +70,8 @@ def setup_flags(workload, batch_override=None, world=1):
         importlib.import_module('pocketflow_b200.learners.weight_sparsification.learner')
     elif learner == 'non-uniform':
         importlib.import_module('pocketflow_b200.learners.nonuniform_quantization.learner')
+    elif learner == 'chn-pruned-gpu':
+        importlib.import_module('pocketflow_b200.learners.channel_pruning_gpu.learner')
     importlib.import_module('pocketflow_b200.learners.distillation_helper')
     # each net module re-declares its own defaults (lrn_rate_init, loss_w_dcy, ...): re-apply them
     importlib.reload(importlib.import_module('pocketflow_b200.datasets.' +

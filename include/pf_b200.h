@@ -270,6 +270,20 @@ int pf_tc_probe(const void* a_dev, const void* b_dev, float* d_dev, int n, int k
                 uint32_t sbo_a, uint32_t lbo_b, uint32_t sbo_b, uint32_t kstep_a, uint32_t kstep_b, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * a4  Depthwise convolution, depth multiplier 1 (pf_dwconv.cu): slim.separable_conv2d's depthwise half
+ *     (utils/external/mobilenet_v1.py:273-280; TF op DepthwiseConv2dNative).  x NHWC, w [r,s,c,1],
+ *     descriptor with k == c, c % 4 == 0, r*s <= 9.  HBM-bound.  wgrad: ws_dev of
+ *     pf_dwconv_wgrad_workspace_bytes(d) bytes; deterministic.
+ * ------------------------------------------------------------------------------------------- */
+#define PF_DWCONV_MAX_SPLITS 1024
+int pf_dwconv_fwd(const pf_conv_desc* d, const float* x_dev, const float* w_dev, float* y_dev, void* stream);
+int pf_dwconv_dgrad(const pf_conv_desc* d, const float* dy_dev, const float* w_dev, int accumulate, float* dx_dev,
+                    void* stream);
+int64_t pf_dwconv_wgrad_workspace_bytes(const pf_conv_desc* d);
+int pf_dwconv_wgrad(const pf_conv_desc* d, const float* x_dev, const float* dy_dev, float* ws_dev, float* dw_dev,
+                    void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * a13 The HBM-bound layers between the convolutions (pf_nn.cu); tensors viewed as [m, c], c % 4 == 0.
  *     tf.layers.batch_normalization(momentum, eps, fused) — utils/external/resnet_model.py:55-62:
  *       stats : batch mean / biased variance / rstd (+ moving-stat update, unbiased moving variance);

@@ -149,6 +149,18 @@ class StepOracle:
                 y = conv2d_nhwc(x, w, op.attrs, op.output.shape) if ty == 'Conv2D' else x @ w
                 if 'bias' in op.vars:
                     y = y + params[op.vars['bias'].name]
+            elif ty == 'DepthwiseConv2dNative':
+                w = params[op.vars['kernel'].name]
+                if op.name in self.wq_bits:
+                    w = weight_fake_quant(w, self.wq_bits[op.name], self.wq.get('use_buckets', False),
+                                          self.wq.get('bucket_type', 'channel'), self.wq.get('bucket_size', 256))
+                (sh, sw), (pt, pl), (kh, kw) = op.attrs['strides'], op.attrs['pad'], op.attrs['ksize']
+                p, q = op.output.shape[1], op.output.shape[2]
+                pb = max((p - 1) * sh + kh - x.shape[1] - pt, 0)
+                pr = max((q - 1) * sw + kw - x.shape[2] - pl, 0)
+                xt = F.pad(x.permute(0, 3, 1, 2), (pl, pr, pt, pb))
+                y = F.conv2d(xt, w.permute(2, 3, 0, 1), stride=(sh, sw), groups=x.shape[-1])
+                y = y[:, :, :p, :q].permute(0, 2, 3, 1).contiguous()
             elif ty == 'FusedBatchNorm':
                 ga, be = params[op.vars['gamma'].name], params[op.vars['beta'].name]
                 mm, mv = params[op.vars['moving_mean'].name], params[op.vars['moving_variance'].name]
@@ -177,7 +189,7 @@ class StepOracle:
                 xt = F.pad(x.permute(0, 3, 1, 2), (pl, pr, pt, pb), value=float('-inf'))
                 y = F.max_pool2d(xt, (kh, kw), (sh, sw)).permute(0, 2, 3, 1).contiguous()
             elif ty == 'Mean':
-                y = x.mean(dim=(1, 2))
+                y = x.mean(dim=(1, 2), keepdim=len(op.output.shape) == 4)
             elif ty == 'Reshape':
                 y = x.reshape(op.output.shape)
             elif ty == 'Identity':

@@ -1,0 +1,231 @@
+// pf_dwconv.cu — depthwise convolution (depth multiplier 1) forward / dgrad / wgrad, NHWC x [R,S,C,1].
+//
+// slim.separable_conv2d(num_outputs=None) of MobileNet-v1
+// (/root/reference/utils/external/mobilenet_v1.py:273-280; op type DepthwiseConv2dNative, which the
+// quantizers re-create on the quantized weight, learners/uniform_quantization/utils.py:92-104).
+// 2*R*S FLOP per output element against >= 8 bytes of traffic: an HBM-bound kernel (SURVEY §8 a4:
+// "depthwise is bandwidth-bound"), so: one thread per (pixel, 4 channels), 128-bit loads of the
+// R*S taps (neighbouring taps hit L1/L2), no tensor cores.
+#include "pf_common.cuh"
+
+namespace {
+constexpr int NT = 256;
+
+struct DwGeom {
+  int N, H, W, C, R, S, P, Q, sh, sw, pt, pl;
+};
+
+__global__ void __launch_bounds__(NT)
+dw_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, DwGeom g, float* __restrict__ y) {
+  const int C4 = g.C >> 2;
+  const int64_t total = (int64_t)g.N * g.P * g.Q * C4;
+  const int64_t stride = (int64_t)gridDim.x * NT;
+  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < total; i += stride) {
+    const int c = (int)(i % C4) << 2;
+    int64_t t = i / C4;
+    const int ow = (int)(t % g.Q); t /= g.Q;
+    const int oh = (int)(t % g.P);
+    const int n = (int)(t / g.P);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < g.R; ++r) {
+      const int ih = oh * g.sh - g.pt + r;
+      if (ih < 0 || ih >= g.H) continue;
+      for (int s = 0; s < g.S; ++s) {
+        const int iw = ow * g.sw - g.pl + s;
+        if (iw < 0 || iw >= g.W) continue;
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (((size_t)n * g.H + ih) * g.W + iw) * g.C + c));
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(w + ((size_t)r * g.S + s) * g.C + c));
+        acc.x = fmaf(xv.x, wv.x, acc.x); acc.y = fmaf(xv.y, wv.y, acc.y);
+        acc.z = fmaf(xv.z, wv.z, acc.z); acc.w = fmaf(xv.w, wv.w, acc.w);
+      }
+    }
+    pf_st_stream(y + (i << 2), acc);
+  }
+}
+
+// dx[n,ih,iw,c] (+)= sum over taps of dy[n,oh,ow,c] * w[r,s,c] with oh*sh - pt + r == ih
+__global__ void __launch_bounds__(NT)
+dw_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w, DwGeom g, int accumulate,
+                float* __restrict__ dx) {
+  const int C4 = g.C >> 2;
+  const int64_t total = (int64_t)g.N * g.H * g.W * C4;
+  const int64_t stride = (int64_t)gridDim.x * NT;
+  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < total; i += stride) {
+    const int c = (int)(i % C4) << 2;
+    int64_t t = i / C4;
+    const int iw = (int)(t % g.W); t /= g.W;
+    const int ih = (int)(t % g.H);
+    const int n = (int)(t / g.H);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < g.R; ++r) {
+      const int th = ih + g.pt - r;
+      if (th < 0 || th % g.sh) continue;
+      const int oh = th / g.sh;
+      if (oh >= g.P) continue;
+      for (int s = 0; s < g.S; ++s) {
+        const int tw = iw + g.pl - s;
+        if (tw < 0 || tw % g.sw) continue;
+        const int ow = tw / g.sw;
+        if (ow >= g.Q) continue;
+        const float4 dv = __ldg(reinterpret_cast<const float4*>(dy + (((size_t)n * g.P + oh) * g.Q + ow) * g.C + c));
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(w + ((size_t)r * g.S + s) * g.C + c));
+        acc.x = fmaf(dv.x, wv.x, acc.x); acc.y = fmaf(dv.y, wv.y, acc.y);
+        acc.z = fmaf(dv.z, wv.z, acc.z); acc.w = fmaf(dv.w, wv.w, acc.w);
+      }
+    }
+    float* p = dx + (i << 2);
+    if (accumulate) {
+      const float4 o = *reinterpret_cast<const float4*>(p);
+      acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+    }
+    pf_st_stream(p, acc);
+  }
+}
+
+// dw[r,s,c] = sum over output pixels of x[n, oh*sh-pt+r, ow*sw-pl+s, c] * dy[n,oh,ow,c]
+// grid: (channel tiles of 128, pixel splits); thread = 4 channels x all taps (R*S <= 9) over a pixel
+// stride; partials [split][R*S][C] -> fixed-order final reduction (deterministic).
+constexpr int kMaxTaps = 9;
+__global__ void __launch_bounds__(NT)
+dw_wgrad_partial_kernel(const float* __restrict__ x, const float* __restrict__ dy, DwGeom g, int pix_per_split,
+                        float* __restrict__ part) {
+  __shared__ float sh[NT * 4];
+  const int taps = g.R * g.S;
+  const int c0 = blockIdx.x * 128;
+  const int tc = min(128, g.C - c0);
+  const int nvec = tc >> 2, nty = NT / nvec;
+  const int tx = threadIdx.x % nvec, ty = threadIdx.x / nvec;
+  const int npix = g.N * g.P * g.Q;
+  const int p0 = blockIdx.y * pix_per_split, p1 = min(npix, p0 + pix_per_split);
+  float acc[kMaxTaps][4];
+#pragma unroll
+  for (int t = 0; t < kMaxTaps; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
+  const int c = c0 + tx * 4;
+  if (ty < nty) {
+    for (int p = p0 + ty; p < p1; p += nty) {
+      const int pq = g.P * g.Q;
+      const int n = p / pq;
+      const int rem = p - n * pq;
+      const int oh = rem / g.Q, ow = rem - oh * g.Q;
+      const float4 dv = pf_ld_stream(dy + (size_t)p * g.C + c);
+#pragma unroll
+      for (int t = 0; t < kMaxTaps; ++t) {
+        if (t < taps) {
+          const int r = t / g.S, s = t - r * g.S;
+          const int ih = oh * g.sh - g.pt + r, iw = ow * g.sw - g.pl + s;
+          if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) {
+            const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (((size_t)n * g.H + ih) * g.W + iw) * g.C + c));
+            acc[t][0] = fmaf(xv.x, dv.x, acc[t][0]); acc[t][1] = fmaf(xv.y, dv.y, acc[t][1]);
+            acc[t][2] = fmaf(xv.z, dv.z, acc[t][2]); acc[t][3] = fmaf(xv.w, dv.w, acc[t][3]);
+          }
+        }
+      }
+    }
+  }
+  // combine over ty per tap, fixed order
+  for (int t = 0; t < taps; ++t) {
+    __syncthreads();
+    if (ty < nty) {
+      float* a = &sh[(ty * nvec + tx) * 4];
+      a[0] = acc[t][0]; a[1] = acc[t][1]; a[2] = acc[t][2]; a[3] = acc[t][3];
+    }
+    __syncthreads();
+    for (int cc = threadIdx.x; cc < tc; cc += NT) {
+      float s = 0.f;
+      for (int y = 0; y < nty; ++y) s += sh[(y * nvec + (cc >> 2)) * 4 + (cc & 3)];
+      part[((size_t)blockIdx.y * taps + t) * g.C + c0 + cc] = s;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NT)
+dw_wgrad_final_kernel(const float* __restrict__ part, int n, int splits, float* __restrict__ dw) {
+  const int i = blockIdx.x * NT + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int z = 0; z < splits; ++z) s += part[(size_t)z * n + i];
+  dw[i] = (float)s;
+}
+
+int dw_geom(const pf_conv_desc* d, DwGeom* g, const char* who) {
+  PF_REQUIRE(d != nullptr, "%s: null descriptor", who);
+  PF_REQUIRE(d->n > 0 && d->h > 0 && d->w > 0 && d->c > 0 && d->r > 0 && d->s > 0 && d->p > 0 && d->q > 0 &&
+                 d->stride_h > 0 && d->stride_w > 0 && d->pad_t >= 0 && d->pad_l >= 0,
+             "%s: non-positive dimension", who);
+  PF_REQUIRE((d->c & 3) == 0 && d->k == d->c, "%s: depthwise needs C %% 4 == 0 and k == c (depth multiplier 1)", who);
+  PF_REQUIRE(d->r * d->s <= kMaxTaps, "%s: at most %d taps", who, kMaxTaps);
+  *g = DwGeom{d->n, d->h, d->w, d->c, d->r, d->s, d->p, d->q, d->stride_h, d->stride_w, d->pad_t, d->pad_l};
+  return PF_OK;
+}
+
+inline unsigned dw_grid(int64_t items) {
+  int64_t want = (items + NT - 1) / NT;
+  const int64_t cap = (int64_t)PF_NUM_SMS * 8;
+  if (want < 1) want = 1;
+  return (unsigned)(want < cap ? want : cap);
+}
+
+inline int dw_splits(const DwGeom& g, int* pps) {
+  const int npix = g.N * g.P * g.Q;
+  const int ctiles = (g.C + 127) / 128;
+  int splits = (4 * PF_NUM_SMS + ctiles - 1) / ctiles;
+  const int max_by_pix = (npix + 63) / 64;
+  if (splits > max_by_pix) splits = max_by_pix;
+  if (splits > PF_DWCONV_MAX_SPLITS) splits = PF_DWCONV_MAX_SPLITS;
+  if (splits < 1) splits = 1;
+  *pps = (npix + splits - 1) / splits;
+  return (npix + *pps - 1) / *pps;
+}
+}  // namespace
+
+extern "C" {
+
+int pf_dwconv_fwd(const pf_conv_desc* d, const float* x_dev, const float* w_dev, float* y_dev, void* stream) {
+  DwGeom g;
+  int rc = dw_geom(d, &g, "pf_dwconv_fwd");
+  if (rc) return rc;
+  PF_REQUIRE(x_dev && w_dev && y_dev, "pf_dwconv_fwd: null pointer");
+  dw_fwd_kernel<<<dw_grid((int64_t)g.N * g.P * g.Q * (g.C >> 2)), NT, 0, (cudaStream_t)stream>>>(x_dev, w_dev, g, y_dev);
+  PF_CHECK_LAUNCH("pf_dwconv_fwd");
+  return PF_OK;
+}
+
+int pf_dwconv_dgrad(const pf_conv_desc* d, const float* dy_dev, const float* w_dev, int accumulate, float* dx_dev,
+                    void* stream) {
+  DwGeom g;
+  int rc = dw_geom(d, &g, "pf_dwconv_dgrad");
+  if (rc) return rc;
+  PF_REQUIRE(dy_dev && w_dev && dx_dev, "pf_dwconv_dgrad: null pointer");
+  dw_dgrad_kernel<<<dw_grid((int64_t)g.N * g.H * g.W * (g.C >> 2)), NT, 0, (cudaStream_t)stream>>>(dy_dev, w_dev, g,
+                                                                                                   accumulate, dx_dev);
+  PF_CHECK_LAUNCH("pf_dwconv_dgrad");
+  return PF_OK;
+}
+
+int64_t pf_dwconv_wgrad_workspace_bytes(const pf_conv_desc* d) {
+  DwGeom g;
+  if (!d || dw_geom(d, &g, "pf_dwconv_wgrad_workspace_bytes")) return 0;
+  int pps;
+  const int splits = dw_splits(g, &pps);
+  return (int64_t)splits * g.R * g.S * g.C * 4;
+}
+
+int pf_dwconv_wgrad(const pf_conv_desc* d, const float* x_dev, const float* dy_dev, float* ws_dev, float* dw_dev,
+                    void* stream) {
+  DwGeom g;
+  int rc = dw_geom(d, &g, "pf_dwconv_wgrad");
+  if (rc) return rc;
+  PF_REQUIRE(x_dev && dy_dev && ws_dev && dw_dev, "pf_dwconv_wgrad: null pointer");
+  int pps;
+  const int splits = dw_splits(g, &pps);
+  dim3 grid((g.C + 127) / 128, splits);
+  cudaStream_t st = (cudaStream_t)stream;
+  dw_wgrad_partial_kernel<<<grid, NT, 0, st>>>(x_dev, dy_dev, g, pps, ws_dev);
+  PF_CHECK_LAUNCH("pf_dwconv_wgrad/partial");
+  const int n = g.R * g.S * g.C;
+  dw_wgrad_final_kernel<<<(n + NT - 1) / NT, NT, 0, st>>>(ws_dev, n, splits, dw_dev);
+  PF_CHECK_LAUNCH("pf_dwconv_wgrad/final");
+  return PF_OK;
+}
+
+}  // extern "C"

@@ -248,6 +248,14 @@ class Executor:
                         max_ws = max(max_ws, ops.conv2d_tc_wgrad_workspace_floats(d))
                     max_ws = max(max_ws, ops.conv2d_wgrad_workspace_floats(d))
                     max_wt = max(max_wt, op.vars['kernel'].numel)
+            if op.type == 'DepthwiseConv2dNative':
+                x, y = op.inputs[0], op.output
+                n, h, w, c = x.shape
+                _, p, q, _ = y.shape
+                (kh, kw), (sh, sw), (pt, pl) = op.attrs['ksize'], op.attrs['strides'], op.attrs['pad']
+                self.desc[op] = ops.conv_desc(n, h, w, c, c, kh, kw, p, q, sh, sw, pt, pl)
+                if self.train:
+                    max_ws = max(max_ws, ops.dwconv_wgrad_workspace_floats(self.desc[op]))
             if op.type == 'MaxPool':
                 x, y = op.inputs[0], op.output
                 n, h, w, c = x.shape
@@ -375,13 +383,14 @@ class Executor:
     # ------------------------------------------------------------------ helpers
     def T(self, t):
         """Buffer that holds tensor t as seen by its consumers."""
+        shape = t.shape
         while t in self.alias:
             op = t.op
             if op in self.aq_out:
-                return self.aq_out[op].view(t.shape)
+                return self.aq_out[op].view(shape)
             t = self.alias[t]
         b = self.buf[t]
-        return b if b.shape == t.shape else b.view(t.shape)
+        return b if b.shape == shape else b.view(shape)
 
     def raw(self, t):
         while t in self.alias:
@@ -447,6 +456,9 @@ class Executor:
                     with self.timed('conv_fwd'):
                         ops.conv2d_fwd(self.desc[op], self.T(op.inputs[0]), self.kernel_of(op), bias,
                                        op in self.fused_act, self.buf[op.output])
+            elif ty == 'DepthwiseConv2dNative':
+                with self.timed('dwconv'):
+                    ops.dwconv_fwd(self.desc[op], self.T(op.inputs[0]), self.kernel_of(op), self.buf[op.output])
             elif ty == 'FusedBatchNorm':
                 x, y = self.T(op.inputs[0]), self.buf[op.output]
                 c = y.shape[-1]
@@ -549,6 +561,14 @@ class Executor:
                             ops.conv2d_tc_dgrad(d, gy, self.tc[op], acc, gx)
                         else:
                             ops.conv2d_dgrad(d, gy, self.kernel_of(op), self.wt_ws, acc, gx)
+            elif ty == 'DepthwiseConv2dNative':
+                d = self.desc[op]
+                x_t = op.inputs[0]
+                with self.timed('dwconv'):
+                    ops.dwconv_wgrad(d, self.T(x_t), gy, self.wgrad_ws, st.view(op.vars['kernel'], self.G))
+                    if x_t.op.type != 'Placeholder':
+                        gx, acc = self.grad_target(x_t)
+                        ops.dwconv_dgrad(d, gy, self.kernel_of(op), acc, gx)
             elif ty == 'FusedBatchNorm':
                 x_t = op.inputs[0]
                 y = self.buf[op.output]

@@ -191,8 +191,9 @@ def _pads(padding, k, s, size):
 
 
 def conv2d(inputs, filters, kernel_size, strides=1, padding='valid', use_bias=True,
-           kernel_initializer=None, name=None):
-    """tf.layers.conv2d, NHWC x HWIO.  `padding`: 'same' | 'valid' | ((top,bottom),(left,right))."""
+           kernel_initializer=None, name=None, kernel_name='kernel', bias_name='bias', exact_name=False):
+    """tf.layers.conv2d / slim.conv2d, NHWC x HWIO.  `padding`: 'same' | 'valid' | ((top,bottom),(left,right)).
+    slim layers pass kernel_name='weights', bias_name='biases', exact_name=True (scope given by the caller)."""
     g = get_default_graph()
     n, h, w, c = inputs.shape
     kh, kw = (kernel_size, kernel_size) if isinstance(kernel_size, int) else kernel_size
@@ -200,19 +201,20 @@ def conv2d(inputs, filters, kernel_size, strides=1, padding='valid', use_bias=Tr
     ph, pw = (padding, padding) if isinstance(padding, str) else padding
     pt, p = _pads(ph, kh, sh, h)
     pl, q = _pads(pw, kw, sw, w)
-    lname = g.unique_name(name or 'conv2d')
-    kernel = g.get_variable(lname + '/kernel', (kh, kw, c, filters),
+    lname = (g.scope_prefix() + name) if exact_name else g.unique_name(name or 'conv2d')
+    kernel = g.get_variable(lname + '/' + kernel_name, (kh, kw, c, filters),
                             kernel_initializer or glorot_uniform_initializer())
     vs = {'kernel': kernel}
     if use_bias:
-        vs['bias'] = g.get_variable(lname + '/bias', (filters,), constant_initializer(0.0))
+        vs['bias'] = g.get_variable(lname + '/' + bias_name, (filters,), constant_initializer(0.0))
     op = g.add_op('Conv2D', 'Conv2D', [inputs], vs,
                   dict(strides=(sh, sw), pad=(pt, pl), padding=padding, ksize=(kh, kw)),
                   (n, p, q, filters), name=lname + '/Conv2D')
     return op.output
 
 
-def depthwise_conv2d(inputs, kernel_size, strides=1, padding='same', kernel_initializer=None, name=None):
+def depthwise_conv2d(inputs, kernel_size, strides=1, padding='same', kernel_initializer=None, name=None,
+                     exact_name=False):
     """slim.separable_conv2d(num_outputs=None) depthwise part, depth_multiplier 1; kernel [kh,kw,C,1]."""
     g = get_default_graph()
     n, h, w, c = inputs.shape
@@ -220,7 +222,7 @@ def depthwise_conv2d(inputs, kernel_size, strides=1, padding='same', kernel_init
     sh = sw = strides
     pt, p = _pads(padding, kh, sh, h)
     pl, q = _pads(padding, kw, sw, w)
-    lname = g.unique_name(name or 'depthwise')
+    lname = (g.scope_prefix() + name) if exact_name else g.unique_name(name or 'depthwise')
     kernel = g.get_variable(lname + '/depthwise_weights', (kh, kw, c, 1),
                             kernel_initializer or glorot_uniform_initializer())
     op = g.add_op('DepthwiseConv2dNative', 'depthwise', [inputs], {'kernel': kernel},
@@ -241,11 +243,12 @@ def dense(inputs, units, use_bias=True, kernel_initializer=None, name=None):
     return op.output
 
 
-def batch_normalization(inputs, training, momentum=0.99, epsilon=1e-3, name=None, scope_style='layers'):
-    """tf.layers.batch_normalization (fused).  Variables: gamma, beta, moving_mean, moving_variance."""
+def batch_normalization(inputs, training, momentum=0.99, epsilon=1e-3, name=None, exact_name=False):
+    """tf.layers.batch_normalization / slim.batch_norm (fused).  Variables: gamma, beta, moving_mean,
+    moving_variance."""
     g = get_default_graph()
     c = inputs.shape[-1]
-    lname = g.unique_name(name or 'batch_normalization')
+    lname = (g.scope_prefix() + name) if exact_name else g.unique_name(name or 'batch_normalization')
     vs = {'gamma': g.get_variable(lname + '/gamma', (c,), constant_initializer(1.0)),
           'beta': g.get_variable(lname + '/beta', (c,), constant_initializer(0.0)),
           'moving_mean': g.get_variable(lname + '/moving_mean', (c,), constant_initializer(0.0), trainable=False),
@@ -279,11 +282,30 @@ def max_pooling2d(inputs, pool_size, strides, padding='valid', name=None):
     return op.output
 
 
-def reduce_mean_hw(inputs, name=None):
-    """tf.reduce_mean(x, [1, 2]) followed by squeeze -> [N, C]."""
+def reduce_mean_hw(inputs, name=None, keepdims=False):
+    """tf.reduce_mean(x, [1, 2]) (+ squeeze unless keepdims) -> [N, C] or [N, 1, 1, C]."""
     g = get_default_graph()
     n, h, w, c = inputs.shape
-    return g.add_op('Mean', name or 'Mean', [inputs], {}, {}, (n, c)).output
+    return g.add_op('Mean', name or 'Mean', [inputs], {}, {}, (n, 1, 1, c) if keepdims else (n, c)).output
+
+
+def squeeze_hw(inputs, name=None):
+    """tf.squeeze(x, [1, 2]) on [N,1,1,C]."""
+    g = get_default_graph()
+    n, h, w, c = inputs.shape
+    assert h == 1 and w == 1
+    return g.add_op('Reshape', name or 'SpatialSqueeze', [inputs], {}, {}, (n, c)).output
+
+
+def truncated_normal_initializer(stddev):
+    def init(rng, shape):
+        x = rng.standard_normal(size=shape)
+        bad = np.abs(x) > 2
+        while bad.any():
+            x[bad] = rng.standard_normal(size=int(bad.sum()))
+            bad = np.abs(x) > 2
+        return (x * stddev).astype(np.float32)
+    return init
 
 
 def flatten(inputs, name=None):

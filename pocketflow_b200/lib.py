@@ -48,6 +48,10 @@ SIGNATURES = {
     'pf_conv2d_tc_wgrad_workspace_bytes': (c_i64, [c_vp]),
     'pf_conv2d_tc_wgrad': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'pf_tc_probe': (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32] + [ctypes.c_uint32] * 6 + [c_vp]),
+    'pf_dwconv_fwd': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'pf_dwconv_dgrad': (c_i32, [c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
+    'pf_dwconv_wgrad_workspace_bytes': (c_i64, [c_vp]),
+    'pf_dwconv_wgrad': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'pf_bn_train_stats': (c_i32, [c_vp, c_i64, c_i32, c_f32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'pf_bn_eval_prepare': (c_i32, [c_vp, c_i32, c_f32, c_vp, c_vp]),
     'pf_bn_apply': (c_i32, [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]),

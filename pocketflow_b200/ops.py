@@ -555,3 +555,22 @@ def conv2d_tc_wgrad_workspace_floats(d):
 def conv2d_tc_wgrad(d, x, dy, ws, dw):
     _lib.check(_lib.load().pf_conv2d_tc_wgrad(ctypes.byref(d), _p(x), _p(dy), _p(ws), _p(dw), _stream()),
                'pf_conv2d_tc_wgrad')
+
+
+# ----------------------------------------------------------------------------- depthwise conv
+def dwconv_fwd(d, x, w, y):
+    _lib.check(_lib.load().pf_dwconv_fwd(ctypes.byref(d), _p(x), _p(w), _p(y), _stream()), 'pf_dwconv_fwd')
+
+
+def dwconv_dgrad(d, dy, w, accumulate, dx):
+    _lib.check(_lib.load().pf_dwconv_dgrad(ctypes.byref(d), _p(dy), _p(w), int(bool(accumulate)), _p(dx), _stream()),
+               'pf_dwconv_dgrad')
+
+
+def dwconv_wgrad_workspace_floats(d):
+    return int(_lib.load().pf_dwconv_wgrad_workspace_bytes(ctypes.byref(d))) // 4
+
+
+def dwconv_wgrad(d, x, dy, ws, dw):
+    _lib.check(_lib.load().pf_dwconv_wgrad(ctypes.byref(d), _p(x), _p(dy), _p(ws), _p(dw), _stream()),
+               'pf_dwconv_wgrad')

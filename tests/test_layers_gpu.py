@@ -199,3 +199,32 @@ def test_avgpool_add_relu_colsum_softmax():
     DXs = torch.empty(33, 10, device=DEV)
     ops.softmax_bwd(dp.to(DEV), P, DXs)
     close(DXs, lgd.grad)
+
+
+@pytest.mark.parametrize('cfg', [(2, 12, 12, 32, 3, 1, 1, 1), (3, 15, 15, 16, 3, 2, 0, 1), (2, 14, 14, 64, 3, 2, 0, 1),
+                                 (1, 7, 7, 1024, 3, 1, 1, 1)])
+def test_depthwise_conv_fwd_dgrad_wgrad(cfg):
+    n, h, w, c, k, st, p0, p1 = cfg
+    g = torch.Generator().manual_seed(sum(cfg))
+    x = torch.randn(n, h, w, c, generator=g)
+    wt = torch.randn(k, k, c, 1, generator=g) * 0.3
+    p = (h + p0 + p1 - k) // st + 1
+    xd = x.double().permute(0, 3, 1, 2).requires_grad_(True)
+    wd = wt.double().permute(2, 3, 0, 1).requires_grad_(True)          # [C,1,kh,kw]
+    yd = F.conv2d(F.pad(xd, (p0, p1, p0, p1)), wd, stride=st, groups=c)
+    dy = torch.randn(n, p, p, c, generator=g)
+    yd.backward(dy.double().permute(0, 3, 1, 2))
+    d = ops.conv_desc(n, h, w, c, c, k, k, p, p, st, st, p0, p0)
+    X, W, DY = x.to(DEV), wt.to(DEV).contiguous(), dy.to(DEV)
+    Y = torch.empty(n, p, p, c, device=DEV)
+    ops.dwconv_fwd(d, X, W, Y)
+    close(Y, yd.permute(0, 2, 3, 1))
+    DX = torch.full((n, h, w, c), 2.0, device=DEV)
+    ops.dwconv_dgrad(d, DY, W, False, DX)
+    close(DX, xd.grad.permute(0, 2, 3, 1))
+    ops.dwconv_dgrad(d, DY, W, True, DX)
+    close(DX, 2 * xd.grad.permute(0, 2, 3, 1))
+    ws = torch.empty(max(ops.dwconv_wgrad_workspace_floats(d), 4), device=DEV)
+    DW = torch.empty_like(W)
+    ops.dwconv_wgrad(d, X, DY, ws, DW)
+    close(DW, wd.grad.permute(2, 3, 0, 1))

@@ -137,3 +137,48 @@ def test_uniform_learner_trains_and_evaluates():
     lrn.train(nb_iters=6)            # includes the CUDA-graph-free eager loop, logging, final save + evaluate
     r = lrn.sess_train.fetch_losses()
     assert np.isfinite(r['loss']) and lrn.sess_train.step_count == 6
+
+
+def make_mobilenet(learner, **flags):
+    FLAGS.reset()
+    import importlib
+    import pocketflow_b200.datasets.ilsvrc12_dataset as D
+    importlib.reload(D)
+    from pocketflow_b200.nets import mobilenet_at_ilsvrc12 as M
+    importlib.reload(M)
+    from pocketflow_b200.learners.learner_utils import create_learner
+    import pocketflow_b200.learners.channel_pruning_gpu.learner  # noqa: F401
+    FLAGS.batch_size, FLAGS.learner, FLAGS.nb_classes = 2, learner, 1001
+    for k, v in flags.items():
+        setattr(FLAGS, k, v)
+    return create_learner(None, M.ModelHelper())
+
+
+def test_mobilenet_channel_pruned_gpu_learner_step(monkeypatch):
+    """Config 4 steady state: MobileNet-v1, input-channel masks on the 13 interior pointwise kernels,
+    masked Momentum step; loss vs the oracle step with the same masks; pruned channels stay zero."""
+    monkeypatch.setenv('PF_CONV_PATH', 'fp32')
+    lrn = make_mobilenet('chn-pruned-gpu', cpg_prune_ratio=0.5)
+    ex = lrn.sess_train
+    assert len(lrn.maskable_vars) == 15 and sum(v.numel for v in lrn.maskable_vars) == 4165472
+    assert lrn.prune_ratios[0] == 0.0 and lrn.prune_ratios[-1] == 0.0 and lrn.prune_ratios[5] == 0.5
+    masks = {v.name: ex.store.view(v, ex.MASK).cpu().numpy().copy() for v in lrn.maskable_vars}
+    for v in lrn.maskable_vars[1:-1]:
+        m = masks[v.name]
+        per_cin = m.reshape(-1, m.shape[2], m.shape[3]).max(axis=(0, 2))
+        assert abs(per_cin.mean() - 0.5) < 0.02                           # half of the input channels kept
+        assert np.all(ex.store.view(v).cpu().numpy()[m == 0] == 0)
+    orc = StepOracle(ex.ops, ex.logits_t, lrn.images, lrn.labels, ex.loss)
+    state = ex.store.state_dict()
+    images, labels = lrn.iterator_train.next_batch()
+    ex.buf[lrn.images].copy_(images)
+    ex.buf[lrn.labels].copy_(labels)
+    lr = lrn.lrn_rate(0)
+    ex.run_step(lr)
+    got = ex.fetch_losses()
+    ref, new_state, _ = orc.step(state, images.numpy(), labels.numpy(), dict(kind='momentum', slots={}, momentum=0.9),
+                                 lr, masks=masks)
+    for k in ('ce', 'l2', 'loss'):
+        assert rel(got[k], ref[k]) <= 1e-5, (k, got[k], ref[k])
+    for v in lrn.maskable_vars[1:-1]:
+        assert np.all(ex.store.view(v).cpu().numpy()[masks[v.name] == 0] == 0)
