@@ -15,6 +15,10 @@
 // each: 64 contiguous channels of one tap = 256 B), split, and written to 128B-swizzled K-major smem
 // tiles; one elected thread issues the MMAs; accumulators live in TMEM; the producer warps then run
 // the epilogue (tcgen05.ld -> global NHWC fp32).  mbarrier ring of kStages smem stages.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
 #include "pf_common.cuh"
 #include "pf_tc_common.cuh"
 
@@ -290,6 +294,369 @@ conv_tc_kernel(const float* __restrict__ src, const __nv_bfloat16* __restrict__ 
 }
 
 
+
+// =============================================================================================
+// v4: PERSISTENT, warp-specialised fwd / dgrad kernel.  One CTA per SM loops over output tiles;
+//   warps 0-3   epilogue  (TMEM -> registers -> per-warp smem transpose -> coalesced global; bias / ReLU /
+//               residual / accumulate), overlapped with the next tile's main loop through a DOUBLE-BUFFERED
+//               TMEM accumulator (2 x BN columns);
+//   warps 4-11  producers (A gather + fp32 -> split-bf16 conversion with a register ping-pong that runs
+//               across tile boundaries; B via cp.async);
+//   warp  12    MMA issuer (one elected thread) + TMEM allocation.
+// BN goes up to 256 (A is read once for 256 output channels).  When one n-tile covers all output channels and
+// the whole split weight matrix fits next to >= 2 A stages, B is loaded ONCE per CTA and stays resident
+// ("B-stationary": every 1x1 layer of the early stages, K <= 256).
+// MODE 2 = dgrad of a strided convolution decomposed into stride_h*stride_w pixel-parity classes: the rows of
+// a tile all belong to one class (h = ph + sh*h', w = pw + sw*w'), and only the filter taps that can reach that
+// class are visited, so no MMA multiplies structural zeros (the gather-with-divisibility-test formulation of
+// MODE 1 wastes 3/4 of the tensor-core work of a 3x3 stride-2 layer).
+struct FastDiv {
+  uint32_t mul, shift;
+};
+inline FastDiv make_fastdiv(uint32_t d) {   // exact for 0 <= n < 2^31 (Granlund-Montgomery round-up method)
+  FastDiv f;
+  uint32_t s = 0;
+  while ((1ull << s) < d) ++s;
+  f.shift = s;
+  f.mul = (uint32_t)((((1ull << 32) * ((1ull << s) - d)) / d) + 1);
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, FastDiv f) { return (__umulhi(n, f.mul) + n) >> f.shift; }
+
+constexpr int kMaxClasses = 4;
+constexpr int kMaxTaps = 9;
+struct TcClass {
+  int tile_begin, Mc, Hc, Wc, ph, pw, ntaps, pad_;
+  FastDiv d_hw, d_w;
+  int8_t eh[kMaxTaps + 3], ew[kMaxTaps + 3], tap[kMaxTaps + 3];
+};
+struct TcP {
+  TcGeom g;
+  int M, Ng, Kdim, Kpad, BN, nk, n_stages, n_bslots, b_stationary, m_tiles, n_tiles, total_tiles, acc_cols;
+  int accumulate, relu, ncls, cblocks;
+  FastDiv d_hw, d_w, d_cc, d_s, d_ntiles, d_cblocks;
+  TcClass cls[kMaxClasses];
+};
+
+constexpr int kEpiWarps = 4, kProdWarps = 8;
+constexpr int kThreadsP = (kEpiWarps + kProdWarps + 1) * 32;   // 416
+constexpr int kStagePitch = 36;                                // floats per staged row (32 + 4: conflict-free)
+
+template <int MODE>
+__device__ __forceinline__ int tile_class(const TcP& p, int mt) {
+  int ci = 0;
+  if (MODE == 2) {
+#pragma unroll
+    for (int j = 1; j < kMaxClasses; ++j)
+      if (j < p.ncls && mt >= p.cls[j].tile_begin) ci = j;
+  }
+  return ci;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreadsP, 1)
+conv_tc_persist_kernel(const float* __restrict__ src, const __nv_bfloat16* __restrict__ b_hi,
+                       const __nv_bfloat16* __restrict__ b_lo, float* __restrict__ out,
+                       const float* __restrict__ bias, const float* __restrict__ residual,
+                       const __grid_constant__ TcP p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const TcGeom& g = p.g;
+  const int BN = p.BN;
+  const uint32_t a_bytes = TM * 128, b_bytes = (uint32_t)BN * 128;
+  uint8_t* smem_a = smem;                                           // n_stages x (hi, lo)
+  uint8_t* smem_b = smem + (size_t)p.n_stages * 2 * a_bytes;        // n_bslots x (hi, lo)
+  float* stage_all = reinterpret_cast<float*>(smem_b + (size_t)p.n_bslots * 2 * b_bytes);
+  long long* rowoff_all = reinterpret_cast<long long*>(stage_all + kEpiWarps * 32 * kStagePitch);
+  __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < p.n_stages; ++s) {
+      mbar_init(&full_bar[s], kProdWarps * 32);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], kEpiWarps * 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kEpiWarps + kProdWarps) tmem_alloc(&tmem_base_s, (uint32_t)(2 * p.acc_cols));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int first_tile = blockIdx.x, tile_step = gridDim.x;
+
+  if (warp >= kEpiWarps && warp < kEpiWarps + kProdWarps) {
+    // =================================== producers ===================================
+    const int pt_ = tid - kEpiWarps * 32;
+    const int l8 = pt_ & 7, rgrp = pt_ >> 3;          // 32-byte slice of the row, row group (rows rgrp + 32*i)
+    const int CC = (MODE == 0) ? g.C : g.K;           // channels of the gathered tensor
+    const uint32_t chunk_off = (((uint32_t)l8) ^ (uint32_t)(rgrp & 7)) << 4;
+    auto tile_nk = [&](int tile) -> int {
+      if (MODE != 2) return p.nk;
+      const int mt = (int)fdiv((uint32_t)tile, p.d_ntiles);
+      return p.cls[tile_class<MODE>(p, mt)].ntaps * p.cblocks;
+    };
+    auto issue_loads_a = [&](int tile, int ks, float4 (&av)[8]) {
+      const int mt = (int)fdiv((uint32_t)tile, p.d_ntiles);
+      const float* ptr[4] = {nullptr, nullptr, nullptr, nullptr};
+      if (MODE != 2) {
+        const int kk = ks * BK + (l8 >> 1) * 16;      // this lane's 16-channel sub-chunk: inside one filter tap
+        const int tap = (int)fdiv((uint32_t)kk, p.d_cc);
+        const int c = kk - tap * CC + (l8 & 1) * 8;
+        const int r = (int)fdiv((uint32_t)tap, p.d_s), q = tap - r * g.S;
+        const int hw = (MODE == 0) ? g.P * g.Q : g.H * g.W;
+        const int wq = (MODE == 0) ? g.Q : g.W;
+        const bool unit_stride = g.sh == 1 && g.sw == 1;
+        if (kk < p.Kdim) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int m = mt * TM + rgrp + 32 * i;
+            if (m < p.M) {
+              const int n_ = (int)fdiv((uint32_t)m, p.d_hw);
+              const int rem = m - n_ * hw;
+              const int y = (int)fdiv((uint32_t)rem, p.d_w), x = rem - y * wq;
+              if (MODE == 0) {
+                const int ih = y * g.sh - g.pt + r, iw = x * g.sw - g.pl + q;
+                if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) ptr[i] = src + (((size_t)n_ * g.H + ih) * g.W + iw) * g.C + c;
+              } else {
+                const int th = y + g.pt - r, tw = x + g.pl - q;
+                if (th >= 0 && tw >= 0) {
+                  if (unit_stride) {
+                    if (th < g.P && tw < g.Q) ptr[i] = src + (((size_t)n_ * g.P + th) * g.Q + tw) * g.K + c;
+                  } else {
+                    const int oh = th / g.sh, ow = tw / g.sw;
+                    if (oh * g.sh == th && ow * g.sw == tw && oh < g.P && ow < g.Q)
+                      ptr[i] = src + (((size_t)n_ * g.P + oh) * g.Q + ow) * g.K + c;
+                  }
+                }
+              }
+            }
+          }
+        }
+      } else {
+        const TcClass& k = p.cls[tile_class<MODE>(p, mt)];
+        const int tap_i = (int)fdiv((uint32_t)ks, p.d_cblocks);
+        const int c = (ks - tap_i * p.cblocks) * BK + l8 * 8;
+        const int eh = k.eh[tap_i], ew = k.ew[tap_i];
+        const int hwc = k.Hc * k.Wc;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int mc = (mt - k.tile_begin) * TM + rgrp + 32 * i;
+          if (mc < k.Mc) {
+            const int n_ = (int)fdiv((uint32_t)mc, k.d_hw);
+            const int rem = mc - n_ * hwc;
+            const int y = (int)fdiv((uint32_t)rem, k.d_w), x = rem - y * k.Wc;
+            const int oh = y + eh, ow = x + ew;
+            if (oh >= 0 && oh < g.P && ow >= 0 && ow < g.Q) ptr[i] = src + (((size_t)n_ * g.P + oh) * g.Q + ow) * g.K + c;
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        av[2 * i] = ptr[i] ? __ldg(reinterpret_cast<const float4*>(ptr[i])) : make_float4(0.f, 0.f, 0.f, 0.f);
+        av[2 * i + 1] = ptr[i] ? __ldg(reinterpret_cast<const float4*>(ptr[i]) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    uint32_t it = 0;                                   // global k-stage counter of this CTA (ring position)
+    auto do_stage = [&](int tile, int ks, bool first, const float4 (&av)[8]) {
+      const uint32_t s = it % (uint32_t)p.n_stages;
+      mbar_wait(&empty_bar[s], ((it / (uint32_t)p.n_stages) & 1u) ^ 1u);   // slot free?
+      uint8_t* sa = smem_a + (size_t)s * 2 * a_bytes;
+      if (!p.b_stationary || first) {
+        const int mt = (int)fdiv((uint32_t)tile, p.d_ntiles);
+        const int n0 = (tile - mt * p.n_tiles) * BN;
+        uint8_t* sb = smem_b + (size_t)(p.b_stationary ? ks : (int)s) * 2 * b_bytes;
+        size_t kcol;
+        if (MODE == 2) {
+          const TcClass& k = p.cls[tile_class<MODE>(p, mt)];
+          const int tap_i = (int)fdiv((uint32_t)ks, p.d_cblocks);
+          kcol = (size_t)k.tap[tap_i] * g.K + (size_t)(ks - tap_i * p.cblocks) * BK + l8 * 8;
+        } else {
+          kcol = (size_t)ks * BK + l8 * 8;
+        }
+        for (int br = rgrp; br < BN; br += 32) {
+          const bool ok = n0 + br < p.Ng;
+          const size_t off = (size_t)(ok ? n0 + br : 0) * p.Kpad + kcol;
+          const uint32_t dst = smem_u32(sb + (size_t)br * 128 + chunk_off);
+          const uint32_t nbytes = ok ? 16u : 0u;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(b_hi + off), "r"(nbytes) : "memory");
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + b_bytes), "l"(b_lo + off), "r"(nbytes) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint2 h0, l0, h1, l1;
+        split4(av[2 * i], h0, l0);
+        split4(av[2 * i + 1], h1, l1);
+        uint8_t* rowp = sa + (size_t)(rgrp + 32 * i) * 128 + chunk_off;
+        *reinterpret_cast<uint4*>(rowp) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+        *reinterpret_cast<uint4*>(rowp + a_bytes) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      fence_proxy_async_smem();   // generic-proxy + cp.async writes -> visible to the tensor core (async proxy)
+      mbar_arrive(&full_bar[s]);
+      ++it;
+    };
+    // flat (tile, k-stage) iteration with a two-deep register ping-pong
+    int t0 = first_tile, k0 = 0, nk0 = (t0 < p.total_tiles) ? tile_nk(t0) : 0;
+    while (t0 < p.total_tiles && nk0 == 0) { t0 += tile_step; nk0 = (t0 < p.total_tiles) ? tile_nk(t0) : 0; }
+    auto advance = [&](int& t, int& k, int& nkt) {
+      if (++k >= nkt) {
+        k = 0;
+        do {
+          t += tile_step;
+          nkt = (t < p.total_tiles) ? tile_nk(t) : 0;
+        } while (t < p.total_tiles && nkt == 0);     // zero-tap classes have no main loop
+      }
+    };
+    if (t0 < p.total_tiles) {
+      float4 a0[8], a1[8];
+      issue_loads_a(t0, k0, a0);
+      while (true) {
+        int t1 = t0, k1 = k0, nk1 = nk0;
+        advance(t1, k1, nk1);
+        const bool v1 = t1 < p.total_tiles;
+        if (v1) issue_loads_a(t1, k1, a1);
+        do_stage(t0, k0, t0 == first_tile, a0);
+        if (!v1) break;
+        int t2 = t1, k2 = k1, nk2 = nk1;
+        advance(t2, k2, nk2);
+        const bool v2 = t2 < p.total_tiles;
+        if (v2) issue_loads_a(t2, k2, a0);
+        do_stage(t1, k1, t1 == first_tile, a1);
+        if (!v2) break;
+        t0 = t2; k0 = k2; nk0 = nk2;
+      }
+    }
+  } else if (warp == kEpiWarps + kProdWarps) {
+    // =================================== MMA issuer ===================================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(TM, BN, 0, 0);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++tcount) {
+        int nk = p.nk;
+        if (MODE == 2) nk = p.cls[tile_class<MODE>(p, (int)fdiv((uint32_t)tile, p.d_ntiles))].ntaps * p.cblocks;
+        const uint32_t buf = tcount & 1u;
+        mbar_wait(&tempty_bar[buf], ((tcount >> 1) & 1u) ^ 1u);     // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * (uint32_t)p.acc_cols;
+        for (int ks = 0; ks < nk; ++ks, ++it) {
+          const uint32_t s = it % (uint32_t)p.n_stages;
+          mbar_wait(&full_bar[s], (it / (uint32_t)p.n_stages) & 1u);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(smem_a + (size_t)s * 2 * a_bytes), a_lo = a_hi + a_bytes;
+          const uint32_t bh = smem_u32(smem_b + (size_t)(p.b_stationary ? ks : (int)s) * 2 * b_bytes), bl = bh + b_bytes;
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t dah = make_smem_desc(a_hi + kk * 32, 16, 1024);
+            const uint64_t dal = make_smem_desc(a_lo + kk * 32, 16, 1024);
+            const uint64_t dbh = make_smem_desc(bh + kk * 32, 16, 1024);
+            const uint64_t dbl = make_smem_desc(bl + kk * 32, 16, 1024);
+            umma_bf16(d_tmem, dah, dbh, idesc, (ks > 0 || kk > 0) ? 1u : 0u);
+            umma_bf16(d_tmem, dah, dbl, idesc, 1u);
+            umma_bf16(d_tmem, dal, dbh, idesc, 1u);
+          }
+          umma_commit(&empty_bar[s]);   // frees the A (and ring B) stage when these MMAs have completed
+        }
+        if (nk > 0) umma_commit(&tfull_bar[buf]);   // accumulator of this tile complete
+        else mbar_arrive(&tfull_bar[buf]);          // zero-tap class: nothing was issued, the epilogue writes zeros
+      }
+    }
+  } else {
+    // =================================== epilogue (warps 0-3) ===================================
+    float* stg = stage_all + (size_t)warp * 32 * kStagePitch;
+    long long* rowoff = rowoff_all + warp * 32;
+    const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
+    const float* extra = residual ? residual : (p.accumulate ? out : nullptr);
+    uint32_t tcount = 0;
+    for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++tcount) {
+      const int mt = (int)fdiv((uint32_t)tile, p.d_ntiles);
+      const int n0 = (tile - mt * p.n_tiles) * BN;
+      bool zero_tile = false;
+      {   // global element offset of this lane's row (-1: beyond the problem)
+        long long off = -1;
+        if (MODE != 2) {
+          const int m = mt * TM + warp * 32 + lane;
+          if (m < p.M) off = (long long)m * p.Ng;
+        } else {
+          const TcClass& k = p.cls[tile_class<MODE>(p, mt)];
+          zero_tile = k.ntaps == 0;
+          const int mc = (mt - k.tile_begin) * TM + warp * 32 + lane;
+          if (mc < k.Mc) {
+            const int hwc = k.Hc * k.Wc;
+            const int n_ = (int)fdiv((uint32_t)mc, k.d_hw);
+            const int rem = mc - n_ * hwc;
+            const int y = (int)fdiv((uint32_t)rem, k.d_w), x = rem - y * k.Wc;
+            off = (((long long)n_ * g.H + (k.ph + y * g.sh)) * g.W + (k.pw + x * g.sw)) * g.C;
+          }
+        }
+        rowoff[lane] = off;
+      }
+      const uint32_t buf = tcount & 1u;
+      mbar_wait(&tfull_bar[buf], (tcount >> 1) & 1u);
+      tc_fence_after();
+      __syncwarp();
+      const uint32_t t_addr = tmem_base + buf * (uint32_t)p.acc_cols + lane_base;
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        if (!zero_tile) {
+          tmem_ld_32x32(t_addr + (uint32_t)c0, r);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = 0u;
+        }
+        if (c0 + 32 >= BN) {                         // last read of this accumulator: hand it back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&tempty_bar[buf]);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<uint4*>(stg + lane * kStagePitch + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+        __syncwarp();
+        // rows 4*j + (lane >> 3), 16-byte chunk (lane & 7): 8 lanes write one row's 128 contiguous bytes
+        const int cv = c0 + (lane & 7) * 4;
+        const bool cok = cv < BN && n0 + cv + 3 < p.Ng;
+        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias && cok) bb = __ldg(reinterpret_cast<const float4*>(bias + n0 + cv));
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float4 xv[4];
+          long long ro[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int rr = 4 * (half * 4 + u) + (lane >> 3);
+            ro[u] = cok ? rowoff[rr] : -1;
+            xv[u] = (extra && ro[u] >= 0) ? *reinterpret_cast<const float4*>(extra + ro[u] + n0 + cv)
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (ro[u] < 0) continue;
+            const int rr = 4 * (half * 4 + u) + (lane >> 3);
+            float4 v = *reinterpret_cast<const float4*>(stg + rr * kStagePitch + (lane & 7) * 4);
+            if (bias) { v.x = __fadd_rn(v.x, bb.x); v.y = __fadd_rn(v.y, bb.y); v.z = __fadd_rn(v.z, bb.z); v.w = __fadd_rn(v.w, bb.w); }
+            if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            if (extra) {   // fused residual add (resnet_model.py:199,314) or dx += (gradient accumulation)
+              v.x = __fadd_rn(v.x, xv[u].x); v.y = __fadd_rn(v.y, xv[u].y); v.z = __fadd_rn(v.z, xv[u].z); v.w = __fadd_rn(v.w, xv[u].w);
+            }
+            *reinterpret_cast<float4*>(out + ro[u] + n0 + cv) = v;
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kEpiWarps + kProdWarps) tmem_dealloc(tmem_base, (uint32_t)(2 * p.acc_cols));
+}
+
 // ---------------------------------------------------------------------------------------------
 // wgrad on tensor cores:  dW[kf][co] = sum_pix im2col(x)[pix][kf] * dy[pix][co]
 // GEMM with M = kf = (r,s,c) tile of 128, N = cout tile, K = pixels; BOTH operands are MN-major
@@ -512,8 +879,8 @@ int tc_geom(const pf_conv_desc* d, TcGeom* g, const char* who) {
 inline int pad64(int64_t k) { return (int)((k + 63) / 64 * 64); }
 
 template <int MODE>
-int launch_tc(const TcGeom& g, const float* src, const void* b_hi, const void* b_lo, float* out, int accumulate,
-              const float* bias, int relu, const float* residual, cudaStream_t st, const char* who) {
+int launch_tc_v3(const TcGeom& g, const float* src, const void* b_hi, const void* b_lo, float* out, int accumulate,
+                 const float* bias, int relu, const float* residual, cudaStream_t st, const char* who) {
   const int64_t M64 = (MODE == 0) ? (int64_t)g.N * g.P * g.Q : (int64_t)g.N * g.H * g.W;
   PF_REQUIRE(M64 < (1ll << 31), "%s: too many rows", who);
   const int M = (int)M64;
@@ -542,6 +909,129 @@ int launch_tc(const TcGeom& g, const float* src, const void* b_hi, const void* b
   }
   PF_CHECK_LAUNCH(who);
   return PF_OK;
+}
+
+inline int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+constexpr int kSmemLimit = 232448;   // 227 KB opt-in maximum of dynamic shared memory per CTA on sm_100
+
+template <int MODE>
+int launch_persist(const TcGeom& g, TcP& p, const float* src, const void* b_hi, const void* b_lo, float* out,
+                   const float* bias, const float* residual, cudaStream_t st, const char* who) {
+  const int Ng = p.Ng;
+  // ---- tile width: wide tiles read A once per 256 channels, but quantise worse over the 148 SMs
+  int BN;
+  if (Ng >= 256) {
+    const int64_t t256 = (int64_t)p.m_tiles * ((Ng + 255) / 256), t128 = (int64_t)p.m_tiles * ((Ng + 127) / 128);
+    const double c256 = (double)((t256 + PF_NUM_SMS - 1) / PF_NUM_SMS) * 1.8;
+    const double c128 = (double)((t128 + PF_NUM_SMS - 1) / PF_NUM_SMS);
+    BN = c256 <= c128 ? 256 : 128;
+  } else {
+    BN = Ng >= 128 ? 128 : (Ng >= 64 ? 64 : (Ng >= 32 ? 32 : 16));
+  }
+  const int forced = env_int("PF_TC_BN", 0);           // development knob
+  if (forced >= 16 && forced <= 256 && forced <= ((Ng + 15) / 16) * 16 && (forced & (forced - 1)) == 0) BN = forced;
+  p.BN = BN;
+  p.n_tiles = (Ng + BN - 1) / BN;
+  p.total_tiles = p.m_tiles * p.n_tiles;
+  p.d_ntiles = make_fastdiv((uint32_t)p.n_tiles);
+  p.acc_cols = 32;
+  while (p.acc_cols < BN) p.acc_cols <<= 1;
+  // ---- shared memory plan
+  const int a_stage = 2 * TM * 128, b_slot = 2 * BN * 128;
+  const int fixed = 1024 + kEpiWarps * 32 * kStagePitch * 4 + kEpiWarps * 32 * 8 + 256;
+  const int budget = kSmemLimit - fixed;
+  int max_nk = p.nk;
+  if (MODE == 2) {
+    max_nk = 0;
+    for (int c = 0; c < p.ncls; ++c) max_nk = std::max(max_nk, p.cls[c].ntaps * p.cblocks);
+  }
+  p.b_stationary = 0;
+  if (MODE != 2 && p.n_tiles == 1 && p.nk <= kMaxStages * 4 && (int64_t)p.nk * b_slot + 2 * a_stage <= budget &&
+      env_int("PF_TC_STATIONARY", 1)) {
+    p.b_stationary = 1;
+    p.n_bslots = p.nk;
+    p.n_stages = std::min(kMaxStages, (budget - p.nk * b_slot) / a_stage);
+  } else {
+    p.n_stages = std::min(kMaxStages, budget / (a_stage + b_slot));
+    p.n_bslots = p.n_stages;
+  }
+  PF_REQUIRE(p.n_stages >= 2 || max_nk <= 1, "%s: shared-memory plan failed (BN %d)", who, BN);
+  if (p.n_stages < 1) p.n_stages = 1;
+  const size_t smem = (size_t)p.n_stages * a_stage + (size_t)p.n_bslots * b_slot + fixed;
+  auto kern = conv_tc_persist_kernel<MODE>;
+  PF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = std::min(p.total_tiles, PF_NUM_SMS);
+  kern<<<grid, kThreadsP, smem, st>>>(src, (const __nv_bfloat16*)b_hi, (const __nv_bfloat16*)b_lo, out, bias, residual, p);
+  PF_CHECK_LAUNCH(who);
+  return PF_OK;
+}
+
+template <int MODE>
+int launch_tc(const TcGeom& g, const float* src, const void* b_hi, const void* b_lo, float* out, int accumulate,
+              const float* bias, int relu, const float* residual, cudaStream_t st, const char* who) {
+  static const int impl = env_int("PF_TC_IMPL", 4);
+  if (impl == 3) return launch_tc_v3<MODE>(g, src, b_hi, b_lo, out, accumulate, bias, relu, residual, st, who);
+  const int64_t M64 = (MODE == 0) ? (int64_t)g.N * g.P * g.Q : (int64_t)g.N * g.H * g.W;
+  PF_REQUIRE(M64 < (1ll << 31), "%s: too many rows", who);
+  TcP p;
+  memset(&p, 0, sizeof(p));
+  p.g = g;
+  p.M = (int)M64;
+  p.Ng = (MODE == 0) ? g.K : g.C;
+  p.Kdim = (MODE == 0) ? g.R * g.S * g.C : g.R * g.S * g.K;
+  p.Kpad = pad64(p.Kdim);
+  p.nk = p.Kpad / BK;
+  p.accumulate = accumulate;
+  p.relu = relu;
+  const int CC = (MODE == 0) ? g.C : g.K;
+  const int hw = (MODE == 0) ? g.P * g.Q : g.H * g.W, wq = (MODE == 0) ? g.Q : g.W;
+  p.d_hw = make_fastdiv((uint32_t)hw);
+  p.d_w = make_fastdiv((uint32_t)wq);
+  p.d_cc = make_fastdiv((uint32_t)CC);
+  p.d_s = make_fastdiv((uint32_t)g.S);
+  p.cblocks = std::max(1, g.K / BK);
+  p.d_cblocks = make_fastdiv((uint32_t)p.cblocks);
+  p.m_tiles = (p.M + TM - 1) / TM;
+  if (MODE == 1 && (g.sh > 1 || g.sw > 1) && g.sh * g.sw <= kMaxClasses && g.R * g.S <= kMaxTaps && g.K % BK == 0 &&
+      env_int("PF_TC_CLASSES", 1)) {
+    // pixel-parity classes of the strided dgrad
+    int tiles = 0;
+    for (int ph = 0; ph < g.sh; ++ph)
+      for (int pw = 0; pw < g.sw; ++pw) {
+        if (ph >= g.H || pw >= g.W) continue;
+        TcClass& k = p.cls[p.ncls];
+        k.ph = ph;
+        k.pw = pw;
+        k.Hc = (g.H - ph + g.sh - 1) / g.sh;
+        k.Wc = (g.W - pw + g.sw - 1) / g.sw;
+        k.Mc = g.N * k.Hc * k.Wc;
+        k.tile_begin = tiles;
+        k.d_hw = make_fastdiv((uint32_t)(k.Hc * k.Wc));
+        k.d_w = make_fastdiv((uint32_t)k.Wc);
+        k.ntaps = 0;
+        for (int r = 0; r < g.R; ++r) {
+          const int nh = ph + g.pt - r;
+          if (((nh % g.sh) + g.sh) % g.sh != 0) continue;
+          for (int q = 0; q < g.S; ++q) {
+            const int nw = pw + g.pl - q;
+            if (((nw % g.sw) + g.sw) % g.sw != 0) continue;
+            k.eh[k.ntaps] = (int8_t)(nh / g.sh);
+            k.ew[k.ntaps] = (int8_t)(nw / g.sw);
+            k.tap[k.ntaps] = (int8_t)(r * g.S + q);
+            ++k.ntaps;
+          }
+        }
+        tiles += (k.Mc + TM - 1) / TM;
+        ++p.ncls;
+      }
+    p.m_tiles = tiles;
+    return launch_persist<2>(g, p, src, b_hi, b_lo, out, bias, residual, st, who);
+  }
+  return launch_persist<MODE>(g, p, src, b_hi, b_lo, out, bias, residual, st, who);
 }
 
 }  // namespace

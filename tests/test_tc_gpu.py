@@ -57,6 +57,16 @@ CASES = [
     (1, 7, 7, 512, 512, 3, 3, 1, 1, 1),
     (5, 10, 10, 32, 64, 5, 5, 1, 0, 0),
     (2, 32, 32, 16, 16, 3, 3, 1, 1, 1),
+    # persistent kernel: several tiles per CTA, B-stationary 1x1 layers, 256-wide tiles, ragged channel tiles
+    (8, 56, 56, 64, 256, 1, 1, 1, 0, 0),
+    (8, 56, 56, 256, 64, 1, 1, 1, 0, 0),
+    (2, 14, 14, 64, 192, 3, 3, 1, 1, 1),
+    (6, 28, 28, 128, 512, 1, 1, 1, 0, 0),
+    # strided dgrad by pixel-parity classes (Cout % 64 == 0): 'SAME' pads 0/1 and 1/1, odd sizes, 1x1 stride 2
+    (16, 28, 28, 128, 128, 3, 3, 2, 0, 1),
+    (4, 15, 15, 64, 128, 3, 3, 2, 1, 1),
+    (2, 14, 14, 256, 512, 1, 1, 2, 0, 0),
+    (3, 13, 16, 32, 64, 3, 3, 2, 1, 1),
 ]
 
 

@@ -1,0 +1,83 @@
+"""Per-layer timing of the tcgen05 conv kernels (fwd / dgrad / wgrad) at ResNet-50 / batch-256 shapes.
+usage: python tools/bench_conv_tc.py [tag]   (env PF_TC_IMPL / PF_TC_BN select kernel variants)"""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pocketflow_b200 import ops  # noqa: E402
+
+SHAPES = [  # (name, n, h, w, c, k, r, s, stride, pad, count in ResNet-50)
+    ('s1 1x1 64->64', 256, 56, 56, 64, 64, 1, 1, 1, 0, 1),
+    ('s1 1x1 64->256', 256, 56, 56, 64, 256, 1, 1, 1, 0, 4),
+    ('s1 1x1 256->64', 256, 56, 56, 256, 64, 1, 1, 1, 0, 2),
+    ('s1 3x3 64->64', 256, 56, 56, 64, 64, 3, 3, 1, 1, 3),
+    ('s2 1x1 256->128', 256, 56, 56, 256, 128, 1, 1, 1, 0, 1),
+    ('s2 3x3 s2 128->128', 256, 56, 56, 128, 128, 3, 3, 2, 1, 1),
+    ('s2 1x1 s2 256->512', 256, 56, 56, 256, 512, 1, 1, 2, 0, 1),
+    ('s2 3x3 128->128', 256, 28, 28, 128, 128, 3, 3, 1, 1, 3),
+    ('s2 1x1 128->512', 256, 28, 28, 128, 512, 1, 1, 1, 0, 4),
+    ('s2 1x1 512->128', 256, 28, 28, 512, 128, 1, 1, 1, 0, 3),
+    ('s3 3x3 256->256', 256, 14, 14, 256, 256, 3, 3, 1, 1, 5),
+    ('s3 1x1 256->1024', 256, 14, 14, 256, 1024, 1, 1, 1, 0, 6),
+    ('s3 1x1 1024->256', 256, 14, 14, 1024, 256, 1, 1, 1, 0, 5),
+    ('s4 3x3 512->512', 256, 7, 7, 512, 512, 3, 3, 1, 1, 2),
+    ('s4 1x1 512->2048', 256, 7, 7, 512, 2048, 1, 1, 1, 0, 3),
+    ('s4 1x1 2048->512', 256, 7, 7, 2048, 512, 1, 1, 1, 0, 2),
+]
+
+
+def timeit(fn, iters=5):
+    for _ in range(2):
+        fn()
+    ts = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return sorted(ts)[len(ts) // 2]
+
+
+def main():
+    tag = sys.argv[1] if len(sys.argv) > 1 else 'run'
+    passes = os.environ.get('PASSES', 'fwd,dgrad,wgrad').split(',')
+    dev = torch.device('cuda:0')
+    res, tot = [], {}
+    for name, n, h, w, c, k, r, s, st, pd, cnt in SHAPES:
+        p = (h + 2 * pd - r) // st + 1
+        d = ops.conv_desc(n, h, w, c, k, r, s, p, p, st, st, pd, pd)
+        x = torch.randn(n, h, w, c, device=dev)
+        wt = torch.randn(r, s, c, k, device=dev) * 0.05
+        y = torch.empty(n, p, p, k, device=dev)
+        dy = torch.randn(n, p, p, k, device=dev)
+        dx = torch.empty_like(x)
+        dw = torch.empty_like(wt)
+        tw = ops.TcWeights(d, dev)
+        tw.prepare(wt)
+        ws = torch.empty(max(ops.conv2d_tc_wgrad_workspace_floats(d), 4), device=dev)
+        fl = 2.0 * n * p * p * k * r * s * c
+        row = dict(layer=name, gflop=fl / 1e9, count=cnt)
+        fns = dict(fwd=lambda: ops.conv2d_tc_fwd(d, x, tw, None, False, y),
+                   dgrad=lambda: ops.conv2d_tc_dgrad(d, dy, tw, False, dx),
+                   wgrad=lambda: ops.conv2d_tc_wgrad(d, x, dy, ws, dw))
+        line = '%-22s' % name
+        for ps in passes:
+            t = timeit(fns[ps])
+            row[ps + '_ms'], row[ps + '_tflops'] = t, fl / t / 1e9
+            tot[ps] = tot.get(ps, 0.0) + t * cnt
+            line += '  %s %.3f ms %6.1f TF' % (ps, t, fl / t / 1e9)
+        print(line, flush=True)
+        res.append(row)
+    print('weighted totals (ms per ResNet-50 pass):', {k: round(v, 2) for k, v in tot.items()})
+    os.makedirs('gpurun_out', exist_ok=True)
+    json.dump(dict(tag=tag, layers=res, totals=tot), open('gpurun_out/bench_conv_tc_%s.json' % tag, 'w'), indent=1)
+
+
+if __name__ == '__main__':
+    main()
