@@ -113,6 +113,9 @@ int pf_uq_weight_ste_bwd(const pf_uq_seg* segs_dev, const pf_work* work_dev, int
 int pf_uq_act_minmax(const float* x_dev, int64_t n, uint32_t* minmax_enc_dev, void* stream);
 int pf_uq_act_quant(const float* x_dev, float* y_dev, int64_t n, const uint32_t* minmax_enc_dev,
                     int bits, void* stream);
+/* same, (also) writing y as split-bf16 planes for the tensor-core conv that consumes it (y_dev may be NULL) */
+int pf_uq_act_quant_planes(const float* x_dev, float* y_dev, void* y_hi_dev, void* y_lo_dev, int64_t n,
+                           const uint32_t* minmax_enc_dev, int bits, void* stream);
 
 int pf_fill_u32(uint32_t* p_dev, int64_t n, uint32_t value, void* stream);
 /* (min,max) ordered-uint pairs <- (0xFFFFFFFF, 0): one launch resets every activation range slot. */
@@ -265,6 +268,20 @@ int pf_conv2d_tc_wgrad_supported(const pf_conv_desc* d);
 int64_t pf_conv2d_tc_wgrad_workspace_bytes(const pf_conv_desc* d);
 int pf_conv2d_tc_wgrad(const pf_conv_desc* d, const float* x_dev, const float* dy_dev, float* ws_dev,
                        float* dw_dev, void* stream);
+/* fp32 -> split-bf16 planes: hi = bf16(x), lo = bf16(x - hi) (n % 8 == 0, 16-byte aligned); the operand format of
+ * the tensor-core kernels.  pf_conv2d_tc_wgrad splits x and dy into its workspace and then runs the same
+ * persistent kernel as pf_conv2d_tc_wgrad_planes, which takes operands that are already split. */
+int pf_split_bf16(const float* src_dev, void* hi_dev, void* lo_dev, int64_t n, void* stream);
+int64_t pf_conv2d_tc_wgrad_planes_workspace_bytes(const pf_conv_desc* d);   /* split-K partials only */
+/* the same fwd / dgrad kernels with the activation operand already split (written by pf_bn_apply_planes,
+ * pf_uq_act_quant_planes, pf_bn_bwd_planes or pf_split_bf16): producers are pure cp.async copies */
+int pf_conv2d_tc_fwd_planes(const pf_conv_desc* d, const void* x_hi_dev, const void* x_lo_dev, const void* w_hi_dev,
+                            const void* w_lo_dev, const float* bias_dev, int relu, const float* residual_dev,
+                            float* y_dev, void* stream);
+int pf_conv2d_tc_dgrad_planes(const pf_conv_desc* d, const void* dy_hi_dev, const void* dy_lo_dev, const void* wd_hi_dev,
+                              const void* wd_lo_dev, int accumulate, float* dx_dev, void* stream);
+int pf_conv2d_tc_wgrad_planes(const pf_conv_desc* d, const void* x_hi_dev, const void* x_lo_dev, const void* dy_hi_dev,
+                              const void* dy_lo_dev, float* ws_dev, float* dw_dev, void* stream);
 /* hardware probe used by tests/test_tc_gpu.py to pin the descriptor conventions (not a product op) */
 int pf_tc_probe(const void* a_dev, const void* b_dev, float* d_dev, int n, int k, int mode, uint32_t lbo_a,
                 uint32_t sbo_a, uint32_t lbo_b, uint32_t sbo_b, uint32_t kstep_a, uint32_t kstep_b, void* stream);
@@ -304,6 +321,16 @@ int pf_bn_bwd(const float* dy_dev, const float* x_dev, int64_t m, int c, const f
               const float* rstd_dev, const float* gamma_dev, const float* beta_dev, int act,
               float* dgamma_dev, float* dbeta_dev, float* dx_dev, int accumulate, float* ws_dev,
               void* stream);
+/* variants that (also) write the result as split-bf16 planes — the operand format of the tensor-core convs that
+ * consume it (y: next conv's fwd + wgrad; dx: the producing conv's dgrad + wgrad).  The fp32 output pointer may
+ * be NULL when every consumer takes planes; `accumulate` needs the fp32 dx. */
+int pf_bn_apply_planes(const float* x_dev, int64_t m, int c, const float* mean_dev, const float* rstd_dev,
+                       const float* gamma_dev, const float* beta_dev, int act, float* y_dev, void* y_hi_dev,
+                       void* y_lo_dev, uint32_t* minmax_enc_dev, void* stream);
+int pf_bn_bwd_planes(const float* dy_dev, const float* x_dev, int64_t m, int c, const float* mean_dev,
+                     const float* rstd_dev, const float* gamma_dev, const float* beta_dev, int act,
+                     float* dgamma_dev, float* dbeta_dev, float* dx_dev, int accumulate, void* dx_hi_dev,
+                     void* dx_lo_dev, float* ws_dev, void* stream);
 /* out (+)= a (+ b): residual add (resnet_model.py:199,314) / gradient fan-out; b_dev may be NULL */
 int pf_add(const float* a_dev, const float* b_dev, int64_t n, int accumulate, float* out_dev, void* stream);
 /* dx (+)= dy * [y > 0] (and [y < 6] for act == 2) */

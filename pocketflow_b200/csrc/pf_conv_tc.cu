@@ -11,10 +11,10 @@
 //   fwd  : M = N*P*Q pixels, N = Cout, K = R*S*Cin;  A = im2col(x) gathered on the fly; B = w^T
 //   dgrad: M = N*H*W pixels, N = Cin,  K = R*S*Cout; A = gathered dy;                  B = w as [Cin][(r,s,cout)]
 // B is pre-split / pre-transposed once per step by pf_conv2d_tc_prep_weight (weights change every
-// step; 20 B per weight).  A rows are gathered from NHWC fp32 by 128 producer threads (one GEMM row
-// each: 64 contiguous channels of one tap = 256 B), split, and written to 128B-swizzled K-major smem
-// tiles; one elected thread issues the MMAs; accumulators live in TMEM; the producer warps then run
-// the epilogue (tcgen05.ld -> global NHWC fp32).  mbarrier ring of kStages smem stages.
+// step; 20 B per weight).  The activation operand comes either as fp32 NHWC (converted to the split
+// representation by the producer warps on the fly) or as PRE-SPLIT bf16 planes written by the kernel that
+// produced the tensor (BN-apply / activation quantizer / BN-backward): then the producers are pure
+// cp.async copies into the 128B-swizzled tiles.  Kernel structure: see conv_tc_persist_kernel below.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -27,273 +27,13 @@ using namespace pftc;
 
 constexpr int TM = 128;      // GEMM rows per CTA (= TMEM lanes)
 constexpr int BK = 64;       // bf16 elements per k-stage (= one 128-byte swizzled row)
-constexpr int kProducerThreads = 256;  // two threads per GEMM row: 8 x 16 B of A and 8 x 16 B of B each per stage
-constexpr int kThreads = 288;          // warps 0-7: producers + epilogue, warp 8: MMA issuer + TMEM alloc
 constexpr int kMaxStages = 4;
 
 struct TcGeom {
   int N, H, W, C, K, R, S, P, Q, sh, sw, pt, pl;
 };
 
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-__device__ __forceinline__ void split4(const float4 v, uint2& hi, uint2& lo) {
-  const __nv_bfloat16 hx = __float2bfloat16_rn(v.x), hy = __float2bfloat16_rn(v.y);
-  const __nv_bfloat16 hz = __float2bfloat16_rn(v.z), hw = __float2bfloat16_rn(v.w);
-  hi.x = (uint32_t)__bfloat16_as_ushort(hx) | ((uint32_t)__bfloat16_as_ushort(hy) << 16);
-  hi.y = (uint32_t)__bfloat16_as_ushort(hz) | ((uint32_t)__bfloat16_as_ushort(hw) << 16);
-  lo.x = pack_bf16(v.x - __bfloat162float(hx), v.y - __bfloat162float(hy));
-  lo.y = pack_bf16(v.z - __bfloat162float(hz), v.w - __bfloat162float(hw));
-}
-
-// MODE 0 = fwd (gather x), 1 = dgrad (gather dy).
-// Producers (8 warps): 8 lanes cover one row's 64-channel chunk (256 contiguous bytes of NHWC fp32):
-// thread t owns bytes [32*(t&7), +32) of rows (t>>3) + 32*i, i < 4 — a warp load touches 4 rows x 256 B
-// of fully used lines (the first version's one-row-per-thread mapping saturated the L1 tag stage:
-// ncu l1tex 79 %, 32 tag lookups per load instruction).  8 channels -> one 16-byte bf16 chunk each for
-// the hi and the lo tile.  A is double-buffered in registers one k-stage ahead (ping-pong sets, no
-// copies); B (pre-split weights, no conversion) goes global -> shared with cp.async straight into the
-// swizzled tile, overlapping the A conversion.
-// NPW = producer warps: 8 (1 CTA/SM, A ping-pong in registers; large K) or 4 (2-3 CTAs/SM so that one CTA's
-// loads / epilogue overlap another's MMAs; the small-K, output-bound 1x1 layers of the early stages).
-template <int MODE, int NPW>
-__global__ void __launch_bounds__(NPW * 32 + 32, NPW == 8 ? 1 : 2)
-conv_tc_kernel(const float* __restrict__ src, const __nv_bfloat16* __restrict__ b_hi,
-               const __nv_bfloat16* __restrict__ b_lo, float* __restrict__ out, TcGeom g, int M, int Ng,
-               int Kdim, int Kpad, int BN, int n_stages, int accumulate, const float* __restrict__ bias,
-               int relu, const float* __restrict__ residual) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const uint32_t a_bytes = TM * 128, b_bytes = (uint32_t)BN * 128;
-  const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
-  __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], accum_bar;
-  __shared__ uint32_t tmem_base_s;
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int m0 = blockIdx.x * TM, n0 = blockIdx.y * BN;
-  const int nk = Kpad / BK;
-  uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < BN) tmem_cols <<= 1;
-
-  if (tid == 0) {
-    for (int s = 0; s < n_stages; ++s) {
-      mbar_init(&full_bar[s], NPW * 32);
-      mbar_init(&empty_bar[s], 1);
-    }
-    mbar_init(&accum_bar, 1);
-    fence_barrier_init();
-  }
-  constexpr int kProd = NPW * 32;          // producer threads
-  constexpr int ROWS = TM * 8 / kProd;     // A rows per thread: 4 (NPW = 8) or 8 (NPW = 4)
-  constexpr int RSTEP = kProd / 8;         // row stride between a thread's rows: 32 or 16 (multiples of 8)
-  if (warp == NPW) tmem_alloc(&tmem_base_s, tmem_cols);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_base_s;
-
-  if (warp < NPW) {
-    const int l8 = tid & 7, rgrp = tid >> 3;          // 32-byte slice of the row, row group
-    const int CC = (MODE == 0) ? g.C : g.K;           // channels of the gathered tensor
-    int pn[ROWS], yx[ROWS];                           // per row: image index (< 0: beyond M), packed (y0, x0)
-    {
-      const int hw = (MODE == 0) ? g.P * g.Q : g.H * g.W;
-      const int wq = (MODE == 0) ? g.Q : g.W;
-#pragma unroll
-      for (int i = 0; i < ROWS; ++i) {
-        const int m = m0 + rgrp + RSTEP * i;
-        pn[i] = -1;
-        yx[i] = 0;
-        if (m < M) {
-          const int n_ = m / hw;
-          const int rem = m - n_ * hw;
-          const int y = rem / wq, x = rem - y * wq;
-          pn[i] = n_;
-          const int y0 = (MODE == 0) ? y * g.sh - g.pt : y + g.pt;
-          const int x0 = (MODE == 0) ? x * g.sw - g.pl : x + g.pl;
-          yx[i] = (int)(((uint32_t)(y0 + 32768) << 16) | (uint32_t)(x0 + 32768));
-        }
-      }
-    }
-    const bool unit_stride = g.sh == 1 && g.sw == 1;
-    const uint32_t sw = (uint32_t)(rgrp & 7);         // (row & 7) for every row of this thread (rows differ by 32)
-    const uint32_t chunk_off = (((uint32_t)l8) ^ sw) << 4;
-    auto issue_loads_a = [&](int ks, float4 (&av)[2 * ROWS]) {
-      const int kk = ks * BK + (l8 >> 1) * 16;        // this lane's 16-channel sub-chunk: inside one filter tap
-      const bool kok = kk < Kdim;
-      const int tap = kk / CC, c = kk - tap * CC + (l8 & 1) * 8;
-      const int r = tap / g.S, q = tap - r * g.S;
-#pragma unroll
-      for (int i = 0; i < ROWS; ++i) {
-        const float* p = nullptr;
-        if (kok && pn[i] >= 0) {
-          const int y0 = (int)((uint32_t)yx[i] >> 16) - 32768, x0 = (int)((uint32_t)yx[i] & 0xFFFFu) - 32768;
-          if (MODE == 0) {
-            const int ih = y0 + r, iw = x0 + q;
-            if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) p = src + (((size_t)pn[i] * g.H + ih) * g.W + iw) * g.C + c;
-          } else {
-            const int th = y0 - r, tw = x0 - q;
-            if (th >= 0 && tw >= 0) {
-              if (unit_stride) {
-                if (th < g.P && tw < g.Q) p = src + (((size_t)pn[i] * g.P + th) * g.Q + tw) * g.K + c;
-              } else {
-                const int oh = th / g.sh, ow = tw / g.sw;
-                if (oh * g.sh == th && ow * g.sw == tw && oh < g.P && ow < g.Q)
-                  p = src + (((size_t)pn[i] * g.P + oh) * g.Q + ow) * g.K + c;
-              }
-            }
-          }
-        }
-        av[2 * i] = p ? __ldg(reinterpret_cast<const float4*>(p)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        av[2 * i + 1] = p ? __ldg(reinterpret_cast<const float4*>(p) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    };
-    auto issue_b_async = [&](int ks, uint8_t* st) {
-      // rows rgrp + RSTEP*i of the BN x 128-byte tile, 16-byte chunk l8, hi and lo; zero-fill out-of-range rows
-#pragma unroll
-      for (int i = 0; i < ROWS; ++i) {
-        const int br = rgrp + RSTEP * i;
-        if (br < BN) {
-          const bool ok = n0 + br < Ng;
-          const size_t off = (size_t)(ok ? n0 + br : 0) * Kpad + (size_t)ks * BK + l8 * 8;
-          const uint32_t dst = smem_u32(st + 2 * a_bytes + (size_t)br * 128 + chunk_off);
-          const uint32_t nbytes = ok ? 16u : 0u;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(b_hi + off), "r"(nbytes) : "memory");
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + b_bytes), "l"(b_lo + off), "r"(nbytes) : "memory");
-        }
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    auto store_a = [&](uint8_t* st, const float4 (&av)[2 * ROWS]) {
-#pragma unroll
-      for (int i = 0; i < ROWS; ++i) {
-        uint2 h0, l0, h1, l1;
-        split4(av[2 * i], h0, l0);
-        split4(av[2 * i + 1], h1, l1);
-        uint8_t* rowp = st + (size_t)(rgrp + RSTEP * i) * 128 + chunk_off;
-        *reinterpret_cast<uint4*>(rowp) = make_uint4(h0.x, h0.y, h1.x, h1.y);
-        *reinterpret_cast<uint4*>(rowp + a_bytes) = make_uint4(l0.x, l0.y, l1.x, l1.y);
-      }
-    };
-    auto do_stage = [&](int ks, const float4 (&av)[2 * ROWS]) {
-      const int s = ks % n_stages;
-      mbar_wait(&empty_bar[s], (((uint32_t)(ks / n_stages)) & 1u) ^ 1u);   // slot free?
-      uint8_t* st = smem + (size_t)s * stage_bytes;
-      issue_b_async(ks, st);
-      store_a(st, av);
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      fence_proxy_async_smem();   // generic-proxy + cp.async writes -> visible to the tensor core (async proxy)
-      mbar_arrive(&full_bar[s]);
-    };
-    if (NPW == 8) {
-      float4 a0[2 * ROWS], a1[2 * ROWS];
-      issue_loads_a(0, a0);
-      for (int ks = 0; ks < nk; ks += 2) {
-        if (ks + 1 < nk) issue_loads_a(ks + 1, a1);
-        do_stage(ks, a0);
-        if (ks + 1 < nk) {
-          if (ks + 2 < nk) issue_loads_a(ks + 2, a0);
-          do_stage(ks + 1, a1);
-        }
-      }
-    } else {
-      for (int ks = 0; ks < nk; ++ks) {
-        float4 a0[2 * ROWS];
-        issue_loads_a(ks, a0);
-        do_stage(ks, a0);
-      }
-    }
-    // ======================= epilogue: TMEM -> registers -> smem -> coalesced global =======================
-    // warp w owns TMEM lanes [32*(w%4), +32); warps 0-3 take the low half of the columns, 4-7 the high half.
-    // The tile is staged row-major in the (now idle) stage memory so that global stores are full rows.
-    mbar_wait(&accum_bar, 0);
-    tc_fence_after();
-    float* stile = reinterpret_cast<float*>(smem);
-    const int pitch = BN + 4;                       // +16 B: conflict-free 128-bit row writes
-    {
-      const int erow = (warp & 3) * 32 + (tid & 31);
-      const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
-      const int cbeg = (NPW == 8 && BN >= 64) ? (warp >> 2) * (BN / 2) : 0;
-      const int cend = (NPW == 8) ? ((BN >= 64) ? cbeg + BN / 2 : ((warp >> 2) == 0 ? BN : 0)) : BN;
-      for (int c0 = cbeg; c0 < cend; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + lane_base + (uint32_t)c0, r);
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          if (c0 + j < BN)
-            *reinterpret_cast<uint4*>(stile + (size_t)erow * pitch + c0 + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-      }
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(NPW * 32) : "memory");   // the epilogue (= producer) warps only
-    {
-      // full rows to global, 4 independent 16-byte pieces per thread per round so that the residual /
-      // accumulate loads of a round are all in flight before the first one is consumed
-      const int vec_per_row = BN >> 2;
-      const int total = TM * vec_per_row;
-      const float* extra = residual ? residual : (accumulate ? out : nullptr);
-      for (int e0 = tid; e0 < total; e0 += 4 * kProd) {
-        float4 xv[4];
-        size_t goff[4];
-        int sidx[4];
-        bool ok[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int e = e0 + u * kProd;
-          const int rr = e / vec_per_row, cv = (e - rr * vec_per_row) << 2;
-          const int mm = m0 + rr, nn = n0 + cv;
-          ok[u] = e < total && mm < M && nn + 3 < Ng;
-          goff[u] = (size_t)mm * Ng + nn;
-          sidx[u] = rr * pitch + cv;
-          xv[u] = (ok[u] && extra) ? *reinterpret_cast<const float4*>(extra + goff[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (!ok[u]) continue;
-          float4 v = *reinterpret_cast<const float4*>(stile + sidx[u]);
-          if (bias) {
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + (goff[u] % (size_t)Ng)));
-            v.x = __fadd_rn(v.x, bb.x); v.y = __fadd_rn(v.y, bb.y); v.z = __fadd_rn(v.z, bb.z); v.w = __fadd_rn(v.w, bb.w);
-          }
-          if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-          if (extra) {   // fused residual add (resnet_model.py:199,314) or dx += (gradient accumulation)
-            v.x = __fadd_rn(v.x, xv[u].x); v.y = __fadd_rn(v.y, xv[u].y); v.z = __fadd_rn(v.z, xv[u].z); v.w = __fadd_rn(v.w, xv[u].w);
-          }
-          *reinterpret_cast<float4*>(out + goff[u]) = v;
-        }
-      }
-    }
-  } else if (warp == NPW) {
-    // ======================= MMA issuer: one elected thread =======================
-    if ((tid & 31) == 0) {
-      const uint32_t idesc = make_idesc_bf16(TM, BN, 0, 0);
-      for (int ks = 0; ks < nk; ++ks) {
-        const int s = ks % n_stages;
-        mbar_wait(&full_bar[s], ((uint32_t)(ks / n_stages)) & 1u);
-        tc_fence_after();
-        const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint32_t a_hi = base, a_lo = base + a_bytes, bh = base + 2 * a_bytes, bl = bh + b_bytes;
-#pragma unroll
-        for (int kk = 0; kk < BK / 16; ++kk) {
-          const uint64_t dah = make_smem_desc(a_hi + kk * 32, 16, 1024);
-          const uint64_t dal = make_smem_desc(a_lo + kk * 32, 16, 1024);
-          const uint64_t dbh = make_smem_desc(bh + kk * 32, 16, 1024);
-          const uint64_t dbl = make_smem_desc(bl + kk * 32, 16, 1024);
-          umma_bf16(tmem_base, dah, dbh, idesc, (ks > 0 || kk > 0) ? 1u : 0u);
-          umma_bf16(tmem_base, dah, dbl, idesc, 1u);
-          umma_bf16(tmem_base, dal, dbh, idesc, 1u);
-        }
-        umma_commit(&empty_bar[s]);   // frees the smem stage when these MMAs have completed
-      }
-      umma_commit(&accum_bar);        // accumulator complete
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == NPW) tmem_dealloc(tmem_base, tmem_cols);
-}
-
-
+__device__ __forceinline__ void split4(const float4 v, uint2& hi, uint2& lo) { pf_split4(v, hi, lo); }
 
 // =============================================================================================
 // v4: PERSISTENT, warp-specialised fwd / dgrad kernel.  One CTA per SM loops over output tiles;
@@ -342,6 +82,95 @@ constexpr int kEpiWarps = 4, kProdWarps = 8;
 constexpr int kThreadsP = (kEpiWarps + kProdWarps + 1) * 32;   // 416
 constexpr int kStagePitch = 36;                                // floats per staged row (32 + 4: conflict-free)
 
+
+// Epilogue of one 128 x BN accumulator tile by the 4 epilogue warps (warp w owns TMEM lanes [32w, 32w+32)):
+// TMEM -> registers (thread = row, 32 columns) -> per-warp smem transpose -> 128-byte row segments to global.
+// `extra` (residual / accumulate operand, same indexing as `out`) is prefetched one 32-column chunk ahead,
+// and the first chunk is requested BEFORE waiting for the accumulator, so its latency hides behind the main loop.
+template <bool EXTRA>
+__device__ __forceinline__ void epilogue_tile_t(uint32_t t_acc, uint64_t* tfull, uint64_t* tempty, uint32_t parity,
+                                                bool zero_tile, long long my_row_off, long long* __restrict__ rowoff,
+                                                float* __restrict__ stg, float* __restrict__ out,
+                                                const float* __restrict__ extra, const float* __restrict__ bias,
+                                                int relu, int n0, int BN, int Ng, int warp, int lane) {
+  rowoff[lane] = my_row_off;
+  __syncwarp();
+  const int csub = (lane & 7) * 4, rsub = lane >> 3;
+  int ro[8];                                     // this lane's 8 rows (4*u + rsub) of the warp's 32, in float4 units
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const long long o = rowoff[4 * u + rsub];
+    ro[u] = o < 0 ? -1 : (int)(o >> 2);          // row offsets are multiples of 4 elements (channel counts % 16 == 0)
+  }
+  auto load_extra = [&](int c0, float4 (&xv)[8]) {
+    const int cv = c0 + csub;
+    const bool cok = cv < BN && n0 + cv + 3 < Ng;
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      xv[u] = (cok && ro[u] >= 0) ? *reinterpret_cast<const float4*>(extra + ((size_t)ro[u] << 2) + n0 + cv)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  float4 xa[8], xb[8];                           // dead (eliminated) when !EXTRA
+  if (EXTRA) load_extra(0, xa);
+  mbar_wait(tfull, parity);
+  tc_fence_after();
+  const uint32_t t_addr = t_acc + (((uint32_t)(warp * 32)) << 16);
+  for (int c0 = 0; c0 < BN; c0 += 32) {
+    uint32_t r[32];
+    if (!zero_tile) {
+      tmem_ld_32x32(t_addr + (uint32_t)c0, r);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r[j] = 0u;
+    }
+    if (c0 + 32 >= BN) {                         // last read of this accumulator: hand it back to the MMA warp
+      tc_fence_before();
+      mbar_arrive(tempty);
+    }
+#pragma unroll
+    for (int j = 0; j < 32; j += 4)
+      *reinterpret_cast<uint4*>(stg + lane * kStagePitch + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+    __syncwarp();
+    if (EXTRA && c0 + 32 < BN) load_extra(c0 + 32, xb);
+    // rows 4*u + (lane >> 3), 16-byte chunk (lane & 7): 8 lanes write one row's 128 contiguous bytes
+    const int cv = c0 + csub;
+    const bool cok = cv < BN && n0 + cv + 3 < Ng;
+    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias && cok) bb = __ldg(reinterpret_cast<const float4*>(bias + n0 + cv));
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4*>(stg + (4 * (4 * half + u) + rsub) * kStagePitch + csub);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int uu = 4 * half + u;
+        if (!cok || ro[uu] < 0) continue;
+        float4 w = v[u];
+        if (bias) { w.x = __fadd_rn(w.x, bb.x); w.y = __fadd_rn(w.y, bb.y); w.z = __fadd_rn(w.z, bb.z); w.w = __fadd_rn(w.w, bb.w); }
+        if (relu) { w.x = fmaxf(w.x, 0.f); w.y = fmaxf(w.y, 0.f); w.z = fmaxf(w.z, 0.f); w.w = fmaxf(w.w, 0.f); }
+        if (EXTRA) {   // fused residual add (resnet_model.py:199,314) or dx += (gradient accumulation)
+          w.x = __fadd_rn(w.x, xa[uu].x); w.y = __fadd_rn(w.y, xa[uu].y); w.z = __fadd_rn(w.z, xa[uu].z); w.w = __fadd_rn(w.w, xa[uu].w);
+        }
+        *reinterpret_cast<float4*>(out + ((size_t)ro[uu] << 2) + n0 + cv) = w;
+      }
+    }
+    __syncwarp();                                // the staging buffer is overwritten by the next chunk
+    if (EXTRA) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) xa[u] = xb[u];
+    }
+  }
+}
+__device__ __forceinline__ void epilogue_tile(uint32_t t_acc, uint64_t* tfull, uint64_t* tempty, uint32_t parity,
+                                              bool zero_tile, long long my_row_off, long long* rowoff, float* stg,
+                                              float* __restrict__ out, const float* __restrict__ extra,
+                                              const float* __restrict__ bias, int relu, int n0, int BN, int Ng,
+                                              int warp, int lane) {
+  if (extra) epilogue_tile_t<true>(t_acc, tfull, tempty, parity, zero_tile, my_row_off, rowoff, stg, out, extra, bias, relu, n0, BN, Ng, warp, lane);
+  else epilogue_tile_t<false>(t_acc, tfull, tempty, parity, zero_tile, my_row_off, rowoff, stg, out, nullptr, bias, relu, n0, BN, Ng, warp, lane);
+}
+
 template <int MODE>
 __device__ __forceinline__ int tile_class(const TcP& p, int mt) {
   int ci = 0;
@@ -353,9 +182,10 @@ __device__ __forceinline__ int tile_class(const TcP& p, int mt) {
   return ci;
 }
 
-template <int MODE>
+template <int MODE, bool PLANES>
 __global__ void __launch_bounds__(kThreadsP, 1)
-conv_tc_persist_kernel(const float* __restrict__ src, const __nv_bfloat16* __restrict__ b_hi,
+conv_tc_persist_kernel(const float* __restrict__ src, const __nv_bfloat16* __restrict__ a_hi_g,
+                       const __nv_bfloat16* __restrict__ a_lo_g, const __nv_bfloat16* __restrict__ b_hi,
                        const __nv_bfloat16* __restrict__ b_lo, float* __restrict__ out,
                        const float* __restrict__ bias, const float* __restrict__ residual,
                        const __grid_constant__ TcP p) {
@@ -401,13 +231,16 @@ conv_tc_persist_kernel(const float* __restrict__ src, const __nv_bfloat16* __res
       const int mt = (int)fdiv((uint32_t)tile, p.d_ntiles);
       return p.cls[tile_class<MODE>(p, mt)].ntaps * p.cblocks;
     };
-    auto issue_loads_a = [&](int tile, int ks, float4 (&av)[8]) {
+    // element offsets (-1: zero row) of this thread's 4 rows of A for k-stage ks of `tile`: this lane's 8-channel
+    // chunk (l8) lies inside one filter tap (channel counts are multiples of 16)
+    auto a_offsets = [&](int tile, int ks, long long (&off)[4]) {
       const int mt = (int)fdiv((uint32_t)tile, p.d_ntiles);
-      const float* ptr[4] = {nullptr, nullptr, nullptr, nullptr};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) off[i] = -1;
       if (MODE != 2) {
-        const int kk = ks * BK + (l8 >> 1) * 16;      // this lane's 16-channel sub-chunk: inside one filter tap
+        const int kk = ks * BK + l8 * 8;
         const int tap = (int)fdiv((uint32_t)kk, p.d_cc);
-        const int c = kk - tap * CC + (l8 & 1) * 8;
+        const int c = kk - tap * CC;
         const int r = (int)fdiv((uint32_t)tap, p.d_s), q = tap - r * g.S;
         const int hw = (MODE == 0) ? g.P * g.Q : g.H * g.W;
         const int wq = (MODE == 0) ? g.Q : g.W;
@@ -422,16 +255,16 @@ conv_tc_persist_kernel(const float* __restrict__ src, const __nv_bfloat16* __res
               const int y = (int)fdiv((uint32_t)rem, p.d_w), x = rem - y * wq;
               if (MODE == 0) {
                 const int ih = y * g.sh - g.pt + r, iw = x * g.sw - g.pl + q;
-                if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) ptr[i] = src + (((size_t)n_ * g.H + ih) * g.W + iw) * g.C + c;
+                if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) off[i] = (((long long)n_ * g.H + ih) * g.W + iw) * g.C + c;
               } else {
                 const int th = y + g.pt - r, tw = x + g.pl - q;
                 if (th >= 0 && tw >= 0) {
                   if (unit_stride) {
-                    if (th < g.P && tw < g.Q) ptr[i] = src + (((size_t)n_ * g.P + th) * g.Q + tw) * g.K + c;
+                    if (th < g.P && tw < g.Q) off[i] = (((long long)n_ * g.P + th) * g.Q + tw) * g.K + c;
                   } else {
                     const int oh = th / g.sh, ow = tw / g.sw;
                     if (oh * g.sh == th && ow * g.sw == tw && oh < g.P && ow < g.Q)
-                      ptr[i] = src + (((size_t)n_ * g.P + oh) * g.Q + ow) * g.K + c;
+                      off[i] = (((long long)n_ * g.P + oh) * g.Q + ow) * g.K + c;
                   }
                 }
               }
@@ -452,21 +285,22 @@ conv_tc_persist_kernel(const float* __restrict__ src, const __nv_bfloat16* __res
             const int rem = mc - n_ * hwc;
             const int y = (int)fdiv((uint32_t)rem, k.d_w), x = rem - y * k.Wc;
             const int oh = y + eh, ow = x + ew;
-            if (oh >= 0 && oh < g.P && ow >= 0 && ow < g.Q) ptr[i] = src + (((size_t)n_ * g.P + oh) * g.Q + ow) * g.K + c;
+            if (oh >= 0 && oh < g.P && ow >= 0 && ow < g.Q) off[i] = (((long long)n_ * g.P + oh) * g.Q + ow) * g.K + c;
           }
         }
       }
+    };
+    auto issue_loads_a = [&](int tile, int ks, float4 (&av)[8]) {
+      long long off[4];
+      a_offsets(tile, ks, off);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        av[2 * i] = ptr[i] ? __ldg(reinterpret_cast<const float4*>(ptr[i])) : make_float4(0.f, 0.f, 0.f, 0.f);
-        av[2 * i + 1] = ptr[i] ? __ldg(reinterpret_cast<const float4*>(ptr[i]) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+        av[2 * i] = off[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(src + off[i])) : make_float4(0.f, 0.f, 0.f, 0.f);
+        av[2 * i + 1] = off[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(src + off[i]) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
     uint32_t it = 0;                                   // global k-stage counter of this CTA (ring position)
-    auto do_stage = [&](int tile, int ks, bool first, const float4 (&av)[8]) {
-      const uint32_t s = it % (uint32_t)p.n_stages;
-      mbar_wait(&empty_bar[s], ((it / (uint32_t)p.n_stages) & 1u) ^ 1u);   // slot free?
-      uint8_t* sa = smem_a + (size_t)s * 2 * a_bytes;
+    auto issue_b = [&](int tile, int ks, bool first, uint32_t s) {
       if (!p.b_stationary || first) {
         const int mt = (int)fdiv((uint32_t)tile, p.d_ntiles);
         const int n0 = (tile - mt * p.n_tiles) * BN;
@@ -487,8 +321,14 @@ conv_tc_persist_kernel(const float* __restrict__ src, const __nv_bfloat16* __res
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(b_hi + off), "r"(nbytes) : "memory");
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + b_bytes), "l"(b_lo + off), "r"(nbytes) : "memory");
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
       }
+    };
+    auto do_stage = [&](int tile, int ks, bool first, const float4 (&av)[8]) {
+      const uint32_t s = it % (uint32_t)p.n_stages;
+      mbar_wait(&empty_bar[s], ((it / (uint32_t)p.n_stages) & 1u) ^ 1u);   // slot free?
+      uint8_t* sa = smem_a + (size_t)s * 2 * a_bytes;
+      issue_b(tile, ks, first, s);
+      asm volatile("cp.async.commit_group;" ::: "memory");
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         uint2 h0, l0, h1, l1;
@@ -503,6 +343,31 @@ conv_tc_persist_kernel(const float* __restrict__ src, const __nv_bfloat16* __res
       mbar_arrive(&full_bar[s]);
       ++it;
     };
+    if (PLANES) {
+      // pre-split operand: both tiles are plain cp.async copies; the stage's barrier arrival fires when this
+      // thread's copies have landed, so the producers only ever wait for a free slot
+      for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
+        const int nkt = tile_nk(tile);
+        for (int ks = 0; ks < nkt; ++ks, ++it) {
+          const uint32_t s = it % (uint32_t)p.n_stages;
+          mbar_wait(&empty_bar[s], ((it / (uint32_t)p.n_stages) & 1u) ^ 1u);
+          long long off[4];
+          a_offsets(tile, ks, off);
+          const uint32_t sa = smem_u32(smem_a + (size_t)s * 2 * a_bytes);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t dst = sa + (uint32_t)(rgrp + 32 * i) * 128 + chunk_off;
+            const uint32_t nb = off[i] >= 0 ? 16u : 0u;
+            const size_t o = off[i] >= 0 ? (size_t)off[i] : 0;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(a_hi_g + o), "r"(nb) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + a_bytes), "l"(a_lo_g + o), "r"(nb) : "memory");
+          }
+          issue_b(tile, ks, tile == first_tile, s);
+          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full_bar[s])) : "memory");
+        }
+      }
+      asm volatile("cp.async.wait_all;" ::: "memory");
+    } else {
     // flat (tile, k-stage) iteration with a two-deep register ping-pong
     int t0 = first_tile, k0 = 0, nk0 = (t0 < p.total_tiles) ? tile_nk(t0) : 0;
     while (t0 < p.total_tiles && nk0 == 0) { t0 += tile_step; nk0 = (t0 < p.total_tiles) ? tile_nk(t0) : 0; }
@@ -534,6 +399,7 @@ conv_tc_persist_kernel(const float* __restrict__ src, const __nv_bfloat16* __res
         t0 = t2; k0 = k2; nk0 = nk2;
       }
     }
+    }
   } else if (warp == kEpiWarps + kProdWarps) {
     // =================================== MMA issuer ===================================
     if (lane == 0) {
@@ -549,6 +415,7 @@ conv_tc_persist_kernel(const float* __restrict__ src, const __nv_bfloat16* __res
         for (int ks = 0; ks < nk; ++ks, ++it) {
           const uint32_t s = it % (uint32_t)p.n_stages;
           mbar_wait(&full_bar[s], (it / (uint32_t)p.n_stages) & 1u);
+          if (PLANES) fence_proxy_async_smem();   // cp.async writes -> visible to the tensor core (async proxy)
           tc_fence_after();
           const uint32_t a_hi = smem_u32(smem_a + (size_t)s * 2 * a_bytes), a_lo = a_hi + a_bytes;
           const uint32_t bh = smem_u32(smem_b + (size_t)(p.b_stationary ? ks : (int)s) * 2 * b_bytes), bl = bh + b_bytes;
@@ -572,84 +439,30 @@ conv_tc_persist_kernel(const float* __restrict__ src, const __nv_bfloat16* __res
     // =================================== epilogue (warps 0-3) ===================================
     float* stg = stage_all + (size_t)warp * 32 * kStagePitch;
     long long* rowoff = rowoff_all + warp * 32;
-    const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
     const float* extra = residual ? residual : (p.accumulate ? out : nullptr);
     uint32_t tcount = 0;
     for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++tcount) {
       const int mt = (int)fdiv((uint32_t)tile, p.d_ntiles);
       const int n0 = (tile - mt * p.n_tiles) * BN;
       bool zero_tile = false;
-      {   // global element offset of this lane's row (-1: beyond the problem)
-        long long off = -1;
-        if (MODE != 2) {
-          const int m = mt * TM + warp * 32 + lane;
-          if (m < p.M) off = (long long)m * p.Ng;
-        } else {
-          const TcClass& k = p.cls[tile_class<MODE>(p, mt)];
-          zero_tile = k.ntaps == 0;
-          const int mc = (mt - k.tile_begin) * TM + warp * 32 + lane;
-          if (mc < k.Mc) {
-            const int hwc = k.Hc * k.Wc;
-            const int n_ = (int)fdiv((uint32_t)mc, k.d_hw);
-            const int rem = mc - n_ * hwc;
-            const int y = (int)fdiv((uint32_t)rem, k.d_w), x = rem - y * k.Wc;
-            off = (((long long)n_ * g.H + (k.ph + y * g.sh)) * g.W + (k.pw + x * g.sw)) * g.C;
-          }
+      long long off = -1;                    // global element offset of this lane's row (-1: beyond the problem)
+      if (MODE != 2) {
+        const int m = mt * TM + warp * 32 + lane;
+        if (m < p.M) off = (long long)m * p.Ng;
+      } else {
+        const TcClass& k = p.cls[tile_class<MODE>(p, mt)];
+        zero_tile = k.ntaps == 0;
+        const int mc = (mt - k.tile_begin) * TM + warp * 32 + lane;
+        if (mc < k.Mc) {
+          const int hwc = k.Hc * k.Wc;
+          const int n_ = (int)fdiv((uint32_t)mc, k.d_hw);
+          const int rem = mc - n_ * hwc;
+          const int y = (int)fdiv((uint32_t)rem, k.d_w), x = rem - y * k.Wc;
+          off = (((long long)n_ * g.H + (k.ph + y * g.sh)) * g.W + (k.pw + x * g.sw)) * g.C;
         }
-        rowoff[lane] = off;
       }
-      const uint32_t buf = tcount & 1u;
-      mbar_wait(&tfull_bar[buf], (tcount >> 1) & 1u);
-      tc_fence_after();
-      __syncwarp();
-      const uint32_t t_addr = tmem_base + buf * (uint32_t)p.acc_cols + lane_base;
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        if (!zero_tile) {
-          tmem_ld_32x32(t_addr + (uint32_t)c0, r);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = 0u;
-        }
-        if (c0 + 32 >= BN) {                         // last read of this accumulator: hand it back to the MMA warp
-          tc_fence_before();
-          mbar_arrive(&tempty_bar[buf]);
-        }
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<uint4*>(stg + lane * kStagePitch + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-        __syncwarp();
-        // rows 4*j + (lane >> 3), 16-byte chunk (lane & 7): 8 lanes write one row's 128 contiguous bytes
-        const int cv = c0 + (lane & 7) * 4;
-        const bool cok = cv < BN && n0 + cv + 3 < p.Ng;
-        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (bias && cok) bb = __ldg(reinterpret_cast<const float4*>(bias + n0 + cv));
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          float4 xv[4];
-          long long ro[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int rr = 4 * (half * 4 + u) + (lane >> 3);
-            ro[u] = cok ? rowoff[rr] : -1;
-            xv[u] = (extra && ro[u] >= 0) ? *reinterpret_cast<const float4*>(extra + ro[u] + n0 + cv)
-                                          : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (ro[u] < 0) continue;
-            const int rr = 4 * (half * 4 + u) + (lane >> 3);
-            float4 v = *reinterpret_cast<const float4*>(stg + rr * kStagePitch + (lane & 7) * 4);
-            if (bias) { v.x = __fadd_rn(v.x, bb.x); v.y = __fadd_rn(v.y, bb.y); v.z = __fadd_rn(v.z, bb.z); v.w = __fadd_rn(v.w, bb.w); }
-            if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-            if (extra) {   // fused residual add (resnet_model.py:199,314) or dx += (gradient accumulation)
-              v.x = __fadd_rn(v.x, xv[u].x); v.y = __fadd_rn(v.y, xv[u].y); v.z = __fadd_rn(v.z, xv[u].z); v.w = __fadd_rn(v.w, xv[u].w);
-            }
-            *reinterpret_cast<float4*>(out + ro[u] + n0 + cv) = v;
-          }
-        }
-        __syncwarp();
-      }
+      epilogue_tile(tmem_base + (tcount & 1u) * (uint32_t)p.acc_cols, &tfull_bar[tcount & 1u], &tempty_bar[tcount & 1u],
+                    (tcount >> 1) & 1u, zero_tile, off, rowoff, stg, out, extra, bias, p.relu, n0, BN, p.Ng, warp, lane);
     }
   }
   tc_fence_before();
@@ -658,159 +471,188 @@ conv_tc_persist_kernel(const float* __restrict__ src, const __nv_bfloat16* __res
 }
 
 // ---------------------------------------------------------------------------------------------
-// wgrad on tensor cores:  dW[kf][co] = sum_pix im2col(x)[pix][kf] * dy[pix][co]
-// GEMM with M = kf = (r,s,c) tile of 128, N = cout tile, K = pixels; BOTH operands are MN-major
-// (channels are the contiguous axis of NHWC): smem tiles are [k/8][mn/64][k%8] rows of 64 bf16
-// (128 B, SWIZZLE_128B), descriptor LBO = 1024 (next 64-wide MN block), SBO = (tile_mn/64)*1024
-// (next group of 8 pixels), one K=16 MMA step = 2*SBO — conventions pinned by tests/test_tc_gpu.py.
-// Split-K over pixel ranges (grid.z); partials go to a workspace and are reduced in fixed order.
-__global__ void __launch_bounds__(kThreads, 1)
-conv_tc_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ partial,
-                     TcGeom g, int Mtot, int Npix, int pix_per_split, int BN, int n_stages) {
+// fp32 -> split bf16 planes (hi = bf16(x), lo = bf16(x - hi)); 8 elements per thread, HBM-bound (8 B/element).
+__global__ void __launch_bounds__(256)
+split_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int64_t n8) {
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n8; i += stride) {
+    const float4 a = pf_ld_stream(src + i * 8), b = pf_ld_stream(src + i * 8 + 4);
+    uint2 h0, l0, h1, l1;
+    split4(a, h0, l0);
+    split4(b, h1, l1);
+    *reinterpret_cast<uint4*>(hi + i * 8) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+    *reinterpret_cast<uint4*>(lo + i * 8) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// wgrad v4: persistent, warp-specialised, operands read from PRE-SPLIT bf16 planes with cp.async straight into
+// the swizzled MN-major tiles (no register staging, no conversion in the loop; completion is signalled by
+// cp.async.mbarrier.arrive so producers never wait for data, only for a free stage).  Work unit = (kf tile of
+// 128, cout tile of BN <= 256, pixel range); units are ordered range-major so that the CTAs running together
+// read the same pixels.  Epilogue: the shared epilogue_tile() into partial[split][kf][cout].
+struct WgP {
+  TcGeom g;
+  int Mtot, Npix, pps, splits, BN, m_tiles, n_tiles, tiles, total_units, n_stages, acc_cols;
+  FastDiv d_pq, d_q, d_c, d_s, d_tiles, d_ntiles;
+};
+
+__global__ void __launch_bounds__(kThreadsP, 1)
+conv_tc_wgrad_persist_kernel(const __nv_bfloat16* __restrict__ x_hi, const __nv_bfloat16* __restrict__ x_lo,
+                             const __nv_bfloat16* __restrict__ dy_hi, const __nv_bfloat16* __restrict__ dy_lo,
+                             float* __restrict__ partial, const __grid_constant__ WgP p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const TcGeom& g = p.g;
+  const int BN = p.BN;
   const uint32_t a_bytes = BK * TM * 2, b_bytes = (uint32_t)BK * BN * 2;   // one bf16 tile
   const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
-  __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], accum_bar;
+  float* stage_all = reinterpret_cast<float*>(smem + (size_t)p.n_stages * stage_bytes);
+  long long* rowoff_all = reinterpret_cast<long long*>(stage_all + kEpiWarps * 32 * kStagePitch);
+  __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_base_s;
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int m0 = blockIdx.x * TM, n0 = blockIdx.y * BN;
-  const int pbeg = blockIdx.z * pix_per_split;
-  const int pend = min(Npix, pbeg + pix_per_split);
-  const int nk = (pend - pbeg + BK - 1) / BK;
-  uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < BN) tmem_cols <<= 1;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int s = 0; s < n_stages; ++s) {
-      mbar_init(&full_bar[s], kProducerThreads);
+    for (int s = 0; s < p.n_stages; ++s) {
+      mbar_init(&full_bar[s], kProdWarps * 32);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(&accum_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], kEpiWarps * 32);
+    }
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(&tmem_base_s, tmem_cols);
+  if (warp == kEpiWarps + kProdWarps) tmem_alloc(&tmem_base_s, (uint32_t)(2 * p.acc_cols));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   const int mbA = TM / 64, mbB = BN / 64;
+  struct Unit {
+    int split, m0, n0, pbeg, nk;
+  };
+  auto decode = [&](int u) -> Unit {
+    Unit r;
+    r.split = (int)fdiv((uint32_t)u, p.d_tiles);
+    const int t = u - r.split * p.tiles;
+    const int mt = (int)fdiv((uint32_t)t, p.d_ntiles);
+    r.m0 = mt * TM;
+    r.n0 = (t - mt * p.n_tiles) * BN;
+    r.pbeg = r.split * p.pps;
+    const int pend = min(p.Npix, r.pbeg + p.pps);
+    r.nk = (pend - r.pbeg + BK - 1) / BK;
+    return r;
+  };
 
-  if (warp < 8) {
-    // producers: 16 lanes cover one pixel's 128-wide MN extent (512 contiguous bytes of NHWC fp32), thread t
-    // owns elements [8*(t&15), +8) of pixels (t>>4) + 16*i, i < 4, of BOTH operands: 8 fp32 -> one 16-byte
-    // bf16 chunk each for the hi and lo tiles.
-    const int l16 = tid & 15, pgrp = tid >> 4;
-    // A: kf = m0 + 8*l16 .. +7 lies inside one filter tap (C % 16 == 0): decode is stage-invariant
-    const int kf = m0 + l16 * 8;
-    const bool a_ok = kf < Mtot;
-    const int a_tap = kf / g.C, a_c = kf - a_tap * g.C;
-    const int a_r = a_tap / g.S, a_q = a_tap - a_r * g.S;
-    // B: couts n0 + 8*l16 .. +7
-    const int bco = n0 + l16 * 8;
-    const bool b_okc = l16 * 8 < BN && bco < g.K;
-    const uint32_t e = (uint32_t)(l16 * 8);                 // element offset inside the 128-wide tile
-    const uint32_t mblk = e >> 6, chunk = (e & 63) >> 3;
-    auto issue_loads = [&](int ks, float4 (&av)[8], float4 (&bv)[8]) {
+  if (warp >= kEpiWarps && warp < kEpiWarps + kProdWarps) {
+    // =================================== producers ===================================
+    const int pt_ = tid - kEpiWarps * 32;
+    const int l16 = pt_ & 15, pg = pt_ >> 4;           // 16-byte chunk of the 128-wide MN extent, pixel group
+    const uint32_t k8 = (uint32_t)(pg & 7);            // (pixel & 7) of every pixel of this thread (pixels pg + 16*i)
+    const uint32_t a_mblk = (uint32_t)(l16 >> 3), chunk = (uint32_t)(l16 & 7);
+    const uint32_t swz = (chunk ^ k8) << 4;
+    const int pq = g.P * g.Q;
+    uint32_t it = 0;
+    for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+      const Unit un = decode(u);
+      const int pend = min(p.Npix, un.pbeg + p.pps);
+      // A: kf = m0 + 8*l16 .. +7 lies inside one filter tap (Cin % 16 == 0): decode is stage-invariant
+      const int kf = un.m0 + l16 * 8;
+      const bool a_ok = kf < p.Mtot;
+      const int a_tap = (int)fdiv((uint32_t)kf, p.d_c), a_c = kf - a_tap * g.C;
+      const int a_r = (int)fdiv((uint32_t)a_tap, p.d_s), a_q = a_tap - a_r * g.S;
+      for (int ks = 0; ks < un.nk; ++ks, ++it) {
+        const uint32_t s = it % (uint32_t)p.n_stages;
+        mbar_wait(&empty_bar[s], ((it / (uint32_t)p.n_stages) & 1u) ^ 1u);
+        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + 2 * a_bytes;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int pix = pbeg + ks * BK + pgrp + 16 * i;
-        const float* pa = nullptr;
-        const float* pb = nullptr;
-        if (pix < pend) {
-          const int pq = g.P * g.Q;
-          const int pn = pix / pq;
-          const int rem = pix - pn * pq;
-          const int oh = rem / g.Q, ow = rem - oh * g.Q;
-          if (a_ok) {
+        for (int i = 0; i < 4; ++i) {
+          const int pix = un.pbeg + ks * BK + pg + 16 * i;
+          const uint32_t kb = (uint32_t)((pg >> 3) + 2 * i);
+          size_t aoff = 0, boff = 0;
+          uint32_t an = 0, bn = 0;
+          if (pix < pend) {
+            const int pn = (int)fdiv((uint32_t)pix, p.d_pq);
+            const int rem = pix - pn * pq;
+            const int oh = (int)fdiv((uint32_t)rem, p.d_q), ow = rem - oh * g.Q;
             const int ih = oh * g.sh - g.pt + a_r, iw = ow * g.sw - g.pl + a_q;
-            if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) pa = x + (((size_t)pn * g.H + ih) * g.W + iw) * g.C + a_c;
+            if (a_ok && ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) {
+              aoff = (((size_t)pn * g.H + ih) * g.W + iw) * g.C + a_c;
+              an = 16;
+            }
+            boff = (size_t)pix * g.K;
+            bn = 16;
           }
-          if (b_okc) pb = dy + (size_t)pix * g.K + bco;
+          const uint32_t da = sa + (kb * (uint32_t)(mbA * 8) + a_mblk * 8 + k8) * 128 + swz;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(da), "l"(x_hi + aoff), "r"(an) : "memory");
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(da + a_bytes), "l"(x_lo + aoff), "r"(an) : "memory");
+          for (int e = l16 * 8; e < BN; e += 128) {
+            const int co = un.n0 + e;
+            const uint32_t nb = (co < g.K) ? bn : 0u;
+            const size_t bo = nb ? boff + co : 0;
+            const uint32_t db = sb + (kb * (uint32_t)(mbB * 8) + (uint32_t)(e >> 6) * 8 + k8) * 128 + swz;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(db), "l"(dy_hi + bo), "r"(nb) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(db + b_bytes), "l"(dy_lo + bo), "r"(nb) : "memory");
+          }
         }
-        av[2 * i] = pa ? __ldg(reinterpret_cast<const float4*>(pa)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        av[2 * i + 1] = pa ? __ldg(reinterpret_cast<const float4*>(pa) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-        bv[2 * i] = pb ? __ldg(reinterpret_cast<const float4*>(pb)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        bv[2 * i + 1] = pb ? __ldg(reinterpret_cast<const float4*>(pb) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    };
-    auto store_stage = [&](int s, const float4 (&av)[8], const float4 (&bv)[8]) {
-      uint8_t* st = smem + (size_t)s * stage_bytes;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t k = (uint32_t)(pgrp + 16 * i), k8 = k & 7, kb = k >> 3;
-        uint2 h0, l0, h1, l1;
-        split4(av[2 * i], h0, l0);
-        split4(av[2 * i + 1], h1, l1);
-        uint8_t* hi = st + (size_t)(kb * (uint32_t)(mbA * 8) + mblk * 8 + k8) * 128 + ((chunk ^ k8) << 4);
-        *reinterpret_cast<uint4*>(hi) = make_uint4(h0.x, h0.y, h1.x, h1.y);
-        *reinterpret_cast<uint4*>(hi + a_bytes) = make_uint4(l0.x, l0.y, l1.x, l1.y);
-        if (l16 * 8 < BN) {
-          split4(bv[2 * i], h0, l0);
-          split4(bv[2 * i + 1], h1, l1);
-          uint8_t* bh = st + 2 * a_bytes + (size_t)(kb * (uint32_t)(mbB * 8) + mblk * 8 + k8) * 128 + ((chunk ^ k8) << 4);
-          *reinterpret_cast<uint4*>(bh) = make_uint4(h0.x, h0.y, h1.x, h1.y);
-          *reinterpret_cast<uint4*>(bh + b_bytes) = make_uint4(l0.x, l0.y, l1.x, l1.y);
-        }
-      }
-    };
-    for (int ks = 0; ks < nk; ++ks) {
-      const int s = ks % n_stages;
-      float4 av[8], bv[8];
-      issue_loads(ks, av, bv);
-      mbar_wait(&empty_bar[s], (((uint32_t)(ks / n_stages)) & 1u) ^ 1u);
-      store_stage(s, av, bv);
-      fence_proxy_async_smem();
-      mbar_arrive(&full_bar[s]);
-    }
-    // ---- epilogue: D rows = kf, columns = cout -> partial[z][kf][cout]
-    mbar_wait(&accum_bar, 0);
-    tc_fence_after();
-    const int erow = (warp & 3) * 32 + (tid & 31);
-    const int em = m0 + erow;
-    const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
-    const int cbeg = (warp >> 2) * (BN / 2), cend = cbeg + BN / 2;
-    float* outp = partial + (size_t)blockIdx.z * Mtot * g.K;
-    for (int c0 = cbeg; c0 < cend; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_base + lane_base + (uint32_t)c0, r);
-      if (em < Mtot) {
-        float* o = outp + (size_t)em * g.K + n0 + c0;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          if (n0 + c0 + j + 3 < g.K)
-            *reinterpret_cast<float4*>(o + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                            __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-        }
+        // the barrier arrival fires when every cp.async issued so far by this thread has landed
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full_bar[s])) : "memory");
       }
     }
-  } else if (warp == 8) {
-    if ((tid & 31) == 0) {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  } else if (warp == kEpiWarps + kProdWarps) {
+    // =================================== MMA issuer ===================================
+    if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(TM, BN, 1, 1);
       const uint32_t sbo_a = (uint32_t)mbA * 1024u, sbo_b = (uint32_t)mbB * 1024u;
-      for (int ks = 0; ks < nk; ++ks) {
-        const int s = ks % n_stages;
-        mbar_wait(&full_bar[s], ((uint32_t)(ks / n_stages)) & 1u);
+      uint32_t it = 0, tcount = 0;
+      for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++tcount) {
+        const Unit un = decode(u);
+        const uint32_t buf = tcount & 1u;
+        mbar_wait(&tempty_bar[buf], ((tcount >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint32_t a_hi = base, a_lo = base + a_bytes, bh = base + 2 * a_bytes, bl = bh + b_bytes;
+        const uint32_t d_tmem = tmem_base + buf * (uint32_t)p.acc_cols;
+        for (int ks = 0; ks < un.nk; ++ks, ++it) {
+          const uint32_t s = it % (uint32_t)p.n_stages;
+          mbar_wait(&full_bar[s], (it / (uint32_t)p.n_stages) & 1u);
+          fence_proxy_async_smem();      // cp.async (generic proxy) writes -> visible to the tensor core (async proxy)
+          tc_fence_after();
+          const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t a_hi = base, a_lo = base + a_bytes, bh = base + 2 * a_bytes, bl = bh + b_bytes;
 #pragma unroll
-        for (int kk = 0; kk < BK / 16; ++kk) {
-          const uint64_t dah = make_smem_desc(a_hi + kk * 2 * sbo_a, 1024, sbo_a);
-          const uint64_t dal = make_smem_desc(a_lo + kk * 2 * sbo_a, 1024, sbo_a);
-          const uint64_t dbh = make_smem_desc(bh + kk * 2 * sbo_b, 1024, sbo_b);
-          const uint64_t dbl = make_smem_desc(bl + kk * 2 * sbo_b, 1024, sbo_b);
-          umma_bf16(tmem_base, dah, dbh, idesc, (ks > 0 || kk > 0) ? 1u : 0u);
-          umma_bf16(tmem_base, dah, dbl, idesc, 1u);
-          umma_bf16(tmem_base, dal, dbh, idesc, 1u);
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t dah = make_smem_desc(a_hi + kk * 2 * sbo_a, 1024, sbo_a);
+            const uint64_t dal = make_smem_desc(a_lo + kk * 2 * sbo_a, 1024, sbo_a);
+            const uint64_t dbh = make_smem_desc(bh + kk * 2 * sbo_b, 1024, sbo_b);
+            const uint64_t dbl = make_smem_desc(bl + kk * 2 * sbo_b, 1024, sbo_b);
+            umma_bf16(d_tmem, dah, dbh, idesc, (ks > 0 || kk > 0) ? 1u : 0u);
+            umma_bf16(d_tmem, dah, dbl, idesc, 1u);
+            umma_bf16(d_tmem, dal, dbh, idesc, 1u);
+          }
+          umma_commit(&empty_bar[s]);
         }
-        umma_commit(&empty_bar[s]);
+        if (un.nk > 0) umma_commit(&tfull_bar[buf]);
+        else mbar_arrive(&tfull_bar[buf]);
       }
-      umma_commit(&accum_bar);
+    }
+  } else {
+    // =================================== epilogue: D rows = kf, columns = cout ===================================
+    float* stg = stage_all + (size_t)warp * 32 * kStagePitch;
+    long long* rowoff = rowoff_all + warp * 32;
+    uint32_t tcount = 0;
+    for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++tcount) {
+      const Unit un = decode(u);
+      const int em = un.m0 + warp * 32 + lane;
+      const long long off = em < p.Mtot ? ((long long)un.split * p.Mtot + em) * g.K : -1;
+      epilogue_tile(tmem_base + (tcount & 1u) * (uint32_t)p.acc_cols, &tfull_bar[tcount & 1u], &tempty_bar[tcount & 1u],
+                    (tcount >> 1) & 1u, un.nk == 0, off, rowoff, stg, partial, nullptr, nullptr, 0, un.n0, BN, g.K, warp,
+                    lane);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem_base, tmem_cols);
+  if (warp == kEpiWarps + kProdWarps) tmem_dealloc(tmem_base, (uint32_t)(2 * p.acc_cols));
 }
 
 __global__ void __launch_bounds__(256)
@@ -823,20 +665,6 @@ tc_splitk_reduce_kernel(const float* __restrict__ partial, float* __restrict__ o
     s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
   }
   *reinterpret_cast<float4*>(out + i) = s;
-}
-
-inline int tc_wgrad_splits(const TcGeom& g, int BN, int* pix_per_split) {
-  const int Mtot = g.R * g.S * g.C, Npix = g.N * g.P * g.Q;
-  const int tiles = ((Mtot + TM - 1) / TM) * ((g.K + BN - 1) / BN);
-  int splits = (2 * PF_NUM_SMS + tiles - 1) / tiles;
-  const int max_by_k = (Npix + 8 * BK - 1) / (8 * BK);
-  if (splits > max_by_k) splits = max_by_k;
-  if (splits > PF_CONV_TC_WGRAD_MAX_SPLITS) splits = PF_CONV_TC_WGRAD_MAX_SPLITS;
-  if (splits < 1) splits = 1;
-  int pps = (Npix + splits - 1) / splits;
-  pps = (pps + BK - 1) / BK * BK;
-  *pix_per_split = pps;
-  return (Npix + pps - 1) / pps;
 }
 
 // ---- weight preparation: fp32 HWIO [R,S,C,K] -> split bf16, K-major for both passes
@@ -878,39 +706,6 @@ int tc_geom(const pf_conv_desc* d, TcGeom* g, const char* who) {
 
 inline int pad64(int64_t k) { return (int)((k + 63) / 64 * 64); }
 
-template <int MODE>
-int launch_tc_v3(const TcGeom& g, const float* src, const void* b_hi, const void* b_lo, float* out, int accumulate,
-                 const float* bias, int relu, const float* residual, cudaStream_t st, const char* who) {
-  const int64_t M64 = (MODE == 0) ? (int64_t)g.N * g.P * g.Q : (int64_t)g.N * g.H * g.W;
-  PF_REQUIRE(M64 < (1ll << 31), "%s: too many rows", who);
-  const int M = (int)M64;
-  const int Ng = (MODE == 0) ? g.K : g.C;
-  const int Kdim = (MODE == 0) ? g.R * g.S * g.C : g.R * g.S * g.K;
-  const int Kpad = pad64(Kdim);
-  int BN = Ng >= 128 ? 128 : (Ng >= 64 ? 64 : (Ng >= 32 ? 32 : 16));
-  const int nk = Kpad / BK;
-  int stages = nk < 3 ? (nk < 2 ? 1 : 2) : 3;
-  if (BN <= 64 && nk >= 4) stages = 4;
-  size_t smem = (size_t)stages * (2 * TM * 128 + 2 * BN * 128);
-  const size_t epi = (size_t)TM * (BN + 4) * 4;          // the epilogue stages the fp32 tile in the same memory
-  if (smem < epi) smem = epi;
-  smem += 1024;
-  dim3 grid((M + TM - 1) / TM, (Ng + BN - 1) / BN);
-  if (nk <= 1) {
-    auto kern = conv_tc_kernel<MODE, 4>;
-    PF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    kern<<<grid, 4 * 32 + 32, smem, st>>>(src, (const __nv_bfloat16*)b_hi, (const __nv_bfloat16*)b_lo, out, g, M, Ng,
-                                          Kdim, Kpad, BN, stages, accumulate, bias, relu, residual);
-  } else {
-    auto kern = conv_tc_kernel<MODE, 8>;
-    PF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    kern<<<grid, 8 * 32 + 32, smem, st>>>(src, (const __nv_bfloat16*)b_hi, (const __nv_bfloat16*)b_lo, out, g, M, Ng,
-                                          Kdim, Kpad, BN, stages, accumulate, bias, relu, residual);
-  }
-  PF_CHECK_LAUNCH(who);
-  return PF_OK;
-}
-
 inline int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return (v && *v) ? atoi(v) : dflt;
@@ -919,14 +714,15 @@ inline int env_int(const char* name, int dflt) {
 constexpr int kSmemLimit = 232448;   // 227 KB opt-in maximum of dynamic shared memory per CTA on sm_100
 
 template <int MODE>
-int launch_persist(const TcGeom& g, TcP& p, const float* src, const void* b_hi, const void* b_lo, float* out,
-                   const float* bias, const float* residual, cudaStream_t st, const char* who) {
+int launch_persist(const TcGeom& g, TcP& p, const float* src, const void* a_hi, const void* a_lo, const void* b_hi,
+                   const void* b_lo, float* out, const float* bias, const float* residual, cudaStream_t st,
+                   const char* who) {
   const int Ng = p.Ng;
   // ---- tile width: wide tiles read A once per 256 channels, but quantise worse over the 148 SMs
   int BN;
   if (Ng >= 256) {
     const int64_t t256 = (int64_t)p.m_tiles * ((Ng + 255) / 256), t128 = (int64_t)p.m_tiles * ((Ng + 127) / 128);
-    const double c256 = (double)((t256 + PF_NUM_SMS - 1) / PF_NUM_SMS) * 1.8;
+    const double c256 = (double)((t256 + PF_NUM_SMS - 1) / PF_NUM_SMS) * 1.3;   // measured: a 256-wide tile costs ~1.3x
     const double c128 = (double)((t128 + PF_NUM_SMS - 1) / PF_NUM_SMS);
     BN = c256 <= c128 ? 256 : 128;
   } else {
@@ -962,19 +758,26 @@ int launch_persist(const TcGeom& g, TcP& p, const float* src, const void* b_hi, 
   PF_REQUIRE(p.n_stages >= 2 || max_nk <= 1, "%s: shared-memory plan failed (BN %d)", who, BN);
   if (p.n_stages < 1) p.n_stages = 1;
   const size_t smem = (size_t)p.n_stages * a_stage + (size_t)p.n_bslots * b_slot + fixed;
-  auto kern = conv_tc_persist_kernel<MODE>;
-  PF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = std::min(p.total_tiles, PF_NUM_SMS);
-  kern<<<grid, kThreadsP, smem, st>>>(src, (const __nv_bfloat16*)b_hi, (const __nv_bfloat16*)b_lo, out, bias, residual, p);
+  if (a_hi) {
+    auto kern = conv_tc_persist_kernel<MODE, true>;
+    PF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kThreadsP, smem, st>>>(nullptr, (const __nv_bfloat16*)a_hi, (const __nv_bfloat16*)a_lo,
+                                        (const __nv_bfloat16*)b_hi, (const __nv_bfloat16*)b_lo, out, bias, residual, p);
+  } else {
+    auto kern = conv_tc_persist_kernel<MODE, false>;
+    PF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kThreadsP, smem, st>>>(src, nullptr, nullptr, (const __nv_bfloat16*)b_hi, (const __nv_bfloat16*)b_lo, out,
+                                        bias, residual, p);
+  }
   PF_CHECK_LAUNCH(who);
   return PF_OK;
 }
 
 template <int MODE>
-int launch_tc(const TcGeom& g, const float* src, const void* b_hi, const void* b_lo, float* out, int accumulate,
-              const float* bias, int relu, const float* residual, cudaStream_t st, const char* who) {
-  static const int impl = env_int("PF_TC_IMPL", 4);
-  if (impl == 3) return launch_tc_v3<MODE>(g, src, b_hi, b_lo, out, accumulate, bias, relu, residual, st, who);
+int launch_tc(const TcGeom& g, const float* src, const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
+              float* out, int accumulate, const float* bias, int relu, const float* residual, cudaStream_t st,
+              const char* who) {
   const int64_t M64 = (MODE == 0) ? (int64_t)g.N * g.P * g.Q : (int64_t)g.N * g.H * g.W;
   PF_REQUIRE(M64 < (1ll << 31), "%s: too many rows", who);
   TcP p;
@@ -1029,9 +832,47 @@ int launch_tc(const TcGeom& g, const float* src, const void* b_hi, const void* b
         ++p.ncls;
       }
     p.m_tiles = tiles;
-    return launch_persist<2>(g, p, src, b_hi, b_lo, out, bias, residual, st, who);
+    return launch_persist<2>(g, p, src, a_hi, a_lo, b_hi, b_lo, out, bias, residual, st, who);
   }
-  return launch_persist<MODE>(g, p, src, b_hi, b_lo, out, bias, residual, st, who);
+  return launch_persist<MODE>(g, p, src, a_hi, a_lo, b_hi, b_lo, out, bias, residual, st, who);
+}
+
+inline int64_t wg_align(int64_t b) { return (b + 255) / 256 * 256; }
+
+// tile width, split-K factor and stage count of the persistent wgrad
+inline void wgrad_plan(const TcGeom& g, WgP* pp) {
+  WgP& p = *pp;
+  memset(&p, 0, sizeof(p));
+  p.g = g;
+  p.Mtot = g.R * g.S * g.C;
+  p.Npix = g.N * g.P * g.Q;
+  int BN = g.K >= 256 ? 256 : (g.K >= 128 ? 128 : 64);
+  const int forced = env_int("PF_TC_WGRAD_BN", 0);
+  if ((forced == 64 || forced == 128 || forced == 256) && forced <= g.K) BN = forced;
+  p.BN = BN;
+  p.m_tiles = (p.Mtot + TM - 1) / TM;
+  p.n_tiles = (g.K + BN - 1) / BN;
+  p.tiles = p.m_tiles * p.n_tiles;
+  // enough units to fill the SMs a few times over, but at least 8 k-stages (512 pixels) per unit
+  // (rounded DOWN: total units just under a whole number of waves over the 148 SMs)
+  int splits = (env_int("PF_TC_WGRAD_WAVES", 2) * PF_NUM_SMS) / p.tiles;
+  const int max_by_k = (p.Npix + 8 * BK - 1) / (8 * BK);
+  splits = std::max(1, std::min(std::min(splits, max_by_k), PF_CONV_TC_WGRAD_MAX_SPLITS));
+  int pps = (p.Npix + splits - 1) / splits;
+  pps = (pps + BK - 1) / BK * BK;
+  p.pps = pps;
+  p.splits = (p.Npix + pps - 1) / pps;
+  p.total_units = p.tiles * p.splits;
+  p.acc_cols = 32;
+  while (p.acc_cols < BN) p.acc_cols <<= 1;
+  const int fixed = 1024 + kEpiWarps * 32 * kStagePitch * 4 + kEpiWarps * 32 * 8 + 256;
+  p.n_stages = std::max(1, std::min(kMaxStages, (kSmemLimit - fixed) / (2 * BK * TM * 2 + 2 * BK * BN * 2)));
+  p.d_pq = make_fastdiv((uint32_t)(g.P * g.Q));
+  p.d_q = make_fastdiv((uint32_t)g.Q);
+  p.d_c = make_fastdiv((uint32_t)g.C);
+  p.d_s = make_fastdiv((uint32_t)g.S);
+  p.d_tiles = make_fastdiv((uint32_t)p.tiles);
+  p.d_ntiles = make_fastdiv((uint32_t)p.n_tiles);
 }
 
 }  // namespace
@@ -1069,31 +910,61 @@ int pf_conv2d_tc_prep_weight(const pf_conv_desc* d, const float* w_dev, void* fw
   return PF_OK;
 }
 
+static int tc_fwd_impl(const pf_conv_desc* d, const float* x_dev, const void* x_hi, const void* x_lo, const void* w_hi_dev,
+                       const void* w_lo_dev, const float* bias_dev, int relu, const float* residual_dev, float* y_dev,
+                       void* stream, const char* who) {
+  TcGeom g;
+  int rc = tc_geom(d, &g, who);
+  if (rc) return rc;
+  PF_REQUIRE(pf_conv2d_tc_supported(d), "%s: Cin and Cout must be multiples of 16", who);
+  PF_REQUIRE((x_dev || (x_hi && x_lo)) && w_hi_dev && w_lo_dev && y_dev, "%s: null pointer", who);
+  PF_REQUIRE((((uintptr_t)x_dev | (uintptr_t)x_hi | (uintptr_t)x_lo | (uintptr_t)y_dev | (uintptr_t)w_hi_dev |
+               (uintptr_t)w_lo_dev | (uintptr_t)residual_dev | (uintptr_t)bias_dev) & 15) == 0,
+             "%s: 16-byte alignment required", who);
+  return launch_tc<0>(g, x_dev, x_hi, x_lo, w_hi_dev, w_lo_dev, y_dev, 0, bias_dev, relu, residual_dev,
+                      (cudaStream_t)stream, who);
+}
+
+static int tc_dgrad_impl(const pf_conv_desc* d, const float* dy_dev, const void* dy_hi, const void* dy_lo,
+                         const void* wd_hi_dev, const void* wd_lo_dev, int accumulate, float* dx_dev, void* stream,
+                         const char* who) {
+  TcGeom g;
+  int rc = tc_geom(d, &g, who);
+  if (rc) return rc;
+  PF_REQUIRE(pf_conv2d_tc_supported(d), "%s: Cin and Cout must be multiples of 16", who);
+  PF_REQUIRE((dy_dev || (dy_hi && dy_lo)) && wd_hi_dev && wd_lo_dev && dx_dev, "%s: null pointer", who);
+  PF_REQUIRE((((uintptr_t)dy_dev | (uintptr_t)dy_hi | (uintptr_t)dy_lo | (uintptr_t)dx_dev | (uintptr_t)wd_hi_dev |
+               (uintptr_t)wd_lo_dev) & 15) == 0, "%s: 16-byte alignment required", who);
+  return launch_tc<1>(g, dy_dev, dy_hi, dy_lo, wd_hi_dev, wd_lo_dev, dx_dev, accumulate, nullptr, 0, nullptr,
+                      (cudaStream_t)stream, who);
+}
+
 int pf_conv2d_tc_fwd(const pf_conv_desc* d, const float* x_dev, const void* w_hi_dev, const void* w_lo_dev,
                      const float* bias_dev, int relu, const float* residual_dev, float* y_dev, void* stream) {
-  TcGeom g;
-  int rc = tc_geom(d, &g, "pf_conv2d_tc_fwd");
-  if (rc) return rc;
-  PF_REQUIRE(pf_conv2d_tc_supported(d), "pf_conv2d_tc_fwd: Cin and Cout must be multiples of 16");
-  PF_REQUIRE(x_dev && w_hi_dev && w_lo_dev && y_dev, "pf_conv2d_tc_fwd: null pointer");
-  PF_REQUIRE((((uintptr_t)x_dev | (uintptr_t)y_dev | (uintptr_t)w_hi_dev | (uintptr_t)w_lo_dev) & 15) == 0,
-             "pf_conv2d_tc_fwd: 16-byte alignment required");
-  PF_REQUIRE(((uintptr_t)residual_dev & 15) == 0, "pf_conv2d_tc_fwd: residual must be 16-byte aligned");
-  return launch_tc<0>(g, x_dev, w_hi_dev, w_lo_dev, y_dev, 0, bias_dev, relu, residual_dev, (cudaStream_t)stream,
-                      "pf_conv2d_tc_fwd");
+  PF_REQUIRE(x_dev != nullptr, "pf_conv2d_tc_fwd: null pointer");
+  return tc_fwd_impl(d, x_dev, nullptr, nullptr, w_hi_dev, w_lo_dev, bias_dev, relu, residual_dev, y_dev, stream,
+                     "pf_conv2d_tc_fwd");
+}
+
+int pf_conv2d_tc_fwd_planes(const pf_conv_desc* d, const void* x_hi_dev, const void* x_lo_dev, const void* w_hi_dev,
+                            const void* w_lo_dev, const float* bias_dev, int relu, const float* residual_dev,
+                            float* y_dev, void* stream) {
+  PF_REQUIRE(x_hi_dev && x_lo_dev, "pf_conv2d_tc_fwd_planes: null pointer");
+  return tc_fwd_impl(d, nullptr, x_hi_dev, x_lo_dev, w_hi_dev, w_lo_dev, bias_dev, relu, residual_dev, y_dev, stream,
+                     "pf_conv2d_tc_fwd_planes");
 }
 
 int pf_conv2d_tc_dgrad(const pf_conv_desc* d, const float* dy_dev, const void* wd_hi_dev, const void* wd_lo_dev,
                        int accumulate, float* dx_dev, void* stream) {
-  TcGeom g;
-  int rc = tc_geom(d, &g, "pf_conv2d_tc_dgrad");
-  if (rc) return rc;
-  PF_REQUIRE(pf_conv2d_tc_supported(d), "pf_conv2d_tc_dgrad: Cin and Cout must be multiples of 16");
-  PF_REQUIRE(dy_dev && wd_hi_dev && wd_lo_dev && dx_dev, "pf_conv2d_tc_dgrad: null pointer");
-  PF_REQUIRE((((uintptr_t)dy_dev | (uintptr_t)dx_dev | (uintptr_t)wd_hi_dev | (uintptr_t)wd_lo_dev) & 15) == 0,
-             "pf_conv2d_tc_dgrad: 16-byte alignment required");
-  return launch_tc<1>(g, dy_dev, wd_hi_dev, wd_lo_dev, dx_dev, accumulate, nullptr, 0, nullptr, (cudaStream_t)stream,
-                      "pf_conv2d_tc_dgrad");
+  PF_REQUIRE(dy_dev != nullptr, "pf_conv2d_tc_dgrad: null pointer");
+  return tc_dgrad_impl(d, dy_dev, nullptr, nullptr, wd_hi_dev, wd_lo_dev, accumulate, dx_dev, stream, "pf_conv2d_tc_dgrad");
+}
+
+int pf_conv2d_tc_dgrad_planes(const pf_conv_desc* d, const void* dy_hi_dev, const void* dy_lo_dev, const void* wd_hi_dev,
+                              const void* wd_lo_dev, int accumulate, float* dx_dev, void* stream) {
+  PF_REQUIRE(dy_hi_dev && dy_lo_dev, "pf_conv2d_tc_dgrad_planes: null pointer");
+  return tc_dgrad_impl(d, nullptr, dy_hi_dev, dy_lo_dev, wd_hi_dev, wd_lo_dev, accumulate, dx_dev, stream,
+                       "pf_conv2d_tc_dgrad_planes");
 }
 
 int pf_conv2d_tc_wgrad_supported(const pf_conv_desc* d) {
@@ -1104,10 +975,60 @@ int pf_conv2d_tc_wgrad_supported(const pf_conv_desc* d) {
 int64_t pf_conv2d_tc_wgrad_workspace_bytes(const pf_conv_desc* d) {
   TcGeom g;
   if (!d || tc_geom(d, &g, "pf_conv2d_tc_wgrad_workspace_bytes")) return 0;
-  const int BN = g.K >= 128 ? 128 : 64;
-  int pps;
-  const int splits = tc_wgrad_splits(g, BN, &pps);
-  return (int64_t)splits * g.R * g.S * g.C * g.K * 4;
+  WgP p;
+  wgrad_plan(g, &p);
+  // split-K partials + the split-bf16 planes of x and dy
+  return (int64_t)p.splits * p.Mtot * g.K * 4 + wg_align((int64_t)g.N * g.H * g.W * g.C * 4) +
+         wg_align((int64_t)g.N * g.P * g.Q * g.K * 4);
+}
+
+int64_t pf_conv2d_tc_wgrad_planes_workspace_bytes(const pf_conv_desc* d) {
+  TcGeom g;
+  if (!d || tc_geom(d, &g, "pf_conv2d_tc_wgrad_planes_workspace_bytes")) return 0;
+  WgP p;
+  wgrad_plan(g, &p);
+  return (int64_t)p.splits * p.Mtot * g.K * 4;
+}
+
+int pf_split_bf16(const float* src_dev, void* hi_dev, void* lo_dev, int64_t n, void* stream) {
+  PF_REQUIRE(n >= 0 && n % 8 == 0, "pf_split_bf16: n must be a non-negative multiple of 8");
+  if (n == 0) return PF_OK;
+  PF_REQUIRE(src_dev && hi_dev && lo_dev, "pf_split_bf16: null pointer");
+  PF_REQUIRE((((uintptr_t)src_dev | (uintptr_t)hi_dev | (uintptr_t)lo_dev) & 15) == 0, "pf_split_bf16: 16-byte alignment required");
+  int64_t blocks = (n / 8 + 255) / 256;
+  if (blocks > PF_NUM_SMS * 16) blocks = PF_NUM_SMS * 16;
+  split_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src_dev, (__nv_bfloat16*)hi_dev, (__nv_bfloat16*)lo_dev, n / 8);
+  PF_CHECK_LAUNCH("pf_split_bf16");
+  return PF_OK;
+}
+
+int pf_conv2d_tc_wgrad_planes(const pf_conv_desc* d, const void* x_hi_dev, const void* x_lo_dev, const void* dy_hi_dev,
+                              const void* dy_lo_dev, float* ws_dev, float* dw_dev, void* stream) {
+  TcGeom g;
+  int rc = tc_geom(d, &g, "pf_conv2d_tc_wgrad_planes");
+  if (rc) return rc;
+  PF_REQUIRE(pf_conv2d_tc_wgrad_supported(d), "pf_conv2d_tc_wgrad_planes: needs Cin %% 16 == 0 and Cout %% 64 == 0");
+  PF_REQUIRE(x_hi_dev && x_lo_dev && dy_hi_dev && dy_lo_dev && ws_dev && dw_dev, "pf_conv2d_tc_wgrad_planes: null pointer");
+  PF_REQUIRE((((uintptr_t)x_hi_dev | (uintptr_t)x_lo_dev | (uintptr_t)dy_hi_dev | (uintptr_t)dy_lo_dev | (uintptr_t)ws_dev |
+               (uintptr_t)dw_dev) & 15) == 0, "pf_conv2d_tc_wgrad_planes: 16-byte alignment required");
+  PF_REQUIRE((int64_t)g.N * g.P * g.Q < (1ll << 31), "pf_conv2d_tc_wgrad_planes: too many pixels");
+  WgP p;
+  wgrad_plan(g, &p);
+  const int fixed = 1024 + kEpiWarps * 32 * kStagePitch * 4 + kEpiWarps * 32 * 8 + 256;
+  const size_t smem = (size_t)p.n_stages * (2 * BK * TM * 2 + 2 * BK * p.BN * 2) + fixed;
+  PF_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = std::min(p.total_units, PF_NUM_SMS);
+  conv_tc_wgrad_persist_kernel<<<grid, kThreadsP, smem, st>>>(
+      (const __nv_bfloat16*)x_hi_dev, (const __nv_bfloat16*)x_lo_dev, (const __nv_bfloat16*)dy_hi_dev,
+      (const __nv_bfloat16*)dy_lo_dev, p.splits == 1 ? dw_dev : ws_dev, p);
+  PF_CHECK_LAUNCH("pf_conv2d_tc_wgrad_planes");
+  if (p.splits > 1) {
+    const int64_t n = (int64_t)p.Mtot * g.K;
+    tc_splitk_reduce_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(ws_dev, dw_dev, n, p.splits);
+    PF_CHECK_LAUNCH("pf_conv2d_tc_wgrad_planes/reduce");
+  }
+  return PF_OK;
 }
 
 int pf_conv2d_tc_wgrad(const pf_conv_desc* d, const float* x_dev, const float* dy_dev, float* ws_dev,
@@ -1121,25 +1042,20 @@ int pf_conv2d_tc_wgrad(const pf_conv_desc* d, const float* x_dev, const float* d
              "pf_conv2d_tc_wgrad: 16-byte alignment required");
   const int64_t np64 = (int64_t)g.N * g.P * g.Q;
   PF_REQUIRE(np64 < (1ll << 31), "pf_conv2d_tc_wgrad: too many pixels");
-  const int Mtot = g.R * g.S * g.C, Npix = (int)np64;
-  const int BN = g.K >= 128 ? 128 : 64;
-  int pps;
-  const int splits = tc_wgrad_splits(g, BN, &pps);
-  const int nk = pps / BK;
-  const int stages = nk < 3 ? (nk < 2 ? 1 : 2) : 3;
-  const size_t smem = (size_t)stages * (2 * BK * TM * 2 + 2 * BK * BN * 2) + 1024;
-  PF_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  dim3 grid((Mtot + TM - 1) / TM, (g.K + BN - 1) / BN, splits);
-  cudaStream_t st = (cudaStream_t)stream;
-  conv_tc_wgrad_kernel<<<grid, kThreads, smem, st>>>(x_dev, dy_dev, splits == 1 ? dw_dev : ws_dev, g, Mtot, Npix,
-                                                    pps, BN, stages);
-  PF_CHECK_LAUNCH("pf_conv2d_tc_wgrad");
-  if (splits > 1) {
-    const int64_t n = (int64_t)Mtot * g.K;
-    tc_splitk_reduce_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(ws_dev, dw_dev, n, splits);
-    PF_CHECK_LAUNCH("pf_conv2d_tc_wgrad/reduce");
-  }
-  return PF_OK;
+  // split both operands into bf16 planes inside the workspace, then the persistent planes kernel
+  WgP p;
+  wgrad_plan(g, &p);
+  const int64_t nx = (int64_t)g.N * g.H * g.W * g.C, ny = np64 * g.K;
+  uint8_t* base = reinterpret_cast<uint8_t*>(ws_dev) + (int64_t)p.splits * p.Mtot * g.K * 4;
+  __nv_bfloat16* xh = reinterpret_cast<__nv_bfloat16*>(base);
+  __nv_bfloat16* xl = xh + nx;
+  __nv_bfloat16* yh = reinterpret_cast<__nv_bfloat16*>(base + wg_align(nx * 4));
+  __nv_bfloat16* yl = yh + ny;
+  rc = pf_split_bf16(x_dev, xh, xl, nx, stream);
+  if (rc) return rc;
+  rc = pf_split_bf16(dy_dev, yh, yl, ny, stream);
+  if (rc) return rc;
+  return pf_conv2d_tc_wgrad_planes(d, xh, xl, yh, yl, ws_dev, dw_dev, stream);
 }
 
 }  // extern "C"

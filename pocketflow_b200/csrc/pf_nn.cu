@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(NT)
 bn_apply_kernel(const float* __restrict__ x, int64_t total, int C, const float* __restrict__ mean,
                 const float* __restrict__ rstd, const float* __restrict__ gamma,
                 const float* __restrict__ beta, int act, float* __restrict__ y,
-                uint32_t* __restrict__ minmax_enc) {
+                uint32_t* __restrict__ minmax_enc, void* __restrict__ y_hi, void* __restrict__ y_lo) {
   __shared__ float s_mn[NT / 32], s_mx[NT / 32];
   const int64_t nvec = total >> 2;
   const int64_t stride = (int64_t)gridDim.x * NT;
@@ -163,7 +163,8 @@ bn_apply_kernel(const float* __restrict__ x, int64_t total, int C, const float* 
     v.y = bn_act(v.y, mu.y, rs.y, ga.y, be.y, act);
     v.z = bn_act(v.z, mu.z, rs.z, ga.z, be.z, act);
     v.w = bn_act(v.w, mu.w, rs.w, ga.w, be.w, act);
-    pf_st_stream(y + (idx << 2), v);
+    if (y) pf_st_stream(y + (idx << 2), v);
+    if (y_hi) pf_st_planes4(y_hi, y_lo, idx << 2, v);
     mn = fminf(fminf(mn, v.x), fminf(v.y, fminf(v.z, v.w)));
     mx = fmaxf(fmaxf(mx, v.x), fmaxf(v.y, fmaxf(v.z, v.w)));
   };
@@ -297,7 +298,7 @@ bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, i
                     float inv_m, const float* __restrict__ mean, const float* __restrict__ rstd,
                     const float* __restrict__ gamma, const float* __restrict__ beta,
                     const float* __restrict__ dgamma, const float* __restrict__ dbeta, int act,
-                    int accumulate, float* __restrict__ dx) {
+                    int accumulate, float* __restrict__ dx, void* __restrict__ dx_hi, void* __restrict__ dx_lo) {
   const int64_t nvec = total >> 2;
   const int64_t stride = (int64_t)gridDim.x * NT;
   int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x;
@@ -325,7 +326,8 @@ bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, i
       const float4 old = *reinterpret_cast<const float4*>(dx + (idx << 2));
       r.x += old.x; r.y += old.y; r.z += old.z; r.w += old.w;
     }
-    pf_st_stream(dx + (idx << 2), r);
+    if (dx) pf_st_stream(dx + (idx << 2), r);
+    if (dx_hi) pf_st_planes4(dx_hi, dx_lo, idx << 2, r);
   };
   if (step == 0) {
     const float4 mu4 = __ldg(reinterpret_cast<const float4*>(mean + c)), rs4 = __ldg(reinterpret_cast<const float4*>(rstd + c));
@@ -608,26 +610,41 @@ int pf_bn_eval_prepare(const float* moving_var_dev, int c, float eps, float* rst
   return PF_OK;
 }
 
-int pf_bn_apply(const float* x_dev, int64_t m, int c, const float* mean_dev, const float* rstd_dev,
-                const float* gamma_dev, const float* beta_dev, int act, float* y_dev,
-                uint32_t* minmax_enc_dev, void* stream) {
+int pf_bn_apply_planes(const float* x_dev, int64_t m, int c, const float* mean_dev, const float* rstd_dev,
+                       const float* gamma_dev, const float* beta_dev, int act, float* y_dev, void* y_hi_dev,
+                       void* y_lo_dev, uint32_t* minmax_enc_dev, void* stream) {
   PF_REQUIRE(m > 0 && c > 0 && (c & 3) == 0, "pf_bn_apply: bad shape (C must be a multiple of 4)");
   PF_REQUIRE(act >= 0 && act <= 2, "pf_bn_apply: act must be 0 (none), 1 (relu) or 2 (relu6)");
-  PF_REQUIRE(x_dev && mean_dev && rstd_dev && gamma_dev && beta_dev && y_dev, "pf_bn_apply: null pointer");
+  PF_REQUIRE(x_dev && mean_dev && rstd_dev && gamma_dev && beta_dev, "pf_bn_apply: null pointer");
+  PF_REQUIRE(y_dev || y_hi_dev, "pf_bn_apply: no output");
+  PF_REQUIRE((y_hi_dev == nullptr) == (y_lo_dev == nullptr), "pf_bn_apply: planes come in pairs");
+  PF_REQUIRE((((uintptr_t)y_hi_dev | (uintptr_t)y_lo_dev) & 7) == 0, "pf_bn_apply: planes must be 8-byte aligned");
   const int64_t total = m * c;
   bn_apply_kernel<<<chan_grid(total >> 2, c), NT, 0, (cudaStream_t)stream>>>(x_dev, total, c, mean_dev, rstd_dev, gamma_dev,
-                                                                     beta_dev, act, y_dev, minmax_enc_dev);
+                                                                     beta_dev, act, y_dev, minmax_enc_dev, y_hi_dev, y_lo_dev);
   PF_CHECK_LAUNCH("pf_bn_apply");
   return PF_OK;
 }
 
-int pf_bn_bwd(const float* dy_dev, const float* x_dev, int64_t m, int c, const float* mean_dev,
-              const float* rstd_dev, const float* gamma_dev, const float* beta_dev, int act,
-              float* dgamma_dev, float* dbeta_dev, float* dx_dev, int accumulate, float* ws_dev,
-              void* stream) {
+int pf_bn_apply(const float* x_dev, int64_t m, int c, const float* mean_dev, const float* rstd_dev,
+                const float* gamma_dev, const float* beta_dev, int act, float* y_dev,
+                uint32_t* minmax_enc_dev, void* stream) {
+  PF_REQUIRE(y_dev != nullptr, "pf_bn_apply: null pointer");
+  return pf_bn_apply_planes(x_dev, m, c, mean_dev, rstd_dev, gamma_dev, beta_dev, act, y_dev, nullptr, nullptr,
+                            minmax_enc_dev, stream);
+}
+
+int pf_bn_bwd_planes(const float* dy_dev, const float* x_dev, int64_t m, int c, const float* mean_dev,
+                     const float* rstd_dev, const float* gamma_dev, const float* beta_dev, int act,
+                     float* dgamma_dev, float* dbeta_dev, float* dx_dev, int accumulate, void* dx_hi_dev,
+                     void* dx_lo_dev, float* ws_dev, void* stream) {
   PF_REQUIRE(m > 0 && c > 0 && (c & 3) == 0 && m < (1ll << 31), "pf_bn_bwd: bad shape (C must be a multiple of 4)");
-  PF_REQUIRE(dy_dev && x_dev && mean_dev && rstd_dev && gamma_dev && beta_dev && dgamma_dev && dbeta_dev &&
-                 dx_dev && ws_dev, "pf_bn_bwd: null pointer");
+  PF_REQUIRE(dy_dev && x_dev && mean_dev && rstd_dev && gamma_dev && beta_dev && dgamma_dev && dbeta_dev && ws_dev,
+             "pf_bn_bwd: null pointer");
+  PF_REQUIRE(dx_dev || dx_hi_dev, "pf_bn_bwd: no output");
+  PF_REQUIRE((dx_hi_dev == nullptr) == (dx_lo_dev == nullptr), "pf_bn_bwd: planes come in pairs");
+  PF_REQUIRE(!accumulate || dx_dev, "pf_bn_bwd: accumulate needs the fp32 dx");
+  PF_REQUIRE((((uintptr_t)dx_hi_dev | (uintptr_t)dx_lo_dev) & 7) == 0, "pf_bn_bwd: planes must be 8-byte aligned");
   int rps;
   const int splits = bn_splits((int)m, c, &rps);
   dim3 grid((c + kColTile - 1) / kColTile, splits);
@@ -640,9 +657,18 @@ int pf_bn_bwd(const float* dy_dev, const float* x_dev, int64_t m, int c, const f
   const int64_t total = m * c;
   bn_bwd_apply_kernel<<<chan_grid(total >> 2, c), NT, 0, st>>>(dy_dev, x_dev, total, c, 1.f / (float)m, mean_dev, rstd_dev,
                                                         gamma_dev, beta_dev, dgamma_dev, dbeta_dev, act, accumulate,
-                                                        dx_dev);
+                                                        dx_dev, dx_hi_dev, dx_lo_dev);
   PF_CHECK_LAUNCH("pf_bn_bwd/apply");
   return PF_OK;
+}
+
+int pf_bn_bwd(const float* dy_dev, const float* x_dev, int64_t m, int c, const float* mean_dev,
+              const float* rstd_dev, const float* gamma_dev, const float* beta_dev, int act,
+              float* dgamma_dev, float* dbeta_dev, float* dx_dev, int accumulate, float* ws_dev,
+              void* stream) {
+  PF_REQUIRE(dx_dev != nullptr, "pf_bn_bwd: null pointer");
+  return pf_bn_bwd_planes(dy_dev, x_dev, m, c, mean_dev, rstd_dev, gamma_dev, beta_dev, act, dgamma_dev, dbeta_dev,
+                          dx_dev, accumulate, nullptr, nullptr, ws_dev, stream);
 }
 
 int pf_add(const float* a_dev, const float* b_dev, int64_t n, int accumulate, float* out_dev, void* stream) {

@@ -247,7 +247,7 @@ uq_act_minmax_kernel(const float* __restrict__ x, int64_t n, uint32_t* __restric
 
 __global__ void __launch_bounds__(kThreads)
 uq_act_quant_kernel(const float* x, float* y, int64_t n, const uint32_t* __restrict__ minmax_enc,
-                    int bits) {
+                    int bits, void* __restrict__ y_hi, void* __restrict__ y_lo) {
   const float mn = pf_dec(__ldg(minmax_enc)), mx = pf_dec(__ldg(minmax_enc + 1));
   const float alpha = __fadd_rn(__fsub_rn(mx, mn), 1e-10f);
   const float k = pf_uq_kf(bits);
@@ -265,7 +265,8 @@ uq_act_quant_kernel(const float* x, float* y, int64_t n, const uint32_t* __restr
       v[u].y = pf_fake_quant(v[u].y, alpha, mn, k, ra, rk);
       v[u].z = pf_fake_quant(v[u].z, alpha, mn, k, ra, rk);
       v[u].w = pf_fake_quant(v[u].w, alpha, mn, k, ra, rk);
-      pf_st_stream(y + ((i + u * stride) << 2), v[u]);
+      if (y) pf_st_stream(y + ((i + u * stride) << 2), v[u]);
+      if (y_hi) pf_st_planes4(y_hi, y_lo, (i + u * stride) << 2, v[u]);
     }
   }
   for (; i < nvec; i += stride) {
@@ -274,9 +275,10 @@ uq_act_quant_kernel(const float* x, float* y, int64_t n, const uint32_t* __restr
     v.y = pf_fake_quant(v.y, alpha, mn, k, ra, rk);
     v.z = pf_fake_quant(v.z, alpha, mn, k, ra, rk);
     v.w = pf_fake_quant(v.w, alpha, mn, k, ra, rk);
-    pf_st_stream(y + (i << 2), v);
+    if (y) pf_st_stream(y + (i << 2), v);
+    if (y_hi) pf_st_planes4(y_hi, y_lo, i << 2, v);
   }
-  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+  if (y && blockIdx.x == 0 && threadIdx.x < (n & 3)) {
     const int64_t j = (nvec << 2) + threadIdx.x;
     y[j] = pf_fake_quant(x[j], alpha, mn, k, ra, rk);
   }
@@ -350,18 +352,27 @@ int pf_uq_act_minmax(const float* x_dev, int64_t n, uint32_t* minmax_enc_dev, vo
   return PF_OK;
 }
 
+int pf_uq_act_quant_planes(const float* x_dev, float* y_dev, void* y_hi_dev, void* y_lo_dev, int64_t n,
+                           const uint32_t* minmax_enc_dev, int bits, void* stream) {
+  PF_REQUIRE(n >= 0, "pf_uq_act_quant: n < 0");
+  PF_REQUIRE(bits >= 1 && bits <= 32, "pf_uq_act_quant: bits must be in [1, 32]");
+  if (n == 0) return PF_OK;
+  PF_REQUIRE(x_dev && (y_dev || y_hi_dev) && minmax_enc_dev, "pf_uq_act_quant: null pointer");
+  PF_REQUIRE((y_hi_dev == nullptr) == (y_lo_dev == nullptr), "pf_uq_act_quant: planes come in pairs");
+  PF_REQUIRE(y_hi_dev == nullptr || (n & 3) == 0, "pf_uq_act_quant: plane output needs n %% 4 == 0");
+  PF_REQUIRE((((uintptr_t)x_dev | (uintptr_t)y_dev) & 15) == 0 && (((uintptr_t)y_hi_dev | (uintptr_t)y_lo_dev) & 7) == 0,
+             "pf_uq_act_quant: x and y must be 16-byte aligned (planes: 8)");
+  uq_act_quant_kernel<<<act_grid(n), kThreads, 0, (cudaStream_t)stream>>>(x_dev, y_dev, n, minmax_enc_dev, bits,
+                                                                         y_hi_dev, y_lo_dev);
+  PF_CHECK_LAUNCH("pf_uq_act_quant");
+  return PF_OK;
+}
+
 int pf_uq_act_quant(const float* x_dev, float* y_dev, int64_t n, const uint32_t* minmax_enc_dev,
                     int bits, void* stream) {
   PF_REQUIRE(n >= 0, "pf_uq_act_quant: n < 0");
-  PF_REQUIRE(bits >= 1 && bits <= 32, "pf_uq_act_quant: bits must be in [1,32], got %d", bits);
-  if (n == 0) return PF_OK;
-  PF_REQUIRE(x_dev && y_dev && minmax_enc_dev, "pf_uq_act_quant: null pointer");
-  PF_REQUIRE((((uintptr_t)x_dev | (uintptr_t)y_dev) & 15) == 0,
-             "pf_uq_act_quant: x and y must be 16-byte aligned");
-  uq_act_quant_kernel<<<act_grid(n), kThreads, 0, (cudaStream_t)stream>>>(x_dev, y_dev, n,
-                                                                         minmax_enc_dev, bits);
-  PF_CHECK_LAUNCH("pf_uq_act_quant");
-  return PF_OK;
+  PF_REQUIRE(n == 0 || y_dev != nullptr, "pf_uq_act_quant: null pointer");
+  return pf_uq_act_quant_planes(x_dev, y_dev, nullptr, nullptr, n, minmax_enc_dev, bits, stream);
 }
 
 }  // extern "C"

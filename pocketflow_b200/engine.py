@@ -245,7 +245,7 @@ class Executor:
                 if self.train:
                     if op in self.tc and ops.conv2d_tc_wgrad_supported(d):
                         self.tc_wgrad.add(op)
-                        max_ws = max(max_ws, ops.conv2d_tc_wgrad_workspace_floats(d))
+                        max_ws = max(max_ws, ops.conv2d_tc_wgrad_planes_workspace_floats(d))
                     max_ws = max(max_ws, ops.conv2d_wgrad_workspace_floats(d))
                     max_wt = max(max_wt, op.vars['kernel'].numel)
             if op.type == 'DepthwiseConv2dNative':
@@ -280,6 +280,28 @@ class Executor:
                     self.add_fused.add(op)
                     self.buf[x_t] = self.buf[op.output]       # the conv output IS the add output
                     break
+        # ---- split-bf16 operand planes (tensor-core path): the BN-apply / activation-quantizer that produces a conv
+        # input writes it directly in the operand format of the tcgen05 kernels (x = hi + lo, two bf16 planes);
+        # the fp32 copy is only written when some other consumer needs it
+        self.xplanes, self.bn_need_f32 = {}, {}
+        max_x = max_dy = 8
+        for op in self.ops:
+            if op in self.tc and op not in self.im2col:
+                r = self._root(op.inputs[0])
+                if r is not None and r.op.type == 'FusedBatchNorm' and r.numel % 8 == 0:
+                    if r.op not in self.xplanes:
+                        self.xplanes[r.op] = ops.Planes(r.numel, dev)
+                        self.bn_need_f32[r.op] = False
+                elif self.train:
+                    max_x = max(max_x, op.inputs[0].numel)
+        for bn_op in self.xplanes:
+            ts = [bn_op.output] + [c.output for c in self._consumers(bn_op.output) if c in self.fused_into]
+            for t in ts:
+                for c in self._consumers(t):
+                    if c in self.fused_into and self.fused_into[c] is bn_op:
+                        continue
+                    if not (c in self.tc and c not in self.im2col and (not self.train or c in self.tc_wgrad)):
+                        self.bn_need_f32[bn_op] = True
         if self.labels_t is not None and self.labels_t not in self.buf:
             self.buf[self.labels_t] = torch.zeros(self.labels_t.shape, dtype=torch.float32, device=dev)
         self.bn_ws = E((max_bnws,))
@@ -329,6 +351,20 @@ class Executor:
                     self.gbuf[t] = E(t.shape)
                 if op.type in ('Conv2D', 'MatMul') and op in self.fused_act:
                     self.relu_scratch[op] = E(t.shape)
+            # dy planes: a conv output consumed ONLY by a BatchNorm gets its gradient straight from BN-backward in
+            # operand format, stored in the memory of the (then unused) fp32 gradient buffer
+            self.gplanes = {}
+            for op in self.ops:
+                if op in self.tc_wgrad:
+                    t = op.output
+                    cons = self._consumers(t)
+                    if op not in self.fused_act and 'bias' not in op.vars and len(cons) == 1 \
+                            and cons[0].type == 'FusedBatchNorm' and t in self.gbuf and t.numel % 8 == 0:
+                        self.gplanes[t] = ops.Planes(t.numel, dev, self.gbuf[t].view(-1).view(torch.bfloat16))
+                    else:
+                        max_dy = max(max_dy, t.numel)
+            self.x_scratch = ops.Planes(max_x, dev) if self.tc_wgrad else None
+            self.dy_scratch = ops.Planes(max_dy, dev) if self.tc_wgrad else None
             if self.maskable:
                 self.MASK = torch.ones(st.n_masked, dtype=torch.float32, device=dev)
                 self.BKUP = st.P[:st.n_masked].clone()
@@ -392,6 +428,19 @@ class Executor:
         b = self.buf[t]
         return b if b.shape == shape else b.view(shape)
 
+    def _root(self, t):
+        """The tensor whose buffer holds t (following Reshape / fused-activation aliases); None when t is
+        held by an out-of-place quantized buffer."""
+        while t in self.alias:
+            if t.op in self.aq_out:
+                return None
+            t = self.alias[t]
+        return t
+
+    def planes_of(self, t):
+        r = self._root(t)
+        return self.xplanes.get(r.op) if r is not None else None
+
     def raw(self, t):
         while t in self.alias:
             t = self.alias[t]
@@ -449,9 +498,14 @@ class Executor:
                     with self.timed('conv_prep'):
                         self.tc[op].prepare(self.kernel_of(op))
                     res = self.T(self.fused_add[op][1]) if op in self.fused_add else None
+                    xp = self.planes_of(op.inputs[0])
                     with self.timed('conv_fwd'):
-                        ops.conv2d_tc_fwd(self.desc[op], self.T(op.inputs[0]), self.tc[op], bias,
-                                          op in self.fused_act, self.buf[op.output], res)
+                        if xp is not None:
+                            ops.conv2d_tc_fwd_planes(self.desc[op], xp, self.tc[op], bias, op in self.fused_act,
+                                                     self.buf[op.output], res)
+                        else:
+                            ops.conv2d_tc_fwd(self.desc[op], self.T(op.inputs[0]), self.tc[op], bias,
+                                              op in self.fused_act, self.buf[op.output], res)
                 else:
                     with self.timed('conv_fwd'):
                         ops.conv2d_fwd(self.desc[op], self.T(op.inputs[0]), self.kernel_of(op), bias,
@@ -469,17 +523,22 @@ class Executor:
                 act = self.fused_act.get(op, 0)
                 relu_op = self._consumers(op.output)[0] if act else None
                 slot = self.aq_slots[self.aq_index[relu_op]] if relu_op in self.aq_index else None
+                pl = self.xplanes.get(op)
+                need_f32 = pl is None or self.bn_need_f32[op]
+                # with an activation quantizer the BN pass writes fp32 (+ range) and the quantizer writes the planes
+                pl_bn = pl if slot is None else None
+                y_bn = y if (need_f32 or slot is not None) else None
                 with self.timed('bn_fwd'):
                     if op.attrs['training'] and training:
                         ops.bn_train_stats(x, m, c, op.attrs['epsilon'], op.attrs['momentum'], b['mean'], b['var'],
                                            b['rstd'], mm, mv, self.bn_ws)
-                        ops.bn_apply(x, m, c, b['mean'], b['rstd'], gamma, beta, act, y, slot)
+                        ops.bn_apply(x, m, c, b['mean'], b['rstd'], gamma, beta, act, y_bn, slot, pl_bn)
                     else:
                         ops.bn_eval_prepare(mv, c, op.attrs['epsilon'], b['rstd'])
-                        ops.bn_apply(x, m, c, mm, b['rstd'], gamma, beta, act, y, slot)
+                        ops.bn_apply(x, m, c, mm, b['rstd'], gamma, beta, act, y_bn, slot, pl_bn)
                 if slot is not None:
                     with self.timed('act_quant'):
-                        ops.act_quant(y, y, slot, self.act_quant['bits'][self.aq_index[relu_op]])
+                        ops.act_quant(y, y if need_f32 else None, slot, self.act_quant['bits'][self.aq_index[relu_op]], pl)
             elif ty in ACT_TYPES:
                 src = self.fused_into[op]
                 if op in self.aq_index and src.type != 'FusedBatchNorm':
@@ -551,13 +610,25 @@ class Executor:
                             ops.conv2d_wgrad(im['d1'], im['cols'], gy, self.wgrad_ws, im['dwpad'])
                         ops.add(im['dwpad'][:gk.numel()], None, gk.reshape(-1))
                     elif op in self.tc_wgrad:
-                        ops.conv2d_tc_wgrad(d, self.T(x_t), gy, self.wgrad_ws, st.view(op.vars['kernel'], self.G))
+                        # operands in split-bf16 planes: native (written by BN-apply / BN-backward) or split here
+                        xp = self.planes_of(x_t)
+                        if xp is None:
+                            xp = ops.Planes(x_t.numel, self.device, self.x_scratch.buf)
+                            ops.split_bf16(self.T(x_t), xp)
+                        gp = self.gplanes.get(op.output)
+                        if gp is None:
+                            gp = ops.Planes(op.output.numel, self.device, self.dy_scratch.buf)
+                            ops.split_bf16(gy, gp)
+                        ops.conv2d_tc_wgrad_planes(d, xp, gp, self.wgrad_ws, st.view(op.vars['kernel'], self.G))
                     else:
+                        gp = None
                         ops.conv2d_wgrad(d, self.T(x_t), gy, self.wgrad_ws, st.view(op.vars['kernel'], self.G))
                 if x_t.op.type != 'Placeholder':
                     gx, acc = self.grad_target(x_t)
                     with self.timed('conv_dgrad'):
-                        if op in self.tc:
+                        if op in self.tc_wgrad and op not in self.im2col:
+                            ops.conv2d_tc_dgrad_planes(d, gp, self.tc[op], acc, gx)
+                        elif op in self.tc:
                             ops.conv2d_tc_dgrad(d, gy, self.tc[op], acc, gx)
                         else:
                             ops.conv2d_dgrad(d, gy, self.kernel_of(op), self.wt_ws, acc, gx)
@@ -576,11 +647,13 @@ class Executor:
                 m = y.numel() // c
                 b = self.bn[op]
                 gx, acc = self.grad_target(x_t)
+                gp = self.gplanes.get(x_t)
+                assert gp is None or not acc
                 with self.timed('bn_bwd'):
                     ops.bn_bwd(gy, self.T(x_t), m, c, b['mean'], b['rstd'], st.view(op.vars['gamma']),
                                st.view(op.vars['beta']), self.fused_act.get(op, 0),
-                               st.view(op.vars['gamma'], self.G), st.view(op.vars['beta'], self.G), gx, acc,
-                               self.bn_ws)
+                               st.view(op.vars['gamma'], self.G), st.view(op.vars['beta'], self.G),
+                               None if gp is not None else gx, acc, self.bn_ws, gp)
             elif ty == 'MaxPool':
                 x_t = op.inputs[0]
                 gx, acc = self.grad_target(x_t)

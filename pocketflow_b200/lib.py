@@ -27,6 +27,7 @@ SIGNATURES = {
     'pf_uq_weight_ste_bwd': (c_i32, [c_vp, c_vp, c_i32, c_vp, c_i32, c_vp]),
     'pf_uq_act_minmax': (c_i32, [c_vp, c_i64, c_vp, c_vp]),
     'pf_uq_act_quant': (c_i32, [c_vp, c_vp, c_i64, c_vp, c_i32, c_vp]),
+    'pf_uq_act_quant_planes': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i32, c_vp]),
     'pf_ws_mask_build': (c_i32, [c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
     'pf_select_desc': (c_i32, [c_vp, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
     'pf_momentum_step': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_f32, c_f32, c_f32, c_vp]),
@@ -47,6 +48,11 @@ SIGNATURES = {
     'pf_conv2d_tc_wgrad_supported': (c_i32, [c_vp]),
     'pf_conv2d_tc_wgrad_workspace_bytes': (c_i64, [c_vp]),
     'pf_conv2d_tc_wgrad': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'pf_split_bf16': (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp]),
+    'pf_conv2d_tc_wgrad_planes_workspace_bytes': (c_i64, [c_vp]),
+    'pf_conv2d_tc_fwd_planes': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]),
+    'pf_conv2d_tc_dgrad_planes': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
+    'pf_conv2d_tc_wgrad_planes': (c_i32, [c_vp] * 8),
     'pf_tc_probe': (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32] + [ctypes.c_uint32] * 6 + [c_vp]),
     'pf_dwconv_fwd': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp]),
     'pf_dwconv_dgrad': (c_i32, [c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
@@ -57,6 +63,9 @@ SIGNATURES = {
     'pf_bn_apply': (c_i32, [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]),
     'pf_bn_bwd': (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_i32,
                           c_vp, c_vp]),
+    'pf_bn_apply_planes': (c_i32, [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'pf_bn_bwd_planes': (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_i32,
+                                 c_vp, c_vp, c_vp, c_vp]),
     'pf_add': (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp]),
     'pf_relu_bwd': (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp]),
     'pf_colsum': (c_i32, [c_vp, c_i64, c_i32, c_vp, c_vp]),

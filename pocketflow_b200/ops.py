@@ -236,12 +236,17 @@ def act_minmax(x, minmax):
     _lib.check(_lib.load().pf_uq_act_minmax(_p(x), x.numel(), _p(minmax), _stream()), 'pf_uq_act_minmax')
 
 
-def act_quant(x, y, minmax, bits):
+def act_quant(x, y, minmax, bits, planes=None):
+    """y = Q(x); `planes` = Planes to (also) receive y in the tensor-core operand format (y may then be None)."""
     _check_f32(x, y)
     if not 1 <= int(bits) <= 32:
         raise ValueError('bit-widths must be in [1, 32]')
-    _lib.check(_lib.load().pf_uq_act_quant(_p(x), _p(y), x.numel(), _p(minmax), int(bits), _stream()),
-               'pf_uq_act_quant')
+    if planes is None:
+        _lib.check(_lib.load().pf_uq_act_quant(_p(x), _p(y), x.numel(), _p(minmax), int(bits), _stream()),
+                   'pf_uq_act_quant')
+    else:
+        _lib.check(_lib.load().pf_uq_act_quant_planes(_p(x), _p(y), _p(planes.hi), _p(planes.lo), x.numel(), _p(minmax),
+                                                      int(bits), _stream()), 'pf_uq_act_quant_planes')
 
 
 def act_fake_quant(x, bits, out=None, minmax=None):
@@ -453,15 +458,25 @@ def bn_eval_prepare(mov_var, c, eps, rstd):
     _lib.check(_lib.load().pf_bn_eval_prepare(_p(mov_var), c, float(eps), _p(rstd), _stream()), 'pf_bn_eval_prepare')
 
 
-def bn_apply(x, m, c, mean, rstd, gamma, beta, act, y, minmax=None):
-    _lib.check(_lib.load().pf_bn_apply(_p(x), m, c, _p(mean), _p(rstd), _p(gamma), _p(beta), int(act), _p(y),
-                                       _p(minmax), _stream()), 'pf_bn_apply')
+def bn_apply(x, m, c, mean, rstd, gamma, beta, act, y, minmax=None, planes=None):
+    if planes is None:
+        _lib.check(_lib.load().pf_bn_apply(_p(x), m, c, _p(mean), _p(rstd), _p(gamma), _p(beta), int(act), _p(y),
+                                           _p(minmax), _stream()), 'pf_bn_apply')
+    else:
+        _lib.check(_lib.load().pf_bn_apply_planes(_p(x), m, c, _p(mean), _p(rstd), _p(gamma), _p(beta), int(act), _p(y),
+                                                  _p(planes.hi), _p(planes.lo), _p(minmax), _stream()),
+                   'pf_bn_apply_planes')
 
 
-def bn_bwd(dy, x, m, c, mean, rstd, gamma, beta, act, dgamma, dbeta, dx, accumulate, ws):
-    _lib.check(_lib.load().pf_bn_bwd(_p(dy), _p(x), m, c, _p(mean), _p(rstd), _p(gamma), _p(beta), int(act),
-                                     _p(dgamma), _p(dbeta), _p(dx), int(bool(accumulate)), _p(ws), _stream()),
-               'pf_bn_bwd')
+def bn_bwd(dy, x, m, c, mean, rstd, gamma, beta, act, dgamma, dbeta, dx, accumulate, ws, planes=None):
+    if planes is None:
+        _lib.check(_lib.load().pf_bn_bwd(_p(dy), _p(x), m, c, _p(mean), _p(rstd), _p(gamma), _p(beta), int(act),
+                                         _p(dgamma), _p(dbeta), _p(dx), int(bool(accumulate)), _p(ws), _stream()),
+                   'pf_bn_bwd')
+    else:
+        _lib.check(_lib.load().pf_bn_bwd_planes(_p(dy), _p(x), m, c, _p(mean), _p(rstd), _p(gamma), _p(beta), int(act),
+                                                _p(dgamma), _p(dbeta), _p(dx), int(bool(accumulate)), _p(planes.hi),
+                                                _p(planes.lo), _p(ws), _stream()), 'pf_bn_bwd_planes')
 
 
 def add(a, b, out, accumulate=False):
@@ -555,6 +570,44 @@ def conv2d_tc_wgrad_workspace_floats(d):
 def conv2d_tc_wgrad(d, x, dy, ws, dw):
     _lib.check(_lib.load().pf_conv2d_tc_wgrad(ctypes.byref(d), _p(x), _p(dy), _p(ws), _p(dw), _stream()),
                'pf_conv2d_tc_wgrad')
+
+
+class Planes:
+    """A tensor in the operand format of the tensor-core kernels: x = hi + lo, two bf16 planes with the layout of
+    the fp32 tensor.  `buf` (optional) = one bf16 buffer of >= 2*numel elements to carve the planes from."""
+
+    def __init__(self, numel, device, buf=None):
+        assert numel % 8 == 0
+        if buf is None:
+            buf = torch.empty(2 * numel, dtype=torch.bfloat16, device=device)
+        assert buf.dtype == torch.bfloat16 and buf.numel() >= 2 * numel
+        self.numel, self.buf = numel, buf
+        self.hi, self.lo = buf[:numel], buf[numel:2 * numel]
+
+
+def split_bf16(src, planes):
+    """fp32 -> (hi, lo) bf16 planes."""
+    _lib.check(_lib.load().pf_split_bf16(_p(src), _p(planes.hi), _p(planes.lo), src.numel(), _stream()), 'pf_split_bf16')
+
+
+def conv2d_tc_fwd_planes(d, xp, tw, bias, relu, y, residual=None):
+    _lib.check(_lib.load().pf_conv2d_tc_fwd_planes(ctypes.byref(d), _p(xp.hi), _p(xp.lo), _p(tw.f_hi), _p(tw.f_lo), _p(bias),
+                                                   int(bool(relu)), _p(residual), _p(y), _stream()),
+               'pf_conv2d_tc_fwd_planes')
+
+
+def conv2d_tc_dgrad_planes(d, dyp, tw, accumulate, dx):
+    _lib.check(_lib.load().pf_conv2d_tc_dgrad_planes(ctypes.byref(d), _p(dyp.hi), _p(dyp.lo), _p(tw.d_hi), _p(tw.d_lo),
+                                                     int(bool(accumulate)), _p(dx), _stream()), 'pf_conv2d_tc_dgrad_planes')
+
+
+def conv2d_tc_wgrad_planes_workspace_floats(d):
+    return int(_lib.load().pf_conv2d_tc_wgrad_planes_workspace_bytes(ctypes.byref(d))) // 4
+
+
+def conv2d_tc_wgrad_planes(d, xp, dyp, ws, dw):
+    _lib.check(_lib.load().pf_conv2d_tc_wgrad_planes(ctypes.byref(d), _p(xp.hi), _p(xp.lo), _p(dyp.hi), _p(dyp.lo), _p(ws),
+                                                     _p(dw), _stream()), 'pf_conv2d_tc_wgrad_planes')
 
 
 # ----------------------------------------------------------------------------- depthwise conv

@@ -228,3 +228,50 @@ def test_depthwise_conv_fwd_dgrad_wgrad(cfg):
     DW = torch.empty_like(W)
     ops.dwconv_wgrad(d, X, DY, ws, DW)
     close(DW, wd.grad.permute(2, 3, 0, 1))
+
+
+def _split_ref(t):
+    hi = t.to(torch.bfloat16)
+    return hi, (t - hi.float()).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize('act', [0, 1, 2])
+def test_bn_and_act_quant_plane_outputs(act):
+    """BN-apply / BN-backward / activation quantizer writing split-bf16 operand planes: the planes are exactly
+    split(fp32 result), with or without the fp32 output."""
+    g = torch.Generator().manual_seed(11 + act)
+    m, c = 4 * 9 * 9, 64
+    x = (torch.randn(m, c, generator=g) * 2 + 0.5).to(DEV)
+    dy = torch.randn(m, c, generator=g).to(DEV)
+    gamma, beta = (torch.rand(c, generator=g) + 0.5).to(DEV), (torch.randn(c, generator=g) * 0.3).to(DEV)
+    mean, var, rstd = [torch.empty(c, device=DEV) for _ in range(3)]
+    ws = torch.empty(3 * c * ops.BN_MAX_SPLITS, device=DEV)
+    ops.bn_train_stats(x, m, c, 1e-5, 0.9, mean, var, rstd, None, None, ws)
+    y = torch.empty_like(x)
+    slot = torch.zeros(2, dtype=torch.int32, device=DEV)
+    ops.minmax_reset(slot.view(1, 2))
+    ops.bn_apply(x, m, c, mean, rstd, gamma, beta, act, y, slot)
+    pl = ops.Planes(x.numel(), torch.device(DEV))
+    y2 = torch.empty_like(x)
+    ops.bn_apply(x, m, c, mean, rstd, gamma, beta, act, y2, None, pl)
+    h, l = _split_ref(y.view(-1))
+    assert torch.equal(y, y2) and torch.equal(pl.hi, h) and torch.equal(pl.lo, l)
+    pl2 = ops.Planes(x.numel(), torch.device(DEV))
+    ops.bn_apply(x, m, c, mean, rstd, gamma, beta, act, None, None, pl2)            # planes only
+    assert torch.equal(pl2.hi, h) and torch.equal(pl2.lo, l)
+    # activation quantizer: fp32 + planes, planes only
+    q = torch.empty_like(y)
+    ops.act_quant(y, q, slot, 8)
+    q2 = torch.empty_like(y)
+    ops.act_quant(y, q2, slot, 8, pl)
+    h, l = _split_ref(q.view(-1))
+    assert torch.equal(q, q2) and torch.equal(pl.hi, h) and torch.equal(pl.lo, l)
+    ops.act_quant(y, None, slot, 8, pl2)
+    assert torch.equal(pl2.hi, h) and torch.equal(pl2.lo, l)
+    # BN backward
+    dga, dbe, dga2, dbe2 = [torch.empty(c, device=DEV) for _ in range(4)]
+    dx = torch.empty_like(x)
+    ops.bn_bwd(dy, x, m, c, mean, rstd, gamma, beta, act, dga, dbe, dx, False, ws)
+    ops.bn_bwd(dy, x, m, c, mean, rstd, gamma, beta, act, dga2, dbe2, None, False, ws, pl)
+    h, l = _split_ref(dx.view(-1))
+    assert torch.equal(dga, dga2) and torch.equal(dbe, dbe2) and torch.equal(pl.hi, h) and torch.equal(pl.lo, l)

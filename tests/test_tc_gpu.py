@@ -107,6 +107,20 @@ def test_conv_tc_fwd_dgrad(case):
     assert err <= 2e-5, 'dgrad err %.3e' % err
     ops.conv2d_tc_dgrad(d, DY, tw, True, DX)
     assert (DX.cpu().double() - 2 * dx_ref).abs().max().item() <= 4e-5 * dx_ref.abs().max().item()
+    # pre-split operand planes: the same kernels fed by cp.async instead of convert-on-the-fly -> identical bits
+    xp, dyp = ops.Planes(X.numel(), torch.device(DEV)), ops.Planes(DY.numel(), torch.device(DEV))
+    ops.split_bf16(X, xp)
+    ops.split_bf16(DY, dyp)
+    Y2 = torch.empty_like(Y)
+    ops.conv2d_tc_fwd(d, X, tw, bias.to(DEV), True, Y, res.to(DEV))
+    ops.conv2d_tc_fwd_planes(d, xp, tw, bias.to(DEV), True, Y2, res.to(DEV))
+    assert torch.equal(Y, Y2)
+    DX2 = torch.full((n, h, w, c), 3.0, device=DEV)
+    ops.conv2d_tc_dgrad(d, DY, tw, False, DX)
+    ops.conv2d_tc_dgrad_planes(d, dyp, tw, False, DX2)
+    assert torch.equal(DX, DX2)
+    ops.conv2d_tc_dgrad_planes(d, dyp, tw, True, DX2)
+    assert (DX2.cpu().double() - 2 * dx_ref).abs().max().item() <= 4e-5 * dx_ref.abs().max().item()
     # against the exact-fp32 kernel: same answer to split-bf16 accuracy
     Y32 = torch.empty_like(Y)
     ops.conv2d_fwd(d, X, W, None, False, Y32)
@@ -150,3 +164,16 @@ def test_conv_tc_rejects_unsupported_shapes():
         f_hi = f_lo = dummy
     with pytest.raises(ValueError):
         ops.conv2d_tc_fwd(d, x, T, None, False, y)
+
+
+def test_split_bf16_planes():
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(4096 * 8, generator=g) * torch.logspace(-20, 20, 4096 * 8)).to(DEV)
+    pl = ops.Planes(x.numel(), torch.device(DEV))
+    ops.split_bf16(x, pl)
+    hi, lo = pl.hi, pl.lo
+    h_ref = x.to(torch.bfloat16)
+    l_ref = (x - h_ref.float()).to(torch.bfloat16)
+    assert torch.equal(hi, h_ref) and torch.equal(lo, l_ref)
+    rec = hi.double() + lo.double()
+    assert ((rec - x.double()).abs() <= x.double().abs() * 2.0 ** -16).all()
