@@ -230,6 +230,9 @@ typedef struct pf_conv_desc {
  * first layers whose Cin (3) the tensor-core path cannot take; the conv then runs as a 1x1 conv over
  * kpad channels. */
 int pf_im2col(const pf_conv_desc* d, const float* x_dev, int kpad, float* cols_dev, void* stream);
+/* same, written directly as split-bf16 operand planes [N*P*Q, kpad] (kpad % 8 == 0) */
+int pf_im2col_planes(const pf_conv_desc* d, const float* x_dev, int kpad, void* cols_hi_dev, void* cols_lo_dev,
+                     void* stream);
 /* y = conv(x, w) (+ bias[k]) (relu if relu != 0) */
 int pf_conv2d_fwd(const pf_conv_desc* d, const float* x_dev, const float* w_dev, const float* bias_dev,
                   int relu, float* y_dev, void* stream);
@@ -313,7 +316,18 @@ int pf_dwconv_wgrad(const pf_conv_desc* d, const float* x_dev, const float* dy_d
 int pf_bn_train_stats(const float* x_dev, int64_t m, int c, float eps, float momentum, float* mean_dev,
                       float* var_dev, float* rstd_dev, float* moving_mean_dev, float* moving_var_dev,
                       float* ws_dev, void* stream);
+/* stats + the per-tensor range of y = act(bn(x)) for the activation quantizer, evaluated from the per-channel
+ * extremes of x (every step of bn/act is monotone in x, so the result is bit-identical to a min/max pass over
+ * y); accumulates into minmax_enc_dev[0..1] (ordered-uint).  ws_dev: 5 * C * PF_BN_MAX_SPLITS floats. */
+int pf_bn_train_stats_range(const float* x_dev, int64_t m, int c, float eps, float momentum, float* mean_dev,
+                            float* var_dev, float* rstd_dev, float* moving_mean_dev, float* moving_var_dev,
+                            const float* gamma_dev, const float* beta_dev, int act, uint32_t* minmax_enc_dev,
+                            float* ws_dev, void* stream);
 int pf_bn_eval_prepare(const float* moving_var_dev, int c, float eps, float* rstd_dev, void* stream);
+/* y = Q(act(bn(x))) in one pass with a known range (pf_bn_train_stats_range): fp32 and/or split-bf16 planes */
+int pf_bn_apply_quant(const float* x_dev, int64_t m, int c, const float* mean_dev, const float* rstd_dev,
+                      const float* gamma_dev, const float* beta_dev, int act, const uint32_t* range_enc_dev, int bits,
+                      float* y_dev, void* y_hi_dev, void* y_lo_dev, void* stream);
 int pf_bn_apply(const float* x_dev, int64_t m, int c, const float* mean_dev, const float* rstd_dev,
                 const float* gamma_dev, const float* beta_dev, int act, float* y_dev,
                 uint32_t* minmax_enc_dev, void* stream);

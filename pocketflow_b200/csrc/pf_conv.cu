@@ -330,6 +330,48 @@ im2col_kernel(const float* __restrict__ x, Geom g, int M, int K, int kpad, float
   }
 }
 
+// im2col straight into split-bf16 operand planes (the 1x1 tensor-core conv's input format): one 16-byte chunk
+// (8 k-values) per thread per plane, consecutive threads -> consecutive chunks of a row; the k -> (r, s, c)
+// decode comes from a shared-memory table, the row decode uses two divisions per 8 outputs.
+__global__ void __launch_bounds__(256)
+im2col_planes_kernel(const float* __restrict__ x, Geom g, int M, int K, int kpad, void* __restrict__ hi,
+                     void* __restrict__ lo) {
+  extern __shared__ int s_tab[];                 // per k: (r << 20) | (q << 10) | c, or -1 beyond K
+  for (int k = threadIdx.x; k < kpad; k += 256) {
+    int e = -1;
+    if (k < K) {
+      const int rs = k / g.C, c = k - rs * g.C;
+      const int r = rs / g.S, q = rs - r * g.S;
+      e = (r << 20) | (q << 10) | c;
+    }
+    s_tab[k] = e;
+  }
+  __syncthreads();
+  const int kc = kpad >> 3;
+  const int64_t total = (int64_t)M * kc;
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  const int pq = g.P * g.Q;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += stride) {
+    const int m = (int)(i / kc);
+    const int k0 = (int)(i - (int64_t)m * kc) << 3;
+    const int n = m / pq;
+    const int rem = m - n * pq;
+    const int oh = rem / g.Q, ow = rem - oh * g.Q;
+    const int ih0 = oh * g.sh - g.pt, iw0 = ow * g.sw - g.pl;
+    const float* xn = x + (size_t)n * g.H * g.W * g.C;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int e = s_tab[k0 + j];
+      const int ih = ih0 + (e >> 20), iw = iw0 + ((e >> 10) & 1023);
+      v[j] = (e >= 0 && ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) ? __ldg(xn + ((size_t)ih * g.W + iw) * g.C + (e & 1023)) : 0.f;
+    }
+    const int64_t o = (int64_t)m * kpad + k0;
+    pf_st_planes4(hi, lo, o, make_float4(v[0], v[1], v[2], v[3]));
+    pf_st_planes4(hi, lo, o + 4, make_float4(v[4], v[5], v[6], v[7]));
+  }
+}
+
 int check_geom(const pf_conv_desc* d, Geom* g, const char* who) {
   PF_REQUIRE(d != nullptr, "%s: null descriptor", who);
   PF_REQUIRE(d->n > 0 && d->h > 0 && d->w > 0 && d->c > 0 && d->k > 0 && d->r > 0 && d->s > 0 &&
@@ -361,6 +403,24 @@ int pf_im2col(const pf_conv_desc* d, const float* x_dev, int kpad, float* cols_d
   if (blocks > PF_NUM_SMS * 16) blocks = PF_NUM_SMS * 16;
   im2col_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x_dev, g, M, K, kpad, cols_dev);
   PF_CHECK_LAUNCH("pf_im2col");
+  return PF_OK;
+}
+
+int pf_im2col_planes(const pf_conv_desc* d, const float* x_dev, int kpad, void* cols_hi_dev, void* cols_lo_dev,
+                     void* stream) {
+  Geom g;
+  int rc = check_geom(d, &g, "pf_im2col_planes");
+  if (rc) return rc;
+  const int K = g.R * g.S * g.C, M = g.N * g.P * g.Q;
+  PF_REQUIRE(x_dev && cols_hi_dev && cols_lo_dev, "pf_im2col_planes: null pointer");
+  PF_REQUIRE(kpad >= K && kpad % 8 == 0 && kpad <= 8192, "pf_im2col_planes: kpad must be a multiple of 8 in [R*S*C, 8192]");
+  PF_REQUIRE(g.R < 1024 && g.S < 1024 && g.C < 1024, "pf_im2col_planes: filter / channel extent too large");
+  PF_REQUIRE((((uintptr_t)cols_hi_dev | (uintptr_t)cols_lo_dev) & 15) == 0, "pf_im2col_planes: planes must be 16-byte aligned");
+  int64_t blocks = ((int64_t)M * (kpad >> 3) + 255) / 256;
+  if (blocks > PF_NUM_SMS * 16) blocks = PF_NUM_SMS * 16;
+  im2col_planes_kernel<<<(unsigned)blocks, 256, kpad * sizeof(int), (cudaStream_t)stream>>>(x_dev, g, M, K, kpad, cols_hi_dev,
+                                                                                           cols_lo_dev);
+  PF_CHECK_LAUNCH("pf_im2col_planes");
   return PF_OK;
 }
 

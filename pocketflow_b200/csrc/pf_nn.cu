@@ -30,18 +30,28 @@ struct ColTile {
 };
 
 // BN statistics partials: per (split, channel): K (shift), s1 = sum(x-K), s2 = sum((x-K)^2)
+// RANGE: also min(x), max(x) per channel.  y = act(bn(x)) is a composition of correctly-rounded monotone steps, so
+// the per-tensor range of y needed by the activation quantizer (utils.py:51-79) is attained at the per-channel
+// extremes of x: the final kernel evaluates it from these, and no pass over y is needed.
+template <bool RANGE>
 __global__ void __launch_bounds__(NT)
 bn_stats_partial_kernel(const float* __restrict__ x, int M, int C, int rows_per_split,
-                        float* __restrict__ part /* [splits][3][C] */) {
-  __shared__ float sh[2][NT * 4];
+                        float* __restrict__ part /* [splits][3 or 5][C] */) {
+  __shared__ float sh[RANGE ? 4 : 2][NT * 4];
+  constexpr int NF = RANGE ? 5 : 3;
   const ColTile t(C);
   const int r0 = blockIdx.y * rows_per_split;
   const int r1 = min(M, r0 + rows_per_split);
   const int col = t.c0 + t.tx * 4;
   float4 K = make_float4(0.f, 0.f, 0.f, 0.f), s1 = K, s2 = K;
+  float4 mn = make_float4(INFINITY, INFINITY, INFINITY, INFINITY), mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
   if (t.ty < t.nty) {
     K = __ldg(reinterpret_cast<const float4*>(x + (size_t)r0 * C + col));
     auto acc = [&](const float4 v) {
+      if (RANGE) {
+        mn.x = fminf(mn.x, v.x); mn.y = fminf(mn.y, v.y); mn.z = fminf(mn.z, v.z); mn.w = fminf(mn.w, v.w);
+        mx.x = fmaxf(mx.x, v.x); mx.y = fmaxf(mx.y, v.y); mx.z = fmaxf(mx.z, v.z); mx.w = fmaxf(mx.w, v.w);
+      }
       const float dx = v.x - K.x, dy = v.y - K.y, dz = v.z - K.z, dw = v.w - K.w;
       s1.x += dx; s1.y += dy; s1.z += dz; s1.w += dw;
       s2.x = fmaf(dx, dx, s2.x); s2.y = fmaf(dy, dy, s2.y); s2.z = fmaf(dz, dz, s2.z); s2.w = fmaf(dw, dw, s2.w);
@@ -59,19 +69,33 @@ bn_stats_partial_kernel(const float* __restrict__ x, int M, int C, int rows_per_
     float* b = &sh[1][(t.ty * t.nvec + t.tx) * 4];
     a[0] = s1.x; a[1] = s1.y; a[2] = s1.z; a[3] = s1.w;
     b[0] = s2.x; b[1] = s2.y; b[2] = s2.z; b[3] = s2.w;
+    if (RANGE) {
+      float* lo = &sh[RANGE ? 2 : 0][(t.ty * t.nvec + t.tx) * 4];
+      float* hi = &sh[RANGE ? 3 : 0][(t.ty * t.nvec + t.tx) * 4];
+      lo[0] = mn.x; lo[1] = mn.y; lo[2] = mn.z; lo[3] = mn.w;
+      hi[0] = mx.x; hi[1] = mx.y; hi[2] = mx.z; hi[3] = mx.w;
+    }
   }
   __syncthreads();
   // fixed-order combine over ty: deterministic
   for (int c = threadIdx.x; c < t.tc; c += NT) {
-    float a = 0.f, b = 0.f;
+    float a = 0.f, b = 0.f, lo = INFINITY, hi = -INFINITY;
     for (int y = 0; y < t.nty; ++y) {
       a += sh[0][(y * t.nvec + (c >> 2)) * 4 + (c & 3)];
       b += sh[1][(y * t.nvec + (c >> 2)) * 4 + (c & 3)];
+      if (RANGE) {
+        lo = fminf(lo, sh[RANGE ? 2 : 0][(y * t.nvec + (c >> 2)) * 4 + (c & 3)]);
+        hi = fmaxf(hi, sh[RANGE ? 3 : 0][(y * t.nvec + (c >> 2)) * 4 + (c & 3)]);
+      }
     }
-    float* p = part + (size_t)blockIdx.y * 3 * C;
+    float* p = part + (size_t)blockIdx.y * NF * C;
     p[t.c0 + c] = __ldg(x + (size_t)r0 * C + t.c0 + c);
     p[C + t.c0 + c] = a;
     p[2 * C + t.c0 + c] = b;
+    if (RANGE) {
+      p[3 * C + t.c0 + c] = lo;
+      p[4 * C + t.c0 + c] = hi;
+    }
   }
 }
 
@@ -93,20 +117,32 @@ __device__ __forceinline__ Moments merge_moments(const Moments a, const Moments 
   r.m2 = a.m2 + b.m2 + delta * delta * (a.n * b.n / r.n);
   return r;
 }
+__device__ __forceinline__ float bn_act(float x, float mu, float rs, float ga, float be, int act);
 __global__ void __launch_bounds__(NT)
 bn_stats_final_kernel(const float* __restrict__ part, int M, int C, int splits, int rows_per_split,
                       float eps, float momentum, float* __restrict__ mean, float* __restrict__ var,
-                      float* __restrict__ rstd, float* __restrict__ mov_mean, float* __restrict__ mov_var) {
+                      float* __restrict__ rstd, float* __restrict__ mov_mean, float* __restrict__ mov_var,
+                      int nf, const float* __restrict__ gamma, const float* __restrict__ beta, int act,
+                      uint32_t* __restrict__ minmax_enc) {
   const int lane = threadIdx.x & 31;
   const int c = blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
   if (c >= C) return;
   Moments acc{0.0, 0.0, 0.0};
+  float xlo = INFINITY, xhi = -INFINITY;
   for (int s = lane; s < splits; s += 32) {
     const int r0 = s * rows_per_split;
     const double n = (double)(min(M, r0 + rows_per_split) - r0);
-    const float* p = part + (size_t)s * 3 * C;
+    const float* p = part + (size_t)s * nf * C;
     const double K = p[c], s1 = p[C + c], s2 = p[2 * C + c];
     acc = merge_moments(acc, Moments{n, K + s1 / n, s2 - s1 * s1 / n});
+    if (nf == 5) {
+      xlo = fminf(xlo, p[3 * C + c]);
+      xhi = fmaxf(xhi, p[4 * C + c]);
+    }
+  }
+  if (nf == 5) {
+    xlo = pf_warp_min(xlo);
+    xhi = pf_warp_max(xhi);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -121,7 +157,14 @@ bn_stats_final_kernel(const float* __restrict__ part, int M, int C, int splits, 
   const float v = (float)(acc.m2 / acc.n);
   mean[c] = mu;
   var[c] = v;
-  rstd[c] = __frsqrt_rn(__fadd_rn(v, eps));
+  const float rs_ = __frsqrt_rn(__fadd_rn(v, eps));
+  rstd[c] = rs_;
+  if (nf == 5 && minmax_enc && xlo <= xhi) {
+    // range of y = act(bn(x)) over this channel: attained at the extremes of x (monotone in x)
+    const float ya = bn_act(xlo, mu, rs_, gamma[c], beta[c], act), yb = bn_act(xhi, mu, rs_, gamma[c], beta[c], act);
+    atomicMin(minmax_enc, pf_enc(fminf(ya, yb)));
+    atomicMax(minmax_enc + 1, pf_enc(fmaxf(ya, yb)));
+  }
   if (mov_mean) {
     // moving = moving*momentum + batch*(1-momentum); the moving variance uses the unbiased estimate
     const float om = __fsub_rn(1.f, momentum);
@@ -150,8 +193,19 @@ __global__ void __launch_bounds__(NT)
 bn_apply_kernel(const float* __restrict__ x, int64_t total, int C, const float* __restrict__ mean,
                 const float* __restrict__ rstd, const float* __restrict__ gamma,
                 const float* __restrict__ beta, int act, float* __restrict__ y,
-                uint32_t* __restrict__ minmax_enc, void* __restrict__ y_hi, void* __restrict__ y_lo) {
+                uint32_t* __restrict__ minmax_enc, void* __restrict__ y_hi, void* __restrict__ y_lo,
+                const uint32_t* __restrict__ q_range, int q_bits) {
   __shared__ float s_mn[NT / 32], s_mx[NT / 32];
+  // fused activation fake-quant (range known beforehand: pf_bn_train_stats_range)
+  float q_alpha = 1.f, q_beta = 0.f, q_k = 1.f, q_ra = 1.f, q_rk = 1.f;
+  if (q_range) {
+    const float qmn = pf_dec(__ldg(q_range)), qmx = pf_dec(__ldg(q_range + 1));
+    q_alpha = __fadd_rn(__fsub_rn(qmx, qmn), 1e-10f);
+    q_beta = qmn;
+    q_k = pf_uq_kf(q_bits);
+    q_ra = __frcp_rn(q_alpha);
+    q_rk = __frcp_rn(q_k);
+  }
   const int64_t nvec = total >> 2;
   const int64_t stride = (int64_t)gridDim.x * NT;
   int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x;
@@ -163,6 +217,12 @@ bn_apply_kernel(const float* __restrict__ x, int64_t total, int C, const float* 
     v.y = bn_act(v.y, mu.y, rs.y, ga.y, be.y, act);
     v.z = bn_act(v.z, mu.z, rs.z, ga.z, be.z, act);
     v.w = bn_act(v.w, mu.w, rs.w, ga.w, be.w, act);
+    if (q_range) {
+      v.x = pf_fake_quant(v.x, q_alpha, q_beta, q_k, q_ra, q_rk);
+      v.y = pf_fake_quant(v.y, q_alpha, q_beta, q_k, q_ra, q_rk);
+      v.z = pf_fake_quant(v.z, q_alpha, q_beta, q_k, q_ra, q_rk);
+      v.w = pf_fake_quant(v.w, q_alpha, q_beta, q_k, q_ra, q_rk);
+    }
     if (y) pf_st_stream(y + (idx << 2), v);
     if (y_hi) pf_st_planes4(y_hi, y_lo, idx << 2, v);
     mn = fminf(fminf(mn, v.x), fminf(v.y, fminf(v.z, v.w)));
@@ -584,23 +644,36 @@ inline int bn_splits(int M, int C, int* rows_per_split) {
 
 extern "C" {
 
-int pf_bn_train_stats(const float* x_dev, int64_t m, int c, float eps, float momentum, float* mean_dev,
-                      float* var_dev, float* rstd_dev, float* moving_mean_dev, float* moving_var_dev,
-                      float* ws_dev, void* stream) {
+int pf_bn_train_stats_range(const float* x_dev, int64_t m, int c, float eps, float momentum, float* mean_dev,
+                            float* var_dev, float* rstd_dev, float* moving_mean_dev, float* moving_var_dev,
+                            const float* gamma_dev, const float* beta_dev, int act, uint32_t* minmax_enc_dev,
+                            float* ws_dev, void* stream) {
   PF_REQUIRE(m > 0 && c > 0 && m < (1ll << 31), "pf_bn_train_stats: bad shape");
   PF_REQUIRE((c & 3) == 0, "pf_bn_train_stats: C must be a multiple of 4 (got %d)", c);
   PF_REQUIRE(x_dev && mean_dev && var_dev && rstd_dev && ws_dev, "pf_bn_train_stats: null pointer");
   PF_REQUIRE((moving_mean_dev == nullptr) == (moving_var_dev == nullptr), "pf_bn_train_stats: moving stats come in pairs");
+  PF_REQUIRE(minmax_enc_dev == nullptr || (gamma_dev && beta_dev && act >= 0 && act <= 2),
+             "pf_bn_train_stats_range: the output range needs gamma, beta and act in {0,1,2}");
   int rps;
   const int splits = bn_splits((int)m, c, &rps);
   dim3 grid((c + kColTile - 1) / kColTile, splits);
   cudaStream_t st = (cudaStream_t)stream;
-  bn_stats_partial_kernel<<<grid, NT, 0, st>>>(x_dev, (int)m, c, rps, ws_dev);
+  const int nf = minmax_enc_dev ? 5 : 3;
+  if (minmax_enc_dev) bn_stats_partial_kernel<true><<<grid, NT, 0, st>>>(x_dev, (int)m, c, rps, ws_dev);
+  else bn_stats_partial_kernel<false><<<grid, NT, 0, st>>>(x_dev, (int)m, c, rps, ws_dev);
   PF_CHECK_LAUNCH("pf_bn_train_stats/partial");
   bn_stats_final_kernel<<<(c + NT / 32 - 1) / (NT / 32), NT, 0, st>>>(ws_dev, (int)m, c, splits, rps, eps, momentum, mean_dev,
-                                                         var_dev, rstd_dev, moving_mean_dev, moving_var_dev);
+                                                         var_dev, rstd_dev, moving_mean_dev, moving_var_dev, nf, gamma_dev,
+                                                         beta_dev, act, minmax_enc_dev);
   PF_CHECK_LAUNCH("pf_bn_train_stats/final");
   return PF_OK;
+}
+
+int pf_bn_train_stats(const float* x_dev, int64_t m, int c, float eps, float momentum, float* mean_dev,
+                      float* var_dev, float* rstd_dev, float* moving_mean_dev, float* moving_var_dev,
+                      float* ws_dev, void* stream) {
+  return pf_bn_train_stats_range(x_dev, m, c, eps, momentum, mean_dev, var_dev, rstd_dev, moving_mean_dev, moving_var_dev,
+                                 nullptr, nullptr, 0, nullptr, ws_dev, stream);
 }
 
 int pf_bn_eval_prepare(const float* moving_var_dev, int c, float eps, float* rstd_dev, void* stream) {
@@ -610,9 +683,9 @@ int pf_bn_eval_prepare(const float* moving_var_dev, int c, float eps, float* rst
   return PF_OK;
 }
 
-int pf_bn_apply_planes(const float* x_dev, int64_t m, int c, const float* mean_dev, const float* rstd_dev,
-                       const float* gamma_dev, const float* beta_dev, int act, float* y_dev, void* y_hi_dev,
-                       void* y_lo_dev, uint32_t* minmax_enc_dev, void* stream) {
+static int bn_apply_impl(const float* x_dev, int64_t m, int c, const float* mean_dev, const float* rstd_dev,
+                         const float* gamma_dev, const float* beta_dev, int act, float* y_dev, void* y_hi_dev,
+                         void* y_lo_dev, uint32_t* minmax_enc_dev, const uint32_t* q_range_dev, int q_bits, void* stream) {
   PF_REQUIRE(m > 0 && c > 0 && (c & 3) == 0, "pf_bn_apply: bad shape (C must be a multiple of 4)");
   PF_REQUIRE(act >= 0 && act <= 2, "pf_bn_apply: act must be 0 (none), 1 (relu) or 2 (relu6)");
   PF_REQUIRE(x_dev && mean_dev && rstd_dev && gamma_dev && beta_dev, "pf_bn_apply: null pointer");
@@ -621,9 +694,26 @@ int pf_bn_apply_planes(const float* x_dev, int64_t m, int c, const float* mean_d
   PF_REQUIRE((((uintptr_t)y_hi_dev | (uintptr_t)y_lo_dev) & 7) == 0, "pf_bn_apply: planes must be 8-byte aligned");
   const int64_t total = m * c;
   bn_apply_kernel<<<chan_grid(total >> 2, c), NT, 0, (cudaStream_t)stream>>>(x_dev, total, c, mean_dev, rstd_dev, gamma_dev,
-                                                                     beta_dev, act, y_dev, minmax_enc_dev, y_hi_dev, y_lo_dev);
+                                                                     beta_dev, act, y_dev, minmax_enc_dev, y_hi_dev, y_lo_dev,
+                                                                     q_range_dev, q_bits);
   PF_CHECK_LAUNCH("pf_bn_apply");
   return PF_OK;
+}
+
+int pf_bn_apply_planes(const float* x_dev, int64_t m, int c, const float* mean_dev, const float* rstd_dev,
+                       const float* gamma_dev, const float* beta_dev, int act, float* y_dev, void* y_hi_dev,
+                       void* y_lo_dev, uint32_t* minmax_enc_dev, void* stream) {
+  return bn_apply_impl(x_dev, m, c, mean_dev, rstd_dev, gamma_dev, beta_dev, act, y_dev, y_hi_dev, y_lo_dev, minmax_enc_dev,
+                       nullptr, 0, stream);
+}
+
+int pf_bn_apply_quant(const float* x_dev, int64_t m, int c, const float* mean_dev, const float* rstd_dev,
+                      const float* gamma_dev, const float* beta_dev, int act, const uint32_t* range_enc_dev, int bits,
+                      float* y_dev, void* y_hi_dev, void* y_lo_dev, void* stream) {
+  PF_REQUIRE(range_enc_dev != nullptr, "pf_bn_apply_quant: null range");
+  PF_REQUIRE(bits >= 1 && bits <= 32, "pf_bn_apply_quant: bits must be in [1, 32]");
+  return bn_apply_impl(x_dev, m, c, mean_dev, rstd_dev, gamma_dev, beta_dev, act, y_dev, y_hi_dev, y_lo_dev, nullptr,
+                       range_enc_dev, bits, stream);
 }
 
 int pf_bn_apply(const float* x_dev, int64_t m, int c, const float* mean_dev, const float* rstd_dev,

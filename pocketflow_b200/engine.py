@@ -64,6 +64,7 @@ class ParamStore:
         self.n_other = max(opos, 4)
         self.P = torch.zeros(self.n_train, dtype=torch.float32, device=device)
         self.O = torch.zeros(self.n_other, dtype=torch.float32, device=device)
+        self.listeners = []                     # called after every bulk (re)load of the parameters
         self.init(seed)
 
     def init(self, seed):
@@ -76,6 +77,8 @@ class ParamStore:
             ho[self.offset[v]:self.offset[v] + v.numel] = v.initializer(rng, v.shape).reshape(-1)
         self.P.copy_(torch.from_numpy(hp))
         self.O.copy_(torch.from_numpy(ho))
+        for f in self.listeners:
+            f()
 
     def view(self, v, flat=None):
         buf = flat if flat is not None else (self.P if v.trainable else self.O)
@@ -94,6 +97,8 @@ class ParamStore:
                 self.view(v).copy_(torch.from_numpy(np.asarray(d[v.name], F32).reshape(v.shape)))
             elif strict:
                 raise KeyError('missing variable in checkpoint: ' + v.name)
+        for f in self.listeners:
+            f()
 
 
 class Executor:
@@ -121,12 +126,35 @@ class Executor:
         wd_of = dict(loss.l2) if loss is not None else {}
         self.wd_of = wd_of
         self.maskable = [v for v in (maskable or []) if v in variables]
+        # an inference-only executor that owns its parameters (the distillation teacher): the split-bf16 weight
+        # copies are prepared once and refreshed only when the store is (re)loaded
+        self.static_weights = (not train) and store is None
+        self._static_ready = False
         self.store = store or ParamStore(variables, device, wd_of, self.maskable, seed)
+        if self.static_weights:
+            self.store.listeners.append(self._invalidate_static)
         self.weight_quant, self.act_quant = weight_quant, act_quant
         self.prof = None
         self._plan()
         self._graph = None
         self.step_count = 0
+
+    def _invalidate_static(self):
+        """Parameters were (re)loaded: refresh the prepared weight copies now (a captured CUDA graph that contains
+        this executor's forward does not re-run the preparation)."""
+        self._static_ready = False
+        if hasattr(self, 'tc'):
+            self.prepare_static_weights()
+
+    def prepare_static_weights(self):
+        for op in self.ops:
+            if op in self.im2col:
+                im, wk = self.im2col[op], self.kernel_of(op)
+                ops.add(wk.reshape(-1), None, im['wpad'][:wk.numel()])
+                im['tw'].prepare(im['wpad'])
+            elif op in self.tc:
+                self.tc[op].prepare(self.kernel_of(op))
+        self._static_ready = True
 
     # ------------------------------------------------------------------ planning
     def _reachable_ops(self, out):
@@ -212,7 +240,7 @@ class Executor:
             if op.type == 'FusedBatchNorm':
                 c = op.output.shape[-1]
                 self.bn[op] = dict(mean=E((c,)), var=E((c,)), rstd=E((c,)))
-                max_bnws = max(max_bnws, 3 * c * ops.BN_MAX_SPLITS)
+                max_bnws = max(max_bnws, 5 * c * ops.BN_MAX_SPLITS)
             if op.type in ('Conv2D', 'MatMul'):
                 x, y = op.inputs[0], op.output
                 if op.type == 'Conv2D':
@@ -231,14 +259,17 @@ class Executor:
                     kdim = kh * kw * c
                     kpad = (kdim + 15) // 16 * 16
                     d1 = ops.conv_desc(n, p, q, kpad, k, 1, 1, p, q, 1, 1, 0, 0)
-                    self.im2col[op] = dict(kdim=kdim, kpad=kpad, d1=d1, compute=True,
-                                           cols=E((n * p * q, kpad)),
+                    # columns directly in operand planes when every consumer is a tensor-core kernel
+                    as_planes = (not self.train) or ops.conv2d_tc_wgrad_supported(d1)
+                    self.im2col[op] = dict(kdim=kdim, kpad=kpad, d1=d1, compute=True, planes=as_planes,
+                                           cols=ops.Planes(n * p * q * kpad, dev) if as_planes else E((n * p * q, kpad)),
                                            wpad=torch.zeros(kpad * k, dtype=torch.float32, device=dev),
                                            tw=ops.TcWeights(d1, dev, need_dgrad=False))
                     if self.train:
                         self.im2col[op]['dwpad'] = torch.zeros(kpad * k, dtype=torch.float32, device=dev)
                         if ops.conv2d_tc_wgrad_supported(d1):
-                            max_ws = max(max_ws, ops.conv2d_tc_wgrad_workspace_floats(d1))
+                            max_ws = max(max_ws, ops.conv2d_tc_wgrad_planes_workspace_floats(d1))
+                            self._stem_dy = max(getattr(self, '_stem_dy', 8), n * p * q * k)
                         max_ws = max(max_ws, ops.conv2d_wgrad_workspace_floats(d1))
                 if self.conv_path == 'tc' and ops.conv2d_tc_supported(d):
                     self.tc[op] = ops.TcWeights(d, dev, need_dgrad=self.train and x.op.type != 'Placeholder')
@@ -363,8 +394,9 @@ class Executor:
                         self.gplanes[t] = ops.Planes(t.numel, dev, self.gbuf[t].view(-1).view(torch.bfloat16))
                     else:
                         max_dy = max(max_dy, t.numel)
-            self.x_scratch = ops.Planes(max_x, dev) if self.tc_wgrad else None
-            self.dy_scratch = ops.Planes(max_dy, dev) if self.tc_wgrad else None
+            max_dy = max(max_dy, getattr(self, '_stem_dy', 8))
+            self.x_scratch = ops.Planes(max_x, dev)
+            self.dy_scratch = ops.Planes(max_dy, dev)
             if self.maskable:
                 self.MASK = torch.ones(st.n_masked, dtype=torch.float32, device=dev)
                 self.BKUP = st.P[:st.n_masked].clone()
@@ -477,6 +509,8 @@ class Executor:
         if self.wq is not None:
             with self.timed('weight_quant'):
                 self.wq.forward()
+        if self.static_weights and not self._static_ready:
+            self.prepare_static_weights()
         for op in self.ops:
             ty = op.type
             if ty in ('Placeholder', 'Reshape', 'Identity'):
@@ -488,15 +522,24 @@ class Executor:
                     wk = self.kernel_of(op)
                     with self.timed('conv_prep'):
                         if im['compute']:
-                            ops.im2col(self.desc[op], self.T(op.inputs[0]), im['kpad'], im['cols'])
-                        ops.add(wk.reshape(-1), None, im['wpad'][:wk.numel()])       # rows >= R*S*C stay zero
-                        im['tw'].prepare(im['wpad'])
+                            if im['planes']:
+                                ops.im2col_planes(self.desc[op], self.T(op.inputs[0]), im['kpad'], im['cols'])
+                            else:
+                                ops.im2col(self.desc[op], self.T(op.inputs[0]), im['kpad'], im['cols'])
+                        if not self.static_weights:
+                            ops.add(wk.reshape(-1), None, im['wpad'][:wk.numel()])       # rows >= R*S*C stay zero
+                            im['tw'].prepare(im['wpad'])
                     with self.timed('conv_fwd'):
-                        ops.conv2d_tc_fwd(im['d1'], im['cols'], im['tw'], bias, op in self.fused_act,
-                                          self.buf[op.output])
+                        if im['planes']:
+                            ops.conv2d_tc_fwd_planes(im['d1'], im['cols'], im['tw'], bias, op in self.fused_act,
+                                                     self.buf[op.output])
+                        else:
+                            ops.conv2d_tc_fwd(im['d1'], im['cols'], im['tw'], bias, op in self.fused_act,
+                                              self.buf[op.output])
                 elif op in self.tc:
-                    with self.timed('conv_prep'):
-                        self.tc[op].prepare(self.kernel_of(op))
+                    if not self.static_weights:
+                        with self.timed('conv_prep'):
+                            self.tc[op].prepare(self.kernel_of(op))
                     res = self.T(self.fused_add[op][1]) if op in self.fused_add else None
                     xp = self.planes_of(op.inputs[0])
                     with self.timed('conv_fwd'):
@@ -529,7 +572,14 @@ class Executor:
                 pl_bn = pl if slot is None else None
                 y_bn = y if (need_f32 or slot is not None) else None
                 with self.timed('bn_fwd'):
-                    if op.attrs['training'] and training:
+                    if op.attrs['training'] and training and slot is not None:
+                        # the statistics pass also yields the range of act(bn(x)); one fused BN + fake-quant pass
+                        ops.bn_train_stats_range(x, m, c, op.attrs['epsilon'], op.attrs['momentum'], b['mean'], b['var'],
+                                                 b['rstd'], mm, mv, gamma, beta, act, slot, self.bn_ws)
+                        ops.bn_apply_quant(x, m, c, b['mean'], b['rstd'], gamma, beta, act, slot,
+                                           self.act_quant['bits'][self.aq_index[relu_op]], y if need_f32 else None, pl)
+                        slot = None                                    # quantized already
+                    elif op.attrs['training'] and training:
                         ops.bn_train_stats(x, m, c, op.attrs['epsilon'], op.attrs['momentum'], b['mean'], b['var'],
                                            b['rstd'], mm, mv, self.bn_ws)
                         ops.bn_apply(x, m, c, b['mean'], b['rstd'], gamma, beta, act, y_bn, slot, pl_bn)
@@ -604,7 +654,11 @@ class Executor:
                     if op in self.im2col:
                         im = self.im2col[op]
                         gk = st.view(op.vars['kernel'], self.G)
-                        if ops.conv2d_tc_wgrad_supported(im['d1']):
+                        if im['planes']:
+                            gp = ops.Planes(op.output.numel, self.device, self.dy_scratch.buf)
+                            ops.split_bf16(gy, gp)
+                            ops.conv2d_tc_wgrad_planes(im['d1'], im['cols'], gp, self.wgrad_ws, im['dwpad'])
+                        elif ops.conv2d_tc_wgrad_supported(im['d1']):
                             ops.conv2d_tc_wgrad(im['d1'], im['cols'], gy, self.wgrad_ws, im['dwpad'])
                         else:
                             ops.conv2d_wgrad(im['d1'], im['cols'], gy, self.wgrad_ws, im['dwpad'])
@@ -724,7 +778,7 @@ class Executor:
         layer (it runs first inside device_step) instead of recomputing it."""
         for op, im in self.im2col.items():
             for op2, im2 in other.im2col.items():
-                if op.inputs[0] is op2.inputs[0] and im['kpad'] == im2['kpad'] and im['cols'].shape == im2['cols'].shape \
+                if op.inputs[0] is op2.inputs[0] and im['kpad'] == im2['kpad'] and im['planes'] == im2['planes'] \
                         and all(op.attrs[a] == op2.attrs[a] for a in ('ksize', 'strides', 'pad')):
                     im['cols'] = im2['cols']
                     im['compute'] = False

@@ -36,6 +36,7 @@ SIGNATURES = {
     'pf_l2_loss': (c_i32, [c_vp, c_i64, c_f32, c_i32, c_vp, c_vp, c_vp]),
     'pf_nuq_weight_quant': (c_i32, [c_vp, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
     'pf_im2col': (c_i32, [c_vp, c_vp, c_i32, c_vp, c_vp]),
+    'pf_im2col_planes': (c_i32, [c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]),
     'pf_conv2d_fwd': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
     'pf_conv2d_dgrad': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
     'pf_conv2d_wgrad_workspace_bytes': (c_i64, [c_vp]),
@@ -63,6 +64,9 @@ SIGNATURES = {
     'pf_bn_apply': (c_i32, [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]),
     'pf_bn_bwd': (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_i32,
                           c_vp, c_vp]),
+    'pf_bn_train_stats_range': (c_i32, [c_vp, c_i64, c_i32, c_f32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32,
+                                        c_vp, c_vp, c_vp]),
+    'pf_bn_apply_quant': (c_i32, [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
     'pf_bn_apply_planes': (c_i32, [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'pf_bn_bwd_planes': (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_i32,
                                  c_vp, c_vp, c_vp, c_vp]),

@@ -454,6 +454,20 @@ def bn_train_stats(x, m, c, eps, momentum, mean, var, rstd, mov_mean, mov_var, w
                                              _p(mov_mean), _p(mov_var), _p(ws), _stream()), 'pf_bn_train_stats')
 
 
+def bn_train_stats_range(x, m, c, eps, momentum, mean, var, rstd, mov_mean, mov_var, gamma, beta, act, minmax, ws):
+    """batch statistics + range of act(bn(x)) (for the activation quantizer) in the same pass over x"""
+    _lib.check(_lib.load().pf_bn_train_stats_range(_p(x), m, c, float(eps), float(momentum), _p(mean), _p(var), _p(rstd),
+                                                   _p(mov_mean), _p(mov_var), _p(gamma), _p(beta), int(act), _p(minmax),
+                                                   _p(ws), _stream()), 'pf_bn_train_stats_range')
+
+
+def bn_apply_quant(x, m, c, mean, rstd, gamma, beta, act, rng, bits, y=None, planes=None):
+    """Q(act(bn(x))) with a known range, to fp32 and/or operand planes"""
+    _lib.check(_lib.load().pf_bn_apply_quant(_p(x), m, c, _p(mean), _p(rstd), _p(gamma), _p(beta), int(act), _p(rng),
+                                             int(bits), _p(y), _p(planes.hi if planes is not None else None),
+                                             _p(planes.lo if planes is not None else None), _stream()), 'pf_bn_apply_quant')
+
+
 def bn_eval_prepare(mov_var, c, eps, rstd):
     _lib.check(_lib.load().pf_bn_eval_prepare(_p(mov_var), c, float(eps), _p(rstd), _stream()), 'pf_bn_eval_prepare')
 
@@ -608,6 +622,11 @@ def conv2d_tc_wgrad_planes_workspace_floats(d):
 def conv2d_tc_wgrad_planes(d, xp, dyp, ws, dw):
     _lib.check(_lib.load().pf_conv2d_tc_wgrad_planes(ctypes.byref(d), _p(xp.hi), _p(xp.lo), _p(dyp.hi), _p(dyp.lo), _p(ws),
                                                      _p(dw), _stream()), 'pf_conv2d_tc_wgrad_planes')
+
+
+def im2col_planes(d, x, kpad, planes):
+    _lib.check(_lib.load().pf_im2col_planes(ctypes.byref(d), _p(x), int(kpad), _p(planes.hi), _p(planes.lo), _stream()),
+               'pf_im2col_planes')
 
 
 # ----------------------------------------------------------------------------- depthwise conv

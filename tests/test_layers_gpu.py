@@ -275,3 +275,45 @@ def test_bn_and_act_quant_plane_outputs(act):
     ops.bn_bwd(dy, x, m, c, mean, rstd, gamma, beta, act, dga2, dbe2, None, False, ws, pl)
     h, l = _split_ref(dx.view(-1))
     assert torch.equal(dga, dga2) and torch.equal(dbe, dbe2) and torch.equal(pl.hi, h) and torch.equal(pl.lo, l)
+
+
+@pytest.mark.parametrize('act', [0, 1, 2])
+def test_bn_stats_range_and_fused_quant(act):
+    """Range of act(bn(x)) from the per-channel extremes of x == min/max pass over y (bit-exact), and the fused
+    BN + fake-quant pass == bn_apply followed by act_quant (bit-exact), incl. negative gammas."""
+    g = torch.Generator().manual_seed(23 + act)
+    m, c = 6 * 11 * 11, 96
+    x = (torch.randn(m, c, generator=g) * 3 - 0.7).to(DEV)
+    gamma, beta = (torch.randn(c, generator=g)).to(DEV), (torch.randn(c, generator=g) * 0.5 + 0.2).to(DEV)
+    mean, var, rstd, mean2, var2, rstd2 = [torch.empty(c, device=DEV) for _ in range(6)]
+    ws = torch.empty(5 * c * ops.BN_MAX_SPLITS, device=DEV)
+    slots = torch.zeros(2, 2, dtype=torch.int32, device=DEV)
+    ops.minmax_reset(slots)
+    ops.bn_train_stats(x, m, c, 1e-5, 0.9, mean, var, rstd, None, None, ws)
+    y = torch.empty_like(x)
+    ops.bn_apply(x, m, c, mean, rstd, gamma, beta, act, y, slots[0])
+    ops.bn_train_stats_range(x, m, c, 1e-5, 0.9, mean2, var2, rstd2, None, None, gamma, beta, act, slots[1], ws)
+    assert torch.equal(mean, mean2) and torch.equal(var, var2) and torch.equal(rstd, rstd2)
+    assert torch.equal(slots[0], slots[1]), (ops.decode_ordered(slots[0].cpu().numpy()), ops.decode_ordered(slots[1].cpu().numpy()))
+    q = torch.empty_like(y)
+    ops.act_quant(y, q, slots[0], 8)
+    q2 = torch.empty_like(y)
+    pl = ops.Planes(x.numel(), torch.device(DEV))
+    ops.bn_apply_quant(x, m, c, mean, rstd, gamma, beta, act, slots[1], 8, q2, pl)
+    h, l = _split_ref(q.view(-1))
+    assert torch.equal(q, q2) and torch.equal(pl.hi, h) and torch.equal(pl.lo, l)
+
+
+def test_im2col_planes_matches_fp32_im2col():
+    g = torch.Generator().manual_seed(3)
+    n, h, w, c, k, r, st, p0 = 3, 23, 23, 3, 64, 7, 2, 2
+    p = (h + 2 * p0 + 1 - r) // st + 1
+    x = torch.randn(n, h, w, c, generator=g).to(DEV)
+    d = ops.conv_desc(n, h, w, c, k, r, r, p, p, st, st, p0, p0)
+    kpad = (r * r * c + 15) // 16 * 16
+    cols = torch.empty(n * p * p, kpad, device=DEV)
+    ops.im2col(d, x, kpad, cols)
+    pl = ops.Planes(cols.numel(), torch.device(DEV))
+    ops.im2col_planes(d, x, kpad, pl)
+    hh, ll = _split_ref(cols.view(-1))
+    assert torch.equal(pl.hi, hh) and torch.equal(pl.lo, ll)

@@ -66,6 +66,13 @@ def main():
         fns = dict(fwd=lambda: ops.conv2d_tc_fwd(d, x, tw, None, False, y),
                    dgrad=lambda: ops.conv2d_tc_dgrad(d, dy, tw, False, dx),
                    wgrad=lambda: ops.conv2d_tc_wgrad(d, x, dy, ws, dw))
+        if os.environ.get('PLANES', '0') == '1':      # operands already split (as inside the training step)
+            xp, dyp = ops.Planes(x.numel(), dev), ops.Planes(dy.numel(), dev)
+            ops.split_bf16(x, xp)
+            ops.split_bf16(dy, dyp)
+            fns = dict(fwd=lambda: ops.conv2d_tc_fwd_planes(d, xp, tw, None, False, y),
+                       dgrad=lambda: ops.conv2d_tc_dgrad_planes(d, dyp, tw, False, dx),
+                       wgrad=lambda: ops.conv2d_tc_wgrad_planes(d, xp, dyp, ws, dw))
         line = '%-22s' % name
         for ps in passes:
             t = timeit(fns[ps])
