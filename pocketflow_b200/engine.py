@@ -352,24 +352,46 @@ class Executor:
             self.l2_ws = E((ops.L2_PARTIALS,))
             self.gbuf, self.galias = {}, {}
             self.relu_scratch = {}
-            # d(out)/d(in) of a residual Add is the identity: an input consumed ONLY by the Add shares the
-            # Add output's gradient buffer (no copy kernel); multi-consumer inputs keep their own buffer
+            # d(out)/d(in) of a residual Add is the identity, so an input can SHARE the Add output's gradient buffer
+            # (no copy kernel):
+            #  - an input consumed only by the Add (the conv3 / projection branch) is a pure reader of it;
+            #  - the identity shortcut x (also consumed by the next BN) turns the buffer into an in-place
+            #    accumulator: x's other consumers add their dx into it.  That is safe when every reader of the Add
+            #    output's gradient runs (in backward order) before every such writer, i.e. comes LATER in forward
+            #    order — checked below.
+            pos = {op: i for i, op in enumerate(self.ops)}
             add_alias = {}
+
+            def root_of(t):
+                while t in add_alias or t in self.alias:
+                    t = add_alias[t] if t in add_alias else self.alias[t]
+                return t
             for op in self.ops:
-                if op.type == 'Add':
-                    for x_t in op.inputs:
-                        root = x_t
-                        while root in self.alias:
-                            root = self.alias[root]
-                        single = len(self._consumers(x_t)) == 1 and root.op.type not in ('Placeholder',)
-                        chain_single = True
-                        tt = x_t
-                        while tt in self.alias:
-                            tt = self.alias[tt]
-                            chain_single = chain_single and len(self._consumers(tt)) == 1
-                        if single and chain_single and root not in add_alias and root is not op.output:
-                            add_alias[root] = op.output
-                            break                              # at most one input per Add
+                if op.type != 'Add':
+                    continue
+                for x_t in op.inputs:
+                    root = x_t
+                    while root in self.alias:
+                        root = self.alias[root]
+                    if root.op.type == 'Placeholder' or root in add_alias or root is op.output:
+                        continue
+                    single = len(self._consumers(x_t)) == 1
+                    chain_single = True
+                    tt = x_t
+                    while tt in self.alias:
+                        tt = self.alias[tt]
+                        chain_single = chain_single and len(self._consumers(tt)) == 1
+                    if single and chain_single:
+                        add_alias[root] = op.output
+                        continue
+                    if x_t in self.alias:
+                        continue
+                    # readers of g(Add out): ops whose output gradient lives in that buffer
+                    key = root_of(op.output)
+                    readers = [o for o in self.ops if o.type != 'Placeholder' and o is not op and root_of(o.output) is key]
+                    writers = [c for c in self._consumers(x_t) if c is not op]
+                    if all(pos[r] > pos[w] for r in readers for w in writers) and all(pos[w] < pos[op] for w in writers):
+                        add_alias[root] = op.output
             for op in self.ops:
                 t = op.output
                 if op.type == 'Placeholder':
@@ -382,18 +404,41 @@ class Executor:
                     self.gbuf[t] = E(t.shape)
                 if op.type in ('Conv2D', 'MatMul') and op in self.fused_act:
                     self.relu_scratch[op] = E(t.shape)
-            # dy planes: a conv output consumed ONLY by a BatchNorm gets its gradient straight from BN-backward in
-            # operand format, stored in the memory of the (then unused) fp32 gradient buffer
-            self.gplanes = {}
+            # ---- dy operand planes.  For every tensor-core conv, the LAST op that writes the gradient of its output
+            # before the conv's own backward runs; when that is a BatchNorm backward, it also emits the gradient as
+            # split-bf16 planes (dgrad + wgrad operands) instead of a separate split pass.  If the BN is the only
+            # writer and the conv the only reader, the fp32 copy is dropped and the planes live in its memory.
+            grad_writers = {}
             for op in self.ops:
-                if op in self.tc_wgrad:
-                    t = op.output
-                    cons = self._consumers(t)
-                    if op not in self.fused_act and 'bias' not in op.vars and len(cons) == 1 \
-                            and cons[0].type == 'FusedBatchNorm' and t in self.gbuf and t.numel % 8 == 0:
-                        self.gplanes[t] = ops.Planes(t.numel, dev, self.gbuf[t].view(-1).view(torch.bfloat16))
-                    else:
-                        max_dy = max(max_dy, t.numel)
+                if op.type in ('Placeholder', 'Reshape', 'Identity') or op in self.fused_into:
+                    continue
+                ins = op.inputs if op.type == 'Add' else op.inputs[:1]
+                for x_t in ins:
+                    if x_t.op.type == 'Placeholder':
+                        continue
+                    k = self.gkey(x_t)
+                    if op.type == 'Add' and k is self.gkey(op.output):
+                        continue
+                    grad_writers.setdefault(k, []).append(op)
+            self.bn_gplanes, self.bn_gplanes_only, self.conv_dy_planes = {}, {}, {}
+            for op in self.ops:
+                if op not in self.tc_wgrad or op in self.fused_act or 'bias' in op.vars or op.output.numel % 8:
+                    if op in self.tc_wgrad:
+                        max_dy = max(max_dy, op.output.numel)
+                    continue
+                k = self.gkey(op.output)
+                later = [w for w in grad_writers.get(k, []) if pos[w] > pos[op]]
+                lw = min(later, key=lambda w: pos[w]) if later else None
+                if lw is None or lw.type != 'FusedBatchNorm' or lw.inputs[0].numel != op.output.numel:
+                    max_dy = max(max_dy, op.output.numel)
+                    continue
+                if lw not in self.bn_gplanes:
+                    readers = [o for o in self.ops if o.type != 'Placeholder' and self.gkey(o.output) is k]
+                    only = len(grad_writers[k]) == 1 and readers == [op]
+                    self.bn_gplanes_only[lw] = only
+                    self.bn_gplanes[lw] = ops.Planes(op.output.numel, dev,
+                                                     self.gbuf[k].view(-1).view(torch.bfloat16) if only else None)
+                self.conv_dy_planes[op] = self.bn_gplanes[lw]
             max_dy = max(max_dy, getattr(self, '_stem_dy', 8))
             self.x_scratch = ops.Planes(max_x, dev)
             self.dy_scratch = ops.Planes(max_dy, dev)
@@ -669,7 +714,7 @@ class Executor:
                         if xp is None:
                             xp = ops.Planes(x_t.numel, self.device, self.x_scratch.buf)
                             ops.split_bf16(self.T(x_t), xp)
-                        gp = self.gplanes.get(op.output)
+                        gp = self.conv_dy_planes.get(op)
                         if gp is None:
                             gp = ops.Planes(op.output.numel, self.device, self.dy_scratch.buf)
                             ops.split_bf16(gy, gp)
@@ -701,13 +746,14 @@ class Executor:
                 m = y.numel() // c
                 b = self.bn[op]
                 gx, acc = self.grad_target(x_t)
-                gp = self.gplanes.get(x_t)
-                assert gp is None or not acc
+                gp = self.bn_gplanes.get(op)
+                only = gp is not None and self.bn_gplanes_only[op]
+                assert not (only and acc)
                 with self.timed('bn_bwd'):
                     ops.bn_bwd(gy, self.T(x_t), m, c, b['mean'], b['rstd'], st.view(op.vars['gamma']),
                                st.view(op.vars['beta']), self.fused_act.get(op, 0),
                                st.view(op.vars['gamma'], self.G), st.view(op.vars['beta'], self.G),
-                               None if gp is not None else gx, acc, self.bn_ws, gp)
+                               None if only else gx, acc, self.bn_ws, gp)
             elif ty == 'MaxPool':
                 x_t = op.inputs[0]
                 gx, acc = self.grad_target(x_t)
