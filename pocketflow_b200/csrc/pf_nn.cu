@@ -99,24 +99,13 @@ bn_stats_partial_kernel(const float* __restrict__ x, int M, int C, int rows_per_
   }
 }
 
-// Combine the partials (Chan et al.) in fp64; emit mean, biased var, rstd; update moving stats.
-// One WARP per channel: lanes stride over the row splits, then a 5-step shuffle merge — the first
-// version walked the splits serially per channel (up to 296 dependent global loads + fp64 divisions:
-// 165 us per launch in the ncu launch list, 5 % of the ResNet-50 step).  Fixed merge order:
-// deterministic.
-struct Moments {
-  double n, mean, m2;
-};
-__device__ __forceinline__ Moments merge_moments(const Moments a, const Moments b) {
-  if (b.n == 0.0) return a;
-  if (a.n == 0.0) return b;
-  Moments r;
-  r.n = a.n + b.n;
-  const double delta = b.mean - a.mean;
-  r.mean = a.mean + delta * (b.n / r.n);
-  r.m2 = a.m2 + b.m2 + delta * delta * (a.n * b.n / r.n);
-  return r;
-}
+// Combine the partials in fp64; emit mean, biased var, rstd; update moving stats.  Every split's shifted sums are
+// re-based to ONE common shift K0 (the first split's), after which they simply add:
+//     d = K - K0;  S1' = s1 + n d;  S2' = s2 + 2 d s1 + n d^2        (exact algebra, fp64)
+// and mean = K0 + S1/N, m2 = S2 - S1^2/N.  No divisions inside the loop (the first version merged Chan-style
+// moments pairwise: four fp64 divisions per split on a GPU with 1/64-rate fp64 — 36 us per launch).
+// kFinalWarps warps per channel stride over the splits; fixed-order shuffle + smem tree: deterministic.
+constexpr int kFinalWarps = 4;
 __device__ __forceinline__ float bn_act(float x, float mu, float rs, float ga, float be, int act);
 __global__ void __launch_bounds__(NT)
 bn_stats_final_kernel(const float* __restrict__ part, int M, int C, int splits, int rows_per_split,
@@ -124,35 +113,49 @@ bn_stats_final_kernel(const float* __restrict__ part, int M, int C, int splits, 
                       float* __restrict__ rstd, float* __restrict__ mov_mean, float* __restrict__ mov_var,
                       int nf, const float* __restrict__ gamma, const float* __restrict__ beta, int act,
                       uint32_t* __restrict__ minmax_enc) {
-  const int lane = threadIdx.x & 31;
-  const int c = blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
-  if (c >= C) return;
-  Moments acc{0.0, 0.0, 0.0};
+  constexpr int CPB = NT / 32 / kFinalWarps;      // channels per block
+  __shared__ double sh1[NT / 32], sh2[NT / 32];
+  __shared__ float shlo[NT / 32], shhi[NT / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cl = warp / kFinalWarps, sub = warp % kFinalWarps;
+  const int c = blockIdx.x * CPB + cl;
+  double S1 = 0.0, S2 = 0.0;
   float xlo = INFINITY, xhi = -INFINITY;
-  for (int s = lane; s < splits; s += 32) {
-    const int r0 = s * rows_per_split;
-    const double n = (double)(min(M, r0 + rows_per_split) - r0);
-    const float* p = part + (size_t)s * nf * C;
-    const double K = p[c], s1 = p[C + c], s2 = p[2 * C + c];
-    acc = merge_moments(acc, Moments{n, K + s1 / n, s2 - s1 * s1 / n});
-    if (nf == 5) {
-      xlo = fminf(xlo, p[3 * C + c]);
-      xhi = fmaxf(xhi, p[4 * C + c]);
+  const double K0 = c < C ? (double)part[c] : 0.0;
+  if (c < C) {
+    for (int s = sub * 32 + lane; s < splits; s += 32 * kFinalWarps) {
+      const int r0 = s * rows_per_split;
+      const double n = (double)(min(M, r0 + rows_per_split) - r0);
+      const float* p = part + (size_t)s * nf * C;
+      const double d = (double)p[c] - K0, s1 = p[C + c], s2 = p[2 * C + c];
+      S1 += s1 + n * d;
+      S2 += s2 + 2.0 * d * s1 + n * d * d;
+      if (nf == 5) {
+        xlo = fminf(xlo, p[3 * C + c]);
+        xhi = fmaxf(xhi, p[4 * C + c]);
+      }
     }
-  }
-  if (nf == 5) {
-    xlo = pf_warp_min(xlo);
-    xhi = pf_warp_max(xhi);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    Moments other;
-    other.n = __shfl_down_sync(0xffffffffu, acc.n, o);
-    other.mean = __shfl_down_sync(0xffffffffu, acc.mean, o);
-    other.m2 = __shfl_down_sync(0xffffffffu, acc.m2, o);
-    acc = merge_moments(acc, other);
+    S1 += __shfl_down_sync(0xffffffffu, S1, o);
+    S2 += __shfl_down_sync(0xffffffffu, S2, o);
   }
-  if (lane != 0) return;
+  xlo = pf_warp_min(xlo);
+  xhi = pf_warp_max(xhi);
+  if (lane == 0) { sh1[warp] = S1; sh2[warp] = S2; shlo[warp] = xlo; shhi[warp] = xhi; }
+  __syncthreads();
+  if (c >= C || sub != 0 || lane != 0) return;
+  for (int w = 1; w < kFinalWarps; ++w) {
+    S1 += sh1[warp + w];
+    S2 += sh2[warp + w];
+    xlo = fminf(xlo, shlo[warp + w]);
+    xhi = fmaxf(xhi, shhi[warp + w]);
+  }
+  struct { double n, mean, m2; } acc;
+  acc.n = (double)M;
+  acc.mean = K0 + S1 / acc.n;
+  acc.m2 = fmax(S2 - S1 * S1 / acc.n, 0.0);
   const float mu = (float)acc.mean;
   const float v = (float)(acc.m2 / acc.n);
   mean[c] = mu;
@@ -332,21 +335,28 @@ bn_bwd_partial_kernel(const float* __restrict__ dy, const float* __restrict__ x,
 __global__ void __launch_bounds__(NT)
 bn_bwd_final_kernel(const float* __restrict__ part, int C, int splits, float* __restrict__ dgamma,
                     float* __restrict__ dbeta) {
-  // one warp per channel, lanes over the splits, fixed-order shuffle tree (deterministic)
-  const int lane = threadIdx.x & 31;
-  const int c = blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
-  if (c >= C) return;
+  // kFinalWarps warps per channel, lanes over the splits, fixed-order shuffle + smem tree (deterministic)
+  constexpr int CPB = NT / 32 / kFinalWarps;
+  __shared__ double sha[NT / 32], shb[NT / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cl = warp / kFinalWarps, sub = warp % kFinalWarps;
+  const int c = blockIdx.x * CPB + cl;
   double sa = 0.0, sb = 0.0;
-  for (int s = lane; s < splits; s += 32) {
-    sa += part[(size_t)s * 2 * C + c];
-    sb += part[(size_t)s * 2 * C + C + c];
+  if (c < C) {
+    for (int s = sub * 32 + lane; s < splits; s += 32 * kFinalWarps) {
+      sa += part[(size_t)s * 2 * C + c];
+      sb += part[(size_t)s * 2 * C + C + c];
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     sa += __shfl_down_sync(0xffffffffu, sa, o);
     sb += __shfl_down_sync(0xffffffffu, sb, o);
   }
-  if (lane == 0) {
+  if (lane == 0) { sha[warp] = sa; shb[warp] = sb; }
+  __syncthreads();
+  if (c < C && sub == 0 && lane == 0) {
+    for (int w = 1; w < kFinalWarps; ++w) { sa += sha[warp + w]; sb += shb[warp + w]; }
     dbeta[c] = (float)sa;
     dgamma[c] = (float)sb;
   }
@@ -473,15 +483,17 @@ colsum_kernel(const float* __restrict__ a, int M, int C, float* __restrict__ out
 __global__ void __launch_bounds__(NT)
 maxpool_fwd_kernel(const float* __restrict__ x, int N, int H, int W, int C, int P, int Q, int kh, int kw,
                    int sh, int sw, int pt, int pl, float* __restrict__ y, uint8_t* __restrict__ argmax) {
-  const int64_t total = (int64_t)N * P * Q * (C >> 2);
-  const int64_t stride = (int64_t)gridDim.x * NT;
-  const int C4 = C >> 2;
-  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < total; i += stride) {
-    const int c = (int)(i % C4) << 2;
-    int64_t t = i / C4;
-    const int ow = (int)(t % Q); t /= Q;
-    const int oh = (int)(t % P);
-    const int n = (int)(t / P);
+  // N*P*Q < 2^31 (checked on the host): 32-bit pixel index, one division chain per 4 channels
+  const uint32_t C4 = (uint32_t)(C >> 2);
+  const uint32_t total = (uint32_t)N * P * Q * C4;         // < 2^31 (checked on the host)
+  const uint32_t stride = gridDim.x * NT;
+  for (uint32_t i = blockIdx.x * NT + threadIdx.x; i < total; i += stride) {
+    const uint32_t pix = i / C4;
+    const int c = (int)((i - pix * C4) << 2);
+    const uint32_t t1 = pix / (uint32_t)Q;
+    const int ow = (int)(pix - t1 * (uint32_t)Q);
+    const int n = (int)(t1 / (uint32_t)P);
+    const int oh = (int)(t1 - (uint32_t)n * (uint32_t)P);
     float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
     int a[4] = {255, 255, 255, 255};
     for (int r = 0; r < kh; ++r) {
@@ -509,15 +521,16 @@ __global__ void __launch_bounds__(NT)
 maxpool_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ argmax, int N, int H, int W, int C,
                    int P, int Q, int kh, int kw, int sh, int sw, int pt, int pl, int accumulate,
                    float* __restrict__ dx) {
-  const int C4 = C >> 2;
-  const int64_t total = (int64_t)N * H * W * C4;
-  const int64_t stride = (int64_t)gridDim.x * NT;
-  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < total; i += stride) {
-    const int c = (int)(i % C4) << 2;
-    int64_t t = i / C4;
-    const int iw = (int)(t % W); t /= W;
-    const int ih = (int)(t % H);
-    const int n = (int)(t / H);
+  const uint32_t C4 = (uint32_t)(C >> 2);
+  const uint32_t total = (uint32_t)N * H * W * C4;         // < 2^31 (checked on the host)
+  const uint32_t stride = gridDim.x * NT;
+  for (uint32_t i = blockIdx.x * NT + threadIdx.x; i < total; i += stride) {
+    const uint32_t pix = i / C4;
+    const int c = (int)((i - pix * C4) << 2);
+    const uint32_t t1 = pix / (uint32_t)W;
+    const int iw = (int)(pix - t1 * (uint32_t)W);
+    const int n = (int)(t1 / (uint32_t)H);
+    const int ih = (int)(t1 - (uint32_t)n * (uint32_t)H);
     float g[4] = {0.f, 0.f, 0.f, 0.f};
     const int oh_lo = max(0, (ih + pt - kh + sh) / sh), oh_hi = min(P - 1, (ih + pt) / sh);
     const int ow_lo = max(0, (iw + pl - kw + sw) / sw), ow_hi = min(Q - 1, (iw + pl) / sw);
@@ -538,7 +551,7 @@ maxpool_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ arg
       }
     }
     float4 o4 = make_float4(g[0], g[1], g[2], g[3]);
-    float* p = dx + (i << 2);
+    float* p = dx + ((size_t)i << 2);
     if (accumulate) {
       const float4 old = *reinterpret_cast<const float4*>(p);
       o4.x += old.x; o4.y += old.y; o4.z += old.z; o4.w += old.w;
@@ -662,7 +675,8 @@ int pf_bn_train_stats_range(const float* x_dev, int64_t m, int c, float eps, flo
   if (minmax_enc_dev) bn_stats_partial_kernel<true><<<grid, NT, 0, st>>>(x_dev, (int)m, c, rps, ws_dev);
   else bn_stats_partial_kernel<false><<<grid, NT, 0, st>>>(x_dev, (int)m, c, rps, ws_dev);
   PF_CHECK_LAUNCH("pf_bn_train_stats/partial");
-  bn_stats_final_kernel<<<(c + NT / 32 - 1) / (NT / 32), NT, 0, st>>>(ws_dev, (int)m, c, splits, rps, eps, momentum, mean_dev,
+  constexpr int kCPB = NT / 32 / kFinalWarps;
+  bn_stats_final_kernel<<<(c + kCPB - 1) / kCPB, NT, 0, st>>>(ws_dev, (int)m, c, splits, rps, eps, momentum, mean_dev,
                                                          var_dev, rstd_dev, moving_mean_dev, moving_var_dev, nf, gamma_dev,
                                                          beta_dev, act, minmax_enc_dev);
   PF_CHECK_LAUNCH("pf_bn_train_stats/final");
@@ -742,7 +756,7 @@ int pf_bn_bwd_planes(const float* dy_dev, const float* x_dev, int64_t m, int c, 
   bn_bwd_partial_kernel<<<grid, NT, 0, st>>>(dy_dev, x_dev, (int)m, c, rps, mean_dev, rstd_dev, gamma_dev, beta_dev,
                                             act, ws_dev);
   PF_CHECK_LAUNCH("pf_bn_bwd/partial");
-  bn_bwd_final_kernel<<<(c + NT / 32 - 1) / (NT / 32), NT, 0, st>>>(ws_dev, c, splits, dgamma_dev, dbeta_dev);
+  bn_bwd_final_kernel<<<(c + NT / 32 / kFinalWarps - 1) / (NT / 32 / kFinalWarps), NT, 0, st>>>(ws_dev, c, splits, dgamma_dev, dbeta_dev);
   PF_CHECK_LAUNCH("pf_bn_bwd/final");
   const int64_t total = m * c;
   bn_bwd_apply_kernel<<<chan_grid(total >> 2, c), NT, 0, st>>>(dy_dev, x_dev, total, c, 1.f / (float)m, mean_dev, rstd_dev,
@@ -792,6 +806,7 @@ int pf_maxpool_fwd(const pf_conv_desc* d, const float* x_dev, float* y_dev, uint
   PF_REQUIRE(d && x_dev && y_dev && d->n > 0 && d->c > 0 && d->p > 0 && d->q > 0, "pf_maxpool_fwd: bad arguments");
   PF_REQUIRE((d->c & 3) == 0 && d->r * d->s < 255, "pf_maxpool_fwd: C must be a multiple of 4 and the window < 255");
   const int64_t total = (int64_t)d->n * d->p * d->q * (d->c >> 2);
+  PF_REQUIRE(total < (1ll << 31), "pf_maxpool_fwd: tensor too large");
   maxpool_fwd_kernel<<<ew_grid(total), NT, 0, (cudaStream_t)stream>>>(x_dev, d->n, d->h, d->w, d->c, d->p, d->q, d->r,
                                                                      d->s, d->stride_h, d->stride_w, d->pad_t,
                                                                      d->pad_l, y_dev, argmax_dev);
@@ -804,6 +819,7 @@ int pf_maxpool_bwd(const pf_conv_desc* d, const float* dy_dev, const uint8_t* ar
   PF_REQUIRE(d && dy_dev && argmax_dev && dx_dev && d->n > 0 && d->c > 0, "pf_maxpool_bwd: bad arguments");
   PF_REQUIRE((d->c & 3) == 0, "pf_maxpool_bwd: C must be a multiple of 4");
   const int64_t total = (int64_t)d->n * d->h * d->w * (d->c >> 2);
+  PF_REQUIRE(total < (1ll << 31), "pf_maxpool_bwd: tensor too large");
   maxpool_bwd_kernel<<<ew_grid(total), NT, 0, (cudaStream_t)stream>>>(dy_dev, argmax_dev, d->n, d->h, d->w, d->c,
                                                                      d->p, d->q, d->r, d->s, d->stride_h,
                                                                      d->stride_w, d->pad_t, d->pad_l, accumulate,

@@ -1,4 +1,5 @@
-"""One tcgen05 conv launch per pass for ncu (tools/gpu_prof_conv.sh)."""
+"""One launch of each tcgen05 conv kernel for ncu (tools/gpu_prof_conv.sh): operands in split-bf16 planes, as
+inside the training step.  usage: python tools/prof_conv.py s3 [s1 ...]"""
 import os
 import sys
 
@@ -8,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pocketflow_b200 import ops  # noqa: E402
 
 SHAPES = {'s3': (256, 14, 14, 256, 256, 3, 3, 1, 1), 's1': (256, 56, 56, 64, 256, 1, 1, 1, 0),
-          's2': (256, 28, 28, 128, 128, 3, 3, 1, 1)}
+          's2': (256, 28, 28, 128, 128, 3, 3, 1, 1), 's1c': (256, 56, 56, 64, 64, 3, 3, 1, 1)}
 dev = torch.device('cuda:0')
 for name in sys.argv[1:]:
     n, h, w, c, k, r, s, st, pd = SHAPES[name]
@@ -18,11 +19,16 @@ for name in sys.argv[1:]:
     wt = torch.randn(r, s, c, k, device=dev) * 0.05
     y = torch.empty(n, p, p, k, device=dev)
     dy = torch.randn(n, p, p, k, device=dev)
+    dx = torch.empty_like(x)
     dw = torch.empty_like(wt)
     tw = ops.TcWeights(d, dev)
     tw.prepare(wt)
-    ws = torch.empty(max(ops.conv2d_tc_wgrad_workspace_floats(d), 4), device=dev)
+    xp, dyp = ops.Planes(x.numel(), dev), ops.Planes(dy.numel(), dev)
+    ops.split_bf16(x, xp)
+    ops.split_bf16(dy, dyp)
+    ws = torch.empty(max(ops.conv2d_tc_wgrad_planes_workspace_floats(d), 4), device=dev)
     for _ in range(3):
-        ops.conv2d_tc_fwd(d, x, tw, None, False, y)
-        ops.conv2d_tc_wgrad(d, x, dy, ws, dw)
+        ops.conv2d_tc_fwd_planes(d, xp, tw, None, False, y)
+        ops.conv2d_tc_dgrad_planes(d, dyp, tw, False, dx)
+        ops.conv2d_tc_wgrad_planes(d, xp, dyp, ws, dw)
     torch.cuda.synchronize()
