@@ -336,8 +336,18 @@ def main():
     conv_flops = (train_pi + teacher_fwd) * B
     conv_tflops = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     step_ms_eager = sum(prof.values())
-    aq_elems = sum(op.output.numel for op in ex.aq_ops)
-    aq_ms = prof.get('act_quant', 0.0)
+    # HBM-bound companion: the BN(+ReLU)(+activation fake-quant) apply pass, 8 B per element
+    # (fp32 conv output in, split-bf16 operand planes or fp32 out); teacher + student
+    aq_elems = sum(op.output.numel for e in ([ex] + ([ex.teacher] if ex.teacher is not None else []))
+                   for op in e.ops if op.type == 'FusedBatchNorm')
+    aq_ms = prof.get('bn_apply', 0.0)
+    conv_traffic = None
+    try:
+        tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r1_ncu_conv_traffic.json')))
+        if tj.get('workload') == args.workload and B == tj.get('batch'):
+            conv_traffic = tj['conv_dram_bytes_per_step']
+    except Exception:  # noqa: BLE001
+        pass
     if rank == 0:
         value = B * world * args.steps / (ms_total * 1e-3)
         e2e_value = B * world * args.steps / (e2e_ms * 1e-3)
@@ -347,22 +357,28 @@ def main():
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': args.workload, 'description': WORKLOADS[args.workload][4],
                        'batch_per_gpu': B, 'global_batch': B * world, 'parallelism': 'dp%d' % world,
-                       'conv_path': ('tcgen05 split-bf16 (3 MMAs) fwd+dgrad where Cin,Cout %% 16 == 0 (%d of %d layers), '
-                                     'exact-fp32 CUDA-core igemm for wgrad and the rest' % (
-                                         len(ex.tc), sum(1 for o in ex.ops if o.type in ('Conv2D', 'MatMul'))))
-                       if ex.tc else 'fp32 CUDA-core implicit GEMM (pf_conv.cu)',
+                       'conv_path': ('tcgen05 split-bf16 (3 bf16 MMAs per k-slice into one fp32 TMEM accumulator = fp32-equivalent '
+                                     'product) fwd+dgrad+wgrad, persistent warp-specialised kernels fed from split-bf16 operand '
+                                     'planes: %d of %d conv/dense layers (+ the stem through im2col planes); exact-fp32 CUDA-core '
+                                     'kernels for the rest' % (len(ex.tc), sum(1 for o in ex.ops if o.type in ('Conv2D', 'MatMul'))))
+                       if ex.tc or ex.im2col else 'fp32 CUDA-core implicit GEMM (pf_conv.cu)',
                        'l2': 'per-step working set (GBs of activations) >> 126 MB L2; no explicit flush',
                        'cuda_graph': graph_ok},
             'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': int(lrn.h2d_bytes),
                     'd2h_bytes_per_step': 20, 'ms_per_step': e2e_ms / args.steps},
             'gpu_launches': int(launches_per_step * args.steps),
             'launches_per_step': int(launches_per_step),
-            'roofline': {'bound': 'tensor', 'kernel': 'conv stack: conv_tc_kernel (fwd, dgrad) + igemm_kernel (wgrad)',
+            'roofline': {'bound': 'tensor',
+                         'kernel': 'conv stack: conv_tc_persist_kernel (fwd, dgrad) + conv_tc_wgrad_persist_kernel',
                          'achieved': conv_tflops, 'peak': tf_sust, 'unit': 'TFLOP/s',
-                         'frac': conv_tflops / tf_sust, 'traffic': None, 'peak_kind': peak_kind + ' bf16 sustained',
+                         'frac': conv_tflops / tf_sust, 'traffic': conv_traffic,
+                         'traffic_note': 'DRAM bytes of the conv kernels per step, ncu launch list (profiles/); achieved '
+                                         'counts ALGORITHMIC flops (2*M*N*K per conv pass); the split-bf16 scheme issues 3x '
+                                         'that on the tensor cores, so frac <= 1/3 by construction',
+                         'peak_kind': peak_kind + ' bf16 sustained',
                          'flops_per_step': conv_flops, 'ms_per_step': conv_ms,
                          'share_of_step': conv_ms / step_ms_eager if step_ms_eager else None},
-            'roofline_hbm': {'bound': 'hbm', 'kernel': 'uq_act_quant_kernel (activation fake-quant, in place)',
+            'roofline_hbm': {'bound': 'hbm', 'kernel': 'bn_apply_kernel (BN + ReLU + activation fake-quant -> operand planes)',
                              'achieved': (8.0 * aq_elems / (aq_ms * 1e-3) / 1e9) if aq_ms > 0 else None,
                              'peak': hbm_peak, 'unit': 'GB/s',
                              'frac': (8.0 * aq_elems / (aq_ms * 1e-3) / 1e9 / hbm_peak) if aq_ms > 0 else None,

@@ -343,26 +343,11 @@ conv_tc_persist_kernel(const float* __restrict__ src, const __nv_bfloat16* __res
       mbar_arrive(&full_bar[s]);
       ++it;
     };
-    // the epilogue's extra operand (residual / accumulated dx) of a tile is requested into L2 when the tile's main
-    // loop starts, a tile ahead of the epilogue warps that will read it
-    const float* extra_pf = residual ? residual : (p.accumulate ? out : nullptr);
-    auto prefetch_extra = [&](int tile) {
-      if (MODE == 2 || extra_pf == nullptr) return;
-      const int mt = (int)fdiv((uint32_t)tile, p.d_ntiles);
-      const int n0 = (tile - mt * p.n_tiles) * BN;
-      const int m = mt * TM + (pt_ >> 1);
-      if (m >= p.M) return;
-      const int cols = min(BN, p.Ng - n0);
-      const char* row = reinterpret_cast<const char*>(extra_pf + (size_t)m * p.Ng + n0);
-      for (int b = (pt_ & 1) * 128; b < cols * 4; b += 256)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(row + b));
-    };
     if (PLANES) {
       // pre-split operand: both tiles are plain cp.async copies; the stage's barrier arrival fires when this
       // thread's copies have landed, so the producers only ever wait for a free slot
       for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
         const int nkt = tile_nk(tile);
-        prefetch_extra(tile);
         for (int ks = 0; ks < nkt; ++ks, ++it) {
           const uint32_t s = it % (uint32_t)p.n_stages;
           mbar_wait(&empty_bar[s], ((it / (uint32_t)p.n_stages) & 1u) ^ 1u);
@@ -403,14 +388,12 @@ conv_tc_persist_kernel(const float* __restrict__ src, const __nv_bfloat16* __res
         advance(t1, k1, nk1);
         const bool v1 = t1 < p.total_tiles;
         if (v1) issue_loads_a(t1, k1, a1);
-        if (k0 == 0) prefetch_extra(t0);
         do_stage(t0, k0, t0 == first_tile, a0);
         if (!v1) break;
         int t2 = t1, k2 = k1, nk2 = nk1;
         advance(t2, k2, nk2);
         const bool v2 = t2 < p.total_tiles;
         if (v2) issue_loads_a(t2, k2, a0);
-        if (k1 == 0) prefetch_extra(t1);
         do_stage(t1, k1, t1 == first_tile, a1);
         if (!v2) break;
         t0 = t2; k0 = k2; nk0 = nk2;

@@ -135,6 +135,16 @@ class Executor:
             self.store.listeners.append(self._invalidate_static)
         self.weight_quant, self.act_quant = weight_quant, act_quant
         self.prof = None
+        # multi-stream overlap inside one step (captured into the CUDA graph as parallel branches): the teacher's
+        # forward runs beside the student's, and the weight-gradient kernels run beside dgrad + BN-backward, so that
+        # tensor-bound and HBM-bound kernels share the GPU (a BN kernel's CTAs fit next to a persistent conv CTA)
+        self.overlap = _os.environ.get('PF_OVERLAP', '1') != '0' and device.type == 'cuda'
+        self.side = torch.cuda.Stream(device=device) if self.overlap else None
+        self.side2 = torch.cuda.Stream(device=device) if self.overlap else None
+        self._shares_cols = False
+        self._side_active = False
+        self.cols_event = None          # recorded after this executor's im2col (shared columns)
+        self.cols_wait = None           # event to wait for before reading shared columns
         self._plan()
         self._graph = None
         self.step_count = 0
@@ -347,6 +357,7 @@ class Executor:
             self.hp = torch.zeros(4, dtype=torch.float32, device=dev)
             self.hp_host = torch.zeros(4, dtype=torch.float32).pin_memory() if dev.type == 'cuda' else torch.zeros(4)
             self.wgrad_ws = E((max_ws,))
+            self.wgrad_ws2 = E((max_ws,)) if self.overlap else None
             self.wt_ws = E((max_wt,))
             self.l2_out = torch.zeros(4, dtype=torch.float32, device=dev)
             self.l2_ws = E((ops.L2_PARTIALS,))
@@ -571,6 +582,10 @@ class Executor:
                                 ops.im2col_planes(self.desc[op], self.T(op.inputs[0]), im['kpad'], im['cols'])
                             else:
                                 ops.im2col(self.desc[op], self.T(op.inputs[0]), im['kpad'], im['cols'])
+                            if self.cols_event is not None:
+                                self.cols_event.record()
+                        elif self.cols_wait is not None:
+                            torch.cuda.current_stream().wait_event(self.cols_wait)
                         if not self.static_weights:
                             ops.add(wk.reshape(-1), None, im['wpad'][:wk.numel()])       # rows >= R*S*C stay zero
                             im['tw'].prepare(im['wpad'])
@@ -616,19 +631,23 @@ class Executor:
                 # with an activation quantizer the BN pass writes fp32 (+ range) and the quantizer writes the planes
                 pl_bn = pl if slot is None else None
                 y_bn = y if (need_f32 or slot is not None) else None
-                with self.timed('bn_fwd'):
-                    if op.attrs['training'] and training and slot is not None:
-                        # the statistics pass also yields the range of act(bn(x)); one fused BN + fake-quant pass
+                if op.attrs['training'] and training and slot is not None:
+                    # the statistics pass also yields the range of act(bn(x)); one fused BN + fake-quant pass
+                    with self.timed('bn_stats'):
                         ops.bn_train_stats_range(x, m, c, op.attrs['epsilon'], op.attrs['momentum'], b['mean'], b['var'],
                                                  b['rstd'], mm, mv, gamma, beta, act, slot, self.bn_ws)
+                    with self.timed('bn_apply'):
                         ops.bn_apply_quant(x, m, c, b['mean'], b['rstd'], gamma, beta, act, slot,
                                            self.act_quant['bits'][self.aq_index[relu_op]], y if need_f32 else None, pl)
-                        slot = None                                    # quantized already
-                    elif op.attrs['training'] and training:
+                    slot = None                                    # quantized already
+                elif op.attrs['training'] and training:
+                    with self.timed('bn_stats'):
                         ops.bn_train_stats(x, m, c, op.attrs['epsilon'], op.attrs['momentum'], b['mean'], b['var'],
                                            b['rstd'], mm, mv, self.bn_ws)
+                    with self.timed('bn_apply'):
                         ops.bn_apply(x, m, c, b['mean'], b['rstd'], gamma, beta, act, y_bn, slot, pl_bn)
-                    else:
+                else:
+                    with self.timed('bn_apply'):
                         ops.bn_eval_prepare(mv, c, op.attrs['epsilon'], b['rstd'])
                         ops.bn_apply(x, m, c, mm, b['rstd'], gamma, beta, act, y_bn, slot, pl_bn)
                 if slot is not None:
@@ -666,6 +685,7 @@ class Executor:
         st = self.store
         L = self.loss
         self._gwritten = set()
+        self._side_active = self.overlap and self.prof is None
         labels = self.T(self.labels_t)
         ce_logits = L.ce[1]
         teacher_logits, w_dst, T_dst = None, 0.0, 1.0
@@ -708,6 +728,15 @@ class Executor:
                         else:
                             ops.conv2d_wgrad(im['d1'], im['cols'], gy, self.wgrad_ws, im['dwpad'])
                         ops.add(im['dwpad'][:gk.numel()], None, gk.reshape(-1))
+                    elif op in self.tc_wgrad and self._side_active and self.planes_of(x_t) is not None \
+                            and self.conv_dy_planes.get(op) is not None:
+                        # both operands exist as planes: the weight gradient runs on the side stream, beside the
+                        # dgrad / BN-backward chain that continues on the main stream
+                        gp = self.conv_dy_planes[op]
+                        self.side2.wait_stream(torch.cuda.current_stream())
+                        with torch.cuda.stream(self.side2):
+                            ops.conv2d_tc_wgrad_planes(d, self.planes_of(x_t), gp, self.wgrad_ws2,
+                                                       st.view(op.vars['kernel'], self.G))
                     elif op in self.tc_wgrad:
                         # operands in split-bf16 planes: native (written by BN-apply / BN-backward) or split here
                         xp = self.planes_of(x_t)
@@ -779,6 +808,8 @@ class Executor:
                 ops.softmax_bwd(gy, self.buf[op.output], gx)
             else:
                 raise NotImplementedError('backward of %s' % ty)
+        if self._side_active:
+            torch.cuda.current_stream().wait_stream(self.side2)
         if self._ste_grads is not None:
             self.wq.ste_backward_(self._ste_grads)
 
@@ -828,13 +859,26 @@ class Executor:
                         and all(op.attrs[a] == op2.attrs[a] for a in ('ksize', 'strides', 'pad')):
                     im['cols'] = im2['cols']
                     im['compute'] = False
+                    self._shares_cols = True
 
     # ------------------------------------------------------------------ one training step
     def device_step(self, allreduce=None):
         """Everything that runs on the GPU for one step (CUDA-graph capturable)."""
-        if self.teacher is not None:
-            self.teacher.forward()
-        self.forward()
+        par = self.overlap and self.prof is None and self.teacher is not None
+        if par:
+            main = torch.cuda.current_stream()
+            self.side.wait_stream(main)
+            if self._shares_cols:
+                self.teacher.cols_event = self.cols_wait = torch.cuda.Event()
+            with torch.cuda.stream(self.side):
+                self.teacher.forward()
+            self.forward()
+            main.wait_stream(self.side)
+            self.teacher.cols_event = self.cols_wait = None
+        else:
+            if self.teacher is not None:
+                self.teacher.forward()
+            self.forward()
         self.loss_and_backward()
         if allreduce is not None:
             with self.timed('allreduce'):

@@ -70,7 +70,8 @@ def main():
             xp, dyp = ops.Planes(x.numel(), dev), ops.Planes(dy.numel(), dev)
             ops.split_bf16(x, xp)
             ops.split_bf16(dy, dyp)
-            fns = dict(fwd=lambda: ops.conv2d_tc_fwd_planes(d, xp, tw, None, False, y),
+            resid = torch.randn_like(y) if os.environ.get('RESIDUAL', '0') == '1' else None
+            fns = dict(fwd=lambda: ops.conv2d_tc_fwd_planes(d, xp, tw, None, False, y, resid),
                        dgrad=lambda: ops.conv2d_tc_dgrad_planes(d, dyp, tw, False, dx),
                        wgrad=lambda: ops.conv2d_tc_wgrad_planes(d, xp, dyp, ws, dw))
         line = '%-22s' % name

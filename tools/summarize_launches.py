@@ -50,6 +50,16 @@ def main():
         out.append('  %-44s grid %-18s %9.1f us  rd %7.1f MB  wr %7.1f MB' % (
             short(r['name'])[:44], r['grid'], r.get('us', 0.0), r.get('dram__bytes_read.sum', 0) / 1e6,
             r.get('dram__bytes_write.sum', 0) / 1e6))
+    conv = [a for k, a in agg.items() if 'conv_tc' in k or 'tc_splitk' in k or 'tc_prep' in k or 'im2col' in k or 'split_bf16' in k]
+    conv_bytes = sum(a['rd'] + a['wr'] for a in conv)
+    out.append('')
+    out.append('conv stack (conv_tc_* + prep/split/reduce helpers): %.3f ms, %.2f GB DRAM traffic per step' % (
+        sum(a['us'] for a in conv) / 1e3, conv_bytes / 1e9))
+    if len(sys.argv) > 3:
+        import json
+        json.dump({'workload': 'resnet50_uq8_dst_b256', 'batch': 256, 'conv_dram_bytes_per_step': conv_bytes,
+                   'conv_serialised_ms': sum(a['us'] for a in conv) / 1e3,
+                   'source': 'ncu launch list (tools/gpu_launchlist.sh), one training step'}, open(sys.argv[3], 'w'))
     text = '\n'.join(out)
     print(text)
     if len(sys.argv) > 2:
