@@ -264,6 +264,19 @@ int pf_conv2d_tc_fwd(const pf_conv_desc* d, const float* x_dev, const void* w_hi
                      const float* bias_dev, int relu, const float* residual_dev, float* y_dev, void* stream);
 int pf_conv2d_tc_dgrad(const pf_conv_desc* d, const float* dy_dev, const void* wd_hi_dev, const void* wd_lo_dev,
                        int accumulate, float* dx_dev, void* stream);
+/* multi-tensor weight preparation: every conv kernel of a network in ONE launch.  segs: one entry per kernel
+ * (kpad = pf_conv2d_tc_weight_elems / rows; dgrad pointers may be NULL), work: kind-0 chunks of the weights. */
+typedef struct pf_tc_prep_seg {
+  const float* w;          /* HWIO fp32 */
+  void* fwd_hi;
+  void* fwd_lo;
+  void* dgrad_hi;
+  void* dgrad_lo;
+  int32_t rs, c, k;        /* R*S, Cin, Cout */
+  int32_t kpad_f, kpad_d;  /* row pitches of the fwd / dgrad copies (multiples of 64) */
+  int32_t reserved;
+} pf_tc_prep_seg;
+int pf_conv2d_tc_prep_weights_multi(const pf_tc_prep_seg* segs_dev, const pf_work* work_dev, int n_work, void* stream);
 /* dw = x (*) dy on the tensor cores (MN-major operands, split-K with a fixed-order reduction).
  * Requires Cin % 16 == 0 and Cout % 64 == 0; ws_dev: pf_conv2d_tc_wgrad_workspace_bytes(d) bytes. */
 #define PF_CONV_TC_WGRAD_MAX_SPLITS 64
@@ -283,6 +296,17 @@ int pf_conv2d_tc_fwd_planes(const pf_conv_desc* d, const void* x_hi_dev, const v
                             float* y_dev, void* stream);
 int pf_conv2d_tc_dgrad_planes(const pf_conv_desc* d, const void* dy_hi_dev, const void* dy_lo_dev, const void* wd_hi_dev,
                               const void* wd_lo_dev, int accumulate, float* dx_dev, void* stream);
+/* dw_dev == NULL: leave the split-K partials [splits][R*S*Cin][Cout] in ws_dev (pf_conv2d_tc_wgrad_splits(d) of
+ * them) for ONE deferred pf_conv2d_tc_wgrad_reduce_multi over every layer of the step */
+typedef struct pf_tc_reduce_seg {
+  const float* partial;    /* [splits][n] */
+  float* out;              /* [n] */
+  int64_t n;               /* multiple of 4 */
+  int32_t splits;
+  int32_t reserved;
+} pf_tc_reduce_seg;
+int pf_conv2d_tc_wgrad_splits(const pf_conv_desc* d);
+int pf_conv2d_tc_wgrad_reduce_multi(const pf_tc_reduce_seg* segs_dev, const pf_work* work_dev, int n_work, void* stream);
 int pf_conv2d_tc_wgrad_planes(const pf_conv_desc* d, const void* x_hi_dev, const void* x_lo_dev, const void* dy_hi_dev,
                               const void* dy_lo_dev, float* ws_dev, float* dw_dev, void* stream);
 /* hardware probe used by tests/test_tc_gpu.py to pin the descriptor conventions (not a product op) */

@@ -695,6 +695,36 @@ tc_prep_weight_kernel(const float* __restrict__ w, int RS, int C, int K, int kpa
   }
 }
 
+// multi-tensor form: one launch prepares every conv kernel of a network (53 launches of 10-15 us each in the
+// ResNet-50 step otherwise); work items are flat chunks of the weight tensors (kind-0 pf_work)
+__global__ void __launch_bounds__(256)
+tc_prep_weights_multi_kernel(const pf_tc_prep_seg* __restrict__ segs, const pf_work* __restrict__ work) {
+  const pf_work wk = work[blockIdx.x];
+  const pf_tc_prep_seg sg = segs[wk.seg];
+  const int C = sg.c, K = sg.k;
+  __nv_bfloat16* f_hi = (__nv_bfloat16*)sg.fwd_hi;
+  __nv_bfloat16* f_lo = (__nv_bfloat16*)sg.fwd_lo;
+  __nv_bfloat16* d_hi = (__nv_bfloat16*)sg.dgrad_hi;
+  __nv_bfloat16* d_lo = (__nv_bfloat16*)sg.dgrad_lo;
+  for (int64_t i = wk.start + threadIdx.x; i < wk.start + wk.count; i += 256) {
+    const int co = (int)(i % K);
+    const int64_t t = i / K;
+    const int c = (int)(t % C);
+    const int rs = (int)(t / C);
+    const float v = __ldg(sg.w + i);
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    const size_t fo = (size_t)co * sg.kpad_f + (size_t)rs * C + c;
+    f_hi[fo] = h;
+    f_lo[fo] = l;
+    if (d_hi) {
+      const size_t dof = (size_t)c * sg.kpad_d + (size_t)rs * K + co;
+      d_hi[dof] = h;
+      d_lo[dof] = l;
+    }
+  }
+}
+
 int tc_geom(const pf_conv_desc* d, TcGeom* g, const char* who) {
   PF_REQUIRE(d != nullptr, "%s: null descriptor", who);
   PF_REQUIRE(d->n > 0 && d->h > 0 && d->w > 0 && d->c > 0 && d->k > 0 && d->r > 0 && d->s > 0 && d->p > 0 &&
@@ -839,6 +869,21 @@ int launch_tc(const TcGeom& g, const float* src, const void* a_hi, const void* a
   return launch_persist<MODE>(g, p, src, a_hi, a_lo, b_hi, b_lo, out, bias, residual, st, who);
 }
 
+// multi-tensor split-K reduction: the partials of every wgrad of a step in ONE launch (kind-0 work items)
+__global__ void __launch_bounds__(256)
+tc_splitk_reduce_multi_kernel(const pf_tc_reduce_seg* __restrict__ segs, const pf_work* __restrict__ work) {
+  const pf_work wk = work[blockIdx.x];
+  const pf_tc_reduce_seg sg = segs[wk.seg];
+  for (int64_t i = wk.start + (int64_t)threadIdx.x * 4; i < wk.start + wk.count; i += 1024) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int z = 0; z < sg.splits; ++z) {
+      const float4 v = *reinterpret_cast<const float4*>(sg.partial + (size_t)z * sg.n + i);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    *reinterpret_cast<float4*>(sg.out + i) = a;
+  }
+}
+
 inline int64_t wg_align(int64_t b) { return (b + 255) / 256 * 256; }
 
 // tile width, split-K factor and stage count of the persistent wgrad
@@ -909,6 +954,15 @@ int pf_conv2d_tc_prep_weight(const pf_conv_desc* d, const float* w_dev, void* fw
                                                          (__nv_bfloat16*)fwd_hi_dev, (__nv_bfloat16*)fwd_lo_dev,
                                                          (__nv_bfloat16*)dgrad_hi_dev, (__nv_bfloat16*)dgrad_lo_dev);
   PF_CHECK_LAUNCH("pf_conv2d_tc_prep_weight");
+  return PF_OK;
+}
+
+int pf_conv2d_tc_prep_weights_multi(const pf_tc_prep_seg* segs_dev, const pf_work* work_dev, int n_work, void* stream) {
+  PF_REQUIRE(n_work >= 0, "pf_conv2d_tc_prep_weights_multi: n_work < 0");
+  if (n_work == 0) return PF_OK;
+  PF_REQUIRE(segs_dev && work_dev, "pf_conv2d_tc_prep_weights_multi: null pointer");
+  tc_prep_weights_multi_kernel<<<(unsigned)n_work, 256, 0, (cudaStream_t)stream>>>(segs_dev, work_dev);
+  PF_CHECK_LAUNCH("pf_conv2d_tc_prep_weights_multi");
   return PF_OK;
 }
 
@@ -992,6 +1046,23 @@ int64_t pf_conv2d_tc_wgrad_planes_workspace_bytes(const pf_conv_desc* d) {
   return (int64_t)p.splits * p.Mtot * g.K * 4;
 }
 
+int pf_conv2d_tc_wgrad_splits(const pf_conv_desc* d) {
+  TcGeom g;
+  if (!d || tc_geom(d, &g, "pf_conv2d_tc_wgrad_splits")) return 0;
+  WgP p;
+  wgrad_plan(g, &p);
+  return p.splits;
+}
+
+int pf_conv2d_tc_wgrad_reduce_multi(const pf_tc_reduce_seg* segs_dev, const pf_work* work_dev, int n_work, void* stream) {
+  PF_REQUIRE(n_work >= 0, "pf_conv2d_tc_wgrad_reduce_multi: n_work < 0");
+  if (n_work == 0) return PF_OK;
+  PF_REQUIRE(segs_dev && work_dev, "pf_conv2d_tc_wgrad_reduce_multi: null pointer");
+  tc_splitk_reduce_multi_kernel<<<(unsigned)n_work, 256, 0, (cudaStream_t)stream>>>(segs_dev, work_dev);
+  PF_CHECK_LAUNCH("pf_conv2d_tc_wgrad_reduce_multi");
+  return PF_OK;
+}
+
 int pf_split_bf16(const float* src_dev, void* hi_dev, void* lo_dev, int64_t n, void* stream) {
   PF_REQUIRE(n >= 0 && n % 8 == 0, "pf_split_bf16: n must be a non-negative multiple of 8");
   if (n == 0) return PF_OK;
@@ -1010,7 +1081,7 @@ int pf_conv2d_tc_wgrad_planes(const pf_conv_desc* d, const void* x_hi_dev, const
   int rc = tc_geom(d, &g, "pf_conv2d_tc_wgrad_planes");
   if (rc) return rc;
   PF_REQUIRE(pf_conv2d_tc_wgrad_supported(d), "pf_conv2d_tc_wgrad_planes: needs Cin %% 16 == 0 and Cout %% 64 == 0");
-  PF_REQUIRE(x_hi_dev && x_lo_dev && dy_hi_dev && dy_lo_dev && ws_dev && dw_dev, "pf_conv2d_tc_wgrad_planes: null pointer");
+  PF_REQUIRE(x_hi_dev && x_lo_dev && dy_hi_dev && dy_lo_dev && ws_dev, "pf_conv2d_tc_wgrad_planes: null pointer");
   PF_REQUIRE((((uintptr_t)x_hi_dev | (uintptr_t)x_lo_dev | (uintptr_t)dy_hi_dev | (uintptr_t)dy_lo_dev | (uintptr_t)ws_dev |
                (uintptr_t)dw_dev) & 15) == 0, "pf_conv2d_tc_wgrad_planes: 16-byte alignment required");
   PF_REQUIRE((int64_t)g.N * g.P * g.Q < (1ll << 31), "pf_conv2d_tc_wgrad_planes: too many pixels");
@@ -1023,9 +1094,9 @@ int pf_conv2d_tc_wgrad_planes(const pf_conv_desc* d, const void* x_hi_dev, const
   const int grid = std::min(p.total_units, PF_NUM_SMS);
   conv_tc_wgrad_persist_kernel<<<grid, kThreadsP, smem, st>>>(
       (const __nv_bfloat16*)x_hi_dev, (const __nv_bfloat16*)x_lo_dev, (const __nv_bfloat16*)dy_hi_dev,
-      (const __nv_bfloat16*)dy_lo_dev, p.splits == 1 ? dw_dev : ws_dev, p);
+      (const __nv_bfloat16*)dy_lo_dev, (p.splits == 1 && dw_dev) ? dw_dev : ws_dev, p);
   PF_CHECK_LAUNCH("pf_conv2d_tc_wgrad_planes");
-  if (p.splits > 1) {
+  if (p.splits > 1 && dw_dev) {
     const int64_t n = (int64_t)p.Mtot * g.K;
     tc_splitk_reduce_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(ws_dev, dw_dev, n, p.splits);
     PF_CHECK_LAUNCH("pf_conv2d_tc_wgrad_planes/reduce");

@@ -343,6 +343,10 @@ class Executor:
                         continue
                     if not (c in self.tc and c not in self.im2col and (not self.train or c in self.tc_wgrad)):
                         self.bn_need_f32[bn_op] = True
+        # one launch refreshes the split-bf16 copies of all (trainable) conv kernels
+        self.tc_batch = None
+        if self.tc and not self.static_weights:
+            self.tc_batch = ops.TcWeightsBatch([(self.tc[op], self.kernel_of(op)) for op in self.ops if op in self.tc], dev)
         if self.labels_t is not None and self.labels_t not in self.buf:
             self.buf[self.labels_t] = torch.zeros(self.labels_t.shape, dtype=torch.float32, device=dev)
         self.bn_ws = E((max_bnws,))
@@ -450,6 +454,17 @@ class Executor:
                     self.bn_gplanes[lw] = ops.Planes(op.output.numel, dev,
                                                      self.gbuf[k].view(-1).view(torch.bfloat16) if only else None)
                 self.conv_dy_planes[op] = self.bn_gplanes[lw]
+            # split-K partials of every tensor-core wgrad get their own buffer; ONE reduction launch at the end of the
+            # backward pass sums them into the flat gradient buffer (fixed order: deterministic)
+            self.wg_part, red_items = {}, []
+            for op in self.ops:
+                if op in self.tc_wgrad:
+                    splits = ops.conv2d_tc_wgrad_splits(self.desc[op])
+                    if splits > 1:
+                        gk = st.view(op.vars['kernel'], self.G)
+                        self.wg_part[op] = E((splits * gk.numel(),))
+                        red_items.append((self.wg_part[op], gk, splits))
+            self.wg_reduce = ops.TcWgradReduceBatch(red_items, dev) if red_items else None
             max_dy = max(max_dy, getattr(self, '_stem_dy', 8))
             self.x_scratch = ops.Planes(max_x, dev)
             self.dy_scratch = ops.Planes(max_dy, dev)
@@ -567,6 +582,9 @@ class Executor:
                 self.wq.forward()
         if self.static_weights and not self._static_ready:
             self.prepare_static_weights()
+        if self.tc_batch is not None:
+            with self.timed('conv_prep'):
+                self.tc_batch.prepare()
         for op in self.ops:
             ty = op.type
             if ty in ('Placeholder', 'Reshape', 'Identity'):
@@ -597,7 +615,7 @@ class Executor:
                             ops.conv2d_tc_fwd(im['d1'], im['cols'], im['tw'], bias, op in self.fused_act,
                                               self.buf[op.output])
                 elif op in self.tc:
-                    if not self.static_weights:
+                    if not self.static_weights and self.tc_batch is None:
                         with self.timed('conv_prep'):
                             self.tc[op].prepare(self.kernel_of(op))
                     res = self.T(self.fused_add[op][1]) if op in self.fused_add else None
@@ -735,8 +753,11 @@ class Executor:
                         gp = self.conv_dy_planes[op]
                         self.side2.wait_stream(torch.cuda.current_stream())
                         with torch.cuda.stream(self.side2):
-                            ops.conv2d_tc_wgrad_planes(d, self.planes_of(x_t), gp, self.wgrad_ws2,
-                                                       st.view(op.vars['kernel'], self.G))
+                            if op in self.wg_part:
+                                ops.conv2d_tc_wgrad_planes(d, self.planes_of(x_t), gp, self.wg_part[op], None)
+                            else:
+                                ops.conv2d_tc_wgrad_planes(d, self.planes_of(x_t), gp, self.wgrad_ws2,
+                                                           st.view(op.vars['kernel'], self.G))
                     elif op in self.tc_wgrad:
                         # operands in split-bf16 planes: native (written by BN-apply / BN-backward) or split here
                         xp = self.planes_of(x_t)
@@ -747,7 +768,10 @@ class Executor:
                         if gp is None:
                             gp = ops.Planes(op.output.numel, self.device, self.dy_scratch.buf)
                             ops.split_bf16(gy, gp)
-                        ops.conv2d_tc_wgrad_planes(d, xp, gp, self.wgrad_ws, st.view(op.vars['kernel'], self.G))
+                        if op in self.wg_part:
+                            ops.conv2d_tc_wgrad_planes(d, xp, gp, self.wg_part[op], None)
+                        else:
+                            ops.conv2d_tc_wgrad_planes(d, xp, gp, self.wgrad_ws, st.view(op.vars['kernel'], self.G))
                     else:
                         gp = None
                         ops.conv2d_wgrad(d, self.T(x_t), gy, self.wgrad_ws, st.view(op.vars['kernel'], self.G))
@@ -810,6 +834,9 @@ class Executor:
                 raise NotImplementedError('backward of %s' % ty)
         if self._side_active:
             torch.cuda.current_stream().wait_stream(self.side2)
+        if self.wg_reduce is not None:
+            with self.timed('conv_wgrad'):
+                self.wg_reduce.reduce()
         if self._ste_grads is not None:
             self.wq.ste_backward_(self._ste_grads)
 

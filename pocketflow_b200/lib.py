@@ -49,6 +49,9 @@ SIGNATURES = {
     'pf_conv2d_tc_wgrad_supported': (c_i32, [c_vp]),
     'pf_conv2d_tc_wgrad_workspace_bytes': (c_i64, [c_vp]),
     'pf_conv2d_tc_wgrad': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'pf_conv2d_tc_prep_weights_multi': (c_i32, [c_vp, c_vp, c_i32, c_vp]),
+    'pf_conv2d_tc_wgrad_splits': (c_i32, [c_vp]),
+    'pf_conv2d_tc_wgrad_reduce_multi': (c_i32, [c_vp, c_vp, c_i32, c_vp]),
     'pf_split_bf16': (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     'pf_conv2d_tc_wgrad_planes_workspace_bytes': (c_i64, [c_vp]),
     'pf_conv2d_tc_fwd_planes': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]),

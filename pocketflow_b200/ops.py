@@ -563,6 +563,34 @@ class TcWeights:
                    'pf_conv2d_tc_prep_weight')
 
 
+TC_PREP_SEG = np.dtype([('w', np.uint64), ('fwd_hi', np.uint64), ('fwd_lo', np.uint64), ('dgrad_hi', np.uint64),
+                        ('dgrad_lo', np.uint64), ('rs', np.int32), ('c', np.int32), ('k', np.int32),
+                        ('kpad_f', np.int32), ('kpad_d', np.int32), ('reserved', np.int32)], align=True)
+
+
+class TcWeightsBatch:
+    """One launch that refreshes the split-bf16 copies of MANY conv kernels (pf_conv2d_tc_prep_weights_multi)."""
+
+    def __init__(self, items, device):
+        """items: list of (TcWeights, fp32 HWIO weight tensor [R,S,C,K])."""
+        segs = np.zeros(len(items), dtype=TC_PREP_SEG)
+        numels = []
+        for i, (tw, w) in enumerate(items):
+            r, s_, c, k = w.shape if w.dim() == 4 else (1, 1) + tuple(w.shape)
+            segs[i] = (w.data_ptr(), tw.f_hi.data_ptr(), tw.f_lo.data_ptr(),
+                       tw.d_hi.data_ptr() if tw.d_hi is not None else 0, tw.d_lo.data_ptr() if tw.d_lo is not None else 0,
+                       r * s_, c, k, tw.f_hi.numel() // k, (tw.d_hi.numel() // c) if tw.d_hi is not None else 0, 0)
+            numels.append(w.numel())
+        self.keep = items
+        self.work = flat_works(numels, 1 << 15)
+        self.segs_dev = torch.from_numpy(segs.view(np.uint8)).to(device)
+        self.work_dev = torch.from_numpy(self.work.view(np.uint8)).to(device)
+
+    def prepare(self):
+        _lib.check(_lib.load().pf_conv2d_tc_prep_weights_multi(_p(self.segs_dev), _p(self.work_dev), len(self.work),
+                                                               _stream()), 'pf_conv2d_tc_prep_weights_multi')
+
+
 def conv2d_tc_fwd(d, x, tw, bias, relu, y, residual=None):
     _lib.check(_lib.load().pf_conv2d_tc_fwd(ctypes.byref(d), _p(x), _p(tw.f_hi), _p(tw.f_lo), _p(bias),
                                             int(bool(relu)), _p(residual), _p(y), _stream()), 'pf_conv2d_tc_fwd')
@@ -617,6 +645,32 @@ def conv2d_tc_dgrad_planes(d, dyp, tw, accumulate, dx):
 
 def conv2d_tc_wgrad_planes_workspace_floats(d):
     return int(_lib.load().pf_conv2d_tc_wgrad_planes_workspace_bytes(ctypes.byref(d))) // 4
+
+
+TC_REDUCE_SEG = np.dtype([('partial', np.uint64), ('out', np.uint64), ('n', np.int64), ('splits', np.int32),
+                          ('reserved', np.int32)], align=True)
+
+
+def conv2d_tc_wgrad_splits(d):
+    return int(_lib.load().pf_conv2d_tc_wgrad_splits(ctypes.byref(d)))
+
+
+class TcWgradReduceBatch:
+    """Deferred split-K reduction of many weight gradients in one launch."""
+
+    def __init__(self, items, device):
+        """items: list of (partials tensor [splits*n], out tensor [n], splits)."""
+        segs = np.zeros(len(items), dtype=TC_REDUCE_SEG)
+        for i, (part, out, splits) in enumerate(items):
+            segs[i] = (part.data_ptr(), out.data_ptr(), out.numel(), splits, 0)
+        self.keep = items
+        self.work = flat_works([o.numel() for _, o, _ in items], 1 << 14)
+        self.segs_dev = torch.from_numpy(segs.view(np.uint8)).to(device)
+        self.work_dev = torch.from_numpy(self.work.view(np.uint8)).to(device)
+
+    def reduce(self):
+        _lib.check(_lib.load().pf_conv2d_tc_wgrad_reduce_multi(_p(self.segs_dev), _p(self.work_dev), len(self.work),
+                                                               _stream()), 'pf_conv2d_tc_wgrad_reduce_multi')
 
 
 def conv2d_tc_wgrad_planes(d, xp, dyp, ws, dw):
