@@ -73,7 +73,7 @@ struct TcClass {
 struct TcP {
   TcGeom g;
   int M, Ng, Kdim, Kpad, BN, nk, n_stages, n_bslots, b_stationary, m_tiles, n_tiles, total_tiles, acc_cols;
-  int accumulate, relu, ncls, cblocks;
+  int accumulate, relu, ncls, cblocks, ring;
   FastDiv d_hw, d_w, d_cc, d_s, d_ntiles, d_cblocks;
   TcClass cls[kMaxClasses];
 };
@@ -87,12 +87,18 @@ constexpr int kStagePitch = 36;                                // floats per sta
 // TMEM -> registers (thread = row, 32 columns) -> per-warp smem transpose -> 128-byte row segments to global.
 // `extra` (residual / accumulate operand, same indexing as `out`) is prefetched one 32-column chunk ahead,
 // and the first chunk is requested BEFORE waiting for the accumulator, so its latency hides behind the main loop.
-template <bool EXTRA>
+// EXTRA: 0 = none; 1 = extra operand prefetched one chunk ahead in registers; 2 = extra operand streamed through a
+// per-warp cp.async ring in shared memory, kRingDepth chunks (4 KB each) in flight per warp.  The output-heavy
+// layers (1x1 64->256 + residual: 128 KB out + 128 KB residual per tile, one k-stage of MMAs) are bound by how many
+// bytes of the extra operand are in flight; registers allow 8 KB per warp, the ring 16 KB.
+constexpr int kRingDepth = 4;
+constexpr int kRingSlotBytes = 32 * 32 * 4;
+template <int EXTRA>
 __device__ __forceinline__ void epilogue_tile_t(uint32_t t_acc, uint64_t* tfull, uint64_t* tempty, uint32_t parity,
                                                 bool zero_tile, long long my_row_off, long long* __restrict__ rowoff,
                                                 float* __restrict__ stg, float* __restrict__ out,
                                                 const float* __restrict__ extra, const float* __restrict__ bias,
-                                                int relu, int n0, int BN, int Ng, int warp, int lane) {
+                                                int relu, int n0, int BN, int Ng, int warp, int lane, uint8_t* ring) {
   rowoff[lane] = my_row_off;
   __syncwarp();
   const int csub = (lane & 7) * 4, rsub = lane >> 3;
@@ -110,8 +116,30 @@ __device__ __forceinline__ void epilogue_tile_t(uint32_t t_acc, uint64_t* tfull,
       xv[u] = (cok && ro[u] >= 0) ? *reinterpret_cast<const float4*>(extra + ((size_t)ro[u] << 2) + n0 + cv)
                                   : make_float4(0.f, 0.f, 0.f, 0.f);
   };
-  float4 xa[8], xb[8];                           // dead (eliminated) when !EXTRA
-  if (EXTRA) load_extra(0, xa);
+  // ring: every lane copies exactly the 16-byte pieces it will read back itself (no cross-lane hand-off); one
+  // commit group per chunk, empty groups past the end keep the wait_group count uniform
+  const uint32_t ring_u32 = (EXTRA == 2) ? smem_u32(ring) : 0u;
+  auto ring_issue = [&](int c0) {
+    if (c0 < BN) {
+      const int cv = c0 + csub;
+      const bool cok = cv < BN && n0 + cv + 3 < Ng;
+      const uint32_t slot = ring_u32 + (uint32_t)((c0 >> 5) & (kRingDepth - 1)) * kRingSlotBytes;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const bool ok = cok && ro[u] >= 0;
+        const float* src = ok ? extra + ((size_t)ro[u] << 2) + n0 + cv : extra;
+        const uint32_t dst = slot + (uint32_t)(((4 * u + rsub) * 32 + csub) * 4);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16u : 0u) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  float4 xa[8], xb[8];                           // dead (eliminated) unless EXTRA == 1
+  if (EXTRA == 1) load_extra(0, xa);
+  if (EXTRA == 2) {
+#pragma unroll
+    for (int c = 0; c < kRingDepth; ++c) ring_issue(32 * c);
+  }
   mbar_wait(tfull, parity);
   tc_fence_after();
   const uint32_t t_addr = t_acc + (((uint32_t)(warp * 32)) << 16);
@@ -131,7 +159,9 @@ __device__ __forceinline__ void epilogue_tile_t(uint32_t t_acc, uint64_t* tfull,
     for (int j = 0; j < 32; j += 4)
       *reinterpret_cast<uint4*>(stg + lane * kStagePitch + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
     __syncwarp();
-    if (EXTRA && c0 + 32 < BN) load_extra(c0 + 32, xb);
+    if (EXTRA == 1 && c0 + 32 < BN) load_extra(c0 + 32, xb);
+    if (EXTRA == 2) asm volatile("cp.async.wait_group %0;" ::"n"(kRingDepth - 1) : "memory");   // chunk c0 has landed
+    const float* slot = reinterpret_cast<const float*>(ring + (size_t)((c0 >> 5) & (kRingDepth - 1)) * kRingSlotBytes);
     // rows 4*u + (lane >> 3), 16-byte chunk (lane & 7): 8 lanes write one row's 128 contiguous bytes
     const int cv = c0 + csub;
     const bool cok = cv < BN && n0 + cv + 3 < Ng;
@@ -139,9 +169,12 @@ __device__ __forceinline__ void epilogue_tile_t(uint32_t t_acc, uint64_t* tfull,
     if (bias && cok) bb = __ldg(reinterpret_cast<const float4*>(bias + n0 + cv));
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
-      float4 v[4];
+      float4 v[4], xr[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4*>(stg + (4 * (4 * half + u) + rsub) * kStagePitch + csub);
+      for (int u = 0; u < 4; ++u) {
+        v[u] = *reinterpret_cast<const float4*>(stg + (4 * (4 * half + u) + rsub) * kStagePitch + csub);
+        if (EXTRA == 2) xr[u] = *reinterpret_cast<const float4*>(slot + (4 * (4 * half + u) + rsub) * 32 + csub);
+      }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int uu = 4 * half + u;
@@ -150,25 +183,29 @@ __device__ __forceinline__ void epilogue_tile_t(uint32_t t_acc, uint64_t* tfull,
         if (bias) { w.x = __fadd_rn(w.x, bb.x); w.y = __fadd_rn(w.y, bb.y); w.z = __fadd_rn(w.z, bb.z); w.w = __fadd_rn(w.w, bb.w); }
         if (relu) { w.x = fmaxf(w.x, 0.f); w.y = fmaxf(w.y, 0.f); w.z = fmaxf(w.z, 0.f); w.w = fmaxf(w.w, 0.f); }
         if (EXTRA) {   // fused residual add (resnet_model.py:199,314) or dx += (gradient accumulation)
-          w.x = __fadd_rn(w.x, xa[uu].x); w.y = __fadd_rn(w.y, xa[uu].y); w.z = __fadd_rn(w.z, xa[uu].z); w.w = __fadd_rn(w.w, xa[uu].w);
+          const float4 x = (EXTRA == 2) ? xr[u] : xa[uu];
+          w.x = __fadd_rn(w.x, x.x); w.y = __fadd_rn(w.y, x.y); w.z = __fadd_rn(w.z, x.z); w.w = __fadd_rn(w.w, x.w);
         }
         *reinterpret_cast<float4*>(out + ((size_t)ro[uu] << 2) + n0 + cv) = w;
       }
     }
     __syncwarp();                                // the staging buffer is overwritten by the next chunk
-    if (EXTRA) {
+    if (EXTRA == 1) {
 #pragma unroll
       for (int u = 0; u < 8; ++u) xa[u] = xb[u];
     }
+    if (EXTRA == 2) ring_issue(c0 + 32 * kRingDepth);   // refill the slot just consumed
   }
+  if (EXTRA == 2) asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 __device__ __forceinline__ void epilogue_tile(uint32_t t_acc, uint64_t* tfull, uint64_t* tempty, uint32_t parity,
                                               bool zero_tile, long long my_row_off, long long* rowoff, float* stg,
                                               float* __restrict__ out, const float* __restrict__ extra,
                                               const float* __restrict__ bias, int relu, int n0, int BN, int Ng,
-                                              int warp, int lane) {
-  if (extra) epilogue_tile_t<true>(t_acc, tfull, tempty, parity, zero_tile, my_row_off, rowoff, stg, out, extra, bias, relu, n0, BN, Ng, warp, lane);
-  else epilogue_tile_t<false>(t_acc, tfull, tempty, parity, zero_tile, my_row_off, rowoff, stg, out, nullptr, bias, relu, n0, BN, Ng, warp, lane);
+                                              int warp, int lane, uint8_t* ring = nullptr) {
+  if (extra && ring) epilogue_tile_t<2>(t_acc, tfull, tempty, parity, zero_tile, my_row_off, rowoff, stg, out, extra, bias, relu, n0, BN, Ng, warp, lane, ring);
+  else if (extra) epilogue_tile_t<1>(t_acc, tfull, tempty, parity, zero_tile, my_row_off, rowoff, stg, out, extra, bias, relu, n0, BN, Ng, warp, lane, nullptr);
+  else epilogue_tile_t<0>(t_acc, tfull, tempty, parity, zero_tile, my_row_off, rowoff, stg, out, nullptr, bias, relu, n0, BN, Ng, warp, lane, nullptr);
 }
 
 template <int MODE>
@@ -198,6 +235,7 @@ conv_tc_persist_kernel(const float* __restrict__ src, const __nv_bfloat16* __res
   uint8_t* smem_b = smem + (size_t)p.n_stages * 2 * a_bytes;        // n_bslots x (hi, lo)
   float* stage_all = reinterpret_cast<float*>(smem_b + (size_t)p.n_bslots * 2 * b_bytes);
   long long* rowoff_all = reinterpret_cast<long long*>(stage_all + kEpiWarps * 32 * kStagePitch);
+  uint8_t* ring_all = reinterpret_cast<uint8_t*>(rowoff_all + kEpiWarps * 32);   // p.ring: 4 warps x kRingDepth slots
   __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -462,7 +500,8 @@ conv_tc_persist_kernel(const float* __restrict__ src, const __nv_bfloat16* __res
         }
       }
       epilogue_tile(tmem_base + (tcount & 1u) * (uint32_t)p.acc_cols, &tfull_bar[tcount & 1u], &tempty_bar[tcount & 1u],
-                    (tcount >> 1) & 1u, zero_tile, off, rowoff, stg, out, extra, bias, p.relu, n0, BN, p.Ng, warp, lane);
+                    (tcount >> 1) & 1u, zero_tile, off, rowoff, stg, out, extra, bias, p.relu, n0, BN, p.Ng, warp, lane,
+                    p.ring ? ring_all + (size_t)warp * kRingDepth * kRingSlotBytes : nullptr);
     }
   }
   tc_fence_before();
@@ -775,19 +814,32 @@ int launch_persist(const TcGeom& g, TcP& p, const float* src, const void* a_hi, 
     max_nk = 0;
     for (int c = 0; c < p.ncls; ++c) max_nk = std::max(max_nk, p.cls[c].ntaps * p.cblocks);
   }
+  // the epilogue's residual / accumulate operand goes through a cp.async ring when the stages leave room for it
+  const int ring_bytes = kEpiWarps * kRingDepth * kRingSlotBytes;
+  const bool has_extra = residual != nullptr || p.accumulate;
+  int budget_r = budget;
+  p.ring = 0;
+  if (has_extra && env_int("PF_TC_RING", 1) && BN >= 64) {
+    const int b2 = budget - ring_bytes;
+    const bool stat_ok = MODE != 2 && p.n_tiles == 1 && p.nk <= kMaxStages * 4 && (int64_t)p.nk * b_slot + 2 * a_stage <= b2;
+    if (stat_ok || b2 / (a_stage + b_slot) >= 2) {
+      p.ring = 1;
+      budget_r = b2;
+    }
+  }
   p.b_stationary = 0;
-  if (MODE != 2 && p.n_tiles == 1 && p.nk <= kMaxStages * 4 && (int64_t)p.nk * b_slot + 2 * a_stage <= budget &&
+  if (MODE != 2 && p.n_tiles == 1 && p.nk <= kMaxStages * 4 && (int64_t)p.nk * b_slot + 2 * a_stage <= budget_r &&
       env_int("PF_TC_STATIONARY", 1)) {
     p.b_stationary = 1;
     p.n_bslots = p.nk;
-    p.n_stages = std::min(kMaxStages, (budget - p.nk * b_slot) / a_stage);
+    p.n_stages = std::min(kMaxStages, (budget_r - p.nk * b_slot) / a_stage);
   } else {
-    p.n_stages = std::min(kMaxStages, budget / (a_stage + b_slot));
+    p.n_stages = std::min(kMaxStages, budget_r / (a_stage + b_slot));
     p.n_bslots = p.n_stages;
   }
   PF_REQUIRE(p.n_stages >= 2 || max_nk <= 1, "%s: shared-memory plan failed (BN %d)", who, BN);
   if (p.n_stages < 1) p.n_stages = 1;
-  const size_t smem = (size_t)p.n_stages * a_stage + (size_t)p.n_bslots * b_slot + fixed;
+  const size_t smem = (size_t)p.n_stages * a_stage + (size_t)p.n_bslots * b_slot + fixed + (p.ring ? ring_bytes : 0);
   if (p.total_tiles == 0) return PF_OK;
   const int grid = std::min(p.total_tiles, PF_NUM_SMS);
   if (a_hi) {
