@@ -254,7 +254,8 @@ def main():
         return
     if args.warmup < 3:
         args.warmup = 3
-    os.environ.setdefault('NCCL_DEBUG', 'WARN')      # keep NCCL's version banner off stdout (one JSON line)
+    os.environ.setdefault('NCCL_DEBUG', 'WARN')      # keep NCCL's chatter off stdout: ONE JSON line
+    os.environ.setdefault('NCCL_DEBUG_FILE', '/tmp/pf_nccl_%h_%p.log')   # (the version banner goes to a file)
     import torch
     import torch.distributed as dist
     from pocketflow_b200 import ops
