@@ -153,8 +153,18 @@ def build_learner(workload, world, batch_override=None):
 
 
 # ------------------------------------------------------------------------------ CPU reference arm
-def cpu_oracle_rate(workload, sample_batch, steps, threads):
-    """images/s of the un-fused PyTorch-CPU oracle step on a bounded sample (batch `sample_batch`)."""
+def host_threads():
+    """Threads this process may actually use (the cgroup / affinity mask, not the machine's core count)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_oracle_rate(workload, sample_batch, steps, threads, budget_s=30.0):
+    """images/s of the un-fused PyTorch-CPU oracle step on a bounded sample (batch `sample_batch`): one warm-up
+    step, then up to `steps` timed steps, fewer when they would not fit `budget_s` seconds (at least one).
+    Returns (images/s, seconds per step, timed steps)."""
     import torch
     from oracle.step_oracle import StepOracle
     from pocketflow_b200 import graph as G
@@ -203,24 +213,26 @@ def cpu_oracle_rate(workload, sample_batch, steps, threads):
     masks = None
     images, labels = it.next_batch()
     img, lb = images.numpy(), labels.numpy()
+    tw = time.perf_counter()
     orc.step(state, img, lb, opt, 1e-3, teacher_state=tstate, masks=masks)       # warm-up
+    tw = time.perf_counter() - tw
+    steps = max(1, min(steps, int(budget_s / max(tw, 1e-3))))
     t0 = time.perf_counter()
     for _ in range(steps):
         _, state, _ = orc.step(state, img, lb, opt, 1e-3, teacher_state=tstate, masks=masks)
     dt = time.perf_counter() - t0
-    return sample_batch * steps / dt, dt / steps
+    return sample_batch * steps / dt, dt / steps, steps
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    sb = args.cpu_batch or (8 if 'resnet50' in args.workload else 64)
-    steps = max(1, min(args.steps, 3))
-    rate, sec = cpu_oracle_rate(args.workload, sb, steps, cores)
+    cores = host_threads()
+    sb = args.cpu_batch or (2 if 'resnet50' in args.workload else (4 if 'mobilenet' in args.workload else 64))
+    rate, sec, steps = cpu_oracle_rate(args.workload, sb, args.steps, cores, budget_s=120.0)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': 'images/s', 'n_gpus': args.gpus,
-        'steps': steps, 'warmup': 1, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'steps': steps, 'warmup': 1, 'steps_requested': args.steps, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': args.workload, 'description': WORKLOADS[args.workload][4],
                    'note': 'TensorFlow 1.x (the reference runtime) is not installable in this image; this is the '
@@ -389,13 +401,13 @@ def main():
             'clocks': sampler.summary(),
         }
         if not args.no_cpu_baseline and world == 1:
-            cores = os.cpu_count() or 1
-            sb = args.cpu_batch or (8 if 'resnet50' in args.workload else 64)
+            cores = host_threads()
+            sb = args.cpu_batch or (2 if 'resnet50' in args.workload else (4 if 'mobilenet' in args.workload else 64))
             try:
-                rate, sec = cpu_oracle_rate(args.workload, sb, 2, cores)
+                rate, sec, nst = cpu_oracle_rate(args.workload, sb, 2, cores, budget_s=25.0)
                 line['cpu_baseline'] = {'value': rate, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-                                        'sample': '2 steps of batch %d of the same graph (bounded sample), '
-                                                  'oracle/step_oracle.py' % sb}
+                                        'sample': '%d step(s) of batch %d of the same graph (bounded sample, %.1f s '
+                                                  'per step), oracle/step_oracle.py' % (nst, sb, sec)}
             except Exception as e:  # noqa: BLE001
                 line['cpu_baseline'] = {'value': None, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
                                         'sample': 'failed: %s' % e}
