@@ -954,7 +954,7 @@ inline void wgrad_plan(const TcGeom& g, WgP* pp) {
   p.tiles = p.m_tiles * p.n_tiles;
   // enough units to fill the SMs a few times over, but at least 8 k-stages (512 pixels) per unit
   // (rounded DOWN: total units just under a whole number of waves over the 148 SMs)
-  int splits = (env_int("PF_TC_WGRAD_WAVES", 2) * PF_NUM_SMS) / p.tiles;
+  int splits = (env_int("PF_TC_WGRAD_WAVES", 1) * PF_NUM_SMS) / p.tiles;
   const int max_by_k = (p.Npix + 8 * BK - 1) / (8 * BK);
   splits = std::max(1, std::min(std::min(splits, max_by_k), PF_CONV_TC_WGRAD_MAX_SPLITS));
   int pps = (p.Npix + splits - 1) / splits;
