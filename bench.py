@@ -154,11 +154,27 @@ def build_learner(workload, world, batch_override=None):
 
 # ------------------------------------------------------------------------------ CPU reference arm
 def host_threads():
-    """Threads this process may actually use (the cgroup / affinity mask, not the machine's core count)."""
+    """Threads this process may actually use: min(affinity mask, cgroup CPU quota, 32).  The GPU boxes expose 128
+    logical cores through the affinity mask while the container's CFS quota is a small fraction of that; 128 OpenMP
+    threads spinning on a few cores' worth of quota made one oracle step take minutes."""
     try:
-        return max(1, len(os.sched_getaffinity(0)))
+        n = len(os.sched_getaffinity(0))
     except AttributeError:
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    try:
+        with open('/sys/fs/cgroup/cpu.max') as f:                      # cgroup v2: "<quota> <period>" or "max <period>"
+            q, per = f.read().split()[:2]
+            if q != 'max':
+                n = min(n, max(1, int(int(q) / int(per))))
+    except (OSError, ValueError):
+        try:
+            with open('/sys/fs/cgroup/cpu/cpu.cfs_quota_us') as f, open('/sys/fs/cgroup/cpu/cpu.cfs_period_us') as g_:
+                q, per = int(f.read()), int(g_.read())
+                if q > 0:
+                    n = min(n, max(1, q // per))
+        except (OSError, ValueError):
+            pass
+    return max(1, min(n, 32))
 
 
 def cpu_oracle_rate(workload, sample_batch, steps, threads, budget_s=30.0):
@@ -224,12 +240,33 @@ def cpu_oracle_rate(workload, sample_batch, steps, threads, budget_s=30.0):
     return sample_batch * steps / dt, dt / steps, steps
 
 
+def cpu_oracle_rate_bounded(workload, sample_batch, steps, threads, budget_s, hard_timeout_s):
+    """cpu_oracle_rate in a child process with a hard wall-clock limit (a contended host must not stall the bench).
+    Returns (images/s | None, seconds per step | None, timed steps, note)."""
+    import subprocess
+    cmd = [sys.executable, os.path.abspath(__file__), '--cpu-leg', workload, str(sample_batch), str(steps), str(threads),
+           str(budget_s)]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=hard_timeout_s, env=dict(os.environ, CUDA_VISIBLE_DEVICES=''))
+        for ln in reversed(out.stdout.strip().split('\n')):
+            if ln.startswith('{'):
+                r = json.loads(ln)
+                return r['rate'], r['sec'], r['steps'], 'ok'
+        return None, None, 0, 'cpu leg failed: %s' % out.stderr.strip().split('\n')[-1][:200]
+    except subprocess.TimeoutExpired:
+        return None, None, 0, 'cpu leg exceeded %d s of wall clock on this host (warm-up + 1 step of batch %d)' % (
+            hard_timeout_s, sample_batch)
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
     cores = host_threads()
     sb = args.cpu_batch or (2 if 'resnet50' in args.workload else (4 if 'mobilenet' in args.workload else 64))
-    rate, sec, steps = cpu_oracle_rate(args.workload, sb, args.steps, cores, budget_s=120.0)
+    rate, sec, steps, note = cpu_oracle_rate_bounded(args.workload, sb, args.steps, cores, 120.0, 280)
+    if rate is None:
+        print(json.dumps({'impl': 'reference', 'unavailable': note}), flush=True)
+        return
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': 'images/s', 'n_gpus': args.gpus,
         'steps': steps, 'warmup': 1, 'steps_requested': args.steps, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
@@ -248,6 +285,11 @@ def run_reference(args, rank):
 
 # ------------------------------------------------------------------------------ GPU arm
 def main():
+    if len(sys.argv) >= 7 and sys.argv[1] == '--cpu-leg':
+        wl, sb, st, th, bud = sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]), float(sys.argv[6])
+        rate, sec, nst = cpu_oracle_rate(wl, sb, st, th, bud)
+        print(json.dumps({'rate': rate, 'sec': sec, 'steps': nst}), flush=True)
+        return
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
@@ -404,10 +446,10 @@ def main():
             cores = host_threads()
             sb = args.cpu_batch or (2 if 'resnet50' in args.workload else (4 if 'mobilenet' in args.workload else 64))
             try:
-                rate, sec, nst = cpu_oracle_rate(args.workload, sb, 2, cores, budget_s=25.0)
+                rate, sec, nst, note = cpu_oracle_rate_bounded(args.workload, sb, 2, cores, 25.0, 120)
                 line['cpu_baseline'] = {'value': rate, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-                                        'sample': '%d step(s) of batch %d of the same graph (bounded sample, %.1f s '
-                                                  'per step), oracle/step_oracle.py' % (nst, sb, sec)}
+                                        'sample': ('%d step(s) of batch %d of the same graph (bounded sample, %.1f s '
+                                                   'per step), oracle/step_oracle.py' % (nst, sb, sec)) if rate else note}
             except Exception as e:  # noqa: BLE001
                 line['cpu_baseline'] = {'value': None, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
                                         'sample': 'failed: %s' % e}
