@@ -265,7 +265,8 @@ int pf_conv2d_tc_fwd(const pf_conv_desc* d, const float* x_dev, const void* w_hi
 int pf_conv2d_tc_dgrad(const pf_conv_desc* d, const float* dy_dev, const void* wd_hi_dev, const void* wd_lo_dev,
                        int accumulate, float* dx_dev, void* stream);
 /* multi-tensor weight preparation: every conv kernel of a network in ONE launch.  segs: one entry per kernel
- * (kpad = pf_conv2d_tc_weight_elems / rows; dgrad pointers may be NULL), work: kind-0 chunks of the weights. */
+ * (kpad = pf_conv2d_tc_weight_elems / rows; dgrad pointers may be NULL), work: one item per 32 x 64 tile of the
+ * [R*S*Cin, Cout] matrix (start = first row, c0 = first column). */
 typedef struct pf_tc_prep_seg {
   const float* w;          /* HWIO fp32 */
   void* fwd_hi;
@@ -348,6 +349,11 @@ int pf_bn_train_stats_range(const float* x_dev, int64_t m, int c, float eps, flo
                             const float* gamma_dev, const float* beta_dev, int act, uint32_t* minmax_enc_dev,
                             float* ws_dev, void* stream);
 int pf_bn_eval_prepare(const float* moving_var_dev, int c, float eps, float* rstd_dev, void* stream);
+/* inference-mode BN in one launch: rstd = rsqrt(moving_var + eps) is formed in the kernel (same roundings as
+ * pf_bn_eval_prepare + pf_bn_apply); fp32 and/or split-bf16 plane output */
+int pf_bn_apply_eval(const float* x_dev, int64_t m, int c, const float* moving_mean_dev, const float* moving_var_dev,
+                     float eps, const float* gamma_dev, const float* beta_dev, int act, float* y_dev, void* y_hi_dev,
+                     void* y_lo_dev, uint32_t* minmax_enc_dev, void* stream);
 /* y = Q(act(bn(x))) in one pass with a known range (pf_bn_train_stats_range): fp32 and/or split-bf16 planes */
 int pf_bn_apply_quant(const float* x_dev, int64_t m, int c, const float* mean_dev, const float* rstd_dev,
                       const float* gamma_dev, const float* beta_dev, int act, const uint32_t* range_enc_dev, int bits,

@@ -197,7 +197,9 @@ bn_apply_kernel(const float* __restrict__ x, int64_t total, int C, const float* 
                 const float* __restrict__ rstd, const float* __restrict__ gamma,
                 const float* __restrict__ beta, int act, float* __restrict__ y,
                 uint32_t* __restrict__ minmax_enc, void* __restrict__ y_hi, void* __restrict__ y_lo,
-                const uint32_t* __restrict__ q_range, int q_bits) {
+                const uint32_t* __restrict__ q_range, int q_bits, float var_eps) {
+  // var_eps >= 0: `rstd` holds the (moving) VARIANCE and rstd = rsqrt(var + eps) is formed here (inference mode;
+  // same two roundings as bn_eval_prepare_kernel, one launch less per layer)
   __shared__ float s_mn[NT / 32], s_mx[NT / 32];
   // fused activation fake-quant (range known beforehand: pf_bn_train_stats_range)
   float q_alpha = 1.f, q_beta = 0.f, q_k = 1.f, q_ra = 1.f, q_rk = 1.f;
@@ -235,7 +237,11 @@ bn_apply_kernel(const float* __restrict__ x, int64_t total, int C, const float* 
     // the grid stride is a multiple of C: this thread's 4 channels never change -> parameters live in
     // registers and the loop is a pure 8 B/element stream with 4 independent loads in flight
     const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + c));
-    const float4 rs = __ldg(reinterpret_cast<const float4*>(rstd + c));
+    float4 rs = __ldg(reinterpret_cast<const float4*>(rstd + c));
+    if (var_eps >= 0.f) {
+      rs.x = __frsqrt_rn(__fadd_rn(rs.x, var_eps)); rs.y = __frsqrt_rn(__fadd_rn(rs.y, var_eps));
+      rs.z = __frsqrt_rn(__fadd_rn(rs.z, var_eps)); rs.w = __frsqrt_rn(__fadd_rn(rs.w, var_eps));
+    }
     const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c));
     const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
     for (; i + 3 * stride < nvec; i += 4 * stride) {
@@ -252,7 +258,11 @@ bn_apply_kernel(const float* __restrict__ x, int64_t total, int C, const float* 
   } else {
     for (; i < nvec; i += stride) {
       const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + c));
-      const float4 rs = __ldg(reinterpret_cast<const float4*>(rstd + c));
+      float4 rs = __ldg(reinterpret_cast<const float4*>(rstd + c));
+      if (var_eps >= 0.f) {
+        rs.x = __frsqrt_rn(__fadd_rn(rs.x, var_eps)); rs.y = __frsqrt_rn(__fadd_rn(rs.y, var_eps));
+        rs.z = __frsqrt_rn(__fadd_rn(rs.z, var_eps)); rs.w = __frsqrt_rn(__fadd_rn(rs.w, var_eps));
+      }
       const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c));
       const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
       apply4(pf_ld_stream(x + (i << 2)), mu, rs, ga, be, i);
@@ -515,6 +525,96 @@ maxpool_fwd_kernel(const float* __restrict__ x, int N, int H, int W, int C, int 
   }
 }
 
+// 3x3 / stride 2 (the ResNet stem pool, resnet_model.py:521-525): taps unrolled, all nine loads issued before the
+// first compare (the generic kernel's data-dependent `continue`s serialise them: 2.5 TB/s -> see profiles/)
+__global__ void __launch_bounds__(NT)
+maxpool3x3s2_fwd_kernel(const float* __restrict__ x, int N, int H, int W, int C, int P, int Q, int pt, int pl,
+                        float* __restrict__ y, uint8_t* __restrict__ argmax) {
+  const uint32_t C4 = (uint32_t)(C >> 2);
+  const uint32_t total = (uint32_t)N * P * Q * C4;
+  const uint32_t stride = gridDim.x * NT;
+  for (uint32_t i = blockIdx.x * NT + threadIdx.x; i < total; i += stride) {
+    const uint32_t pix = i / C4;
+    const int c = (int)((i - pix * C4) << 2);
+    const uint32_t t1 = pix / (uint32_t)Q;
+    const int ow = (int)(pix - t1 * (uint32_t)Q);
+    const int n = (int)(t1 / (uint32_t)P);
+    const int oh = (int)(t1 - (uint32_t)n * (uint32_t)P);
+    const int ih0 = oh * 2 - pt, iw0 = ow * 2 - pl;
+    float4 v[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int ih = ih0 + r, iw = iw0 + q;
+        const bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
+        v[r * 3 + q] = ok ? __ldg(reinterpret_cast<const float4*>(x + (((size_t)n * H + ih) * W + iw) * C + c))
+                          : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      }
+    float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    int a[4] = {255, 255, 255, 255};
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const float vv[4] = {v[t].x, v[t].y, v[t].z, v[t].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (vv[j] > m[j]) { m[j] = vv[j]; a[j] = t; }
+    }
+    const size_t o = (size_t)pix * C + c;
+    *reinterpret_cast<float4*>(y + o) = make_float4(m[0], m[1], m[2], m[3]);
+    if (argmax) *reinterpret_cast<uchar4*>(argmax + o) = make_uchar4((uint8_t)a[0], (uint8_t)a[1], (uint8_t)a[2], (uint8_t)a[3]);
+  }
+}
+
+// backward of the same pool: an input position belongs to at most 2x2 windows; their argmax bytes and dy values are
+// all requested up front
+__global__ void __launch_bounds__(NT)
+maxpool3x3s2_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ argmax, int N, int H, int W, int C,
+                        int P, int Q, int pt, int pl, int accumulate, float* __restrict__ dx) {
+  const uint32_t C4 = (uint32_t)(C >> 2);
+  const uint32_t total = (uint32_t)N * H * W * C4;
+  const uint32_t stride = gridDim.x * NT;
+  for (uint32_t i = blockIdx.x * NT + threadIdx.x; i < total; i += stride) {
+    const uint32_t pix = i / C4;
+    const int c = (int)((i - pix * C4) << 2);
+    const uint32_t t1 = pix / (uint32_t)W;
+    const int iw = (int)(pix - t1 * (uint32_t)W);
+    const int n = (int)(t1 / (uint32_t)H);
+    const int ih = (int)(t1 - (uint32_t)n * (uint32_t)H);
+    // windows oh in {ceil((ih+pt-2)/2) .. floor((ih+pt)/2)}: at most two per axis
+    const int ohb = (ih + pt) >> 1, owb = (iw + pl) >> 1;
+    uchar4 a[4];
+    float4 d[4];
+    int code[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int oh = ohb - (k >> 1), ow = owb - (k & 1);
+      const int r = ih + pt - oh * 2, q = iw + pl - ow * 2;
+      const bool ok = oh >= 0 && oh < P && ow >= 0 && ow < Q && r >= 0 && r < 3 && q >= 0 && q < 3;
+      code[k] = ok ? r * 3 + q : 254;
+      const size_t o = (((size_t)n * P + (ok ? oh : 0)) * Q + (ok ? ow : 0)) * C + c;
+      a[k] = ok ? __ldg(reinterpret_cast<const uchar4*>(argmax + o)) : make_uchar4(255, 255, 255, 255);
+      d[k] = ok ? __ldg(reinterpret_cast<const float4*>(dy + o)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // same accumulation order as the generic kernel: oh ascending, then ow ascending
+    float g[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 3; k >= 0; --k) {
+      if (a[k].x == code[k]) g[0] += d[k].x;
+      if (a[k].y == code[k]) g[1] += d[k].y;
+      if (a[k].z == code[k]) g[2] += d[k].z;
+      if (a[k].w == code[k]) g[3] += d[k].w;
+    }
+    float4 o4 = make_float4(g[0], g[1], g[2], g[3]);
+    float* p = dx + ((size_t)i << 2);
+    if (accumulate) {
+      const float4 old = *reinterpret_cast<const float4*>(p);
+      o4.x += old.x; o4.y += old.y; o4.z += old.z; o4.w += old.w;
+    }
+    *reinterpret_cast<float4*>(p) = o4;
+  }
+}
+
 // dx[n,ih,iw,c] (+)= sum of dy over the windows whose recorded argmax is (ih,iw).  Gather form: no
 // atomics, deterministic; each input position belongs to at most ceil(kh/sh)*ceil(kw/sw) windows.
 __global__ void __launch_bounds__(NT)
@@ -699,7 +799,8 @@ int pf_bn_eval_prepare(const float* moving_var_dev, int c, float eps, float* rst
 
 static int bn_apply_impl(const float* x_dev, int64_t m, int c, const float* mean_dev, const float* rstd_dev,
                          const float* gamma_dev, const float* beta_dev, int act, float* y_dev, void* y_hi_dev,
-                         void* y_lo_dev, uint32_t* minmax_enc_dev, const uint32_t* q_range_dev, int q_bits, void* stream) {
+                         void* y_lo_dev, uint32_t* minmax_enc_dev, const uint32_t* q_range_dev, int q_bits, void* stream,
+                         float var_eps = -1.f) {
   PF_REQUIRE(m > 0 && c > 0 && (c & 3) == 0, "pf_bn_apply: bad shape (C must be a multiple of 4)");
   PF_REQUIRE(act >= 0 && act <= 2, "pf_bn_apply: act must be 0 (none), 1 (relu) or 2 (relu6)");
   PF_REQUIRE(x_dev && mean_dev && rstd_dev && gamma_dev && beta_dev, "pf_bn_apply: null pointer");
@@ -709,7 +810,7 @@ static int bn_apply_impl(const float* x_dev, int64_t m, int c, const float* mean
   const int64_t total = m * c;
   bn_apply_kernel<<<chan_grid(total >> 2, c), NT, 0, (cudaStream_t)stream>>>(x_dev, total, c, mean_dev, rstd_dev, gamma_dev,
                                                                      beta_dev, act, y_dev, minmax_enc_dev, y_hi_dev, y_lo_dev,
-                                                                     q_range_dev, q_bits);
+                                                                     q_range_dev, q_bits, var_eps);
   PF_CHECK_LAUNCH("pf_bn_apply");
   return PF_OK;
 }
@@ -719,6 +820,14 @@ int pf_bn_apply_planes(const float* x_dev, int64_t m, int c, const float* mean_d
                        void* y_lo_dev, uint32_t* minmax_enc_dev, void* stream) {
   return bn_apply_impl(x_dev, m, c, mean_dev, rstd_dev, gamma_dev, beta_dev, act, y_dev, y_hi_dev, y_lo_dev, minmax_enc_dev,
                        nullptr, 0, stream);
+}
+
+int pf_bn_apply_eval(const float* x_dev, int64_t m, int c, const float* moving_mean_dev, const float* moving_var_dev,
+                     float eps, const float* gamma_dev, const float* beta_dev, int act, float* y_dev, void* y_hi_dev,
+                     void* y_lo_dev, uint32_t* minmax_enc_dev, void* stream) {
+  PF_REQUIRE(eps >= 0.f, "pf_bn_apply_eval: eps < 0");
+  return bn_apply_impl(x_dev, m, c, moving_mean_dev, moving_var_dev, gamma_dev, beta_dev, act, y_dev, y_hi_dev, y_lo_dev,
+                       minmax_enc_dev, nullptr, 0, stream, eps);
 }
 
 int pf_bn_apply_quant(const float* x_dev, int64_t m, int c, const float* mean_dev, const float* rstd_dev,
@@ -807,6 +916,12 @@ int pf_maxpool_fwd(const pf_conv_desc* d, const float* x_dev, float* y_dev, uint
   PF_REQUIRE((d->c & 3) == 0 && d->r * d->s < 255, "pf_maxpool_fwd: C must be a multiple of 4 and the window < 255");
   const int64_t total = (int64_t)d->n * d->p * d->q * (d->c >> 2);
   PF_REQUIRE(total < (1ll << 31), "pf_maxpool_fwd: tensor too large");
+  if (d->r == 3 && d->s == 3 && d->stride_h == 2 && d->stride_w == 2) {
+    maxpool3x3s2_fwd_kernel<<<ew_grid(total), NT, 0, (cudaStream_t)stream>>>(x_dev, d->n, d->h, d->w, d->c, d->p, d->q,
+                                                                            d->pad_t, d->pad_l, y_dev, argmax_dev);
+    PF_CHECK_LAUNCH("pf_maxpool_fwd");
+    return PF_OK;
+  }
   maxpool_fwd_kernel<<<ew_grid(total), NT, 0, (cudaStream_t)stream>>>(x_dev, d->n, d->h, d->w, d->c, d->p, d->q, d->r,
                                                                      d->s, d->stride_h, d->stride_w, d->pad_t,
                                                                      d->pad_l, y_dev, argmax_dev);
@@ -820,6 +935,12 @@ int pf_maxpool_bwd(const pf_conv_desc* d, const float* dy_dev, const uint8_t* ar
   PF_REQUIRE((d->c & 3) == 0, "pf_maxpool_bwd: C must be a multiple of 4");
   const int64_t total = (int64_t)d->n * d->h * d->w * (d->c >> 2);
   PF_REQUIRE(total < (1ll << 31), "pf_maxpool_bwd: tensor too large");
+  if (d->r == 3 && d->s == 3 && d->stride_h == 2 && d->stride_w == 2) {
+    maxpool3x3s2_bwd_kernel<<<ew_grid(total), NT, 0, (cudaStream_t)stream>>>(dy_dev, argmax_dev, d->n, d->h, d->w, d->c, d->p,
+                                                                            d->q, d->pad_t, d->pad_l, accumulate, dx_dev);
+    PF_CHECK_LAUNCH("pf_maxpool_bwd");
+    return PF_OK;
+  }
   maxpool_bwd_kernel<<<ew_grid(total), NT, 0, (cudaStream_t)stream>>>(dy_dev, argmax_dev, d->n, d->h, d->w, d->c,
                                                                      d->p, d->q, d->r, d->s, d->stride_h,
                                                                      d->stride_w, d->pad_t, d->pad_l, accumulate,

@@ -666,8 +666,7 @@ class Executor:
                         ops.bn_apply(x, m, c, b['mean'], b['rstd'], gamma, beta, act, y_bn, slot, pl_bn)
                 else:
                     with self.timed('bn_apply'):
-                        ops.bn_eval_prepare(mv, c, op.attrs['epsilon'], b['rstd'])
-                        ops.bn_apply(x, m, c, mm, b['rstd'], gamma, beta, act, y_bn, slot, pl_bn)
+                        ops.bn_apply_eval(x, m, c, mm, mv, op.attrs['epsilon'], gamma, beta, act, y_bn, slot, pl_bn)
                 if slot is not None:
                     with self.timed('act_quant'):
                         ops.act_quant(y, y if need_f32 else None, slot, self.act_quant['bits'][self.aq_index[relu_op]], pl)

@@ -461,6 +461,14 @@ def bn_train_stats_range(x, m, c, eps, momentum, mean, var, rstd, mov_mean, mov_
                                                    _p(ws), _stream()), 'pf_bn_train_stats_range')
 
 
+def bn_apply_eval(x, m, c, mov_mean, mov_var, eps, gamma, beta, act, y, minmax=None, planes=None):
+    """inference-mode BN (+act) in one launch, to fp32 and/or operand planes"""
+    _lib.check(_lib.load().pf_bn_apply_eval(_p(x), m, c, _p(mov_mean), _p(mov_var), float(eps), _p(gamma), _p(beta), int(act),
+                                            _p(y), _p(planes.hi if planes is not None else None),
+                                            _p(planes.lo if planes is not None else None), _p(minmax), _stream()),
+               'pf_bn_apply_eval')
+
+
 def bn_apply_quant(x, m, c, mean, rstd, gamma, beta, act, rng, bits, y=None, planes=None):
     """Q(act(bn(x))) with a known range, to fp32 and/or operand planes"""
     _lib.check(_lib.load().pf_bn_apply_quant(_p(x), m, c, _p(mean), _p(rstd), _p(gamma), _p(beta), int(act), _p(rng),
@@ -574,15 +582,17 @@ class TcWeightsBatch:
     def __init__(self, items, device):
         """items: list of (TcWeights, fp32 HWIO weight tensor [R,S,C,K])."""
         segs = np.zeros(len(items), dtype=TC_PREP_SEG)
-        numels = []
+        rows = []
         for i, (tw, w) in enumerate(items):
             r, s_, c, k = w.shape if w.dim() == 4 else (1, 1) + tuple(w.shape)
             segs[i] = (w.data_ptr(), tw.f_hi.data_ptr(), tw.f_lo.data_ptr(),
                        tw.d_hi.data_ptr() if tw.d_hi is not None else 0, tw.d_lo.data_ptr() if tw.d_lo is not None else 0,
                        r * s_, c, k, tw.f_hi.numel() // k, (tw.d_hi.numel() // c) if tw.d_hi is not None else 0, 0)
-            numels.append(w.numel())
+            for k0 in range(0, r * s_ * c, 32):                 # 32 x 64 tiles of the [R*S*Cin, Cout] matrix
+                for co0 in range(0, k, 64):
+                    rows.append((i, 0, k0, 0, co0, 0, 0))
         self.keep = items
-        self.work = flat_works(numels, 1 << 15)
+        self.work = np.array(rows, dtype=WORK) if rows else np.zeros(0, dtype=WORK)
         self.segs_dev = torch.from_numpy(segs.view(np.uint8)).to(device)
         self.work_dev = torch.from_numpy(self.work.view(np.uint8)).to(device)
 

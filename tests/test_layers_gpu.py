@@ -139,6 +139,9 @@ def test_batch_norm_eval():
     ops.bn_apply(x.to(DEV), 4 * 36, 32, mm.to(DEV), rstd, ga.to(DEV), be.to(DEV), 1, Y)
     ref = torch.relu((x.double() - mm.double()) * torch.rsqrt(mv.double() + 1e-5) * ga.double() + be.double())
     close(Y, ref)
+    Y2 = torch.empty_like(Y)                                            # one-launch inference BN: identical bits
+    ops.bn_apply_eval(x.to(DEV), 4 * 36, 32, mm.to(DEV), mv.to(DEV), 1e-5, ga.to(DEV), be.to(DEV), 1, Y2)
+    assert torch.equal(Y, Y2)
 
 
 @pytest.mark.parametrize('cfg', [(2, 12, 12, 16, 3, 2, 0), (2, 11, 11, 8, 3, 2, 1), (3, 28, 28, 32, 2, 2, 0)])

@@ -177,3 +177,37 @@ def test_split_bf16_planes():
     assert torch.equal(hi, h_ref) and torch.equal(lo, l_ref)
     rec = hi.double() + lo.double()
     assert ((rec - x.double()).abs() <= x.double().abs() * 2.0 ** -16).all()
+
+
+def test_multi_tensor_weight_prep_and_deferred_reduce():
+    """One launch preparing several kernels == the per-kernel preparation (bit-equal); deferred multi-tensor split-K
+    reduction == the immediate one."""
+    dev = torch.device(DEV)
+    g = torch.Generator().manual_seed(9)
+    shapes = [(3, 3, 64, 64), (1, 1, 256, 64), (1, 1, 48, 160), (3, 3, 16, 32), (1, 1, 512, 2048)]
+    items, singles, ws_ = [], [], []
+    for (r, s, c, k) in shapes:
+        w = (torch.randn(r, s, c, k, generator=g) * 0.1).to(dev).contiguous()
+        d = ops.conv_desc(2, 8, 8, c, k, r, s, 8, 8, 1, 1, r // 2, s // 2)
+        a, b = ops.TcWeights(d, dev), ops.TcWeights(d, dev)
+        b.prepare(w)
+        items.append((a, w))
+        singles.append(b)
+        ws_.append(w)
+    ops.TcWeightsBatch(items, dev).prepare()
+    for (a, _), b in zip(items, singles):
+        assert torch.equal(a.f_hi, b.f_hi) and torch.equal(a.f_lo, b.f_lo)
+        assert torch.equal(a.d_hi, b.d_hi) and torch.equal(a.d_lo, b.d_lo)
+    # deferred reduction
+    red, refs = [], []
+    for n, splits in [(4096, 3), (36864, 7), (64 * 160, 1)]:
+        part = torch.randn(splits * n, generator=g).to(dev)
+        out = torch.empty(n, device=dev)
+        red.append((part, out, splits))
+        acc = torch.zeros(n, device=dev)
+        for z in range(splits):
+            acc = acc + part[z * n:(z + 1) * n]
+        refs.append(acc)
+    ops.TcWgradReduceBatch(red, dev).reduce()
+    for (_, out, _), ref in zip(red, refs):
+        assert torch.equal(out, ref)
