@@ -230,6 +230,12 @@ typedef struct pf_conv_desc {
  * first layers whose Cin (3) the tensor-core path cannot take; the conv then runs as a 1x1 conv over
  * kpad channels. */
 int pf_im2col(const pf_conv_desc* d, const float* x_dev, int kpad, float* cols_dev, void* stream);
+/* Space-to-depth form of a stride-2 first layer: x' [n, hp, wp, cpad] (split-bf16 planes) with
+ * x'[.., y', x', (dy*2+dx)*c + cc] = x[.., 2y'+dy-pad_t, 2x'+dx-pad_l, cc]; the RxS stride-2 conv equals a stride-1
+ * ceil(R/2) x ceil(S/2) conv over x' whose kernel rows are re-arranged with pf_gather_rows (idx < 0: zero row). */
+int pf_s2d_planes(const float* x_dev, int n, int h, int w, int c, int pad_t, int pad_l, int hp, int wp, int cpad,
+                  void* hi_dev, void* lo_dev, void* stream);
+int pf_gather_rows(const float* src_dev, const int32_t* idx_dev, int n_rows, int row_len, float* dst_dev, void* stream);
 /* same, written directly as split-bf16 operand planes [N*P*Q, kpad] (kpad % 8 == 0) */
 int pf_im2col_planes(const pf_conv_desc* d, const float* x_dev, int kpad, void* cols_hi_dev, void* cols_lo_dev,
                      void* stream);

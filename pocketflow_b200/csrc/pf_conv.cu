@@ -372,6 +372,49 @@ im2col_planes_kernel(const float* __restrict__ x, Geom g, int M, int K, int kpad
   }
 }
 
+// Space-to-depth of a stride-2 first layer (7x7x3 stem): x'[n][y'][x'][(dy*2+dx)*C + c] = x[n][2y'+dy-pt][2x'+dx-pl][c]
+// (zero outside the image, zero in the padding channels), written straight as split-bf16 operand planes.  The
+// stride-2 RxS conv over C channels then IS a stride-1 ceil(R/2) x ceil(S/2) conv over 4C (-> cpad) channels, which the
+// tensor-core kernels take directly: no [N*P*Q, R*S*C] column matrix (2 GB at B = 256) is ever materialised.
+__global__ void __launch_bounds__(256)
+s2d_planes_kernel(const float* __restrict__ x, int N, int H, int W, int C, int pt, int pl, int HP, int WP, int cpad,
+                  void* __restrict__ hi, void* __restrict__ lo) {
+  const int c4 = cpad >> 2;
+  const int64_t total = (int64_t)N * HP * WP * c4;
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += stride) {
+    const int ch0 = (int)(i % c4) << 2;
+    int64_t t = i / c4;
+    const int xq = (int)(t % WP); t /= WP;
+    const int yq = (int)(t % HP);
+    const int n = (int)(t / HP);
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ch = ch0 + j;
+      v[j] = 0.f;
+      if (ch < 4 * C) {
+        const int blk = ch / C, c = ch - blk * C;
+        const int ih = 2 * yq + (blk >> 1) - pt, iw = 2 * xq + (blk & 1) - pl;
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W) v[j] = __ldg(x + (((size_t)n * H + ih) * W + iw) * C + c);
+      }
+    }
+    pf_st_planes4(hi, lo, i << 2, make_float4(v[0], v[1], v[2], v[3]));
+  }
+}
+
+// dst[j][:] = idx[j] >= 0 ? src[idx[j]][:] : 0 — re-arranges a small weight (gradient) matrix by rows
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx, int n_rows, int row_len,
+                   float* __restrict__ dst) {
+  const int64_t total = (int64_t)n_rows * row_len;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int j = (int)(i / row_len), e = (int)(i - (int64_t)j * row_len);
+    const int s = idx[j];
+    dst[i] = s >= 0 ? src[(size_t)s * row_len + e] : 0.f;
+  }
+}
+
 int check_geom(const pf_conv_desc* d, Geom* g, const char* who) {
   PF_REQUIRE(d != nullptr, "%s: null descriptor", who);
   PF_REQUIRE(d->n > 0 && d->h > 0 && d->w > 0 && d->c > 0 && d->k > 0 && d->r > 0 && d->s > 0 &&
@@ -421,6 +464,32 @@ int pf_im2col_planes(const pf_conv_desc* d, const float* x_dev, int kpad, void* 
   im2col_planes_kernel<<<(unsigned)blocks, 256, kpad * sizeof(int), (cudaStream_t)stream>>>(x_dev, g, M, K, kpad, cols_hi_dev,
                                                                                            cols_lo_dev);
   PF_CHECK_LAUNCH("pf_im2col_planes");
+  return PF_OK;
+}
+
+int pf_s2d_planes(const float* x_dev, int n, int h, int w, int c, int pad_t, int pad_l, int hp, int wp, int cpad,
+                  void* hi_dev, void* lo_dev, void* stream) {
+  PF_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && hp > 0 && wp > 0 && pad_t >= 0 && pad_l >= 0, "pf_s2d_planes: bad shape");
+  PF_REQUIRE(cpad % 8 == 0 && cpad >= 4 * c, "pf_s2d_planes: cpad must be a multiple of 8 and >= 4*C");
+  PF_REQUIRE(x_dev && hi_dev && lo_dev, "pf_s2d_planes: null pointer");
+  PF_REQUIRE((((uintptr_t)hi_dev | (uintptr_t)lo_dev) & 15) == 0, "pf_s2d_planes: planes must be 16-byte aligned");
+  const int64_t total = (int64_t)n * hp * wp * (cpad >> 2);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > PF_NUM_SMS * 16) blocks = PF_NUM_SMS * 16;
+  s2d_planes_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x_dev, n, h, w, c, pad_t, pad_l, hp, wp, cpad, hi_dev,
+                                                                       lo_dev);
+  PF_CHECK_LAUNCH("pf_s2d_planes");
+  return PF_OK;
+}
+
+int pf_gather_rows(const float* src_dev, const int32_t* idx_dev, int n_rows, int row_len, float* dst_dev, void* stream) {
+  PF_REQUIRE(n_rows >= 0 && row_len > 0, "pf_gather_rows: bad shape");
+  if (n_rows == 0) return PF_OK;
+  PF_REQUIRE(src_dev && idx_dev && dst_dev, "pf_gather_rows: null pointer");
+  int64_t blocks = ((int64_t)n_rows * row_len + 255) / 256;
+  if (blocks > PF_NUM_SMS * 8) blocks = PF_NUM_SMS * 8;
+  gather_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src_dev, idx_dev, n_rows, row_len, dst_dev);
+  PF_CHECK_LAUNCH("pf_gather_rows");
   return PF_OK;
 }
 

@@ -160,11 +160,19 @@ class Executor:
         for op in self.ops:
             if op in self.im2col:
                 im, wk = self.im2col[op], self.kernel_of(op)
-                ops.add(wk.reshape(-1), None, im['wpad'][:wk.numel()])
-                im['tw'].prepare(im['wpad'])
+                self._stem_weights(im, wk)
             elif op in self.tc:
                 self.tc[op].prepare(self.kernel_of(op))
         self._static_ready = True
+
+    def _stem_weights(self, im, wk):
+        """fp32 kernel of the first layer -> the (re-arranged / padded) matrix its tensor-core conv multiplies by"""
+        k = wk.shape[-1]
+        if im['mode'] == 's2d':
+            ops.gather_rows(wk, im['fwd_map'], im['wpad'], k)
+        else:
+            ops.add(wk.reshape(-1), None, im['wpad'][:wk.numel()])       # rows >= R*S*C stay zero
+        im['tw'].prepare(im['wpad'])
 
     # ------------------------------------------------------------------ planning
     def _reachable_ops(self, out):
@@ -271,10 +279,21 @@ class Executor:
                     d1 = ops.conv_desc(n, p, q, kpad, k, 1, 1, p, q, 1, 1, 0, 0)
                     # columns directly in operand planes when every consumer is a tensor-core kernel
                     as_planes = (not self.train) or ops.conv2d_tc_wgrad_supported(d1)
-                    self.im2col[op] = dict(kdim=kdim, kpad=kpad, d1=d1, compute=True, planes=as_planes,
-                                           cols=ops.Planes(n * p * q * kpad, dev) if as_planes else E((n * p * q, kpad)),
+                    mode = 'im2col'
+                    if sh == 2 and sw == 2 and 4 * c <= 16 and _os.environ.get('PF_STEM_S2D', '1') != '0':
+                        # stride-2 stem: space-to-depth instead of im2col — a stride-1 conv over 16 channels that the
+                        # tensor-core kernels gather themselves (no 2 GB column matrix)
+                        r2, s2, fwd_map, bwd_map = ops.s2d_weight_maps(kh, kw, c, 16)
+                        d2 = ops.conv_desc(n, p + r2 - 1, q + s2 - 1, 16, k, r2, s2, p, q, 1, 1, 0, 0)
+                        if ops.conv2d_tc_supported(d2) and ((not self.train) or ops.conv2d_tc_wgrad_supported(d2)):
+                            mode, d1, as_planes, kpad = 's2d', d2, True, r2 * s2 * 16
+                    self.im2col[op] = dict(kdim=kdim, kpad=kpad, d1=d1, compute=True, planes=as_planes, mode=mode,
+                                           cols=ops.Planes(n * d1.h * d1.w * d1.c, dev) if as_planes else E((n * p * q, kpad)),
                                            wpad=torch.zeros(kpad * k, dtype=torch.float32, device=dev),
                                            tw=ops.TcWeights(d1, dev, need_dgrad=False))
+                    if mode == 's2d':
+                        self.im2col[op]['fwd_map'] = torch.from_numpy(fwd_map).to(dev)
+                        self.im2col[op]['bwd_map'] = torch.from_numpy(bwd_map).to(dev)
                     if self.train:
                         self.im2col[op]['dwpad'] = torch.zeros(kpad * k, dtype=torch.float32, device=dev)
                         if ops.conv2d_tc_wgrad_supported(d1):
@@ -596,7 +615,10 @@ class Executor:
                     wk = self.kernel_of(op)
                     with self.timed('conv_prep'):
                         if im['compute']:
-                            if im['planes']:
+                            if im['mode'] == 's2d':
+                                pt_, pl_ = op.attrs['pad']
+                                ops.s2d_planes(self.T(op.inputs[0]), pt_, pl_, im['d1'].h, im['d1'].w, im['d1'].c, im['cols'])
+                            elif im['planes']:
                                 ops.im2col_planes(self.desc[op], self.T(op.inputs[0]), im['kpad'], im['cols'])
                             else:
                                 ops.im2col(self.desc[op], self.T(op.inputs[0]), im['kpad'], im['cols'])
@@ -605,8 +627,7 @@ class Executor:
                         elif self.cols_wait is not None:
                             torch.cuda.current_stream().wait_event(self.cols_wait)
                         if not self.static_weights:
-                            ops.add(wk.reshape(-1), None, im['wpad'][:wk.numel()])       # rows >= R*S*C stay zero
-                            im['tw'].prepare(im['wpad'])
+                            self._stem_weights(im, wk)
                     with self.timed('conv_fwd'):
                         if im['planes']:
                             ops.conv2d_tc_fwd_planes(im['d1'], im['cols'], im['tw'], bias, op in self.fused_act,
@@ -744,7 +765,10 @@ class Executor:
                             ops.conv2d_tc_wgrad(im['d1'], im['cols'], gy, self.wgrad_ws, im['dwpad'])
                         else:
                             ops.conv2d_wgrad(im['d1'], im['cols'], gy, self.wgrad_ws, im['dwpad'])
-                        ops.add(im['dwpad'][:gk.numel()], None, gk.reshape(-1))
+                        if im['mode'] == 's2d':
+                            ops.gather_rows(im['dwpad'], im['bwd_map'], gk, gk.shape[-1])
+                        else:
+                            ops.add(im['dwpad'][:gk.numel()], None, gk.reshape(-1))
                     elif op in self.tc_wgrad and self._side_active and self.planes_of(x_t) is not None \
                             and self.conv_dy_planes.get(op) is not None:
                         # both operands exist as planes: the weight gradient runs on the side stream, beside the
@@ -882,6 +906,7 @@ class Executor:
         for op, im in self.im2col.items():
             for op2, im2 in other.im2col.items():
                 if op.inputs[0] is op2.inputs[0] and im['kpad'] == im2['kpad'] and im['planes'] == im2['planes'] \
+                        and im['mode'] == im2['mode'] \
                         and all(op.attrs[a] == op2.attrs[a] for a in ('ksize', 'strides', 'pad')):
                     im['cols'] = im2['cols']
                     im['compute'] = False

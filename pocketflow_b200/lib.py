@@ -36,6 +36,8 @@ SIGNATURES = {
     'pf_l2_loss': (c_i32, [c_vp, c_i64, c_f32, c_i32, c_vp, c_vp, c_vp]),
     'pf_nuq_weight_quant': (c_i32, [c_vp, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
     'pf_im2col': (c_i32, [c_vp, c_vp, c_i32, c_vp, c_vp]),
+    'pf_s2d_planes': (c_i32, [c_vp] + [c_i32] * 9 + [c_vp, c_vp, c_vp]),
+    'pf_gather_rows': (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
     'pf_im2col_planes': (c_i32, [c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]),
     'pf_conv2d_fwd': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
     'pf_conv2d_dgrad': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),

@@ -688,6 +688,33 @@ def conv2d_tc_wgrad_planes(d, xp, dyp, ws, dw):
                                                      _p(dw), _stream()), 'pf_conv2d_tc_wgrad_planes')
 
 
+def s2d_planes(x, pad_t, pad_l, hp, wp, cpad, planes):
+    """space-to-depth of a stride-2 first layer's input [n,h,w,c] into operand planes [n,hp,wp,cpad]"""
+    n, h, w, c = x.shape
+    _lib.check(_lib.load().pf_s2d_planes(_p(x), n, h, w, c, int(pad_t), int(pad_l), int(hp), int(wp), int(cpad),
+                                         _p(planes.hi), _p(planes.lo), _stream()), 'pf_s2d_planes')
+
+
+def gather_rows(src, idx, dst, row_len):
+    """dst[j] = src[idx[j]] (zero row where idx[j] < 0); rows of `row_len` floats"""
+    _lib.check(_lib.load().pf_gather_rows(_p(src), _p(idx), idx.numel(), int(row_len), _p(dst), _stream()), 'pf_gather_rows')
+
+
+def s2d_weight_maps(r, s, c, cpad):
+    """Row maps between the HWIO kernel [r,s,c,K] of a stride-2 conv and its space-to-depth form [r2,s2,cpad,K]:
+    fwd[j] = source row of s2d row j (-1: zero), bwd[i] = s2d row holding the gradient of source row i."""
+    r2, s2 = (r + 1) // 2, (s + 1) // 2
+    fwd = -np.ones(r2 * s2 * cpad, np.int32)
+    bwd = np.zeros(r * s * c, np.int32)
+    for rr in range(r):
+        for ss in range(s):
+            for cc in range(c):
+                j = ((rr // 2) * s2 + (ss // 2)) * cpad + ((rr % 2) * 2 + (ss % 2)) * c + cc
+                i = (rr * s + ss) * c + cc
+                fwd[j], bwd[i] = i, j
+    return r2, s2, fwd, bwd
+
+
 def im2col_planes(d, x, kpad, planes):
     _lib.check(_lib.load().pf_im2col_planes(ctypes.byref(d), _p(x), int(kpad), _p(planes.hi), _p(planes.lo), _stream()),
                'pf_im2col_planes')

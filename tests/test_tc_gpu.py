@@ -211,3 +211,42 @@ def test_multi_tensor_weight_prep_and_deferred_reduce():
     ops.TcWgradReduceBatch(red, dev).reduce()
     for (_, out, _), ref in zip(red, refs):
         assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize('cfg', [(2, 23, 23, 3, 64, 7, 3, 3), (2, 24, 24, 3, 64, 7, 2, 3), (3, 17, 17, 3, 64, 3, 0, 1),
+                                 (1, 32, 32, 4, 128, 5, 2, 2)])
+def test_space_to_depth_stem(cfg):
+    """Stride-2 first layer as space-to-depth + stride-1 tensor-core conv: forward and weight gradient vs float64."""
+    n, h, w, c, k, r, p0, p1 = cfg
+    dev = torch.device(DEV)
+    g = torch.Generator().manual_seed(sum(cfg))
+    x = torch.randn(n, h, w, c, generator=g)
+    wt = torch.randn(r, r, c, k, generator=g) * (2.0 / (r * r * c)) ** 0.5
+    p = (h + p0 + p1 - r) // 2 + 1
+    xd = x.double().permute(0, 3, 1, 2)
+    wd = wt.double().permute(3, 2, 0, 1).requires_grad_(True)
+    yd = F.conv2d(F.pad(xd, (p0, p1, p0, p1)), wd, stride=2)
+    dy = torch.randn(n, p, p, k, generator=g)
+    yd.backward(dy.double().permute(0, 3, 1, 2))
+    r2, s2, fwd_map, bwd_map = ops.s2d_weight_maps(r, r, c, 16)
+    d2 = ops.conv_desc(n, p + r2 - 1, p + s2 - 1, 16, k, r2, s2, p, p, 1, 1, 0, 0)
+    X, W, DY = x.to(dev), wt.to(dev).contiguous(), dy.to(dev)
+    cols = ops.Planes(n * (p + r2 - 1) * (p + s2 - 1) * 16, dev)
+    ops.s2d_planes(X, p0, p0, p + r2 - 1, p + s2 - 1, 16, cols)
+    wpad = torch.zeros(r2 * s2 * 16 * k, device=dev)
+    ops.gather_rows(W, torch.from_numpy(fwd_map).to(dev), wpad, k)
+    tw = ops.TcWeights(d2, dev, need_dgrad=False)
+    tw.prepare(wpad)
+    Y = torch.empty(n, p, p, k, device=dev)
+    ops.conv2d_tc_fwd_planes(d2, cols, tw, None, False, Y)
+    y_ref = yd.permute(0, 2, 3, 1).detach()
+    assert (Y.cpu().double() - y_ref).abs().max().item() <= 2e-5 * y_ref.abs().max().item()
+    gp = ops.Planes(DY.numel(), dev)
+    ops.split_bf16(DY, gp)
+    ws = torch.empty(max(ops.conv2d_tc_wgrad_planes_workspace_floats(d2), 4), device=dev)
+    dwpad = torch.empty(r2 * s2 * 16 * k, device=dev)
+    ops.conv2d_tc_wgrad_planes(d2, cols, gp, ws, dwpad)
+    DW = torch.empty_like(W)
+    ops.gather_rows(dwpad, torch.from_numpy(bwd_map).to(dev), DW, k)
+    dw_ref = wd.grad.permute(2, 3, 1, 0)
+    assert (DW.cpu().double() - dw_ref).abs().max().item() <= 2e-5 * dw_ref.abs().max().item()
