@@ -9,6 +9,7 @@ collective over one buffer and (b) the optimizer / mask / weight-d
 handful of launches instead of ~110 per step.
 """
 import math
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -280,7 +281,7 @@ class Executor:
                     # columns directly in operand planes when every consumer is a tensor-core kernel
                     as_planes = (not self.train) or ops.conv2d_tc_wgrad_supported(d1)
                     mode = 'im2col'
-                    if sh == 2 and sw == 2 and 4 * c <= 16 and _os.environ.get('PF_STEM_S2D', '1') != '0':
+                    if sh == 2 and sw == 2 and 4 * c <= 16 and os.environ.get('PF_STEM_S2D', '1') != '0':
                         # stride-2 stem: space-to-depth instead of im2col — a stride-1 conv over 16 channels that the
                         # tensor-core kernels gather themselves (no 2 GB column matrix)
                         r2, s2, fwd_map, bwd_map = ops.s2d_weight_maps(kh, kw, c, 16)
