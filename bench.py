@@ -418,7 +418,9 @@ def main():
                                      'kernels for the rest' % (len(ex.tc), sum(1 for o in ex.ops if o.type in ('Conv2D', 'MatMul'))))
                        if ex.tc or ex.im2col else 'fp32 CUDA-core implicit GEMM (pf_conv.cu)',
                        'l2': 'per-step working set (GBs of activations) >> 126 MB L2; no explicit flush',
-                       'cuda_graph': graph_ok},
+                       'cuda_graph': graph_ok,
+                       'input_pipeline': 'e2e: batch i+1 is copied host->device (pinned memory, copy stream) while step i '
+                                         'runs, then moved into the graph input buffers device-to-device; one H2D per step'},
             'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': int(lrn.h2d_bytes),
                     'd2h_bytes_per_step': 20, 'ms_per_step': e2e_ms / args.steps},
             'gpu_launches': int(launches_per_step * args.steps),

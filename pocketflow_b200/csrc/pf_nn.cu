@@ -9,6 +9,8 @@
 // BN+ReLU AND accumulates the per-tensor min/max the activation quantizer needs
 // (uniform_quantization/utils.py:51-79), so the separate reduce_max/reduce_min passes of the
 // reference disappear.
+#include <cstdlib>
+
 #include "pf_common.cuh"
 
 namespace {
@@ -722,9 +724,16 @@ softmax_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, in
 }
 
 // grid whose stride (gridDim*NT float4s) is a multiple of C/4, so that threads keep their channels
+inline int bn_grid_cap() {
+  static const int cap = [] {
+    const char* v = getenv("PF_BN_GRIDCAP");
+    return (v && *v) ? atoi(v) : 8;
+  }();
+  return cap;
+}
 inline unsigned chan_grid(int64_t nvec, int C) {
   int64_t want = (nvec + NT - 1) / NT;
-  const int64_t cap = (int64_t)PF_NUM_SMS * 8;
+  const int64_t cap = (int64_t)PF_NUM_SMS * bn_grid_cap();
   if (want > cap) want = cap;
   if (want < 1) want = 1;
   const int c4 = C >> 2;
