@@ -70,7 +70,11 @@ def main():
             xp, dyp = ops.Planes(x.numel(), dev), ops.Planes(dy.numel(), dev)
             ops.split_bf16(x, xp)
             ops.split_bf16(dy, dyp)
-            resid = torch.randn_like(y) if os.environ.get('RESIDUAL', '0') == '1' else None
+            resid = None
+            if os.environ.get('RESIDUAL', '0') == '1':     # RES_OFFSET: shift the residual buffer by that many bytes
+                off = int(os.environ.get('RES_OFFSET', '0')) // 4
+                rbuf = torch.randn(y.numel() + off, device=dev)
+                resid = rbuf[off:].view(y.shape)
             fns = dict(fwd=lambda: ops.conv2d_tc_fwd_planes(d, xp, tw, None, False, y, resid),
                        dgrad=lambda: ops.conv2d_tc_dgrad_planes(d, dyp, tw, False, dx),
                        wgrad=lambda: ops.conv2d_tc_wgrad_planes(d, xp, dyp, ws, dw))

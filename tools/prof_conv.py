@@ -27,8 +27,9 @@ for name in sys.argv[1:]:
     ops.split_bf16(x, xp)
     ops.split_bf16(dy, dyp)
     ws = torch.empty(max(ops.conv2d_tc_wgrad_planes_workspace_floats(d), 4), device=dev)
+    resid = torch.randn_like(y) if os.environ.get('RESIDUAL', '0') == '1' else None
     for _ in range(3):
-        ops.conv2d_tc_fwd_planes(d, xp, tw, None, False, y)
+        ops.conv2d_tc_fwd_planes(d, xp, tw, None, False, y, resid)
         ops.conv2d_tc_dgrad_planes(d, dyp, tw, False, dx)
         ops.conv2d_tc_wgrad_planes(d, xp, dyp, ws, dw)
     torch.cuda.synchronize()
