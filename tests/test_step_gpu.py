@@ -193,6 +193,32 @@ def test_uq_step_cuda_graph_replay_matches_eager():
     assert torch.equal(ex.store.P, P1)
 
 
+def test_multi_stream_step_is_bit_identical_to_serial(monkeypatch):
+    """The multi-stream schedule (teacher forward beside the student's, wgrad beside dgrad/BN-backward, input staging
+    on a copy stream) must not change a single bit: three learner-level steps, serial vs overlapped vs overlapped +
+    captured graph, from the same seeds."""
+    results = []
+    for overlap, graph in (('0', False), ('1', False), ('1', True)):
+        monkeypatch.setenv('PF_OVERLAP', overlap)
+        monkeypatch.setenv('PF_CONV_PATH', 'tc')
+        lrn = make_uq_learner(resnet_size=20, batch=32, dst=True)
+        ex = lrn.sess_train
+        lrn.iterator_train.prefill()                      # fixed cycle of pre-generated batches
+        if graph:
+            P0, O0 = ex.store.P.clone(), ex.store.O.clone()
+            lrn.feed(ex, lrn.iterator_train)              # capture runs the step twice: rewind afterwards
+            ex.capture()
+            ex.store.P.copy_(P0); ex.store.O.copy_(O0); ex.S1.zero_(); ex.S2.zero_()
+            lrn.iterator_train.cursor = 0
+            lrn.iterator_train._staging = None
+        for _ in range(3):
+            lrn.train_step()
+        torch.cuda.synchronize()
+        results.append((ex.store.P.clone(), ex.store.O.clone(), ex.fetch_losses()['loss']))
+    for P, O_, loss in results[1:]:
+        assert torch.equal(P, results[0][0]) and torch.equal(O_, results[0][1]) and loss == results[0][2]
+
+
 def test_lenet_uq_step_matches_oracle():
     FLAGS.reset()
     from pocketflow_b200.nets import lenet_at_cifar10 as Lnet
