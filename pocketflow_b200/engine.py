@@ -199,7 +199,11 @@ class Executor:
         dev = self.device
         self._opset = set(self.ops)
         st = self.store
-        E = lambda shape: torch.empty(shape, dtype=torch.float32, device=dev)
+        # PF_POISON=1 (debugging): every scratch / activation buffer starts as NaN, so that a read of memory no kernel
+        # has written this step shows up in the losses instead of depending on what the allocator recycled
+        poison = os.environ.get('PF_POISON', '0') == '1'
+        E = (lambda shape: torch.full(shape, float('nan'), dtype=torch.float32, device=dev)) if poison else \
+            (lambda shape: torch.empty(shape, dtype=torch.float32, device=dev))
         self.buf, self.alias = {}, {}
         self.fused_act, self.fused_into = {}, {}
         # ---- fusion: BN -> Relu/Relu6 and Conv/MatMul(bias) -> Relu with a single consumer
@@ -379,7 +383,11 @@ class Executor:
             self.S2 = torch.zeros(st.n_train, dtype=torch.float32, device=dev) \
                 if self.optimizer.get('kind') == 'adam' else None
             self.hp = torch.zeros(4, dtype=torch.float32, device=dev)
-            self.hp_host = torch.zeros(4, dtype=torch.float32).pin_memory() if dev.type == 'cuda' else torch.zeros(4)
+            # per-step scalars (lr, Adam beta powers) travel through a RING of pinned slots: the async upload of step
+            # i must have executed before the host rewrites its slot (a single slot let step i pick up step i+1's
+            # beta powers whenever the host ran ahead of the GPU)
+            self.hp_ring = torch.zeros(16, 4, dtype=torch.float32).pin_memory() if dev.type == 'cuda' else torch.zeros(16, 4)
+            self.hp_events, self._hp_i = [None] * 16, 0
             self.wgrad_ws = E((max_ws,))
             self.wgrad_ws2 = E((max_ws,)) if self.overlap else None
             self.wt_ws = E((max_wt,))
@@ -940,10 +948,19 @@ class Executor:
             self.apply_gradients()
 
     def set_hyper(self, lr):
-        self.hp_host[0] = float(lr)
-        self.hp_host[1] = float(self.beta1_power)
-        self.hp_host[2] = float(self.beta2_power)
-        self.hp.copy_(self.hp_host, non_blocking=True)
+        i = self._hp_i % self.hp_ring.shape[0]
+        self._hp_i += 1
+        if self.hp_events[i] is not None:
+            self.hp_events[i].synchronize()            # slot's previous upload has executed (16 steps ago: no wait)
+        slot = self.hp_ring[i]
+        slot[0] = float(lr)
+        slot[1] = float(self.beta1_power)
+        slot[2] = float(self.beta2_power)
+        self.hp.copy_(slot, non_blocking=True)
+        if self.hp.device.type == 'cuda':
+            ev = torch.cuda.Event()
+            ev.record()
+            self.hp_events[i] = ev
 
     def advance_optimizer_state(self):
         if self.optimizer.get('kind') == 'adam':

@@ -5,6 +5,7 @@ class/function names the reference op chain it replaces.  Pure host logic (bucke
 tables, percentile ranks) lives in functions that need no GPU, so it is unit-tested on CPU.
 """
 import ctypes
+import os
 import math
 
 import numpy as np
@@ -632,6 +633,8 @@ class Planes:
         assert numel % 8 == 0
         if buf is None:
             buf = torch.empty(2 * numel, dtype=torch.bfloat16, device=device)
+            if os.environ.get('PF_POISON', '0') == '1':
+                buf.fill_(float('nan'))
         assert buf.dtype == torch.bfloat16 and buf.numel() >= 2 * numel
         self.numel, self.buf = numel, buf
         self.hi, self.lo = buf[:numel], buf[numel:2 * numel]
