@@ -147,6 +147,157 @@ dw_wgrad_final_kernel(const float* __restrict__ part, int n, int splits, float* 
   dw[i] = (float)s;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// 3x3 specialisations (every depthwise layer of MobileNet-v1), stride ST in {1, 2}: taps unrolled with predicated
+// loads (all nine in flight at once instead of a chain of data-dependent `continue`s), 32-bit index arithmetic, and
+// the 9 x 4 filter values of the thread's channels hoisted into registers (256 threads per block is a multiple of
+// C/4 for every power-of-two C <= 1024, so a thread's channels never change).  The generic kernels above ran the
+// 13 depthwise layers at ~1 TB/s: 15.3 of the 32 ms of the MobileNet step.
+template <int ST>
+__global__ void __launch_bounds__(NT)
+dw3x3_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, DwGeom g, float* __restrict__ y) {
+  const uint32_t C4 = (uint32_t)(g.C >> 2);
+  const uint32_t total = (uint32_t)g.N * g.P * g.Q * C4;
+  const uint32_t stride = gridDim.x * NT;
+  uint32_t i = blockIdx.x * NT + threadIdx.x;
+  const int c = (int)((i % C4) << 2);
+  float4 wv[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) wv[t] = __ldg(reinterpret_cast<const float4*>(w + (size_t)t * g.C + c));
+  for (; i < total; i += stride) {
+    const uint32_t pix = i / C4;
+    const uint32_t t1 = pix / (uint32_t)g.Q;
+    const int ow = (int)(pix - t1 * (uint32_t)g.Q);
+    const int n = (int)(t1 / (uint32_t)g.P);
+    const int oh = (int)(t1 - (uint32_t)n * (uint32_t)g.P);
+    const int ih0 = oh * ST - g.pt, iw0 = ow * ST - g.pl;
+    const float* xn = x + (size_t)n * g.H * g.W * g.C + c;
+    float4 xv[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int ih = ih0 + r, iw = iw0 + q;
+        const bool ok = ih >= 0 && ih < g.H && iw >= 0 && iw < g.W;
+        xv[r * 3 + q] = ok ? __ldg(reinterpret_cast<const float4*>(xn + ((size_t)ih * g.W + iw) * g.C)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {     // same accumulation order as the generic kernel (taps ascending); skipped taps add 0*w
+      acc.x = fmaf(xv[t].x, wv[t].x, acc.x); acc.y = fmaf(xv[t].y, wv[t].y, acc.y);
+      acc.z = fmaf(xv[t].z, wv[t].z, acc.z); acc.w = fmaf(xv[t].w, wv[t].w, acc.w);
+    }
+    pf_st_stream(y + ((size_t)i << 2), acc);
+  }
+}
+
+template <int ST>
+__global__ void __launch_bounds__(NT)
+dw3x3_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w, DwGeom g, int accumulate,
+                   float* __restrict__ dx) {
+  const uint32_t C4 = (uint32_t)(g.C >> 2);
+  const uint32_t total = (uint32_t)g.N * g.H * g.W * C4;
+  const uint32_t stride = gridDim.x * NT;
+  uint32_t i = blockIdx.x * NT + threadIdx.x;
+  const int c = (int)((i % C4) << 2);
+  float4 wv[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) wv[t] = __ldg(reinterpret_cast<const float4*>(w + (size_t)t * g.C + c));
+  for (; i < total; i += stride) {
+    const uint32_t pix = i / C4;
+    const uint32_t t1 = pix / (uint32_t)g.W;
+    const int iw = (int)(pix - t1 * (uint32_t)g.W);
+    const int n = (int)(t1 / (uint32_t)g.H);
+    const int ih = (int)(t1 - (uint32_t)n * (uint32_t)g.H);
+    const float* dn = dy + (size_t)n * g.P * g.Q * g.C + c;
+    float4 dv[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int th = ih + g.pt - r, tw = iw + g.pl - q;
+        bool ok = th >= 0 && tw >= 0;
+        if (ST == 2) ok = ok && ((th | tw) & 1) == 0;
+        const int oh = ST == 2 ? th >> 1 : th, ow = ST == 2 ? tw >> 1 : tw;
+        ok = ok && oh < g.P && ow < g.Q;
+        dv[r * 3 + q] = ok ? __ldg(reinterpret_cast<const float4*>(dn + ((size_t)oh * g.Q + ow) * g.C)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      acc.x = fmaf(dv[t].x, wv[t].x, acc.x); acc.y = fmaf(dv[t].y, wv[t].y, acc.y);
+      acc.z = fmaf(dv[t].z, wv[t].z, acc.z); acc.w = fmaf(dv[t].w, wv[t].w, acc.w);
+    }
+    float* p = dx + ((size_t)i << 2);
+    if (accumulate) {
+      const float4 o = *reinterpret_cast<const float4*>(p);
+      acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+    }
+    pf_st_stream(p, acc);
+  }
+}
+
+template <int ST>
+__global__ void __launch_bounds__(NT)
+dw3x3_wgrad_partial_kernel(const float* __restrict__ x, const float* __restrict__ dy, DwGeom g, int pix_per_split,
+                           float* __restrict__ part) {
+  __shared__ float sh[NT * 4];
+  const int c0 = blockIdx.x * 128;
+  const int tc = min(128, g.C - c0);
+  const int nvec = tc >> 2, nty = NT / nvec;
+  const int tx = threadIdx.x % nvec, ty = threadIdx.x / nvec;
+  const uint32_t npix = (uint32_t)g.N * g.P * g.Q, pq = (uint32_t)g.P * g.Q;
+  const uint32_t p0 = blockIdx.y * (uint32_t)pix_per_split, p1 = min(npix, p0 + (uint32_t)pix_per_split);
+  float acc[9][4];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
+  const int c = c0 + tx * 4;
+  if (ty < nty) {
+    for (uint32_t p = p0 + ty; p < p1; p += nty) {
+      const uint32_t n = p / pq;
+      const uint32_t rem = p - n * pq;
+      const int oh = (int)(rem / (uint32_t)g.Q), ow = (int)(rem - (uint32_t)oh * g.Q);
+      const int ih0 = oh * ST - g.pt, iw0 = ow * ST - g.pl;
+      const float* xn = x + (size_t)n * g.H * g.W * g.C + c;
+      const float4 dv = pf_ld_stream(dy + (size_t)p * g.C + c);
+      float4 xv[9];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const int ih = ih0 + r, iw = iw0 + q;
+          const bool ok = ih >= 0 && ih < g.H && iw >= 0 && iw < g.W;
+          xv[r * 3 + q] = ok ? __ldg(reinterpret_cast<const float4*>(xn + ((size_t)ih * g.W + iw) * g.C)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        acc[t][0] = fmaf(xv[t].x, dv.x, acc[t][0]); acc[t][1] = fmaf(xv[t].y, dv.y, acc[t][1]);
+        acc[t][2] = fmaf(xv[t].z, dv.z, acc[t][2]); acc[t][3] = fmaf(xv[t].w, dv.w, acc[t][3]);
+      }
+    }
+  }
+  for (int t = 0; t < 9; ++t) {     // combine over ty per tap, fixed order
+    __syncthreads();
+    if (ty < nty) {
+      float* a = &sh[(ty * nvec + tx) * 4];
+      a[0] = acc[t][0]; a[1] = acc[t][1]; a[2] = acc[t][2]; a[3] = acc[t][3];
+    }
+    __syncthreads();
+    for (int cc = threadIdx.x; cc < tc; cc += NT) {
+      float s = 0.f;
+      for (int y = 0; y < nty; ++y) s += sh[(y * nvec + (cc >> 2)) * 4 + (cc & 3)];
+      part[((size_t)blockIdx.y * 9 + t) * g.C + c0 + cc] = s;
+    }
+  }
+}
+
+inline bool dw_is3x3(const DwGeom& g) {
+  const int c4 = g.C >> 2;
+  return g.R == 3 && g.S == 3 && g.sh == g.sw && (g.sh == 1 || g.sh == 2) && c4 > 0 && (NT % c4) == 0 &&
+         (int64_t)g.N * g.H * g.W * c4 < (1ll << 31) && (int64_t)g.N * g.P * g.Q * c4 < (1ll << 31);
+}
+
 int dw_geom(const pf_conv_desc* d, DwGeom* g, const char* who) {
   PF_REQUIRE(d != nullptr, "%s: null descriptor", who);
   PF_REQUIRE(d->n > 0 && d->h > 0 && d->w > 0 && d->c > 0 && d->r > 0 && d->s > 0 && d->p > 0 && d->q > 0 &&
@@ -185,7 +336,10 @@ int pf_dwconv_fwd(const pf_conv_desc* d, const float* x_dev, const float* w_dev,
   int rc = dw_geom(d, &g, "pf_dwconv_fwd");
   if (rc) return rc;
   PF_REQUIRE(x_dev && w_dev && y_dev, "pf_dwconv_fwd: null pointer");
-  dw_fwd_kernel<<<dw_grid((int64_t)g.N * g.P * g.Q * (g.C >> 2)), NT, 0, (cudaStream_t)stream>>>(x_dev, w_dev, g, y_dev);
+  const unsigned grid = dw_grid((int64_t)g.N * g.P * g.Q * (g.C >> 2));
+  if (dw_is3x3(g) && g.sh == 1) dw3x3_fwd_kernel<1><<<grid, NT, 0, (cudaStream_t)stream>>>(x_dev, w_dev, g, y_dev);
+  else if (dw_is3x3(g)) dw3x3_fwd_kernel<2><<<grid, NT, 0, (cudaStream_t)stream>>>(x_dev, w_dev, g, y_dev);
+  else dw_fwd_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(x_dev, w_dev, g, y_dev);
   PF_CHECK_LAUNCH("pf_dwconv_fwd");
   return PF_OK;
 }
@@ -196,8 +350,10 @@ int pf_dwconv_dgrad(const pf_conv_desc* d, const float* dy_dev, const float* w_d
   int rc = dw_geom(d, &g, "pf_dwconv_dgrad");
   if (rc) return rc;
   PF_REQUIRE(dy_dev && w_dev && dx_dev, "pf_dwconv_dgrad: null pointer");
-  dw_dgrad_kernel<<<dw_grid((int64_t)g.N * g.H * g.W * (g.C >> 2)), NT, 0, (cudaStream_t)stream>>>(dy_dev, w_dev, g,
-                                                                                                   accumulate, dx_dev);
+  const unsigned grid = dw_grid((int64_t)g.N * g.H * g.W * (g.C >> 2));
+  if (dw_is3x3(g) && g.sh == 1) dw3x3_dgrad_kernel<1><<<grid, NT, 0, (cudaStream_t)stream>>>(dy_dev, w_dev, g, accumulate, dx_dev);
+  else if (dw_is3x3(g)) dw3x3_dgrad_kernel<2><<<grid, NT, 0, (cudaStream_t)stream>>>(dy_dev, w_dev, g, accumulate, dx_dev);
+  else dw_dgrad_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(dy_dev, w_dev, g, accumulate, dx_dev);
   PF_CHECK_LAUNCH("pf_dwconv_dgrad");
   return PF_OK;
 }
@@ -220,7 +376,9 @@ int pf_dwconv_wgrad(const pf_conv_desc* d, const float* x_dev, const float* dy_d
   const int splits = dw_splits(g, &pps);
   dim3 grid((g.C + 127) / 128, splits);
   cudaStream_t st = (cudaStream_t)stream;
-  dw_wgrad_partial_kernel<<<grid, NT, 0, st>>>(x_dev, dy_dev, g, pps, ws_dev);
+  if (dw_is3x3(g) && g.sh == 1) dw3x3_wgrad_partial_kernel<1><<<grid, NT, 0, st>>>(x_dev, dy_dev, g, pps, ws_dev);
+  else if (dw_is3x3(g)) dw3x3_wgrad_partial_kernel<2><<<grid, NT, 0, st>>>(x_dev, dy_dev, g, pps, ws_dev);
+  else dw_wgrad_partial_kernel<<<grid, NT, 0, st>>>(x_dev, dy_dev, g, pps, ws_dev);
   PF_CHECK_LAUNCH("pf_dwconv_wgrad/partial");
   const int n = g.R * g.S * g.C;
   dw_wgrad_final_kernel<<<(n + NT - 1) / NT, NT, 0, st>>>(ws_dev, n, splits, dw_dev);
