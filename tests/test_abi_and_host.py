@@ -137,3 +137,36 @@ def test_oracle_reproduces_golden():
         assert np.array_equal(m2, g[tag + '_mask']) and np.array_equal(v2, g[tag + '_w'])
     qx, c, idx = O.nonuniform_quantize(g['nuq_w'], 4)
     assert np.array_equal(qx, g['nuq_q']) and np.array_equal(c, g['nuq_c'])
+
+
+def test_space_to_depth_maps_reproduce_the_strided_conv():
+    """Host logic of the stride-2 stem: x' = space-to-depth(x), w' = gather(w, fwd_map) turns the RxS stride-2 conv
+    into a ceil(R/2) x ceil(S/2) stride-1 conv (float64 on the CPU), and bwd_map inverts fwd_map."""
+    import torch
+    import torch.nn.functional as F
+    from pocketflow_b200 import ops
+    for (n, h, c, k, r, pt) in [(2, 23, 3, 8, 7, 3), (1, 16, 3, 4, 3, 0), (2, 20, 4, 6, 5, 2)]:
+        g = torch.Generator().manual_seed(n + h + r)
+        x = torch.randn(n, h, h, c, generator=g, dtype=torch.float64)
+        w = torch.randn(r, r, c, k, generator=g, dtype=torch.float64)
+        pb = max(r - 1 - pt, 0)
+        p = (h + pt + pb - r) // 2 + 1
+        ref = F.conv2d(F.pad(x.permute(0, 3, 1, 2), (pt, pb, pt, pb)), w.permute(3, 2, 0, 1), stride=2).permute(0, 2, 3, 1)
+        r2, s2, fwd, bwd = ops.s2d_weight_maps(r, r, c, 16)
+        hp = p + r2 - 1
+        xs = torch.zeros(n, hp, hp, 16, dtype=torch.float64)
+        for yq in range(hp):
+            for xq in range(hp):
+                for dy in range(2):
+                    for dx in range(2):
+                        ih, iw = 2 * yq + dy - pt, 2 * xq + dx - pt
+                        if 0 <= ih < h and 0 <= iw < h:
+                            xs[:, yq, xq, (dy * 2 + dx) * c:(dy * 2 + dx) * c + c] = x[:, ih, iw, :]
+        w2 = torch.zeros(r2 * s2 * 16, k, dtype=torch.float64)
+        wf = w.reshape(-1, k)
+        for j, src in enumerate(fwd):
+            if src >= 0:
+                w2[j] = wf[src]
+        out = F.conv2d(xs.permute(0, 3, 1, 2), w2.reshape(r2, s2, 16, k).permute(3, 2, 0, 1)).permute(0, 2, 3, 1)
+        assert out.shape == ref.shape and (out - ref).abs().max().item() < 1e-10
+        assert all(fwd[bwd[i]] == i for i in range(r * r * c))
