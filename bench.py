@@ -265,7 +265,7 @@ def run_reference(args, rank):
     sb = args.cpu_batch or (2 if 'resnet50' in args.workload else (4 if 'mobilenet' in args.workload else 64))
     rate, sec, steps, note = cpu_oracle_rate_bounded(args.workload, sb, args.steps, cores, 120.0, 280)
     if rate is None:
-        print(json.dumps({'impl': 'reference', 'unavailable': note}), flush=True)
+        emit({'impl': 'reference', 'unavailable': note})
         return
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': 'images/s', 'n_gpus': args.gpus,
@@ -280,10 +280,33 @@ def run_reference(args, rank):
         'e2e': {'value': rate, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------ GPU arm
+_RESULT_FD = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Native libraries (NCCL's version banner, ...) write to file
+    descriptor 1 directly, so fd 1 is pointed at stderr for the whole run and the result line goes to a saved copy
+    of the original stdout."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + '\n').encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
     if len(sys.argv) >= 7 and sys.argv[1] == '--cpu-leg':
         wl, sb, st, th, bud = sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]), float(sys.argv[6])
@@ -301,6 +324,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true')
     args = ap.parse_args()
+    quiet_stdout()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     if args.impl == 'reference':
@@ -455,7 +479,7 @@ def main():
             except Exception as e:  # noqa: BLE001
                 line['cpu_baseline'] = {'value': None, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
                                         'sample': 'failed: %s' % e}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
 
