@@ -27,9 +27,15 @@ POOL_SIZE = 8   # distinct synthetic mini-batches kept in pinned host memory
 
 
 class BatchIterator(object):
-    def __init__(self, batch_size, image_shape, nb_classes, generator):
+    def __init__(self, batch_size, image_shape, nb_classes, generator, stream=False):
+        """generator(b) -> (images [b,...] float32, one-hot labels [b,k] float32) as numpy arrays.
+        stream=False: the synthetic case — POOL_SIZE batches are generated once and cycled.
+        stream=True : a real dataset — every call draws a fresh batch from the generator into one of POOL_SIZE
+                      rotating pinned buffers (a buffer is reused POOL_SIZE calls later, long after its async
+                      host->device copy has run)."""
         self.batch_size, self.image_shape, self.nb_classes = batch_size, tuple(image_shape), nb_classes
         self.generator = generator
+        self.stream = stream
         self.images, self.labels = None, None
         self.pin = torch.cuda.is_available()
         self.pool, self.pool_size, self.cursor = [], POOL_SIZE, 0
@@ -60,6 +66,10 @@ class BatchIterator(object):
             return hi, hl
         out = self.pool[self.cursor % self.pool_size]
         self.cursor += 1
+        if self.stream:
+            img, lab = self.generator(self.batch_size)
+            out[0].copy_(torch.from_numpy(img))
+            out[1].copy_(torch.from_numpy(lab))
         return out
 
 
@@ -87,7 +97,15 @@ class AbstractDataset(ABC):
             return img, lab
         return gen
 
+    def _file_generators(self, enbl_trn_val_split):
+        """Real-data hook: subclasses that can read their files return generator(s) here (None: synthetic)."""
+        return None
+
     def build(self, enbl_trn_val_split=False):
+        gens = self._file_generators(enbl_trn_val_split) if FLAGS.data_dir_local else None
+        if gens is not None:
+            its = [BatchIterator(self.batch_size, self.image_shape, self.nb_classes, g_, stream=True) for g_ in gens]
+            return tuple(its) if len(its) > 1 else its[0]
         it = BatchIterator(self.batch_size, self.image_shape, self.nb_classes, self._generator())
         if self.is_train and enbl_trn_val_split:
             return it, BatchIterator(self.batch_size, self.image_shape, self.nb_classes, self._generator())
