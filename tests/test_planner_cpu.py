@@ -119,3 +119,38 @@ def test_fp32_copy_of_a_bn_output_is_dropped_only_when_every_consumer_reads_plan
         assert planes.numel == bn_op.output.numel
     n_dy = len(ex.conv_dy_planes)
     assert n_dy > 0 and all(op in ex.tc_wgrad for op in ex.conv_dy_planes)
+
+
+def test_unsafe_identity_sharing_is_refused():
+    """A tensor that is consumed again AFTER the residual Add (so one of its gradient writers would run BEFORE the
+    readers of the Add's gradient) must keep its own gradient buffer; the symbolic check still holds."""
+    FLAGS.reset()
+    import pocketflow_b200.datasets.cifar10_dataset  # noqa: F401  (flags)
+    g = G.Graph()
+    with g.as_default():
+        im = G.placeholder((2, 8, 8, 64), 'images')
+        lab = G.placeholder((2, 10), 'labels')
+        with G.variable_scope('model'):
+            a = G.relu(G.batch_normalization(G.conv2d(im, 64, 3, padding='same', use_bias=False), training=True))
+            b = G.conv2d(a, 64, 3, padding='same', use_bias=False)
+            s = G.add(b, a)                                   # `a` feeds the Add ...
+            c = G.conv2d(a, 64, 1, use_bias=False)            # ... and is consumed AGAIN later in forward order
+            t = G.add(s, c)
+            out = G.dense(G.reduce_mean_hw(G.relu(G.batch_normalization(t, training=True))), 10)
+            loss = G.softmax_cross_entropy(lab, out)
+    ex = Executor(g, im, out, torch.device('cpu'), train=True, loss=loss, labels=lab,
+                  optimizer=dict(kind='momentum', momentum=0.9))
+    add_s = s.op
+    a_root = ex._root(a)
+    assert ex.gkey(a_root) is not ex.gkey(add_s.output), 'unsafe in-place sharing was planned'
+    assert ex.gkey(b) is ex.gkey(add_s.output)                # the single-consumer branch still shares
+    # and the general invariant holds for this graph too
+    memo, state = {}, {ex.gkey(ex.loss.ce[1]): {'loss'}}
+    for op in reversed(ex.ops):
+        if op.type == 'Placeholder' or ex.gkey(op.output) not in state:
+            continue
+        if not (op.type in ('Reshape', 'Identity') or op in ex.fused_into):
+            assert state[ex.gkey(op.output)] == expected_contributions(ex, op.output, memo), op.name
+        for x in grad_inputs(ex, op):
+            kk = ex.gkey(x)
+            state[kk] = (state[kk] | {op}) if kk in state else {op}
