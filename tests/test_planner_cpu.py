@@ -131,9 +131,9 @@ def test_unsafe_identity_sharing_is_refused():
         im = G.placeholder((2, 8, 8, 64), 'images')
         lab = G.placeholder((2, 10), 'labels')
         with G.variable_scope('model'):
-            a = G.relu(G.batch_normalization(G.conv2d(im, 64, 3, padding='same', use_bias=False), training=True))
-            b = G.conv2d(a, 64, 3, padding='same', use_bias=False)
-            s = G.add(b, a)                                   # `a` feeds the Add ...
+            a = G.conv2d(im, 64, 3, padding='same', use_bias=False)
+            b = G.conv2d(G.relu(G.batch_normalization(a, training=True)), 64, 3, padding='same', use_bias=False)
+            s = G.add(b, a)                                   # `a` feeds the BN, the Add ...
             c = G.conv2d(a, 64, 1, use_bias=False)            # ... and is consumed AGAIN later in forward order
             t = G.add(s, c)
             out = G.dense(G.reduce_mean_hw(G.relu(G.batch_normalization(t, training=True))), 10)
