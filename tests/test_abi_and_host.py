@@ -170,3 +170,24 @@ def test_space_to_depth_maps_reproduce_the_strided_conv():
         out = F.conv2d(xs.permute(0, 3, 1, 2), w2.reshape(r2, s2, 16, k).permute(3, 2, 0, 1)).permute(0, 2, 3, 1)
         assert out.shape == ref.shape and (out - ref).abs().max().item() < 1e-10
         assert all(fwd[bwd[i]] == i for i in range(r * r * c))
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver times beside the GPU arm): exactly ONE line on stdout, valid
+    JSON, with the contract's keys; runs without a GPU."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '1',
+                          '--workload', 'lenet_uq8_b128'], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.split('\n') if ln.strip()]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    for k in ('impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+              'vs_baseline', 'dtype', 'data', 'config', 'cpu_baseline', 'e2e'):
+        assert k in d, k
+    assert d['impl'] == 'reference' and d['value'] > 0 and d['config']['workload'] == 'lenet_uq8_b128'
+    assert set(('value', 'unit', 'cores', 'kind', 'sample')) <= set(d['cpu_baseline'])
+    assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
