@@ -206,3 +206,105 @@ def test_ste_grad_is_near_identity():
     g = np.random.RandomState(3).randn(1000).astype(F32)
     out = O.uq_ste_grad(g, F32(0.731), 8)
     np.testing.assert_allclose(out, g, rtol=3e-7)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Values produced by the REFERENCE'S OWN host-side functions (tests/golden/make_golden_from_reference.py runs them from
+# /root/reference under a stub tensorflow module): schedules and the 'heurist' pruning-ratio formula.
+def _ref_gold():
+    import json
+    import os
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref_host_schedules_v1.json')))
+
+
+@pytest.mark.parametrize('which', ['uq', 'nuq'])
+def test_finetune_schedules_match_the_reference_functions(which, monkeypatch):
+    from pocketflow_b200.flags import FLAGS
+    from pocketflow_b200.utils.multi_gpu_wrapper import MultiGpuWrapper as mgw
+    FLAGS.reset()
+    import importlib
+    import pocketflow_b200.datasets.cifar10_dataset  # noqa: F401  (dataset flags)
+    mod = importlib.import_module('pocketflow_b200.learners.%s.learner' % ('uniform_quantization' if which == 'uq' else 'nonuniform_quantization'))
+    gold = _ref_gold()['%s_setup_bnds_decay_rates' % which]
+    assert len(gold) == 36
+    for g in gold:
+        FLAGS.nb_smpls_train, FLAGS.batch_size = g['nb_smpls_train'], g['batch_size']
+        FLAGS.enbl_multi_gpu, FLAGS.enbl_warm_start = g['enbl_multi_gpu'], g['enbl_warm_start']
+        FLAGS.lrn_rate_init, FLAGS.batch_size_norm = 1e-1, 128.0
+        setattr(FLAGS, 'uql_quant_epochs' if which == 'uq' else 'nuql_quant_epochs', 60)
+        monkeypatch.setattr(mgw, 'size', classmethod(lambda cls, w=g['world']: w))
+        init_lr, bnds, rates, steps = mod.setup_bnds_decay_rates(g['model'], g['dataset'])
+        assert float(init_lr) == g['init_lr'] and [int(b) for b in bnds] == g['bnds'], g
+        assert [float(r) for r in rates] == g['decay_rates'] and int(steps) == g['finetune_steps'], g
+    FLAGS.reset()
+
+
+def test_piecewise_constant_lr_matches_the_reference_function():
+    from pocketflow_b200.flags import FLAGS
+    FLAGS.reset()
+    import pocketflow_b200.datasets.cifar10_dataset  # noqa: F401
+    from pocketflow_b200.utils import lrn_rate_utils as L
+    for g in _ref_gold()['lrn_rate_piecewise_constant']:
+        FLAGS.nb_smpls_train, FLAGS.nb_epochs_rat = g['nb_smpls_train'], g['nb_epochs_rat']
+        FLAGS.lrn_rate_init, FLAGS.batch_size_norm = 1e-1, 128.0
+        fn = L.setup_lrn_rate_piecewise_constant(None, g['batch_size'], g['idxs_epoch'], g['decay_rates'])
+        bnds, vals = g['bnds'], g['vals']
+        # tf.train.piecewise_constant: vals[0] for step <= bnds[0]; vals[i] for bnds[i-1] < step <= bnds[i]; vals[-1] after
+        for i, b in enumerate(bnds):
+            assert fn(b) == vals[i] and fn(b + 1) == vals[i + 1], (g, i)
+        assert fn(0) == vals[0] and fn(bnds[-1] * 10) == vals[-1]
+    FLAGS.reset()
+
+
+def test_heurist_prune_ratios_match_the_reference_function():
+    for g in _ref_gold()['ws_heurist_prune_ratios']:
+        n = [int(np.prod(s)) for s in g['shapes']]
+        got = O.ws_heurist_ratios(n, g['ws_prune_ratio'])
+        assert np.array_equal(np.asarray(got, np.float64), np.asarray(g['ratios'], np.float64)), g
+
+
+def test_quantized_op_selection_matches_the_reference_functions():
+    """search_matmul_op / search_activation_op of the reference (run under the stub on the (type, name) lists of this
+    repo's graphs) select exactly the ops this repo's UniformQuantization selects — teacher ops excluded, first and
+    last matmul kept at full precision unless quantize_all_layers."""
+    import sys
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from tests.golden.graphs_for_golden import GRAPHS, build_graph
+    from pocketflow_b200.learners.uniform_quantization.utils import UniformQuantization
+    gold = _ref_gold()['uq_op_selection']
+    assert len(gold) == 2 * len(GRAPHS)
+    for g in gold:
+        net, flags, dst = GRAPHS[g['graph']]
+        graph = build_graph(net, flags, dst)
+        assert len(graph.ops) == g['n_ops'], 'graph changed: regenerate tests/golden/ref_host_schedules_v1.json'
+        uq = UniformQuantization(graph, 256, True, 'channel')
+        assert [o.name for o in uq.search_matmul_op(g['quantize_all_layers'])] == g['matmul'], g['graph']
+        assert [o.name for o in uq.search_activation_op()] == g['activation'], g['graph']
+    from pocketflow_b200.flags import FLAGS
+    FLAGS.reset()
+
+
+def test_dynamic_prune_ratio_matches_the_reference_function():
+    """WeightSparseLearner.__calc_prune_ratio_dyn executed from the reference source (tf scalar ops mapped onto numpy
+    float32) vs the oracle restatement: bit-identical float32 at the schedule's corner steps."""
+    gold = _ref_gold()['ws_prune_ratio_dyn']
+    assert len(gold) >= 30
+    for g in gold:
+        got = O.ws_prune_ratio_dyn(g['global_step'], g['nb_iters_train'], g['prune_ratio_fnl'])
+        assert np.float32(got).tobytes().hex() == g['value_f32_hex'], (g, float(got))
+
+
+def test_product_dynamic_prune_ratio_matches_the_reference_function():
+    """The learner's own host-side schedule (not the oracle) against the same reference-generated values."""
+    from pocketflow_b200.flags import FLAGS
+    FLAGS.reset()
+    import importlib
+    W = importlib.import_module('pocketflow_b200.learners.weight_sparsification.learner')
+    fn = getattr(W.WeightSparseLearner, '_WeightSparseLearner__calc_prune_ratio_dyn')
+    import types
+    for g in _ref_gold()['ws_prune_ratio_dyn']:
+        fake = types.SimpleNamespace(nb_iters_train=g['nb_iters_train'])
+        got = fn(fake, g['prune_ratio_fnl'], g['global_step'])
+        assert np.float32(got).tobytes().hex() == g['value_f32_hex'], g
+    FLAGS.reset()
