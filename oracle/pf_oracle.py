@@ -5,8 +5,9 @@ TEST INFRASTRUCTURE ONLY.  Only ``tests/``, ``__graft_entry__.smoke()`` and the
 module; the product path (``pocketflow_b200``) never does and fails loudly when
 ``libpf_b200.so`` is missing.
 
-PARITY UNPINNED (tensor arithmetic; the host-side schedule / ratio functions ARE pinned against the reference's own
-code run under a stub tensorflow, tests/golden/make_golden_from_reference.py): the reference (Tencent/PocketFlow @53b82cb) ships no golden
+PARITY UNPINNED in the strict sense — but the STRUCTURE of uniform_quantize, nonuniform_quantize, ws_build_mask,
+ws_prune_ratio_dyn, distillation_loss and the schedules IS pinned bit-for-bit against the reference's own Python, executed
+from /root/reference on numpy-backed stub tensors (tests/golden/make_golden_from_reference.py): the reference (Tencent/PocketFlow @53b82cb) ships no golden
 vectors, known-answer tests or fixtures for this path, and its arithmetic lives
 in TensorFlow 1.x, which cannot be imported in this image.  This file restates
 the reference's op chains literally, in the reference's op ORDER, in numpy

@@ -3,7 +3,7 @@ stub `tensorflow` module (TensorFlow 1.x itself cannot be imported here).  Only 
 path can run this way — the learning-rate / fine-tuning schedule helpers and the 'heurist' pruning-ratio formula; the
 tensor arithmetic (fake-quant, masks, losses) lives inside TensorFlow ops and stays pinned by hand-derived KATs only.
 
-  python tests/golden/make_golden_from_reference.py        ->  tests/golden/ref_host_schedules_v1.json
+  python tests/golden/make_golden_from_reference.py        ->  tests/golden/ref_executed_v1.json
 
 The stub provides exactly what the imported reference modules touch at import / call time: tf.app.flags (DEFINE_* +
 FLAGS), tf.logging.info, tf.train.piecewise_constant (records its arguments), tf.shape (identity on .shape)."""
@@ -14,7 +14,7 @@ import sys
 import types
 
 REF = '/root/reference'
-OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'ref_host_schedules_v1.json')
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'ref_executed_v1.json')
 
 
 class Flags(object):
@@ -168,6 +168,239 @@ def main():
             v = np.float32(fnl) * 1 if False else dyn(fake, np.float32(fnl))
             gold['ws_prune_ratio_dyn'].append(dict(nb_iters_train=nb_iters, prune_ratio_fnl=fnl, global_step=st,
                                                    value_f32_hex=np.float32(v).tobytes().hex(), value=float(np.float32(v))))
+    # ---- UniformQuantization.__uniform_quantize ITSELF (learners/uniform_quantization/utils.py:163-289: __scale,
+    # __inv_scale, __split_bucket, __channel_bucket) executed from the reference source on numpy-backed tensors.  The
+    # tensor stub maps every op one-to-one onto the numpy float32 op (each individually rounded, no FMA); the only
+    # semantic assumption is tf.round = round-half-to-even (np.rint).  This pins the STRUCTURE of the restatement: where
+    # eps is added, the bucket reshapes, last-element padding, the op order of scale / inverse scale, k = 2^bits - 1.
+    import builtins
+    import hashlib
+
+    class Dim(object):
+        def __init__(self, v):
+            self.value = int(v)
+
+    class Shape(list):
+        pass
+
+    class T(object):
+        def __init__(self, a):
+            self.a = np.asarray(a, dtype=np.float32)
+
+        def get_shape(self):
+            return Shape(Dim(d) for d in self.a.shape)
+
+        def __getitem__(self, i):
+            return T(self.a[i])
+
+        @staticmethod
+        def _v(o):
+            return o.a if isinstance(o, T) else np.float32(o)
+
+        def __add__(self, o):
+            return T(self.a + T._v(o))
+
+        def __radd__(self, o):
+            return T(T._v(o) + self.a)
+
+        def __sub__(self, o):
+            return T(self.a - T._v(o))
+
+        def __rsub__(self, o):
+            return T(T._v(o) - self.a)
+
+        def __mul__(self, o):
+            return T(self.a * T._v(o))
+
+        def __rmul__(self, o):
+            return T(T._v(o) * self.a)
+
+        def __truediv__(self, o):
+            return T(self.a / T._v(o))
+
+        def __rtruediv__(self, o):
+            return T(T._v(o) / self.a)
+
+    class Ctx(object):
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+    def reshape(t, shape):
+        return T(t.a.reshape([d.value if isinstance(d, Dim) else int(d) for d in shape]))
+    tf.variable_scope = lambda *a, **k: Ctx()
+    tf.get_variable_scope = lambda: types.SimpleNamespace(name='scope')
+    tf.reduce_max = lambda w, axis=None: T(np.max(w.a, axis=axis))
+    tf.reduce_min = lambda w, axis=None: T(np.min(w.a, axis=axis))
+    tf.stop_gradient = lambda x: x
+    tf.constant = lambda value=0, dtype=None: T(value) if dtype is np.float32 else 0
+    tf.cast = lambda x, dt: x if isinstance(x, T) else T(np.float32(x))
+    tf.round = lambda x: T(np.rint(x.a))
+    tf.reshape = reshape
+    tf.ones = lambda n: T(np.ones(int(n), np.float32))
+    tf.concat = lambda ts, axis=0: T(np.concatenate([t.a for t in ts], axis=axis))
+    uqu2 = load('learners/uniform_quantization/utils.py', 'ref_uq_utils2', stubs2)
+    quant = getattr(uqu2.UniformQuantization, '_UniformQuantization__uniform_quantize')
+    fake_graph = types.SimpleNamespace(gradient_override_map=lambda m: Ctx())
+    gold['uniform_quantize'] = []
+    cases = []
+    for shape in [(3, 3, 8, 16), (1, 1, 64, 10), (5, 5, 3, 7), (64, 10), (3, 3, 3, 1), (2, 2, 2, 2)]:
+        for bits in (1, 2, 4, 8, 32):
+            for mode, use_b, btype in (('weight', False, 'channel'), ('weight', True, 'channel'), ('weight', True, 'split'),
+                                       ('activation', False, 'channel')):
+                cases.append((shape, bits, mode, use_b, btype))
+    _print = builtins.print
+    builtins.print = lambda *a, **k: None                      # the reference prints "Quantized: ..." per call
+    try:
+        for ci, (shape, bits, mode, use_b, btype) in enumerate(cases):
+            rng = np.random.default_rng(1000 + ci)
+            x = (rng.standard_normal(shape) * rng.choice([1e-3, 1.0, 37.0])).astype(np.float32)
+            if ci % 7 == 3:
+                x[...] = x.flat[0]                              # constant tensor: alpha = 1e-10
+            obj = uqu2.UniformQuantization(types.SimpleNamespace(graph=fake_graph), 256, use_b, btype)
+            q = quant(obj, T(x), bits, mode, 'p')
+            out = np.ascontiguousarray(q.a, np.float32)
+            assert out.shape == tuple(shape)
+            gold['uniform_quantize'].append(dict(seed=1000 + ci, shape=list(shape), bits=bits, mode=mode, use_buckets=use_b,
+                                                 bucket_type=btype, constant=(ci % 7 == 3),
+                                                 sha256=hashlib.sha256(out.tobytes()).hexdigest(),
+                                                 first=[float(v) for v in out.reshape(-1)[:3]]))
+    finally:
+        builtins.print = _print
+    # ---- WeightSparseLearner.__build_masks (learners/weight_sparsification/learner.py:260-294) executed from the
+    # reference source on numpy-backed variables: bkup refresh, threshold on |bkup|, strict '>', var = bkup * mask, and the
+    # order the control dependencies impose.  tf.contrib.distributions.percentile is NOT available: the stub calls the
+    # oracle's percentile_nearest (the 'nearest' index rule stays a documented recollection); everything around it is
+    # the reference's own code.
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    from oracle import pf_oracle as ORC
+
+    class BT(object):                                       # boolean tensor
+        def __init__(self, a):
+            self.a = np.asarray(a, dtype=bool)
+
+    class V(T):                                             # variable
+        def __init__(self, name, a):
+            T.__init__(self, a)
+            self.name, self.shape = name, tuple(np.asarray(a).shape)
+
+        def assign(self, t):
+            self.a = np.array(t.a, dtype=np.float32)
+            return self
+
+        def initialized_value(self):
+            return T(self.a.copy())
+    T.__gt__ = lambda self, o: BT(self.a > T._v(o))
+    variables = {}
+
+    def get_variable(name, initializer=None, trainable=True):
+        if name not in variables:
+            variables[name] = V(name, np.array(initializer.a, dtype=np.float32))
+        return variables[name]
+    tf.get_variable = get_variable
+    tf.ones = lambda shape: T(np.ones(shape if isinstance(shape, tuple) else int(shape), np.float32))
+    tf.where = lambda c, a, b: T(np.where(c.a, a.a, b.a))
+    tf.abs = lambda x: T(np.abs(x.a))
+    tf.cast = lambda x, dt: T(x.a.astype(np.float32)) if isinstance(x, BT) else (x if isinstance(x, T) else T(np.float32(x)))
+    tf.minimum = lambda a, b: T(np.minimum(T._v(a), T._v(b)))
+    tf.maximum = lambda a, b: T(np.maximum(T._v(a), T._v(b)))
+    tf.pow = lambda a, b: T(np.power(T._v(a), T._v(b)))
+    tf.control_dependencies = lambda deps: Ctx()
+    tf.group = lambda ops_: ops_
+    contrib.distributions = types.SimpleNamespace(
+        percentile=lambda x, q: T(ORC.percentile_nearest(x.a, np.float32(q.a if isinstance(q, T) else q))))
+    wsl2 = load('learners/weight_sparsification/learner.py', 'ref_ws_learner2', stubs3)
+    build = getattr(wsl2.WeightSparseLearner, '_WeightSparseLearner__build_masks')
+    dyn2 = getattr(wsl2.WeightSparseLearner, '_WeightSparseLearner__calc_prune_ratio_dyn')
+    gold['ws_build_masks'] = []
+    for ci, (shape, fnl, nb_iters, steps) in enumerate([((3, 3, 8, 16), 0.5, 1000, (150, 300, 700)),
+                                                        ((1, 1, 64, 32), 0.75, 1000, (100, 101, 499, 500)),
+                                                        ((257,), 0.9, 400, (60, 120, 200)),
+                                                        ((16, 10), 0.3, 1000, (250, 260))]):
+        rng = np.random.default_rng(2000 + ci)
+        variables.clear()
+        var = V('model/w%d:0' % ci, rng.standard_normal(shape).astype(np.float32))
+        var.a[var.a.reshape(-1).argsort()[:2].tolist()] if False else None
+        flat = var.a.reshape(-1)
+        flat[1] = flat[0]                                   # a tie in |w|
+        fake = types.SimpleNamespace(mask_scope='mask', maskable_vars=[var], var_names_n_prune_ratios=[(var.name, fnl)],
+                                     nb_iters_train=nb_iters, global_step=0)
+        fake._WeightSparseLearner__calc_prune_ratio_dyn = types.MethodType(dyn2, fake)
+        rec = dict(seed=2000 + ci, shape=list(shape), prune_ratio_fnl=fnl, nb_iters_train=nb_iters, updates=[])
+        for st in steps:
+            fake.global_step = st
+            masks, _ = build(fake)
+            mask, bkup = masks[0], variables[var.name.replace(':0', '_var_bkup')]
+            rec['updates'].append(dict(global_step=st, noise_seed=3000 + st,
+                                       var=hashlib.sha256(np.ascontiguousarray(var.a).tobytes()).hexdigest(),
+                                       bkup=hashlib.sha256(np.ascontiguousarray(bkup.a).tobytes()).hexdigest(),
+                                       mask=hashlib.sha256(np.ascontiguousarray(mask.a).tobytes()).hexdigest(),
+                                       kept=int(mask.a.sum())))
+            # "training" between mask updates: surviving weights move, pruned ones stay zero (masked gradients)
+            nz = np.random.default_rng(3000 + st).standard_normal(shape).astype(np.float32) * np.float32(0.05)
+            var.a = (var.a + nz * mask.a).astype(np.float32)
+        gold['ws_build_masks'].append(rec)
+    # ---- NonUniformQuantization.__nonuni_quantize (learners/nonuniform_quantization/utils.py:168-194 with __scale,
+    # __quantile_init, __build_norm_quant_point, __inv_scale) executed from the reference source on numpy tensors
+    # (no buckets, 'weights' mode — the built configuration).  percentile = the oracle's 'nearest' rule again; argmin,
+    # gather, tile, sign, expand_dims map one-to-one onto numpy.
+    T.shape = property(lambda self: tuple(self.a.shape))
+    tf.int64 = 'int64'
+    tf.cast = lambda x, dtype=None, dt=None: (int(x) if (dtype or dt) == 'int64' else
+                                              (T(x.a.astype(np.float32)) if isinstance(x, BT) else
+                                               (x if isinstance(x, T) else T(np.float32(x)))))
+    tf.range = lambda n: list(range(int(n)))
+    tf.map_fn = lambda fn, elems, dtype=None: T(np.stack([np.asarray(T._v(fn(e)), np.float32) for e in elems]))
+    contrib.distributions = types.SimpleNamespace(
+        percentile=lambda x, q, axis=None: T(ORC.percentile_nearest(x.a, float(q), axis=axis)))
+    tf.get_variable = lambda name, validate_shape=True, initializer=None, trainable=True: T(np.array(initializer.a, np.float32))
+    tf.ones = lambda n, dtype=None: [1] * int(n) if dtype == 'int64' else T(np.ones(int(n), np.float32))
+    tf.concat = lambda ts, axis=0: ([int(v) for part in ts for v in part] if isinstance(ts[0], list)
+                                    else T(np.concatenate([t.a for t in ts], axis=axis)))
+    tf.expand_dims = lambda x, axis: T(np.expand_dims(x.a, axis))
+    tf.tile = lambda x, reps: T(np.tile(x.a, reps))
+    tf.argmin = lambda x, axis=-1: np.argmin(x.a, axis=axis)
+    tf.gather = lambda c, idx: T(c.a[idx])
+    tf.sign = lambda x: T(np.sign(x.a))
+    tf.abs = lambda x: T(np.abs(x.a))
+    nuqu = load('learners/nonuniform_quantization/utils.py', 'ref_nuq_utils', stubs2)
+    nquant = getattr(nuqu.NonUniformQuantization, '_NonUniformQuantization__nonuni_quantize')
+    gold['nonuniform_quantize'] = []
+    builtins.print = lambda *a, **k: None
+    try:
+        ci = 0
+        for shape in [(3, 3, 8, 16), (1, 1, 64, 10), (5, 5, 3, 7), (64, 10)]:
+            for bits in (1, 2, 4):
+                rng = np.random.default_rng(4000 + ci)
+                x = (rng.standard_normal(shape) * rng.choice([1e-2, 1.0, 9.0])).astype(np.float32)
+                obj = nuqu.NonUniformQuantization(types.SimpleNamespace(graph=fake_graph), 256, False, 'quantile', 'split')
+                q = nquant(obj, T(x), bits, 'weight', 'p')
+                out = np.ascontiguousarray(q.a, np.float32)
+                assert out.shape == tuple(shape)
+                gold['nonuniform_quantize'].append(dict(seed=4000 + ci, shape=list(shape), bits=bits,
+                                                        sha256=hashlib.sha256(out.tobytes()).hexdigest(),
+                                                        distinct=int(len(np.unique(out)))))
+                ci += 1
+    finally:
+        builtins.print = _print
+    # ---- DistillationHelper.calc_loss (learners/distillation_helper.py:86-103) from the reference source: the WIRING
+    # (temperature on both sides, soft-label cross-entropy, weight, no T^2); softmax / softmax_cross_entropy themselves
+    # are TF kernels and are supplied by the oracle's numpy versions.
+    tf.nn = types.SimpleNamespace(softmax=lambda x: T(ORC.softmax(x.a)))
+    tf.losses = types.SimpleNamespace(softmax_cross_entropy=lambda labels, logits: T(ORC.softmax_cross_entropy(labels.a, logits.a)[0]))
+    tf.summary = types.SimpleNamespace(scalar=lambda *a, **k: None)
+    dh = load('learners/distillation_helper.py', 'ref_dst_helper', stubs3)
+    gold['distillation_loss'] = []
+    for ci, (n, k, w, tt) in enumerate([(8, 10, 4.0, 4.0), (5, 1001, 4.0, 4.0), (3, 7, 1.0, 2.0), (16, 10, 0.5, 8.0)]):
+        rng = np.random.default_rng(5000 + ci)
+        s_ = (rng.standard_normal((n, k)) * 3).astype(np.float32)
+        t_ = (rng.standard_normal((n, k)) * 5).astype(np.float32)
+        flags.loss_w_dst, flags.tempr_dst = w, tt
+        v = dh.DistillationHelper.calc_loss(T(s_), T(t_))
+        gold['distillation_loss'].append(dict(seed=5000 + ci, n=n, k=k, loss_w_dst=w, tempr_dst=tt,
+                                              value_f32_hex=np.float32(v.a).tobytes().hex(), value=float(v.a)))
     json.dump(gold, open(OUT, 'w'), indent=1)
     print('wrote', OUT, {k: len(v) for k, v in gold.items() if isinstance(v, list)})
 

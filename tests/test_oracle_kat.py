@@ -214,7 +214,7 @@ def test_ste_grad_is_near_identity():
 def _ref_gold():
     import json
     import os
-    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref_host_schedules_v1.json')))
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref_executed_v1.json')))
 
 
 @pytest.mark.parametrize('which', ['uq', 'nuq'])
@@ -277,7 +277,7 @@ def test_quantized_op_selection_matches_the_reference_functions():
     for g in gold:
         net, flags, dst = GRAPHS[g['graph']]
         graph = build_graph(net, flags, dst)
-        assert len(graph.ops) == g['n_ops'], 'graph changed: regenerate tests/golden/ref_host_schedules_v1.json'
+        assert len(graph.ops) == g['n_ops'], 'graph changed: regenerate tests/golden/ref_executed_v1.json'
         uq = UniformQuantization(graph, 256, True, 'channel')
         assert [o.name for o in uq.search_matmul_op(g['quantize_all_layers'])] == g['matmul'], g['graph']
         assert [o.name for o in uq.search_activation_op()] == g['activation'], g['graph']
@@ -308,3 +308,64 @@ def test_product_dynamic_prune_ratio_matches_the_reference_function():
         got = fn(fake, g['prune_ratio_fnl'], g['global_step'])
         assert np.float32(got).tobytes().hex() == g['value_f32_hex'], g
     FLAGS.reset()
+
+
+def test_uniform_quantize_matches_the_reference_function_structure():
+    """UniformQuantization.__uniform_quantize (with __scale / __inv_scale / __split_bucket / __channel_bucket) executed
+    FROM THE REFERENCE SOURCE on numpy-backed tensors (every tf op mapped one-to-one onto the numpy float32 op; tf.round =
+    np.rint) vs the oracle restatement: bit-identical on 120 cases — per-layer / per-channel / strided split buckets
+    with last-element padding, activations, 1..32 bits, constant tensors."""
+    import hashlib
+    gold = _ref_gold()['uniform_quantize']
+    assert len(gold) == 120
+    for g in gold:
+        rng = np.random.default_rng(g['seed'])
+        x = (rng.standard_normal(tuple(g['shape'])) * rng.choice([1e-3, 1.0, 37.0])).astype(np.float32)
+        if g['constant']:
+            x[...] = x.flat[0]
+        q = O.uniform_quantize(x, g['bits'], mode=g['mode'], use_buckets=g['use_buckets'], bucket_type=g['bucket_type'],
+                               bucket_size=256)
+        q = np.ascontiguousarray(q, np.float32)
+        assert hashlib.sha256(q.tobytes()).hexdigest() == g['sha256'], (g, q.reshape(-1)[:3])
+
+
+def test_mask_build_matches_the_reference_function_structure():
+    """WeightSparseLearner.__build_masks executed FROM THE REFERENCE SOURCE on numpy-backed variables (percentile = the
+    oracle's 'nearest' rule, a documented recollection) over several mask updates with simulated training in between vs
+    the oracle's ws_build_mask + ws_prune_ratio_dyn: var / backup / mask bit-identical after every update."""
+    import hashlib
+    h = lambda a: hashlib.sha256(np.ascontiguousarray(a, np.float32).tobytes()).hexdigest()   # noqa: E731
+    for rec in _ref_gold()['ws_build_masks']:
+        shape = tuple(rec['shape'])
+        var = np.random.default_rng(rec['seed']).standard_normal(shape).astype(np.float32)
+        var.reshape(-1)[1] = var.reshape(-1)[0]
+        bkup, mask = var.copy(), np.ones(shape, np.float32)       # get_variable initializers: var's value, ones
+        for u in rec['updates']:
+            ratio = O.ws_prune_ratio_dyn(u['global_step'], rec['nb_iters_train'], rec['prune_ratio_fnl'])
+            var, bkup, mask, _ = O.ws_build_mask(var, bkup, mask, ratio)
+            assert (h(var), h(bkup), h(mask), int(mask.sum())) == (u['var'], u['bkup'], u['mask'], u['kept']), (rec['shape'], u)
+            nz = np.random.default_rng(u['noise_seed']).standard_normal(shape).astype(np.float32) * np.float32(0.05)
+            var = (var + nz * mask).astype(np.float32)
+
+
+def test_nonuniform_quantize_matches_the_reference_function_structure():
+    """NonUniformQuantization.__nonuni_quantize (scale, quantile init, nearest centroid * sign, inverse scale) executed
+    FROM THE REFERENCE SOURCE on numpy tensors vs the oracle restatement: bit-identical."""
+    import hashlib
+    gold = _ref_gold()['nonuniform_quantize']
+    assert len(gold) == 12
+    for g in gold:
+        rng = np.random.default_rng(g['seed'])
+        x = (rng.standard_normal(tuple(g['shape'])) * rng.choice([1e-2, 1.0, 9.0])).astype(np.float32)
+        q, _, _ = O.nonuniform_quantize(x, g['bits'])
+        q = np.ascontiguousarray(q, np.float32)
+        assert hashlib.sha256(q.tobytes()).hexdigest() == g['sha256'] and len(np.unique(q)) == g['distinct'], g
+
+
+def test_distillation_loss_wiring_matches_the_reference_function():
+    for g in _ref_gold()['distillation_loss']:
+        rng = np.random.default_rng(g['seed'])
+        s_ = (rng.standard_normal((g['n'], g['k'])) * 3).astype(np.float32)
+        t_ = (rng.standard_normal((g['n'], g['k'])) * 5).astype(np.float32)
+        loss, _ = O.distillation_loss(s_, t_, g['loss_w_dst'], g['tempr_dst'])
+        assert np.float32(loss).tobytes().hex() == g['value_f32_hex'], (g, float(loss))
