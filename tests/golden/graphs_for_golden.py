@@ -7,7 +7,7 @@ def build_graph(net, flags, dst=True):
     from pocketflow_b200 import graph as G
     from pocketflow_b200.flags import FLAGS
     FLAGS.reset()
-    mod = importlib.import_module('pocketflow_b200.nets.' + net)
+    mod = importlib.reload(importlib.import_module('pocketflow_b200.nets.' + net))   # re-DEFINE this net's flag defaults
     for k, v in flags.items():
         setattr(FLAGS, k, v)
     mh = mod.ModelHelper()

@@ -401,6 +401,39 @@ def main():
         v = dh.DistillationHelper.calc_loss(T(s_), T(t_))
         gold['distillation_loss'].append(dict(seed=5000 + ci, n=n, k=k, loss_w_dst=w, tempr_dst=tt,
                                               value_f32_hex=np.float32(v.a).tobytes().hex(), value=float(v.a)))
+    # ---- ModelHelper.calc_loss of every net on the path (a8): WHICH variables receive the L2 term (the name filter) and
+    # the default loss_w_dcy, by running the reference's calc_loss on the trainable-variable NAMES of this repo's graphs
+    from tests.golden.graphs_for_golden import GRAPHS, build_graph
+    l2_seen = []
+    tf.nn = types.SimpleNamespace(l2_loss=lambda v: (l2_seen.append(v.name), T(0.0))[1], softmax=tf.nn.softmax,
+                                  in_top_k=lambda *a: BT(np.zeros(1, bool)))
+    tf.add_n = lambda ts: T(sum(np.float32(t.a) for t in ts))
+    tf.losses = types.SimpleNamespace(softmax_cross_entropy=lambda labels, logits: T(0.0))
+    tf.argmax = lambda x, axis=1: T(np.zeros(1))
+    tf.equal = lambda a, b: BT(np.zeros(1, bool))
+    tf.reduce_mean = lambda x: T(0.0)
+    contrib.slim = types.SimpleNamespace()
+    stubs4 = dict(stubs3)
+    stubs4.update({'tensorflow.contrib': contrib, 'tensorflow.contrib.slim': contrib.slim})
+    stubs4.update({'nets': types.ModuleType('nets'), 'nets.abstract_model_helper': blank(AbstractModelHelper=object),
+                   'datasets': types.ModuleType('datasets'), 'datasets.cifar10_dataset': blank(Cifar10Dataset=object),
+                   'datasets.ilsvrc12_dataset': blank(Ilsvrc12Dataset=object),
+                   'utils.external': types.ModuleType('utils.external'), 'utils.external.resnet_model': types.ModuleType('rm'),
+                   'utils.external.mobilenet_v1': types.ModuleType('mv1'), 'utils.external.mobilenet_v2': types.ModuleType('mv2'),
+                   'utils.lrn_rate_utils': blank(setup_lrn_rate_piecewise_constant=None, setup_lrn_rate_exponential_decay=None)})
+    gold['calc_loss_l2'] = []
+    for gname, ref_file in [('resnet20_cifar10_dst', 'nets/resnet_at_cifar10.py'), ('mobilenet_v1_ilsvrc12', 'nets/mobilenet_at_ilsvrc12.py'),
+                            ('lenet_cifar10', 'nets/lenet_at_cifar10.py')]:
+        if hasattr(flags, 'loss_w_dcy'):
+            delattr(flags, 'loss_w_dcy')
+        mod = load(ref_file, 'ref_' + gname, stubs4)
+        net, fl, dst = GRAPHS[gname]
+        graph = build_graph(net, fl, dst)
+        tv = [types.SimpleNamespace(name=v.name) for v in graph.variables.values() if v.name.startswith('model/') and v.trainable]
+        del l2_seen[:]
+        mod.ModelHelper.calc_loss(types.SimpleNamespace(), T(np.zeros((1, 2))), T(np.zeros((1, 2))), tv)
+        gold['calc_loss_l2'].append(dict(graph=gname, loss_w_dcy=float(flags.loss_w_dcy), n_trainable=len(tv),
+                                         regularised=list(l2_seen)))
     json.dump(gold, open(OUT, 'w'), indent=1)
     print('wrote', OUT, {k: len(v) for k, v in gold.items() if isinstance(v, list)})
 

@@ -369,3 +369,36 @@ def test_distillation_loss_wiring_matches_the_reference_function():
         t_ = (rng.standard_normal((g['n'], g['k'])) * 5).astype(np.float32)
         loss, _ = O.distillation_loss(s_, t_, g['loss_w_dst'], g['tempr_dst'])
         assert np.float32(loss).tobytes().hex() == g['value_f32_hex'], (g, float(loss))
+
+
+def test_l2_regularised_variables_match_the_reference_calc_loss():
+    """ModelHelper.calc_loss of the reference (run under the stub on this repo's trainable-variable names): the set of
+    variables that receive the L2 term (name filter; MobileNet's slim BatchNorm parameters ARE regularised, SURVEY
+    A.6-9) and the default loss_w_dcy equal what this repo's ModelHelpers put into their LossSpec."""
+    import importlib
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from tests.golden.graphs_for_golden import GRAPHS
+    from pocketflow_b200 import graph as G
+    from pocketflow_b200.flags import FLAGS
+    for g in _ref_gold()['calc_loss_l2']:
+        net, flags, _ = GRAPHS[g['graph']]
+        FLAGS.reset()
+        mod = importlib.reload(importlib.import_module('pocketflow_b200.nets.' + net))   # re-DEFINE this net's defaults
+        for k, v in flags.items():
+            setattr(FLAGS, k, v)
+        mh = mod.ModelHelper()
+        gr = G.Graph()
+        with gr.as_default():
+            with G.variable_scope('data'):
+                im, lab = mh.build_dataset_train().get_next()
+            with G.variable_scope('model'):
+                out = mh.forward_train(im)
+                tv = [v for v in gr.variables.values() if v.name.startswith('model/') and v.trainable]
+                loss, _ = mh.calc_loss(lab, out, tv)
+        assert len(tv) == g['n_trainable']
+        mine = [(v.name, float(wd)) for v, wd in loss.l2.items()]
+        assert sorted(n for n, _ in mine) == sorted(g['regularised']), g['graph']
+        assert all(abs(wd - g['loss_w_dcy']) <= 1e-12 for _, wd in mine), (g['graph'], g['loss_w_dcy'])
+    FLAGS.reset()
