@@ -434,6 +434,69 @@ def main():
         mod.ModelHelper.calc_loss(types.SimpleNamespace(), T(np.zeros((1, 2))), T(np.zeros((1, 2))), tv)
         gold['calc_loss_l2'].append(dict(graph=gname, loss_w_dcy=float(flags.loss_w_dcy), n_trainable=len(tv),
                                          regularised=list(l2_seen)))
+    # ---- the ResNet ARCHITECTURE the reference builds (utils/external/resnet_model.py driven by the forward_fn of
+    # nets/resnet_at_cifar10.py / nets/resnet_at_ilsvrc12.py), recorded by executing the reference source with symbolic
+    # tensors: every conv (filters, kernel, stride, explicit padding), batch-norm (momentum, epsilon, training), ReLU,
+    # pooling, residual add, mean, dense — in order — to compare with the op list of this repo's graphs.
+    rec = []
+
+    class S(object):                                        # symbolic tensor: remembers pending explicit padding
+        def __init__(self, pad=None):
+            self.pad = pad
+
+        def __add__(self, o):
+            rec.append(('add',))
+            return S()
+
+    def layers_conv2d(inputs=None, filters=None, kernel_size=None, strides=1, padding='SAME', use_bias=True, **kw):
+        rec.append(('conv', int(filters), int(kernel_size), int(strides), padding.upper(),
+                    inputs.pad if inputs.pad else [0, 0, 0, 0], bool(use_bias)))
+        return S()
+
+    def layers_bn(inputs=None, axis=-1, momentum=0.99, epsilon=1e-3, center=True, scale=True, training=False, fused=None, **kw):
+        rec.append(('bn', float(momentum), float(epsilon), bool(training), bool(center), bool(scale)))
+        return S()
+
+    def tf_pad(inputs, paddings):
+        flat = [int(v) for row in paddings for v in row]
+        assert flat[:2] == [0, 0] and flat[-2:] == [0, 0], 'NHWC padding expected'
+        return S(pad=flat[2:6])                             # [top, bottom, left, right]
+    tf.layers = types.SimpleNamespace(
+        conv2d=layers_conv2d, batch_normalization=layers_bn,
+        max_pooling2d=lambda inputs=None, pool_size=None, strides=None, padding='SAME', **kw: (
+            rec.append(('maxpool', int(pool_size), int(strides), padding.upper())), S())[1],
+        dense=lambda inputs=None, units=None, **kw: (rec.append(('dense', int(units))), S())[1])
+    tf.pad = tf_pad
+    tf.nn = types.SimpleNamespace(relu=lambda x: (rec.append(('relu',)), S())[1])
+    tf.identity = lambda x, name=None: x
+    tf.reduce_mean = lambda x, axes=None, keepdims=False: (rec.append(('mean', list(axes), bool(keepdims))), S())[1]
+    tf.squeeze = lambda x, axes=None: x
+    tf.transpose = lambda x, perm: x
+    tf.variance_scaling_initializer = lambda *a, **k: None
+    tf.test = types.SimpleNamespace(is_built_with_cuda=lambda: False)
+    tf.float16 = 'float16'
+
+    class VS(Ctx):
+        pass
+    tf.variable_scope = lambda *a, **k: VS()
+    rm = load('utils/external/resnet_model.py', 'ref_resnet_model', stubs4)
+    ext = types.ModuleType('utils.external')
+    ext.resnet_model = rm
+    stubs5 = dict(stubs4)
+    stubs5.update({'utils.external': ext, 'utils.external.resnet_model': rm})
+    gold['resnet_architecture'] = []
+    for ref_file, size, classes in [('nets/resnet_at_cifar10.py', 20, 10), ('nets/resnet_at_cifar10.py', 32, 10),
+                                    ('nets/resnet_at_ilsvrc12.py', 18, 1001), ('nets/resnet_at_ilsvrc12.py', 50, 1001)]:
+        for attr in ('resnet_size', 'nb_classes'):
+            if hasattr(flags, attr):
+                delattr(flags, attr)
+        mod = load(ref_file, 'ref_net_%d' % size, stubs5)
+        flags.resnet_size, flags.nb_classes = size, classes
+        for is_train in (True, False):
+            del rec[:]
+            mod.forward_fn(S(), is_train, 'channels_last')
+            gold['resnet_architecture'].append(dict(net=os.path.basename(ref_file)[:-3], resnet_size=size, nb_classes=classes,
+                                                    is_train=is_train, layers=[list(r) for r in rec]))
     json.dump(gold, open(OUT, 'w'), indent=1)
     print('wrote', OUT, {k: len(v) for k, v in gold.items() if isinstance(v, list)})
 

@@ -402,3 +402,103 @@ def test_l2_regularised_variables_match_the_reference_calc_loss():
         assert sorted(n for n, _ in mine) == sorted(g['regularised']), g['graph']
         assert all(abs(wd - g['loss_w_dcy']) <= 1e-12 for _, wd in mine), (g['graph'], g['loss_w_dcy'])
     FLAGS.reset()
+
+
+def _canonical_layers(graph_ops):
+    """This repo's op list in the vocabulary of the recorded reference architecture."""
+    out = []
+    for op in graph_ops:
+        t = op.type
+        if t == 'Conv2D':
+            (kh, kw), (sh, sw), (pt, pl) = op.attrs['ksize'], op.attrs['strides'], op.attrs['pad']
+            out.append(('conv', op.output.shape[-1], kh, sh, pt, pl, op.output.shape[1], 'bias' in op.vars))
+        elif t == 'FusedBatchNorm':
+            out.append(('bn', float(op.attrs['momentum']), float(op.attrs['epsilon']), bool(op.attrs['training'])))
+        elif t == 'Relu':
+            out.append(('relu',))
+        elif t == 'MaxPool':
+            (kh, kw), (sh, sw), (pt, pl) = op.attrs['ksize'], op.attrs['strides'], op.attrs['pad']
+            out.append(('maxpool', kh, sh, pt, pl, op.output.shape[1]))
+        elif t == 'Add':
+            out.append(('add',))
+        elif t == 'Mean':
+            out.append(('mean',))
+        elif t == 'MatMul':
+            out.append(('dense', op.output.shape[-1]))
+    return out
+
+
+def _same_pad(h, k, s):
+    total = max((-(-h // s) - 1) * s + k - h, 0)
+    return total // 2, -(-h // s)
+
+
+@pytest.mark.parametrize('idx', range(8))
+def test_resnet_architecture_matches_the_reference_source(idx):
+    """The layer sequence the reference's resnet_model.py + forward_fn emit (recorded by executing them with symbolic
+    tensors) vs the op list of this repo's graphs: every conv's filters / kernel / stride / effective padding / output
+    size, BN momentum-epsilon-mode, ReLU, pooling, residual adds, mean, dense — same order, same parameters."""
+    import importlib
+    from pocketflow_b200 import graph as G
+    from pocketflow_b200.flags import FLAGS
+    g = _ref_gold()['resnet_architecture'][idx]
+    FLAGS.reset()
+    mod = importlib.reload(importlib.import_module('pocketflow_b200.nets.' + g['net']))
+    FLAGS.resnet_size, FLAGS.nb_classes, FLAGS.batch_size = g['resnet_size'], g['nb_classes'], 2
+    mh = mod.ModelHelper()
+    gr = G.Graph()
+    with gr.as_default():
+        with G.variable_scope('data'):
+            im, _ = mh.build_dataset_train().get_next()
+        with G.variable_scope('model'):
+            (mh.forward_train if g['is_train'] else mh.forward_eval)(im)
+    mine = _canonical_layers(gr.ops)
+    h = im.shape[1]
+    want = []
+    for r in g['layers']:
+        if r[0] == 'conv':
+            _, f, k, s, padding, pad, bias = r
+            if padding == 'SAME':
+                pt, oh = _same_pad(h, k, s)
+                pl = pt
+            else:
+                pt, pl = pad[0], pad[2]
+                oh = (h + pad[0] + pad[1] - k) // s + 1
+            want.append(('conv', f, k, s, pt, pl, oh, bias))
+            h_next = oh
+        elif r[0] == 'bn':
+            want.append(('bn', r[1], r[2], r[3]))
+            h_next = h
+        elif r[0] == 'maxpool':
+            _, k, s, padding = r
+            pt, oh = _same_pad(h, k, s) if padding == 'SAME' else (0, (h - k) // s + 1)
+            want.append(('maxpool', k, s, pt, pt, oh))
+            h_next = oh
+        elif r[0] == 'dense':
+            want.append(('dense', r[1]))
+            h_next = h
+        else:
+            want.append((r[0],))
+            h_next = h
+        # shortcut convs run on the block INPUT: track the spatial size per op from this repo's own tensors instead
+        h = h_next
+    # spatial sizes of the reference records are re-derived per layer from this repo's graph (projection shortcuts branch
+    # off the block input), so compare everything except the derived sizes first, then the sizes this repo produces
+    strip = lambda L: [tuple(x[:4]) if x[0] == 'conv' else (tuple(x[:3]) if x[0] == 'maxpool' else x) for x in L]   # noqa: E731
+    assert strip(mine) == strip(want), g['net']
+    # effective padding and output size of every conv / pool: the reference's rule (explicit fixed padding + VALID, or SAME)
+    # applied to the input size THIS repo's op actually sees
+    my_ops = [op for op in gr.ops if op.type in ('Conv2D', 'MaxPool')]
+    ref_ops = [r for r in g['layers'] if r[0] in ('conv', 'maxpool')]
+    assert len(my_ops) == len(ref_ops)
+    for op, r in zip(my_ops, ref_ops):
+        hin = op.inputs[0].shape[1]
+        k, s_ = (r[2], r[3]) if r[0] == 'conv' else (r[1], r[2])
+        padding = r[4] if r[0] == 'conv' else r[3]
+        if padding == 'SAME':
+            pt, oh = _same_pad(hin, k, s_)
+        else:
+            pad = r[5]
+            pt, oh = pad[0], (hin + pad[0] + pad[1] - k) // s_ + 1
+        assert tuple(op.attrs['pad']) == (pt, pt) and op.output.shape[1] == oh and op.output.shape[2] == oh, (op.name, r)
+    FLAGS.reset()
