@@ -497,6 +497,117 @@ def main():
             mod.forward_fn(S(), is_train, 'channels_last')
             gold['resnet_architecture'].append(dict(net=os.path.basename(ref_file)[:-3], resnet_size=size, nb_classes=classes,
                                                     is_train=is_train, layers=[list(r) for r in rec]))
+    # ---- the MobileNet-v1 ARCHITECTURE (utils/external/mobilenet_v1.py driven by nets/mobilenet_at_ilsvrc12.py:forward_fn),
+    # recorded by executing the reference source against a stub of tf.contrib.slim with arg_scope semantics and
+    # shape-tracking symbolic tensors
+    mrec = []
+
+    class S4(object):
+        def __init__(self, shape):
+            self.shape4 = list(shape)
+
+        def get_shape(self):
+            return types.SimpleNamespace(as_list=lambda: list(self.shape4))
+
+    def out_hw(h, k, s, padding):
+        return -(-h // s) if padding == 'SAME' else (h - k) // s + 1
+    scope_stack = [{}]
+
+    class ArgScope(object):
+        def __init__(self, fns_or_scope, kw):
+            cur = {k: dict(v) for k, v in scope_stack[-1].items()}
+            if isinstance(fns_or_scope, dict):
+                for k, v in fns_or_scope.items():
+                    cur.setdefault(k, {}).update(v)
+            else:
+                for f in fns_or_scope:
+                    cur.setdefault(f.__name__, {}).update(kw)
+            self.scope = cur
+
+        def __enter__(self):
+            scope_stack.append(self.scope)
+            return self.scope
+
+        def __exit__(self, *a):
+            scope_stack.pop()
+            return False
+
+    def scoped(fn):
+        def wrapper(*a, **kw):
+            merged = dict(scope_stack[-1].get(fn.__name__, {}))
+            merged.update(kw)
+            return fn(*a, **merged)
+        wrapper.__name__ = fn.__name__
+        return wrapper
+
+    def _after(net, normalizer_fn, activation_fn):
+        if normalizer_fn is not None:
+            bn = scope_stack[-1].get('batch_norm', {})
+            mrec.append(('bn', float(bn.get('decay', 0.999)), float(bn.get('epsilon', 0.001)), bool(bn.get('is_training', True)),
+                         bool(bn.get('center', True)), bool(bn.get('scale', False))))
+        if activation_fn is not None:
+            mrec.append((activation_fn.__name__,))
+        return net
+
+    @scoped
+    def conv2d(inputs, num_outputs, kernel_size, stride=1, padding='SAME', activation_fn=None, normalizer_fn=None, scope=None, **kw):
+        n, h, w, c = inputs.shape4
+        k = kernel_size if isinstance(kernel_size, int) else kernel_size[0]
+        mrec.append(('conv', scope, int(num_outputs), int(k), int(stride), padding, normalizer_fn is None))
+        return _after(S4([n, out_hw(h, k, stride, padding), out_hw(w, k, stride, padding), num_outputs]), normalizer_fn, activation_fn)
+
+    @scoped
+    def separable_conv2d(inputs, num_outputs, kernel_size, depth_multiplier=1, stride=1, rate=1, padding='SAME', activation_fn=None,
+                         normalizer_fn=None, scope=None, **kw):
+        assert num_outputs is None and rate == 1
+        n, h, w, c = inputs.shape4
+        k = kernel_size if isinstance(kernel_size, int) else kernel_size[0]
+        mrec.append(('dwconv', scope, int(k), int(stride), padding, int(depth_multiplier)))
+        return _after(S4([n, out_hw(h, k, stride, padding), out_hw(w, k, stride, padding), c * depth_multiplier]), normalizer_fn, activation_fn)
+
+    def batch_norm(*a, **k):
+        raise AssertionError('batch_norm is only used as normalizer_fn')
+
+    @scoped
+    def dropout(inputs, keep_prob=0.5, is_training=True, scope=None, **kw):
+        mrec.append(('dropout', float(keep_prob), bool(is_training)))
+        return inputs
+
+    def avg_pool2d(inputs, kernel_size, stride=2, padding='VALID', scope=None):
+        n, h, w, c = inputs.shape4
+        mrec.append(('avgpool', [int(v) for v in kernel_size], padding))
+        return S4([n, out_hw(h, kernel_size[0], stride, padding), out_hw(w, kernel_size[1], stride, padding), c])
+
+    def relu6(x):
+        return x
+    slim = types.SimpleNamespace(conv2d=conv2d, separable_conv2d=separable_conv2d, batch_norm=batch_norm, dropout=dropout,
+                                 avg_pool2d=avg_pool2d, arg_scope=lambda f, **kw: ArgScope(f, kw))
+    contrib.slim = slim
+    contrib.layers = types.SimpleNamespace(softmax=lambda logits, scope=None: logits, l2_regularizer=lambda wd: ('l2', wd))
+    tf.nn = types.SimpleNamespace(relu6=relu6, relu=lambda x: x)
+    tf.GraphKeys = types.SimpleNamespace(UPDATE_OPS='update_ops')
+    tf.truncated_normal_initializer = lambda stddev=1.0: ('tn', stddev)
+    tf.variable_scope = lambda *a, **k: Ctx()
+    tf.squeeze = lambda x, axes=None, name=None: x
+    tf.reduce_mean = lambda x, axes=None, keep_dims=False, name=None: (mrec.append(('mean', list(axes))), S4([x.shape4[0], 1, 1, x.shape4[3]]))[1]
+    stubs6 = dict(stubs4)
+    stubs6.update({'tensorflow.contrib': contrib, 'tensorflow.contrib.slim': slim})
+    mv1 = load('utils/external/mobilenet_v1.py', 'ref_mobilenet_v1', stubs6)
+    ext2 = types.ModuleType('utils.external')
+    ext2.mobilenet_v1, ext2.mobilenet_v2 = mv1, types.ModuleType('mv2')
+    stubs6.update({'utils.external': ext2, 'utils.external.mobilenet_v1': mv1, 'utils.external.mobilenet_v2': ext2.mobilenet_v2})
+    for attr in ('nb_classes', 'mobilenet_version', 'mobilenet_depth_mult'):
+        if hasattr(flags, attr):
+            delattr(flags, attr)
+    mbn = load('nets/mobilenet_at_ilsvrc12.py', 'ref_mobilenet_net', stubs6)
+    gold['mobilenet_architecture'] = []
+    flags.nb_classes = 1001
+    for is_train in (True, False):
+        del mrec[:]
+        mbn.forward_fn(S4([2, 224, 224, 3]), is_train)
+        gold['mobilenet_architecture'].append(dict(is_train=is_train, mobilenet_version=int(flags.mobilenet_version),
+                                                   depth_mult=float(flags.mobilenet_depth_mult),
+                                                   layers=[list(r) for r in mrec]))
     json.dump(gold, open(OUT, 'w'), indent=1)
     print('wrote', OUT, {k: len(v) for k, v in gold.items() if isinstance(v, list)})
 

@@ -502,3 +502,60 @@ def test_resnet_architecture_matches_the_reference_source(idx):
             pt, oh = pad[0], (hin + pad[0] + pad[1] - k) // s_ + 1
         assert tuple(op.attrs['pad']) == (pt, pt) and op.output.shape[1] == oh and op.output.shape[2] == oh, (op.name, r)
     FLAGS.reset()
+
+
+@pytest.mark.parametrize('idx', [0, 1])
+def test_mobilenet_v1_architecture_matches_the_reference_source(idx):
+    """utils/external/mobilenet_v1.py + forward_fn executed against a slim stub (arg_scope semantics, shape-tracking
+    symbolic tensors) vs this repo's MobileNet-v1 graph: layer order, scopes, filters, kernels, strides, depthwise
+    multiplier, BN decay 0.9997 / epsilon 1e-3 / mode, ReLU6, 7x7 average pool (= the global mean at 224x224), logits conv
+    with bias.  Flagged deviation: the reference's Dropout_1b (keep_prob 0.999, training only) is the identity here."""
+    import importlib
+    from pocketflow_b200 import graph as G
+    from pocketflow_b200.flags import FLAGS
+    g = _ref_gold()['mobilenet_architecture'][idx]
+    assert g['mobilenet_version'] == 1 and g['depth_mult'] == 1.0
+    FLAGS.reset()
+    mod = importlib.reload(importlib.import_module('pocketflow_b200.nets.mobilenet_at_ilsvrc12'))
+    FLAGS.batch_size, FLAGS.nb_classes = 2, 1001
+    mh = mod.ModelHelper()
+    gr = G.Graph()
+    with gr.as_default():
+        with G.variable_scope('data'):
+            im, _ = mh.build_dataset_train().get_next()
+        with G.variable_scope('model'):
+            (mh.forward_train if g['is_train'] else mh.forward_eval)(im)
+    mine = []
+    for op in gr.ops:
+        scope = op.name.split('/')[-2] if '/' in op.name else ''
+        if op.type == 'Conv2D':
+            mine.append(['conv', scope, op.output.shape[-1], op.attrs['ksize'][0], op.attrs['strides'][0], 'bias' in op.vars])
+        elif op.type == 'DepthwiseConv2dNative':
+            mine.append(['dwconv', scope, op.attrs['ksize'][0], op.attrs['strides'][0]])
+        elif op.type == 'FusedBatchNorm':
+            mine.append(['bn', float(op.attrs['momentum']), float(op.attrs['epsilon']), bool(op.attrs['training'])])
+        elif op.type == 'Relu6':
+            mine.append(['relu6'])
+        elif op.type == 'Mean':
+            assert op.inputs[0].shape[1:3] == (7, 7)
+            mine.append(['avgpool7'])
+    want = []
+    for r in g['layers']:
+        if r[0] == 'conv':
+            assert r[5] == 'SAME'
+            want.append(['conv', r[1], r[2], r[3], r[4], r[6]])
+        elif r[0] == 'dwconv':
+            assert r[4] == 'SAME' and r[5] == 1
+            want.append(['dwconv', r[1], r[2], r[3]])
+        elif r[0] == 'bn':
+            assert r[4] and r[5]                                   # center and scale
+            want.append(['bn', r[1], r[2], r[3]])
+        elif r[0] == 'avgpool':
+            assert r[1] == [7, 7] and r[2] == 'VALID'
+            want.append(['avgpool7'])
+        elif r[0] == 'dropout':
+            assert r[1] == 0.999                                   # identity here (flagged deviation), identity in eval anyway
+        else:
+            want.append([r[0]])
+    assert mine == want
+    FLAGS.reset()
