@@ -608,6 +608,15 @@ def main():
         gold['mobilenet_architecture'].append(dict(is_train=is_train, mobilenet_version=int(flags.mobilenet_version),
                                                    depth_mult=float(flags.mobilenet_depth_mult),
                                                    layers=[list(r) for r in mrec]))
+    # ---- get_maskable_vars (learners/weight_sparsification/utils.py:21-41): which trainable variables the
+    # WeightSparseLearner masks, run on the trainable-variable names of this repo's graphs
+    wsu = load('learners/weight_sparsification/utils.py', 'ref_ws_utils', stubs3)
+    gold['ws_maskable_vars'] = []
+    for gname in ('resnet20_cifar10_dst', 'mobilenet_v1_ilsvrc12', 'lenet_cifar10'):
+        net, fl, dst = GRAPHS[gname]
+        graph = build_graph(net, fl, dst)
+        tv = [types.SimpleNamespace(name=v.name) for v in graph.variables.values() if v.name.startswith('model/') and v.trainable]
+        gold['ws_maskable_vars'].append(dict(graph=gname, n_trainable=len(tv), maskable=[v.name for v in wsu.get_maskable_vars(tv)]))
     json.dump(gold, open(OUT, 'w'), indent=1)
     print('wrote', OUT, {k: len(v) for k, v in gold.items() if isinstance(v, list)})
 

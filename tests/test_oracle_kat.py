@@ -559,3 +559,19 @@ def test_mobilenet_v1_architecture_matches_the_reference_source(idx):
             want.append([r[0]])
     assert mine == want
     FLAGS.reset()
+
+
+def test_maskable_variable_selection_matches_the_reference_function():
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from tests.golden.graphs_for_golden import GRAPHS, build_graph
+    from pocketflow_b200.learners.weight_sparsification.utils import get_maskable_vars
+    from pocketflow_b200.flags import FLAGS
+    for g in _ref_gold()['ws_maskable_vars']:
+        net, flags, dst = GRAPHS[g['graph']]
+        graph = build_graph(net, flags, dst)
+        tv = [v for v in graph.variables.values() if v.name.startswith('model/') and v.trainable]
+        assert len(tv) == g['n_trainable']
+        assert [v.name for v in get_maskable_vars(tv)] == g['maskable'], g['graph']
+    FLAGS.reset()
