@@ -135,7 +135,8 @@ def main():
     stubs2.update({'tensorflow.contrib': contrib, 'tensorflow.contrib.graph_editor': contrib.graph_editor})
     uqu = load('learners/uniform_quantization/utils.py', 'ref_uq_utils', stubs2)
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
-    from tests.golden.graphs_for_golden import op_lists
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from graphs_for_golden import op_lists
     gold['uq_op_selection'] = []
     for name, ops_ in op_lists().items():
         fake_ops = [types.SimpleNamespace(type=t, name=n) for t, n in ops_]
@@ -403,7 +404,7 @@ def main():
                                               value_f32_hex=np.float32(v.a).tobytes().hex(), value=float(v.a)))
     # ---- ModelHelper.calc_loss of every net on the path (a8): WHICH variables receive the L2 term (the name filter) and
     # the default loss_w_dcy, by running the reference's calc_loss on the trainable-variable NAMES of this repo's graphs
-    from tests.golden.graphs_for_golden import GRAPHS, build_graph
+    from graphs_for_golden import GRAPHS, build_graph
     l2_seen = []
     tf.nn = types.SimpleNamespace(l2_loss=lambda v: (l2_seen.append(v.name), T(0.0))[1], softmax=tf.nn.softmax,
                                   in_top_k=lambda *a: BT(np.zeros(1, bool)))

@@ -269,8 +269,8 @@ def test_quantized_op_selection_matches_the_reference_functions():
     last matmul kept at full precision unless quantize_all_layers."""
     import sys
     import os
-    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    from tests.golden.graphs_for_golden import GRAPHS, build_graph
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+    from graphs_for_golden import GRAPHS, build_graph
     from pocketflow_b200.learners.uniform_quantization.utils import UniformQuantization
     gold = _ref_gold()['uq_op_selection']
     assert len(gold) == 2 * len(GRAPHS)
@@ -378,8 +378,8 @@ def test_l2_regularised_variables_match_the_reference_calc_loss():
     import importlib
     import os
     import sys
-    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    from tests.golden.graphs_for_golden import GRAPHS
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+    from graphs_for_golden import GRAPHS
     from pocketflow_b200 import graph as G
     from pocketflow_b200.flags import FLAGS
     for g in _ref_gold()['calc_loss_l2']:
@@ -564,8 +564,8 @@ def test_mobilenet_v1_architecture_matches_the_reference_source(idx):
 def test_maskable_variable_selection_matches_the_reference_function():
     import os
     import sys
-    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    from tests.golden.graphs_for_golden import GRAPHS, build_graph
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+    from graphs_for_golden import GRAPHS, build_graph
     from pocketflow_b200.learners.weight_sparsification.utils import get_maskable_vars
     from pocketflow_b200.flags import FLAGS
     for g in _ref_gold()['ws_maskable_vars']:
