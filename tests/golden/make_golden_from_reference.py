@@ -618,6 +618,30 @@ def main():
         graph = build_graph(net, fl, dst)
         tv = [types.SimpleNamespace(name=v.name) for v in graph.variables.values() if v.name.startswith('model/') and v.trainable]
         gold['ws_maskable_vars'].append(dict(graph=gname, n_trainable=len(tv), maskable=[v.name for v in wsu.get_maskable_vars(tv)]))
+    # ---- LeNet (nets/lenet_at_cifar10.py:forward_fn) with the same recorder
+    lrec = []
+
+    def l_conv(inputs, filters, kernel_size, strides=1, padding='valid', use_bias=True, **kw):
+        k = kernel_size if isinstance(kernel_size, int) else kernel_size[0]
+        lrec.append(('conv', int(filters), int(k), int(strides), padding.upper(), bool(use_bias)))
+        return S()
+
+    def l_pool(inputs, pool_size, strides, padding='valid', **kw):
+        k = pool_size if isinstance(pool_size, int) else pool_size[0]
+        lrec.append(('maxpool', int(k), int(strides), padding.upper()))
+        return S()
+    tf.layers = types.SimpleNamespace(conv2d=l_conv, max_pooling2d=l_pool,
+                                      flatten=lambda x, name=None: (lrec.append(('flatten',)), S())[1],
+                                      dense=lambda x, units, name=None, **kw: (lrec.append(('dense', int(units))), S())[1])
+    tf.nn = types.SimpleNamespace(relu=lambda x, name=None: (lrec.append(('relu',)), S())[1],
+                                  softmax=lambda x, name=None: (lrec.append(('softmax',)), S())[1])
+    for attr in ('nb_classes',):
+        if hasattr(flags, attr):
+            delattr(flags, attr)
+    ln = load('nets/lenet_at_cifar10.py', 'ref_lenet_net', stubs5)
+    flags.nb_classes = 10
+    ln.forward_fn(S(), 'channels_last')
+    gold['lenet_architecture'] = [list(r) for r in lrec]
     json.dump(gold, open(OUT, 'w'), indent=1)
     print('wrote', OUT, {k: len(v) for k, v in gold.items() if isinstance(v, list)})
 

@@ -575,3 +575,37 @@ def test_maskable_variable_selection_matches_the_reference_function():
         assert len(tv) == g['n_trainable']
         assert [v.name for v in get_maskable_vars(tv)] == g['maskable'], g['graph']
     FLAGS.reset()
+
+
+def test_lenet_architecture_matches_the_reference_source():
+    import importlib
+    from pocketflow_b200 import graph as G
+    from pocketflow_b200.flags import FLAGS
+    FLAGS.reset()
+    mod = importlib.reload(importlib.import_module('pocketflow_b200.nets.lenet_at_cifar10'))
+    FLAGS.batch_size = 2
+    mh = mod.ModelHelper()
+    gr = G.Graph()
+    with gr.as_default():
+        with G.variable_scope('data'):
+            im, _ = mh.build_dataset_train().get_next()
+        with G.variable_scope('model'):
+            mh.forward_train(im)
+    mine = []
+    for op in gr.ops:
+        if op.type == 'Conv2D':
+            assert tuple(op.attrs['pad']) == (0, 0)                                  # 'valid'
+            mine.append(['conv', op.output.shape[-1], op.attrs['ksize'][0], op.attrs['strides'][0], 'VALID', 'bias' in op.vars])
+        elif op.type == 'MaxPool':
+            assert tuple(op.attrs['pad']) == (0, 0)
+            mine.append(['maxpool', op.attrs['ksize'][0], op.attrs['strides'][0], 'VALID'])
+        elif op.type == 'Relu':
+            mine.append(['relu'])
+        elif op.type == 'MatMul':
+            mine.append(['dense', op.output.shape[-1]])
+        elif op.type == 'Softmax':
+            mine.append(['softmax'])
+        elif op.type == 'Reshape':
+            mine.append(['flatten'])
+    assert mine == _ref_gold()['lenet_architecture']
+    FLAGS.reset()
