@@ -584,6 +584,7 @@ def test_lenet_architecture_matches_the_reference_source():
     FLAGS.reset()
     mod = importlib.reload(importlib.import_module('pocketflow_b200.nets.lenet_at_cifar10'))
     FLAGS.batch_size = 2
+    FLAGS.nb_classes = 10          # the flag's default belongs to whichever dataset module was imported first
     mh = mod.ModelHelper()
     gr = G.Graph()
     with gr.as_default():
