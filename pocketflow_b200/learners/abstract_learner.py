@@ -14,32 +14,52 @@ from ..flags import FLAGS, DEFINE_string, DEFINE_integer, DEFINE_boolean
 from ..utils.misc_utils import auto_barrier as auto_barrier_impl
 from ..utils.misc_utils import is_primary_worker as is_primary_worker_impl
 from ..utils.multi_gpu_wrapper import MultiGpuWrapper as mgw
+from ..utils import tf_bundle
 
 DEFINE_string('model_http_url', None, 'HTTP/HTTPS url for remote model files')
 DEFINE_integer('summ_step', 100, 'summarizaton step size')
 DEFINE_integer('save_step', 10000, 'model saving step size')
 DEFINE_string('save_path', './models/model.ckpt', 'model\'s save path')
 DEFINE_string('save_path_eval', './models_eval/model.ckpt', 'model\'s save path for evaluation')
+DEFINE_string('ckpt_format', 'npz', 'checkpoint format to write: npz | tf (TensorFlow V2 bundle)')
 DEFINE_boolean('enbl_dst', False, 'enable the distillation loss for training')
 DEFINE_boolean('enbl_warm_start', False, 'enable warm start for training')
 
 
 def latest_checkpoint(ckpt_dir):
-    """tf.train.latest_checkpoint for the .npz checkpoints this build writes."""
+    """tf.train.latest_checkpoint over both formats this build reads: its own .npz files and TensorFlow V2 bundles
+    named by the directory's `checkpoint` state file (what the reference's savers and model archives contain);
+    the newer of the two wins."""
     files = sorted(glob.glob(os.path.join(ckpt_dir, '*.npz')), key=os.path.getmtime)
-    return files[-1] if files else None
+    native = files[-1] if files else None
+    bundle = tf_bundle.latest_checkpoint(ckpt_dir)
+    if bundle is not None and (native is None or os.path.getmtime(bundle + '.index') >= os.path.getmtime(native)):
+        return bundle
+    return native
 
 
 def save_checkpoint(path, state, step=None):
+    """tf.train.Saver.save(sess, path, global_step): `--ckpt_format npz` (default) or `tf`, the V2 bundle the
+    reference's own tools restore (variable names without the ':0' output suffix, plus `global_step`)."""
     os.makedirs(os.path.dirname(path) or '.', exist_ok=True)
+    if FLAGS.ckpt_format == 'tf':
+        tensors = {(k[:-2] if k.endswith(':0') else k): v for k, v in state.items()}
+        if step is not None:
+            tensors.setdefault('global_step', np.asarray(step, np.int64))
+        return tf_bundle.save(path, tensors, step)
+    if FLAGS.ckpt_format != 'npz':
+        raise ValueError('unknown --ckpt_format %r (npz | tf)' % FLAGS.ckpt_format)
     fn = path + ('-%d' % step if step is not None else '') + '.npz'
     np.savez(fn, **{k.replace('/', '|'): v for k, v in state.items()})
     return fn
 
 
 def load_checkpoint(fn):
-    d = np.load(fn)
-    return {k.replace('|', '/'): d[k] for k in d.files}
+    """{variable name (with ':0'): array} from either format; `fn` is what latest_checkpoint returned."""
+    if fn.endswith('.npz'):
+        d = np.load(fn)
+        return {k.replace('|', '/'): d[k] for k in d.files}
+    return {k + ':0': v for k, v in tf_bundle.load(fn).items()}
 
 
 class AbstractLearner(ABC):  # pylint: disable=too-many-instance-attributes
