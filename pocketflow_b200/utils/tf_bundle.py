@@ -82,34 +82,47 @@ def _zero_operator(nbytes):
     return result
 
 
-def crc32c(data, crc=0):
-    """CRC-32C (Castagnoli) of `data`, continuing from a previous value `crc` (tensorflow/core/lib/hash/crc32c.h
-    Extend/Value).  Large inputs run as many lanes in lock-step with numpy and are folded with the zero-shift
-    operator (the register update is GF(2)-linear in (state, data))."""
-    buf = np.frombuffer(memoryview(data).cast('B'), np.uint8) if not isinstance(data, np.ndarray) \
-        else np.ascontiguousarray(data).view(np.uint8).reshape(-1)
-    state = (crc ^ 0xffffffff) & 0xffffffff
-    n = buf.size
-    lanes = min(8192, n // 256)
-    if lanes >= 2:
-        m = n // lanes
-        body = buf[:lanes * m].reshape(lanes, m)
-        st = np.zeros(lanes, np.uint32)
-        st[0] = state
-        for j in range(m):
-            st = _T[(st ^ body[:, j]) & 0xff] ^ (st >> 8)
-        cols = _zero_operator(m)
-        tabs = np.zeros((4, 256), np.uint32)                    # byte-sliced form of the operator
+LANE_BYTES = 256
+CHUNK_BYTES = 1 << 21
+_FOLD = []          # byte-sliced tables of the 'LANE_BYTES zero bytes' operator, built on first use
+
+
+def _fold_tables():
+    if not _FOLD:
+        cols = _zero_operator(LANE_BYTES)
+        tabs = np.zeros((4, 256), np.uint32)
         for k in range(4):
             for j in range(8):
                 bit = 1 << j
                 tabs[k, bit:2 * bit] = tabs[k, :bit] ^ np.uint32(cols[8 * k + j])
-        t0, t1, t2, t3 = ([int(v) for v in tabs[k]] for k in range(4))
-        acc = int(st[0])
-        for v in st[1:]:
-            acc = t0[acc & 0xff] ^ t1[(acc >> 8) & 0xff] ^ t2[(acc >> 16) & 0xff] ^ t3[acc >> 24] ^ int(v)
+        _FOLD.extend([int(v) for v in tabs[k]] for k in range(4))
+    return _FOLD
+
+
+def crc32c(data, crc=0):
+    """CRC-32C (Castagnoli) of `data`, continuing from a previous value `crc` (tensorflow/core/lib/hash/crc32c.h
+    Extend/Value).  Inputs of more than a few lanes run as LANE_BYTES-long lanes in lock-step with numpy and are
+    folded with the zero-shift operator (the register update is GF(2)-linear in (state, data))."""
+    buf = np.frombuffer(memoryview(data).cast('B'), np.uint8) if not isinstance(data, np.ndarray) \
+        else np.ascontiguousarray(data).view(np.uint8).reshape(-1)
+    state = (crc ^ 0xffffffff) & 0xffffffff
+    while buf.size > CHUNK_BYTES:                              # cache-sized pieces, chained through the register
+        state = crc32c(buf[:CHUNK_BYTES], state ^ 0xffffffff) ^ 0xffffffff
+        buf = buf[CHUNK_BYTES:]
+    lanes = buf.size // LANE_BYTES
+    if lanes >= 4:
+        body = np.ascontiguousarray(buf[:lanes * LANE_BYTES].reshape(lanes, LANE_BYTES).T)
+        st = np.zeros(lanes, np.uint32)
+        st[0] = state
+        for j in range(LANE_BYTES):
+            st = _T[(st ^ body[j]) & 0xff] ^ (st >> 8)
+        t0, t1, t2, t3 = _fold_tables()
+        lane_states = st.tolist()
+        acc = lane_states[0]
+        for v in lane_states[1:]:
+            acc = t0[acc & 0xff] ^ t1[(acc >> 8) & 0xff] ^ t2[(acc >> 16) & 0xff] ^ t3[acc >> 24] ^ v
         state = acc
-        buf = buf[lanes * m:]
+        buf = buf[lanes * LANE_BYTES:]
     state = _raw_update(state, buf.tobytes())
     return state ^ 0xffffffff
 

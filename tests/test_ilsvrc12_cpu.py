@@ -1,0 +1,181 @@
+"""ILSVRC-12 input pipeline without TensorFlow: TFRecord framing, tf.train.Example parsing,
+the reference's eval / training preprocessing and the shuffled, sharded, prefetched stream."""
+import io
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from pocketflow_b200.utils import tf_record as R
+from pocketflow_b200.utils.tf_bundle import crc32c, mask_crc
+
+PIL = pytest.importorskip('PIL.Image')
+
+
+def _jpeg(h, w, seed, mode='RGB'):
+    rng = np.random.RandomState(seed)
+    base = rng.randint(0, 256, (h // 8 + 1, w // 8 + 1, 3)).astype(np.uint8)
+    img = PIL.fromarray(np.kron(base, np.ones((8, 8, 1), np.uint8))[:h, :w])
+    if mode != 'RGB':
+        img = img.convert(mode)
+    b = io.BytesIO()
+    img.save(b, format='JPEG', quality=92)
+    return b.getvalue()
+
+
+def _example(jpeg, label, boxes=()):
+    boxes = np.asarray(boxes, np.float32).reshape(-1, 4)
+    return R.encode_example({
+        'image/encoded': jpeg, 'image/class/label': [label], 'image/class/text': b'n0000',
+        'image/object/bbox/ymin': boxes[:, 0], 'image/object/bbox/xmin': boxes[:, 1],
+        'image/object/bbox/ymax': boxes[:, 2], 'image/object/bbox/xmax': boxes[:, 3]})
+
+
+def test_record_framing_bytes_and_corruption(tmp_path):
+    p = str(tmp_path / 'a.tfrecord')
+    payloads = [b'', b'x', bytes(range(256)) * 5]
+    R.write_records(p, payloads)
+    raw = open(p, 'rb').read()
+    # first record, spelled out: length 0, crc of the 8 length bytes, no data, crc of the empty string
+    assert raw[:16] == struct.pack('<Q', 0) + struct.pack('<I', mask_crc(crc32c(bytes(8)))) + struct.pack('<I', mask_crc(0))
+    assert list(R.read_records(p)) == payloads
+    for pos in (3, 9, 20, len(raw) - 2):
+        bad = bytearray(raw)
+        bad[pos] ^= 4
+        open(p, 'wb').write(bad)
+        with pytest.raises(ValueError):
+            list(R.read_records(p))
+    open(p, 'wb').write(raw[:-5])
+    with pytest.raises(ValueError, match='truncated'):
+        list(R.read_records(p))
+
+
+def test_example_parsing_packed_and_unpacked():
+    ex = R.encode_example({'image/encoded': b'\xff\xd8jpeg', 'image/class/label': [7], 'f': np.array([0.5, -2.0], np.float32),
+                           'neg': np.array([-3, 1 << 40]), 'empty': np.zeros(0, np.float32)})
+    f = R.parse_example(ex)
+    assert f['image/encoded'] == [b'\xff\xd8jpeg'] and f['image/class/label'].tolist() == [7]
+    assert f['f'].dtype == np.float32 and f['f'].tolist() == [0.5, -2.0]
+    assert f['neg'].tolist() == [-3, 1 << 40] and len(f['empty']) == 0
+    # the same message with UNPACKED repeated scalars, written out by hand:
+    # Example{features{feature{key:"l" value{int64_list{value:5 value:6}}} feature{key:"x" value{float_list{value:1.5}}}}}
+    int_list = bytes([0x08, 5, 0x08, 6])
+    flt_list = bytes([0x0d]) + struct.pack('<f', 1.5)
+    def entry(k, feat):
+        body = bytes([0x0a, len(k)]) + k + bytes([0x12, len(feat)]) + feat
+        return bytes([0x0a, len(body)]) + body
+    feats = entry(b'l', bytes([0x1a, len(int_list)]) + int_list) + entry(b'x', bytes([0x12, len(flt_list)]) + flt_list)
+    f = R.parse_example(bytes([0x0a, len(feats)]) + feats)
+    assert f['l'].tolist() == [5, 6] and f['x'].tolist() == [1.5]
+
+
+def test_legacy_bilinear_resize_known_answers():
+    from pocketflow_b200.datasets.ilsvrc12_dataset import resize_bilinear
+    ramp = np.arange(4, dtype=np.float32).reshape(1, 4, 1) * np.ones((3, 1, 2), np.float32)
+    # x2 up-sampling without half-pixel centres: even outputs hit a source pixel, odd ones the mid-point to the next
+    # pixel, and the last one clamps
+    up = resize_bilinear(ramp, 3, 8)
+    np.testing.assert_array_equal(up[0, :, 0], [0, 0.5, 1, 1.5, 2, 2.5, 3, 3])
+    # x2 down-sampling picks every other pixel (no averaging) — the hallmark of the TF1 kernel
+    img = np.random.RandomState(0).rand(8, 6, 3).astype(np.float32)
+    np.testing.assert_array_equal(resize_bilinear(img, 4, 3), img[::2, ::2])
+    np.testing.assert_array_equal(resize_bilinear(img, 8, 6), img)
+    # a non-integer ratio against the formula spelled out per output pixel
+    out = resize_bilinear(img, 5, 4)
+    for y in range(5):
+        for x in range(4):
+            sy, sx = np.float32(y) * (np.float32(8) / np.float32(5)), np.float32(x) * (np.float32(6) / np.float32(4))
+            y0, x0 = int(np.floor(sy)), int(np.floor(sx))
+            y1, x1 = min(int(np.ceil(sy)), 7), min(int(np.ceil(sx)), 5)
+            ly, lx = np.float32(sy - y0), np.float32(sx - x0)
+            top = img[y0, x0] + (img[y0, x1] - img[y0, x0]) * lx
+            bot = img[y1, x0] + (img[y1, x1] - img[y1, x0]) * lx
+            np.testing.assert_array_equal(out[y, x], top + (bot - top) * ly)
+
+
+def test_eval_preprocessing_follows_the_reference_steps():
+    from pocketflow_b200.datasets import ilsvrc12_dataset as D
+    assert D.smallest_size_at_least(375, 500) == (256, 341)            # 500 * (256 / 375) = 341.33 -> 341
+    assert D.smallest_size_at_least(500, 375) == (341, 256)
+    assert D.smallest_size_at_least(256, 256) == (256, 256)
+    j = _jpeg(300, 400, 1)
+    out = D.preprocess_image(j, np.zeros((0, 4)), False)
+    assert out.shape == (224, 224, 3) and out.dtype == np.float32
+    dec = D.decode_jpeg(j)
+    assert dec.shape == (300, 400, 3) and D.jpeg_shape(j) == (300, 400)
+    nh, nw = D.smallest_size_at_least(300, 400)
+    ref = D.resize_bilinear(dec, nh, nw)
+    ref = ref[(nh - 224) // 2:(nh - 224) // 2 + 224, (nw - 224) // 2:(nw - 224) // 2 + 224] - np.array([123.68, 116.78, 103.94], np.float32)
+    np.testing.assert_array_equal(out, ref)
+    grey = D.decode_jpeg(_jpeg(64, 48, 2, mode='L'))
+    assert grey.shape == (64, 48, 3) and np.array_equal(grey[..., 0], grey[..., 1])
+
+
+def test_distorted_bounding_box_respects_its_constraints():
+    from pocketflow_b200.datasets.ilsvrc12_dataset import sample_distorted_bounding_box
+    rng = np.random.default_rng(0)
+    H, W = 375, 500
+    box = np.array([[0.2, 0.3, 0.7, 0.9]], np.float32)
+    bx0, by0, bx1, by1 = int(0.3 * W), int(0.2 * H), int(0.9 * W), int(0.7 * H)
+    areas, aspects = [], []
+    for _ in range(400):
+        y, x, h, w = sample_distorted_bounding_box(H, W, box, rng)
+        assert 0 <= y and 0 <= x and y + h <= H and x + w <= W and h > 0 and w > 0
+        inter = max(min(x + w, bx1) - max(x, bx0), 0) * max(min(y + h, by1) - max(y, by0), 0)
+        assert inter / float((bx1 - bx0) * (by1 - by0)) >= 0.1
+        areas.append(h * w / float(H * W))
+        aspects.append(w / float(h))
+    assert 0.05 - 1e-3 <= min(areas) and max(areas) <= 1.0
+    assert 0.74 <= min(aspects) and max(aspects) <= 1.35                # rounding to whole pixels
+    assert np.std(areas) > 0.15 and min(areas) < 0.15 and max(areas) > 0.8      # the whole area range is used
+    # no boxes: the image itself is the object; impossible constraints: the whole image comes back
+    y, x, h, w = sample_distorted_bounding_box(H, W, np.zeros((0, 4)), rng)
+    assert h * w >= 0.05 * H * W - H
+    assert sample_distorted_bounding_box(H, W, box, rng, min_object_covered=1.0, area_range=(0.05, 0.06)) == (0, 0, H, W)
+
+
+def test_dataset_stream_reads_shards_and_preprocesses(tmp_path):
+    from pocketflow_b200 import graph as G
+    from pocketflow_b200.flags import FLAGS
+    import importlib
+    D = importlib.import_module('pocketflow_b200.datasets.ilsvrc12_dataset')
+    d = str(tmp_path)
+    labels = {}
+    for shard in range(3):
+        recs = []
+        for i in range(5):
+            idx = shard * 5 + i
+            labels[idx] = 1 + idx
+            recs.append(_example(_jpeg(240 + 8 * idx, 320 - 8 * idx, idx), 1 + idx, [[0.1, 0.1, 0.9, 0.9]] if idx % 2 else []))
+        R.write_records(os.path.join(d, 'train-%05d-of-00003' % shard), recs)
+    R.write_records(os.path.join(d, 'validation-00000-of-00001'), [_example(_jpeg(256, 300, 99), 42)])
+    FLAGS.reset()
+    FLAGS.data_dir_local, FLAGS.batch_size, FLAGS.batch_size_eval, FLAGS.nb_classes = d, 4, 2, 1001
+    FLAGS.buffer_size, FLAGS.nb_threads, FLAGS.prefetch_size, FLAGS.nb_smpls_val = 6, 2, 2, 5
+    gr = G.Graph()
+    with gr.as_default():
+        it = D.Ilsvrc12Dataset(is_train=True).build()
+        seen = []
+        for _ in range(15):                                  # 60 samples = 4 passes over the 15 records
+            img, lab = it.next_batch()
+            assert tuple(img.shape) == (4, 224, 224, 3) and tuple(lab.shape) == (4, 1001)
+            assert np.isfinite(img.numpy()).all() and (lab.numpy().sum(1) == 1).all()
+            seen.extend(lab.numpy().argmax(1).tolist())
+        counts = np.bincount(seen, minlength=17)[1:16]
+        assert counts.min() >= 3 and counts.max() <= 5 and counts.sum() == 60          # every record, every pass
+        assert seen[:15] != sorted(seen[:15])                                        # shuffled
+        # train / validation split of the training files: disjoint, nb_smpls_val records on the validation side
+        trn, val = D.Ilsvrc12Dataset(is_train=True).build(enbl_trn_val_split=True)
+        tl = set(np.concatenate([trn.next_batch()[1].numpy().argmax(1) for _ in range(10)]).tolist())
+        vl = set(np.concatenate([val.next_batch()[1].numpy().argmax(1) for _ in range(10)]).tolist())
+        assert len(vl) == 5 and len(tl) == 10 and not (tl & vl)
+        ev = D.Ilsvrc12Dataset(is_train=False).build()
+        img, lab = ev.next_batch()
+        assert tuple(img.shape) == (2, 224, 224, 3) and lab.numpy().argmax(1).tolist() == [42, 42]
+        want = D.preprocess_image(_jpeg(256, 300, 99), np.zeros((0, 4)), False)
+        np.testing.assert_array_equal(img.numpy()[0], want)
+    FLAGS.data_dir_local = os.path.join(d, 'nothing_here')
+    with pytest.raises(FileNotFoundError):
+        D.Ilsvrc12Dataset(is_train=True).build()
+    FLAGS.reset()
