@@ -975,6 +975,32 @@ class Executor:
         if self.S2 is not None:
             self.S2.zero_()
 
+    def reset_optimizer_state(self):
+        """A fresh optimizer: zero slots, Adam's beta powers and the step counter back to their initial values."""
+        self.reset_optimizer_slots()
+        self.beta1_power = F32(self.optimizer.get('beta1', 0.9))
+        self.beta2_power = F32(self.optimizer.get('beta2', 0.999))
+        self.step_count = 0
+
+    def set_quant_bits(self, w_bits=None, a_bits=None):
+        """New bit-widths for the quantized layers / activations.  The reference feeds them through placeholders on
+        every sess.run (uniform_quantization/learner.py:330-337); here they are launch arguments (the weight
+        quantizer's segment table, the activation kernels' `bits`), so a captured step graph is dropped and the next
+        steps run eagerly until `capture` is called again."""
+        if w_bits is not None:
+            if self.wq is None:
+                raise ValueError('this executor has no weight quantizer')
+            self.wq.set_bits(list(w_bits))
+            self.weight_quant['bits'] = list(w_bits)
+        if a_bits is not None:
+            if len(a_bits) != len(self.aq_ops):
+                raise ValueError('one bit-width per quantized activation expected (%d)' % len(self.aq_ops))
+            if any(int(b) < 1 or int(b) > 32 for b in a_bits):
+                raise ValueError('bit-widths must be in [1, 32]')
+            if self.act_quant:
+                self.act_quant['bits'] = [int(b) for b in a_bits]
+        self._graph = None
+
     def capture(self, allreduce=None):
         """Capture device_step into a CUDA graph (after one eager warm-up on a side stream)."""
         s = torch.cuda.Stream()

@@ -66,14 +66,24 @@ class UniformQuantLearner(AbstractLearner):
         self.ops = {}
         self.bit_placeholders = {}
         self.statistics = {}
+        self._rl_initial_state = None
         self.__build_train()
         # The reference requires a pre-trained checkpoint here (download_model, learner.py:95-97);
         # the synthetic benchmark path starts from the seeded initialisation instead.
         self.auto_barrier()
-        bit_optimizer = BitOptimizer(self.dataset_name, self.weights, self.statistics)
-        self.optimal_w_bit_list, self.optimal_a_bit_list = bit_optimizer.run()
+        bit_optimizer = BitOptimizer(self.dataset_name, self.weights, self.statistics, tuner=self,
+                                     barrier_fn=self.auto_barrier)
+        # the step is compiled with the flag bit-widths; the RL search (if enabled) then drives that step with
+        # per-roll-out bit-widths and leaves the best allocation in place (learner.py:108-111)
+        self.optimal_w_bit_list = [FLAGS.uql_weight_bits] * self.statistics['nb_matmuls']
+        self.optimal_a_bit_list = [FLAGS.uql_activation_bits] * self.statistics['nb_activations']
         self.__compile()
         self.auto_barrier()
+        if FLAGS.uql_enbl_rl_agent:
+            self.optimal_w_bit_list, self.optimal_a_bit_list = bit_optimizer.run()
+            self.rl_restore()
+            self.rl_set_bits(self.optimal_w_bit_list, self.optimal_a_bit_list)
+            self.auto_barrier()
 
     # ------------------------------------------------------------------ training
     def train(self, nb_iters=None):
@@ -118,6 +128,46 @@ class UniformQuantLearner(AbstractLearner):
         if FLAGS.uql_use_buckets:
             self.__show_bucket_storage(self.ops['bucket_storage'])
         return float(np.mean(losses)), float(np.mean(accuracies))
+
+    # ------------------------------------------------------------------ what the RL bit search drives
+    def rl_restore(self):
+        """Back to the pre-trained weights with a fresh optimizer (bit_optimizer.py:196-201): the latest checkpoint
+        under --save_path if there is one, else the state this learner was built with."""
+        ex = self.sess_train
+        if self._rl_initial_state is None:
+            fn = latest_checkpoint(os.path.dirname(FLAGS.save_path)) if os.path.isdir(os.path.dirname(FLAGS.save_path)) \
+                else None
+            self._rl_initial_state = load_checkpoint(fn) if fn is not None else ex.store.state_dict()
+        ex.store.load_state_dict(self._rl_initial_state, strict=False)
+        ex.reset_optimizer_state()
+        if FLAGS.enbl_multi_gpu:
+            mgw.broadcast_global_variables([ex.store.P, ex.store.O])
+
+    def rl_set_bits(self, w_bits, a_bits):
+        self.sess_train.set_quant_bits(w_bits, a_bits)
+
+    def rl_finetune(self, nb_steps, disp_steps):
+        """`nb_steps` training steps at the current bit-widths, then the fine-tuning step counter back to zero
+        (bit_optimizer.py:243-252)."""
+        time_prev = timer()
+        for t_step in range(nb_steps):
+            self.train_step()
+            if disp_steps and (t_step + 1) % disp_steps == 0:
+                time_prev = self.__monitor_progress(self.sess_train.fetch_losses(), time_prev, t_step)
+        self.sess_train.step_count = 0
+
+    def rl_evaluate(self):
+        """(loss, top-1, top-5) averaged over nb_smpls_eval // batch_size_eval mini-batches (bit_optimizer.py:278-289)."""
+        ex = self.sess_train
+        losses, top1, top5 = [], [], []
+        for _ in range(max(1, FLAGS.nb_smpls_eval // FLAGS.batch_size_eval)):
+            self.feed(ex, self.iterator_train)
+            ex.forward_eval_loss()
+            r = ex.fetch_losses()
+            losses.append(r['loss'])
+            top1.append(r['acc_top1'])
+            top5.append(r['acc_top5'])
+        return float(np.mean(losses)), float(np.mean(top1)), float(np.mean(top5))
 
     # ------------------------------------------------------------------ graph
     def __build_train(self):

@@ -642,6 +642,92 @@ def main():
     flags.nb_classes = 10
     ln.forward_fn(S(), 'channels_last')
     gold['lenet_architecture'] = [list(r) for r in lrec]
+    # ---- the RL bit search's bookkeeping (learners/uniform_quantization/rl_helper.py, bit_optimizer.py) and the DDPG
+    # agent's numpy parts (rl_agents/ddpg/replay_buffer.py, noise.py), executed from the reference source
+    import random as _random
+    rlh = load('learners/uniform_quantization/rl_helper.py', 'ref_uq_rl_helper', stubs)
+    fake_sess = types.SimpleNamespace(run=lambda x: np.array(x))
+    layer_sets = {
+        'lenet': [(5, 5, 32, 64), (1600, 256)],
+        'resnet8': [(1, 1, 16, 16), (3, 3, 16, 16), (3, 3, 16, 16), (1, 1, 16, 32), (3, 3, 16, 32), (3, 3, 32, 32),
+                    (1, 1, 32, 64), (3, 3, 32, 64), (3, 3, 64, 64)],
+        'mixed': [(3, 3, 3, 8), (64, 10), (1, 1, 8, 128), (3, 3, 128, 4)],
+    }
+    gold['uq_rl_helper'] = []
+    ci = 0
+    for lname, shapes in layer_sets.items():
+        nums = [int(np.prod(s)) for s in shapes]
+        for eq_bits in (2.0, 3.0, 4.0, 6.5, 8.0):
+            for (bmin, bmax) in ((2, 8), (1, 4)):
+                if eq_bits < bmin:
+                    continue
+                for rand_layers in (False, True):
+                    ci += 1
+                    flags.uql_w_bit_min, flags.uql_w_bit_max = bmin, bmax
+                    vars_list = [types.SimpleNamespace(shape=s) for s in shapes]
+                    h = rlh.RLHelper(fake_sess, sum(nums) * eq_bits, nums, vars_list, random_layers=rand_layers)
+                    rng = np.random.RandomState(7000 + ci)
+                    rollouts = []
+                    _random.seed(100 + ci)
+                    for _ in range(3):
+                        h.reset()
+                        order = list(h.layer_idxs)
+                        raw = rng.uniform(0, bmax - bmin, len(shapes))
+                        out = [float(h.calc_w(np.array([[raw[k]]]), idx)[0][0]) for k, idx in enumerate(order)]
+                        rollouts.append(dict(order=order, raw=raw.tolist(), bits=out, used=float(h.w_bits_used)))
+                    gold['uq_rl_helper'].append(dict(
+                        shapes=[list(s) for s in shapes], equivalent_bits=eq_bits, w_bit_min=bmin, w_bit_max=bmax,
+                        random_layers=rand_layers, py_seed=100 + ci, s_dims=int(h.s_dims),
+                        states=[h.calc_state(i)[0].tolist() for i in range(len(shapes))], rollouts=rollouts,
+                        reward=h.calc_reward(0.625).tolist()))
+    rb = load('rl_agents/ddpg/replay_buffer.py', 'ref_replay_buffer', stubs)
+    gold['ddpg_replay_buffer'] = []
+    for ci, (buf_size, chunks) in enumerate([(5, [2, 2, 2, 1, 3]), (4, [4, 1]), (7, [3, 3, 3, 3]), (3, [1, 1])]):
+        rng = np.random.RandomState(8000 + ci)
+        buf = rb.ReplayBuffer(3, 2, buf_size)
+        trace = []
+        for n in chunks:
+            batch = [rng.randn(n, 3), rng.randn(n, 2), rng.randn(n, 1), (rng.rand(n, 1) < 0.3).astype(float), rng.randn(n, 3)]
+            buf.append(*batch)
+            trace.append(dict(n=n, idx_smpl=int(buf.idx_smpl), nb_smpls=int(buf.nb_smpls), ready=bool(buf.is_ready()),
+                              states=buf.buffers['states'].tolist(), rewards=buf.buffers['rewards'].tolist()))
+        gold['ddpg_replay_buffer'].append(dict(seed=8000 + ci, buf_size=buf_size, chunks=chunks, trace=trace))
+    nz = load('rl_agents/ddpg/noise.py', 'ref_noise', stubs)
+    gold['ddpg_noise'] = []
+    for init, finl, nb in ((1.0, 1e-5, 200), (0.5, 1e-2, 30)):
+        flags.ddpg_noise_std_init, flags.ddpg_noise_std_finl = init, finl
+        flags.ddpg_noise_dst_finl, flags.ddpg_noise_adpt_rat = 1e-2, 1.03
+        td = nz.TimeDecayNoiseSpec(nb)
+        seq = []
+        for _ in range(5):
+            td.adapt()
+            seq.append(td.stdev_curr)
+        ad = nz.AdaptiveNoiseSpec()
+        seq2 = []
+        for dst in (0.5, 0.02, 0.001, 0.0, 0.3):
+            ad.adapt(dst)
+            seq2.append(ad.stdev_curr)
+        gold['ddpg_noise'].append(dict(std_init=init, std_finl=finl, nb_rlouts=nb, tdecy=seq, adapt=seq2))
+    # BitOptimizer's budget check and transition recording, called unbound on a minimal stand-in for `self`
+    stubs_bo = dict(stubs)
+    stubs_bo['learners.uniform_quantization.rl_helper'] = blank(RLHelper=object)
+    stubs_bo['rl_agents.ddpg.agent'] = blank(Agent=object)
+    bo = load('learners/uniform_quantization/bit_optimizer.py', 'ref_bit_optimizer', stubs_bo)
+    recorded = []
+    me = types.SimpleNamespace(statistics=dict(nb_matmuls=3, num_weights=[10, 20, 5]), total_bits=35 * 4.0, s_dims=9,
+                               agent=types.SimpleNamespace(record=lambda *a: recorded.append([np.asarray(x).tolist() for x in a])))
+    check = bo.BitOptimizer._BitOptimizer__check_bits
+    me._BitOptimizer__check_bits = lambda bits: check(me, bits)
+    gold['uq_bit_optimizer'] = dict(
+        check_ok=float(check(me, [4, 3, 8])), arrange=bo.BitOptimizer._BitOptimizer__arrange_layer_bits(me, [2, 0, 1], [8.0, 4.0, 3.0])[0])
+    try:
+        check(me, [8, 8, 8])
+        gold['uq_bit_optimizer']['check_over'] = 'no error'
+    except ValueError as e:
+        gold['uq_bit_optimizer']['check_over'] = str(e)
+    sa = [(np.full((1, 9), float(i)), np.array([[float(2 + i)]])) for i in range(3)]
+    bo.BitOptimizer._BitOptimizer__record_rollout_transitions(me, sa, 0.75 * np.ones((1, 1)))
+    gold['uq_bit_optimizer']['transitions'] = recorded
     json.dump(gold, open(OUT, 'w'), indent=1)
     print('wrote', OUT, {k: len(v) for k, v in gold.items() if isinstance(v, list)})
 

@@ -115,3 +115,53 @@ def test_single_process_wrapper_defaults():
             mgw.init()
     finally:
         os.environ.update(env)
+
+
+class _BitTuner(object):
+    """Stand-in learner for the RL bit search: records what every rank is asked to do."""
+    device = 'cpu'
+
+    def __init__(self):
+        self.bits_seen = []
+
+    def rl_restore(self):
+        pass
+
+    def rl_set_bits(self, w_bits, a_bits):
+        self.bits_seen.append(list(w_bits))
+        self.bits = list(w_bits)
+
+    def rl_finetune(self, nb_steps, disp_steps):
+        self.steps = nb_steps
+
+    def rl_evaluate(self):
+        acc = float(np.mean(1.0 - 2.0 ** (-np.asarray(self.bits, float) / 2.0)))
+        return 1.0 - acc, acc, acc
+
+
+def _bit_search(rank, world, mgw):
+    """learners/uniform_quantization/bit_optimizer.py:137-190 on two ranks: rank 0 searches, both ranks fine-tune with
+    the same broadcast bit-widths (no arranged_layer_bits.txt round trip) and end with the same allocation."""
+    import random
+    from types import SimpleNamespace
+    from pocketflow_b200.flags import FLAGS
+    from pocketflow_b200.learners.uniform_quantization.bit_optimizer import BitOptimizer
+    FLAGS.reset()
+    FLAGS.enbl_multi_gpu, FLAGS.uql_enbl_rl_agent, FLAGS.uql_nb_rlouts = True, True, 6
+    FLAGS.uql_tune_global_steps, FLAGS.uql_equivalent_bits = 100, 5
+    random.seed(rank)                                  # the ranks' own random streams differ: only rank 0's matters
+    shapes = [(3, 3, 4, 8), (3, 3, 8, 8), (8, 10)]
+    tuner = _BitTuner()
+    bo = BitOptimizer('cifar_10', [SimpleNamespace(shape=s) for s in shapes],
+                      dict(nb_matmuls=3, nb_activations=2, num_weights=[int(np.prod(s)) for s in shapes]),
+                      tuner=tuner, barrier_fn=mgw.barrier, seed=rank)
+    w_bits, a_bits = bo.run()
+    return w_bits, a_bits, tuner.bits_seen, tuner.steps, len(bo.reward_list)
+
+
+def test_rl_bit_search_broadcasts_rank0_choices():
+    (w0, a0, seen0, steps0, n0), (w1, a1, seen1, steps1, n1) = run_ranks(_bit_search)
+    assert w0 == w1 and a0 == a1 == [32, 32] and seen0 == seen1 and len(seen0) == 6
+    assert steps0 == steps1 == 50                       # uql_tune_global_steps / world size
+    assert n0 == 6 and n1 == 0                          # rewards, agent and replay live on the primary worker only
+    assert all(2 <= b <= 8 for b in w0)
