@@ -97,6 +97,7 @@ class AbstractLearner(ABC):  # pylint: disable=too-many-instance-attributes
 
         self.ckpt_file = 'models_%s_at_%s.tar.gz' % (self.model_name, self.dataset_name)
         self.graph_train = None
+        self._iterator_eval = None
 
     @abstractmethod
     def train(self):
@@ -141,6 +142,20 @@ class AbstractLearner(ABC):  # pylint: disable=too-many-instance-attributes
     def update_ops(self):
         """BN moving-statistic updates: fused into the BN statistics kernel here."""
         return []
+
+    def eval_iterator(self):
+        """The stream `evaluate()` draws from.  The reference evaluates on `build_dataset_eval()` in a separate graph
+        (e.g. learners/full_precision/learner.py:140-160); here the evaluation pass reuses the step's buffers, so the
+        evaluation split is read at the TRAINING batch size and copied into the same input placeholders.  Synthetic
+        runs (no --data_dir_local) have no split and keep cycling the training pool."""
+        if not FLAGS.data_dir_local:
+            return self.iterator_train
+        if self._iterator_eval is None:
+            it = self.build_dataset_eval()
+            it.batch_size = self.iterator_train.batch_size          # buffers are allocated lazily, at the first batch
+            it.images, it.labels = self.iterator_train.images, self.iterator_train.labels
+            self._iterator_eval = it
+        return self._iterator_eval
 
     # ------------------------------------------------------------------ shared step plumbing
     def feed(self, executor, iterator):

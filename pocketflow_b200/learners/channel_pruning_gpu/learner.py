@@ -74,7 +74,7 @@ class ChannelPrunedGpuLearner(AbstractLearner):  # pylint: disable=too-many-inst
         ex = self.sess_train
         out = []
         for _ in range(nb_iters):
-            self.feed(ex, self.iterator_train)
+            self.feed(ex, self.eval_iterator())
             ex.forward_eval_loss()
             out.append(ex.fetch_losses()['loss'])
         return float(np.mean(out)), float(self.pr_maskable())

@@ -49,7 +49,7 @@ class FullPrecLearner(AbstractLearner):  # pylint: disable=too-many-instance-att
         ex = self.sess_train
         out = []
         for _ in range(nb_iters):
-            self.feed(ex, self.iterator_train)
+            self.feed(ex, self.eval_iterator())
             ex.forward_eval_loss()
             out.append(ex.fetch_losses()['loss'])
         print('loss = %.4e' % np.mean(out))

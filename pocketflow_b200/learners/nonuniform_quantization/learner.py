@@ -92,7 +92,7 @@ class NonUniformQuantLearner(AbstractLearner):
         ex = self.sess_train
         out = []
         for _ in range(nb_iters):
-            self.feed(ex, self.iterator_train)
+            self.feed(ex, self.eval_iterator())
             ex.forward_eval_loss()
             out.append(ex.fetch_losses()['loss'])
         return float(np.mean(out))

@@ -118,7 +118,7 @@ class UniformQuantLearner(AbstractLearner):
         nb_iters = nb_iters or int(np.ceil(float(FLAGS.nb_smpls_eval) / FLAGS.batch_size_eval))
         losses, accuracies = [], []
         for _ in range(nb_iters):
-            self.feed(ex, self.iterator_train)
+            self.feed(ex, self.eval_iterator())
             ex.forward_eval_loss()
             r = ex.fetch_losses()
             losses.append(r['loss'])
@@ -161,7 +161,7 @@ class UniformQuantLearner(AbstractLearner):
         ex = self.sess_train
         losses, top1, top5 = [], [], []
         for _ in range(max(1, FLAGS.nb_smpls_eval // FLAGS.batch_size_eval)):
-            self.feed(ex, self.iterator_train)
+            self.feed(ex, self.eval_iterator())
             ex.forward_eval_loss()
             r = ex.fetch_losses()
             losses.append(r['loss'])

@@ -93,7 +93,7 @@ class WeightSparseLearner(AbstractLearner):  # pylint: disable=too-many-instance
         ex = self.sess_train
         losses = []
         for _ in range(nb_iters):
-            self.feed(ex, self.iterator_train)
+            self.feed(ex, self.eval_iterator())
             ex.forward_eval_loss()
             losses.append(ex.fetch_losses()['loss'])
         pr = calc_prune_ratio([ex.store.view(v) for v in self.maskable_vars])

@@ -117,3 +117,45 @@ def test_rotating_pinned_buffers_are_refilled(cifar):
     first = [it.next_batch()[0].numpy().copy() for _ in range(it.pool_size)]
     again = it.next_batch()[0].numpy()                                                   # reuses buffer 0 with NEW data
     assert not np.array_equal(again, first[0])
+
+
+def test_learner_evaluates_on_the_eval_split_when_real_data_is_configured(cifar):
+    """AbstractLearner.eval_iterator: with --data_dir_local the evaluation pass reads test_batch.bin (at the step's
+    batch size, into the step's input placeholders); without it the synthetic training pool is reused."""
+    import torch
+    from types import SimpleNamespace
+    from pocketflow_b200 import graph as G
+    from pocketflow_b200.learners.abstract_learner import AbstractLearner
+    from pocketflow_b200.nets import resnet_at_cifar10 as R
+    import importlib
+    importlib.reload(R)
+    C, truth, (test_lab, test_img) = cifar
+
+    class Probe(AbstractLearner):
+        def train(self):
+            pass
+
+        def evaluate(self):
+            pass
+
+    FLAGS.batch_size, FLAGS.batch_size_eval = 6, 100
+    lrn = Probe(None, R.ModelHelper())
+    lrn.graph_train = G.Graph()
+    with lrn.graph_train.as_default():
+        lrn.iterator_train = lrn.build_dataset_train()
+        images, labels = lrn.iterator_train.get_next()
+    ex = SimpleNamespace(buf={images: torch.zeros(images.shape), labels: torch.zeros(labels.shape)})
+    it = lrn.eval_iterator()
+    assert it is not lrn.iterator_train and it is lrn.eval_iterator() and it.batch_size == 6
+    seen = []
+    for _ in range(5):                                         # 30 test records = 5 batches of 6: one epoch
+        nbytes = lrn.feed(ex, it)
+        assert nbytes == 6 * 32 * 32 * 3 * 4 + 6 * 10 * 4
+        seen.append((ex.buf[images].numpy().copy(), ex.buf[labels].numpy().argmax(1)))
+    got_labels = np.sort(np.concatenate([s[1] for s in seen]))
+    np.testing.assert_array_equal(got_labels, np.sort(test_lab))               # exactly the evaluation split
+    want = C.standardize(test_img.transpose(0, 2, 3, 1))                       # and un-augmented
+    got = np.concatenate([s[0] for s in seen])
+    assert sorted(np.round(got.reshape(30, -1).sum(1), 2).tolist()) == sorted(np.round(want.reshape(30, -1).sum(1), 2).tolist())
+    FLAGS.data_dir_local = None
+    assert lrn.eval_iterator() is lrn.iterator_train
