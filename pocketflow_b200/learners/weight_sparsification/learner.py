@@ -116,7 +116,7 @@ class WeightSparseLearner(AbstractLearner):  # pylint: disable=too-many-instance
                     loss += self.helper_dst.calc_loss(logits, logits_dst)
                 self.lrn_rate, self.nb_iters_train = self.setup_lrn_rate(None)
         if FLAGS.exec_mode == 'train':
-            self.var_names_n_prune_ratios = PROptimizer(self.maskable_vars).run()
+            self.var_names_n_prune_ratios = PROptimizer(self.maskable_vars, self.dataset_name).run()
         for var, (name, _) in zip(self.maskable_vars, self.var_names_n_prune_ratios):
             assert var.name == name, 'unmatched variable names: %s vs. %s' % (var.name, name)
         world = mgw.size() if FLAGS.enbl_multi_gpu else 1

@@ -728,6 +728,33 @@ def main():
     sa = [(np.full((1, 9), float(i)), np.array([[float(2 + i)]])) for i in range(3)]
     bo.BitOptimizer._BitOptimizer__record_rollout_transitions(me, sa, 0.75 * np.ones((1, 1)))
     gold['uq_bit_optimizer']['transitions'] = recorded
+    # ---- weight sparsification: RLHelper (learners/weight_sparsification/rl_helper.py) executed from the reference
+    wsrl = load('learners/weight_sparsification/rl_helper.py', 'ref_ws_rl_helper', stubs)
+    gold['ws_rl_helper'] = []
+    ci = 0
+    for lname, shapes in layer_sets.items():
+        for target in (0.5, 0.75, 0.9):
+            for reward_type in ('single-obj', 'multi-obj'):
+                for skip in (False, True):
+                    ci += 1
+                    flags.ws_prune_ratio, flags.ws_reward_type = target, reward_type
+                    vars_list = [types.SimpleNamespace(shape=s) for s in shapes]
+                    h = wsrl.RLHelper(fake_sess, vars_list, skip)
+                    rng = np.random.RandomState(9000 + ci)
+                    rollouts = []
+                    for _ in range(3):
+                        acts = rng.uniform(0, 1, len(shapes))
+                        states, ratios, error = [], [], None
+                        try:
+                            for idx in range(len(shapes)):
+                                states.append(h.calc_state(idx)[0].tolist())
+                                ratios.append(float(h.cvt_action_to_prune_ratio(idx, acts[idx])))
+                        except AssertionError as e:          # the target cannot be reached (e.g. every layer skipped)
+                            error = str(e)
+                        rollouts.append(dict(actions=acts.tolist(), states=states, ratios=ratios, error=error,
+                                             overall=float(h.calc_overall_prune_ratio()), reward=float(h.calc_reward(0.8))))
+                    gold['ws_rl_helper'].append(dict(shapes=[list(s) for s in shapes], ws_prune_ratio=target, reward_type=reward_type,
+                                                     skip_head_n_tail=skip, s_dims=int(h.s_dims), rollouts=rollouts))
     json.dump(gold, open(OUT, 'w'), indent=1)
     print('wrote', OUT, {k: len(v) for k, v in gold.items() if isinstance(v, list)})
 

@@ -234,3 +234,93 @@ def test_bit_optimizer_refuses_what_it_cannot_do():
     FLAGS.uql_enbl_rl_layerwise_tune = True
     with pytest.raises(NotImplementedError):
         BitOptimizer('cifar_10', [], stats, tuner=_Tuner([1.0]))
+
+
+def test_ws_rl_helper_matches_the_executed_reference():
+    import pocketflow_b200.learners.weight_sparsification.learner  # noqa: F401  (defines the ws_* flags)
+    from pocketflow_b200.learners.weight_sparsification.rl_helper import RLHelper
+    assert len(GOLD['ws_rl_helper']) == 36
+    n_err = 0
+    for g in GOLD['ws_rl_helper']:
+        FLAGS.ws_prune_ratio, FLAGS.ws_reward_type = g['ws_prune_ratio'], g['reward_type']
+        h = RLHelper([tuple(s) for s in g['shapes']], g['skip_head_n_tail'])
+        assert h.s_dims == g['s_dims']
+        for ro in g['rollouts']:
+            states, ratios, error = [], [], None
+            try:
+                for idx, a in enumerate(ro['actions']):
+                    states.append(h.calc_state(idx)[0].tolist())
+                    ratios.append(float(h.cvt_action_to_prune_ratio(idx, a)))
+            except AssertionError as e:
+                error = str(e)
+                n_err += 1
+            assert error == ro['error']
+            assert states == ro['states'] and ratios == ro['ratios']
+            assert float(h.calc_overall_prune_ratio()) == ro['overall'] and float(h.calc_reward(0.8)) == ro['reward']
+            if error is None and g['reward_type'] == 'single-obj':
+                assert ro['overall'] >= g['ws_prune_ratio'] - 1e-9                 # the target is a hard constraint
+    assert n_err == 27
+
+
+class _PruneTuner(object):
+    """Stand-in for the device half of the 'optimal' protocol: accuracy falls with the pruning of 'sensitive' layers and
+    recovers a little with retraining."""
+    device = 'cpu'
+
+    def __init__(self, sens):
+        self.sens = np.asarray(sens, float)
+        self.calls, self.retrained = [], False
+
+    def pr_prune(self, prune_ratios):
+        self.calls.append('prune')
+        self.ratios, self.retrained = np.asarray(prune_ratios, float), False
+
+    def pr_retrain(self, nb_iters_rg, nb_iters_ft):
+        self.calls.append(('retrain', nb_iters_rg, nb_iters_ft))
+        self.retrained = True
+
+    def pr_evaluate(self):
+        self.calls.append('evaluate')
+        acc = 1.0 - float(np.sum(self.sens * self.ratios ** 2) / np.sum(self.sens)) * (0.6 if self.retrained else 1.0)
+        return 1.0 - acc, {'accuracy': acc, 'acc_top5': min(1.0, acc + 0.05)}
+
+
+def test_pr_optimizer_protocols_and_the_optimal_search(capsys):
+    from types import SimpleNamespace
+    import pocketflow_b200.learners.weight_sparsification.learner  # noqa: F401
+    from pocketflow_b200.learners.weight_sparsification.pr_optimizer import PROptimizer
+    shapes = [(3, 3, 3, 16), (3, 3, 16, 32), (3, 3, 32, 32), (1, 1, 32, 64), (64, 10)]
+    mvars = [SimpleNamespace(name='model/v%d:0' % i, shape=s, numel=int(np.prod(s))) for i, s in enumerate(shapes)]
+    FLAGS.ws_prune_ratio, FLAGS.ws_prune_ratio_prtl = 0.6, 'uniform'
+    assert PROptimizer(mvars).run() == [(v.name, 0.6) for v in mvars]
+    FLAGS.ws_prune_ratio_prtl = 'heurist'
+    heur = PROptimizer(mvars).run()
+    n = np.array([v.numel for v in mvars], float)
+    assert abs(sum(r * k for (_, r), k in zip(heur, n)) / n.sum() - 0.6) < 1e-12          # overall ratio = the target
+    FLAGS.ws_prune_ratio_prtl = 'optimal'
+    with pytest.raises(NotImplementedError, match='device half'):
+        PROptimizer(mvars, 'cifar_10').run()
+    FLAGS.ws_prune_ratio_prtl = 'random'
+    with pytest.raises(ValueError):
+        PROptimizer(mvars)
+    FLAGS.ws_prune_ratio_prtl = 'optimal'
+    FLAGS.ws_nb_rlouts, FLAGS.ws_nb_rlouts_min, FLAGS.ws_nb_iters_rg, FLAGS.ws_nb_iters_ft = 20, 4, 20, 400
+    tuner = _PruneTuner([5.0, 1.0, 0.2, 0.2, 3.0])
+    opt = PROptimizer(mvars, 'ilsvrc_12', tuner=tuner, seed=0)
+    out = opt.run()
+    text = capsys.readouterr().out
+    assert [name for name, _ in out] == [v.name for v in mvars]
+    ratios = np.array([r for _, r in out])
+    assert (ratios >= 0).all() and (ratios <= 1.0 - 0.4 / 3.0 + 1e-12).all()
+    assert float(np.sum(ratios * n) / n.sum()) >= 0.6 - 1e-9                              # single-obj: target reached
+    per = [tuner.calls[i:i + 4] for i in range(0, len(tuner.calls), 4)]
+    assert len(per) == 20 and all(c == ['prune', 'evaluate', ('retrain', 20, 400), 'evaluate'] for c in per)
+    assert len(opt.rewards) == 20 and text.count('starting') == 20 and 'best reward updated' in text
+    tuner.pr_prune(ratios)
+    tuner.pr_retrain(0, 0)
+    assert abs(tuner.pr_evaluate()[1]['accuracy'] - max(opt.rewards)) < 1e-12             # the best roll-out is returned
+    assert opt.agent.memory.is_ready() and opt.agent.memory.buf_size == 5 * 4
+    # CIFAR-10: head and tail layers are never pruned
+    FLAGS.ws_nb_rlouts = 3
+    out = PROptimizer(mvars, 'cifar_10', tuner=_PruneTuner([1.0] * 5), seed=0).run()
+    assert out[0][1] == 0.0 and out[-1][1] == 0.0 and all(r > 0 for _, r in out[1:-1])
