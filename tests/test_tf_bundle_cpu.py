@@ -262,3 +262,28 @@ def test_learner_checkpoint_helpers_speak_both_formats(tmp_path):
     with pytest.raises(ValueError):
         save_checkpoint(path, state, 30)
     FLAGS.reset()
+
+
+def test_ckpt_tool_converts_both_ways(tmp_path, capsys):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        'ckpt_tool', os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tools', 'ckpt_tool.py'))
+    tool = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tool)
+    from pocketflow_b200.flags import FLAGS
+    from pocketflow_b200.learners.abstract_learner import save_checkpoint, load_checkpoint
+    FLAGS.reset()
+    rng = np.random.RandomState(5)
+    state = {'model/conv2d/kernel:0': rng.randn(3, 3, 2, 4).astype(np.float32), 'model/dense/bias:0': rng.randn(10).astype(np.float32)}
+    npz = save_checkpoint(str(tmp_path / 'a' / 'model.ckpt'), state, 7)
+    assert tool.main(['to-tf', npz, str(tmp_path / 'b' / 'model.ckpt')]) == 0
+    assert B.BundleReader(str(tmp_path / 'b' / 'model.ckpt')).keys() == ['model/conv2d/kernel', 'model/dense/bias']
+    assert tool.main(['to-npz', str(tmp_path / 'b' / 'model.ckpt'), str(tmp_path / 'c' / 'model.ckpt')]) == 0
+    back = load_checkpoint(str(tmp_path / 'c' / 'model.ckpt.npz'))
+    assert sorted(back) == sorted(state)
+    for k in state:
+        np.testing.assert_array_equal(back[k], state[k])
+    capsys.readouterr()
+    assert tool.main(['list', str(tmp_path / 'b' / 'model.ckpt')]) == 0
+    out = capsys.readouterr().out
+    assert 'model/conv2d/kernel' in out and '(3, 3, 2, 4)' in out and '2 tensors, 82 values' in out
