@@ -165,3 +165,53 @@ def test_rl_bit_search_broadcasts_rank0_choices():
     assert steps0 == steps1 == 50                       # uql_tune_global_steps / world size
     assert n0 == 6 and n1 == 0                          # rewards, agent and replay live on the primary worker only
     assert all(2 <= b <= 8 for b in w0)
+
+
+def _sharded_files(rank, world, mgw):
+    """filenames.shard(size, rank) (datasets/abstract_dataset.py:80-81) on real files: CIFAR-10 binaries and ILSVRC-12
+    TFRecord shards — every rank streams its own files only."""
+    from pocketflow_b200.flags import FLAGS
+    from pocketflow_b200.datasets.cifar10_dataset import Cifar10Dataset
+    root = os.environ['PF_TEST_DATA']
+    FLAGS.reset()
+    FLAGS.enbl_multi_gpu, FLAGS.batch_size, FLAGS.data_dir_local, FLAGS.nb_classes = True, 5, os.path.join(root, 'cifar'), 10
+    it = Cifar10Dataset(is_train=True).build()
+    cifar_labels = sorted(set(np.concatenate([it.next_batch()[1].numpy().argmax(1) for _ in range(8)]).tolist()))
+    import importlib
+    D = importlib.import_module('pocketflow_b200.datasets.ilsvrc12_dataset')
+    FLAGS.data_dir_local, FLAGS.batch_size, FLAGS.nb_classes = os.path.join(root, 'ilsvrc'), 2, 1001
+    FLAGS.nb_threads, FLAGS.prefetch_size, FLAGS.buffer_size = 1, 1, 4
+    ds = D.Ilsvrc12Dataset(is_train=True)
+    ds.batch_size, ds.nb_classes = 2, 1001              # (the flag defaults belong to the first dataset module imported)
+    it = ds.build()
+    ilsvrc_labels = sorted(set(np.concatenate([it.next_batch()[1].numpy().argmax(1) for _ in range(6)]).tolist()))
+    return cifar_labels, ilsvrc_labels
+
+
+def test_rank_sharded_real_files(tmp_path):
+    pytest.importorskip('PIL.Image')
+    import io
+    from PIL import Image
+    from pocketflow_b200.utils import tf_record as R
+    cifar, ilsvrc = tmp_path / 'cifar', tmp_path / 'ilsvrc'
+    cifar.mkdir()
+    ilsvrc.mkdir()
+    rng = np.random.RandomState(0)
+    for f in range(2):                                  # file f holds only the labels {2f, 2f + 1}
+        lab = (2 * f + rng.randint(0, 2, 20)).astype(np.uint8)
+        img = rng.randint(0, 256, (20, 3 * 32 * 32)).astype(np.uint8)
+        np.concatenate([lab[:, None], img], axis=1).tofile(str(cifar / ('data_batch_%d.bin' % (f + 1))))
+    for f in range(2):                                  # shard f holds only the labels {10f + 1 .. 10f + 4}
+        recs = []
+        for i in range(4):
+            b = io.BytesIO()
+            Image.fromarray(rng.randint(0, 256, (40, 48, 3)).astype(np.uint8)).save(b, format='JPEG')
+            recs.append(R.encode_example({'image/encoded': b.getvalue(), 'image/class/label': [10 * f + 1 + i]}))
+        R.write_records(str(ilsvrc / ('train-%05d-of-00002' % f)), recs)
+    os.environ['PF_TEST_DATA'] = str(tmp_path)
+    try:
+        (c0, i0), (c1, i1) = run_ranks(_sharded_files)
+    finally:
+        os.environ.pop('PF_TEST_DATA')
+    assert c0 == [0, 1] and c1 == [2, 3]
+    assert i0 == [1, 2, 3, 4] and i1 == [11, 12, 13, 14]
