@@ -395,6 +395,23 @@ int pf_colsum(const float* a_dev, int64_t m, int c, float* out_dev, void* stream
 int pf_maxpool_fwd(const pf_conv_desc* d, const float* x_dev, float* y_dev, uint8_t* argmax_dev, void* stream);
 int pf_maxpool_bwd(const pf_conv_desc* d, const float* dy_dev, const uint8_t* argmax_dev, int accumulate,
                    float* dx_dev, void* stream);
+/* ILSVRC-12 preprocessing of a mini-batch of decoded uint8 RGB crops in one launch — what
+ * utils/external/imagenet_preprocessing.py:225-260 does after decoding: TF1 bilinear resize (align_corners=False, no
+ * half-pixel centres) of the [h, w, 3] crop at crops_dev + offset to [rh, rw], optional left-right flip of the SOURCE
+ * (training flips before resizing), the [out_h, out_w] window at (top, left) of the resized image (evaluation:
+ * central crop of the 256-short-side resize; training: rh = out_h, rw = out_w, top = left = 0), minus the channel
+ * means.  dst_dev: fp32 [n, out_h, out_w, 3].  Bit-identical to the host restatement in
+ * pocketflow_b200/datasets/ilsvrc12_dataset.py (every operation individually rounded). */
+typedef struct pf_img_desc {
+  int64_t offset;        /* byte offset of this crop in crops_dev */
+  int32_t h, w;          /* crop size */
+  int32_t rh, rw;        /* size it is resized to */
+  int32_t top, left;     /* window origin inside the resized image */
+  int32_t flip;          /* != 0: mirror the crop left-right before resizing */
+  int32_t reserved;
+} pf_img_desc;
+int pf_preprocess_images(const uint8_t* crops_dev, const pf_img_desc* desc_dev, int n, int out_h, int out_w,
+                         float mean_r, float mean_g, float mean_b, float* dst_dev, void* stream);
 /* tf.reduce_mean over H,W (resnet_model.py:547-548) */
 int pf_global_avgpool_fwd(const float* x_dev, int n, int hw, int c, float* y_dev, void* stream);
 int pf_global_avgpool_bwd(const float* dy_dev, int n, int hw, int c, int accumulate, float* dx_dev, void* stream);

@@ -189,6 +189,46 @@ def preprocess_image(image_buffer, bbox, is_training, rng=None):
     return image - CHANNEL_MEANS
 
 
+IMG_DESC = np.dtype([('offset', '<i8'), ('h', '<i4'), ('w', '<i4'), ('rh', '<i4'), ('rw', '<i4'), ('top', '<i4'),
+                     ('left', '<i4'), ('flip', '<i4'), ('reserved', '<i4')])        # pf_img_desc (include/pf_b200.h)
+
+
+def crop_and_descriptor(image_buffer, bbox, is_training, rng=None):
+    """The host half of device-side preprocessing: (uint8 crop [h, w, 3], one IMG_DESC record with offset 0) such
+    that pf_preprocess_images — or `preprocess_from_descriptor`, its numpy statement — yields exactly
+    `preprocess_image(...)`.  Training: the distorted-bounding-box crop, flip flag drawn here, resized straight to
+    224x224.  Evaluation: the whole image, resized to a 256 short side, central 224x224 window."""
+    d = np.zeros((), IMG_DESC)
+    if is_training:
+        h, w = jpeg_shape(image_buffer)
+        crop = decode_jpeg(image_buffer, sample_distorted_bounding_box(h, w, bbox, rng))
+        d['flip'] = int(rng.random() < 0.5)
+        d['rh'], d['rw'] = IMAGE_HEI, IMAGE_WID
+    else:
+        crop = decode_jpeg(image_buffer)
+        d['rh'], d['rw'] = smallest_size_at_least(crop.shape[0], crop.shape[1])
+        d['top'], d['left'] = (int(d['rh']) - IMAGE_HEI) // 2, (int(d['rw']) - IMAGE_WID) // 2
+    d['h'], d['w'] = crop.shape[:2]
+    return np.ascontiguousarray(crop), d
+
+
+def preprocess_from_descriptor(crop, d, out_h=IMAGE_HEI, out_w=IMAGE_WID):
+    """What the device kernel computes for one image, in numpy (the parity reference of pf_preprocess_images)."""
+    h, w = int(d['h']), int(d['w'])
+    sy = (np.arange(out_h, dtype=F32) + F32(d['top'])) * (F32(h) / F32(d['rh']))
+    sx = (np.arange(out_w, dtype=F32) + F32(d['left'])) * (F32(w) / F32(d['rw']))
+    y0, x0 = np.floor(sy).astype(np.int64), np.floor(sx).astype(np.int64)
+    y1, x1 = np.minimum(np.ceil(sy).astype(np.int64), h - 1), np.minimum(np.ceil(sx).astype(np.int64), w - 1)
+    ly, lx = (sy - y0.astype(F32))[:, None, None], (sx - x0.astype(F32))[None, :, None]
+    if d['flip']:
+        x0, x1 = w - 1 - x0, w - 1 - x1
+    img = np.asarray(crop, F32).reshape(h, w, 3)
+    tl, tr, bl, br = img[y0][:, x0], img[y0][:, x1], img[y1][:, x0], img[y1][:, x1]
+    top = tl + (tr - tl) * lx
+    bot = bl + (br - bl) * lx
+    return (top + (bot - top) * ly) - CHANNEL_MEANS
+
+
 def parse_fn(example_serialized, is_train, nb_classes, rng=None):
     """ilsvrc12_dataset.py:39-97: (image fp32 [224,224,3], one-hot label [nb_classes])."""
     f = parse_example(example_serialized)

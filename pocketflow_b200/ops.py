@@ -740,3 +740,20 @@ def dwconv_wgrad_workspace_floats(d):
 def dwconv_wgrad(d, x, dy, ws, dw):
     _lib.check(_lib.load().pf_dwconv_wgrad(ctypes.byref(d), _p(x), _p(dy), _p(ws), _p(dw), _stream()),
                'pf_dwconv_wgrad')
+
+
+def preprocess_images(crops_u8, desc, out, mean=(123.68, 116.78, 103.94)):
+    """ILSVRC-12 preprocessing of a packed mini-batch on the device (pf_preprocess_images): crops_u8 = uint8 CUDA buffer
+    holding every decoded crop back to back, desc = uint8 CUDA view of n pf_img_desc records
+    (datasets/ilsvrc12_dataset.py:IMG_DESC), out = fp32 [n, out_h, out_w, 3]."""
+    L = _lib.load()
+    _check_f32(out)
+    if crops_u8.dtype != torch.uint8 or desc.dtype != torch.uint8 or not crops_u8.is_cuda or not desc.is_cuda:
+        raise ValueError('expected uint8 CUDA buffers for the crops and the descriptor table')
+    n, out_h, out_w, c = out.shape
+    if c != 3 or desc.numel() != n * 40:
+        raise ValueError('out must be [n, h, w, 3] with one 40-byte descriptor per image')
+    _lib.check(L.pf_preprocess_images(_p(crops_u8), _p(desc), n, out_h, out_w, float(mean[0]), float(mean[1]),
+                                      float(mean[2]), _p(out), _stream()), 'pf_preprocess_images')
+    return out
+

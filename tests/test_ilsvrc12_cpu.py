@@ -179,3 +179,25 @@ def test_dataset_stream_reads_shards_and_preprocesses(tmp_path):
     with pytest.raises(FileNotFoundError):
         D.Ilsvrc12Dataset(is_train=True).build()
     FLAGS.reset()
+
+
+def test_descriptor_form_equals_the_host_preprocessing():
+    """crop_and_descriptor + preprocess_from_descriptor (the numpy statement of the device kernel pf_preprocess_images)
+    == preprocess_image, bit for bit: training (random crop, flip BEFORE the asymmetric resize) and evaluation (256
+    short side + central window)."""
+    from pocketflow_b200.datasets import ilsvrc12_dataset as D
+    assert D.IMG_DESC.itemsize == 40
+    box = np.array([[0.1, 0.2, 0.8, 0.9]], np.float32)
+    flips = 0
+    for seed in range(12):
+        j = _jpeg(200 + 17 * seed, 330 - 13 * seed, seed)
+        want = D.preprocess_image(j, box, True, np.random.default_rng(seed))
+        crop, d = D.crop_and_descriptor(j, box, True, np.random.default_rng(seed))
+        flips += int(d['flip'])
+        assert crop.dtype == np.uint8 and crop.shape == (int(d['h']), int(d['w']), 3) and (int(d['rh']), int(d['rw'])) == (224, 224)
+        np.testing.assert_array_equal(D.preprocess_from_descriptor(crop, d), want)
+        want = D.preprocess_image(j, box, False)
+        crop, d = D.crop_and_descriptor(j, box, False)
+        assert int(d['flip']) == 0 and min(int(d['rh']), int(d['rw'])) == 256
+        np.testing.assert_array_equal(D.preprocess_from_descriptor(crop, d), want)
+    assert 0 < flips < 12
