@@ -324,3 +324,46 @@ def test_pr_optimizer_protocols_and_the_optimal_search(capsys):
     FLAGS.ws_nb_rlouts = 3
     out = PROptimizer(mvars, 'cifar_10', tuner=_PruneTuner([1.0] * 5), seed=0).run()
     assert out[0][1] == 0.0 and out[-1][1] == 0.0 and all(r > 0 for _, r in out[1:-1])
+
+
+def test_uq_learner_rl_hooks_compose_the_executor_calls(tmp_path):
+    """The learner side of the bit search (rl_restore / rl_set_bits / rl_finetune / rl_evaluate), run against a
+    recording stand-in for the executor: the learner itself only constructs on a GPU."""
+    from types import SimpleNamespace
+    from pocketflow_b200.learners.uniform_quantization.learner import UniformQuantLearner as L
+    from pocketflow_b200.learners.abstract_learner import save_checkpoint
+    log = []
+    state = {'model/w:0': np.arange(4, dtype=np.float32)}
+    store = SimpleNamespace(state_dict=lambda: {k: v.copy() for k, v in state.items()},
+                            load_state_dict=lambda d, strict=True: log.append(('load', sorted(d), strict, d['model/w:0'].tolist())),
+                            P='P', O='O')
+    ex = SimpleNamespace(store=store, step_count=37,
+                         reset_optimizer_state=lambda: log.append('reset_opt'),
+                         set_quant_bits=lambda w, a: log.append(('bits', list(w), list(a))),
+                         forward_eval_loss=lambda: log.append('eval_fwd'),
+                         fetch_losses=lambda: dict(loss=2.0, acc_top1=0.25, acc_top5=0.5))
+    me = SimpleNamespace(sess_train=ex, _rl_initial_state=None, iterator_train='it',
+                         train_step=lambda: log.append('step'),
+                         feed=lambda e, it: log.append(('feed', it)), eval_iterator=lambda: 'eval_it',
+                         _UniformQuantLearner__monitor_progress=lambda r, t, i: (log.append(('monitor', i)), t)[1])
+    FLAGS.save_path = str(tmp_path / 'models' / 'model.ckpt')
+    # no checkpoint on disk: the state the learner was built with is the restore point, taken once
+    L.rl_restore(me)
+    state['model/w:0'] += 100.0                                  # later training must not leak into the restore point
+    L.rl_restore(me)
+    assert log == [('load', ['model/w:0'], False, [0.0, 1.0, 2.0, 3.0]), 'reset_opt'] * 2
+    # a pre-trained checkpoint under --save_path wins
+    del log[:]
+    me._rl_initial_state = None
+    save_checkpoint(FLAGS.save_path, {'model/w:0': np.full(4, 7.0, np.float32)}, 5)
+    L.rl_restore(me)
+    assert log[0] == ('load', ['model/w:0'], False, [7.0] * 4)
+    del log[:]
+    L.rl_set_bits(me, [2, 8], [32])
+    L.rl_finetune(me, 5, 2)
+    assert log == [('bits', [2, 8], [32]), 'step', 'step', ('monitor', 1), 'step', 'step', ('monitor', 3), 'step']
+    assert ex.step_count == 0                                    # reset_ft_step
+    del log[:]
+    FLAGS.nb_smpls_eval, FLAGS.batch_size_eval = 300, 100
+    assert L.rl_evaluate(me) == (2.0, 0.25, 0.5)
+    assert log == [('feed', 'eval_it'), 'eval_fwd'] * 3
