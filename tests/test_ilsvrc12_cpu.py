@@ -201,3 +201,42 @@ def test_descriptor_form_equals_the_host_preprocessing():
         assert int(d['flip']) == 0 and min(int(d['rh']), int(d['rw'])) == 256
         np.testing.assert_array_equal(D.preprocess_from_descriptor(crop, d), want)
     assert 0 < flips < 12
+
+
+def test_device_kernel_source_run_on_the_host_matches_bit_for_bit(tmp_path):
+    """csrc/pf_preproc.cu keeps its per-value arithmetic and its index decomposition in __host__ __device__ functions;
+    compiled with -DPF_PREPROC_HOST_TEST (no kernel, no launcher, a plain loop instead) the SAME source runs here and
+    must reproduce the host pipeline exactly.  What this leaves to the GPU run: the launch configuration and the
+    device intrinsics' rounding (__f*_rn = IEEE, like the host ops compiled with -ffp-contract=off)."""
+    import ctypes
+    import shutil
+    import subprocess
+    from pocketflow_b200.datasets import ilsvrc12_dataset as D
+    if shutil.which('g++') is None:
+        pytest.skip('no host compiler')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = str(tmp_path / 'libpreproc_host.so')
+    subprocess.check_call(['g++', '-O2', '-std=c++17', '-x', 'c++', '-D__host__=', '-D__device__=', '-DPF_PREPROC_HOST_TEST',
+                           '-ffp-contract=off', '-fPIC', '-shared', '-I', os.path.join(root, 'include'), '-o', lib,
+                           os.path.join(root, 'pocketflow_b200', 'csrc', 'pf_preproc.cu')])
+    fn = ctypes.CDLL(lib).pf_test_preprocess_host
+    fn.restype = None
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                   ctypes.c_float, ctypes.c_float, ctypes.c_void_p]
+    box = np.array([[0.1, 0.2, 0.8, 0.9]], np.float32)
+    for is_training in (True, False):
+        crops, descs, want = [], [], []
+        offset = 0
+        for seed in range(7):
+            j = _jpeg(150 + 23 * seed, 310 - 19 * seed, seed)
+            crop, d = D.crop_and_descriptor(j, box, is_training, np.random.default_rng(seed))
+            d['offset'] = offset
+            offset += crop.size
+            crops.append(crop.reshape(-1))
+            descs.append(d)
+            want.append(D.preprocess_image(j, box, is_training, np.random.default_rng(seed)))
+        packed = np.concatenate(crops)
+        table = np.stack(descs)
+        out = np.full((7, 224, 224, 3), np.nan, np.float32)
+        fn(packed.ctypes.data, table.ctypes.data, 7, 224, 224, 123.68, 116.78, 103.94, out.ctypes.data)
+        np.testing.assert_array_equal(out, np.stack(want))
