@@ -73,6 +73,37 @@ class BatchIterator(object):
         return out
 
 
+class PackedBatchIterator(BatchIterator):
+    """Mini-batches for device-side preprocessing: generator(b) -> (uint8 array holding every decoded crop back to
+    back, descriptor table [b] (one 40-byte pf_img_desc each), one-hot labels [b, k]).  `next_packed()` stages them in
+    rotating pinned buffers (the crop buffer of a slot grows on demand); the learner copies the three pieces to the
+    GPU and runs pf_preprocess_images into the step's image placeholder."""
+
+    def __init__(self, batch_size, image_shape, nb_classes, generator):
+        super(PackedBatchIterator, self).__init__(batch_size, image_shape, nb_classes, generator, stream=True)
+        self.slots = [None] * POOL_SIZE
+
+    def next_batch(self):
+        raise TypeError('a packed iterator yields undecoded-size crops: use next_packed()')
+
+    def next_packed(self):
+        """(crops uint8 [capacity >= nbytes], nbytes, descriptors uint8 [b * 40], labels fp32 [b, k]) in pinned memory."""
+        crops, desc, lab = self.generator(self.batch_size)
+        desc_bytes = np.ascontiguousarray(desc).view(np.uint8).reshape(-1)
+        i = self.cursor % POOL_SIZE
+        self.cursor += 1
+        slot = self.slots[i]
+        if slot is None or slot[0].numel() < crops.size:
+            cap = int(crops.size * 1.25) + 4096
+            slot = self.slots[i] = (torch.empty(cap, dtype=torch.uint8, pin_memory=self.pin),
+                                    torch.empty(desc_bytes.size, dtype=torch.uint8, pin_memory=self.pin),
+                                    torch.empty((self.batch_size, self.nb_classes), dtype=torch.float32, pin_memory=self.pin))
+        slot[0][:crops.size].copy_(torch.from_numpy(crops))
+        slot[1].copy_(torch.from_numpy(desc_bytes))
+        slot[2].copy_(torch.from_numpy(lab))
+        return slot[0], int(crops.size), slot[1], slot[2]
+
+
 class AbstractDataset(ABC):
     def __init__(self, is_train):
         self.is_train = is_train
@@ -104,7 +135,9 @@ class AbstractDataset(ABC):
     def build(self, enbl_trn_val_split=False):
         gens = self._file_generators(enbl_trn_val_split) if FLAGS.data_dir_local else None
         if gens is not None:
-            its = [BatchIterator(self.batch_size, self.image_shape, self.nb_classes, g_, stream=True) for g_ in gens]
+            its = [PackedBatchIterator(self.batch_size, self.image_shape, self.nb_classes, g_)
+                   if getattr(g_, 'packed', False) else
+                   BatchIterator(self.batch_size, self.image_shape, self.nb_classes, g_, stream=True) for g_ in gens]
             return tuple(its) if len(its) > 1 else its[0]
         it = BatchIterator(self.batch_size, self.image_shape, self.nb_classes, self._generator())
         if self.is_train and enbl_trn_val_split:

@@ -31,7 +31,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
-from ..flags import FLAGS, DEFINE_integer
+from ..flags import FLAGS, DEFINE_integer, DEFINE_boolean
 from ..utils.multi_gpu_wrapper import MultiGpuWrapper as mgw
 from ..utils.tf_record import parse_example, read_records
 from .abstract_dataset import AbstractDataset
@@ -42,6 +42,8 @@ DEFINE_integer('nb_smpls_val', 10000, '# of samples for validation')
 DEFINE_integer('nb_smpls_eval', 50000, '# of samples for evaluation')
 DEFINE_integer('batch_size', 64, 'batch size per GPU for training')
 DEFINE_integer('batch_size_eval', 100, 'batch size for evaluation')
+DEFINE_boolean('enbl_device_preprocess', False, 'ILSVRC-12: decode + crop on the host, resize / flip / mean on the GPU '
+               '(pf_preprocess_images; not validated on a GPU yet)')
 
 IMAGE_HEI, IMAGE_WID, IMAGE_CHN = 224, 224, 3
 CHANNEL_MEANS = np.array([123.68, 116.78, 103.94], np.float32)       # imagenet_preprocessing.py:40-43
@@ -229,26 +231,39 @@ def preprocess_from_descriptor(crop, d, out_h=IMAGE_HEI, out_w=IMAGE_WID):
     return (top + (bot - top) * ly) - CHANNEL_MEANS
 
 
-def parse_fn(example_serialized, is_train, nb_classes, rng=None):
-    """ilsvrc12_dataset.py:39-97: (image fp32 [224,224,3], one-hot label [nb_classes])."""
+def parse_example_proto(example_serialized, nb_classes):
+    """ilsvrc12_dataset.py:39-76: (JPEG bytes, one-hot label [nb_classes], bbox [m, 4] as ymin, xmin, ymax, xmax)."""
     f = parse_example(example_serialized)
     encoded = f.get('image/encoded') or [b'']
     label = int(np.asarray(f.get('image/class/label', [-1])).reshape(-1)[0])
     coords = [np.asarray(f.get('image/object/bbox/' + k, []), F32).reshape(-1) for k in ('ymin', 'xmin', 'ymax', 'xmax')]
     n = min(len(c) for c in coords)
     bbox = np.stack([c[:n] for c in coords], axis=1) if n else np.zeros((0, 4), F32)
-    image = preprocess_image(encoded[0], bbox, is_train, rng)
     onehot = np.zeros(nb_classes, F32)
     if 0 <= label < nb_classes:                  # tf.one_hot: an out-of-range index gives an all-zero row
         onehot[label] = 1.0
-    return image, onehot
+    return encoded[0], onehot, bbox
+
+
+def parse_fn(example_serialized, is_train, nb_classes, rng=None):
+    """ilsvrc12_dataset.py:78-97: (image fp32 [224,224,3], one-hot label [nb_classes])."""
+    encoded, onehot, bbox = parse_example_proto(example_serialized, nb_classes)
+    return preprocess_image(encoded, bbox, is_train, rng), onehot
+
+
+def parse_packed_fn(example_serialized, is_train, nb_classes, rng=None):
+    """The host half only: (uint8 crop, descriptor, one-hot label) — resize / flip / mean happen on the device."""
+    encoded, onehot, bbox = parse_example_proto(example_serialized, nb_classes)
+    crop, desc = crop_and_descriptor(encoded, bbox, is_train, rng)
+    return crop, desc, onehot
 
 
 class ExampleStream(object):
     """generator(b) for BatchIterator(stream=True): endless, shuffled, decoded in a thread pool, prepared ahead."""
 
-    def __init__(self, files, nb_classes, is_train, seed, skip=0, take=None, augment=None):
+    def __init__(self, files, nb_classes, is_train, seed, skip=0, take=None, augment=None, packed=False):
         self.files, self.k, self.is_train = list(files), nb_classes, is_train
+        self.packed = packed                                  # True: yield (crops, descriptors, labels), see PackedBatchIterator
         self.augment = is_train if augment is None else augment
         self.skip, self.take = skip, take
         self.rng = np.random.default_rng(seed)
@@ -309,9 +324,16 @@ class ExampleStream(object):
             while True:
                 raw = [next(records) for _ in range(b)]
                 seeds = self.rng.integers(0, 2 ** 62, size=b)
+                fn = parse_packed_fn if self.packed else parse_fn
                 out = list(self.pool.map(
-                    lambda a: parse_fn(a[0], self.augment, self.k, np.random.default_rng(int(a[1]))), zip(raw, seeds)))
-                self.ready.put((np.stack([o[0] for o in out]).astype(F32, copy=False), np.stack([o[1] for o in out])))
+                    lambda a: fn(a[0], self.augment, self.k, np.random.default_rng(int(a[1]))), zip(raw, seeds)))
+                if self.packed:
+                    desc = np.stack([o[1] for o in out])
+                    sizes = np.array([o[0].size for o in out], np.int64)
+                    desc['offset'] = np.concatenate([[0], np.cumsum(sizes)[:-1]])
+                    self.ready.put((np.concatenate([o[0].reshape(-1) for o in out]), desc, np.stack([o[2] for o in out])))
+                else:
+                    self.ready.put((np.stack([o[0] for o in out]).astype(F32, copy=False), np.stack([o[1] for o in out])))
         except BaseException as e:  # pylint: disable=broad-except
             self.error = e
             self.ready.put(None)
@@ -348,6 +370,6 @@ class Ilsvrc12Dataset(AbstractDataset):
         seed = 8765 + 7919 * rank + (0 if self.is_train else 1)
         if self.is_train and enbl_trn_val_split:
             nv = FLAGS.nb_smpls_val
-            return [ExampleStream(files, self.nb_classes, True, seed, skip=nv),
-                    ExampleStream(files, self.nb_classes, True, seed, take=nv)]
-        return [ExampleStream(files, self.nb_classes, self.is_train, seed)]
+            return [ExampleStream(files, self.nb_classes, True, seed, skip=nv, packed=FLAGS.enbl_device_preprocess),
+                    ExampleStream(files, self.nb_classes, True, seed, take=nv, packed=FLAGS.enbl_device_preprocess)]
+        return [ExampleStream(files, self.nb_classes, self.is_train, seed, packed=FLAGS.enbl_device_preprocess)]

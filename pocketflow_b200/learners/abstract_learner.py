@@ -10,6 +10,7 @@ import subprocess
 import numpy as np
 import torch
 
+from .. import ops
 from ..flags import FLAGS, DEFINE_string, DEFINE_integer, DEFINE_boolean
 from ..utils.misc_utils import auto_barrier as auto_barrier_impl
 from ..utils.misc_utils import is_primary_worker as is_primary_worker_impl
@@ -166,6 +167,8 @@ class AbstractLearner(ABC):  # pylint: disable=too-many-instance-attributes
         step i computes; at the start of step i+1 the staged batch is moved into the graph's input buffers with a
         device-to-device copy (155 MB: ~0.05 ms).  Every step still copies exactly one batch host -> device."""
         dev_images, dev_labels = executor.buf[iterator.images], executor.buf[iterator.labels]
+        if hasattr(iterator, 'next_packed'):
+            return self._feed_packed(iterator, dev_images, dev_labels)
         if dev_images.device.type != 'cuda' or os.environ.get('PF_INPUT_PREFETCH', '1') == '0':
             images, labels = iterator.next_batch()
             dev_images.copy_(images, non_blocking=True)
@@ -195,6 +198,21 @@ class AbstractLearner(ABC):  # pylint: disable=too-many-instance-attributes
         dev_labels.copy_(st['labels'], non_blocking=True)
         st['free'].record(main)
         return stage_next()                                    # overlaps with the step that is about to run
+
+    def _feed_packed(self, iterator, dev_images, dev_labels):
+        """Device-side input preprocessing (--enbl_device_preprocess): the host decodes and crops, the uint8 crops
+        (about a third of the fp32 batch's bytes), their descriptor table and the labels are copied, and ONE kernel
+        (pf_preprocess_images) resizes / flips / centres them straight into the step's image placeholder."""
+        crops, nbytes, desc, labels = iterator.next_packed()
+        dev = getattr(iterator, '_packed_dev', None)
+        if dev is None or dev[0].numel() < nbytes:
+            dev = iterator._packed_dev = (torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=dev_images.device),
+                                          torch.empty(desc.numel(), dtype=torch.uint8, device=dev_images.device))
+        dev[0][:nbytes].copy_(crops[:nbytes], non_blocking=True)
+        dev[1].copy_(desc, non_blocking=True)
+        dev_labels.copy_(labels, non_blocking=True)
+        ops.preprocess_images(dev[0], dev[1], dev_images)
+        return nbytes + desc.numel() + labels.numel() * 4
 
     def grad_allreduce(self):
         """The one collective of the data-parallel step (replaces DistributedOptimizer,

@@ -240,3 +240,84 @@ def test_device_kernel_source_run_on_the_host_matches_bit_for_bit(tmp_path):
         out = np.full((7, 224, 224, 3), np.nan, np.float32)
         fn(packed.ctypes.data, table.ctypes.data, 7, 224, 224, 123.68, 116.78, 103.94, out.ctypes.data)
         np.testing.assert_array_equal(out, np.stack(want))
+
+
+def _host_preprocess_lib(tmp_path):
+    import ctypes
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = str(tmp_path / 'libpreproc_host.so')
+    subprocess.check_call(['g++', '-O2', '-std=c++17', '-x', 'c++', '-D__host__=', '-D__device__=', '-DPF_PREPROC_HOST_TEST',
+                           '-ffp-contract=off', '-fPIC', '-shared', '-I', os.path.join(root, 'include'), '-o', lib,
+                           os.path.join(root, 'pocketflow_b200', 'csrc', 'pf_preproc.cu')])
+    fn = ctypes.CDLL(lib).pf_test_preprocess_host
+    fn.restype = None
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                   ctypes.c_float, ctypes.c_float, ctypes.c_void_p]
+    return fn
+
+
+def test_packed_stream_through_feed_equals_the_host_pipeline(tmp_path, monkeypatch):
+    """--enbl_device_preprocess end to end on the CPU: PackedBatchIterator -> AbstractLearner.feed ->
+    ops.preprocess_images (here: the kernel's source compiled for the host) fills the step's image placeholder with
+    exactly the batches the host pipeline produces from the same records and seeds."""
+    import shutil
+    import torch
+    from types import SimpleNamespace
+    from pocketflow_b200 import graph as G, ops
+    from pocketflow_b200.flags import FLAGS
+    from pocketflow_b200.datasets import ilsvrc12_dataset as D
+    from pocketflow_b200.datasets.abstract_dataset import PackedBatchIterator
+    from pocketflow_b200.learners.abstract_learner import AbstractLearner
+    if shutil.which('g++') is None:
+        pytest.skip('no host compiler')
+    host_fn = _host_preprocess_lib(tmp_path)
+
+    def on_host(crops, desc, out, mean=(123.68, 116.78, 103.94)):
+        assert crops.dtype == torch.uint8 and desc.numel() == out.shape[0] * 40 and out.is_contiguous()
+        host_fn(crops.data_ptr(), desc.data_ptr(), out.shape[0], out.shape[1], out.shape[2], mean[0], mean[1], mean[2],
+                out.data_ptr())
+        return out
+    monkeypatch.setattr(ops, 'preprocess_images', on_host)
+    d = str(tmp_path / 'data')
+    os.makedirs(d)
+    for shard in range(2):
+        R.write_records(os.path.join(d, 'train-%05d-of-00002' % shard),
+                        [_example(_jpeg(180 + 16 * i, 260 - 8 * i, 10 * shard + i), 1 + 10 * shard + i,
+                                  [[0.2, 0.2, 0.9, 0.8]] if i % 2 else []) for i in range(6)])
+    R.write_records(os.path.join(d, 'validation-00000-of-00001'), [_example(_jpeg(300, 280, 77 + i), 500 + i) for i in range(4)])
+
+    class Probe(AbstractLearner):
+        def train(self):
+            pass
+
+        def evaluate(self):
+            pass
+
+    def batches(packed, is_train, n):
+        FLAGS.reset()
+        FLAGS.data_dir_local, FLAGS.batch_size, FLAGS.batch_size_eval, FLAGS.nb_classes = d, 4, 4, 1001
+        FLAGS.buffer_size, FLAGS.nb_threads, FLAGS.prefetch_size = 5, 2, 1
+        FLAGS.enbl_device_preprocess = packed
+        with G.Graph().as_default():
+            ds = D.Ilsvrc12Dataset(is_train)
+            ds.batch_size, ds.nb_classes = 4, 1001
+            it = ds.build()
+            assert isinstance(it, PackedBatchIterator) == packed
+            images, labels = it.get_next()
+        ex = SimpleNamespace(buf={images: torch.full(images.shape, float('nan')), labels: torch.zeros(labels.shape)})
+        out, nbytes = [], []
+        for _ in range(n):
+            nbytes.append(AbstractLearner.feed(SimpleNamespace(_feed_packed=lambda *a: AbstractLearner._feed_packed(None, *a)),
+                                               ex, it))
+            out.append((ex.buf[images].numpy().copy(), ex.buf[labels].numpy().copy()))
+        return out, nbytes
+    for is_train in (True, False):
+        host, host_bytes = batches(False, is_train, 5)
+        dev, dev_bytes = batches(True, is_train, 5)
+        for (hi, hl), (di, dl) in zip(host, dev):
+            np.testing.assert_array_equal(dl, hl)
+            np.testing.assert_array_equal(di, hi)
+        assert all(b == 4 * 224 * 224 * 3 * 4 + 4 * 1001 * 4 for b in host_bytes)
+        assert all(b < 0.6 * host_bytes[0] for b in dev_bytes)                  # uint8 crops: far fewer bytes per step
+    FLAGS.reset()

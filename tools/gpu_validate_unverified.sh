@@ -1,6 +1,8 @@
 #!/bin/bash
 # First GPU call of the next round: everything that was written after the previous round's GPU budget ran out.
 #   1. pf_preprocess_images against its numpy statement (tests/test_preproc_gpu.py, opt-in)
+#      (then: run a real-data ILSVRC-12 step with --enbl_device_preprocess and compare the image placeholder with the
+#      host pipeline's batch before turning the flag on by default)
 #   2. the RL bit search through the real UniformQuantLearner (tools/rl_smoke.py)
 #   3. the regular GPU suite + a bench line, to confirm nothing else moved
 # usage: gpurun --timeout 1500 -- 'bash tools/gpu_validate_unverified.sh'
