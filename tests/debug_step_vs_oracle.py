@@ -1,5 +1,5 @@
 """Diagnostic: per-op forward and per-variable gradient differences between the CUDA step and the
-CPU oracle step, for several learner configurations (not a test; prints a report)."""
+CPU oracle step, for several learner configurations (not a collected test — it lives under tests/ because only tests may use the oracle; prints a report)."""
 import os
 import sys
 
