@@ -115,7 +115,7 @@ class UniformQuantLearner(AbstractLearner):
         if not self.is_primary_worker():
             return None
         ex = self.sess_train
-        nb_iters = nb_iters or int(np.ceil(float(FLAGS.nb_smpls_eval) / FLAGS.batch_size_eval))
+        nb_iters = nb_iters or int(np.ceil(float(FLAGS.nb_smpls_eval) / self.__eval_batch_size()))
         losses, accuracies = [], []
         for _ in range(nb_iters):
             self.feed(ex, self.eval_iterator())
@@ -128,6 +128,11 @@ class UniformQuantLearner(AbstractLearner):
         if FLAGS.uql_use_buckets:
             self.__show_bucket_storage(self.ops['bucket_storage'])
         return float(np.mean(losses)), float(np.mean(accuracies))
+
+    def __eval_batch_size(self):
+        """Real data is evaluated at the step's batch size (AbstractLearner.eval_iterator); the synthetic pool keeps
+        the reference's nb_smpls_eval / batch_size_eval iteration count."""
+        return self.iterator_train.batch_size if FLAGS.data_dir_local else FLAGS.batch_size_eval
 
     # ------------------------------------------------------------------ what the RL bit search drives
     def rl_restore(self):
@@ -160,7 +165,7 @@ class UniformQuantLearner(AbstractLearner):
         """(loss, top-1, top-5) averaged over nb_smpls_eval // batch_size_eval mini-batches (bit_optimizer.py:278-289)."""
         ex = self.sess_train
         losses, top1, top5 = [], [], []
-        for _ in range(max(1, FLAGS.nb_smpls_eval // FLAGS.batch_size_eval)):
+        for _ in range(max(1, FLAGS.nb_smpls_eval // self.__eval_batch_size())):
             self.feed(ex, self.eval_iterator())
             ex.forward_eval_loss()
             r = ex.fetch_losses()

@@ -345,7 +345,8 @@ def test_uq_learner_rl_hooks_compose_the_executor_calls(tmp_path):
     me = SimpleNamespace(sess_train=ex, _rl_initial_state=None, iterator_train='it',
                          train_step=lambda: log.append('step'),
                          feed=lambda e, it: log.append(('feed', it)), eval_iterator=lambda: 'eval_it',
-                         _UniformQuantLearner__monitor_progress=lambda r, t, i: (log.append(('monitor', i)), t)[1])
+                         _UniformQuantLearner__monitor_progress=lambda r, t, i: (log.append(('monitor', i)), t)[1],
+                         _UniformQuantLearner__eval_batch_size=lambda: FLAGS.batch_size_eval)
     FLAGS.save_path = str(tmp_path / 'models' / 'model.ckpt')
     # no checkpoint on disk: the state the learner was built with is the restore point, taken once
     L.rl_restore(me)
