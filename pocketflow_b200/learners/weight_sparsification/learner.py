@@ -45,6 +45,7 @@ class WeightSparseLearner(AbstractLearner):  # pylint: disable=too-many-instance
     def __init__(self, sm_writer, model_helper):
         super(WeightSparseLearner, self).__init__(sm_writer, model_helper)
         self.mask_scope = 'mask'
+        self._pr_full_state = None
         if FLAGS.enbl_dst:
             self.helper_dst = DistillationHelper(sm_writer, model_helper, self.mpi_comm)
         self.__build_train()
@@ -100,6 +101,49 @@ class WeightSparseLearner(AbstractLearner):  # pylint: disable=too-many-instance
         print('loss = %.4e | pr_msk = %.4e' % (np.mean(losses), pr))
         return float(np.mean(losses)), float(pr)
 
+    # ------------------------------------------------------------------ what the 'optimal' ratio search drives
+    # (pr_optimizer.py:495-548 runs these on a second pair of graphs; here they compose calls of the training step's own
+    # executor.  Deviations, flagged: no layer-wise regression stage (`nb_iters_rg` is ignored), the short fine-tuning
+    # uses this learner's momentum optimizer at --ws_lrn_rate_ft instead of Adam, and BN runs in training mode.)
+    def pr_reset(self):
+        """The full (pre-trained) model with every weight alive and a fresh optimizer."""
+        ex = self.sess_train
+        if self._pr_full_state is None:
+            ckpt_dir = os.path.dirname(FLAGS.save_path)
+            fn = latest_checkpoint(ckpt_dir) if os.path.isdir(ckpt_dir) else None
+            self._pr_full_state = load_checkpoint(fn) if fn is not None else ex.store.state_dict()
+        ex.store.load_state_dict(self._pr_full_state, strict=False)
+        ex.MASK.fill_(1.0)
+        ex.reset_optimizer_state()
+        if FLAGS.enbl_multi_gpu:
+            mgw.broadcast_global_variables([ex.store.P, ex.store.O])
+
+    def pr_prune(self, prune_ratios):
+        """init_op of the search (pr_optimizer.py:192-199): pruned = full * (|full| > percentile(|full|, ratio))."""
+        self.pr_reset()
+        self.sess_train.mask_builder.build([float(r) for r in prune_ratios])
+
+    def pr_retrain(self, nb_iters_rg, nb_iters_ft):
+        ex = self.sess_train
+        for _ in range(nb_iters_ft):
+            self.feed(ex, self.iterator_train)
+            ex.run_step(FLAGS.ws_lrn_rate_ft, self.grad_allreduce())
+
+    def pr_evaluate(self):
+        """(loss, metrics) over ws_nb_iters_feval mini-batches (pr_optimizer.py:566-590)."""
+        ex = self.sess_train
+        nb_iters = FLAGS.ws_nb_iters_feval if FLAGS.ws_nb_iters_feval > 0 else \
+            max(1, FLAGS.nb_smpls_eval // FLAGS.batch_size_eval)
+        rows = []
+        for _ in range(nb_iters):
+            self.feed(ex, self.eval_iterator())
+            ex.forward_eval_loss()
+            r = ex.fetch_losses()
+            rows.append((r['loss'], r['acc_top1'], r['acc_top5']))
+        loss, top1, top5 = [float(v) for v in np.mean(np.array(rows, np.float64), axis=0)]
+        metrics = {'accuracy': top1} if self.dataset_name == 'cifar_10' else {'acc_top1': top1, 'acc_top5': top5}
+        return loss, metrics
+
     def __build_train(self):
         self.graph_train = G.Graph()
         with self.graph_train.as_default():
@@ -115,10 +159,6 @@ class WeightSparseLearner(AbstractLearner):  # pylint: disable=too-many-instance
                 if FLAGS.enbl_dst:
                     loss += self.helper_dst.calc_loss(logits, logits_dst)
                 self.lrn_rate, self.nb_iters_train = self.setup_lrn_rate(None)
-        if FLAGS.exec_mode == 'train':
-            self.var_names_n_prune_ratios = PROptimizer(self.maskable_vars, self.dataset_name).run()
-        for var, (name, _) in zip(self.maskable_vars, self.var_names_n_prune_ratios):
-            assert var.name == name, 'unmatched variable names: %s vs. %s' % (var.name, name)
         world = mgw.size() if FLAGS.enbl_multi_gpu else 1
         teacher = None
         if FLAGS.enbl_dst:
@@ -131,6 +171,13 @@ class WeightSparseLearner(AbstractLearner):  # pylint: disable=too-many-instance
             teacher.buf[images] = self.sess_train.buf[images]
             self.sess_train.share_im2col_from(teacher)
         self.masks = [self.sess_train.store.view(v, self.sess_train.MASK) for v in self.maskable_vars]
+        # pruning ratios: host formulas, or ('optimal') the RL search driving this very step (pr_* methods below)
+        if FLAGS.exec_mode == 'train':
+            self.var_names_n_prune_ratios = PROptimizer(self.maskable_vars, self.dataset_name, tuner=self).run()
+            if FLAGS.ws_prune_ratio_prtl == 'optimal':
+                self.pr_reset()
+        for var, (name, _) in zip(self.maskable_vars, self.var_names_n_prune_ratios):
+            assert var.name == name, 'unmatched variable names: %s vs. %s' % (var.name, name)
 
     def __calc_prune_ratio_dyn(self, prune_ratio_fnl, global_step):
         """float32 graph arithmetic of learner.py:296-312, evaluated on the host."""

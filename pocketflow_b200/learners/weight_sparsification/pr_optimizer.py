@@ -4,13 +4,12 @@
 'uniform' and 'heurist' are host-side formulas (:385-409).  'optimal' is a DDPG search (:411-470): each roll-out walks
 the maskable layers in order, maps the actor's action to a pruning ratio that keeps the overall target reachable
 (RLHelper), prunes the pre-trained model at those ratios, retrains briefly and takes the validation accuracy as the
-reward of every transition.  The search loop, the agent and the bookkeeping are built and tested here; the
-device half it drives — pruning the full model at given ratios, layer-wise regression of every pruned layer onto the
-full model's activations plus a short masked fine-tuning with BN in inference mode (:232-292,528-548), fast evaluation
-on the validation split — is reached through a `tuner` object with four methods and is NOT provided by the
-WeightSparseLearner yet (paired full / pruned graphs and the regression losses need kernels that must be validated on
-a GPU): without a tuner the 'optimal' protocol fails loudly.  The ratios and the reward travel between ranks by
-broadcast instead of the reference's ./ws.prune.ratios and ./ws.reward files."""
+reward of every transition.  The device half is reached through a `tuner` object (the WeightSparseLearner):
+`pr_prune(ratios)` (restore the full model, mask it), `pr_retrain(nb_iters_rg, nb_iters_ft)`,
+`pr_evaluate() -> (loss, {metric: value})`.  The learner implements them on its own training step — WITHOUT the
+reference's layer-wise regression stage (:232-257: regressing every pruned layer's output onto the full model's needs
+paired full / pruned graphs that are not built), see the deviations listed there.  The ratios and the reward travel
+between ranks by broadcast instead of the reference's ./ws.prune.ratios and ./ws.reward files."""
 import math
 
 import numpy as np
@@ -56,9 +55,8 @@ class PROptimizer(object):
     # ------------------------------------------------------------------ 'optimal'
     def __calc_optimal_prune_ratios(self):
         if self.tuner is None:
-            raise NotImplementedError(
-                "--ws_prune_ratio_prtl optimal: the roll-out search is built, its device half (pruned-model retraining "
-                "with layer-wise regression) is not; use 'uniform' or 'heurist'")
+            raise ValueError("--ws_prune_ratio_prtl optimal needs the learner (tuner=) to prune, retrain and evaluate "
+                             "the roll-outs")
         from ...rl_agents.ddpg.agent import Agent as DdpgAgent
         nb_vars = len(self.maskable_vars)
         primary = is_primary_worker()

@@ -298,7 +298,7 @@ def test_pr_optimizer_protocols_and_the_optimal_search(capsys):
     n = np.array([v.numel for v in mvars], float)
     assert abs(sum(r * k for (_, r), k in zip(heur, n)) / n.sum() - 0.6) < 1e-12          # overall ratio = the target
     FLAGS.ws_prune_ratio_prtl = 'optimal'
-    with pytest.raises(NotImplementedError, match='device half'):
+    with pytest.raises(ValueError, match='needs the learner'):
         PROptimizer(mvars, 'cifar_10').run()
     FLAGS.ws_prune_ratio_prtl = 'random'
     with pytest.raises(ValueError):
@@ -368,3 +368,42 @@ def test_uq_learner_rl_hooks_compose_the_executor_calls(tmp_path):
     FLAGS.nb_smpls_eval, FLAGS.batch_size_eval = 300, 100
     assert L.rl_evaluate(me) == (2.0, 0.25, 0.5)
     assert log == [('feed', 'eval_it'), 'eval_fwd'] * 3
+
+
+def test_ws_learner_search_hooks_compose_the_executor_calls(tmp_path):
+    """pr_reset / pr_prune / pr_retrain / pr_evaluate of the WeightSparseLearner against a recording stand-in."""
+    from types import SimpleNamespace
+    from pocketflow_b200.learners.weight_sparsification.learner import WeightSparseLearner as L
+    log = []
+    state = {'model/w:0': np.arange(3, dtype=np.float32)}
+    store = SimpleNamespace(state_dict=lambda: {k: v.copy() for k, v in state.items()},
+                            load_state_dict=lambda d, strict=True: log.append(('load', d['model/w:0'].tolist(), strict)),
+                            P='P', O='O')
+    ex = SimpleNamespace(store=store, MASK=SimpleNamespace(fill_=lambda v: log.append(('mask_fill', v))),
+                         mask_builder=SimpleNamespace(build=lambda r: log.append(('build', r))),
+                         reset_optimizer_state=lambda: log.append('reset_opt'),
+                         run_step=lambda lr, ar: log.append(('step', lr, ar)),
+                         forward_eval_loss=lambda: log.append('eval_fwd'),
+                         fetch_losses=lambda: dict(loss=1.5, acc_top1=0.5, acc_top5=0.75))
+    me = SimpleNamespace(sess_train=ex, _pr_full_state=None, iterator_train='it', dataset_name='cifar_10',
+                         feed=lambda e, it: log.append(('feed', it)), eval_iterator=lambda: 'eval_it',
+                         grad_allreduce=lambda: None)
+    me.pr_reset = lambda: L.pr_reset(me)
+    FLAGS.save_path = str(tmp_path / 'none' / 'model.ckpt')
+    L.pr_prune(me, np.array([0.0, 0.5, 0.25]))
+    state['model/w:0'] += 9.0
+    L.pr_prune(me, [0.1, 0.1, 0.1])
+    restore = [('load', [0.0, 1.0, 2.0], False), ('mask_fill', 1.0), 'reset_opt']
+    assert log == restore + [('build', [0.0, 0.5, 0.25])] + restore + [('build', [0.1, 0.1, 0.1])]
+    del log[:]
+    FLAGS.ws_lrn_rate_ft = 3e-4
+    L.pr_retrain(me, 20, 3)
+    assert log == [('feed', 'it'), ('step', 3e-4, None)] * 3                      # (no layer-wise regression stage)
+    del log[:]
+    FLAGS.ws_nb_iters_feval = 2
+    assert L.pr_evaluate(me) == (1.5, {'accuracy': 0.5})
+    assert log == [('feed', 'eval_it'), 'eval_fwd'] * 2
+    me.dataset_name = 'ilsvrc_12'
+    FLAGS.ws_nb_iters_feval, FLAGS.nb_smpls_eval, FLAGS.batch_size_eval = 0, 300, 100
+    del log[:]
+    assert L.pr_evaluate(me) == (1.5, {'acc_top1': 0.5, 'acc_top5': 0.75}) and len(log) == 6

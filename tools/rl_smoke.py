@@ -40,5 +40,28 @@ def main():
     print('rl smoke ok: %d tensors restored' % changed)
 
 
+def ws_main():
+    """The pruning-ratio search through the real WeightSparseLearner: 4 roll-outs, 6 fine-tuning steps each."""
+    from pocketflow_b200.learners.weight_sparsification.learner import WeightSparseLearner, calc_prune_ratio
+    FLAGS.reset()
+    FLAGS.resnet_size, FLAGS.batch_size, FLAGS.batch_size_eval = 8, 32, 32
+    FLAGS.ws_prune_ratio, FLAGS.ws_prune_ratio_prtl = 0.5, 'optimal'
+    FLAGS.ws_nb_rlouts, FLAGS.ws_nb_rlouts_min, FLAGS.ws_nb_iters_ft, FLAGS.ws_nb_iters_feval = 4, 2, 6, 2
+    lrn = WeightSparseLearner(None, R.ModelHelper())
+    ex = lrn.sess_train
+    ratios = [r for _, r in lrn.var_names_n_prune_ratios]
+    nums = [v.numel for v in lrn.maskable_vars]
+    overall = sum(r * n for r, n in zip(ratios, nums)) / sum(nums)
+    print('ratios:', ['%.2f' % r for r in ratios], 'overall %.3f' % overall)
+    assert ratios[0] == 0.0 and ratios[-1] == 0.0 and overall >= 0.5 - 1e-6            # CIFAR-10: head / tail kept
+    assert float(ex.MASK.min()) == 1.0 and ex.step_count == 0                          # the search left no trace
+    assert calc_prune_ratio([ex.store.view(v) for v in lrn.maskable_vars]) < 0.01
+    lrn.pr_prune(ratios)
+    got = calc_prune_ratio([ex.store.view(v) for v in lrn.maskable_vars])
+    assert abs(got - overall) < 0.02, (got, overall)
+    print('ws smoke ok: pruned model at %.3f' % got)
+
+
 if __name__ == '__main__':
     main()
+    ws_main()
