@@ -1,6 +1,10 @@
-"""Roll-out bookkeeping for the bit-allocation search (/root/reference/learners/uniform_quantization/rl_helper.py:26-122):
-the state vector of every layer and the projection of the actor's raw action onto the bit-widths the remaining budget
-still allows."""
+"""Roll-out bookkeeping of the bit-allocation search (behaviour of
+/root/reference/learners/uniform_quantization/rl_helper.py:26-122): the state vector the agent sees for every layer
+and the projection of its raw action onto the bit-widths the remaining budget still allows.
+
+State of layer i (length L + 6 for L layers): one-hot(i) | kernel shape as 4 numbers (a dense [in, out] kernel is
+read as [1, 1, in, out]) | #weights(i) / max #weights | #weights of the layers after i / total #weights.
+Every number is float64 numpy, as in the reference (the pinned tests compare exactly)."""
 import random
 
 import numpy as np
@@ -11,58 +15,62 @@ from ...flags import FLAGS
 class RLHelper(object):
     # pylint: disable=too-many-instance-attributes
     def __init__(self, total_bits, num_weights, var_shapes, random_layers=False):
-        """total_bits: the budget (sum over layers of bits x #weights); num_weights: #weights per layer;
-        var_shapes: the kernels' shapes (rank 2 = dense, rank 4 = conv), in layer order."""
-        self.nb_vars = len(num_weights)
+        """total_bits: budget = sum over layers of bits x #weights; num_weights: per layer; var_shapes: kernel shapes
+        (rank 2 or 4) in layer order; random_layers: visit the layers in a fresh random order every roll-out."""
         self.num_weights = num_weights
-        self.total_num_weights = sum(num_weights)
-        self.s_dims = self.nb_vars + 6             # one-hot layer id, 4 shape entries, 2 size ratios
+        self.nb_vars = len(num_weights)
         self.total_bits = total_bits
-        self.w_bits_used = 0
+        self.total_num_weights = sum(num_weights)
         self.random_layers = random_layers
         self.layer_idxs = list(range(self.nb_vars))
-        self.num_weights_to_quantize = self.total_num_weights
-        self.quantized_layers = 0
-        self.var_shapes = []
-        for shape in var_shapes:
-            assert len(shape) in [2, 4], 'Unknown weight shape. Must be a 2 (fc) or 4 (conv) dimensional.'
-            shape = np.asarray(shape, np.float64)
-            self.var_shapes.append(np.hstack((np.ones(2), shape)) if len(shape) == 2 else shape)
+        self.s_dims = self.nb_vars + 6
+        self.var_shapes = [self._as_conv_shape(s) for s in var_shapes]
+        later = [np.sum(num_weights[i + 1:]) / self.total_num_weights for i in range(self.nb_vars)]
+        largest = np.max(num_weights)
         self.states = np.zeros((self.nb_vars, self.s_dims))
-        for idx in range(self.nb_vars):
-            state = self.states[idx]
-            state[idx] = 1.0
-            state[self.nb_vars:self.nb_vars + 4] = self.var_shapes[idx]
-            state[self.nb_vars + 4] = self.num_weights[idx] / np.max(self.num_weights)
-            state[self.nb_vars + 5] = np.sum(self.num_weights[idx + 1:]) / self.total_num_weights
+        self.states[:, :self.nb_vars] = np.eye(self.nb_vars)
+        for i in range(self.nb_vars):
+            self.states[i, self.nb_vars:] = np.hstack((self.var_shapes[i], [num_weights[i] / largest, later[i]]))
+        self.reset_budget()
+
+    @staticmethod
+    def _as_conv_shape(shape):
+        assert len(shape) in [2, 4], 'Unknown weight shape. Must be a 2 (fc) or 4 (conv) dimensional.'
+        shape = np.asarray(shape, np.float64)
+        return shape if shape.size == 4 else np.hstack((np.ones(2), shape))
+
+    def reset_budget(self):
+        self.w_bits_used = 0
+        self.quantized_layers = 0
+        self.num_weights_to_quantize = self.total_num_weights
+
+    def reset(self):
+        """Start of a roll-out: nothing spent yet; optionally a new visiting order."""
+        self.reset_budget()
+        if self.random_layers:
+            random.shuffle(self.layer_idxs)
 
     def calc_state(self, idx):
-        return np.copy(self.states[idx])[None, :]
+        return self.states[idx:idx + 1].copy()
 
     def calc_reward(self, accuracy):
         return accuracy * np.ones((1, 1))
 
-    def reset(self):
-        """Before each roll-out."""
-        self.w_bits_used = 0
-        self.quantized_layers = 0
-        if self.random_layers:
-            random.shuffle(self.layer_idxs)
-        self.num_weights_to_quantize = self.total_num_weights
-
     def calc_w(self, action, idx):
-        """Bit-width for layer `idx` from the actor's output `action` (shape (1, 1), in [0, w_bit_max - w_bit_min]):
-        rounded, shifted by the minimum, capped so that every layer still to come can get the minimum; the last
-        layer of the roll-out takes whatever the budget has left (at most the maximum)."""
-        duty = self.total_bits - self.w_bits_used - self.num_weights_to_quantize * FLAGS.uql_w_bit_min
-        assert duty >= 0, 'Not enough budget for layer {}'.format(idx)
-        if self.quantized_layers != self.nb_vars - 1:
-            action = np.round(action) + FLAGS.uql_w_bit_min
-            action = np.minimum(action, FLAGS.uql_w_bit_min + np.floor(duty * 1.0 / self.num_weights[idx]))
+        """Bit-width (array of shape (1, 1)) for layer `idx` given the actor's output in [0, w_bit_max - w_bit_min].
+        All but the last visited layer: round, add the minimum, and cap at what leaves every unvisited layer its
+        minimum.  The last visited layer takes the whole remainder.  Both are capped at the maximum."""
+        lo, hi = FLAGS.uql_w_bit_min, FLAGS.uql_w_bit_max
+        n_here = self.num_weights[idx]
+        spare = self.total_bits - self.w_bits_used - self.num_weights_to_quantize * lo
+        assert spare >= 0, 'Not enough budget for layer {}'.format(idx)
+        is_last = self.quantized_layers == self.nb_vars - 1
+        if is_last:
+            bits = np.floor((self.total_bits - self.w_bits_used) / n_here) * np.ones((1, 1))
         else:
-            action = np.floor((self.total_bits - self.w_bits_used) / self.num_weights[idx]) * np.ones((1, 1))
-        action = np.minimum(action, FLAGS.uql_w_bit_max)
-        self.w_bits_used += action[0][0] * self.num_weights[idx]
-        self.num_weights_to_quantize -= self.num_weights[idx]
+            bits = np.minimum(np.round(action) + lo, lo + np.floor(spare * 1.0 / n_here))
+        bits = np.minimum(bits, hi)
         self.quantized_layers += 1
-        return action
+        self.num_weights_to_quantize -= n_here
+        self.w_bits_used += bits[0][0] * n_here
+        return bits

@@ -1,80 +1,79 @@
-"""Roll-out bookkeeping for the pruning-ratio search (/root/reference/learners/weight_sparsification/rl_helper.py:24-161):
-per-layer state vectors (normalised by their column maxima) and the map from the actor's action in [0, 1] to a pruning
-ratio that keeps the overall target reachable."""
+"""Roll-out bookkeeping of the pruning-ratio search (behaviour of
+/root/reference/learners/weight_sparsification/rl_helper.py:24-161).
+
+State of layer i (length L + 7 for L maskable layers), divided column-wise by the largest value the column can take:
+one-hot(i) | kernel shape as 4 numbers | #params(i) | #params kept so far in layers < i (depends on the ratios already
+chosen in this roll-out) | #params in layers > i.  An action a in [0, 1] maps linearly to a ratio: a = 0.5 is the
+overall target, 0 the layer's floor, 1 its ceiling; with the single-objective reward the floor is raised so that the
+overall target stays reachable even if every later layer is pruned at its ceiling.  float64 numpy throughout."""
 import numpy as np
 
 from ...flags import FLAGS
 
 
+def _conv_shape(shape):
+    shape = np.asarray(shape, np.float64)
+    assert shape.size in [2, 4], '# of variable dimensions is %d (invalid)' % shape.size
+    return shape if shape.size == 4 else np.hstack((np.ones(2), shape))
+
+
 class RLHelper(object):
     def __init__(self, var_shapes, skip_head_n_tail):
-        """var_shapes: shapes of the maskable kernels in layer order (rank 2 or 4); skip_head_n_tail: never prune the
-        first and the last layer (the reference does this on CIFAR-10)."""
-        nb_vars = len(var_shapes)
-        shapes = []
-        self.prune_ratios = np.zeros(nb_vars)
-        self.nb_params_full = np.zeros(nb_vars)
-        for idx, shape in enumerate(var_shapes):
-            shape = np.asarray(shape, np.float64)
-            assert shape.size in [2, 4], '# of variable dimensions is %d (invalid)' % shape.size
-            shape = np.hstack((np.ones(2), shape)) if shape.size == 2 else shape
-            shapes.append(shape)
-            self.nb_params_full[idx] = np.prod(shape)
-        self.s_dims = nb_vars + 4 + 3              # one-hot id, shape, #params of this / earlier (kept) / later layers
-        self.states = np.zeros((nb_vars, self.s_dims))
-        for idx in range(nb_vars):
-            state = self.states[idx]
-            state[idx] = 1.0
-            state[nb_vars:nb_vars + 4] = shapes[idx]
-            state[nb_vars + 4] = self.nb_params_full[idx]
-            state[nb_vars + 6] = np.sum(self.nb_params_full[idx + 1:])
-        # column nb_vars + 5 (parameters kept in the earlier layers) is filled in per call; it shares the last
-        # column's normaliser
-        self.state_normalizer = np.max(self.states, axis=0)
-        self.state_normalizer[-2] = self.state_normalizer[-1]
+        """var_shapes: kernel shapes of the maskable variables in layer order; skip_head_n_tail: pin the first and the
+        last layer at ratio 0 (what the reference does on CIFAR-10)."""
+        shapes = [_conv_shape(s) for s in var_shapes]
+        L = len(shapes)
+        self.nb_params_full = np.array([np.prod(s) for s in shapes]) if L else np.zeros(0)
+        self.prune_ratios = np.zeros(L)
+        self.s_dims = L + 7
+        after = np.array([np.sum(self.nb_params_full[i + 1:]) for i in range(L)])
+        self.states = np.zeros((L, self.s_dims))
+        self.states[:, :L] = np.eye(L)
+        self.states[:, L:L + 4] = np.array(shapes).reshape(L, 4)
+        self.states[:, L + 4] = self.nb_params_full
+        self.states[:, L + 6] = after                       # column L + 5 is filled in by calc_state
+        self.state_normalizer = self.states.max(axis=0)
+        self.state_normalizer[L + 5] = self.state_normalizer[L + 6]
         keep = 1.0 - FLAGS.ws_prune_ratio
-        self.prune_ratios_min = max(0.0, 1.0 - keep * 3.0) * np.ones(nb_vars)
-        self.prune_ratios_max = (1.0 - keep / 3.0) * np.ones(nb_vars)
+        floor, ceiling = max(0.0, 1.0 - 3.0 * keep), 1.0 - keep / 3.0
+        self.prune_ratios_min = np.full(L, floor)
+        self.prune_ratios_max = np.full(L, ceiling)
         if skip_head_n_tail:
-            for arr in (self.prune_ratios_min, self.prune_ratios_max):
-                arr[0] = 0.0
-                arr[-1] = 0.0
+            self.prune_ratios_min[[0, -1]] = 0.0
+            self.prune_ratios_max[[0, -1]] = 0.0
 
     def calc_state(self, idx):
-        state = np.copy(self.states[idx])
+        state = self.states[idx].copy()
         state[-2] = np.sum(self.nb_params_full[:idx] * (1.0 - self.prune_ratios[:idx]))
-        state /= self.state_normalizer
-        return state[None, :]
-
-    def calc_reward(self, accuracy):
-        if FLAGS.ws_reward_type == 'single-obj':
-            return accuracy
-        if FLAGS.ws_reward_type == 'multi-obj':
-            return accuracy * np.log(1.0 + self.calc_overall_prune_ratio())
-        raise ValueError('unrecognized reward type: ' + FLAGS.ws_reward_type)
-
-    def cvt_action_to_prune_ratio(self, idx, action):
-        """action 0.5 -> the target ratio; 0 -> this layer's minimum, 1 -> its maximum, linear in between; clipped."""
-        pr_min, pr_max = self.__calc_prune_ratio_min_max(idx)
-        if action > 0.5:
-            prune_ratio = pr_max - (1.0 - action) / 0.5 * (pr_max - FLAGS.ws_prune_ratio)
-        else:
-            prune_ratio = pr_min + (action - 0.0) / 0.5 * (FLAGS.ws_prune_ratio - pr_min)
-        self.prune_ratios[idx] = max(pr_min, min(pr_max, prune_ratio))
-        return self.prune_ratios[idx]
+        return (state / self.state_normalizer)[None, :]
 
     def calc_overall_prune_ratio(self):
         return np.sum(self.nb_params_full * self.prune_ratios) / np.sum(self.nb_params_full)
 
-    def __calc_prune_ratio_min_max(self, idx):
-        """With the single-objective reward the overall target is a hard constraint: the minimum for layer idx is
-        raised to what is still needed if every later layer were pruned at its maximum."""
-        pr_min, pr_max = self.prune_ratios_min[idx], self.prune_ratios_max[idx]
+    def calc_reward(self, accuracy):
+        kind = FLAGS.ws_reward_type
+        if kind == 'multi-obj':
+            return accuracy * np.log(1.0 + self.calc_overall_prune_ratio())
+        if kind != 'single-obj':
+            raise ValueError('unrecognized reward type: ' + kind)
+        return accuracy
+
+    def _bounds(self, idx):
+        lo, hi = self.prune_ratios_min[idx], self.prune_ratios_max[idx]
         if FLAGS.ws_reward_type == 'single-obj':
-            pruned_at_most = np.sum(self.nb_params_full[:idx] * self.prune_ratios[:idx]) \
-                + np.sum(self.nb_params_full[idx + 1:] * self.prune_ratios_max[idx + 1:])
-            pruned_needed = np.sum(self.nb_params_full) * FLAGS.ws_prune_ratio
-            pr_req = (pruned_needed - pruned_at_most) / self.nb_params_full[idx]
-            assert pr_req < pr_max + 1e-4, 'cannot reach the required pruning ratio: %f vs. %f' % (pr_req, pr_max)
-            pr_min = max(pr_min, pr_req)
-        return pr_min, pr_max
+            n = self.nb_params_full
+            best_case = np.sum(n[:idx] * self.prune_ratios[:idx]) + np.sum(n[idx + 1:] * self.prune_ratios_max[idx + 1:])
+            needed = (np.sum(n) * FLAGS.ws_prune_ratio - best_case) / n[idx]
+            assert needed < hi + 1e-4, 'cannot reach the required pruning ratio: %f vs. %f' % (needed, hi)
+            lo = max(lo, needed)
+        return lo, hi
+
+    def cvt_action_to_prune_ratio(self, idx, action):
+        lo, hi = self._bounds(idx)
+        target = FLAGS.ws_prune_ratio
+        if action > 0.5:
+            ratio = hi - (1.0 - action) / 0.5 * (hi - target)
+        else:
+            ratio = lo + (action - 0.0) / 0.5 * (target - lo)
+        self.prune_ratios[idx] = max(lo, min(hi, ratio))
+        return self.prune_ratios[idx]

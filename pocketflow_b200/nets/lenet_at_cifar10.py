@@ -1,74 +1,39 @@
-"""Model helper for creating a LeNet-like model for the CIFAR-10 dataset
-(/root/reference/nets/lenet_at_cifar10.py:28-135).  Note the forward pass ends in softmax, so both
-cross-entropy terms see probabilities as logits — mirrored."""
+"""LeNet-like model on CIFAR-10 behind the ModelHelper plugin surface (/root/reference/nets/lenet_at_cifar10.py:28-135).
+The forward pass ends in a softmax, so both cross-entropy terms see probabilities where logits are expected
+ — kept, it is what the reference trains."""
 from .. import graph as G
 from ..flags import FLAGS, DEFINE_float
 from ..datasets.cifar10_dataset import Cifar10Dataset
-from ..utils.lrn_rate_utils import setup_lrn_rate_piecewise_constant
-from ..utils.multi_gpu_wrapper import MultiGpuWrapper as mgw
-from .abstract_model_helper import AbstractModelHelper
+from .classification_helper import ClassificationModelHelper
 
-DEFINE_float('nb_epochs_rat', 1.0, '# of training epochs\'s ratio')
-DEFINE_float('lrn_rate_init', 1e-2, 'initial learning rate')
-DEFINE_float('batch_size_norm', 128, 'normalization factor of batch size')
-DEFINE_float('momentum', 0.9, 'momentum coefficient')
-DEFINE_float('loss_w_dcy', 5e-4, 'weight decaying loss\'s coefficient')
+DEFINE_float('nb_epochs_rat', 1.0, 'scales the number of training epochs')
+DEFINE_float('lrn_rate_init', 1e-2, 'learning rate at batch size batch_size_norm')
+DEFINE_float('batch_size_norm', 128, 'batch size the initial learning rate is quoted for')
+DEFINE_float('momentum', 0.9, 'momentum of the SGD optimizer')
+DEFINE_float('loss_w_dcy', 5e-4, 'weight of the L2 term')
+
+CONV_STAGES = ((32, 'conv1', 'relu1', 'pool1'), (64, 'conv2', 'relu2', 'pool2'))
 
 
 def forward_fn(inputs, data_format):
+    """two x (5x5 VALID conv + bias, ReLU, 2x2 max-pool), flatten, dense 256 + ReLU, dense nb_classes, softmax."""
     if data_format != 'channels_last':
         raise ValueError('NHWC (channels_last) only')
-    inputs = G.conv2d(inputs, 32, [5, 5], name='conv1')
-    inputs = G.relu(inputs, name='relu1')
-    inputs = G.max_pooling2d(inputs, [2, 2], 2, name='pool1')
-    inputs = G.conv2d(inputs, 64, [5, 5], name='conv2')
-    inputs = G.relu(inputs, name='relu2')
-    inputs = G.max_pooling2d(inputs, [2, 2], 2, name='pool2')
-    inputs = G.flatten(inputs, name='flatten')
-    inputs = G.dense(inputs, 256, name='fc3')
-    inputs = G.relu(inputs, name='relu3')
-    inputs = G.dense(inputs, FLAGS.nb_classes, name='fc4')
-    inputs = G.softmax(inputs, name='softmax')
-    return inputs
+    net = inputs
+    for filters, conv, relu, pool in CONV_STAGES:
+        net = G.max_pooling2d(G.relu(G.conv2d(net, filters, [5, 5], name=conv), name=relu), [2, 2], 2, name=pool)
+    net = G.relu(G.dense(G.flatten(net, name='flatten'), 256, name='fc3'), name='relu3')
+    return G.softmax(G.dense(net, FLAGS.nb_classes, name='fc4'), name='softmax')
 
 
-class ModelHelper(AbstractModelHelper):
-    def __init__(self, data_format='channels_last'):
-        super(ModelHelper, self).__init__(data_format)
-        self.dataset_train = Cifar10Dataset(is_train=True)
-        self.dataset_eval = Cifar10Dataset(is_train=False)
+class ModelHelper(ClassificationModelHelper):
+    DATASET, DATASET_NAME = Cifar10Dataset, 'cifar_10'
+    NB_EPOCHS, IDXS_EPOCH, DECAY_RATES = 250, [100, 150, 200], [1.0, 0.1, 0.01, 0.001]
+    L2_SKIPS = None                                   # every trainable variable is regularised (:105-107)
 
-    def build_dataset_train(self, enbl_trn_val_split=False):
-        return self.dataset_train.build(enbl_trn_val_split)
-
-    def build_dataset_eval(self):
-        return self.dataset_eval.build()
-
-    def forward_train(self, inputs):
+    def network(self, inputs, is_train):
         return forward_fn(inputs, self.data_format)
-
-    def forward_eval(self, inputs):
-        return forward_fn(inputs, self.data_format)
-
-    def calc_loss(self, labels, outputs, trainable_vars):
-        loss = G.softmax_cross_entropy(labels, outputs)
-        loss += FLAGS.loss_w_dcy * G.add_n([G.l2_loss(var) for var in trainable_vars])
-        metrics = {'accuracy': G.accuracy(labels, outputs)}
-        return loss, metrics
-
-    def setup_lrn_rate(self, global_step):
-        nb_epochs = 250
-        idxs_epoch = [100, 150, 200]
-        decay_rates = [1.0, 0.1, 0.01, 0.001]
-        batch_size = FLAGS.batch_size * (1 if not FLAGS.enbl_multi_gpu else mgw.size())
-        lrn_rate = setup_lrn_rate_piecewise_constant(global_step, batch_size, idxs_epoch, decay_rates)
-        nb_iters = int(FLAGS.nb_smpls_train * nb_epochs * FLAGS.nb_epochs_rat / batch_size)
-        return lrn_rate, nb_iters
 
     @property
     def model_name(self):
         return 'lenet'
-
-    @property
-    def dataset_name(self):
-        return 'cifar_10'

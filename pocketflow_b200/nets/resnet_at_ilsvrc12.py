@@ -1,75 +1,43 @@
-"""Model helper for creating a ResNet model for the ILSVRC-12 dataset
+"""ResNet-18/34/50/101/152/200 on ILSVRC-12 behind the ModelHelper plugin surface
 (/root/reference/nets/resnet_at_ilsvrc12.py:29-165)."""
-from .. import graph as G
 from ..flags import FLAGS, DEFINE_integer, DEFINE_float
 from ..datasets.ilsvrc12_dataset import Ilsvrc12Dataset
-from ..utils.lrn_rate_utils import setup_lrn_rate_piecewise_constant
-from ..utils.multi_gpu_wrapper import MultiGpuWrapper as mgw
-from .abstract_model_helper import AbstractModelHelper
+from .classification_helper import ClassificationModelHelper
 from . import resnet_model as ResNet
 
-DEFINE_integer('resnet_size', 18, '# of layers in the ResNet model')
-DEFINE_float('nb_epochs_rat', 1.0, '# of training epochs\'s ratio')
-DEFINE_float('lrn_rate_init', 1e-1, 'initial learning rate')
-DEFINE_float('batch_size_norm', 256, 'normalization factor of batch size')
-DEFINE_float('momentum', 0.9, 'momentum coefficient')
-DEFINE_float('loss_w_dcy', 1e-4, 'weight decaying loss\'s coefficient')
+DEFINE_integer('resnet_size', 18, 'depth of the ResNet')
+DEFINE_float('nb_epochs_rat', 1.0, 'scales the number of training epochs')
+DEFINE_float('lrn_rate_init', 1e-1, 'learning rate at batch size batch_size_norm')
+DEFINE_float('batch_size_norm', 256, 'batch size the initial learning rate is quoted for')
+DEFINE_float('momentum', 0.9, 'momentum of the SGD optimizer')
+DEFINE_float('loss_w_dcy', 1e-4, 'weight of the L2 term')
+
+BLOCKS_PER_STAGE = {18: [2, 2, 2, 2], 34: [3, 4, 6, 3], 50: [3, 4, 6, 3], 101: [3, 4, 23, 3], 152: [3, 8, 36, 3],
+                    200: [3, 24, 36, 3]}
 
 
 def get_block_sizes(resnet_size):
-    choices = {18: [2, 2, 2, 2], 34: [3, 4, 6, 3], 50: [3, 4, 6, 3], 101: [3, 4, 23, 3],
-               152: [3, 8, 36, 3], 200: [3, 24, 36, 3]}
-    try:
-        return choices[resnet_size]
-    except KeyError:
+    if resnet_size not in BLOCKS_PER_STAGE:
         raise ValueError('invalid # of layers for ResNet: {}'.format(resnet_size))
+    return BLOCKS_PER_STAGE[resnet_size]
 
 
 def forward_fn(inputs, is_train, data_format):
-    bottleneck = FLAGS.resnet_size >= 50
-    model = ResNet.Model(FLAGS.resnet_size, bottleneck, FLAGS.nb_classes, 64, 7, 2, 3, 2,
+    """64 filters, 7x7 stride-2 stem + 3x3 stride-2 max-pool, four stages; bottleneck blocks from depth 50 on."""
+    model = ResNet.Model(FLAGS.resnet_size, FLAGS.resnet_size >= 50, FLAGS.nb_classes, 64, 7, 2, 3, 2,
                          get_block_sizes(FLAGS.resnet_size), [1, 2, 2, 2], data_format=data_format)
     return model(inputs, is_train)
 
 
-class ModelHelper(AbstractModelHelper):
-    def __init__(self, data_format='channels_last'):
-        super(ModelHelper, self).__init__(data_format)
-        self.dataset_train = Ilsvrc12Dataset(is_train=True)
-        self.dataset_eval = Ilsvrc12Dataset(is_train=False)
+class ModelHelper(ClassificationModelHelper):
+    DATASET, DATASET_NAME = Ilsvrc12Dataset, 'ilsvrc_12'
+    NB_EPOCHS, IDXS_EPOCH, DECAY_RATES = 100, [30, 60, 80, 90], [1.0, 0.1, 0.01, 0.001, 0.0001]
+    L2_SKIPS = 'batch_normalization'
+    TOP5 = True
 
-    def build_dataset_train(self, enbl_trn_val_split=False):
-        return self.dataset_train.build(enbl_trn_val_split)
-
-    def build_dataset_eval(self):
-        return self.dataset_eval.build()
-
-    def forward_train(self, inputs):
-        return forward_fn(inputs, is_train=True, data_format=self.data_format)
-
-    def forward_eval(self, inputs):
-        return forward_fn(inputs, is_train=False, data_format=self.data_format)
-
-    def calc_loss(self, labels, outputs, trainable_vars):
-        loss = G.softmax_cross_entropy(labels, outputs)
-        loss_filter = lambda var: 'batch_normalization' not in var.name
-        loss += FLAGS.loss_w_dcy * G.add_n([G.l2_loss(var) for var in trainable_vars if loss_filter(var)])
-        metrics = {'acc_top1': G.accuracy(labels, outputs), 'acc_top5': G.in_top_k_accuracy(labels, outputs, 5)}
-        return loss, metrics
-
-    def setup_lrn_rate(self, global_step):
-        nb_epochs = 100
-        idxs_epoch = [30, 60, 80, 90]
-        decay_rates = [1.0, 0.1, 0.01, 0.001, 0.0001]
-        batch_size = FLAGS.batch_size * (1 if not FLAGS.enbl_multi_gpu else mgw.size())
-        lrn_rate = setup_lrn_rate_piecewise_constant(global_step, batch_size, idxs_epoch, decay_rates)
-        nb_iters = int(FLAGS.nb_smpls_train * nb_epochs * FLAGS.nb_epochs_rat / batch_size)
-        return lrn_rate, nb_iters
+    def network(self, inputs, is_train):
+        return forward_fn(inputs, is_train=is_train, data_format=self.data_format)
 
     @property
     def model_name(self):
         return 'resnet_%d' % FLAGS.resnet_size
-
-    @property
-    def dataset_name(self):
-        return 'ilsvrc_12'
