@@ -14,6 +14,7 @@ import sys
 import types
 
 REF = '/root/reference'
+HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'ref_executed_v1.json')
 
 
@@ -755,6 +756,125 @@ def main():
                                              overall=float(h.calc_overall_prune_ratio()), reward=float(h.calc_reward(0.8))))
                     gold['ws_rl_helper'].append(dict(shapes=[list(s) for s in shapes], ws_prune_ratio=target, reward_type=reward_type,
                                                      skip_head_n_tail=skip, s_dims=int(h.s_dims), rollouts=rollouts))
+    # ---- input pipelines: datasets/cifar10_dataset.py:parse_fn and utils/external/imagenet_preprocessing.py executed from
+    # the reference source.  Random ops are stubs that take their draws from `ctl`; JPEG decoding is Pillow and
+    # tf.image.resize_images is this repo's resize_bilinear (so the resize ARITHMETIC is not pinned here — its call
+    # arguments, the target-size arithmetic, crop offsets, flip order, mean subtraction and the
+    # sample_distorted_bounding_box parameters are).
+    import base64
+    import hashlib
+    import io as _io
+    from PIL import Image as _Image
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from pocketflow_b200.datasets.ilsvrc12_dataset import resize_bilinear as _resize
+
+    class TT(np.ndarray):
+        def get_shape(self):
+            return types.SimpleNamespace(ndims=self.ndim)
+
+        def set_shape(self, shape):
+            assert list(self.shape) == list(shape), (self.shape, shape)
+
+    def T(x, dtype=None):
+        return np.asarray(x, dtype).view(TT)
+    ctl = {}
+    calls = []
+
+    def _decode(buf):
+        return T(np.asarray(_Image.open(_io.BytesIO(buf)).convert('RGB'), np.uint8))
+
+    def _sdbb(shape, bounding_boxes=None, **kw):
+        calls.append(('sample_distorted_bounding_box', {k: (list(v) if isinstance(v, (list, tuple)) else v) for k, v in kw.items()},
+                      np.asarray(bounding_boxes).shape))
+        y, x, h, w = ctl['crop']
+        return T([y, x, 0]), T([h, w, -1]), None
+
+    def _crop_jpeg(buf, window, channels=3):
+        y, x, h, w = [int(v) for v in window]
+        return _decode(buf)[y:y + h, x:x + w]
+
+    def _resize_images(image, size, method=None, align_corners=None):
+        calls.append(('resize_images', [int(size[0]), int(size[1])], method, align_corners))
+        return T(_resize(np.asarray(image), int(size[0]), int(size[1])))
+
+    def _slice(t, begin, size):
+        idx = tuple(slice(int(b), None if int(s) == -1 else int(b) + int(s)) for b, s in zip(begin, size))
+        return t[idx]
+
+    def _cast(x, dtype):
+        return T(np.asarray(x).astype(dtype)) if np.ndim(x) else dtype(x)
+    tfd = make_tf_stub(flags)
+    tfd.float32, tfd.int32, tfd.uint8 = np.float32, np.int32, np.uint8
+    tfd.constant = lambda v, dtype=None: T(v, dtype)
+    tfd.shape = lambda t: np.array(t.shape)
+    tfd.cast = _cast
+    tfd.minimum = lambda a, b: min(a, b)
+    tfd.unstack = lambda t: list(t)
+    tfd.stack = lambda vals: T(vals)
+    tfd.slice = _slice
+    tfd.expand_dims = lambda t, axis: T(np.expand_dims(np.asarray(t, np.float32), axis))
+    tfd.reshape = lambda t, shape: T(np.reshape(t, shape))
+    tfd.transpose = lambda t, perm: T(np.transpose(t, perm))
+    tfd.decode_raw = lambda s, dtype: T(np.frombuffer(s, dtype))
+    tfd.one_hot = lambda i, k: T(np.eye(int(k), dtype=np.float32)[int(i)])
+    tfd.random_crop = lambda t, size: t[ctl['oy']:ctl['oy'] + size[0], ctl['ox']:ctl['ox'] + size[1]]
+
+    def _crop_or_pad(image, th, tw):
+        h, w = image.shape[:2]
+        assert th >= h and tw >= w
+        out = np.zeros((th, tw, image.shape[2]), image.dtype)
+        out[(th - h) // 2:(th - h) // 2 + h, (tw - w) // 2:(tw - w) // 2 + w] = image
+        return T(out)
+    tfd.image = types.SimpleNamespace(
+        sample_distorted_bounding_box=_sdbb, extract_jpeg_shape=lambda b: np.array(_decode(b).shape),
+        decode_and_crop_jpeg=_crop_jpeg, decode_jpeg=lambda b, channels=3: _decode(b),
+        random_flip_left_right=lambda t: t[:, ::-1] if ctl['flip'] else t,
+        resize_images=_resize_images, ResizeMethod=types.SimpleNamespace(BILINEAR='BILINEAR'),
+        resize_image_with_crop_or_pad=_crop_or_pad)
+    stubs_d = dict(stubs)
+    stubs_d['tensorflow'] = tfd
+    stubs_d['datasets'] = types.ModuleType('datasets')
+    stubs_d['datasets.abstract_dataset'] = blank(AbstractDataset=object)
+    ipp = load('utils/external/imagenet_preprocessing.py', 'ref_imagenet_preprocessing', stubs_d)
+    cif = load('datasets/cifar10_dataset.py', 'ref_cifar10_dataset', stubs_d)
+
+    def digest(a):
+        a = np.ascontiguousarray(np.asarray(a, np.float32))
+        return dict(shape=list(a.shape), sha256=hashlib.sha256(a.tobytes()).hexdigest(),
+                    samples=[float(a.reshape(-1)[i]) for i in (0, a.size // 3, a.size - 1)])
+    gold['imagenet_preprocessing'] = []
+    rng = np.random.RandomState(31)
+    for ci, (h, w) in enumerate([(300, 400), (375, 500), (256, 256), (500, 333), (90, 120)]):
+        base_img = rng.randint(0, 256, (h // 8 + 1, w // 8 + 1, 3)).astype(np.uint8)
+        b = _io.BytesIO()
+        _Image.fromarray(np.kron(base_img, np.ones((8, 8, 1), np.uint8))[:h, :w]).save(b, format='JPEG', quality=90)
+        jpeg = b.getvalue()
+        rec = dict(jpeg_b64=base64.b64encode(jpeg).decode('ascii'), height=h, width=w)
+        del calls[:]
+        rec['eval'] = digest(ipp.preprocess_image(jpeg, np.zeros((1, 0, 4), np.float32), 224, 224, 3, is_training=False))
+        rec['eval_calls'] = [list(c) for c in calls]
+        rec['train'] = []
+        for flip in (False, True):
+            ch, cw = int(rng.randint(h // 3, h + 1)), int(rng.randint(w // 3, w + 1))
+            cy, cx = int(rng.randint(0, h - ch + 1)), int(rng.randint(0, w - cw + 1))
+            ctl.update(crop=(cy, cx, ch, cw), flip=flip)
+            del calls[:]
+            out = ipp.preprocess_image(jpeg, np.zeros((1, 2, 4), np.float32), 224, 224, 3, is_training=True)
+            rec['train'].append(dict(crop=[cy, cx, ch, cw], flip=flip, out=digest(out), calls=[list(c) for c in calls]))
+        gold['imagenet_preprocessing'].append(rec)
+    gold['imagenet_constants'] = dict(means=[float(v) for v in ipp._CHANNEL_MEANS], resize_min=int(ipp._RESIZE_MIN))
+    gold['cifar10_parse_fn'] = []
+    flags.nb_classes = 10
+    for ci in range(6):
+        record = rng.randint(0, 256, 1 + 3 * 32 * 32).astype(np.uint8)
+        record[0] = ci + 2
+        img, lab = cif.parse_fn(record.tobytes(), is_train=False)
+        item = dict(record_b64=base64.b64encode(record.tobytes()).decode('ascii'), label=np.asarray(lab).tolist(), eval=digest(img), train=[])
+        for oy, ox, flip in ((0, 0, False), (8, 8, True), (3, 5, False), (4, 4, True)):
+            ctl.update(oy=oy, ox=ox, flip=flip)
+            img, _ = cif.parse_fn(record.tobytes(), is_train=True)
+            item['train'].append(dict(oy=oy, ox=ox, flip=flip, out=digest(img)))
+        gold['cifar10_parse_fn'].append(item)
     json.dump(gold, open(OUT, 'w'), indent=1)
     print('wrote', OUT, {k: len(v) for k, v in gold.items() if isinstance(v, list)})
 

@@ -159,3 +159,42 @@ def test_learner_evaluates_on_the_eval_split_when_real_data_is_configured(cifar)
     assert sorted(np.round(got.reshape(30, -1).sum(1), 2).tolist()) == sorted(np.round(want.reshape(30, -1).sum(1), 2).tolist())
     FLAGS.data_dir_local = None
     assert lrn.eval_iterator() is lrn.iterator_train
+
+
+def test_parse_fn_matches_the_executed_reference_source(cifar):
+    """datasets/cifar10_dataset.py:parse_fn executed from the reference source with numpy stand-ins (controlled crop
+    offsets / flip): record layout, standardisation (true fp32 division), +8 zero padding, crop, flip."""
+    import base64
+    import hashlib
+    import json
+    C, _, _ = cifar
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'ref_executed_v1.json')))['cifar10_parse_fn']
+    assert len(gold) == 6
+
+    def digest(a):
+        a = np.ascontiguousarray(np.asarray(a, np.float32))
+        return list(a.shape), hashlib.sha256(a.tobytes()).hexdigest()
+
+    class Draws(object):
+        """stands in for numpy's Generator inside `augment`: hands out the golden's crop offsets and flip."""
+
+        def __init__(self, oy, ox, flip):
+            self.ints, self.flip = [np.array([oy]), np.array([ox])], flip
+
+        def integers(self, lo, hi, size):
+            return self.ints.pop(0)
+
+        def random(self, n):
+            return np.array([0.25 if self.flip else 0.75])
+    for g in gold:
+        path = os.path.join(FLAGS.data_dir_local, 'one_record.bin')
+        open(path, 'wb').write(base64.b64decode(g['record_b64']))
+        lab, img = C.read_records(path)
+        onehot = np.zeros(10, np.float32)
+        onehot[lab[0]] = 1.0
+        assert onehot.tolist() == g['label']
+        std = C.standardize(img)
+        assert digest(std[0]) == (g['eval']['shape'], g['eval']['sha256'])
+        for tr in g['train']:
+            out = C.augment(std, Draws(tr['oy'], tr['ox'], tr['flip']))
+            assert digest(out[0]) == (tr['out']['shape'], tr['out']['sha256']), tr

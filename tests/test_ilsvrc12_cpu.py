@@ -321,3 +321,48 @@ def test_packed_stream_through_feed_equals_the_host_pipeline(tmp_path, monkeypat
         assert all(b == 4 * 224 * 224 * 3 * 4 + 4 * 1001 * 4 for b in host_bytes)
         assert all(b < 0.6 * host_bytes[0] for b in dev_bytes)                  # uint8 crops: far fewer bytes per step
     FLAGS.reset()
+
+
+def _digest(a):
+    import hashlib
+    a = np.ascontiguousarray(np.asarray(a, np.float32))
+    return list(a.shape), hashlib.sha256(a.tobytes()).hexdigest()
+
+
+def test_preprocessing_matches_the_executed_reference_source():
+    """utils/external/imagenet_preprocessing.py:preprocess_image was executed (tests/golden/make_golden_from_reference.py)
+    with numpy stand-ins for the TensorFlow ops — Pillow for the JPEG decode, this repo's resize_bilinear for
+    tf.image.resize_images, controlled draws for the random ops.  Pinned here: the resize target arithmetic, crop
+    offsets, crop -> flip -> resize order, mean subtraction, and the sample_distorted_bounding_box parameters."""
+    import base64
+    import json
+    from pocketflow_b200.datasets import ilsvrc12_dataset as D
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'ref_executed_v1.json')))
+    assert gold['imagenet_constants'] == dict(means=[float(np.float64(v)) for v in (123.68, 116.78, 103.94)], resize_min=D.RESIZE_MIN)
+    assert [float(v) for v in D.CHANNEL_MEANS] == [float(np.float32(v)) for v in gold['imagenet_constants']['means']]
+    import inspect
+    sig = inspect.signature(D.sample_distorted_bounding_box).parameters
+    for rec in gold['imagenet_preprocessing']:
+        jpeg = base64.b64decode(rec['jpeg_b64'])
+        assert D.jpeg_shape(jpeg) == (rec['height'], rec['width'])
+        out = D.preprocess_image(jpeg, np.zeros((0, 4), np.float32), False)
+        assert _digest(out) == (rec['eval']['shape'], rec['eval']['sha256'])
+        (name, size, method, align), = rec['eval_calls']
+        assert name == 'resize_images' and tuple(size) == D.smallest_size_at_least(rec['height'], rec['width'])
+        assert method == 'BILINEAR' and align is False
+        for tr in rec['train']:
+            cy, cx, ch, cw = tr['crop']
+            # the same crop and flip draw, through this repo's functions
+            crop = D.decode_jpeg(jpeg, (cy, cx, ch, cw))
+            img = D.resize_bilinear(crop[:, ::-1] if tr['flip'] else crop, 224, 224) - D.CHANNEL_MEANS
+            assert _digest(img) == (tr['out']['shape'], tr['out']['sha256'])
+            d = np.zeros((), D.IMG_DESC)
+            d['h'], d['w'], d['rh'], d['rw'], d['flip'] = ch, cw, 224, 224, int(tr['flip'])
+            assert _digest(D.preprocess_from_descriptor(crop, d)) == (tr['out']['shape'], tr['out']['sha256'])
+            sdbb = tr['calls'][0]
+            assert sdbb[0] == 'sample_distorted_bounding_box' and sdbb[1]['use_image_if_no_bounding_boxes'] is True
+            assert sdbb[1]['min_object_covered'] == sig['min_object_covered'].default
+            assert tuple(sdbb[1]['aspect_ratio_range']) == sig['aspect_ratio_range'].default
+            assert tuple(sdbb[1]['area_range']) == sig['area_range'].default
+            assert sdbb[1]['max_attempts'] == sig['max_attempts'].default
+            assert tr['calls'][1] == ['resize_images', [224, 224], 'BILINEAR', False]
