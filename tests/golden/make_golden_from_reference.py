@@ -875,6 +875,36 @@ def main():
             img, _ = cif.parse_fn(record.tobytes(), is_train=True)
             item['train'].append(dict(oy=oy, ox=ox, flip=flip, out=digest(img)))
         gold['cifar10_parse_fn'].append(item)
+    # ---- every ModelHelper's flag defaults, schedule constants and names (nets/*_at_*.py), from the reference source
+    gold['net_helpers'] = []
+    for ref_file, extra in [('nets/lenet_at_cifar10.py', {}), ('nets/resnet_at_cifar10.py', dict(resnet_size=20)),
+                            ('nets/resnet_at_ilsvrc12.py', dict(resnet_size=50)), ('nets/mobilenet_at_ilsvrc12.py', {})]:
+        fl = Flags()
+        tfn = make_tf_stub(fl)
+        seen = []
+        st = dict(stubs4)
+        st['tensorflow'] = tfn
+        st['utils.lrn_rate_utils'] = blank(
+            setup_lrn_rate_piecewise_constant=lambda gs, bs, idxs, rates: (seen.append((bs, list(idxs), list(rates))), 'lr')[1],
+            setup_lrn_rate_exponential_decay=None)
+        world_n = {'size': 1}
+        st['utils.multi_gpu_wrapper'] = blank(MultiGpuWrapper=types.SimpleNamespace(size=lambda: world_n['size'], rank=lambda: 0))
+        mod = load(ref_file, 'ref_helper_' + os.path.basename(ref_file)[:-3], st)
+        defaults = {k: v for k, v in vars(fl).items()}
+        for k, v in extra.items():
+            setattr(fl, k, v)
+        me = types.SimpleNamespace()
+        rec = dict(file=ref_file, flag_defaults=defaults, model_name=mod.ModelHelper.model_name.fget(me),
+                   dataset_name=mod.ModelHelper.dataset_name.fget(me), schedules=[])
+        for multi, size, bs, nsmp, rat in [(False, 1, 128, 50000, 1.0), (True, 4, 64, 1281167, 1.0), (True, 8, 32, 1281167, 0.5)]:
+            fl.enbl_multi_gpu, fl.batch_size, fl.nb_smpls_train, fl.nb_epochs_rat = multi, bs, nsmp, rat
+            world_n['size'] = size
+            del seen[:]
+            lr, nb_iters = mod.ModelHelper.setup_lrn_rate(me, None)
+            (gbs, idxs, rates), = seen
+            rec['schedules'].append(dict(enbl_multi_gpu=multi, world=size, batch_size=bs, nb_smpls_train=nsmp, nb_epochs_rat=rat,
+                                         global_batch=gbs, idxs_epoch=idxs, decay_rates=rates, nb_iters=int(nb_iters)))
+        gold['net_helpers'].append(rec)
     json.dump(gold, open(OUT, 'w'), indent=1)
     print('wrote', OUT, {k: len(v) for k, v in gold.items() if isinstance(v, list)})
 

@@ -610,3 +610,39 @@ def test_lenet_architecture_matches_the_reference_source():
             mine.append(['flatten'])
     assert mine == _ref_gold()['lenet_architecture']
     FLAGS.reset()
+
+
+def test_model_helpers_flag_defaults_schedules_and_names_match_the_reference_source(monkeypatch):
+    """Every nets/*_at_*.py of the reference, loaded under the stub: the flag defaults it declares, model / dataset names
+    and what its setup_lrn_rate hands to the schedule (global batch, drop epochs, multipliers) and returns (# of
+    iterations) — against this repo's ModelHelpers."""
+    import importlib
+    from pocketflow_b200.flags import FLAGS
+    from pocketflow_b200.utils.multi_gpu_wrapper import MultiGpuWrapper as mgw
+    gold = _ref_gold()['net_helpers']
+    assert [g['file'] for g in gold] == ['nets/lenet_at_cifar10.py', 'nets/resnet_at_cifar10.py', 'nets/resnet_at_ilsvrc12.py',
+                                         'nets/mobilenet_at_ilsvrc12.py']
+    world = {'size': 1}
+    monkeypatch.setattr(mgw, 'size', classmethod(lambda cls: world['size']))
+    from pocketflow_b200.nets import classification_helper as CH
+    seen = []
+    real = CH.setup_lrn_rate_piecewise_constant
+    monkeypatch.setattr(CH, 'setup_lrn_rate_piecewise_constant',
+                        lambda gs, bs, idxs, rates: (seen.append((bs, list(idxs), list(rates))), real(gs, bs, idxs, rates))[1])
+    for g in gold:
+        FLAGS.reset()
+        mod = importlib.reload(importlib.import_module('pocketflow_b200.' + g['file'][:-3].replace('/', '.')))
+        for name, default in g['flag_defaults'].items():
+            assert getattr(FLAGS, name) == default, (g['file'], name)      # (DEFINE_float(…, 128) holds 128.0)
+        if 'resnet' in g['file']:
+            FLAGS.resnet_size = int(g['model_name'].split('_')[1])
+        mh = mod.ModelHelper()
+        assert (mh.model_name, mh.dataset_name) == (g['model_name'], g['dataset_name'])
+        for s in g['schedules']:
+            FLAGS.enbl_multi_gpu, FLAGS.batch_size = s['enbl_multi_gpu'], s['batch_size']
+            FLAGS.nb_smpls_train, FLAGS.nb_epochs_rat = s['nb_smpls_train'], s['nb_epochs_rat']
+            world['size'] = s['world']
+            del seen[:]
+            _, nb_iters = mh.setup_lrn_rate(None)
+            assert seen == [(s['global_batch'], s['idxs_epoch'], s['decay_rates'])] and nb_iters == s['nb_iters'], (g['file'], s)
+    FLAGS.reset()
