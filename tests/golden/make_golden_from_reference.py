@@ -905,6 +905,44 @@ def main():
             rec['schedules'].append(dict(enbl_multi_gpu=multi, world=size, batch_size=bs, nb_smpls_train=nsmp, nb_epochs_rat=rat,
                                          global_batch=gbs, idxs_epoch=idxs, decay_rates=rates, nb_iters=int(nb_iters)))
         gold['net_helpers'].append(rec)
+    # ---- the flag defaults every reference module on the path declares (tf.app.flags.DEFINE_* at import time)
+    gold['flag_defaults'] = {}
+    flag_files = ['learners/abstract_learner.py', 'learners/distillation_helper.py',
+                  'learners/uniform_quantization/learner.py', 'learners/uniform_quantization/bit_optimizer.py',
+                  'learners/nonuniform_quantization/learner.py', 'learners/weight_sparsification/learner.py',
+                  'learners/channel_pruning_gpu/learner.py', 'learners/full_precision/learner.py',
+                  'datasets/abstract_dataset.py', 'datasets/cifar10_dataset.py', 'datasets/ilsvrc12_dataset.py',
+                  'rl_agents/ddpg/agent.py', 'rl_agents/ddpg/actor_critic.py', 'rl_agents/ddpg/noise.py',
+                  'rl_agents/ddpg/running_mean_std.py', 'utils/lrn_rate_utils.py']
+
+    class _Anything(types.ModuleType):
+        def __getattr__(self, name):
+            if name.startswith('__'):
+                raise AttributeError(name)
+            if name[0].isupper():                      # something the module may subclass
+                return type(name, (object,), {})
+            return _Anything(name)
+
+        def __call__(self, *a, **k):
+            return _Anything('call')
+    for ref_file in flag_files:
+        fl = Flags()
+        tff = make_tf_stub(fl)
+        st = {k: _Anything(k) for k in list(stubs_d) + list(stubs4) + [
+            'mpi4py', 'rl_agents.ddpg.actor_critic', 'rl_agents.ddpg.noise', 'rl_agents.ddpg.replay_buffer',
+            'rl_agents.ddpg.running_mean_std', 'utils.external.imagenet_preprocessing', 'learners.full_precision',
+            'learners.full_precision.learner', 'learners.channel_pruning_gpu', 'learners.weight_sparsification.pr_optimizer',
+            'learners.nonuniform_quantization.rl_helper', 'learners.uniform_quantization.rl_helper', 'tensorflow.contrib']}
+        tff.constant = lambda *a, **k: None
+        tff.float32, tff.int32, tff.uint8 = np.float32, np.int32, np.uint8
+        tff.contrib = _Anything('contrib')
+        st['tensorflow'] = tff
+        try:
+            load(ref_file, 'ref_flags_' + ref_file.replace('/', '_')[:-3], st)
+        except Exception as e:  # pylint: disable=broad-except
+            print('flag_defaults: could not load', ref_file, repr(e)[:200])
+            continue
+        gold['flag_defaults'][ref_file] = dict(vars(fl))
     json.dump(gold, open(OUT, 'w'), indent=1)
     print('wrote', OUT, {k: len(v) for k, v in gold.items() if isinstance(v, list)})
 

@@ -646,3 +646,44 @@ def test_model_helpers_flag_defaults_schedules_and_names_match_the_reference_sou
             _, nb_iters = mh.setup_lrn_rate(None)
             assert seen == [(s['global_batch'], s['idxs_epoch'], s['decay_rates'])] and nb_iters == s['nb_iters'], (g['file'], s)
     FLAGS.reset()
+
+
+def test_flag_defaults_match_the_reference_modules():
+    """Every tf.app.flags.DEFINE_* of the reference modules on the path (collected by importing them under the stub)
+    against the flag this repo's same-named module declares: same name, same default."""
+    import ast
+    import os
+    from pocketflow_b200.flags import FLAGS
+    gold = _ref_gold()['flag_defaults']
+    assert len(gold) == 16 and sum(len(v) for v in gold.values()) >= 100
+    # flags this build deliberately does not declare (the subsystem behind them is out of scope, DESIGN §7)
+    absent = {
+        'learners/channel_pruning_gpu/learner.py': set(),
+        'rl_agents/ddpg/running_mean_std.py': {'ddpg_rms_eps'},          # state / return normalisation: dead code upstream
+    }
+    changed = {
+        # the reference ships 'optimal' pruning ratios through files and a separate session; semantics kept, default kept
+    }
+    missing, different = [], []
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for ref_file, defaults in gold.items():
+        if ref_file == 'rl_agents/ddpg/running_mean_std.py':
+            continue
+        # this repo's declarations, read from the source (several modules re-declare a flag with their own default,
+        # so the process-global FLAGS only knows the last one imported)
+        tree = ast.parse(open(os.path.join(root, 'pocketflow_b200', ref_file)).read())
+        mine = {}
+        for node in ast.walk(tree):
+            if isinstance(node, ast.Call) and getattr(node.func, 'id', '').startswith('DEFINE_'):
+                value = ast.literal_eval(node.args[1])
+                mine[ast.literal_eval(node.args[0])] = float(value) if node.func.id == 'DEFINE_float' and value is not None else value
+        for name, default in defaults.items():
+            if name in absent.get(ref_file, ()):
+                continue
+            if name not in mine:
+                missing.append((ref_file, name))
+            elif mine[name] != default and (ref_file, name) not in changed:
+                different.append((ref_file, name, default, mine[name]))
+    FLAGS.reset()
+    assert not different, different
+    assert not missing, missing
