@@ -943,6 +943,62 @@ def main():
             print('flag_defaults: could not load', ref_file, repr(e)[:200])
             continue
         gold['flag_defaults'][ref_file] = dict(vars(fl))
+    # ---- WeightSparseLearner.train (learners/weight_sparsification/learner.py:101-143): WHEN masks are rebuilt and the
+    # model saved, from the reference's own loop driven with a recording session
+    wsl = load('learners/weight_sparsification/learner.py', 'ref_ws_learner_loop', stubs3)
+    gold['ws_train_loop'] = []
+    for nb_iters, upd, beg, end, save, summ in [(1000, 100, 0.1, 0.5, 400, 250), (1000, 100, 0.0, 1.0, 10000, 100),
+                                                (4000, 500, 0.1, 0.5, 1000, 100), (1000, 300, 0.25, 0.6, 10000, 100),
+                                                (777, 50, 0.33, 0.34, 10000, 100), (1000, 100, 0.95, 0.99, 10000, 100)]:
+        flags.ws_mask_update_step, flags.ws_iter_ratio_beg, flags.ws_iter_ratio_end = upd, beg, end
+        flags.save_step, flags.summ_step, flags.enbl_multi_gpu = save, summ, False
+        ev = dict(train=0, prune=[], save=[], evaluate=0, monitor=[])
+        it = {'i': 0}
+
+        def run(op, ev=ev, it=it):
+            ops_ = op if isinstance(op, list) else [op]
+            if 'train' in ops_:
+                ev['train'] += 1
+                it['i'] = ev['train']
+            if 'prune' in ops_:
+                assert 'init_opt' in ops_
+                ev['prune'].append(it['i'])
+            return [None, None, None]
+        me = types.SimpleNamespace(sess_train=types.SimpleNamespace(run=run), init_op='init', bcast_op='bcast', train_op='train',
+                                   summary_op='summary', log_op='log', prune_op='prune', init_opt_op='init_opt',
+                                   nb_iters_train=nb_iters, is_primary_worker=lambda scope='global': True,
+                                   evaluate=lambda ev=ev: ev.__setitem__('evaluate', ev['evaluate'] + 1))
+        me._WeightSparseLearner__monitor_progress = lambda s, l, i, t, ev=ev: ev['monitor'].append(i + 1)
+        me._WeightSparseLearner__save_model = lambda ev=ev, it=it: ev['save'].append(it['i'])
+        wsl.WeightSparseLearner.train(me)
+        gold['ws_train_loop'].append(dict(nb_iters_train=nb_iters, ws_mask_update_step=upd, ws_iter_ratio_beg=beg, ws_iter_ratio_end=end,
+                                          save_step=save, summ_step=summ, events=ev))
+    # ---- UniformQuantLearner.train (learners/uniform_quantization/learner.py:113-149): cadence of logging, saving,
+    # evaluating and barriers; warm start restores first
+    gold['uq_train_loop'] = []
+    for steps, save, summ, warm in [(1000, 400, 250, False), (1200, 300, 100, True), (50, 10000, 100, False)]:
+        flags.save_step, flags.summ_step, flags.enbl_warm_start, flags.enbl_multi_gpu = save, summ, warm, False
+        ev = []
+        n = {'train': 0}
+
+        def run(op, feed_dict=None, ev=ev, n=n):
+            ops_ = op if isinstance(op, list) else [op]
+            if 'train' in ops_:
+                n['train'] += 1
+            elif ops_ == ['init']:
+                ev.append('init')
+            return [None, None, None]
+        me = types.SimpleNamespace(sess_train=types.SimpleNamespace(run=run), finetune_steps=steps,
+                                   ops=dict(init='init', bcast='bcast', train='train', summary='summary', log='log'),
+                                   bit_placeholders=dict(w_train='w', a_train='a'), optimal_w_bit_list=[8], optimal_a_bit_list=[8],
+                                   auto_barrier=lambda ev=ev, n=n: ev.append(('barrier', n['train'])),
+                                   evaluate=lambda ev=ev, n=n: ev.append(('evaluate', n['train'])))
+        me._UniformQuantLearner__restore_model = lambda is_train, ev=ev, n=n: ev.append(('restore', is_train, n['train']))
+        me._UniformQuantLearner__save_model = lambda ev=ev, n=n: ev.append(('save', n['train']))
+        me._UniformQuantLearner__monitor_progress = lambda s, l, t, i, ev=ev: (ev.append(('monitor', i + 1)), t)[1]
+        uq.UniformQuantLearner.train(me)
+        gold['uq_train_loop'].append(dict(finetune_steps=steps, save_step=save, summ_step=summ, enbl_warm_start=warm,
+                                          nb_train=n['train'], events=[list(e) if isinstance(e, tuple) else e for e in ev]))
     json.dump(gold, open(OUT, 'w'), indent=1)
     print('wrote', OUT, {k: len(v) for k, v in gold.items() if isinstance(v, list)})
 

@@ -687,3 +687,51 @@ def test_flag_defaults_match_the_reference_modules():
     FLAGS.reset()
     assert not different, different
     assert not missing, missing
+
+
+def test_ws_training_loop_prunes_and_saves_when_the_reference_loop_does():
+    """WeightSparseLearner.train of the reference was run with a recording session (golden 'ws_train_loop'); this
+    repo's train() driven with recording stand-ins must rebuild the masks after the same iterations (including the one
+    late application after ws_iter_ratio_end) and save at the same steps."""
+    from types import SimpleNamespace
+    from pocketflow_b200.flags import FLAGS
+    from pocketflow_b200.learners.weight_sparsification.learner import WeightSparseLearner as L
+    for g in _ref_gold()['ws_train_loop']:
+        FLAGS.reset()
+        FLAGS.ws_mask_update_step, FLAGS.ws_iter_ratio_beg = g['ws_mask_update_step'], g['ws_iter_ratio_beg']
+        FLAGS.ws_iter_ratio_end, FLAGS.save_step, FLAGS.summ_step = g['ws_iter_ratio_end'], g['save_step'], g['summ_step']
+        ev = dict(train=0, prune=[], save=[], monitor=[])
+        me = SimpleNamespace(sess_train=SimpleNamespace(store=SimpleNamespace(P=None, O=None)), nb_iters_train=g['nb_iters_train'],
+                             is_primary_worker=lambda scope='global': True)
+        me.train_step = lambda: ev.__setitem__('train', ev['train'] + 1)
+        me.prune = lambda: ev['prune'].append(ev['train'])
+        me._WeightSparseLearner__save_model = lambda: ev['save'].append(ev['train'])
+        me._WeightSparseLearner__monitor_progress = lambda i, t: ev['monitor'].append(i + 1)
+        L.train(me)
+        want = g['events']
+        assert ev['train'] == want['train'] and ev['prune'] == want['prune'], g
+        assert ev['save'] == want['save'] and ev['monitor'] == want['monitor'], g
+    FLAGS.reset()
+
+
+def test_uq_training_loop_cadence_matches_the_reference_loop():
+    """UniformQuantLearner.train of the reference, run with a recording session (golden 'uq_train_loop'): warm-start
+    restore, barriers, logging / saving / evaluating steps — against this repo's train() with recording stand-ins."""
+    from types import SimpleNamespace
+    from pocketflow_b200.flags import FLAGS
+    from pocketflow_b200.learners.uniform_quantization.learner import UniformQuantLearner as L
+    for g in _ref_gold()['uq_train_loop']:
+        FLAGS.reset()
+        FLAGS.save_step, FLAGS.summ_step, FLAGS.enbl_warm_start = g['save_step'], g['summ_step'], g['enbl_warm_start']
+        ev, n = [], {'train': 0}
+        me = SimpleNamespace(finetune_steps=g['finetune_steps'], sess_train=SimpleNamespace(fetch_losses=lambda: {}),
+                             train_step=lambda: n.__setitem__('train', n['train'] + 1),
+                             auto_barrier=lambda: ev.append(['barrier', n['train']]),
+                             evaluate=lambda: ev.append(['evaluate', n['train']]))
+        me._UniformQuantLearner__restore_model = lambda is_train: ev.append(['restore', is_train, n['train']])
+        me._UniformQuantLearner__save_model = lambda: ev.append(['save', n['train']])
+        me._UniformQuantLearner__monitor_progress = lambda r, t, i: (ev.append(['monitor', i + 1]), t)[1]
+        L.train(me)
+        assert n['train'] == g['nb_train']
+        assert ev == [e for e in g['events'] if e != 'init'], g          # ('init': variables are initialised at build time here)
+    FLAGS.reset()
