@@ -37,8 +37,17 @@ class FullPrecLearner(AbstractLearner):  # pylint: disable=too-many-instance-att
                 print('iter #%d: lr = %.4e | loss = %.4e | speed = %.2f pics / sec'
                       % (idx_iter + 1, self.lrn_rate(idx_iter), r['loss'], speed))
                 time_prev = timer()
+            # save & evaluate the model at certain steps (learner.py:79-82)
+            if self.is_primary_worker('global') and (idx_iter + 1) % FLAGS.save_step == 0:
+                self.__save_model()
+                self.evaluate()
         if self.is_primary_worker('global'):
-            print('model saved to ' + save_checkpoint(FLAGS.save_path, ex.store.state_dict(), ex.step_count))
+            self.__save_model()
+            self.evaluate()
+
+    def __save_model(self):
+        ex = self.sess_train
+        print('model saved to ' + save_checkpoint(FLAGS.save_path, ex.store.state_dict(), ex.step_count))
 
     def train_step(self):
         ex = self.sess_train

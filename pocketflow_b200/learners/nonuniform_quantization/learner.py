@@ -79,9 +79,20 @@ class NonUniformQuantLearner(AbstractLearner):
                 print('iter #%d: lr = %e | model_loss = %.4f | loss = %.4f | acc_top1 = %.4f | speed = %.2f pics / sec'
                       % (idx_iter + 1, self.lrn_rate(idx_iter), r['model_loss'], r['loss'], r['acc_top1'], speed))
                 time_prev = timer()
-        if self.is_primary_worker():
-            print('quantized model saved to ' + save_checkpoint(FLAGS.nuql_save_quant_model_path,
-                                                                ex.store.state_dict(), ex.step_count))
+            # save & evaluate the model at certain steps (learner.py:148-153)
+            if (idx_iter + 1) % FLAGS.save_step == 0:
+                self.__save_model()
+                self.evaluate()
+                self.auto_barrier()
+        self.__save_model()
+        self.evaluate()
+
+    def __save_model(self):
+        if not self.is_primary_worker():
+            return
+        ex = self.sess_train
+        print('quantized model saved to ' + save_checkpoint(FLAGS.nuql_save_quant_model_path,
+                                                            ex.store.state_dict(), ex.step_count))
 
     def train_step(self):
         ex = self.sess_train
@@ -89,6 +100,8 @@ class NonUniformQuantLearner(AbstractLearner):
         ex.run_step(self.lrn_rate(ex.step_count), self.grad_allreduce())
 
     def evaluate(self, nb_iters=1):
+        if not self.is_primary_worker():
+            return None
         ex = self.sess_train
         out = []
         for _ in range(nb_iters):

@@ -999,6 +999,47 @@ def main():
         uq.UniformQuantLearner.train(me)
         gold['uq_train_loop'].append(dict(finetune_steps=steps, save_step=save, summ_step=summ, enbl_warm_start=warm,
                                           nb_train=n['train'], events=[list(e) if isinstance(e, tuple) else e for e in ev]))
+    # ---- FullPrecLearner.train / NonUniformQuantLearner.train: same cadence pins
+    fpl = load('learners/full_precision/learner.py', 'ref_fp_learner_loop', stubs3)
+    gold['fp_train_loop'] = []
+    for steps, save, summ in [(900, 400, 250), (60, 10000, 100)]:
+        flags.save_step, flags.summ_step, flags.enbl_multi_gpu = save, summ, False
+        ev, n = [], {'train': 0}
+
+        def run_fp(op, ev=ev, n=n):
+            ops_ = op if isinstance(op, list) else [op]
+            if 'train' in ops_:
+                n['train'] += 1
+            return [None, None, None]
+        me = types.SimpleNamespace(sess_train=types.SimpleNamespace(run=run_fp), init_op='init', bcast_op='bcast', train_op='train',
+                                   summary_op='summary', log_op='log', nb_iters_train=steps,
+                                   warm_start=lambda sess, ev=ev: ev.append('warm_start'),
+                                   is_primary_worker=lambda scope='global': True,
+                                   evaluate=lambda ev=ev, n=n: ev.append(['evaluate', n['train']]))
+        me._FullPrecLearner__monitor_progress = lambda s, l, i, t, ev=ev: ev.append(['monitor', i + 1])
+        me._FullPrecLearner__save_model = lambda is_train, ev=ev, n=n: ev.append(['save', bool(is_train), n['train']])
+        me._FullPrecLearner__restore_model = lambda is_train, ev=ev, n=n: ev.append(['restore', bool(is_train), n['train']])
+        fpl.FullPrecLearner.train(me)
+        gold['fp_train_loop'].append(dict(nb_iters_train=steps, save_step=save, summ_step=summ, nb_train=n['train'], events=ev))
+    gold['nuq_train_loop'] = []
+    for steps, save, summ in [(900, 400, 250), (60, 10000, 100)]:
+        flags.save_step, flags.summ_step, flags.enbl_warm_start, flags.enbl_multi_gpu = save, summ, False, False
+        ev, n = [], {'train': 0}
+
+        def run_nuq(op, feed_dict=None, ev=ev, n=n):
+            ops_ = op if isinstance(op, list) else [op]
+            if 'train' in ops_:
+                n['train'] += 1
+            return [None, None, None]
+        me = types.SimpleNamespace(sess_train=types.SimpleNamespace(run=run_nuq), finetune_steps=steps,
+                                   ops=dict(non_cluster_init='nci', cluster_init='ci', bcast='bcast', train='train', summary='summary', log='log'),
+                                   bit_placeholders=dict(w_train='w', a_train='a'), optimal_w_bit_list=[4], optimal_a_bit_list=[32],
+                                   auto_barrier=lambda ev=ev, n=n: ev.append(['barrier', n['train']]),
+                                   evaluate=lambda ev=ev, n=n: ev.append(['evaluate', n['train']]))
+        me._NonUniformQuantLearner__save_model = lambda ev=ev, n=n: ev.append(['save', n['train']])
+        me._NonUniformQuantLearner__monitor_progress = lambda s, l, t, i, ev=ev: (ev.append(['monitor', i + 1]), t)[1]
+        nuq.NonUniformQuantLearner.train(me)
+        gold['nuq_train_loop'].append(dict(finetune_steps=steps, save_step=save, summ_step=summ, nb_train=n['train'], events=ev))
     json.dump(gold, open(OUT, 'w'), indent=1)
     print('wrote', OUT, {k: len(v) for k, v in gold.items() if isinstance(v, list)})
 

@@ -735,3 +735,40 @@ def test_uq_training_loop_cadence_matches_the_reference_loop():
         assert n['train'] == g['nb_train']
         assert ev == [e for e in g['events'] if e != 'init'], g          # ('init': variables are initialised at build time here)
     FLAGS.reset()
+
+
+def test_full_prec_and_nuq_training_loop_cadence_matches_the_reference_loops():
+    from types import SimpleNamespace
+    from pocketflow_b200.flags import FLAGS
+    from pocketflow_b200.learners.full_precision.learner import FullPrecLearner as FP
+    from pocketflow_b200.learners.nonuniform_quantization.learner import NonUniformQuantLearner as NUQ
+    import pocketflow_b200.datasets.cifar10_dataset  # noqa: F401  (declares batch_size for the progress lines)
+    for g in _ref_gold()['fp_train_loop']:
+        FLAGS.reset()
+        FLAGS.save_step, FLAGS.summ_step = g['save_step'], g['summ_step']
+        ev, n = [], {'train': 0}
+        ex = SimpleNamespace(store=SimpleNamespace(P=None, O=None), fetch_losses=lambda: dict(loss=0.0))
+        me = SimpleNamespace(sess_train=ex, nb_iters_train=g['nb_iters_train'], lrn_rate=lambda i: 0.0,
+                             warm_start=lambda sess: ev.append('warm_start'), is_primary_worker=lambda scope='global': True,
+                             train_step=lambda: n.__setitem__('train', n['train'] + 1),
+                             evaluate=lambda: ev.append(['evaluate', n['train']]))
+        me._FullPrecLearner__save_model = lambda: ev.append(['save', True, n['train']])
+        FP.train(me)
+        # one model, one format here: the reference's train-graph -> eval-graph hand-over (restore(False), save(False)) and
+        # its log lines have no counterpart
+        want = [e for e in g['events'] if e[0] not in ('monitor', 'restore') and e[:2] != ['save', False]]
+        assert n['train'] == g['nb_train'] and ev == want, g
+    for g in _ref_gold()['nuq_train_loop']:
+        FLAGS.reset()
+        FLAGS.save_step, FLAGS.summ_step = g['save_step'], g['summ_step']
+        ev, n = [], {'train': 0}
+        ex = SimpleNamespace(store=SimpleNamespace(P=None, O=None), fetch_losses=lambda: dict(loss=0.0, model_loss=0.0, acc_top1=0.0))
+        me = SimpleNamespace(sess_train=ex, finetune_steps=g['finetune_steps'], lrn_rate=lambda i: 0.0,
+                             is_primary_worker=lambda scope='global': True,
+                             train_step=lambda: n.__setitem__('train', n['train'] + 1),
+                             auto_barrier=lambda: ev.append(['barrier', n['train']]),
+                             evaluate=lambda: ev.append(['evaluate', n['train']]))
+        me._NonUniformQuantLearner__save_model = lambda: ev.append(['save', n['train']])
+        NUQ.train(me)
+        assert n['train'] == g['nb_train'] and ev == [e for e in g['events'] if e[0] != 'monitor'], g
+    FLAGS.reset()
