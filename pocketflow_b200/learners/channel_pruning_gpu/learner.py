@@ -62,8 +62,18 @@ class ChannelPrunedGpuLearner(AbstractLearner):  # pylint: disable=too-many-inst
                 print('iter #%d: lr = %.4e | loss = %.4e | pr_msk = %.4e | speed = %.2f pics / sec'
                       % (idx_iter + 1, self.lrn_rate(idx_iter), r['loss'], self.pr_maskable(), speed))
                 time_prev = timer()
+            # save the model at certain steps (learner.py:171-175)
+            if self.is_primary_worker('global') and (idx_iter + 1) % FLAGS.save_step == 0:
+                self.__save_model()
+                self.evaluate()
+            self.auto_barrier()
         if self.is_primary_worker('global'):
-            print('model saved to ' + save_checkpoint(FLAGS.cpg_save_path, ex.store.state_dict(), ex.step_count))
+            self.__save_model()
+            self.evaluate()
+
+    def __save_model(self):
+        ex = self.sess_train
+        print('model saved to ' + save_checkpoint(FLAGS.cpg_save_path, ex.store.state_dict(), ex.step_count))
 
     def train_step(self):
         ex = self.sess_train
