@@ -62,11 +62,14 @@ class ChannelPrunedGpuLearner(AbstractLearner):  # pylint: disable=too-many-inst
                 print('iter #%d: lr = %.4e | loss = %.4e | pr_msk = %.4e | speed = %.2f pics / sec'
                       % (idx_iter + 1, self.lrn_rate(idx_iter), r['loss'], self.pr_maskable(), speed))
                 time_prev = timer()
-            # save the model at certain steps (learner.py:171-175)
-            if self.is_primary_worker('global') and (idx_iter + 1) % FLAGS.save_step == 0:
-                self.__save_model()
-                self.evaluate()
-            self.auto_barrier()
+            # save the model at certain steps (learner.py:171-175).  The reference barriers after EVERY iteration; the
+            # gradient all-reduce already keeps the ranks in step, so only the iterations where the primary worker
+            # does extra work need one (a per-step NCCL barrier would drain the device queue every step).
+            if (idx_iter + 1) % FLAGS.save_step == 0:
+                if self.is_primary_worker('global'):
+                    self.__save_model()
+                    self.evaluate()
+                self.auto_barrier()
         if self.is_primary_worker('global'):
             self.__save_model()
             self.evaluate()
