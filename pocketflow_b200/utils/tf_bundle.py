@@ -464,8 +464,10 @@ class BundleReader:
         if shard_id not in self._files:
             if not 0 <= shard_id < self.header['num_shards']:
                 raise ValueError('shard %d of %d' % (shard_id, self.header['num_shards']))
-            self._files[shard_id] = np.memmap(data_filename(self.prefix, shard_id, self.header['num_shards']),
-                                              dtype=np.uint8, mode='r')
+            path = data_filename(self.prefix, shard_id, self.header['num_shards'])
+            # (a shard that holds only empty tensors is a zero-byte file, which cannot be mapped)
+            self._files[shard_id] = np.memmap(path, dtype=np.uint8, mode='r') if os.path.getsize(path) else \
+                np.zeros(0, np.uint8)
         return self._files[shard_id]
 
     def get_tensor(self, name):

@@ -366,3 +366,30 @@ def test_preprocessing_matches_the_executed_reference_source():
             assert tuple(sdbb[1]['area_range']) == sig['area_range'].default
             assert sdbb[1]['max_attempts'] == sig['max_attempts'].default
             assert tr['calls'][1] == ['resize_images', [224, 224], 'BILINEAR', False]
+
+
+def test_example_and_record_round_trip_property(tmp_path):
+    hyp = pytest.importorskip('hypothesis')
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    key = st.text(alphabet=st.sampled_from(list('abcdefghijklmnopqrstuvwxyz/_')), min_size=1, max_size=20)
+    value = st.one_of(st.lists(st.binary(max_size=300), max_size=3),
+                      st.lists(st.integers(-2 ** 62, 2 ** 62), max_size=6).map(lambda v: np.asarray(v, np.int64)),
+                      st.lists(st.floats(width=32, allow_nan=False), max_size=6).map(lambda v: np.asarray(v, np.float32)))
+    counter = {'n': 0}
+
+    @settings(max_examples=50, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+    @given(st.lists(st.dictionaries(key, value, max_size=5), min_size=0, max_size=6))
+    def check(examples):
+        counter['n'] += 1
+        path = str(tmp_path / ('f%d.tfrecord' % counter['n']))
+        R.write_records(path, [R.encode_example(e) for e in examples])
+        back = [R.parse_example(rec) for rec in R.read_records(path)]
+        assert len(back) == len(examples)
+        for want, got in zip(examples, back):
+            assert sorted(got) == sorted(want)
+            for k, v in want.items():
+                if isinstance(v, list):
+                    assert got[k] == v
+                else:
+                    assert got[k].dtype == v.dtype and got[k].tolist() == v.tolist()
+    check()

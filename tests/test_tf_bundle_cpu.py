@@ -287,3 +287,42 @@ def test_ckpt_tool_converts_both_ways(tmp_path, capsys):
     assert tool.main(['list', str(tmp_path / 'b' / 'model.ckpt')]) == 0
     out = capsys.readouterr().out
     assert 'model/conv2d/kernel' in out and '(3, 3, 2, 4)' in out and '2 tensors, 82 values' in out
+
+
+def test_round_trip_property(tmp_path):
+    """Randomised names / dtypes / shapes / block sizes (hypothesis): whatever the writer accepts comes back identical."""
+    hyp = pytest.importorskip('hypothesis')
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    dtypes = [np.float32, np.float64, np.int32, np.int64, np.uint8, np.int8, np.int16, np.bool_, np.float16, np.uint16]
+    name = st.text(alphabet=st.sampled_from(list('abcdefghijklmnopqrstuvwxyz_/0123456789')), min_size=1, max_size=40)
+    shape = st.lists(st.integers(0, 5), min_size=0, max_size=4)
+    entry = st.tuples(name, st.sampled_from(range(len(dtypes))), shape, st.integers(0, 2 ** 31 - 1))
+    counter = {'n': 0}
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+    @given(st.lists(entry, min_size=1, max_size=25, unique_by=lambda e: e[0]), st.sampled_from([48, 200, 4096, 262144]),
+           st.sampled_from([1, 2, 16]))
+    def check(entries, block_size, restart_interval):
+        counter['n'] += 1
+        tensors = {}
+        for nm, di, shp, seed in entries:
+            rng = np.random.RandomState(seed)
+            tensors[nm] = (rng.randn(*shp) * 50).astype(dtypes[di]) if shp else np.asarray(rng.randn() * 50).astype(dtypes[di])
+        prefix = str(tmp_path / ('p%d' % counter['n']) / 'model.ckpt')
+        w = B.BundleWriter(prefix)
+        for nm in sorted(tensors):
+            w.add(nm, tensors[nm])
+        real = B.build_table
+        B.build_table = lambda items: real(items, block_size=block_size, restart_interval=restart_interval)
+        try:
+            w.finish()
+        finally:
+            B.build_table = real
+        r = B.BundleReader(prefix)
+        assert r.keys() == sorted(tensors)
+        for nm, t in tensors.items():
+            got = r.get_tensor(nm)
+            assert got.dtype == t.dtype and got.shape == t.shape
+            np.testing.assert_array_equal(got, t)
+    check()
+    assert counter['n'] >= 40
