@@ -80,7 +80,7 @@ class PackedBatchIterator(BatchIterator):
     GPU and runs pf_preprocess_images into the step's image placeholder."""
 
     def __init__(self, batch_size, image_shape, nb_classes, generator):
-        super(PackedBatchIterator, self).__init__(batch_size, image_shape, nb_classes, generator, stream=True)
+        super().__init__(batch_size, image_shape, nb_classes, generator, stream=True)
         self.slots = [None] * POOL_SIZE
 
     def next_batch(self):

@@ -89,7 +89,7 @@ class RecordStream(object):
 
 class Cifar10Dataset(AbstractDataset):
     def __init__(self, is_train):
-        super(Cifar10Dataset, self).__init__(is_train)
+        super().__init__(is_train)   # zero-arg form: survives importlib.reload of this module
         self.batch_size = FLAGS.batch_size if is_train else FLAGS.batch_size_eval
         self.image_shape = (IMAGE_HEI, IMAGE_WID, IMAGE_CHN)
         self.nb_classes = FLAGS.nb_classes

@@ -353,7 +353,7 @@ class ExampleStream(object):
 
 class Ilsvrc12Dataset(AbstractDataset):
     def __init__(self, is_train):
-        super(Ilsvrc12Dataset, self).__init__(is_train)
+        super().__init__(is_train)   # zero-arg form: survives importlib.reload of this module
         self.batch_size = FLAGS.batch_size if is_train else FLAGS.batch_size_eval
         self.image_shape = (IMAGE_HEI, IMAGE_WID, IMAGE_CHN)
         self.nb_classes = FLAGS.nb_classes
