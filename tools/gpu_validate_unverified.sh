@@ -8,6 +8,7 @@
 # usage: gpurun --timeout 1500 -- 'bash tools/gpu_validate_unverified.sh'
 mkdir -p gpurun_out
 PF_TEST_UNVALIDATED=1 timeout 300 python -m pytest tests/test_preproc_gpu.py -q 2>&1 | tail -5 | tee gpurun_out/unverified_preproc.log
+timeout 300 python tools/preproc_e2e_check.py 2>&1 | tail -4 | tee gpurun_out/unverified_preproc_e2e.log
 timeout 600 python tools/rl_smoke.py 2>&1 | tail -8 | tee gpurun_out/unverified_rl.log
 timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -5 | tee gpurun_out/gpu_suite.log
 timeout 600 python bench.py --steps 20 --warmup 5 2>gpurun_out/bench.err | tail -1 | tee gpurun_out/bench.json
