@@ -393,3 +393,27 @@ def test_example_and_record_round_trip_property(tmp_path):
                 else:
                     assert got[k].dtype == v.dtype and got[k].tolist() == v.tolist()
     check()
+
+
+def test_make_tfrecords_tool_feeds_the_dataset(tmp_path, capsys):
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('make_tfrecords', os.path.join(root, 'tools', 'make_tfrecords.py'))
+    tool = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tool)
+    src = tmp_path / 'jpegs'
+    for c, cls in enumerate(['n01', 'n02', 'n03']):
+        (src / cls).mkdir(parents=True)
+        for i in range(4):
+            (src / cls / ('img_%d.JPEG' % i)).write_bytes(_jpeg(64 + 8 * i, 80, 10 * c + i))
+    out = str(tmp_path / 'records')
+    assert tool.main([str(src), out, 'train', '2']) == 0
+    assert '12 images of 3 classes in 2 shards' in capsys.readouterr().out
+    assert sorted(os.listdir(out)) == ['train-00000-of-00002', 'train-00001-of-00002']
+    labels = []
+    for f in sorted(os.listdir(out)):
+        for rec in R.read_records(os.path.join(out, f)):
+            ex = R.parse_example(rec)
+            assert ex['image/encoded'][0][:2] == b'\xff\xd8' and ex['image/class/text'][0] in (b'n01', b'n02', b'n03')
+            labels.append(int(ex['image/class/label'][0]))
+    assert sorted(labels) == [1] * 4 + [2] * 4 + [3] * 4
