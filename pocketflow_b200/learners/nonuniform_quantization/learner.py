@@ -13,6 +13,7 @@ from ...utils.lrn_rate_utils import piecewise_constant
 from ..abstract_learner import AbstractLearner, save_checkpoint
 from ..distillation_helper import DistillationHelper
 from .utils import NonUniformQuantization
+from .bit_optimizer import BitOptimizer
 
 DEFINE_string('nuql_opt_mode', 'weights', 'the variables to optimize: [clusters, weights, both]')
 DEFINE_string('nuql_init_style', 'quantile', 'the initialization of quantization points: [quantile, uniform]')
@@ -132,8 +133,9 @@ class NonUniformQuantLearner(AbstractLearner):
                                             FLAGS.nuql_init_style, FLAGS.nuql_bucket_type)
                 matmul_ops = nq.search_matmul_op(FLAGS.nuql_quantize_all_layers)
                 act_ops = nq.search_activation_op()
-                nq.insert_quant_op_for_weights({op.name: FLAGS.nuql_weight_bits for op in matmul_ops})
-                nq.insert_quant_op_for_activations({op.name: FLAGS.nuql_activation_bits for op in act_ops})
+                w_bits, a_bits = BitOptimizer(len(matmul_ops), len(act_ops)).run()
+                nq.insert_quant_op_for_weights({op.name: b for op, b in zip(matmul_ops, w_bits)})
+                nq.insert_quant_op_for_activations({op.name: b for op, b in zip(act_ops, a_bits)})
                 loss, metrics = self.calc_loss(labels, logits, self.trainable_vars)
                 if FLAGS.enbl_dst:
                     loss += self.helper_dst.calc_loss(logits, logits_dst)

@@ -909,7 +909,8 @@ def main():
     gold['flag_defaults'] = {}
     flag_files = ['learners/abstract_learner.py', 'learners/distillation_helper.py',
                   'learners/uniform_quantization/learner.py', 'learners/uniform_quantization/bit_optimizer.py',
-                  'learners/nonuniform_quantization/learner.py', 'learners/weight_sparsification/learner.py',
+                  'learners/nonuniform_quantization/learner.py', 'learners/nonuniform_quantization/bit_optimizer.py',
+                  'learners/weight_sparsification/learner.py',
                   'learners/channel_pruning_gpu/learner.py', 'learners/full_precision/learner.py',
                   'datasets/abstract_dataset.py', 'datasets/cifar10_dataset.py', 'datasets/ilsvrc12_dataset.py',
                   'rl_agents/ddpg/agent.py', 'rl_agents/ddpg/actor_critic.py', 'rl_agents/ddpg/noise.py',

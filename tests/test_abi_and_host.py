@@ -191,3 +191,23 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d['impl'] == 'reference' and d['value'] > 0 and d['config']['workload'] == 'lenet_uq8_b128'
     assert set(('value', 'unit', 'cores', 'kind', 'sample')) <= set(d['cpu_baseline'])
     assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
+
+
+def test_run_scripts_parse_flags_and_map_value_errors_to_exit_status_1(capsys):
+    """nets/*_run.py: every learner's flags are known before parsing; a bad execution mode or learner name is a
+    ValueError -> exit status 1 (nets/resnet_at_cifar10_run.py:62-66), not a traceback to the shell."""
+    import importlib
+    from pocketflow_b200.flags import FLAGS
+    from pocketflow_b200.nets import run_utils
+    for net in ('lenet_at_cifar10', 'resnet_at_cifar10', 'resnet_at_ilsvrc12', 'mobilenet_at_ilsvrc12'):
+        FLAGS.reset()
+        mod = importlib.import_module('pocketflow_b200.nets.' + net + '_run')
+        assert run_utils.run(mod.ModelHelper, ['--learner', 'uniform', '--uql_weight_bits', '8', '--ws_prune_ratio', '0.5',
+                                               '--exec_mode', 'bogus', '--nuql_equivalent_bits=3', '--noenbl_dst']) == 1
+        assert FLAGS.uql_weight_bits == 8 and FLAGS.ws_prune_ratio == 0.5 and FLAGS.enbl_dst is False
+        assert 'unrecognized' in capsys.readouterr().err
+        FLAGS.reset()
+        assert run_utils.run(mod.ModelHelper, ['--learner', 'dis-chn-pruned']) == 1
+        assert 'outside the hot-path scope' in capsys.readouterr().err
+        assert run_utils.run(mod.ModelHelper, ['--no_such_flag', '1']) == 1
+    FLAGS.reset()
