@@ -19,8 +19,6 @@ function that encodes them.
 
 All citations are file:line into /root/reference.
 """
-import math
-
 import numpy as np
 
 F32 = np.float32

@@ -8,14 +8,12 @@ optimizer slots live in FLAT fp32 buffers so that (a) the data-parallel gradient
 collective over one buffer and (b) the optimizer / mask / weight-decay work is a
 handful of launches instead of ~110 per step.
 """
-import math
 import os
 from collections import OrderedDict
 
 import numpy as np
 import torch
 
-from . import graph as G
 from . import ops
 
 F32 = np.float32

@@ -3,7 +3,6 @@ import os
 
 from .. import graph as G
 from ..flags import FLAGS, DEFINE_float, DEFINE_string
-from ..utils.misc_utils import is_primary_worker
 from .abstract_learner import latest_checkpoint, load_checkpoint
 
 DEFINE_float('loss_w_dst', 4.0, 'distillation loss\'s multiplier')

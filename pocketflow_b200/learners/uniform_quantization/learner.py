@@ -4,7 +4,6 @@ import os
 from timeit import default_timer as timer
 
 import numpy as np
-import torch
 
 from ... import graph as G
 from ...engine import Executor

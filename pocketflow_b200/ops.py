@@ -6,7 +6,6 @@ tables, percentile ranks) lives in functions that need no GPU, so it is unit-tes
 """
 import ctypes
 import os
-import math
 
 import numpy as np
 import torch

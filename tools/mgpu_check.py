@@ -3,7 +3,6 @@ replicas are bit-identical and that the update equals the single-GPU update with
 import os
 import sys
 
-import numpy as np
 import torch
 import torch.distributed as dist
 

@@ -1,6 +1,5 @@
 """Sweep descriptor conventions of the tcgen05 probe on a real B200 and print which are correct."""
 import ctypes
-import itertools
 import os
 import sys
 
