@@ -215,3 +215,48 @@ def test_rank_sharded_real_files(tmp_path):
         os.environ.pop('PF_TEST_DATA')
     assert c0 == [0, 1] and c1 == [2, 3]
     assert i0 == [1, 2, 3, 4] and i1 == [11, 12, 13, 14]
+
+
+class _RatioTuner(object):
+    device = 'cpu'
+
+    def __init__(self):
+        self.seen, self.retrain = [], None
+
+    def pr_prune(self, prune_ratios):
+        self.ratios = np.asarray(prune_ratios, float)
+        self.seen.append(self.ratios.round(6).tolist())
+
+    def pr_retrain(self, nb_iters_rg, nb_iters_ft):
+        self.retrain = (nb_iters_rg, nb_iters_ft)
+
+    def pr_evaluate(self):
+        acc = 1.0 - float(np.mean(self.ratios ** 2))
+        return 1.0 - acc, {'acc_top1': acc - 0.1, 'acc_top5': acc}
+
+
+def _ratio_search(rank, world, mgw):
+    """learners/weight_sparsification/pr_optimizer.py:411-470 on two ranks: ratios and rewards come from rank 0 by
+    broadcast (no ./ws.prune.ratios / ./ws.reward files); iteration counts are divided by the world size."""
+    from types import SimpleNamespace
+    from pocketflow_b200.flags import FLAGS
+    import pocketflow_b200.learners.weight_sparsification.learner  # noqa: F401  (declares the ws_* flags)
+    from pocketflow_b200.learners.weight_sparsification.pr_optimizer import PROptimizer
+    FLAGS.reset()
+    FLAGS.enbl_multi_gpu, FLAGS.ws_prune_ratio_prtl, FLAGS.ws_prune_ratio = True, 'optimal', 0.5
+    FLAGS.ws_nb_rlouts, FLAGS.ws_nb_rlouts_min, FLAGS.ws_nb_iters_rg, FLAGS.ws_nb_iters_ft = 5, 2, 20, 401
+    shapes = [(3, 3, 3, 8), (3, 3, 8, 16), (3, 3, 16, 16), (16, 10)]
+    mvars = [SimpleNamespace(name='model/v%d:0' % i, shape=s, numel=int(np.prod(s))) for i, s in enumerate(shapes)]
+    tuner = _RatioTuner()
+    opt = PROptimizer(mvars, 'ilsvrc_12', tuner=tuner, seed=10 + rank)
+    out = opt.run()
+    return [r for _, r in out], tuner.seen, tuner.retrain, len(opt.rewards), hasattr(opt, 'agent')
+
+
+def test_rl_ratio_search_broadcasts_rank0_choices():
+    (r0, seen0, rt0, n0, a0), (r1, seen1, rt1, n1, a1) = run_ranks(_ratio_search)
+    assert r0 == r1 and seen0 == seen1 and len(seen0) == 5
+    assert rt0 == rt1 == (10, 201)                       # ceil(20 / 2), ceil(401 / 2)
+    assert (n0, a0) == (5, True) and (n1, a1) == (0, False)      # the agent and the rewards exist on rank 0 only
+    n = np.array([216, 1152, 2304, 160], float)
+    assert float(np.sum(np.array(r0) * n) / n.sum()) >= 0.5 - 1e-9
