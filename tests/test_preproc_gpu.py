@@ -1,17 +1,15 @@
 """pf_preprocess_images (ILSVRC-12 resize / flip / crop / mean subtraction of a packed mini-batch on the device) against
 its numpy statement, bit for bit.
 
-NOT YET RUN ON A GPU: the kernel was written after this round's GPU budget was spent, so the test is opt-in
-(PF_TEST_UNVALIDATED=1) until it has passed once on a B200; nothing in the training path calls the kernel yet."""
+Validated on a B200 in round 2 (profiles/r2_gpu_validate_unverified.txt): kernel == numpy statement bit for bit, and
+the --enbl_device_preprocess path fills the image placeholder with exactly the host pipeline's batches."""
 import io
 import os
 
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('PF_TEST_UNVALIDATED') != '1',
-                                 reason='kernel not validated on a GPU yet; set PF_TEST_UNVALIDATED=1 to run')]
+pytestmark = pytest.mark.gpu
 
 
 def _jpeg(h, w, seed):
