@@ -316,6 +316,50 @@ int pf_conv2d_tc_wgrad_splits(const pf_conv_desc* d);
 int pf_conv2d_tc_wgrad_reduce_multi(const pf_tc_reduce_seg* segs_dev, const pf_work* work_dev, int n_work, void* stream);
 int pf_conv2d_tc_wgrad_planes(const pf_conv_desc* d, const void* x_hi_dev, const void* x_lo_dev, const void* dy_hi_dev,
                               const void* dy_lo_dev, float* ws_dev, float* dw_dev, void* stream);
+/* ---- TMA-fed kernels with EXACT quantizer-level operands (pf_conv_tma.cu; SURVEY §7 hard part 1b) ----
+ * When channel counts are multiples of 64 the same entry points above feed the tensor cores with TMA
+ * (cp.async.bulk.tensor: im2col-mode tensor maps for the NHWC operand, tiled maps for the weight / gradient matrices;
+ * PF_TC_FEED=lsu forces the cp.async kernels).  The *_ex entry points additionally accept operands of <= 8-bit
+ * fake-quantized tensors as their INTEGER LEVELS, which bf16 represents exactly, so one MMA per k-slice replaces
+ * three (two where the other operand is a split-bf16 gradient):
+ *   activation (reference: learners/uniform_quantization/utils.py:51-79, 175-199):  qa = scale * level,
+ *     plane0 = levels (plane1 unused) when the tensor's minimum is 0, otherwise plane0/plane1 = hi/lo of qa and
+ *     scale = 1 — the producer (pf_bn_apply_quant_levels) decides on the device and records it in `hdr`;
+ *     csum[pixel][nseg] = sums of the stored plane values over channel segments of min(C,128) (for the rank-1
+ *     correction that the weight offset needs: sum_k qa[m,k] over the filter window);
+ *   weights (utils.py:81-113, 224-245):  qw = (alpha_c / k) (level - centre) + (beta_c + centre alpha_c / k),
+ *     plane0 = bf16(level - centre), centre = 2^(bits-1), k = 2^bits - 1; alpha / beta = the quantizer's bucket
+ *     scales (per layer or per output channel).  plane1 != NULL, alpha == NULL: plain split-bf16 weights. */
+typedef struct pf_tc_act_hdr {
+  float scale;             /* value of one level (1.0 when the planes hold hi / lo) */
+  int32_t nplanes;         /* 1: plane0 = integer levels; 2: plane0 / plane1 = hi / lo */
+} pf_tc_act_hdr;
+typedef struct pf_tc_act {
+  const void* plane0;      /* bf16, layout of the fp32 tensor */
+  const void* plane1;      /* bf16 or NULL (then hdr must say 1 plane, or hdr == NULL and the tensor is bf16-exact) */
+  const pf_tc_act_hdr* hdr;/* device, or NULL: nplanes = (plane1 ? 2 : 1), scale = 1 */
+  const float* csum;       /* device [pixels][nseg] or NULL (only needed with weight levels) */
+  int32_t nseg;
+  int32_t reserved;
+} pf_tc_act;
+typedef struct pf_tc_wt {
+  const void* plane0;      /* bf16 K-major [rows][kpad] as written by pf_conv2d_tc_prep_weight* */
+  const void* plane1;      /* lo plane, or NULL with levels */
+  const float* alpha;      /* device bucket scales (levels) or NULL */
+  const float* beta;
+  int32_t per_channel;     /* 1: one bucket per output channel; 0: one per layer */
+  int32_t bits;
+} pf_tc_wt;
+int pf_conv2d_tc_tma_supported(const pf_conv_desc* d, int pass /* 0 fwd, 1 dgrad, 2 wgrad */);
+/* operand feed of the tensor-core kernels: 1 = TMA where eligible (default), 0 = cp.async everywhere, -1 = back to the
+ * PF_TC_FEED environment default.  Process-wide; used by the tests to run both kernels on the same inputs. */
+int pf_conv2d_tc_set_feed(int mode);
+int pf_conv2d_tc_fwd_ex(const pf_conv_desc* d, const pf_tc_act* x, const pf_tc_wt* w, const float* bias_dev, int relu,
+                        const float* residual_dev, float* y_dev, void* stream);
+int pf_conv2d_tc_dgrad_ex(const pf_conv_desc* d, const pf_tc_act* dy, const pf_tc_wt* wd, int accumulate, float* dx_dev,
+                          void* stream);
+int pf_conv2d_tc_wgrad_ex(const pf_conv_desc* d, const pf_tc_act* x, const pf_tc_act* dy, float* ws_dev, float* dw_dev,
+                          void* stream);
 /* hardware probe used by tests/test_tc_gpu.py to pin the descriptor conventions (not a product op) */
 int pf_tc_probe(const void* a_dev, const void* b_dev, float* d_dev, int n, int k, int mode, uint32_t lbo_a,
                 uint32_t sbo_a, uint32_t lbo_b, uint32_t sbo_b, uint32_t kstep_a, uint32_t kstep_b, void* stream);

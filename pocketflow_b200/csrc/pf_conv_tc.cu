@@ -15,23 +15,23 @@
 // representation by the producer warps on the fly) or as PRE-SPLIT bf16 planes written by the kernel that
 // produced the tensor (BN-apply / activation quantizer / BN-backward): then the producers are pure
 // cp.async copies into the 128B-swizzled tiles.  Kernel structure: see conv_tc_persist_kernel below.
-#include <algorithm>
-#include <cstdlib>
-#include <cstring>
+#include "pf_conv_tc.cuh"
 
-#include "pf_common.cuh"
-#include "pf_tc_common.cuh"
+namespace pfconv {
+int tc_geom(const pf_conv_desc* d, TcGeom* g, const char* who) {
+  PF_REQUIRE(d != nullptr, "%s: null descriptor", who);
+  PF_REQUIRE(d->n > 0 && d->h > 0 && d->w > 0 && d->c > 0 && d->k > 0 && d->r > 0 && d->s > 0 && d->p > 0 &&
+                 d->q > 0 && d->stride_h > 0 && d->stride_w > 0 && d->pad_t >= 0 && d->pad_l >= 0,
+             "%s: non-positive dimension in conv descriptor", who);
+  *g = TcGeom{d->n, d->h, d->w, d->c, d->k, d->r, d->s, d->p, d->q, d->stride_h, d->stride_w, d->pad_t, d->pad_l};
+  return PF_OK;
+}
+}  // namespace pfconv
 
 namespace {
-using namespace pftc;
+using namespace pfconv;
 
-constexpr int TM = 128;      // GEMM rows per CTA (= TMEM lanes)
-constexpr int BK = 64;       // bf16 elements per k-stage (= one 128-byte swizzled row)
 constexpr int kMaxStages = 4;
-
-struct TcGeom {
-  int N, H, W, C, K, R, S, P, Q, sh, sw, pt, pl;
-};
 
 __device__ __forceinline__ void split4(const float4 v, uint2& hi, uint2& lo) { pf_split4(v, hi, lo); }
 
@@ -50,19 +50,6 @@ __device__ __forceinline__ void split4(const float4 v, uint2& hi, uint2& lo) { p
 // a tile all belong to one class (h = ph + sh*h', w = pw + sw*w'), and only the filter taps that can reach that
 // class are visited, so no MMA multiplies structural zeros (the gather-with-divisibility-test formulation of
 // MODE 1 wastes 3/4 of the tensor-core work of a 3x3 stride-2 layer).
-struct FastDiv {
-  uint32_t mul, shift;
-};
-inline FastDiv make_fastdiv(uint32_t d) {   // exact for 0 <= n < 2^31 (Granlund-Montgomery round-up method)
-  FastDiv f;
-  uint32_t s = 0;
-  while ((1ull << s) < d) ++s;
-  f.shift = s;
-  f.mul = (uint32_t)((((1ull << 32) * ((1ull << s) - d)) / d) + 1);
-  return f;
-}
-__device__ __forceinline__ uint32_t fdiv(uint32_t n, FastDiv f) { return (__umulhi(n, f.mul) + n) >> f.shift; }
-
 constexpr int kMaxClasses = 4;
 constexpr int kMaxTaps = 9;
 struct TcClass {
@@ -78,135 +65,8 @@ struct TcP {
   TcClass cls[kMaxClasses];
 };
 
-constexpr int kEpiWarps = 4, kProdWarps = 8;
+constexpr int kProdWarps = 8;
 constexpr int kThreadsP = (kEpiWarps + kProdWarps + 1) * 32;   // 416
-constexpr int kStagePitch = 36;                                // floats per staged row (32 + 4: conflict-free)
-
-
-// Epilogue of one 128 x BN accumulator tile by the 4 epilogue warps (warp w owns TMEM lanes [32w, 32w+32)):
-// TMEM -> registers (thread = row, 32 columns) -> per-warp smem transpose -> 128-byte row segments to global.
-// `extra` (residual / accumulate operand, same indexing as `out`) is prefetched one 32-column chunk ahead,
-// and the first chunk is requested BEFORE waiting for the accumulator, so its latency hides behind the main loop.
-// EXTRA: 0 = none; 1 = extra operand prefetched one chunk ahead in registers; 2 = extra operand streamed through a
-// per-warp cp.async ring in shared memory, kRingDepth chunks (4 KB each) in flight per warp.  The output-heavy
-// layers (1x1 64->256 + residual: 128 KB out + 128 KB residual per tile, one k-stage of MMAs) are bound by how many
-// bytes of the extra operand are in flight; registers allow 8 KB per warp, the ring 16 KB.
-constexpr int kRingDepth = 4;
-constexpr int kRingSlotBytes = 32 * 32 * 4;
-template <int EXTRA>
-__device__ __forceinline__ void epilogue_tile_t(uint32_t t_acc, uint64_t* tfull, uint64_t* tempty, uint32_t parity,
-                                                bool zero_tile, long long my_row_off, long long* __restrict__ rowoff,
-                                                float* __restrict__ stg, float* __restrict__ out,
-                                                const float* __restrict__ extra, const float* __restrict__ bias,
-                                                int relu, int n0, int BN, int Ng, int warp, int lane, uint8_t* ring) {
-  rowoff[lane] = my_row_off;
-  __syncwarp();
-  const int csub = (lane & 7) * 4, rsub = lane >> 3;
-  int ro[8];                                     // this lane's 8 rows (4*u + rsub) of the warp's 32, in float4 units
-#pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    const long long o = rowoff[4 * u + rsub];
-    ro[u] = o < 0 ? -1 : (int)(o >> 2);          // row offsets are multiples of 4 elements (channel counts % 16 == 0)
-  }
-  auto load_extra = [&](int c0, float4 (&xv)[8]) {
-    const int cv = c0 + csub;
-    const bool cok = cv < BN && n0 + cv + 3 < Ng;
-#pragma unroll
-    for (int u = 0; u < 8; ++u)
-      xv[u] = (cok && ro[u] >= 0) ? *reinterpret_cast<const float4*>(extra + ((size_t)ro[u] << 2) + n0 + cv)
-                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-  };
-  // ring: every lane copies exactly the 16-byte pieces it will read back itself (no cross-lane hand-off); one
-  // commit group per chunk, empty groups past the end keep the wait_group count uniform
-  const uint32_t ring_u32 = (EXTRA == 2) ? smem_u32(ring) : 0u;
-  auto ring_issue = [&](int c0) {
-    if (c0 < BN) {
-      const int cv = c0 + csub;
-      const bool cok = cv < BN && n0 + cv + 3 < Ng;
-      const uint32_t slot = ring_u32 + (uint32_t)((c0 >> 5) & (kRingDepth - 1)) * kRingSlotBytes;
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const bool ok = cok && ro[u] >= 0;
-        const float* src = ok ? extra + ((size_t)ro[u] << 2) + n0 + cv : extra;
-        const uint32_t dst = slot + (uint32_t)(((4 * u + rsub) * 32 + csub) * 4);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16u : 0u) : "memory");
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  float4 xa[8], xb[8];                           // dead (eliminated) unless EXTRA == 1
-  if (EXTRA == 1) load_extra(0, xa);
-  if (EXTRA == 2) {
-#pragma unroll
-    for (int c = 0; c < kRingDepth; ++c) ring_issue(32 * c);
-  }
-  mbar_wait(tfull, parity);
-  tc_fence_after();
-  const uint32_t t_addr = t_acc + (((uint32_t)(warp * 32)) << 16);
-  for (int c0 = 0; c0 < BN; c0 += 32) {
-    uint32_t r[32];
-    if (!zero_tile) {
-      tmem_ld_32x32(t_addr + (uint32_t)c0, r);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) r[j] = 0u;
-    }
-    if (c0 + 32 >= BN) {                         // last read of this accumulator: hand it back to the MMA warp
-      tc_fence_before();
-      mbar_arrive(tempty);
-    }
-#pragma unroll
-    for (int j = 0; j < 32; j += 4)
-      *reinterpret_cast<uint4*>(stg + lane * kStagePitch + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-    __syncwarp();
-    if (EXTRA == 1 && c0 + 32 < BN) load_extra(c0 + 32, xb);
-    if (EXTRA == 2) asm volatile("cp.async.wait_group %0;" ::"n"(kRingDepth - 1) : "memory");   // chunk c0 has landed
-    const float* slot = reinterpret_cast<const float*>(ring + (size_t)((c0 >> 5) & (kRingDepth - 1)) * kRingSlotBytes);
-    // rows 4*u + (lane >> 3), 16-byte chunk (lane & 7): 8 lanes write one row's 128 contiguous bytes
-    const int cv = c0 + csub;
-    const bool cok = cv < BN && n0 + cv + 3 < Ng;
-    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (bias && cok) bb = __ldg(reinterpret_cast<const float4*>(bias + n0 + cv));
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      float4 v[4], xr[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        v[u] = *reinterpret_cast<const float4*>(stg + (4 * (4 * half + u) + rsub) * kStagePitch + csub);
-        if (EXTRA == 2) xr[u] = *reinterpret_cast<const float4*>(slot + (4 * (4 * half + u) + rsub) * 32 + csub);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int uu = 4 * half + u;
-        if (!cok || ro[uu] < 0) continue;
-        float4 w = v[u];
-        if (bias) { w.x = __fadd_rn(w.x, bb.x); w.y = __fadd_rn(w.y, bb.y); w.z = __fadd_rn(w.z, bb.z); w.w = __fadd_rn(w.w, bb.w); }
-        if (relu) { w.x = fmaxf(w.x, 0.f); w.y = fmaxf(w.y, 0.f); w.z = fmaxf(w.z, 0.f); w.w = fmaxf(w.w, 0.f); }
-        if (EXTRA) {   // fused residual add (resnet_model.py:199,314) or dx += (gradient accumulation)
-          const float4 x = (EXTRA == 2) ? xr[u] : xa[uu];
-          w.x = __fadd_rn(w.x, x.x); w.y = __fadd_rn(w.y, x.y); w.z = __fadd_rn(w.z, x.z); w.w = __fadd_rn(w.w, x.w);
-        }
-        *reinterpret_cast<float4*>(out + ((size_t)ro[uu] << 2) + n0 + cv) = w;
-      }
-    }
-    __syncwarp();                                // the staging buffer is overwritten by the next chunk
-    if (EXTRA == 1) {
-#pragma unroll
-      for (int u = 0; u < 8; ++u) xa[u] = xb[u];
-    }
-    if (EXTRA == 2) ring_issue(c0 + 32 * kRingDepth);   // refill the slot just consumed
-  }
-  if (EXTRA == 2) asm volatile("cp.async.wait_group 0;" ::: "memory");
-}
-__device__ __forceinline__ void epilogue_tile(uint32_t t_acc, uint64_t* tfull, uint64_t* tempty, uint32_t parity,
-                                              bool zero_tile, long long my_row_off, long long* rowoff, float* stg,
-                                              float* __restrict__ out, const float* __restrict__ extra,
-                                              const float* __restrict__ bias, int relu, int n0, int BN, int Ng,
-                                              int warp, int lane, uint8_t* ring = nullptr) {
-  if (extra && ring) epilogue_tile_t<2>(t_acc, tfull, tempty, parity, zero_tile, my_row_off, rowoff, stg, out, extra, bias, relu, n0, BN, Ng, warp, lane, ring);
-  else if (extra) epilogue_tile_t<1>(t_acc, tfull, tempty, parity, zero_tile, my_row_off, rowoff, stg, out, extra, bias, relu, n0, BN, Ng, warp, lane, nullptr);
-  else epilogue_tile_t<0>(t_acc, tfull, tempty, parity, zero_tile, my_row_off, rowoff, stg, out, nullptr, bias, relu, n0, BN, Ng, warp, lane, nullptr);
-}
 
 template <int MODE>
 __device__ __forceinline__ int tile_class(const TcP& p, int mt) {
@@ -787,24 +647,6 @@ tc_prep_weights_multi_kernel(const pf_tc_prep_seg* __restrict__ segs, const pf_w
   }
 }
 
-int tc_geom(const pf_conv_desc* d, TcGeom* g, const char* who) {
-  PF_REQUIRE(d != nullptr, "%s: null descriptor", who);
-  PF_REQUIRE(d->n > 0 && d->h > 0 && d->w > 0 && d->c > 0 && d->k > 0 && d->r > 0 && d->s > 0 && d->p > 0 &&
-                 d->q > 0 && d->stride_h > 0 && d->stride_w > 0 && d->pad_t >= 0 && d->pad_l >= 0,
-             "%s: non-positive dimension in conv descriptor", who);
-  *g = TcGeom{d->n, d->h, d->w, d->c, d->k, d->r, d->s, d->p, d->q, d->stride_h, d->stride_w, d->pad_t, d->pad_l};
-  return PF_OK;
-}
-
-inline int pad64(int64_t k) { return (int)((k + 63) / 64 * 64); }
-
-inline int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return (v && *v) ? atoi(v) : dflt;
-}
-
-constexpr int kSmemLimit = 232448;   // 227 KB opt-in maximum of dynamic shared memory per CTA on sm_100
-
 template <int MODE>
 int launch_persist(const TcGeom& g, TcP& p, const float* src, const void* a_hi, const void* a_lo, const void* b_hi,
                    const void* b_lo, float* out, const float* bias, const float* residual, cudaStream_t st,
@@ -1052,6 +894,11 @@ static int tc_fwd_impl(const pf_conv_desc* d, const float* x_dev, const void* x_
   PF_REQUIRE((((uintptr_t)x_dev | (uintptr_t)x_hi | (uintptr_t)x_lo | (uintptr_t)y_dev | (uintptr_t)w_hi_dev |
                (uintptr_t)w_lo_dev | (uintptr_t)residual_dev | (uintptr_t)bias_dev) & 15) == 0,
              "%s: 16-byte alignment required", who);
+  if (x_hi && conv_tma_eligible(0, g)) {
+    const pf_tc_act a{x_hi, x_lo, nullptr, nullptr, 0, 0};
+    const pf_tc_wt w{w_hi_dev, w_lo_dev, nullptr, nullptr, 0, 0};
+    return conv_tma_launch(0, g, a, w, y_dev, 0, bias_dev, relu, residual_dev, (cudaStream_t)stream, who);
+  }
   return launch_tc<0>(g, x_dev, x_hi, x_lo, w_hi_dev, w_lo_dev, y_dev, 0, bias_dev, relu, residual_dev,
                       (cudaStream_t)stream, who);
 }
@@ -1066,6 +913,11 @@ static int tc_dgrad_impl(const pf_conv_desc* d, const float* dy_dev, const void*
   PF_REQUIRE((dy_dev || (dy_hi && dy_lo)) && wd_hi_dev && wd_lo_dev && dx_dev, "%s: null pointer", who);
   PF_REQUIRE((((uintptr_t)dy_dev | (uintptr_t)dy_hi | (uintptr_t)dy_lo | (uintptr_t)dx_dev | (uintptr_t)wd_hi_dev |
                (uintptr_t)wd_lo_dev) & 15) == 0, "%s: 16-byte alignment required", who);
+  if (dy_hi && conv_tma_eligible(1, g)) {
+    const pf_tc_act a{dy_hi, dy_lo, nullptr, nullptr, 0, 0};
+    const pf_tc_wt w{wd_hi_dev, wd_lo_dev, nullptr, nullptr, 0, 0};
+    return conv_tma_launch(1, g, a, w, dx_dev, accumulate, nullptr, 0, nullptr, (cudaStream_t)stream, who);
+  }
   return launch_tc<1>(g, dy_dev, dy_hi, dy_lo, wd_hi_dev, wd_lo_dev, dx_dev, accumulate, nullptr, 0, nullptr,
                       (cudaStream_t)stream, who);
 }
@@ -1150,33 +1002,98 @@ int pf_split_bf16(const float* src_dev, void* hi_dev, void* lo_dev, int64_t n, v
   return PF_OK;
 }
 
-int pf_conv2d_tc_wgrad_planes(const pf_conv_desc* d, const void* x_hi_dev, const void* x_lo_dev, const void* dy_hi_dev,
-                              const void* dy_lo_dev, float* ws_dev, float* dw_dev, void* stream) {
+static int tc_wgrad_impl(const pf_conv_desc* d, const pf_tc_act& x, const pf_tc_act& dy, float* ws_dev, float* dw_dev,
+                         void* stream, const char* who) {
   TcGeom g;
-  int rc = tc_geom(d, &g, "pf_conv2d_tc_wgrad_planes");
+  int rc = tc_geom(d, &g, who);
   if (rc) return rc;
-  PF_REQUIRE(pf_conv2d_tc_wgrad_supported(d), "pf_conv2d_tc_wgrad_planes: needs Cin %% 16 == 0 and Cout %% 64 == 0");
-  PF_REQUIRE(x_hi_dev && x_lo_dev && dy_hi_dev && dy_lo_dev && ws_dev, "pf_conv2d_tc_wgrad_planes: null pointer");
-  PF_REQUIRE((((uintptr_t)x_hi_dev | (uintptr_t)x_lo_dev | (uintptr_t)dy_hi_dev | (uintptr_t)dy_lo_dev | (uintptr_t)ws_dev |
-               (uintptr_t)dw_dev) & 15) == 0, "pf_conv2d_tc_wgrad_planes: 16-byte alignment required");
-  PF_REQUIRE((int64_t)g.N * g.P * g.Q < (1ll << 31), "pf_conv2d_tc_wgrad_planes: too many pixels");
+  PF_REQUIRE(pf_conv2d_tc_wgrad_supported(d), "%s: needs Cin %% 16 == 0 and Cout %% 64 == 0", who);
+  PF_REQUIRE(x.plane0 && dy.plane0 && dy.plane1 && ws_dev, "%s: null pointer", who);
+  PF_REQUIRE((((uintptr_t)x.plane0 | (uintptr_t)x.plane1 | (uintptr_t)dy.plane0 | (uintptr_t)dy.plane1 | (uintptr_t)ws_dev |
+               (uintptr_t)dw_dev) & 15) == 0, "%s: 16-byte alignment required", who);
+  PF_REQUIRE((int64_t)g.N * g.P * g.Q < (1ll << 31), "%s: too many pixels", who);
   WgP p;
   wgrad_plan(g, &p);
-  const int fixed = 1024 + kEpiWarps * 32 * kStagePitch * 4 + kEpiWarps * 32 * 8 + 256;
-  const size_t smem = (size_t)p.n_stages * (2 * BK * TM * 2 + 2 * BK * p.BN * 2) + fixed;
-  PF_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = std::min(p.total_units, PF_NUM_SMS);
-  conv_tc_wgrad_persist_kernel<<<grid, kThreadsP, smem, st>>>(
-      (const __nv_bfloat16*)x_hi_dev, (const __nv_bfloat16*)x_lo_dev, (const __nv_bfloat16*)dy_hi_dev,
-      (const __nv_bfloat16*)dy_lo_dev, (p.splits == 1 && dw_dev) ? dw_dev : ws_dev, p);
-  PF_CHECK_LAUNCH("pf_conv2d_tc_wgrad_planes");
+  float* partial = (p.splits == 1 && dw_dev) ? dw_dev : ws_dev;
+  if (conv_tma_eligible(2, g)) {
+    rc = conv_tma_wgrad_launch(g, x, dy, p.BN, p.pps, p.splits, partial, st, who);
+    if (rc) return rc;
+  } else {
+    PF_REQUIRE(x.hdr == nullptr && x.plane1 != nullptr, "%s: quantizer-level operands need the TMA kernels (Cin %% 64 == 0)", who);
+    const int fixed = 1024 + kEpiWarps * 32 * kStagePitch * 4 + kEpiWarps * 32 * 8 + 256;
+    const size_t smem = (size_t)p.n_stages * (2 * BK * TM * 2 + 2 * BK * p.BN * 2) + fixed;
+    PF_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = std::min(p.total_units, PF_NUM_SMS);
+    conv_tc_wgrad_persist_kernel<<<grid, kThreadsP, smem, st>>>(
+        (const __nv_bfloat16*)x.plane0, (const __nv_bfloat16*)x.plane1, (const __nv_bfloat16*)dy.plane0,
+        (const __nv_bfloat16*)dy.plane1, partial, p);
+    PF_CHECK_LAUNCH(who);
+  }
   if (p.splits > 1 && dw_dev) {
     const int64_t n = (int64_t)p.Mtot * g.K;
     tc_splitk_reduce_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(ws_dev, dw_dev, n, p.splits);
-    PF_CHECK_LAUNCH("pf_conv2d_tc_wgrad_planes/reduce");
+    PF_CHECK_LAUNCH(who);
   }
   return PF_OK;
+}
+
+int pf_conv2d_tc_wgrad_planes(const pf_conv_desc* d, const void* x_hi_dev, const void* x_lo_dev, const void* dy_hi_dev,
+                              const void* dy_lo_dev, float* ws_dev, float* dw_dev, void* stream) {
+  PF_REQUIRE(x_hi_dev && x_lo_dev, "pf_conv2d_tc_wgrad_planes: null pointer");
+  const pf_tc_act x{x_hi_dev, x_lo_dev, nullptr, nullptr, 0, 0}, dy{dy_hi_dev, dy_lo_dev, nullptr, nullptr, 0, 0};
+  return tc_wgrad_impl(d, x, dy, ws_dev, dw_dev, stream, "pf_conv2d_tc_wgrad_planes");
+}
+
+int pf_conv2d_tc_wgrad_ex(const pf_conv_desc* d, const pf_tc_act* x, const pf_tc_act* dy, float* ws_dev, float* dw_dev,
+                          void* stream) {
+  PF_REQUIRE(x && dy, "pf_conv2d_tc_wgrad_ex: null operand");
+  return tc_wgrad_impl(d, *x, *dy, ws_dev, dw_dev, stream, "pf_conv2d_tc_wgrad_ex");
+}
+
+int pf_conv2d_tc_set_feed(int mode) {
+  conv_tma_set_feed(mode);
+  return PF_OK;
+}
+
+int pf_conv2d_tc_tma_supported(const pf_conv_desc* d, int pass) {
+  TcGeom g;
+  if (!d || pass < 0 || pass > 2 || tc_geom(d, &g, "pf_conv2d_tc_tma_supported")) return 0;
+  if (pass == 2) return pf_conv2d_tc_wgrad_supported(d) && conv_tma_eligible(2, g);
+  return pf_conv2d_tc_supported(d) && conv_tma_eligible(pass, g);
+}
+
+int pf_conv2d_tc_fwd_ex(const pf_conv_desc* d, const pf_tc_act* x, const pf_tc_wt* w, const float* bias_dev, int relu,
+                        const float* residual_dev, float* y_dev, void* stream) {
+  const char* who = "pf_conv2d_tc_fwd_ex";
+  PF_REQUIRE(x && w && x->plane0 && w->plane0 && y_dev, "%s: null pointer", who);
+  const bool plain = x->hdr == nullptr && x->plane1 != nullptr && w->alpha == nullptr && w->plane1 != nullptr;
+  if (plain)
+    return tc_fwd_impl(d, nullptr, x->plane0, x->plane1, w->plane0, w->plane1, bias_dev, relu, residual_dev, y_dev, stream, who);
+  TcGeom g;
+  int rc = tc_geom(d, &g, who);
+  if (rc) return rc;
+  PF_REQUIRE(pf_conv2d_tc_supported(d) && conv_tma_eligible(0, g),
+             "%s: quantizer-level operands need the TMA kernels (Cin %% 64 == 0)", who);
+  PF_REQUIRE((((uintptr_t)x->plane0 | (uintptr_t)x->plane1 | (uintptr_t)w->plane0 | (uintptr_t)w->plane1 | (uintptr_t)y_dev |
+               (uintptr_t)residual_dev | (uintptr_t)bias_dev | (uintptr_t)w->alpha | (uintptr_t)w->beta) & 15) == 0,
+             "%s: 16-byte alignment required", who);
+  return conv_tma_launch(0, g, *x, *w, y_dev, 0, bias_dev, relu, residual_dev, (cudaStream_t)stream, who);
+}
+
+int pf_conv2d_tc_dgrad_ex(const pf_conv_desc* d, const pf_tc_act* dy, const pf_tc_wt* wd, int accumulate, float* dx_dev,
+                          void* stream) {
+  const char* who = "pf_conv2d_tc_dgrad_ex";
+  PF_REQUIRE(dy && wd && dy->plane0 && wd->plane0 && dx_dev, "%s: null pointer", who);
+  const bool plain = dy->hdr == nullptr && dy->plane1 != nullptr && wd->alpha == nullptr && wd->plane1 != nullptr;
+  if (plain)
+    return tc_dgrad_impl(d, nullptr, dy->plane0, dy->plane1, wd->plane0, wd->plane1, accumulate, dx_dev, stream, who);
+  TcGeom g;
+  int rc = tc_geom(d, &g, who);
+  if (rc) return rc;
+  PF_REQUIRE(pf_conv2d_tc_supported(d) && conv_tma_eligible(1, g),
+             "%s: quantizer-level operands need the TMA kernels (unit stride, Cout %% 64 == 0)", who);
+  return conv_tma_launch(1, g, *dy, *wd, dx_dev, accumulate, nullptr, 0, nullptr, (cudaStream_t)stream, who);
 }
 
 int pf_conv2d_tc_wgrad(const pf_conv_desc* d, const float* x_dev, const float* dy_dev, float* ws_dev,

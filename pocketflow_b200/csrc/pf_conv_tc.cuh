@@ -119,7 +119,7 @@ __device__ __forceinline__ void epilogue_tile_t(uint32_t t_acc, uint64_t* tfull,
 #pragma unroll
     for (int c = 0; c < kRingDepth; ++c) ring_issue(32 * c);
   }
-  mbar_wait(tfull, parity);
+  mbar_wait_bounded(tfull, parity);
   tc_fence_after();
   const uint32_t t_addr = t_acc + (((uint32_t)(q * 32)) << 16);
   for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -220,5 +220,13 @@ __device__ __forceinline__ void epilogue_tile(uint32_t t_acc, uint64_t* tfull, u
   epilogue_tile_a<0>(t_acc, tfull, tempty, parity, zero_tile, my_row_off, rowoff, stg, out, extra, bias, relu, n0, BN, Ng,
                      q, lane, ring, none, 0.f, nullptr);
 }
+
+// ---- TMA-fed kernels (pf_conv_tma.cu)
+void conv_tma_set_feed(int mode);
+bool conv_tma_eligible(int pass, const TcGeom& g);      // pass: 0 fwd, 1 dgrad, 2 wgrad
+int conv_tma_launch(int pass, const TcGeom& g, const pf_tc_act& a, const pf_tc_wt& w, float* out, int accumulate,
+                    const float* bias, int relu, const float* residual, cudaStream_t st, const char* who);
+int conv_tma_wgrad_launch(const TcGeom& g, const pf_tc_act& x, const pf_tc_act& dy, int BN, int pps, int splits,
+                          float* partial, cudaStream_t st, const char* who);
 
 }  // namespace pfconv

@@ -60,6 +60,11 @@ SIGNATURES = {
     'pf_conv2d_tc_fwd_planes': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]),
     'pf_conv2d_tc_dgrad_planes': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
     'pf_conv2d_tc_wgrad_planes': (c_i32, [c_vp] * 8),
+    'pf_conv2d_tc_tma_supported': (c_i32, [c_vp, c_i32]),
+    'pf_conv2d_tc_set_feed': (c_i32, [c_i32]),
+    'pf_conv2d_tc_fwd_ex': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]),
+    'pf_conv2d_tc_dgrad_ex': (c_i32, [c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
+    'pf_conv2d_tc_wgrad_ex': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'pf_tc_probe': (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32] + [ctypes.c_uint32] * 6 + [c_vp]),
     'pf_dwconv_fwd': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp]),
     'pf_dwconv_dgrad': (c_i32, [c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
@@ -93,6 +98,19 @@ class ConvDesc(ctypes.Structure):
     """pf_conv_desc (host struct)."""
     _fields_ = [(n, c_i32) for n in ('n', 'h', 'w', 'c', 'k', 'r', 's', 'p', 'q',
                                      'stride_h', 'stride_w', 'pad_t', 'pad_l')]
+
+
+
+class TcAct(ctypes.Structure):
+    """pf_tc_act: activation / gradient operand of the tensor-core kernels (host struct of device pointers)."""
+    _fields_ = [('plane0', c_vp), ('plane1', c_vp), ('hdr', c_vp), ('csum', c_vp), ('nseg', c_i32), ('reserved', c_i32)]
+
+
+class TcWt(ctypes.Structure):
+    """pf_tc_wt: weight operand (split-bf16 planes, or integer levels + the quantizer's bucket scales)."""
+    _fields_ = [('plane0', c_vp), ('plane1', c_vp), ('alpha', c_vp), ('beta', c_vp), ('per_channel', c_i32),
+                ('bits', c_i32)]
+
 
 _lib = None
 

@@ -690,6 +690,46 @@ def conv2d_tc_wgrad_planes(d, xp, dyp, ws, dw):
                                                      _p(dw), _stream()), 'pf_conv2d_tc_wgrad_planes')
 
 
+# ---- TMA-fed kernels, operands as quantizer levels (include/pf_b200.h: pf_tc_act / pf_tc_wt)
+ACT_HDR = np.dtype([('scale', np.float32), ('nplanes', np.int32)])
+
+
+def conv2d_tc_set_feed(mode):
+    """1: TMA kernels where eligible (default), 0: cp.async kernels everywhere, -1: PF_TC_FEED environment default."""
+    _lib.check(_lib.load().pf_conv2d_tc_set_feed(int(mode)), 'pf_conv2d_tc_set_feed')
+
+
+def conv2d_tc_tma_supported(d, which):
+    """which: 0 fwd, 1 dgrad, 2 wgrad"""
+    return bool(_lib.load().pf_conv2d_tc_tma_supported(ctypes.byref(d), int(which)))
+
+
+def tc_act(planes, hdr=None, csum=None, nseg=0, single=False):
+    """pf_tc_act of a Planes object (+ the producer's device header / channel sums); single: only plane0 is valid"""
+    return _lib.TcAct(planes.hi.data_ptr(), 0 if single else planes.lo.data_ptr(), hdr.data_ptr() if hdr is not None else 0,
+                      csum.data_ptr() if csum is not None else 0, int(nseg), 0)
+
+
+def tc_wt(p0, p1=None, alpha=None, beta=None, per_channel=False, bits=0):
+    return _lib.TcWt(p0.data_ptr(), p1.data_ptr() if p1 is not None else 0, alpha.data_ptr() if alpha is not None else 0,
+                     beta.data_ptr() if beta is not None else 0, int(bool(per_channel)), int(bits))
+
+
+def conv2d_tc_fwd_ex(d, act, wt, bias, relu, y, residual=None):
+    _lib.check(_lib.load().pf_conv2d_tc_fwd_ex(ctypes.byref(d), ctypes.byref(act), ctypes.byref(wt), _p(bias), int(bool(relu)),
+                                               _p(residual), _p(y), _stream()), 'pf_conv2d_tc_fwd_ex')
+
+
+def conv2d_tc_dgrad_ex(d, act, wt, accumulate, dx):
+    _lib.check(_lib.load().pf_conv2d_tc_dgrad_ex(ctypes.byref(d), ctypes.byref(act), ctypes.byref(wt), int(bool(accumulate)),
+                                                 _p(dx), _stream()), 'pf_conv2d_tc_dgrad_ex')
+
+
+def conv2d_tc_wgrad_ex(d, x_act, dy_act, ws, dw):
+    _lib.check(_lib.load().pf_conv2d_tc_wgrad_ex(ctypes.byref(d), ctypes.byref(x_act), ctypes.byref(dy_act), _p(ws), _p(dw),
+                                                 _stream()), 'pf_conv2d_tc_wgrad_ex')
+
+
 def s2d_planes(x, pad_t, pad_l, hp, wp, cpad, planes):
     """space-to-depth of a stride-2 first layer's input [n,h,w,c] into operand planes [n,hp,wp,cpad]"""
     n, h, w, c = x.shape
