@@ -281,6 +281,13 @@ typedef struct pf_tc_prep_seg {
   void* dgrad_lo;
   int32_t rs, c, k;        /* R*S, Cin, Cout */
   int32_t kpad_f, kpad_d;  /* row pitches of the fwd / dgrad copies (multiples of 64) */
+  int32_t q_bits;          /* 0: w holds the values to split.  1..8: w holds the UNQUANTIZED kernel and the copies are
+                            * derived with the weight quantizer's own op chain (a1): fwd_hi <- bf16(level - 2^(bits-1))
+                            * (integer levels, fwd_lo untouched), dgrad_hi / dgrad_lo <- split of the quantized value */
+  const float* q_alpha;    /* bucket scales of pf_uq_weight_scales at this tensor's first bucket: alpha, */
+  const float* q_beta;     /*   beta, */
+  const float* q_ralpha;   /*   RN(1 / alpha) */
+  int32_t q_ncols;         /* 1 (per layer) or k (per output channel) */
   int32_t reserved;
 } pf_tc_prep_seg;
 int pf_conv2d_tc_prep_weights_multi(const pf_tc_prep_seg* segs_dev, const pf_work* work_dev, int n_work, void* stream);
@@ -351,6 +358,13 @@ typedef struct pf_tc_wt {
   int32_t bits;
 } pf_tc_wt;
 int pf_conv2d_tc_tma_supported(const pf_conv_desc* d, int pass /* 0 fwd, 1 dgrad, 2 wgrad */);
+/* producer of a pf_tc_act: Q(act(bn(x))) with a known range (as pf_bn_apply_quant), written as levels / planes +
+ * header + channel sums (csum_dev: m * ceil(c / 128) floats).  C must be a power of two >= 16.  y_dev (fp32 copy) may
+ * be NULL.  Reference ops: utils/external/resnet_model.py:55-62 + learners/uniform_quantization/utils.py:51-79. */
+int pf_bn_apply_quant_levels(const float* x_dev, int64_t m, int c, const float* mean_dev, const float* rstd_dev,
+                             const float* gamma_dev, const float* beta_dev, int act, const uint32_t* range_enc_dev,
+                             int bits, float* y_dev, void* plane0_dev, void* plane1_dev, pf_tc_act_hdr* hdr_dev,
+                             float* csum_dev, void* stream);
 /* operand feed of the tensor-core kernels: 1 = TMA where eligible (default), 0 = cp.async everywhere, -1 = back to the
  * PF_TC_FEED environment default.  Process-wide; used by the tests to run both kernels on the same inputs. */
 int pf_conv2d_tc_set_feed(int mode);

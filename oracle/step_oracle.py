@@ -130,8 +130,11 @@ class StepOracle:
         if threads:
             torch.set_num_threads(threads)
 
-    def forward(self, params, images, training=True, stats_out=None):
-        """params: name -> torch tensor.  Returns dict tensor-name -> value (NHWC)."""
+    def forward(self, params, images, training=True, stats_out=None, force=None, local_out=None):
+        """params: name -> torch tensor.  Returns dict tensor-name -> value (NHWC).
+        force / local_out (layer-local parity tests): after an op has been evaluated its result is recorded in
+        local_out[name] and then REPLACED by force[name] when given — every op is thus applied to inputs produced by
+        the implementation under test, so a difference cannot be amplified by the quantizers downstream."""
         val = {self.images_t.name: images}
         for op in self.ops:
             ty = op.type
@@ -200,6 +203,10 @@ class StepOracle:
                 y = torch.softmax(x, dim=-1)
             else:
                 raise NotImplementedError(ty)
+            if local_out is not None:
+                local_out[op.output.name] = y
+            if force is not None and op.output.name in force:
+                y = force[op.output.name]
             val[op.output.name] = y
         return val
 

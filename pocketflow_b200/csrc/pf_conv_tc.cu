@@ -618,7 +618,14 @@ tc_prep_weights_multi_kernel(const pf_tc_prep_seg* __restrict__ segs, const pf_w
       const int kr = (threadIdx.x >> 6) + 4 * j, kidx = k0 + kr;
       __nv_bfloat16 h = __float2bfloat16_rn(0.f), l = h;
       if (kidx < KR && co < K) {
-        const float v = __ldg(sg.w + (size_t)kidx * K + co);
+        float v = __ldg(sg.w + (size_t)kidx * K + co);
+        float level = 0.f;
+        if (sg.q_bits > 0) {
+          // the weight quantizer's op chain (pf_uq.cu: uq_weight_apply_kernel) on the unquantized kernel
+          const int b = sg.q_ncols == 1 ? 0 : co;
+          const float kq = pf_uq_kf(sg.q_bits);
+          v = pf_fake_quant_lv(v, __ldg(sg.q_alpha + b), __ldg(sg.q_beta + b), kq, __ldg(sg.q_ralpha + b), __frcp_rn(kq), level);
+        }
         h = __float2bfloat16_rn(v);
         l = __float2bfloat16_rn(v - __bfloat162float(h));
         if (d_hi) {
@@ -627,6 +634,7 @@ tc_prep_weights_multi_kernel(const pf_tc_prep_seg* __restrict__ segs, const pf_w
           d_hi[dof] = h;
           d_lo[dof] = l;
         }
+        if (sg.q_bits > 0) h = __float2bfloat16_rn(level - (float)(1 << (sg.q_bits - 1)));   // exact: |.| <= 128
       }
       sh_h[threadIdx.x & 63][kr] = h;
       sh_l[threadIdx.x & 63][kr] = l;
@@ -641,7 +649,7 @@ tc_prep_weights_multi_kernel(const pf_tc_prep_seg* __restrict__ segs, const pf_w
       if (kidx < KR && co < K) {
         const size_t fo = (size_t)co * sg.kpad_f + kidx;
         f_hi[fo] = sh_h[cl][kr];
-        f_lo[fo] = sh_l[cl][kr];
+        if (sg.q_bits == 0) f_lo[fo] = sh_l[cl][kr];
       }
     }
   }

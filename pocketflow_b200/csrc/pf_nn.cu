@@ -291,6 +291,82 @@ bn_apply_kernel(const float* __restrict__ x, int64_t total, int C, const float* 
   }
 }
 
+// BN + activation + fake-quant (known range) writing the tensor-core operand as INTEGER LEVELS where it can:
+// y = act(bn(x)), qa = Q(y).  When the tensor's minimum is exactly 0 (every ReLU / ReLU6 output in practice) and
+// bits <= 8, qa = scale * level with level in [0, 2^bits - 1] exactly representable in bf16: plane0 <- bf16(level),
+// plane1 is not written, hdr <- {scale = alpha / k, 1} and a consuming MMA needs ONE operand plane instead of two.
+// Otherwise plane0 / plane1 <- hi / lo of qa and hdr <- {1, 2}.  Either way csum[pixel][segment] receives the sum of
+// the stored plane values over channel segments of min(C, 128) — the rank-1 term the weight quantizer's offset needs
+// (pf_conv_tma.cu).  One warp owns whole segments (C a power of two >= 16), reduced by a fixed xor butterfly: the sums
+// are deterministic, and exact for levels.  HBM traffic: 4 B read + 2 B (levels) or 4 B (planes) written per element.
+__global__ void __launch_bounds__(NT)
+bn_apply_levels_kernel(const float* __restrict__ x, int64_t total, int C, int cshift, const float* __restrict__ mean,
+                       const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                       int act, float* __restrict__ y, void* __restrict__ p0, void* __restrict__ p1,
+                       const uint32_t* __restrict__ q_range, int q_bits, pf_tc_act_hdr* __restrict__ hdr,
+                       float* __restrict__ csum, int nseg) {
+  const float qmn = pf_dec(__ldg(q_range)), qmx = pf_dec(__ldg(q_range + 1));
+  const float q_alpha = __fadd_rn(__fsub_rn(qmx, qmn), 1e-10f), q_beta = qmn;
+  const float q_k = pf_uq_kf(q_bits), q_ra = __frcp_rn(q_alpha), q_rk = __frcp_rn(q_k);
+  const bool lev = q_bits <= 8 && q_beta == 0.f;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    hdr->scale = lev ? __fdiv_rn(q_alpha, q_k) : 1.f;
+    hdr->nplanes = lev ? 1 : 2;
+  }
+  const int lane = threadIdx.x & 31;
+  const int L = min(C >> 2, 32);                       // lanes per channel segment
+  const int64_t nvec = total >> 2;
+  const int64_t stride = (int64_t)gridDim.x * NT;      // a multiple of C / 4 (host): this thread's channels never change
+  const int64_t first = (int64_t)blockIdx.x * NT + threadIdx.x;
+  const uint32_t c = (uint32_t)((first << 2) & (int64_t)(C - 1));
+  const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + c));
+  const float4 rs = __ldg(reinterpret_cast<const float4*>(rstd + c));
+  const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c));
+  const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
+  auto emit = [&](float4 v, int64_t i, bool valid) {
+    float4 lv;
+    v.x = pf_fake_quant_lv(bn_act(v.x, mu.x, rs.x, ga.x, be.x, act), q_alpha, q_beta, q_k, q_ra, q_rk, lv.x);
+    v.y = pf_fake_quant_lv(bn_act(v.y, mu.y, rs.y, ga.y, be.y, act), q_alpha, q_beta, q_k, q_ra, q_rk, lv.y);
+    v.z = pf_fake_quant_lv(bn_act(v.z, mu.z, rs.z, ga.z, be.z, act), q_alpha, q_beta, q_k, q_ra, q_rk, lv.z);
+    v.w = pf_fake_quant_lv(bn_act(v.w, mu.w, rs.w, ga.w, be.w, act), q_alpha, q_beta, q_k, q_ra, q_rk, lv.w);
+    const float4 s = lev ? lv : v;
+    float part = 0.f;
+    if (valid) {
+      const int64_t e = i << 2;
+      if (y) pf_st_stream(y + e, v);
+      if (lev) {
+        const __nv_bfloat162 a = __floats2bfloat162_rn(s.x, s.y), b = __floats2bfloat162_rn(s.z, s.w);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p0) + e) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+      } else {
+        pf_st_planes4(p0, p1, e, s);
+      }
+      part = (s.x + s.y) + (s.z + s.w);
+    }
+    for (int o = L >> 1; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (valid && (lane & (L - 1)) == 0) {
+      const int64_t e = i << 2;
+      csum[(e >> cshift) * nseg + (int)((e & (int64_t)(C - 1)) >> 7)] = part;
+    }
+  };
+  // warp-uniform trip count (the segment reduction uses full-warp shuffles); two independent loads in flight
+  const int64_t wbase = first - lane;
+  int64_t off = 0;
+  for (; wbase + off + stride < nvec; off += 2 * stride) {
+    const int64_t i0 = first + off, i1 = i0 + stride;
+    const bool v1 = i1 < nvec;
+    const float4 a = pf_ld_stream(x + (i0 << 2));        // wbase + off + stride < nvec  =>  i0 < nvec
+    const float4 b = v1 ? pf_ld_stream(x + (i1 << 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    emit(a, i0, true);
+    emit(b, i1, v1);
+  }
+  if (wbase + off < nvec) {
+    const int64_t i0 = first + off;
+    const bool v0 = i0 < nvec;
+    emit(v0 ? pf_ld_stream(x + (i0 << 2)) : make_float4(0.f, 0.f, 0.f, 0.f), i0, v0);
+  }
+}
+
 // BN backward, phase 1: per channel sum(dz) and sum(dz * xhat), dz = dy masked by the activation.
 __global__ void __launch_bounds__(NT)
 bn_bwd_partial_kernel(const float* __restrict__ dy, const float* __restrict__ x, int M, int C,
@@ -846,6 +922,31 @@ int pf_bn_apply_quant(const float* x_dev, int64_t m, int c, const float* mean_de
   PF_REQUIRE(bits >= 1 && bits <= 32, "pf_bn_apply_quant: bits must be in [1, 32]");
   return bn_apply_impl(x_dev, m, c, mean_dev, rstd_dev, gamma_dev, beta_dev, act, y_dev, y_hi_dev, y_lo_dev, nullptr,
                        range_enc_dev, bits, stream);
+}
+
+int pf_bn_apply_quant_levels(const float* x_dev, int64_t m, int c, const float* mean_dev, const float* rstd_dev,
+                             const float* gamma_dev, const float* beta_dev, int act, const uint32_t* range_enc_dev,
+                             int bits, float* y_dev, void* plane0_dev, void* plane1_dev, pf_tc_act_hdr* hdr_dev,
+                             float* csum_dev, void* stream) {
+  PF_REQUIRE(m > 0 && c >= 16 && (c & (c - 1)) == 0, "pf_bn_apply_quant_levels: C must be a power of two >= 16 (got %d)", c);
+  PF_REQUIRE(act >= 0 && act <= 2, "pf_bn_apply_quant_levels: act must be 0 (none), 1 (relu) or 2 (relu6)");
+  PF_REQUIRE(bits >= 1 && bits <= 32, "pf_bn_apply_quant_levels: bits must be in [1, 32]");
+  PF_REQUIRE(x_dev && mean_dev && rstd_dev && gamma_dev && beta_dev && range_enc_dev && plane0_dev && plane1_dev && hdr_dev &&
+                 csum_dev, "pf_bn_apply_quant_levels: null pointer");
+  PF_REQUIRE((((uintptr_t)plane0_dev | (uintptr_t)plane1_dev | (uintptr_t)hdr_dev) & 7) == 0,
+             "pf_bn_apply_quant_levels: planes / header must be 8-byte aligned");
+  const int64_t total = m * c;
+  int cshift = 0;
+  while ((1 << cshift) < c) ++cshift;
+  const int nseg = (c + 127) / 128;
+  // grid: a multiple of (C/4)/gcd(C/4, NT) blocks so that every thread keeps its 4 channels (C/4 <= NT * 64 here)
+  unsigned grid = chan_grid(total >> 2, c);
+  PF_REQUIRE(((int64_t)grid * NT) % (c >> 2) == 0, "pf_bn_apply_quant_levels: C = %d too large for the channel-stationary grid", c);
+  bn_apply_levels_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(x_dev, total, c, cshift, mean_dev, rstd_dev, gamma_dev, beta_dev,
+                                                               act, y_dev, plane0_dev, plane1_dev, range_enc_dev, bits, hdr_dev,
+                                                               csum_dev, nseg);
+  PF_CHECK_LAUNCH("pf_bn_apply_quant_levels");
+  return PF_OK;
 }
 
 int pf_bn_apply(const float* x_dev, int64_t m, int c, const float* mean_dev, const float* rstd_dev,

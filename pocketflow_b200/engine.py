@@ -365,10 +365,60 @@ class Executor:
                         continue
                     if not (c in self.tc and c not in self.im2col and (not self.train or c in self.tc_wgrad)):
                         self.bn_need_f32[bn_op] = True
+        # ---- integer-level operands (TMA-fed kernels, SURVEY §7 hard part 1b): a <= 8-bit fake-quantized tensor is
+        # exactly scale * level, and the levels are exact in bf16 — one operand plane instead of hi + lo, one MMA per
+        # k-slice instead of three (two against a split gradient).  Activation side: the fused BN + ReLU + fake-quant
+        # pass writes levels + a device header + per-pixel channel sums when EVERY consumer of its planes is a TMA-fed
+        # kernel.  Weight side: the preparation launch derives the levels from the unquantized kernel with the
+        # quantizer's own op chain; needs per-layer / per-output-channel buckets and the input's channel sums.
+        self.act_lv, self.w_lv = {}, {}
+        use_lv = os.environ.get('PF_TC_LEVELS', '1') != '0' and self.train and dev.type == 'cuda'
+        if use_lv and self.aq_ops:
+            cons = {}
+            for op in self.ops:
+                if op in self.tc and op not in self.im2col:
+                    r = self._root(op.inputs[0])
+                    if r is not None and r.op in self.xplanes:
+                        cons.setdefault(r.op, []).append(op)
+            for bn_op, users in cons.items():
+                act = self.fused_act.get(bn_op, 0)
+                relu_op = self._consumers(bn_op.output)[0] if act else None
+                c = bn_op.output.shape[-1]
+                if relu_op not in self.aq_index or not bn_op.attrs['training'] or c < 16 or (c & (c - 1)):
+                    continue
+                if all(ops.conv2d_tc_tma_supported(self.desc[u], 0) and u in self.tc_wgrad
+                       and ops.conv2d_tc_tma_supported(self.desc[u], 2) for u in users):
+                    m = bn_op.output.numel // c
+                    nseg = (c + 127) // 128
+                    self.act_lv[bn_op] = dict(hdr=torch.zeros(2, dtype=torch.int32, device=dev),
+                                              csum=E((m * nseg,)), nseg=nseg)
+            wq = self.weight_quant
+            if self.wq is not None and isinstance(self.wq, ops.UniformWeightQuantizer) and \
+                    (not wq.get('use_buckets', False) or wq.get('bucket_type', 'channel') == 'channel'):
+                nbk = self.wq.n_buckets
+                for i, op in enumerate(self.wq_ops):
+                    if op not in self.tc or op in self.im2col or op.type != 'Conv2D':
+                        continue
+                    r = self._root(op.inputs[0])
+                    if r is None or r.op not in self.act_lv or not 1 <= self.wq.bits[i] <= 8:
+                        continue
+                    b0, ncols = int(self.wq.segs[i]['bucket0']), int(self.wq.segs[i]['ncols'])
+                    sc = self.wq.scales
+                    self.w_lv[op] = dict(index=i, ncols=ncols, alpha=sc[b0:b0 + ncols], beta=sc[nbk + b0:nbk + b0 + ncols],
+                                         ralpha=sc[2 * nbk + b0:2 * nbk + b0 + ncols])
         # one launch refreshes the split-bf16 copies of all (trainable) conv kernels
         self.tc_batch = None
         if self.tc and not self.static_weights:
-            self.tc_batch = ops.TcWeightsBatch([(self.tc[op], self.kernel_of(op)) for op in self.ops if op in self.tc], dev)
+            tc_ops = [op for op in self.ops if op in self.tc]
+            levels = {}
+            for j, op in enumerate(tc_ops):
+                if op in self.w_lv:
+                    lv = self.w_lv[op]
+                    levels[j] = (self.store.view(op.vars['kernel']), lv['alpha'], lv['beta'], lv['ralpha'], lv['ncols'],
+                                 self.wq.bits[lv['index']])
+                    lv['batch_index'] = j
+            self.tc_batch = ops.TcWeightsBatch([(self.tc[op], self.kernel_of(op)) for op in tc_ops], dev, levels)
+        self._lv_on = False            # set per forward(): levels only in training-mode passes
         if self.labels_t is not None and self.labels_t not in self.buf:
             self.buf[self.labels_t] = torch.zeros(self.labels_t.shape, dtype=torch.float32, device=dev)
         self.bn_ws = E((max_bnws,))
@@ -570,6 +620,22 @@ class Executor:
         r = self._root(t)
         return self.xplanes.get(r.op) if r is not None else None
 
+    def _act_lv_of(self, t):
+        """level-operand record of the BN that produced tensor t's planes (None: plain split-bf16 planes)"""
+        r = self._root(t)
+        return self.act_lv.get(r.op) if r is not None else None
+
+    def _tc_act(self, t):
+        lv, xp = self._act_lv_of(t), self.planes_of(t)
+        return ops.tc_act(xp, lv['hdr'], lv['csum'], lv['nseg']) if lv is not None else ops.tc_act(xp)
+
+    def _tc_wt(self, op):
+        tw = self.tc[op]
+        lv = self.w_lv.get(op) if self._lv_on else None
+        if lv is not None and self.wq.bits[lv['index']] <= 8:
+            return ops.tc_wt(tw.f_hi, None, lv['alpha'], lv['beta'], lv['ncols'] > 1, self.wq.bits[lv['index']])
+        return ops.tc_wt(tw.f_hi, tw.f_lo)
+
     def raw(self, t):
         while t in self.alias:
             t = self.alias[t]
@@ -608,9 +674,10 @@ class Executor:
                 self.wq.forward()
         if self.static_weights and not self._static_ready:
             self.prepare_static_weights()
+        self._lv_on = bool(training and (self.act_lv or self.w_lv))
         if self.tc_batch is not None:
             with self.timed('conv_prep'):
-                self.tc_batch.prepare()
+                self.tc_batch.prepare(levels=self._lv_on)
         for op in self.ops:
             ty = op.type
             if ty in ('Placeholder', 'Reshape', 'Identity'):
@@ -649,7 +716,10 @@ class Executor:
                     res = self.T(self.fused_add[op][1]) if op in self.fused_add else None
                     xp = self.planes_of(op.inputs[0])
                     with self.timed('conv_fwd'):
-                        if xp is not None:
+                        if xp is not None and self._lv_on and self._act_lv_of(op.inputs[0]) is not None:
+                            ops.conv2d_tc_fwd_ex(self.desc[op], self._tc_act(op.inputs[0]), self._tc_wt(op), bias,
+                                                 op in self.fused_act, self.buf[op.output], res)
+                        elif xp is not None:
                             ops.conv2d_tc_fwd_planes(self.desc[op], xp, self.tc[op], bias, op in self.fused_act,
                                                      self.buf[op.output], res)
                         else:
@@ -683,8 +753,14 @@ class Executor:
                         ops.bn_train_stats_range(x, m, c, op.attrs['epsilon'], op.attrs['momentum'], b['mean'], b['var'],
                                                  b['rstd'], mm, mv, gamma, beta, act, slot, self.bn_ws)
                     with self.timed('bn_apply'):
-                        ops.bn_apply_quant(x, m, c, b['mean'], b['rstd'], gamma, beta, act, slot,
-                                           self.act_quant['bits'][self.aq_index[relu_op]], y if need_f32 else None, pl)
+                        bits = self.act_quant['bits'][self.aq_index[relu_op]]
+                        if self._lv_on and op in self.act_lv:
+                            lv = self.act_lv[op]
+                            ops.bn_apply_quant_levels(x, m, c, b['mean'], b['rstd'], gamma, beta, act, slot, bits,
+                                                      y if need_f32 else None, pl, lv['hdr'], lv['csum'])
+                        else:
+                            ops.bn_apply_quant(x, m, c, b['mean'], b['rstd'], gamma, beta, act, slot, bits,
+                                               y if need_f32 else None, pl)
                     slot = None                                    # quantized already
                 elif op.attrs['training'] and training:
                     with self.timed('bn_stats'):
@@ -783,11 +859,14 @@ class Executor:
                         gp = self.conv_dy_planes[op]
                         self.side2.wait_stream(torch.cuda.current_stream())
                         with torch.cuda.stream(self.side2):
-                            if op in self.wg_part:
-                                ops.conv2d_tc_wgrad_planes(d, self.planes_of(x_t), gp, self.wg_part[op], None)
+                            part = self.wg_part.get(op)
+                            dw = None if part is not None else st.view(op.vars['kernel'], self.G)
+                            if self._lv_on and self._act_lv_of(x_t) is not None:
+                                ops.conv2d_tc_wgrad_ex(d, self._tc_act(x_t), ops.tc_act(gp),
+                                                       part if part is not None else self.wgrad_ws2, dw)
                             else:
-                                ops.conv2d_tc_wgrad_planes(d, self.planes_of(x_t), gp, self.wgrad_ws2,
-                                                           st.view(op.vars['kernel'], self.G))
+                                ops.conv2d_tc_wgrad_planes(d, self.planes_of(x_t), gp,
+                                                           part if part is not None else self.wgrad_ws2, dw)
                     elif op in self.tc_wgrad:
                         # operands in split-bf16 planes: native (written by BN-apply / BN-backward) or split here
                         xp = self.planes_of(x_t)
@@ -798,10 +877,13 @@ class Executor:
                         if gp is None:
                             gp = ops.Planes(op.output.numel, self.device, self.dy_scratch.buf)
                             ops.split_bf16(gy, gp)
-                        if op in self.wg_part:
-                            ops.conv2d_tc_wgrad_planes(d, xp, gp, self.wg_part[op], None)
+                        part = self.wg_part.get(op)
+                        dw = None if part is not None else st.view(op.vars['kernel'], self.G)
+                        if self._lv_on and self._act_lv_of(x_t) is not None:
+                            ops.conv2d_tc_wgrad_ex(d, self._tc_act(x_t), ops.tc_act(gp),
+                                                   part if part is not None else self.wgrad_ws, dw)
                         else:
-                            ops.conv2d_tc_wgrad_planes(d, xp, gp, self.wgrad_ws, st.view(op.vars['kernel'], self.G))
+                            ops.conv2d_tc_wgrad_planes(d, xp, gp, part if part is not None else self.wgrad_ws, dw)
                     else:
                         gp = None
                         ops.conv2d_wgrad(d, self.T(x_t), gy, self.wgrad_ws, st.view(op.vars['kernel'], self.G))
@@ -990,6 +1072,8 @@ class Executor:
                 raise ValueError('this executor has no weight quantizer')
             self.wq.set_bits(list(w_bits))
             self.weight_quant['bits'] = list(w_bits)
+            if self.tc_batch is not None and self.w_lv:
+                self.tc_batch.set_bits({lv['batch_index']: self.wq.bits[lv['index']] for lv in self.w_lv.values()})
         if a_bits is not None:
             if len(a_bits) != len(self.aq_ops):
                 raise ValueError('one bit-width per quantized activation expected (%d)' % len(self.aq_ops))

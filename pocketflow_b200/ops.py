@@ -476,6 +476,13 @@ def bn_apply_quant(x, m, c, mean, rstd, gamma, beta, act, rng, bits, y=None, pla
                                              _p(planes.lo if planes is not None else None), _stream()), 'pf_bn_apply_quant')
 
 
+def bn_apply_quant_levels(x, m, c, mean, rstd, gamma, beta, act, rng, bits, y, planes, hdr, csum):
+    """Q(act(bn(x))) as a pf_tc_act: integer levels (or hi / lo planes) + device header + channel sums"""
+    _lib.check(_lib.load().pf_bn_apply_quant_levels(_p(x), m, c, _p(mean), _p(rstd), _p(gamma), _p(beta), int(act), _p(rng),
+                                                    int(bits), _p(y), _p(planes.hi), _p(planes.lo), _p(hdr), _p(csum), _stream()),
+               'pf_bn_apply_quant_levels')
+
+
 def bn_eval_prepare(mov_var, c, eps, rstd):
     _lib.check(_lib.load().pf_bn_eval_prepare(_p(mov_var), c, float(eps), _p(rstd), _stream()), 'pf_bn_eval_prepare')
 
@@ -573,31 +580,62 @@ class TcWeights:
 
 TC_PREP_SEG = np.dtype([('w', np.uint64), ('fwd_hi', np.uint64), ('fwd_lo', np.uint64), ('dgrad_hi', np.uint64),
                         ('dgrad_lo', np.uint64), ('rs', np.int32), ('c', np.int32), ('k', np.int32),
-                        ('kpad_f', np.int32), ('kpad_d', np.int32), ('reserved', np.int32)], align=True)
+                        ('kpad_f', np.int32), ('kpad_d', np.int32), ('q_bits', np.int32), ('q_alpha', np.uint64),
+                        ('q_beta', np.uint64), ('q_ralpha', np.uint64), ('q_ncols', np.int32), ('reserved', np.int32)],
+                       align=True)
+assert TC_PREP_SEG.itemsize == 96
 
 
 class TcWeightsBatch:
     """One launch that refreshes the split-bf16 copies of MANY conv kernels (pf_conv2d_tc_prep_weights_multi)."""
 
-    def __init__(self, items, device):
-        """items: list of (TcWeights, fp32 HWIO weight tensor [R,S,C,K])."""
+    def __init__(self, items, device, levels=None):
+        """items: list of (TcWeights, fp32 HWIO weight tensor [R,S,C,K]).
+        levels: {item index: (unquantized weight tensor, alpha, beta, ralpha device views at the tensor's first bucket,
+        ncols, bits)} — those kernels are prepared as integer levels from the UNQUANTIZED weights (pf_tc_prep_seg)."""
         segs = np.zeros(len(items), dtype=TC_PREP_SEG)
         rows = []
+        self.levels = dict(levels or {})
         for i, (tw, w) in enumerate(items):
             r, s_, c, k = w.shape if w.dim() == 4 else (1, 1) + tuple(w.shape)
             segs[i] = (w.data_ptr(), tw.f_hi.data_ptr(), tw.f_lo.data_ptr(),
                        tw.d_hi.data_ptr() if tw.d_hi is not None else 0, tw.d_lo.data_ptr() if tw.d_lo is not None else 0,
-                       r * s_, c, k, tw.f_hi.numel() // k, (tw.d_hi.numel() // c) if tw.d_hi is not None else 0, 0)
+                       r * s_, c, k, tw.f_hi.numel() // k, (tw.d_hi.numel() // c) if tw.d_hi is not None else 0, 0, 0, 0, 0, 0, 0)
+        self.segs_plain = segs.copy()
+        for i, (tw, w) in enumerate(items):
+            r, s_, c, k = w.shape if w.dim() == 4 else (1, 1) + tuple(w.shape)
+            if i in self.levels:
+                w0, al, be, ra, ncols, bits = self.levels[i]
+                if ncols not in (1, k) or not 1 <= int(bits) <= 8:
+                    raise ValueError('weight levels need per-layer or per-output-channel buckets and 1..8 bits')
+                segs[i]['w'], segs[i]['q_bits'], segs[i]['q_ncols'] = w0.data_ptr(), int(bits), int(ncols)
+                segs[i]['q_alpha'], segs[i]['q_beta'], segs[i]['q_ralpha'] = al.data_ptr(), be.data_ptr(), ra.data_ptr()
             for k0 in range(0, r * s_ * c, 32):                 # 32 x 64 tiles of the [R*S*Cin, Cout] matrix
                 for co0 in range(0, k, 64):
                     rows.append((i, 0, k0, 0, co0, 0, 0))
         self.keep = items
+        self.segs = segs
+        self.device = device
         self.work = np.array(rows, dtype=WORK) if rows else np.zeros(0, dtype=WORK)
-        self.segs_dev = torch.from_numpy(segs.view(np.uint8)).to(device)
+        self.segs_dev = torch.from_numpy(segs.view(np.uint8).copy()).to(device)
+        self.segs_plain_dev = torch.from_numpy(self.segs_plain.view(np.uint8).copy()).to(device) if self.levels else self.segs_dev
         self.work_dev = torch.from_numpy(self.work.view(np.uint8)).to(device)
 
-    def prepare(self):
-        _lib.check(_lib.load().pf_conv2d_tc_prep_weights_multi(_p(self.segs_dev), _p(self.work_dev), len(self.work),
+    def set_bits(self, bits_of):
+        """{item index: bits} for the level-prepared kernels (the RL bit search changes them between roll-outs);
+        above 8 bits a kernel goes back to split-bf16 planes of its quantized values"""
+        for i, b in bits_of.items():
+            if i in self.levels:
+                if 1 <= int(b) <= 8:
+                    self.segs[i]['q_bits'], self.segs[i]['w'] = int(b), self.levels[i][0].data_ptr()
+                else:
+                    self.segs[i]['q_bits'], self.segs[i]['w'] = 0, self.segs_plain[i]['w']
+        self.segs_dev = torch.from_numpy(self.segs.view(np.uint8).copy()).to(self.device)
+
+    def prepare(self, levels=True):
+        """levels=False: every kernel as split-bf16 planes of the tensors given at construction (evaluation passes)"""
+        segs = self.segs_dev if levels else self.segs_plain_dev
+        _lib.check(_lib.load().pf_conv2d_tc_prep_weights_multi(_p(segs), _p(self.work_dev), len(self.work),
                                                                _stream()), 'pf_conv2d_tc_prep_weights_multi')
 
 

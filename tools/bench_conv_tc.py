@@ -29,12 +29,20 @@ SHAPES = [  # (name, n, h, w, c, k, r, s, stride, pad, count in ResNet-50)
 ]
 
 
+_FLUSH = None
+
+
 def timeit(fn, iters=5):
+    global _FLUSH
     for _ in range(2):
         fn()
     ts = []
     for _ in range(iters):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if os.environ.get('FLUSH', '1') == '1':          # evict the operands from the 126 MB L2 between iterations
+            if _FLUSH is None:
+                _FLUSH = torch.empty(64 << 20, dtype=torch.float32, device='cuda:0')
+            _FLUSH.fill_(1.0)
         torch.cuda.synchronize()
         a.record()
         fn()
@@ -78,6 +86,33 @@ def main():
             fns = dict(fwd=lambda: ops.conv2d_tc_fwd_planes(d, xp, tw, None, False, y, resid),
                        dgrad=lambda: ops.conv2d_tc_dgrad_planes(d, dyp, tw, False, dx),
                        wgrad=lambda: ops.conv2d_tc_wgrad_planes(d, xp, dyp, ws, dw))
+        variant = os.environ.get('VARIANT', '')
+        if variant:
+            # lsu: cp.async-fed kernels on split planes; tma: TMA-fed, split planes (3 MMAs per k-slice);
+            # levels: TMA-fed, x and the weights as integer quantizer levels (fwd 1 MMA, wgrad 2 MMAs, dgrad as tma)
+            import numpy as np
+            ops.conv2d_tc_set_feed(0 if variant == 'lsu' else 1)
+            xp, dyp = ops.Planes(x.numel(), dev), ops.Planes(dy.numel(), dev)
+            ops.split_bf16(x, xp)
+            ops.split_bf16(dy, dyp)
+            fns = dict(fwd=lambda: ops.conv2d_tc_fwd_planes(d, xp, tw, None, False, y),
+                       dgrad=lambda: ops.conv2d_tc_dgrad_planes(d, dyp, tw, False, dx),
+                       wgrad=lambda: ops.conv2d_tc_wgrad_planes(d, xp, dyp, ws, dw))
+            if variant == 'levels' and ops.conv2d_tc_tma_supported(d, 0) and ops.conv2d_tc_tma_supported(d, 2):
+                lv = torch.randint(0, 256, (n, h, w, c), device=dev).float() * (torch.rand(n, h, w, c, device=dev) > 0.4)
+                lp = ops.Planes(x.numel(), dev)
+                lp.hi.copy_(lv.reshape(-1).to(torch.bfloat16))
+                nseg = (c + 127) // 128
+                csum = lv.reshape(-1, nseg, c // nseg).sum(2).contiguous()
+                hdr = torch.from_numpy(np.array([(0.02, 1)], dtype=ops.ACT_HDR).view(np.uint8)).to(dev)
+                act = ops.tc_act(lp, hdr, csum, nseg)
+                wl = torch.randint(-128, 128, (k, r * s * c), device=dev).to(torch.bfloat16)
+                al, be = torch.rand(k, device=dev) + 0.1, -torch.rand(k, device=dev)
+                wq = ops.tc_wt(wl, None, al, be, True, 8)
+                dya = ops.tc_act(dyp)
+                keep = (lv, lp, csum, hdr, wl, al, be)      # noqa: F841 — keep the device buffers alive
+                fns['fwd'] = lambda: ops.conv2d_tc_fwd_ex(d, act, wq, None, False, y)
+                fns['wgrad'] = lambda: ops.conv2d_tc_wgrad_ex(d, act, dya, ws, dw)
         line = '%-22s' % name
         for ps in passes:
             t = timeit(fns[ps])

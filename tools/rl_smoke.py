@@ -16,6 +16,9 @@ from pocketflow_b200.learners.uniform_quantization.learner import UniformQuantLe
 
 
 def main():
+    import torch
+    torch.manual_seed(0)            # the agent's exploration draws from torch's global generator unless it is seeded
+    np.random.seed(0)
     FLAGS.reset()
     FLAGS.resnet_size, FLAGS.batch_size, FLAGS.batch_size_eval, FLAGS.nb_smpls_eval = 8, 32, 32, 64
     FLAGS.uql_enbl_rl_agent, FLAGS.uql_nb_rlouts, FLAGS.uql_equivalent_bits = True, 6, 5
@@ -43,6 +46,9 @@ def main():
 def ws_main():
     """The pruning-ratio search through the real WeightSparseLearner: 4 roll-outs, 6 fine-tuning steps each."""
     from pocketflow_b200.learners.weight_sparsification.learner import WeightSparseLearner, calc_prune_ratio
+    import torch
+    torch.manual_seed(0)
+    np.random.seed(0)
     FLAGS.reset()
     FLAGS.resnet_size, FLAGS.batch_size, FLAGS.batch_size_eval = 8, 32, 32
     FLAGS.ws_prune_ratio, FLAGS.ws_prune_ratio_prtl = 0.5, 'optimal'

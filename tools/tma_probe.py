@@ -37,6 +37,11 @@ CASES = [
     (2, 14, 14, 64, 192, 3, 3, 1, 1, 1),
     (5, 10, 10, 64, 64, 5, 5, 1, 0, 0),
     (4, 28, 28, 128, 128, 3, 3, 1, 1, 1),
+    # ResNet-50 shapes at batch 2 (the parity tests' configuration)
+    (2, 56, 56, 64, 64, 3, 3, 1, 1, 1),
+    (2, 56, 56, 128, 128, 3, 3, 2, 1, 1),
+    (2, 28, 28, 128, 128, 3, 3, 1, 1, 1),
+    (2, 14, 14, 256, 256, 3, 3, 1, 1, 1),
 ]
 
 
