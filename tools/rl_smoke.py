@@ -10,8 +10,21 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
+import importlib  # noqa: E402
+
 from pocketflow_b200.flags import FLAGS  # noqa: E402
 from pocketflow_b200.nets import resnet_at_cifar10 as R  # noqa: E402
+
+
+def _cifar_defaults():
+    """Dataset / net modules declare their flag defaults at import: re-declare CIFAR-10's (another dataset module may
+    have been imported since, e.g. by an earlier test in the same process)."""
+    global R
+    FLAGS.reset()
+    import pocketflow_b200.datasets.cifar10_dataset as D
+    importlib.reload(D)
+    R = importlib.reload(R)
+
 from pocketflow_b200.learners.uniform_quantization.learner import UniformQuantLearner  # noqa: E402
 
 
@@ -19,7 +32,7 @@ def main():
     import torch
     torch.manual_seed(0)            # the agent's exploration draws from torch's global generator unless it is seeded
     np.random.seed(0)
-    FLAGS.reset()
+    _cifar_defaults()
     FLAGS.resnet_size, FLAGS.batch_size, FLAGS.batch_size_eval, FLAGS.nb_smpls_eval = 8, 32, 32, 64
     FLAGS.uql_enbl_rl_agent, FLAGS.uql_nb_rlouts, FLAGS.uql_equivalent_bits = True, 6, 5
     FLAGS.uql_tune_global_steps, FLAGS.uql_tune_disp_steps = 8, 4
@@ -49,7 +62,7 @@ def ws_main():
     import torch
     torch.manual_seed(0)
     np.random.seed(0)
-    FLAGS.reset()
+    _cifar_defaults()
     FLAGS.resnet_size, FLAGS.batch_size, FLAGS.batch_size_eval = 8, 32, 32
     FLAGS.ws_prune_ratio, FLAGS.ws_prune_ratio_prtl = 0.5, 'optimal'
     FLAGS.ws_nb_rlouts, FLAGS.ws_nb_rlouts_min, FLAGS.ws_nb_iters_ft, FLAGS.ws_nb_iters_feval = 4, 2, 6, 2
