@@ -55,7 +55,7 @@ WORKLOADS = {
     'lenet_uq8_b128': ('lenet_at_cifar10', 0, 'uniform', dict(batch_size=128, uql_weight_bits=8),
                        'LeNet-5 / synthetic CIFAR-10, UniformQuantLearner 8-bit (configs[0], plumbing)'),
 }
-DEFAULT_WORKLOAD = 'resnet50_uq8_dst_b256'
+DEFAULT_WORKLOAD = os.environ.get('PF_BENCH_WORKLOAD', 'resnet50_uq8_dst_b256')    # the driver passes no --workload
 
 
 def setup_flags(workload, batch_override=None, world=1):
@@ -258,12 +258,33 @@ def cpu_oracle_rate_bounded(workload, sample_batch, steps, threads, budget_s, ha
             hard_timeout_s, sample_batch)
 
 
+def cpu_sample_batch(args):
+    """Mini-batch of the CPU legs: the workload's own batch where a step fits the time budget (CIFAR / LeNet), 16 for the
+    224x224 networks (a batch-2 sample would handicap the CPU: its GEMMs do not fill 16 cores)."""
+    if args.cpu_batch:
+        return args.cpu_batch
+    full = WORKLOADS[args.workload][3]['batch_size']
+    return min(full, 16 if ('resnet50' in args.workload or 'mobilenet' in args.workload) else 64)
+
+
+def kernel_source_stamp():
+    """sha1 over the conv kernel sources: profiles/*_conv_traffic.json carries the stamp of the binary it was measured
+    with, and a stale file is refused (the GPU box has no .git to ask for a commit id)."""
+    import hashlib
+    h = hashlib.sha1()
+    d = os.path.join(ROOT, 'pocketflow_b200', 'csrc')
+    for fn in ('pf_conv_tc.cu', 'pf_conv_tma.cu', 'pf_conv_tc.cuh', 'pf_tma.cuh', 'pf_tc_common.cuh'):
+        with open(os.path.join(d, fn), 'rb') as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
     cores = host_threads()
-    sb = args.cpu_batch or (2 if 'resnet50' in args.workload else (4 if 'mobilenet' in args.workload else 64))
-    rate, sec, steps, note = cpu_oracle_rate_bounded(args.workload, sb, args.steps, cores, 120.0, 280)
+    sb = cpu_sample_batch(args)
+    rate, sec, steps, note = cpu_oracle_rate_bounded(args.workload, sb, args.steps, cores, 150.0, 290)
     if rate is None:
         emit({'impl': 'reference', 'unavailable': note})
         return
@@ -271,7 +292,7 @@ def run_reference(args, rank):
         'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': 'images/s', 'n_gpus': args.gpus,
         'steps': steps, 'warmup': 1, 'steps_requested': args.steps, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': args.workload, 'description': WORKLOADS[args.workload][4],
+        'config': {'workload': args.workload, 'description': WORKLOADS[args.workload][4], 'sample_batch': sb,
                    'note': 'TensorFlow 1.x (the reference runtime) is not installable in this image; this is the '
                            'oracle restatement of the reference step, un-fused, PyTorch-CPU fp32'},
         'cpu_baseline': {'value': rate, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
@@ -420,13 +441,22 @@ def main():
     aq_elems = sum(op.output.numel for e in ([ex] + ([ex.teacher] if ex.teacher is not None else []))
                    for op in e.ops if op.type == 'FusedBatchNorm')
     aq_ms = prof.get('bn_apply', 0.0)
-    conv_traffic = None
+    conv_traffic, traffic_src = None, 'no ncu launch list of this binary under profiles/ (run tools/gpu_launchlist.sh)'
     try:
-        tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r1_ncu_conv_traffic.json')))
-        if tj.get('workload') == args.workload and B == tj.get('batch'):
+        tj = json.load(open(os.path.join(ROOT, 'profiles', 'r2_ncu_conv_traffic.json')))
+        if tj.get('workload') != args.workload or B != tj.get('batch'):
+            traffic_src = 'profiles/r2_ncu_conv_traffic.json is for another workload / batch'
+        elif tj.get('kernel_source_stamp') != kernel_source_stamp():
+            traffic_src = 'profiles/r2_ncu_conv_traffic.json is stale (kernel sources changed since it was measured)'
+        else:
             conv_traffic = tj['conv_dram_bytes_per_step']
+            traffic_src = 'ncu launch list of this binary (kernel source stamp %s), profiles/r2_ncu_conv_traffic.json' % tj['kernel_source_stamp']
     except Exception:  # noqa: BLE001
         pass
+    # MMA multiplicity per pass (tensor-core work issued per algorithmic product)
+    n_lv_w = len(getattr(ex, 'w_lv', {}))
+    n_lv_a = len(getattr(ex, 'act_lv', {}))
+    n_tc = len(ex.tc)
     if rank == 0:
         value = B * world * args.steps / (ms_total * 1e-3)
         e2e_value = B * world * args.steps / (e2e_ms * 1e-3)
@@ -436,26 +466,34 @@ def main():
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': args.workload, 'description': WORKLOADS[args.workload][4],
                        'batch_per_gpu': B, 'global_batch': B * world, 'parallelism': 'dp%d' % world,
-                       'conv_path': ('tcgen05 split-bf16 (3 bf16 MMAs per k-slice into one fp32 TMEM accumulator = fp32-equivalent '
-                                     'product) fwd+dgrad+wgrad, persistent warp-specialised kernels fed from split-bf16 operand '
-                                     'planes: %d of %d conv/dense layers (+ the stem through im2col planes); exact-fp32 CUDA-core '
-                                     'kernels for the rest' % (len(ex.tc), sum(1 for o in ex.ops if o.type in ('Conv2D', 'MatMul'))))
+                       'conv_path': ('tcgen05 + TMEM, persistent warp-specialised kernels, operands fed by TMA (im2col-mode '
+                                     'tensor maps for the NHWC operand, tiled maps for weights / dy) where channel counts are '
+                                     'multiples of 64, cp.async elsewhere: %d of %d conv/dense layers (+ the stem through '
+                                     'space-to-depth planes); exact-fp32 CUDA-core kernels for the rest.  MMAs per k-slice: '
+                                     'student fwd 1 on %d layers (integer quantizer levels x levels, exact in bf16; 3 on the '
+                                     'others), wgrad 2 on %d layers (levels x split-bf16 dy), dgrad 3, teacher fwd 3 '
+                                     '(split-bf16 x split-bf16 = fp32-equivalent product)'
+                                     % (n_tc, sum(1 for o in ex.ops if o.type in ('Conv2D', 'MatMul')), n_lv_w, n_lv_a))
                        if ex.tc or ex.im2col else 'fp32 CUDA-core implicit GEMM (pf_conv.cu)',
                        'l2': 'per-step working set (GBs of activations) >> 126 MB L2; no explicit flush',
                        'cuda_graph': graph_ok,
                        'input_pipeline': 'e2e: batch i+1 is copied host->device (pinned memory, copy stream) while step i '
                                          'runs, then moved into the graph input buffers device-to-device; one H2D per step'},
             'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': int(lrn.h2d_bytes),
-                    'd2h_bytes_per_step': 20, 'ms_per_step': e2e_ms / args.steps},
+                    'd2h_bytes_per_step': int(getattr(ex, 'last_d2h_bytes', 0)), 'ms_per_step': e2e_ms / args.steps},
             'gpu_launches': int(launches_per_step * args.steps),
             'launches_per_step': int(launches_per_step),
             'roofline': {'bound': 'tensor',
-                         'kernel': 'conv stack: conv_tc_persist_kernel (fwd, dgrad) + conv_tc_wgrad_persist_kernel',
+                         'kernel': 'conv stack: conv_tma_kernel (fwd, dgrad) + conv_tma_wgrad_kernel (+ conv_tc_persist_kernel for '
+                                   'the stem and strided dgrad)',
                          'achieved': conv_tflops, 'peak': tf_sust, 'unit': 'TFLOP/s',
                          'frac': conv_tflops / tf_sust, 'traffic': conv_traffic,
-                         'traffic_note': 'DRAM bytes of the conv kernels per step, ncu launch list (profiles/); achieved '
-                                         'counts ALGORITHMIC flops (2*M*N*K per conv pass); the split-bf16 scheme issues 3x '
-                                         'that on the tensor cores, so frac <= 1/3 by construction',
+                         'traffic_source': traffic_src,
+                         'traffic_note': 'achieved counts ALGORITHMIC flops (2*M*N*K per conv pass: student fwd, teacher fwd, '
+                                         'dgrad, wgrad) over the conv kernels\' summed device time in ONE EAGER INSTRUMENTED '
+                                         'step (CUDA events per launch group; `value` comes from the graph replay); the tensor '
+                                         'cores issue 1 / 3 / 3 / 2 MMAs per product on those passes (9 units per 4 passes '
+                                         'against 12 for all-split-bf16), so frac <= 4/9 by construction',
                          'peak_kind': peak_kind + ' bf16 sustained',
                          'flops_per_step': conv_flops, 'ms_per_step': conv_ms,
                          'share_of_step': conv_ms / step_ms_eager if step_ms_eager else None},
@@ -470,9 +508,9 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             cores = host_threads()
-            sb = args.cpu_batch or (2 if 'resnet50' in args.workload else (4 if 'mobilenet' in args.workload else 64))
+            sb = cpu_sample_batch(args)
             try:
-                rate, sec, nst, note = cpu_oracle_rate_bounded(args.workload, sb, 2, cores, 25.0, 120)
+                rate, sec, nst, note = cpu_oracle_rate_bounded(args.workload, sb, 2, cores, 30.0, 150)
                 line['cpu_baseline'] = {'value': rate, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
                                         'sample': ('%d step(s) of batch %d of the same graph (bounded sample, %.1f s '
                                                    'per step), oracle/step_oracle.py' % (nst, sb, sec)) if rate else note}

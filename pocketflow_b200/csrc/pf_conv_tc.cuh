@@ -59,6 +59,11 @@ constexpr int kRingDepth = 4;
 constexpr int kRingSlotBytes = 32 * 32 * 4;
 constexpr int kEpiFixedBytes = 1024 + kEpiWarps * 32 * kStagePitch * 4 + kEpiWarps * 32 * 8 + kEpiWarps * 32 * 4 + 256;
 
+// TMA-fed kernels: 8 epilogue warps (two per TMEM lane quarter, even / odd 32-column chunks), each with its own staging
+// tile, row-offset table, J table and (optional) residual ring
+constexpr int kTmaEpiWarps = 8;
+constexpr int kTmaEpiFixedBytes = 1024 + kTmaEpiWarps * (32 * kStagePitch * 4 + 32 * 8 + 32 * 4) + 256;
+
 struct EpiAff {
   const float* w_alpha;    // per-bucket alpha = (max - min) + 1e-10 of the weight quantizer (device)
   const float* w_beta;     // per-bucket beta = min
@@ -73,7 +78,10 @@ __device__ __forceinline__ void epilogue_tile_t(uint32_t t_acc, uint64_t* tfull,
                                                 float* __restrict__ stg, float* __restrict__ out,
                                                 const float* __restrict__ extra, const float* __restrict__ bias,
                                                 int relu, int n0, int BN, int Ng, int q, int lane, uint8_t* ring,
-                                                const EpiAff& aff, float my_j, float* __restrict__ jrow) {
+                                                const EpiAff& aff, float my_j, float* __restrict__ jrow,
+                                                int c_begin = 0, int c_step = 32) {
+  // c_begin / c_step: this warp handles the 32-column chunks c_begin, c_begin + c_step, ... (two warps of the same TMEM
+  // lane quarter split a tile's columns between them in the TMA-fed kernels: c_step = 64)
   rowoff[lane] = my_row_off;
   if (AFF == 2) jrow[lane] = my_j;
   __syncwarp();
@@ -98,11 +106,11 @@ __device__ __forceinline__ void epilogue_tile_t(uint32_t t_acc, uint64_t* tfull,
   // ring: every lane copies exactly the 16-byte pieces it will read back itself (no cross-lane hand-off); one
   // commit group per chunk, empty groups past the end keep the wait_group count uniform
   const uint32_t ring_u32 = (EXTRA == 2) ? smem_u32(ring) : 0u;
-  auto ring_issue = [&](int c0) {
+  auto ring_issue = [&](int c0, int it) {
     if (c0 < BN) {
       const int cv = c0 + csub;
       const bool cok = cv < BN && n0 + cv + 3 < Ng;
-      const uint32_t slot = ring_u32 + (uint32_t)((c0 >> 5) & (kRingDepth - 1)) * kRingSlotBytes;
+      const uint32_t slot = ring_u32 + (uint32_t)(it & (kRingDepth - 1)) * kRingSlotBytes;
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const bool ok = cok && ro[u] >= 0;
@@ -114,33 +122,17 @@ __device__ __forceinline__ void epilogue_tile_t(uint32_t t_acc, uint64_t* tfull,
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   float4 xa[8], xb[8];                           // dead (eliminated) unless EXTRA == 1
-  if (EXTRA == 1) load_extra(0, xa);
+  if (EXTRA == 1) load_extra(c_begin, xa);
   if (EXTRA == 2) {
 #pragma unroll
-    for (int c = 0; c < kRingDepth; ++c) ring_issue(32 * c);
+    for (int c = 0; c < kRingDepth; ++c) ring_issue(c_begin + c_step * c, c);
   }
   mbar_wait_bounded(tfull, parity);
   tc_fence_after();
   const uint32_t t_addr = t_acc + (((uint32_t)(q * 32)) << 16);
-  for (int c0 = 0; c0 < BN; c0 += 32) {
-    uint32_t r[32];
-    if (!zero_tile) {
-      tmem_ld_32x32(t_addr + (uint32_t)c0, r);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) r[j] = 0u;
-    }
-    if (c0 + 32 >= BN) {                         // last read of this accumulator: hand it back to the MMA warp
-      tc_fence_before();
-      mbar_arrive(tempty);
-    }
-#pragma unroll
-    for (int j = 0; j < 32; j += 4)
-      *reinterpret_cast<uint4*>(stg + lane * kStagePitch + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-    __syncwarp();
-    if (EXTRA == 1 && c0 + 32 < BN) load_extra(c0 + 32, xb);
-    if (EXTRA == 2) asm volatile("cp.async.wait_group %0;" ::"n"(kRingDepth - 1) : "memory");   // chunk c0 has landed
-    const float* slot = reinterpret_cast<const float*>(ring + (size_t)((c0 >> 5) & (kRingDepth - 1)) * kRingSlotBytes);
+  int it = 0;
+  for (int c0 = c_begin; c0 < BN; c0 += c_step, ++it) {
+    // per-column constants first: their global loads overlap the TMEM read below
     // rows 4*u + (lane >> 3), 16-byte chunk (lane & 7): 8 lanes write one row's 128 contiguous bytes
     const int cv = c0 + csub;
     const bool cok = cv < BN && n0 + cv + 3 < Ng;
@@ -162,6 +154,24 @@ __device__ __forceinline__ void epilogue_tile_t(uint32_t t_acc, uint64_t* tfull,
       e2 = make_float4(fmaf(aff.w_centre, sx, be.x) * a_s, fmaf(aff.w_centre, sy, be.y) * a_s,
                        fmaf(aff.w_centre, sz, be.z) * a_s, fmaf(aff.w_centre, sw_, be.w) * a_s);
     }
+    uint32_t r[32];
+    if (!zero_tile) {
+      tmem_ld_32x32(t_addr + (uint32_t)c0, r);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r[j] = 0u;
+    }
+    if (c0 + c_step >= BN) {                     // last read of this accumulator: hand it back to the MMA warp
+      tc_fence_before();
+      mbar_arrive(tempty);
+    }
+#pragma unroll
+    for (int j = 0; j < 32; j += 4)
+      *reinterpret_cast<uint4*>(stg + lane * kStagePitch + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+    __syncwarp();
+    if (EXTRA == 1 && c0 + c_step < BN) load_extra(c0 + c_step, xb);
+    if (EXTRA == 2) asm volatile("cp.async.wait_group %0;" ::"n"(kRingDepth - 1) : "memory");   // chunk c0 has landed
+    const float* slot = reinterpret_cast<const float*>(ring + (size_t)(it & (kRingDepth - 1)) * kRingSlotBytes);
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       float4 v[4], xr[4];
@@ -195,9 +205,13 @@ __device__ __forceinline__ void epilogue_tile_t(uint32_t t_acc, uint64_t* tfull,
 #pragma unroll
       for (int u = 0; u < 8; ++u) xa[u] = xb[u];
     }
-    if (EXTRA == 2) ring_issue(c0 + 32 * kRingDepth);   // refill the slot just consumed
+    if (EXTRA == 2) ring_issue(c0 + c_step * kRingDepth, it + kRingDepth);   // refill the slot just consumed
   }
   if (EXTRA == 2) asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if (c_begin >= BN) {                           // no chunk for this warp (BN < 64): release the accumulator all the same
+    tc_fence_before();
+    mbar_arrive(tempty);
+  }
 }
 
 template <int AFF>
@@ -206,10 +220,10 @@ __device__ __forceinline__ void epilogue_tile_a(uint32_t t_acc, uint64_t* tfull,
                                                 float* __restrict__ out, const float* __restrict__ extra,
                                                 const float* __restrict__ bias, int relu, int n0, int BN, int Ng,
                                                 int q, int lane, uint8_t* ring, const EpiAff& aff, float my_j,
-                                                float* jrow) {
-  if (extra && ring) epilogue_tile_t<2, AFF>(t_acc, tfull, tempty, parity, zero_tile, my_row_off, rowoff, stg, out, extra, bias, relu, n0, BN, Ng, q, lane, ring, aff, my_j, jrow);
-  else if (extra) epilogue_tile_t<1, AFF>(t_acc, tfull, tempty, parity, zero_tile, my_row_off, rowoff, stg, out, extra, bias, relu, n0, BN, Ng, q, lane, nullptr, aff, my_j, jrow);
-  else epilogue_tile_t<0, AFF>(t_acc, tfull, tempty, parity, zero_tile, my_row_off, rowoff, stg, out, nullptr, bias, relu, n0, BN, Ng, q, lane, nullptr, aff, my_j, jrow);
+                                                float* jrow, int c_begin = 0, int c_step = 32) {
+  if (extra && ring) epilogue_tile_t<2, AFF>(t_acc, tfull, tempty, parity, zero_tile, my_row_off, rowoff, stg, out, extra, bias, relu, n0, BN, Ng, q, lane, ring, aff, my_j, jrow, c_begin, c_step);
+  else if (extra) epilogue_tile_t<1, AFF>(t_acc, tfull, tempty, parity, zero_tile, my_row_off, rowoff, stg, out, extra, bias, relu, n0, BN, Ng, q, lane, nullptr, aff, my_j, jrow, c_begin, c_step);
+  else epilogue_tile_t<0, AFF>(t_acc, tfull, tempty, parity, zero_tile, my_row_off, rowoff, stg, out, nullptr, bias, relu, n0, BN, Ng, q, lane, nullptr, aff, my_j, jrow, c_begin, c_step);
 }
 __device__ __forceinline__ void epilogue_tile(uint32_t t_acc, uint64_t* tfull, uint64_t* tempty, uint32_t parity,
                                               bool zero_tile, long long my_row_off, long long* rowoff, float* stg,

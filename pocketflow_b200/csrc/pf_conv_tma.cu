@@ -20,7 +20,7 @@ namespace pfconv {
 using namespace pftma;
 
 constexpr int kTmaMaxStages = 8;
-constexpr int kTmaThreads = 192;     // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int kTmaThreads = (2 + kTmaEpiWarps) * 32;     // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: epilogue
 constexpr uint32_t kATileBytes = TM * 128;
 
 struct TmaP {
@@ -30,7 +30,7 @@ struct TmaP {
   int src_h, src_w;                        // gathered tensor
   int base_w, base_h, str_w, str_h, flip;  // window origin of row (y, x): (base + x * str); flip: tap offsets mirrored
   int na, nb;                              // operand planes (na: upper bound when a_hdr decides)
-  int accumulate, relu, ring, stage_budget;
+  int accumulate, relu, ring, stage_budget, epi_warps;
   FastDiv d_hw, d_w, d_ntiles, d_cblocks, d_s;
   EpiAff aff;
   const pf_tc_act_hdr* a_hdr;
@@ -61,9 +61,9 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   const uint32_t n_stages = min((uint32_t)kTmaMaxStages, (uint32_t)p.stage_budget / stage_bytes);
   uint8_t* epi = smem + p.stage_budget;
   float* stage_all = reinterpret_cast<float*>(epi);
-  long long* rowoff_all = reinterpret_cast<long long*>(stage_all + kEpiWarps * 32 * kStagePitch);
-  float* jrow_all = reinterpret_cast<float*>(rowoff_all + kEpiWarps * 32);
-  uint8_t* ring_all = reinterpret_cast<uint8_t*>(jrow_all + kEpiWarps * 32);
+  long long* rowoff_all = reinterpret_cast<long long*>(stage_all + p.epi_warps * 32 * kStagePitch);
+  float* jrow_all = reinterpret_cast<float*>(rowoff_all + p.epi_warps * 32);
+  uint8_t* ring_all = reinterpret_cast<uint8_t*>(jrow_all + p.epi_warps * 32);
 
   if (tid == 0) {
     for (int s = 0; s < kTmaMaxStages; ++s) {
@@ -72,7 +72,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], kEpiWarps * 32);
+      mbar_init(&tempty_bar[b], p.epi_warps * 32);
     }
     fence_barrier_init();
   }
@@ -145,12 +145,13 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         umma_commit(&tfull_bar[buf]);        // accumulator of this tile complete
       }
     }
-  } else {
-    // =================================== epilogue (warps 2-5) ===================================
+  } else if (warp < 2 + p.epi_warps) {
+    // =================================== epilogue (warps 2-9, or 2-5 when shared memory is short) =================
     const int q = warp & 3;                  // TMEM lane quarter this warp may read
-    float* stg = stage_all + (size_t)q * 32 * kStagePitch;
-    long long* rowoff = rowoff_all + q * 32;
-    float* jrow = jrow_all + q * 32;
+    const int ew = warp - 2, half = ew >> 2; // two warps per quarter: even / odd 32-column chunks
+    float* stg = stage_all + (size_t)ew * 32 * kStagePitch;
+    long long* rowoff = rowoff_all + ew * 32;
+    float* jrow = jrow_all + ew * 32;
     const float* extra = residual ? residual : (p.accumulate ? out : nullptr);
     uint32_t tcount = 0;
     for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++tcount) {
@@ -178,8 +179,8 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       }
       epilogue_tile_a<AFF>(tmem_base + (tcount & 1u) * (uint32_t)p.acc_cols, &tfull_bar[tcount & 1u],
                            &tempty_bar[tcount & 1u], (tcount >> 1) & 1u, false, off, rowoff, stg, out, extra, bias, p.relu,
-                           n0, BN, p.Ng, q, lane, p.ring ? ring_all + (size_t)q * kRingDepth * kRingSlotBytes : nullptr,
-                           p.aff, my_j, jrow);
+                           n0, BN, p.Ng, q, lane, p.ring ? ring_all + (size_t)ew * kRingDepth * kRingSlotBytes : nullptr,
+                           p.aff, my_j, jrow, 32 * half, 8 * p.epi_warps);
     }
   }
   tc_fence_before();
@@ -196,7 +197,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 struct WgTmaP {
   TcGeom g;
   int Mtot, Npix, pps, splits, BN, n_tiles, tiles, total_units, acc_cols;
-  int na, nb, stage_budget;
+  int na, nb, stage_budget, epi_warps;
   FastDiv d_pq, d_q, d_c, d_s, d_tiles, d_ntiles;
   EpiAff aff;
   const pf_tc_act_hdr* x_hdr;
@@ -223,8 +224,8 @@ conv_tma_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_con
   const uint32_t n_stages = min((uint32_t)kTmaMaxStages, (uint32_t)p.stage_budget / stage_bytes);
   uint8_t* epi = smem + p.stage_budget;
   float* stage_all = reinterpret_cast<float*>(epi);
-  long long* rowoff_all = reinterpret_cast<long long*>(stage_all + kEpiWarps * 32 * kStagePitch);
-  float* jrow_all = reinterpret_cast<float*>(rowoff_all + kEpiWarps * 32);
+  long long* rowoff_all = reinterpret_cast<long long*>(stage_all + p.epi_warps * 32 * kStagePitch);
+  float* jrow_all = reinterpret_cast<float*>(rowoff_all + p.epi_warps * 32);
   if (tid == 0) {
     for (int s = 0; s < kTmaMaxStages; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -232,7 +233,7 @@ conv_tma_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_con
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], kEpiWarps * 32);
+      mbar_init(&tempty_bar[b], p.epi_warps * 32);
     }
     fence_barrier_init();
   }
@@ -335,11 +336,12 @@ conv_tma_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_con
         else mbar_arrive(&tfull_bar[buf]);
       }
     }
-  } else {
+  } else if (warp < 2 + p.epi_warps) {
     const int q = warp & 3;
-    float* stg = stage_all + (size_t)q * 32 * kStagePitch;
-    long long* rowoff = rowoff_all + q * 32;
-    float* jrow = jrow_all + q * 32;
+    const int ew = warp - 2, half = ew >> 2;
+    float* stg = stage_all + (size_t)ew * 32 * kStagePitch;
+    long long* rowoff = rowoff_all + ew * 32;
+    float* jrow = jrow_all + ew * 32;
     uint32_t tcount = 0;
     for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++tcount) {
       const Unit un = decode(u);
@@ -347,7 +349,7 @@ conv_tma_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_con
       const long long off = em < p.Mtot ? ((long long)un.split * p.Mtot + em) * g.K : -1;
       epilogue_tile_a<AFF>(tmem_base + (tcount & 1u) * (uint32_t)p.acc_cols, &tfull_bar[tcount & 1u],
                            &tempty_bar[tcount & 1u], (tcount >> 1) & 1u, un.nk == 0, off, rowoff, stg, partial, nullptr,
-                           nullptr, 0, un.n0, BN, g.K, q, lane, nullptr, p.aff, 0.f, jrow);
+                           nullptr, 0, un.n0, BN, g.K, q, lane, nullptr, p.aff, 0.f, jrow, 32 * half, 8 * p.epi_warps);
     }
   }
   tc_fence_before();
@@ -461,19 +463,31 @@ int conv_tma_launch(int pass, const TcGeom& g, const pf_tc_act& a, const pf_tc_w
     aff = 1;
     p.aff.a_scale = &a.hdr->scale;
   }
-  // ---- shared memory: [stages][epilogue staging, row offsets, J][residual ring]
+  // ---- shared memory: [stages][epilogue staging, row offsets, J][residual ring]; 8 epilogue warps when at least two
+  // (three with a residual ring) stages still fit beside their staging tiles, else 4
   const int stage_max = p.na * (int)kATileBytes + p.nb * BN * 128;
-  const int ring_bytes = kEpiWarps * kRingDepth * kRingSlotBytes;
   const bool has_extra = residual != nullptr || accumulate;
-  int budget = (kSmemLimit - kEpiFixedBytes) / 1024 * 1024;
+  auto epi_bytes = [](int warps) { return 1024 + warps * (32 * kStagePitch * 4 + 32 * 8 + 32 * 4) + 256; };
+  // 8 epilogue warps unless their staging tiles cost a pipeline stage that 4 warps would leave (below 4 stages)
+  const int st8 = (kSmemLimit - epi_bytes(kTmaEpiWarps)) / 1024 * 1024 / stage_max, st4 = (kSmemLimit - epi_bytes(4)) / 1024 * 1024 / stage_max;
+  p.epi_warps = (BN >= 64 && st8 >= 2 && (st8 >= 4 || st8 == st4)) ? kTmaEpiWarps : 4;
+  p.epi_warps = env_int("PF_TC_EPI_WARPS", p.epi_warps) == 4 ? 4 : p.epi_warps;
+  int ring_bytes = p.epi_warps * kRingDepth * kRingSlotBytes;
+  int budget = (kSmemLimit - epi_bytes(p.epi_warps)) / 1024 * 1024;
   p.ring = 0;
-  if (has_extra && env_int("PF_TC_RING", 1) && BN >= 64 && (budget - ring_bytes) / stage_max >= 3) {
-    p.ring = 1;
-    budget = (kSmemLimit - kEpiFixedBytes - ring_bytes) / 1024 * 1024;
+  if (has_extra && env_int("PF_TC_RING", 1) && BN >= 64) {
+    if ((budget - ring_bytes) / stage_max < 3 && p.epi_warps == kTmaEpiWarps) {       // try the ring with 4 warps
+      const int b4 = (kSmemLimit - epi_bytes(4)) / 1024 * 1024, r4 = 4 * kRingDepth * kRingSlotBytes;
+      if ((b4 - r4) / stage_max >= 3 && env_int("PF_TC_RING_PREFER", 0)) { p.epi_warps = 4; budget = b4; ring_bytes = r4; }
+    }
+    if ((budget - ring_bytes) / stage_max >= 3) {
+      p.ring = 1;
+      budget = (kSmemLimit - epi_bytes(p.epi_warps) - ring_bytes) / 1024 * 1024;
+    }
   }
   PF_REQUIRE(budget / stage_max >= 2 || p.nk <= 1, "%s: shared-memory plan failed (BN %d)", who, BN);
   p.stage_budget = budget;
-  const size_t smem = 1024 + (size_t)budget + (kEpiFixedBytes - 1024) + (p.ring ? ring_bytes : 0);
+  const size_t smem = 1024 + (size_t)budget + (epi_bytes(p.epi_warps) - 1024) + (p.ring ? ring_bytes : 0);
   if (p.total_tiles == 0) return PF_OK;
   // ---- tensor maps
   alignas(64) CUtensorMap tA0, tA1, tB0, tB1;
@@ -536,10 +550,13 @@ int conv_tma_wgrad_launch(const TcGeom& g, const pf_tc_act& x, const pf_tc_act& 
     p.aff.a_scale = &x.hdr->scale;
   }
   const int stage_max = p.na * 2 * (int)kWgBlockBytes + p.nb * (BN / 64) * (int)kWgBlockBytes;
-  const int budget = (kSmemLimit - kEpiFixedBytes) / 1024 * 1024;
+  auto epi_bytes = [](int warps) { return 1024 + warps * (32 * kStagePitch * 4 + 32 * 8 + 32 * 4) + 256; };
+  const int st8 = (kSmemLimit - epi_bytes(kTmaEpiWarps)) / 1024 * 1024 / stage_max, st4 = (kSmemLimit - epi_bytes(4)) / 1024 * 1024 / stage_max;
+  p.epi_warps = (st8 >= 2 && (st8 >= 4 || st8 == st4)) ? kTmaEpiWarps : 4;
+  const int budget = (kSmemLimit - epi_bytes(p.epi_warps)) / 1024 * 1024;
   PF_REQUIRE(budget / stage_max >= 2, "%s: shared-memory plan failed (BN %d)", who, BN);
   p.stage_budget = budget;
-  const size_t smem = 1024 + (size_t)budget + (kEpiFixedBytes - 1024);
+  const size_t smem = 1024 + (size_t)budget + (epi_bytes(p.epi_warps) - 1024);
   if (p.total_units == 0) return PF_OK;
   alignas(64) CUtensorMap tX0, tX1, tY0, tY1;
   PF_TMA_ENCODE(encode_im2col_bf16(&tX0, x.plane0, g.N, g.H, g.W, g.C, -g.pl, -g.pt, g.Q, g.P, g.sw, g.sh, BK, BK), who);

@@ -1106,7 +1106,9 @@ class Executor:
 
     def fetch_losses(self):
         """(hard CE, distillation, l2, total, top1, top5) of the last step — one small D2H read."""
-        o = torch.cat([self.loss_out[:4], self.l2_out[:1]]).cpu().numpy()
+        dev_vals = torch.cat([self.loss_out[:4], self.l2_out[:1]])
+        self.last_d2h_bytes = dev_vals.numel() * dev_vals.element_size()      # what this call reads back
+        o = dev_vals.cpu().numpy()
         hard, dst, top1, top5, l2 = [F32(x) for x in o]
         total = F32(F32(hard + l2) + dst)
         return dict(model_loss=F32(hard + l2), dst_loss=dst, l2=l2, ce=hard, loss=total, acc_top1=top1,

@@ -57,7 +57,10 @@ def main():
     passes = os.environ.get('PASSES', 'fwd,dgrad,wgrad').split(',')
     dev = torch.device('cuda:0')
     res, tot = [], {}
+    only = os.environ.get('ONLY', '')
     for name, n, h, w, c, k, r, s, st, pd, cnt in SHAPES:
+        if only and only not in name:
+            continue
         p = (h + 2 * pd - r) // st + 1
         d = ops.conv_desc(n, h, w, c, k, r, s, p, p, st, st, pd, pd)
         x = torch.randn(n, h, w, c, device=dev)
