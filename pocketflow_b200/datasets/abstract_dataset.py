@@ -31,14 +31,30 @@ class BatchIterator(object):
         """generator(b) -> (images [b,...] float32, one-hot labels [b,k] float32) as numpy arrays.
         stream=False: the synthetic case — POOL_SIZE batches are generated once and cycled.
         stream=True : a real dataset — every call draws a fresh batch from the generator into one of POOL_SIZE
-                      rotating pinned buffers (a buffer is reused POOL_SIZE calls later, long after its async
-                      host->device copy has run)."""
+                      rotating pinned buffers.  The consumer calls `copy_enqueued()` right after it has enqueued
+                      the async host->device copy of the batch it was handed; a slot is rewritten only after THAT
+                      copy has executed (the host can run many steps ahead of the GPU — steps are enqueued without a
+                      per-step synchronisation — so "POOL_SIZE calls later" alone is not a guarantee)."""
         self.batch_size, self.image_shape, self.nb_classes = batch_size, tuple(image_shape), nb_classes
         self.generator = generator
         self.stream = stream
         self.images, self.labels = None, None
         self.pin = torch.cuda.is_available()
         self.pool, self.pool_size, self.cursor = [], POOL_SIZE, 0
+        self.slot_copied, self.last_slot = {}, None        # slot -> CUDA event recorded after its H2D copy was enqueued
+
+    def copy_enqueued(self):
+        """To be called by the consumer on the stream it has just enqueued the H2D copy of the last batch on."""
+        if self.stream and self.pin and self.last_slot is not None:
+            ev = self.slot_copied.get(self.last_slot)
+            if ev is None:
+                ev = self.slot_copied[self.last_slot] = torch.cuda.Event()
+            ev.record()
+
+    def _wait_slot_free(self, slot):
+        ev = self.slot_copied.get(slot)
+        if ev is not None:
+            ev.synchronize()
 
     def get_next(self):
         """Symbolic (images, labels) of the current default graph."""
@@ -63,11 +79,14 @@ class BatchIterator(object):
             hi.copy_(torch.from_numpy(img))
             hl.copy_(torch.from_numpy(lab))
             self.pool.append((hi, hl))
+            self.last_slot = len(self.pool) - 1
             return hi, hl
-        out = self.pool[self.cursor % self.pool_size]
+        self.last_slot = self.cursor % self.pool_size
+        out = self.pool[self.last_slot]
         self.cursor += 1
         if self.stream:
             img, lab = self.generator(self.batch_size)
+            self._wait_slot_free(self.last_slot)
             out[0].copy_(torch.from_numpy(img))
             out[1].copy_(torch.from_numpy(lab))
         return out
@@ -90,8 +109,9 @@ class PackedBatchIterator(BatchIterator):
         """(crops uint8 [capacity >= nbytes], nbytes, descriptors uint8 [b * 40], labels fp32 [b, k]) in pinned memory."""
         crops, desc, lab = self.generator(self.batch_size)
         desc_bytes = np.ascontiguousarray(desc).view(np.uint8).reshape(-1)
-        i = self.cursor % POOL_SIZE
+        i = self.last_slot = self.cursor % POOL_SIZE
         self.cursor += 1
+        self._wait_slot_free(i)
         slot = self.slots[i]
         if slot is None or slot[0].numel() < crops.size:
             cap = int(crops.size * 1.25) + 4096

@@ -90,14 +90,30 @@ class ParamStore:
             d[v.name] = self.view(v).detach().cpu().numpy().copy()
         return d
 
-    def load_state_dict(self, d, strict=True):
+    def load_state_dict(self, d, strict=True, require=None):
+        """Copy the variables `d` names into the store.  Returns (trainable variables found, trainable variables).
+        strict: every variable must be present.  require ('any' | 'all' | None) applies to the TRAINABLE variables of a
+        non-strict load: a checkpoint of another net / scope matches nothing and must not pass for a restore."""
+        found = 0
         for v in self.train_vars + self.other_vars:
             if v.name in d:
-                self.view(v).copy_(torch.from_numpy(np.asarray(d[v.name], F32).reshape(v.shape)))
+                a = np.asarray(d[v.name], F32)
+                if a.size != v.numel:
+                    raise ValueError('checkpoint variable %s has %d elements, the model\'s has %d'
+                                     % (v.name, a.size, v.numel))
+                self.view(v).copy_(torch.from_numpy(a.reshape(v.shape)))
+                found += 1 if v.trainable else 0
             elif strict:
                 raise KeyError('missing variable in checkpoint: ' + v.name)
+        total = len(self.train_vars)
+        if require is not None and total > 0:
+            if found == 0 or (require == 'all' and found < total):
+                missing = [v.name for v in self.train_vars if v.name not in d][:5]
+                raise ValueError('checkpoint matches %d of the model\'s %d trainable variables (e.g. missing %s; the '
+                                 'checkpoint holds %s ...)' % (found, total, missing, sorted(d)[:3]))
         for f in self.listeners:
             f()
+        return found, total
 
 
 class Executor:

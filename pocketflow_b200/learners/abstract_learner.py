@@ -126,6 +126,36 @@ class AbstractLearner(ABC):  # pylint: disable=too-many-instance-attributes
     def auto_barrier(self):
         auto_barrier_impl(self.mpi_comm)
 
+    # ------------------------------------------------------------------ checkpoints
+    def restore_model(self, path, store=None, require='all'):
+        """saver.restore(sess, tf.train.latest_checkpoint(dirname(path))) — every learner's __restore_model (e.g.
+        learners/full_precision/learner.py:193-205).  A checkpoint that does not hold the model's trainable variables
+        (wrong net, wrong scope) raises instead of 'restoring' nothing."""
+        ckpt_dir = os.path.dirname(path)
+        fn = latest_checkpoint(ckpt_dir) if os.path.isdir(ckpt_dir) else None
+        if fn is None:
+            raise ValueError('no checkpoint found in ' + ckpt_dir)
+        store = self.sess_train.store if store is None else store
+        found, total = store.load_state_dict(load_checkpoint(fn), strict=False, require=require)
+        print('model restored from %s (%d of %d trainable variables)' % (fn, found, total))
+        return fn
+
+    def restore_for_eval(self, path):
+        """The reference's evaluate() first restores the latest checkpoint into its separate evaluation graph.  Here the
+        evaluation pass runs on the training executor's own parameters: while training they ARE what was just saved
+        (nothing to do); under --exec_mode eval nothing has been trained, so the checkpoint must be loaded."""
+        if FLAGS.exec_mode == 'eval':
+            self.restore_model(path)
+
+    def eval_nb_iters(self, nb_iters=None):
+        """ceil(nb_smpls_eval / batch_size_eval) (e.g. learners/full_precision/learner.py:95).  Real data is read at
+        the step's batch size (eval_iterator), so the count follows that size; the synthetic pool keeps the
+        reference's count."""
+        if nb_iters:
+            return int(nb_iters)
+        bs = self.iterator_train.batch_size if FLAGS.data_dir_local else FLAGS.batch_size_eval
+        return int(np.ceil(float(FLAGS.nb_smpls_eval) / bs))
+
     @classmethod
     def is_primary_worker(cls, scope='global'):
         return is_primary_worker_impl(scope)
@@ -173,6 +203,7 @@ class AbstractLearner(ABC):  # pylint: disable=too-many-instance-attributes
             images, labels = iterator.next_batch()
             dev_images.copy_(images, non_blocking=True)
             dev_labels.copy_(labels, non_blocking=True)
+            iterator.copy_enqueued()
             return images.numel() * 4 + labels.numel() * 4
         st = getattr(iterator, '_staging', None)
         main = torch.cuda.current_stream()
@@ -189,6 +220,7 @@ class AbstractLearner(ABC):  # pylint: disable=too-many-instance-attributes
                 st['images'].copy_(images, non_blocking=True)
                 st['labels'].copy_(labels, non_blocking=True)
                 st['ready'].record()
+                iterator.copy_enqueued()
             return images.numel() * 4 + labels.numel() * 4
         if not st['primed']:
             stage_next()
@@ -211,6 +243,7 @@ class AbstractLearner(ABC):  # pylint: disable=too-many-instance-attributes
         dev[0][:nbytes].copy_(crops[:nbytes], non_blocking=True)
         dev[1].copy_(desc, non_blocking=True)
         dev_labels.copy_(labels, non_blocking=True)
+        iterator.copy_enqueued()
         ops.preprocess_images(dev[0], dev[1], dev_images)
         return nbytes + desc.numel() + labels.numel() * 4
 

@@ -83,10 +83,11 @@ class ChannelPrunedGpuLearner(AbstractLearner):  # pylint: disable=too-many-inst
         self.h2d_bytes = self.feed(ex, self.iterator_train)
         ex.run_step(self.lrn_rate(ex.step_count), self.grad_allreduce())
 
-    def evaluate(self, nb_iters=1):
+    def evaluate(self, nb_iters=None):
+        self.restore_for_eval(FLAGS.cpg_save_path)
         ex = self.sess_train
         out = []
-        for _ in range(nb_iters):
+        for _ in range(self.eval_nb_iters(nb_iters)):
             self.feed(ex, self.eval_iterator())
             ex.forward_eval_loss()
             out.append(ex.fetch_losses()['loss'])
@@ -118,6 +119,7 @@ class ChannelPrunedGpuLearner(AbstractLearner):  # pylint: disable=too-many-inst
         teacher = None
         if FLAGS.enbl_dst:
             teacher = Executor(self.graph_train, images, logits_dst, self.device, train=False, seed=2)
+            self.helper_dst.restore(teacher.store)
         self.sess_train = Executor(self.graph_train, images, logits, self.device, train=True, loss=loss, labels=labels,
                                    optimizer=dict(kind='momentum', momentum=FLAGS.momentum),
                                    maskable=self.maskable_vars, teacher=teacher, seed=1, grad_scale=1.0 / world)

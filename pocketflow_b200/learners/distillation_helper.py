@@ -23,6 +23,9 @@ class DistillationHelper(object):
         fn = latest_checkpoint(ckpt_dir) if os.path.isdir(ckpt_dir) else None
         if fn is not None:
             self.ckpt = load_checkpoint(fn)
+        elif FLAGS.data_dir_local:
+            # real data and no teacher checkpoint: distilling from a random teacher is never what was asked for
+            raise ValueError('--enbl_dst with real data needs a pre-trained teacher checkpoint in ' + ckpt_dir)
         # The reference downloads a pre-trained checkpoint here; on the synthetic benchmark path the
         # teacher keeps its own random initialisation (seed 2) — distribution, not accuracy, matters.
 
@@ -39,7 +42,9 @@ class DistillationHelper(object):
         if self.ckpt is None:
             return False
         renamed = {self.model_scope + '/' + '/'.join(k.split('/')[1:]): v for k, v in self.ckpt.items()}
-        store.load_state_dict(renamed, strict=False)
+        found, total = store.load_state_dict(renamed, strict=False, require='all')
+        print('distillation teacher restored from %s (%d of %d trainable variables)'
+              % (os.path.dirname(FLAGS.save_path_dst), found, total))
         return True
 
     @classmethod

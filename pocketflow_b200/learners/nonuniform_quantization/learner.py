@@ -4,16 +4,19 @@ are in place (learner.py:127-129), frozen; weights trained with Adam through the
 from timeit import default_timer as timer
 
 import numpy as np
+import torch
 
 from ... import graph as G
 from ...engine import Executor
 from ...flags import FLAGS, DEFINE_integer, DEFINE_boolean, DEFINE_string
 from ...utils.multi_gpu_wrapper import MultiGpuWrapper as mgw
 from ...utils.lrn_rate_utils import piecewise_constant
-from ..abstract_learner import AbstractLearner, save_checkpoint
+from ..abstract_learner import AbstractLearner, load_checkpoint, save_checkpoint
 from ..distillation_helper import DistillationHelper
 from .utils import NonUniformQuantization
 from .bit_optimizer import BitOptimizer
+
+CLUSTERS_KEY = 'nuql/clusters:0'          # [layers, 256] codebooks in a quantized-model checkpoint
 
 DEFINE_string('nuql_opt_mode', 'weights', 'the variables to optimize: [clusters, weights, both]')
 DEFINE_string('nuql_init_style', 'quantile', 'the initialization of quantization points: [quantile, uniform]')
@@ -69,6 +72,10 @@ class NonUniformQuantLearner(AbstractLearner):
     def train(self, nb_iters=None):
         total = self.finetune_steps if nb_iters is None else nb_iters
         ex = self.sess_train
+        if FLAGS.enbl_warm_start:
+            # use the latest model for warm start, THEN fit the codebooks to it (learner.py:124-129)
+            self.restore_model(FLAGS.save_path)
+            self.cluster_init()
         if FLAGS.enbl_multi_gpu:
             mgw.broadcast_global_variables([ex.store.P, ex.store.O])
         time_prev = timer()
@@ -92,20 +99,32 @@ class NonUniformQuantLearner(AbstractLearner):
         if not self.is_primary_worker():
             return
         ex = self.sess_train
-        print('quantized model saved to ' + save_checkpoint(FLAGS.nuql_save_quant_model_path,
-                                                            ex.store.state_dict(), ex.step_count))
+        state = ex.store.state_dict()
+        # the codebooks are variables of the reference's quantized graph (utils.py:297-347) and travel with its
+        # checkpoints; here they live in the quantizer, so they are written beside the model's variables
+        state[CLUSTERS_KEY] = ex.wq.clusters.detach().cpu().numpy().copy()
+        print('quantized model saved to ' + save_checkpoint(FLAGS.nuql_save_quant_model_path, state, ex.step_count))
+
+    def restore_for_eval(self, path):
+        if FLAGS.exec_mode != 'eval':
+            return
+        ckpt = load_checkpoint(self.restore_model(path))
+        if CLUSTERS_KEY not in ckpt or ckpt[CLUSTERS_KEY].shape != tuple(self.sess_train.wq.clusters.shape):
+            raise ValueError('checkpoint holds no codebooks for this model (%s)' % CLUSTERS_KEY)
+        self.sess_train.wq.clusters.copy_(torch.from_numpy(np.asarray(ckpt[CLUSTERS_KEY], np.float32)))
 
     def train_step(self):
         ex = self.sess_train
         self.h2d_bytes = self.feed(ex, self.iterator_train)
         ex.run_step(self.lrn_rate(ex.step_count), self.grad_allreduce())
 
-    def evaluate(self, nb_iters=1):
+    def evaluate(self, nb_iters=None):
         if not self.is_primary_worker():
             return None
+        self.restore_for_eval(FLAGS.nuql_save_quant_model_path)
         ex = self.sess_train
         out = []
-        for _ in range(nb_iters):
+        for _ in range(self.eval_nb_iters(nb_iters)):
             self.feed(ex, self.eval_iterator())
             ex.forward_eval_loss()
             out.append(ex.fetch_losses()['loss'])

@@ -113,10 +113,10 @@ class UniformQuantLearner(AbstractLearner):
     def evaluate(self, nb_iters=None):
         if not self.is_primary_worker():
             return None
+        self.restore_for_eval(FLAGS.uql_save_quant_model_path)
         ex = self.sess_train
-        nb_iters = nb_iters or int(np.ceil(float(FLAGS.nb_smpls_eval) / self.__eval_batch_size()))
         losses, accuracies = [], []
-        for _ in range(nb_iters):
+        for _ in range(self.eval_nb_iters(nb_iters)):
             self.feed(ex, self.eval_iterator())
             ex.forward_eval_loss()
             r = ex.fetch_losses()
@@ -246,12 +246,7 @@ class UniformQuantLearner(AbstractLearner):
         print('quantized model saved to ' + fn)
 
     def __restore_model(self, is_train):
-        path = FLAGS.save_path if is_train else FLAGS.uql_save_quant_model_path
-        fn = latest_checkpoint(os.path.dirname(path))
-        if fn is None:
-            raise ValueError('no checkpoint found in ' + os.path.dirname(path))
-        self.sess_train.store.load_state_dict(load_checkpoint(fn), strict=False)
-        print('model restored from ' + fn)
+        self.restore_model(FLAGS.save_path if is_train else FLAGS.uql_save_quant_model_path)
 
     def __monitor_progress(self, r, time_prev, idx_iter):
         if not self.is_primary_worker():

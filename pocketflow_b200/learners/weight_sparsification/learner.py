@@ -70,10 +70,13 @@ class WeightSparseLearner(AbstractLearner):  # pylint: disable=too-many-instance
                     elif not last_mask_applied:
                         last_mask_applied = True
                         self.prune()
+            # save & evaluate the model at certain steps (learner.py:131-134)
             if self.is_primary_worker('global') and (idx_iter + 1) % FLAGS.save_step == 0:
                 self.__save_model()
+                self.evaluate()
         if self.is_primary_worker('global'):
             self.__save_model()
+            self.evaluate()
 
     def train_step(self):
         ex = self.sess_train
@@ -90,10 +93,11 @@ class WeightSparseLearner(AbstractLearner):  # pylint: disable=too-many-instance
         ex.reset_optimizer_slots()
         return ratios
 
-    def evaluate(self, nb_iters=1):
+    def evaluate(self, nb_iters=None):
+        self.restore_for_eval(FLAGS.ws_save_path)
         ex = self.sess_train
         losses = []
-        for _ in range(nb_iters):
+        for _ in range(self.eval_nb_iters(nb_iters)):
             self.feed(ex, self.eval_iterator())
             ex.forward_eval_loss()
             losses.append(ex.fetch_losses()['loss'])
@@ -176,8 +180,8 @@ class WeightSparseLearner(AbstractLearner):  # pylint: disable=too-many-instance
             self.var_names_n_prune_ratios = PROptimizer(self.maskable_vars, self.dataset_name, tuner=self).run()
             if FLAGS.ws_prune_ratio_prtl == 'optimal':
                 self.pr_reset()
-        for var, (name, _) in zip(self.maskable_vars, self.var_names_n_prune_ratios):
-            assert var.name == name, 'unmatched variable names: %s vs. %s' % (var.name, name)
+            for var, (name, _) in zip(self.maskable_vars, self.var_names_n_prune_ratios):
+                assert var.name == name, 'unmatched variable names: %s vs. %s' % (var.name, name)
 
     def __calc_prune_ratio_dyn(self, prune_ratio_fnl, global_step):
         """float32 graph arithmetic of learner.py:296-312, evaluated on the host."""

@@ -182,3 +182,45 @@ def test_mobilenet_channel_pruned_gpu_learner_step(monkeypatch):
         assert rel(got[k], ref[k]) <= 1e-5, (k, got[k], ref[k])
     for v in lrn.maskable_vars[1:-1]:
         assert np.all(ex.store.view(v).cpu().numpy()[masks[v.name] == 0] == 0)
+
+
+@pytest.mark.parametrize('learner,path_flag,extra', [
+    ('full-prec', 'save_path', {}),
+    ('weight-sparse', 'ws_save_path', dict(ws_prune_ratio=0.5, ws_prune_ratio_prtl='uniform', ws_mask_update_step=2)),
+    ('uniform', 'uql_save_quant_model_path', dict(uql_weight_bits=8, uql_use_buckets=True)),
+    ('non-uniform', 'nuql_save_quant_model_path', dict(nuql_weight_bits=4)),
+])
+def test_exec_mode_eval_restores_the_saved_model(tmp_path, learner, path_flag, extra):
+    """--exec_mode eval (nets/*_run.py:62-64): evaluate() restores the latest checkpoint first — a freshly built learner
+    must score the TRAINED model, not its seed initialisation.  Both passes average the same 8 pooled batches."""
+    from pocketflow_b200.datasets.abstract_dataset import POOL_SIZE
+    flags = dict(extra, summ_step=10 ** 9, save_step=10 ** 9)
+    flags[path_flag] = str(tmp_path / 'ckpt' / 'model.ckpt')
+    lrn = make(learner, **flags)
+    lrn.nb_iters_train = 6
+    lrn.train(nb_iters=6)                                               # ends with save + evaluate
+    first = lambda r: float(r[0] if isinstance(r, tuple) else r)
+    trained = first(lrn.evaluate(nb_iters=POOL_SIZE))
+    del lrn
+    flags['exec_mode'] = 'eval'
+    fresh = make(learner, **flags)
+    restored = first(fresh.evaluate(nb_iters=POOL_SIZE))
+    assert rel(restored, trained) <= 1e-6, (restored, trained)
+    # and the default iteration count is the reference's ceil(nb_smpls_eval / batch_size_eval)
+    assert fresh.eval_nb_iters() == int(np.ceil(FLAGS.nb_smpls_eval / FLAGS.batch_size_eval))
+
+
+def test_exec_mode_eval_without_a_checkpoint_raises(tmp_path):
+    flags = dict(exec_mode='eval', save_path=str(tmp_path / 'none' / 'model.ckpt'))
+    lrn = make('full-prec', **flags)
+    with pytest.raises(ValueError):
+        lrn.evaluate()
+
+
+def test_restore_refuses_a_checkpoint_of_another_scope(tmp_path):
+    from pocketflow_b200.learners.abstract_learner import save_checkpoint
+    lrn = make('full-prec', save_path=str(tmp_path / 'm' / 'model.ckpt'))
+    state = {('other/' + k): v for k, v in lrn.sess_train.store.state_dict().items()}
+    save_checkpoint(FLAGS.save_path, state, 1)
+    with pytest.raises(ValueError):
+        lrn.restore_model(FLAGS.save_path)

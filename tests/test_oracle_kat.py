@@ -700,8 +700,9 @@ def test_ws_training_loop_prunes_and_saves_when_the_reference_loop_does():
         FLAGS.reset()
         FLAGS.ws_mask_update_step, FLAGS.ws_iter_ratio_beg = g['ws_mask_update_step'], g['ws_iter_ratio_beg']
         FLAGS.ws_iter_ratio_end, FLAGS.save_step, FLAGS.summ_step = g['ws_iter_ratio_end'], g['save_step'], g['summ_step']
-        ev = dict(train=0, prune=[], save=[], monitor=[])
+        ev = dict(train=0, prune=[], save=[], monitor=[], evaluate=0)
         me = SimpleNamespace(sess_train=SimpleNamespace(store=SimpleNamespace(P=None, O=None)), nb_iters_train=g['nb_iters_train'],
+                             evaluate=lambda: ev.__setitem__('evaluate', ev['evaluate'] + 1),
                              is_primary_worker=lambda scope='global': True)
         me.train_step = lambda: ev.__setitem__('train', ev['train'] + 1)
         me.prune = lambda: ev['prune'].append(ev['train'])
@@ -711,6 +712,7 @@ def test_ws_training_loop_prunes_and_saves_when_the_reference_loop_does():
         want = g['events']
         assert ev['train'] == want['train'] and ev['prune'] == want['prune'], g
         assert ev['save'] == want['save'] and ev['monitor'] == want['monitor'], g
+        assert ev['evaluate'] == want['evaluate'], g                     # evaluated after every save (learner.py:131-140)
     FLAGS.reset()
 
 
