@@ -149,7 +149,13 @@ def peaks():
 def build_learner(workload, world, batch_override=None):
     mod = setup_flags(workload, batch_override, world)
     from pocketflow_b200.learners.learner_utils import create_learner
-    return create_learner(None, mod.ModelHelper())
+    lrn = create_learner(None, mod.ModelHelper())
+    if hasattr(lrn, 'choose_channels'):
+        # config 4 times the steady-state masked step: a SHORT run of the layer-wise channel selection (2 proximal +
+        # 2 fine-tune iterations per layer instead of cpg_nb_iters_layer = 1000) yields the 50 % input-channel masks
+        lrn.init_from_full()
+        lrn.choose_channels(nb_iters_layer=2)
+    return lrn
 
 
 # ------------------------------------------------------------------------------ CPU reference arm

@@ -477,6 +477,27 @@ int pf_global_avgpool_bwd(const float* dy_dev, int n, int hw, int c, int accumul
 int pf_softmax_fwd(const float* x_dev, int n, int k, float* y_dev, void* stream);
 int pf_softmax_bwd(const float* dy_dev, const float* y_dev, int n, int k, float* dx_dev, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * f4  Layer-wise channel selection of the channel-pruning learner (pf_cpg.cu).
+ *     Replaces, per proximal-gradient iteration of ChannelPrunedGpuLearner.__choose_channels
+ *     (learners/channel_pruning_gpu/learner.py:445-518), the TF ops of __build_extra_losses (:339-354) and
+ *     __build_layer_ops (:356-402); kernels W are [R,S,Cin,Cout] row-major, rs = R*S:
+ *   pf_cpg_diff_l2     diff = a - b ; loss[0] = sum(diff^2)/2    (tf.nn.l2_loss of the two conv outputs, :352;
+ *                      with a = pruned, b = full, diff is also d loss / d a).  partial_ws: PF_L2_PARTIALS floats.
+ *   pf_cpg_group_norms norms[c] = sqrt(sum_{rs,k} (w - lr*g)^2)  (:378-379; g NULL: the norm of w itself, :256)
+ *   pf_cpg_prox_apply  w = (w - lr*g) * max(1 - thr[0] / norms[c], 0)   (:378-382; thr = the percentile of norms)
+ *   pf_cpg_channel_mask mask[rs,c,k] = norms[c] > 0               (:256-259)
+ *   pf_mul             out = a * b                                 (masked gradient g * mask, :438)
+ * ------------------------------------------------------------------------------------------- */
+int pf_cpg_diff_l2(const float* a_dev, const float* b_dev, int64_t n, float* diff_dev, float* loss_dev,
+                   float* partial_ws_dev, void* stream);
+int pf_cpg_group_norms(const float* w_dev, const float* g_dev, float lr, int rs, int cin, int cout,
+                       float* norms_dev, void* stream);
+int pf_cpg_prox_apply(float* w_dev, const float* g_dev, float lr, const float* norms_dev, const float* thr_dev,
+                      int rs, int cin, int cout, void* stream);
+int pf_cpg_channel_mask(const float* norms_dev, int rs, int cin, int cout, float* mask_dev, void* stream);
+int pf_mul(const float* a_dev, const float* b_dev, int64_t n, float* out_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -151,6 +151,52 @@ def percentile_nearest(x, q, axis=None):
 
 
 # ----------------------------------------------------------------------------
+# channel pruning, GPU variant  (learners/channel_pruning_gpu/learner.py:250-260, 356-402, 445-518)
+# ----------------------------------------------------------------------------
+def cpg_group_norms(w):
+    """var_norm = sqrt(reduce_sum(square(var), axis=[0, 1, 3], keepdims=True)) (learner.py:255, :379) of a kernel
+    [R,S,Cin,Cout] — one norm per INPUT channel, float32.  The order of TF's reduction is not specified: this is numpy's
+    float32 sum (what the golden generator's stub evaluates the reference's op with); device results are compared with a
+    tolerance, the SET of zeroed channels exactly."""
+    w = np.asarray(w, F32)
+    return np.sqrt(np.sum(w * w, axis=(0, 1, 3), dtype=F32)).astype(F32)
+
+
+def cpg_prox_step(w, g, lrn_rate_pgd, prune_perctl):
+    """ops['prune'] of one layer (learner.py:375-383):
+        var_new = var - lr * grad ; var_norm = ||var_new||_{[0,1,3]} ; threshold = percentile(var_norm, prune_perctl)
+        shrk_vec = maximum(1 - threshold / var_norm, 0) ; var <- var_new * shrk_vec
+    Returns (var, var_norm, threshold).  (0/0 gives NaN in TF's shrk_vec; this restatement returns 0 there.)"""
+    w, g = np.asarray(w, F32), np.asarray(g, F32)
+    var_new = (w - F32(lrn_rate_pgd) * g).astype(F32)
+    var_norm = cpg_group_norms(var_new)
+    threshold = F32(percentile_nearest(var_norm, F32(prune_perctl)))     # fed through a float32 placeholder (:365)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        shrk = np.maximum(F32(1.0) - threshold / var_norm, F32(0.0)).astype(F32)
+    shrk = np.where(np.isnan(shrk), F32(0.0), shrk).astype(F32)
+    return (var_new * shrk[None, None, :, None]).astype(F32), var_norm, threshold
+
+
+def cpg_channel_mask(w):
+    """mask_updt_ops (learner.py:255-259): tile(cast(var_norm > 0, float32)) over the kernel's shape."""
+    w = np.asarray(w, F32)
+    keep = (cpg_group_norms(w) > 0).astype(F32)
+    return np.broadcast_to(keep[None, None, :, None], w.shape).astype(F32).copy()
+
+
+def cpg_selection_schedule(reg_losses, prune_ratio, nb_iters_layer, lr_init=1e-10, incr=1.4, decr=0.7):
+    """The host loop of __choose_channels (learner.py:476-497) for one layer, given the regression losses it observed:
+    [(lrn_rate_pgd, prune_perctl)] fed at every iteration.  lr grows when the loss fell (loss < loss_prev, loss_prev
+    starting at 0.0), shrinks otherwise; the percentile ramps linearly to prune_ratio * 100."""
+    out, lr, prev = [], lr_init, 0.0
+    for it in range(nb_iters_layer):
+        out.append((lr, prune_ratio * 100.0 * (it + 1) / nb_iters_layer))
+        lr = lr * incr if reg_losses[it] < prev else lr * decr
+        prev = reg_losses[it]
+    return out
+
+
+# ----------------------------------------------------------------------------
 # weight sparsification  (learners/weight_sparsification/learner.py:260-332)
 # ----------------------------------------------------------------------------
 def ws_prune_ratio_dyn(global_step, nb_iters_train, prune_ratio_fnl,

@@ -121,8 +121,14 @@ class Executor:
 
     def __init__(self, graph, images, logits, device, store=None, train=True, loss=None, labels=None,
                  optimizer=None, weight_quant=None, act_quant=None, maskable=None, teacher=None,
-                 seed=1, exact_ste=True, grad_scale=1.0, scope=None, conv_path=None):
+                 seed=1, exact_ste=True, grad_scale=1.0, scope=None, conv_path=None, fuse_add=True,
+                 update_moving_stats=True):
         self.g, self.device, self.train = graph, device, train
+        # fuse_add=False: every Conv2D output is materialised on its own (the channel-pruning learner regresses conv
+        # outputs of a pruned model onto those of the full model, learners/channel_pruning_gpu/learner.py:339-354);
+        # update_moving_stats=False: training-mode BN without the moving-average update ops (the FULL model of that
+        # learner runs forward_train but only the pruned model's update ops are ever executed, :283-286)
+        self.fuse_add, self.update_moving_stats = bool(fuse_add), bool(update_moving_stats)
         self.images, self.logits_t, self.labels_t = images, logits, labels
         self.loss, self.teacher = loss, teacher
         self.optimizer = optimizer or {}
@@ -348,7 +354,7 @@ class Executor:
         self.fused_add = {}        # conv op -> (add op, other input tensor)
         self.add_fused = set()
         for op in self.ops:
-            if op.type != 'Add':
+            if op.type != 'Add' or not self.fuse_add:
                 continue
             for i, x_t in enumerate(op.inputs):
                 src, other = x_t.op, op.inputs[1 - i]
@@ -680,7 +686,8 @@ class Executor:
         return self.store.view(v)
 
     # ------------------------------------------------------------------ forward
-    def forward(self, training=None):
+    def forward(self, training=None, upto=None):
+        """upto: stop after this op has run (its output buffer is the result wanted)."""
         st = self.store
         training = self.train if training is None else training
         if self.aq_ops:
@@ -694,7 +701,11 @@ class Executor:
         if self.tc_batch is not None:
             with self.timed('conv_prep'):
                 self.tc_batch.prepare(levels=self._lv_on)
+        prev = None
         for op in self.ops:
+            if prev is not None and prev is upto:
+                return None
+            prev = op
             ty = op.type
             if ty in ('Placeholder', 'Reshape', 'Identity'):
                 continue
@@ -763,10 +774,11 @@ class Executor:
                 # with an activation quantizer the BN pass writes fp32 (+ range) and the quantizer writes the planes
                 pl_bn = pl if slot is None else None
                 y_bn = y if (need_f32 or slot is not None) else None
+                bn_mom = op.attrs['momentum'] if self.update_moving_stats else 1.0
                 if op.attrs['training'] and training and slot is not None:
                     # the statistics pass also yields the range of act(bn(x)); one fused BN + fake-quant pass
                     with self.timed('bn_stats'):
-                        ops.bn_train_stats_range(x, m, c, op.attrs['epsilon'], op.attrs['momentum'], b['mean'], b['var'],
+                        ops.bn_train_stats_range(x, m, c, op.attrs['epsilon'], bn_mom, b['mean'], b['var'],
                                                  b['rstd'], mm, mv, gamma, beta, act, slot, self.bn_ws)
                     with self.timed('bn_apply'):
                         bits = self.act_quant['bits'][self.aq_index[relu_op]]
@@ -780,7 +792,7 @@ class Executor:
                     slot = None                                    # quantized already
                 elif op.attrs['training'] and training:
                     with self.timed('bn_stats'):
-                        ops.bn_train_stats(x, m, c, op.attrs['epsilon'], op.attrs['momentum'], b['mean'], b['var'],
+                        ops.bn_train_stats(x, m, c, op.attrs['epsilon'], bn_mom, b['mean'], b['var'],
                                            b['rstd'], mm, mv, self.bn_ws)
                     with self.timed('bn_apply'):
                         ops.bn_apply(x, m, c, b['mean'], b['rstd'], gamma, beta, act, y_bn, slot, pl_bn)
@@ -967,6 +979,45 @@ class Executor:
                 self.wg_reduce.reduce()
         if self._ste_grads is not None:
             self.wq.ste_backward_(self._ste_grads)
+
+    def layer_wgrad(self, op, gy, dw):
+        """dW of ONE Conv2D / MatMul for an externally supplied gradient `gy` of its output, after a training-mode
+        forward() of this executor: the weight gradient of the layer-wise regression loss of the channel-pruning
+        learner (learners/channel_pruning_gpu/learner.py:370, :391 — compute_gradients(reg_loss_i, [kernel_i])).
+        Same kernels as the step's own backward; `dw` is an fp32 tensor of the kernel's shape."""
+        d, x_t = self.desc[op], op.inputs[0]
+        # own dy planes: the step's dy_scratch is only sized for the layers whose gradient is split in a separate pass
+        lw = getattr(self, '_lw_planes', None)
+        if lw is None or lw.numel < op.output.numel:
+            lw = self._lw_planes = ops.Planes(op.output.numel, self.device)
+        with self.timed('conv_wgrad'):
+            if op in self.im2col:
+                im = self.im2col[op]
+                if im['planes']:
+                    gp = ops.Planes(op.output.numel, self.device, lw.buf)
+                    ops.split_bf16(gy, gp)
+                    ops.conv2d_tc_wgrad_planes(im['d1'], im['cols'], gp, self.wgrad_ws, im['dwpad'])
+                elif ops.conv2d_tc_wgrad_supported(im['d1']):
+                    ops.conv2d_tc_wgrad(im['d1'], im['cols'], gy, self.wgrad_ws, im['dwpad'])
+                else:
+                    ops.conv2d_wgrad(im['d1'], im['cols'], gy, self.wgrad_ws, im['dwpad'])
+                if im['mode'] == 's2d':
+                    ops.gather_rows(im['dwpad'], im['bwd_map'], dw, dw.shape[-1])
+                else:
+                    ops.add(im['dwpad'][:dw.numel()], None, dw.reshape(-1))
+            elif op in self.tc_wgrad:
+                xp = self.planes_of(x_t)
+                if xp is None:
+                    xp = ops.Planes(x_t.numel, self.device, self.x_scratch.buf)
+                    ops.split_bf16(self.T(x_t), xp)
+                gp = ops.Planes(op.output.numel, self.device, lw.buf)
+                ops.split_bf16(gy, gp)
+                if self._lv_on and self._act_lv_of(x_t) is not None:
+                    ops.conv2d_tc_wgrad_ex(d, self._tc_act(x_t), ops.tc_act(gp), self.wgrad_ws, dw)
+                else:
+                    ops.conv2d_tc_wgrad_planes(d, xp, gp, self.wgrad_ws, dw)
+            else:
+                ops.conv2d_wgrad(d, self.T(x_t), gy, self.wgrad_ws, dw)
 
     def forward_eval_loss(self):
         """Evaluation pass: BN in inference mode, quantizers active, losses/metrics only."""

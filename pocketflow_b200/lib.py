@@ -93,6 +93,11 @@ SIGNATURES = {
     'pf_global_avgpool_bwd': (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     'pf_softmax_fwd': (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp]),
     'pf_softmax_bwd': (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
+    'pf_cpg_diff_l2': (c_i32, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    'pf_cpg_group_norms': (c_i32, [c_vp, c_vp, c_f32, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    'pf_cpg_prox_apply': (c_i32, [c_vp, c_vp, c_f32, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
+    'pf_cpg_channel_mask': (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    'pf_mul': (c_i32, [c_vp, c_vp, c_i64, c_vp, c_vp]),
 }
 
 

@@ -834,3 +834,62 @@ def preprocess_images(crops_u8, desc, out, mean=(123.68, 116.78, 103.94)):
                                       float(mean[2]), _p(out), _stream()), 'pf_preprocess_images')
     return out
 
+
+
+# ----------------------------------------------------------------------------- f4 channel selection (pf_cpg.cu)
+def cpg_diff_l2(a, b, diff, loss, partial_ws):
+    """diff = a - b, loss[0] = sum(diff^2) / 2 — tf.nn.l2_loss of two conv outputs
+    (learners/channel_pruning_gpu/learner.py:352); partial_ws: L2_PARTIALS floats."""
+    _check_f32(a, b, diff, loss, partial_ws)
+    if a.numel() != b.numel() or a.numel() != diff.numel():
+        raise ValueError('cpg_diff_l2: size mismatch')
+    _lib.check(_lib.load().pf_cpg_diff_l2(_p(a), _p(b), a.numel(), _p(diff), _p(loss), _p(partial_ws), _stream()),
+               'pf_cpg_diff_l2')
+
+
+def _rs_cin_cout(w):
+    if w.dim() == 4:
+        return w.shape[0] * w.shape[1], w.shape[2], w.shape[3]
+    if w.dim() == 2:
+        return 1, w.shape[0], w.shape[1]
+    raise ValueError('kernel must be [R,S,Cin,Cout] or [Cin,Cout]')
+
+
+def cpg_group_norms(w, g, lr, norms):
+    """norms[c] = sqrt(sum_{r,s,k} (w - lr*g)^2) (learner.py:378-379); g None: norm of w itself (:256)."""
+    _check_f32(w, g, norms)
+    rs, cin, cout = _rs_cin_cout(w)
+    _lib.check(_lib.load().pf_cpg_group_norms(_p(w), _p(g), float(lr), rs, cin, cout, _p(norms), _stream()),
+               'pf_cpg_group_norms')
+
+
+def cpg_prox_step(w, g, lr, prune_perctl, norms=None):
+    """One proximal (group soft-threshold) step of the channel selection, in place on w (learner.py:375-383):
+    w' = w - lr g ; n_c = ||w'[:, :, c, :]|| ; t = percentile(n, prune_perctl) ('nearest') ; w = w' max(1 - t/n_c, 0).
+    Returns the threshold (device tensor [1])."""
+    rs, cin, cout = _rs_cin_cout(w)
+    if norms is None:
+        norms = torch.empty(cin, dtype=torch.float32, device=w.device)
+    lr = float(np.float32(lr))
+    cpg_group_norms(w, g, lr, norms)
+    # the percentile is fed through a float32 placeholder (learner.py:365) and widened to double by percentile()
+    thr = select_desc([norms], [(0, percentile_rank_desc(cin, np.float32(prune_perctl)))])
+    _lib.check(_lib.load().pf_cpg_prox_apply(_p(w), _p(g), float(lr), _p(norms), _p(thr), rs, cin, cout, _stream()),
+               'pf_cpg_prox_apply')
+    return thr
+
+
+def cpg_channel_mask(w, mask, norms=None):
+    """mask = tile(||w[:, :, c, :]|| > 0) (learner.py:256-259)."""
+    _check_f32(w, mask)
+    rs, cin, cout = _rs_cin_cout(w)
+    if norms is None:
+        norms = torch.empty(cin, dtype=torch.float32, device=w.device)
+    cpg_group_norms(w, None, 0.0, norms)
+    _lib.check(_lib.load().pf_cpg_channel_mask(_p(norms), rs, cin, cout, _p(mask), _stream()), 'pf_cpg_channel_mask')
+    return norms
+
+
+def mul(a, b, out):
+    _check_f32(a, b, out)
+    _lib.check(_lib.load().pf_mul(_p(a), _p(b), a.numel(), _p(out), _stream()), 'pf_mul')

@@ -154,14 +154,19 @@ def make_mobilenet(learner, **flags):
     return create_learner(None, M.ModelHelper())
 
 
-def test_mobilenet_channel_pruned_gpu_learner_step(monkeypatch):
-    """Config 4 steady state: MobileNet-v1, input-channel masks on the 13 interior pointwise kernels,
-    masked Momentum step; loss vs the oracle step with the same masks; pruned channels stay zero."""
-    monkeypatch.setenv('PF_CONV_PATH', 'fp32')
+@pytest.mark.parametrize('conv_path', ['fp32', 'tc'])
+def test_mobilenet_channel_pruned_gpu_learner_step(monkeypatch, conv_path):
+    """Config 4 steady state: MobileNet-v1, input-channel masks on the 13 interior pointwise kernels (chosen by a short
+    run of the selection phase), masked Momentum step; loss vs the oracle step with the same masks; pruned channels
+    stay zero.  Both the exact-fp32 and the (default) tensor-core conv path."""
+    monkeypatch.setenv('PF_CONV_PATH', conv_path)
     lrn = make_mobilenet('chn-pruned-gpu', cpg_prune_ratio=0.5)
     ex = lrn.sess_train
     assert len(lrn.maskable_vars) == 15 and sum(v.numel for v in lrn.maskable_vars) == 4165472
+    assert all(v.name.startswith('pruned_model/') for v in lrn.maskable_vars)
     assert lrn.prune_ratios[0] == 0.0 and lrn.prune_ratios[-1] == 0.0 and lrn.prune_ratios[5] == 0.5
+    lrn.init_from_full()
+    lrn.choose_channels(nb_iters_layer=2)
     masks = {v.name: ex.store.view(v, ex.MASK).cpu().numpy().copy() for v in lrn.maskable_vars}
     for v in lrn.maskable_vars[1:-1]:
         m = masks[v.name]
@@ -182,6 +187,87 @@ def test_mobilenet_channel_pruned_gpu_learner_step(monkeypatch):
         assert rel(got[k], ref[k]) <= 1e-5, (k, got[k], ref[k])
     for v in lrn.maskable_vars[1:-1]:
         assert np.all(ex.store.view(v).cpu().numpy()[masks[v.name] == 0] == 0)
+
+
+@pytest.mark.parametrize('conv_path', ['fp32', 'tc'])
+def test_channel_selection_phase_matches_the_oracle(monkeypatch, tmp_path, conv_path):
+    """SURVEY §8 f4 — the layer-wise channel selection (learners/channel_pruning_gpu/learner.py:445-518) of ONE MobileNet
+    layer, iteration by iteration against the oracle's restatement driven on the same mini-batches: regression loss
+    and its weight gradient, the proximal step (threshold, surviving channels), the lr / percentile schedule, the
+    mask, the masked-Adam layer fine-tuning, the pruned model's BN moving statistics."""
+    from oracle.step_oracle import cpg_layer_regression
+    monkeypatch.setenv('PF_CONV_PATH', conv_path)
+    layers, nb_iters = (3, 4), 3
+    ratios = ['0'] * 15
+    for idx in layers:
+        ratios[idx] = '0.5'
+    (tmp_path / 'ratios.txt').write_text(','.join(ratios) + '\n')
+    lrn = make_mobilenet('chn-pruned-gpu', cpg_prune_ratio_type='list', cpg_prune_ratio_file=str(tmp_path / 'ratios.txt'),
+                         cpg_lrn_rate_pgd_init=1e-7)
+    ex = lrn.sess_train
+    lrn.init_from_full()
+    g = lrn.graph_train
+    ops_full = [op for op in g.ops if op.name.startswith('model/')]
+    ops_prnd = [op for op in g.ops if op.name.startswith('pruned_model/')]
+    orc_f = StepOracle(ops_full, lrn.logits_full, lrn.images)
+    orc_p = StepOracle(ops_prnd, ex.logits_t, lrn.images)
+    st_f, st_p = lrn.store_full.state_dict(), ex.store.state_dict()
+    pool = lrn.iterator_train
+    pool.prefill()
+    # ---- the oracle's run of the same loop (layer 3 first: layer 4 then sees a pruned input, as in a real run)
+    ref_log, mask_ref, batch = [], {}, 0
+    for idx in layers:
+        conv_f, conv_p = lrn.conv_ops_full[idx], lrn.conv_ops_prnd[idx]
+        kname = conv_p.vars['kernel'].name
+        lr, prev = 1e-7, 0.0
+        for it in range(nb_iters):
+            images = pool.pool[batch % len(pool.pool)][0].numpy()
+            batch += 1
+            loss, grad, stats = cpg_layer_regression(orc_f, orc_p, st_f, st_p, images, conv_f, conv_p)
+            perctl = 0.5 * 100.0 * (it + 1) / nb_iters
+            st_p[kname], norms, thr = O.cpg_prox_step(st_p[kname], grad, lr, perctl)
+            st_p.update(stats)
+            ref_log.append(('prune', loss, lr, perctl, thr))
+            lr = lr * 1.4 if loss < prev else lr * 0.7
+            prev = loss
+        mask_ref[kname] = O.cpg_channel_mask(st_p[kname])
+        m_, v_, b1p, b2p = np.zeros_like(st_p[kname]), np.zeros_like(st_p[kname]), F32(0.9), F32(0.999)
+        for it in range(nb_iters):
+            images = pool.pool[batch % len(pool.pool)][0].numpy()
+            batch += 1
+            loss, grad, stats = cpg_layer_regression(orc_f, orc_p, st_f, st_p, images, conv_f, conv_p)
+            st_p[kname], m_, v_ = O.adam_step(st_p[kname], m_, v_, grad * mask_ref[kname], 1e-2, b1p, b2p)
+            st_p.update(stats)
+            b1p, b2p = F32(b1p * F32(0.9)), F32(b2p * F32(0.999))
+            ref_log.append(('finetune', loss))
+    # ---- the learner's
+    lrn.choose_channels(nb_iters_layer=nb_iters)
+    got_log = lrn.selection_log
+    assert len(got_log) == len(ref_log) == 2 * nb_iters * len(layers)
+    bar = 1e-5 if conv_path == 'fp32' else 2e-5
+    scale = max(r[1] for r in ref_log)
+    assert scale > 0
+    for gl, rl in zip(got_log, ref_log):
+        assert gl[0] == rl[0]
+        assert abs(gl[3] - rl[1]) <= (bar if gl[0] == 'prune' else 10 * bar) * abs(rl[1]) + 1e-9 * scale, (gl, rl)
+        if gl[0] == 'prune':
+            assert rel(gl[4], rl[2]) <= 1e-12 and rel(gl[5], rl[3]) <= 1e-12           # lr / percentile schedule
+    new = ex.store.state_dict()
+    for idx in layers:
+        var = lrn.conv_ops_prnd[idx].vars['kernel']
+        w, mask = ex.store.view(var).cpu().numpy(), ex.store.view(var, ex.MASK).cpu().numpy()
+        assert np.array_equal(mask, mask_ref[var.name])                                # the SAME channels survive
+        assert abs(mask.reshape(-1, mask.shape[2], mask.shape[3]).max(axis=(0, 2)).mean() - 0.5) < 0.02
+        assert np.all(w[mask == 0] == 0)
+        assert np.abs(w - st_p[var.name]).max() <= 2e-3 * np.abs(st_p[var.name]).max()  # after 3 Adam steps at lr 1e-2
+    for k, v in st_p.items():
+        if 'moving_' in k:
+            assert np.abs(new[k] - v).max() <= 1e-5 * max(np.abs(v).max(), 1e-3), k
+    # the other layers are untouched and unmasked
+    for j, v in enumerate(lrn.maskable_vars):
+        if j not in layers:
+            assert float(ex.store.view(v, ex.MASK).min()) == 1.0
+            assert np.array_equal(new[v.name], st_p[v.name])
 
 
 @pytest.mark.parametrize('learner,path_flag,extra', [

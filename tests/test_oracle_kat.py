@@ -774,3 +774,87 @@ def test_full_prec_and_nuq_training_loop_cadence_matches_the_reference_loops():
         NUQ.train(me)
         assert n['train'] == g['nb_train'] and ev == [e for e in g['events'] if e[0] != 'monitor'], g
     FLAGS.reset()
+
+
+# ---------------------------------------------------------------------------- channel selection
+def _cpg_gold():
+    import json
+    import os
+    return json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'ref_executed_cpg_v1.json')))
+
+
+def test_cpg_prox_step_matches_the_reference_op_chain():
+    """oracle.cpg_prox_step / cpg_channel_mask against the output of the reference's own __build_layer_ops
+    (learners/channel_pruning_gpu/learner.py:356-402) executed on numpy tensors (tests/golden/make_golden_cpg.py)."""
+    import hashlib
+    from oracle import pf_oracle as O
+    for g in _cpg_gold()['prox_step']:
+        rng = np.random.default_rng(g['seed'])
+        w0 = rng.standard_normal(g['shape']).astype(np.float32)
+        g0 = rng.standard_normal(g['shape']).astype(np.float32)
+        if g['zero_channel'] is not None:
+            w0[:, :, g['zero_channel'], :] = 0.0
+            g0[:, :, g['zero_channel'], :] = 0.0
+        keep = (rng.random(g['shape'][2]) > 0.3).astype(np.float32)
+        out, norms, thr = O.cpg_prox_step(w0, g0, g['lrn_rate_pgd'], g['prune_perctl'])
+        assert hashlib.sha256(np.ascontiguousarray(out).tobytes()).hexdigest() == g['sha256'], g
+        assert [int(c) for c in np.where(np.abs(out).sum(axis=(0, 1, 3)) == 0)[0]] == g['zero_channels']
+        assert [int(v) for v in keep] == g['mask_keep']
+        masked = (g0 * (keep[None, None, :, None] * np.ones(g['shape'], np.float32))).astype(np.float32)
+        assert hashlib.sha256(masked.tobytes()).hexdigest() == g['masked_grad_sha256']       # grad * mask (:438)
+        m = O.cpg_channel_mask(out)
+        assert sorted(set(np.where(m[0, 0, :, 0] == 0)[0].tolist())) == g['zero_channels']
+
+
+def test_cpg_selection_loop_feeds_what_the_reference_loop_feeds():
+    """ChannelPrunedGpuLearner.__choose_channels of the reference, run with a recording session that replays given
+    regression losses (golden 'choose_channels'), against (a) the oracle's schedule and (b) this repo's
+    choose_channels() driven with recording stand-ins for the device methods."""
+    from types import SimpleNamespace
+    from oracle import pf_oracle as O
+    from pocketflow_b200.flags import FLAGS
+    from pocketflow_b200.learners.channel_pruning_gpu.learner import ChannelPrunedGpuLearner as L
+    gold = _cpg_gold()
+    FLAGS.reset()
+    for k, v in gold['flag_defaults'].items():
+        assert getattr(FLAGS, k) == v, k
+    for g in gold['choose_channels']:
+        FLAGS.reset()
+        n_it = int(g['cpg_nb_iters_layer'] / g['world'])
+        ratios = [g['cpg_prune_ratio']] * g['nb_layers']
+        if g['cpg_skip_ht_layers']:
+            ratios[0] = ratios[-1] = 0.0
+        # (a) the oracle's schedule, layer by layer
+        want = []
+        for layer, r in enumerate(ratios):
+            if r == 0.0:
+                continue
+            for lr, pc in O.cpg_selection_schedule([g['reg_losses'][i % len(g['reg_losses'])] for i in range(n_it)], r, n_it):
+                want.append(['prune', layer, lr, pc])
+            want.append(['mask_updt', layer])
+            want += [['finetune', layer]] * n_it
+        assert len(want) == len(g['events'])
+        for a, b in zip(want, g['events']):
+            assert a[:2] == b[:2]
+            if a[0] == 'prune':
+                assert abs(a[2] - b[2]) <= 1e-7 * b[2]                       # fed through a float32 placeholder
+                assert abs(a[3] - b[3]) <= 1e-6 * max(b[3], 1.0)
+        # (b) this repo's host loop
+        ev, cnt = [], {}
+
+        def sel_prune(layer, lr, pc, ev=ev, cnt=cnt, g=g):
+            i = cnt.get(layer, 0)
+            cnt[layer] = i + 1
+            ev.append(['prune', layer, lr, pc])
+            return g['reg_losses'][i % len(g['reg_losses'])]
+        me = SimpleNamespace(prune_ratios=ratios, nb_layers=g['nb_layers'], is_primary_worker=lambda scope='global': False,
+                             sel_prune=sel_prune, sel_update_mask=lambda layer: ev.append(['mask_updt', layer]),
+                             sel_finetune=lambda layer, it: (ev.append(['finetune', layer]), 1.0)[1],
+                             sel_prune_ratio=lambda layer: 0.0)
+        L.choose_channels(me, nb_iters_layer=n_it)
+        assert len(ev) == len(g['events'])
+        for a, b in zip(ev, g['events']):
+            assert a[:2] == b[:2]
+            if a[0] == 'prune':
+                assert abs(a[2] - b[2]) <= 1e-7 * b[2] and abs(a[3] - b[3]) <= 1e-6 * max(b[3], 1.0)
+    FLAGS.reset()
