@@ -208,6 +208,24 @@ int pf_nuq_weight_quant(const pf_uq_seg* segs_dev, const pf_work* work_dev, int 
                         const float* scales_dev, int n_buckets,
                         const float* clusters_dev, uint8_t* idx_out_dev,
                         const int64_t* idx_base_dev, void* stream);
+/* same, with the codebook of tensor `seg` at clusters_base_dev + cluster_off_dev[seg] (floats): codebooks that live
+ * among the model's trainable variables (the reference's `clusters` variables, utils.py:297) */
+int pf_nuq_weight_quant_ex(const pf_uq_seg* segs_dev, const pf_work* work_dev, int n_work,
+                           const float* scales_dev, int n_buckets, const float* clusters_base_dev,
+                           const int64_t* cluster_off_dev, uint8_t* idx_out_dev, const int64_t* idx_base_dev,
+                           void* stream);
+/* f4  Codebook gradient of the `cluster` / `both` optimisation modes (learners/nonuniform_quantization/
+ *     learner.py:252-261): backward of tf.gather(c, min_index) under the Mul->Add / Sign->Identity override
+ *     (utils.py:303-306) through the inverse scale alpha*q+beta (:433):
+ *        dL/dc_j = alpha * sum_{i : idx_i = j} g_i ,   g = gradient w.r.t. the quantized tensor.
+ *     gsegs[i].src = g of tensor i (numel floats; bits, bucket0 as in the forward's segs); work: kind-0 chunks, all
+ *     chunks of a tensor contiguous, work_first_dev[seg .. seg+1) = its range (n_seg + 1 entries); idx/idx_base: what
+ *     pf_nuq_weight_quant wrote; partial_ws_dev: n_work * 256 floats; result at grad_base_dev + cluster_off_dev[seg].
+ *     Deterministic (fixed-order two-stage reduction). */
+int pf_nuq_cluster_grad(const pf_uq_seg* gsegs_dev, int n_seg, const pf_work* work_dev, int n_work,
+                        const int32_t* work_first_dev, const uint8_t* idx_dev, const int64_t* idx_base_dev,
+                        const float* scales_dev, float* partial_ws_dev, float* grad_base_dev,
+                        const int64_t* cluster_off_dev, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a4  Convolution / dense layers, exact-fp32 CUDA-core path (pf_conv.cu).
@@ -497,6 +515,24 @@ int pf_cpg_prox_apply(float* w_dev, const float* g_dev, float lr, const float* n
                       int rs, int cin, int cout, void* stream);
 int pf_cpg_channel_mask(const float* norms_dev, int rs, int cin, int cout, float* mask_dev, void* stream);
 int pf_mul(const float* a_dev, const float* b_dev, int64_t n, float* out_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a10 The collective of the data-parallel step (pf_comm.cu).  Replaces mgw.DistributedOptimizer's per-variable
+ *     Horovod all-reduces and mgw.broadcast_global_variables (utils/multi_gpu_wrapper.py:82-98; call sites
+ *     learners/uniform_quantization/learner.py:245-247, :271): ONE in-place ncclAllReduce (sum, fp32) over the flat
+ *     gradient buffer — or over contiguous buckets of it as the backward pass completes them — enqueued on the
+ *     caller's stream (CUDA-graph capturable); the division by the worker count is the optimizers' grad_scale.
+ *     NCCL (libnccl.so.2, or the path in PF_NCCL_LIB) is bound at run time, not linked.
+ *       pf_comm_unique_id  rank 0: 128 bytes to distribute to every rank (any host-side channel)
+ *       pf_comm_init       collective over all ranks, on the calling thread's current device; *comm_out = handle
+ *       pf_allreduce_flat / pf_broadcast_flat   asynchronous on `stream`
+ * ------------------------------------------------------------------------------------------- */
+int pf_comm_nccl_version(int* version_out);
+int pf_comm_unique_id(void* id128_out);
+int pf_comm_init(const void* id128, int n_ranks, int rank, void** comm_out);
+int pf_comm_destroy(void* comm);
+int pf_allreduce_flat(void* comm, float* buf_dev, int64_t n, void* stream);
+int pf_broadcast_flat(void* comm, float* buf_dev, int64_t n, int root, void* stream);
 
 #ifdef __cplusplus
 }

@@ -75,24 +75,14 @@ def codebook_quant(w, clusters):
     alpha = w_max - w_min + torch.tensor(1e-10)
     beta = w_min
     xn = (w - beta) / alpha
-    c = torch.as_tensor(clusters, dtype=torch.float32)
+    c = clusters if torch.is_tensor(clusters) else torch.as_tensor(clusters, dtype=torch.float32)
     with torch.no_grad():
         idx = torch.argmin(torch.abs(xn.unsqueeze(-1) - c), dim=-1)
-        q_val = c[idx] * torch.sign(xn + 1e-6)
-    q = _Replace.apply(xn, q_val)
+        sgn = torch.sign(xn + 1e-6)
+    # gradient_override_map {'Mul': 'Add', 'Sign': 'Identity'} (utils.py:303-306): the upstream gradient goes unchanged
+    # to BOTH factors — to tf.gather(c, min_index) (a segment sum into the codebook) and, through Sign-as-Identity, to x_n
+    q = c[idx] * sgn + (xn - xn.detach())
     return alpha * q + beta
-
-
-class _Replace(torch.autograd.Function):
-    """forward: the quantized value; backward: identity to x_n (Mul->Add, Sign->Identity STE)."""
-
-    @staticmethod
-    def forward(ctx, x, q):
-        return q.clone()
-
-    @staticmethod
-    def backward(ctx, g):
-        return g, None
 
 
 def _conv(x, w, attrs):
@@ -148,7 +138,10 @@ class StepOracle:
                         w = weight_fake_quant(w, self.wq_bits[op.name], self.wq.get('use_buckets', False),
                                               self.wq.get('bucket_type', 'channel'), self.wq.get('bucket_size', 256))
                     else:
-                        w = codebook_quant(w, self.clusters[op.name])
+                        # the codebook: the op's `clusters` variable when the graph carries one, else set by the test
+                        cv = op.vars.get('clusters')
+                        w = codebook_quant(w, params[cv.name] if cv is not None and cv.name in params
+                                           else self.clusters[op.name])
                 y = conv2d_nhwc(x, w, op.attrs, op.output.shape) if ty == 'Conv2D' else x @ w
                 if 'bias' in op.vars:
                     y = y + params[op.vars['bias'].name]
@@ -211,8 +204,10 @@ class StepOracle:
         return val
 
     def step(self, state, images, labels, optimizer, lr, teacher_state=None, masks=None, grad_scale=1.0,
-             beta_powers=(0.9, 0.999)):
-        """One training step from `state` (name -> np array).  Returns (losses dict, new_state, grads)."""
+             beta_powers=(0.9, 0.999), frozen=()):
+        """One training step from `state` (name -> np array).  Returns (losses dict, new_state, grads).
+        frozen: names of trainable variables the optimizer leaves alone (var_list of compute_gradients,
+        nonuniform_quantization/learner.py:252-270); they still count in the l2 loss."""
         params = {}
         for k, v in state.items():
             t = torch.from_numpy(np.array(v, dtype=F32, copy=True))
@@ -249,6 +244,8 @@ class StepOracle:
         for n, g in zip(train_names, grads):
             g = np.zeros_like(state[n]) if g is None else g.numpy()
             gout[n] = g
+            if n in frozen:
+                continue
             wd = wd_of.get(n, 0.0)
             if optimizer['kind'] == 'adam':
                 m0 = optimizer['slots'].setdefault(n + '/m', np.zeros_like(state[n]))

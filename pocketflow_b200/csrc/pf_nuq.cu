@@ -32,13 +32,16 @@ __device__ __forceinline__ float nuq_one(float w, float alpha, float beta, float
 __global__ void __launch_bounds__(kThreads)
 nuq_quant_kernel(const pf_uq_seg* __restrict__ segs, const pf_work* __restrict__ work,
                  const float* __restrict__ scales, int n_buckets,
-                 const float* __restrict__ clusters, uint8_t* __restrict__ idx_out,
-                 const int64_t* __restrict__ idx_base) {
+                 const float* __restrict__ clusters, const int64_t* __restrict__ cluster_off,
+                 uint8_t* __restrict__ idx_out, const int64_t* __restrict__ idx_base) {
   __shared__ float sc[256];
   const pf_work w = work[blockIdx.x];
   const pf_uq_seg s = segs[w.seg];
   const int nc = 1 << s.bits;
-  if ((int)threadIdx.x < nc) sc[threadIdx.x] = __ldg(clusters + (size_t)w.seg * 256 + threadIdx.x);
+  // the codebook of this tensor: at cluster_off[seg] floats from `clusters` (codebooks that live among the model's
+  // trainable variables), or at seg * 256 (a [segments, 256] table)
+  const float* cb = clusters + (cluster_off ? (size_t)cluster_off[w.seg] : (size_t)w.seg * 256);
+  if ((int)threadIdx.x < nc) sc[threadIdx.x] = cb[threadIdx.x];
   __syncthreads();
   const float alpha = __ldg(scales + s.bucket0), mn = __ldg(scales + n_buckets + s.bucket0);
   const float ra = __ldg(scales + 2 * n_buckets + s.bucket0);
@@ -59,6 +62,66 @@ nuq_quant_kernel(const pf_uq_seg* __restrict__ segs, const pf_work* __restrict__
     }
   }
 }
+
+// ---- codebook gradient (cluster / both optimisation modes): the gather's backward is a segment sum,
+//   dL/dc_j = alpha * sum_{i: idx_i = j} g_i        (g = dL/d(quantized weight); inverse scale alpha*q + beta)
+// Deterministic two-stage reduction: every CTA sums its chunk per centroid in registers (16 centroids per pass, the
+// chunk is re-read from L2 for codebooks with more), block-reduces, and writes partial[work][j]; the final kernel adds
+// the partials of a tensor in work order and applies alpha.
+constexpr int kNcPass = 16;
+
+__global__ void __launch_bounds__(kThreads)
+nuq_cluster_grad_partial_kernel(const pf_uq_seg* __restrict__ segs, const pf_work* __restrict__ work,
+                                const uint8_t* __restrict__ idx, const int64_t* __restrict__ idx_base,
+                                float* __restrict__ partial) {
+  __shared__ float sh[kThreads / 32][kNcPass];
+  const pf_work w = work[blockIdx.x];
+  const pf_uq_seg s = segs[w.seg];
+  const int nc = 1 << s.bits;
+  const uint8_t* io = idx + idx_base[w.seg];
+  const float* g = s.src;                       // the gradient w.r.t. the quantized tensor
+  const int64_t end = w.start + w.count;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int j0 = 0; j0 < nc; j0 += kNcPass) {
+    float acc[kNcPass];
+#pragma unroll
+    for (int j = 0; j < kNcPass; ++j) acc[j] = 0.f;
+    for (int64_t i = w.start + threadIdx.x; i < end; i += kThreads) {
+      const int id = (int)io[i] - j0;
+      const float gv = g[i];
+#pragma unroll
+      for (int j = 0; j < kNcPass; ++j) acc[j] += (id == j) ? gv : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < kNcPass; ++j) {
+      const float t = pf_warp_sum(acc[j]);
+      if (lane == 0) sh[warp][j] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < kNcPass && j0 + (int)threadIdx.x < nc) {
+      float t = 0.f;
+#pragma unroll
+      for (int wv = 0; wv < kThreads / 32; ++wv) t += sh[wv][threadIdx.x];
+      partial[(size_t)blockIdx.x * 256 + j0 + threadIdx.x] = t;
+    }
+    __syncthreads();
+  }
+}
+
+// one CTA per tensor: sum the partials of its work items (a contiguous range of the work table) in order
+__global__ void __launch_bounds__(256)
+nuq_cluster_grad_final_kernel(const pf_uq_seg* __restrict__ segs, const int32_t* __restrict__ work_first,
+                              const float* __restrict__ partial, const float* __restrict__ scales,
+                              float* __restrict__ grad_base, const int64_t* __restrict__ cluster_off) {
+  const int seg = blockIdx.x;
+  const pf_uq_seg s = segs[seg];
+  const int nc = 1 << s.bits;
+  const int j = threadIdx.x;
+  if (j >= nc) return;
+  float t = 0.f;
+  for (int wi = work_first[seg]; wi < work_first[seg + 1]; ++wi) t += partial[(size_t)wi * 256 + j];
+  grad_base[cluster_off[seg] + j] = __fmul_rn(t, __ldg(scales + s.bucket0));     // * alpha
+}
 }  // namespace
 
 extern "C" {
@@ -74,8 +137,41 @@ int pf_nuq_weight_quant(const pf_uq_seg* segs_dev, const pf_work* work_dev, int 
   PF_REQUIRE((idx_out_dev == nullptr) == (idx_base_dev == nullptr),
              "pf_nuq_weight_quant: idx_out and idx_base must be given together");
   nuq_quant_kernel<<<n_work, kThreads, 0, (cudaStream_t)stream>>>(
-      segs_dev, work_dev, scales_dev, n_buckets, clusters_dev, idx_out_dev, idx_base_dev);
+      segs_dev, work_dev, scales_dev, n_buckets, clusters_dev, nullptr, idx_out_dev, idx_base_dev);
   PF_CHECK_LAUNCH("pf_nuq_weight_quant");
+  return PF_OK;
+}
+
+int pf_nuq_weight_quant_ex(const pf_uq_seg* segs_dev, const pf_work* work_dev, int n_work,
+                           const float* scales_dev, int n_buckets, const float* clusters_base_dev,
+                           const int64_t* cluster_off_dev, uint8_t* idx_out_dev, const int64_t* idx_base_dev,
+                           void* stream) {
+  PF_REQUIRE(n_work >= 0, "pf_nuq_weight_quant_ex: n_work < 0");
+  if (n_work == 0) return PF_OK;
+  PF_REQUIRE(segs_dev && work_dev && scales_dev && clusters_base_dev && cluster_off_dev,
+             "pf_nuq_weight_quant_ex: null pointer");
+  PF_REQUIRE((idx_out_dev == nullptr) == (idx_base_dev == nullptr),
+             "pf_nuq_weight_quant_ex: idx_out and idx_base must be given together");
+  nuq_quant_kernel<<<n_work, kThreads, 0, (cudaStream_t)stream>>>(
+      segs_dev, work_dev, scales_dev, n_buckets, clusters_base_dev, cluster_off_dev, idx_out_dev, idx_base_dev);
+  PF_CHECK_LAUNCH("pf_nuq_weight_quant_ex");
+  return PF_OK;
+}
+
+int pf_nuq_cluster_grad(const pf_uq_seg* gsegs_dev, int n_seg, const pf_work* work_dev, int n_work,
+                        const int32_t* work_first_dev, const uint8_t* idx_dev, const int64_t* idx_base_dev,
+                        const float* scales_dev, float* partial_ws_dev, float* grad_base_dev,
+                        const int64_t* cluster_off_dev, void* stream) {
+  PF_REQUIRE(n_seg >= 0 && n_work >= 0, "pf_nuq_cluster_grad: negative count");
+  if (n_seg == 0 || n_work == 0) return PF_OK;
+  PF_REQUIRE(gsegs_dev && work_dev && work_first_dev && idx_dev && idx_base_dev && scales_dev && partial_ws_dev &&
+                 grad_base_dev && cluster_off_dev, "pf_nuq_cluster_grad: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  nuq_cluster_grad_partial_kernel<<<n_work, kThreads, 0, st>>>(gsegs_dev, work_dev, idx_dev, idx_base_dev, partial_ws_dev);
+  PF_CHECK_LAUNCH("pf_nuq_cluster_grad(partial)");
+  nuq_cluster_grad_final_kernel<<<n_seg, 256, 0, st>>>(gsegs_dev, work_first_dev, partial_ws_dev, scales_dev, grad_base_dev,
+                                                      cluster_off_dev);
+  PF_CHECK_LAUNCH("pf_nuq_cluster_grad(final)");
   return PF_OK;
 }
 

@@ -31,29 +31,39 @@ class ParamStore:
     Order: maskable variables first, then by weight-decay coefficient, so that the optimizer runs
     over at most a few contiguous ranges."""
 
-    def __init__(self, variables, device, wd_of=None, maskable=None, seed=1):
+    def __init__(self, variables, device, wd_of=None, maskable=None, seed=1, frozen=None):
+        """frozen: trainable variables the optimizer must NOT update (they still count in the weight-decay loss and
+        receive gradients): the codebooks in the non-uniform learner's 'weights' mode, everything but the codebooks in
+        its 'cluster' mode (learners/nonuniform_quantization/learner.py:252-268).  They form their own ranges."""
         self.device = device
         wd_of = wd_of or {}
         maskable = set(maskable or [])
+        frozen = set(frozen or [])
         train = [v for v in variables if v.trainable]
         other = [v for v in variables if not v.trainable]
-        key = lambda v: (0 if v in maskable else 1, -float(wd_of.get(v, 0.0)))
+        key = lambda v: (0 if v in maskable else 1, 1 if v in frozen else 0, -float(wd_of.get(v, 0.0)))
         order = sorted(range(len(train)), key=lambda i: (key(train[i]), i))
         self.train_vars = [train[i] for i in order]
         self.other_vars = other
         self.offset, self.ranges = {}, []      # ranges: (start, end, masked, wd)
+        self.frozen_ranges = set()             # (start, end) of the ranges the optimizer skips
         pos = 0
         cur = None
+
+        def close(cur, pos):
+            self.ranges.append((cur[0], pos, cur[2], cur[3]))
+            if cur[4]:
+                self.frozen_ranges.add((cur[0], pos))
         for v in self.train_vars:
-            k = (v in maskable, float(wd_of.get(v, 0.0)))
+            k = (v in maskable, float(wd_of.get(v, 0.0)), v in frozen)
             if cur is None or cur[2:] != k:
                 if cur is not None:
-                    self.ranges.append((cur[0], pos, cur[2], cur[3]))
+                    close(cur, pos)
                 cur = (pos, None) + k
             self.offset[v] = pos
             pos += _align4(v.numel)
         if cur is not None:
-            self.ranges.append((cur[0], pos, cur[2], cur[3]))
+            close(cur, pos)
         self.n_train = max(pos, 4)
         self.n_masked = max([e for (s, e, m, w) in self.ranges if m] + [0])
         opos = 0
@@ -90,10 +100,11 @@ class ParamStore:
             d[v.name] = self.view(v).detach().cpu().numpy().copy()
         return d
 
-    def load_state_dict(self, d, strict=True, require=None):
+    def load_state_dict(self, d, strict=True, require=None, optional=()):
         """Copy the variables `d` names into the store.  Returns (trainable variables found, trainable variables).
         strict: every variable must be present.  require ('any' | 'all' | None) applies to the TRAINABLE variables of a
-        non-strict load: a checkpoint of another net / scope matches nothing and must not pass for a restore."""
+        non-strict load: a checkpoint of another net / scope matches nothing and must not pass for a restore;
+        variables whose name contains one of the `optional` substrings are not required."""
         found = 0
         for v in self.train_vars + self.other_vars:
             if v.name in d:
@@ -105,10 +116,12 @@ class ParamStore:
                 found += 1 if v.trainable else 0
             elif strict:
                 raise KeyError('missing variable in checkpoint: ' + v.name)
-        total = len(self.train_vars)
+        needed = [v for v in self.train_vars if not any(o in v.name for o in optional)]
+        total = len(needed)
+        found = sum(1 for v in needed if v.name in d)
         if require is not None and total > 0:
             if found == 0 or (require == 'all' and found < total):
-                missing = [v.name for v in self.train_vars if v.name not in d][:5]
+                missing = [v.name for v in needed if v.name not in d][:5]
                 raise ValueError('checkpoint matches %d of the model\'s %d trainable variables (e.g. missing %s; the '
                                  'checkpoint holds %s ...)' % (found, total, missing, sorted(d)[:3]))
         for f in self.listeners:
@@ -122,7 +135,7 @@ class Executor:
     def __init__(self, graph, images, logits, device, store=None, train=True, loss=None, labels=None,
                  optimizer=None, weight_quant=None, act_quant=None, maskable=None, teacher=None,
                  seed=1, exact_ste=True, grad_scale=1.0, scope=None, conv_path=None, fuse_add=True,
-                 update_moving_stats=True):
+                 update_moving_stats=True, frozen=None):
         self.g, self.device, self.train = graph, device, train
         # fuse_add=False: every Conv2D output is materialised on its own (the channel-pruning learner regresses conv
         # outputs of a pruned model onto those of the full model, learners/channel_pruning_gpu/learner.py:339-354);
@@ -151,7 +164,7 @@ class Executor:
         # copies are prepared once and refreshed only when the store is (re)loaded
         self.static_weights = (not train) and store is None
         self._static_ready = False
-        self.store = store or ParamStore(variables, device, wd_of, self.maskable, seed)
+        self.store = store or ParamStore(variables, device, wd_of, self.maskable, seed, frozen=frozen)
         if self.static_weights:
             self.store.listeners.append(self._invalidate_static)
         self.weight_quant, self.act_quant = weight_quant, act_quant
@@ -254,7 +267,17 @@ class Executor:
                 self.wq = ops.UniformWeightQuantizer(srcs, dsts, wq['bits'], wq.get('use_buckets', False),
                                                      wq.get('bucket_type', 'channel'), wq.get('bucket_size', 256))
             else:
-                self.wq = ops.CodebookWeightQuantizer(srcs, dsts, wq['bits'])
+                # codebooks: the reference's trainable `clusters` variables when the graph carries them (then they
+                # live in the parameter store), else a private table of the quantizer
+                cvars = [op.vars.get('clusters') for op in self.wq_ops]
+                self.train_clusters = bool(wq.get('train_clusters', False)) and self.train
+                if all(c is not None for c in cvars):
+                    self.wq = ops.CodebookWeightQuantizer(srcs, dsts, wq['bits'], keep_index=self.train_clusters,
+                                                          cluster_views=[st.view(c) for c in cvars], cluster_base=st.P)
+                else:
+                    if self.train_clusters:
+                        raise ValueError('training the codebooks needs `clusters` variables on the quantized ops')
+                    self.wq = ops.CodebookWeightQuantizer(srcs, dsts, wq['bits'])
         self.qvars = {op: op.vars['kernel'] for op in self.wq_ops}
         # ---- tensors
         for op in self.ops:
@@ -562,6 +585,7 @@ class Executor:
                         gk = st.view(op.vars['kernel'], self.G)
                         self.wg_part[op] = E((splits * gk.numel(),))
                         red_items.append((self.wg_part[op], gk, splits))
+            self._red_items = red_items
             self.wg_reduce = ops.TcWgradReduceBatch(red_items, dev) if red_items else None
             max_dy = max(max_dy, getattr(self, '_stem_dy', 8))
             self.x_scratch = ops.Planes(max_x, dev)
@@ -829,12 +853,72 @@ class Executor:
                 raise NotImplementedError('op type %s' % ty)
         return self.T(self.logits_t)
 
+    # ------------------------------------------------------------------ gradient buckets of the data-parallel step
+    def _bucket_plan(self):
+        """The flat gradient buffer is summed over the workers in TWO all-reduces instead of one: the
+        kernels of the LAST layers — about half of the first (weight-decayed) range of the parameter store, which is laid
+        out in forward order — are complete long before the backward pass ends (stage 4 + the dense layer of ResNet-50
+        hold 2/3 of its parameters and take ~10 % of its backward time), so their all-reduce runs on a communication
+        stream underneath the rest of the backward pass.  Returns None when the split does not apply."""
+        if hasattr(self, '_bk'):
+            return self._bk
+        self._bk = None
+        st = self.store
+        if os.environ.get('PF_AR_BUCKETS', '2') == '1' or not self.overlap or getattr(self, 'train_clusters', False) \
+                or not st.ranges:
+            return None
+        s0, e0 = st.ranges[0][0], st.ranges[0][1]
+        pos = {op: i for i, op in enumerate(self.ops)}
+        owners = sorted((st.offset[v], v.numel, pos[op]) for op in self.ops for v in op.vars.values()
+                        if v.trainable and s0 <= st.offset[v] < e0)
+        if len(owners) < 4 or any(b[2] < a[2] for a, b in zip(owners, owners[1:])):
+            return None                                    # store order is not the forward order: no valid split
+        acc, cut = 0, None
+        for i in range(len(owners) - 1, 0, -1):
+            acc += owners[i][1]
+            if acc >= 0.5 * (e0 - s0) and owners[i][2] > owners[i - 1][2]:
+                cut = i
+                break
+        if cut is None:
+            return None
+        split, bpos = owners[cut][0], owners[cut][2]
+        off = lambda t: (t.data_ptr() - self.G.data_ptr()) // 4
+        hi = [it for it in self._red_items if off(it[1]) >= split]
+        lo = [it for it in self._red_items if off(it[1]) < split]
+        ste_hi = ste_lo = None
+        if self._ste_grads is not None:
+            ste_hi = [i for i, g in enumerate(self._ste_grads) if off(g) >= split]
+            ste_lo = [i for i, g in enumerate(self._ste_grads) if off(g) < split]
+        self._bk = dict(split=split, end=e0, pos=bpos, stream=torch.cuda.Stream(device=self.device),
+                        red_hi=ops.TcWgradReduceBatch(hi, self.device) if hi else None,
+                        red_lo=ops.TcWgradReduceBatch(lo, self.device) if lo else None, ste_hi=ste_hi, ste_lo=ste_lo)
+        return self._bk
+
+    def _bucket_hi(self, bk, allreduce):
+        """the last layers' gradients are final: reduce their split-K partials, apply their STE, start their all-reduce —
+        all on the communication stream, behind what the main and the weight-gradient streams have enqueued so far"""
+        cs, main = bk['stream'], torch.cuda.current_stream()
+        cs.wait_stream(main)
+        if self._side_active:
+            cs.wait_stream(self.side2)
+        with torch.cuda.stream(cs):
+            if bk['red_hi'] is not None:
+                bk['red_hi'].reduce()
+            if bk['ste_hi']:
+                self.wq.ste_backward_(self._ste_grads, bk['ste_hi'])
+            allreduce(self.G[bk['split']:bk['end']])
+
     # ------------------------------------------------------------------ loss + backward
-    def loss_and_backward(self):
+    def loss_and_backward(self, allreduce=None):
+        """allreduce (data-parallel step): callable summing a contiguous range of the flat gradient buffer over the
+        workers on the current stream; called for every range of the buffer before this method returns."""
         st = self.store
         L = self.loss
         self._gwritten = set()
         self._side_active = self.overlap and self.prof is None
+        bk = self._bucket_plan() if (allreduce is not None and self._side_active) else None
+        bk_fired = False
+        op_pos = {op: i for i, op in enumerate(self.ops)} if bk is not None else None
         labels = self.T(self.labels_t)
         ce_logits = L.ce[1]
         teacher_logits, w_dst, T_dst = None, 0.0, 1.0
@@ -845,6 +929,9 @@ class Executor:
         ops.softmax_ce(self.T(ce_logits), labels, teacher_logits, T_dst, w_dst, gl.view(ce_logits.shape),
                        self.loss_out[:4], self.row_ws)
         for op in reversed(self.ops):
+            if bk is not None and not bk_fired and op_pos[op] < bk['pos']:
+                bk_fired = True
+                self._bucket_hi(bk, allreduce)
             ty = op.type
             if ty == 'Placeholder':
                 continue
@@ -974,11 +1061,27 @@ class Executor:
                 raise NotImplementedError('backward of %s' % ty)
         if self._side_active:
             torch.cuda.current_stream().wait_stream(self.side2)
+        if bk is not None and bk_fired:
+            # the rest of the buffer: [0, split) of the first range and everything behind it (BN scales / offsets, ...)
+            if bk['red_lo'] is not None:
+                bk['red_lo'].reduce()
+            if bk['ste_lo']:
+                self.wq.ste_backward_(self._ste_grads, bk['ste_lo'])
+            allreduce(self.G[:bk['split']])
+            if bk['end'] < self.G.numel():
+                allreduce(self.G[bk['end']:])
+            torch.cuda.current_stream().wait_stream(bk['stream'])
+            return
         if self.wg_reduce is not None:
             with self.timed('conv_wgrad'):
                 self.wg_reduce.reduce()
         if self._ste_grads is not None:
             self.wq.ste_backward_(self._ste_grads)
+        if getattr(self, 'train_clusters', False):
+            # codebook gradients from the gradients w.r.t. the quantized kernels (which stay, unchanged, as the kernels'
+            # own gradients: the straight-through estimator of utils.py:303-306)
+            with self.timed('weight_quant'):
+                self.wq.cluster_grad([st.view(op.vars['kernel'], self.G) for op in self.wq_ops], self.G)
 
     def layer_wgrad(self, op, gy, dw):
         """dW of ONE Conv2D / MatMul for an externally supplied gradient `gy` of its output, after a training-mode
@@ -1046,7 +1149,7 @@ class Executor:
     def apply_gradients(self):
         st, o = self.store, self.optimizer
         for (s, e, masked, wd) in st.ranges:
-            if e <= s:
+            if e <= s or (s, e) in st.frozen_ranges:
                 continue
             if o['kind'] == 'momentum':
                 mask = self.MASK[s:e] if (masked and self.MASK is not None) else None
@@ -1086,8 +1189,8 @@ class Executor:
             if self.teacher is not None:
                 self.teacher.forward()
             self.forward()
-        self.loss_and_backward()
-        if allreduce is not None:
+        self.loss_and_backward(allreduce)
+        if allreduce is not None and not (self._side_active and self._bucket_plan() is not None):
             with self.timed('allreduce'):
                 allreduce(self.G)
         with self.timed('optimizer'):

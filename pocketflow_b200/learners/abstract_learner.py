@@ -127,7 +127,7 @@ class AbstractLearner(ABC):  # pylint: disable=too-many-instance-attributes
         auto_barrier_impl(self.mpi_comm)
 
     # ------------------------------------------------------------------ checkpoints
-    def restore_model(self, path, store=None, require='all'):
+    def restore_model(self, path, store=None, require='all', optional=()):
         """saver.restore(sess, tf.train.latest_checkpoint(dirname(path))) — every learner's __restore_model (e.g.
         learners/full_precision/learner.py:193-205).  A checkpoint that does not hold the model's trainable variables
         (wrong net, wrong scope) raises instead of 'restoring' nothing."""
@@ -136,7 +136,7 @@ class AbstractLearner(ABC):  # pylint: disable=too-many-instance-attributes
         if fn is None:
             raise ValueError('no checkpoint found in ' + ckpt_dir)
         store = self.sess_train.store if store is None else store
-        found, total = store.load_state_dict(load_checkpoint(fn), strict=False, require=require)
+        found, total = store.load_state_dict(load_checkpoint(fn), strict=False, require=require, optional=optional)
         print('model restored from %s (%d of %d trainable variables)' % (fn, found, total))
         return fn
 

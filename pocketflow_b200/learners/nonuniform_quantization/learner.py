@@ -4,19 +4,16 @@ are in place (learner.py:127-129), frozen; weights trained with Adam through the
 from timeit import default_timer as timer
 
 import numpy as np
-import torch
 
 from ... import graph as G
 from ...engine import Executor
 from ...flags import FLAGS, DEFINE_integer, DEFINE_boolean, DEFINE_string
 from ...utils.multi_gpu_wrapper import MultiGpuWrapper as mgw
 from ...utils.lrn_rate_utils import piecewise_constant
-from ..abstract_learner import AbstractLearner, load_checkpoint, save_checkpoint
+from ..abstract_learner import AbstractLearner, save_checkpoint
 from ..distillation_helper import DistillationHelper
 from .utils import NonUniformQuantization
 from .bit_optimizer import BitOptimizer
-
-CLUSTERS_KEY = 'nuql/clusters:0'          # [layers, 256] codebooks in a quantized-model checkpoint
 
 DEFINE_string('nuql_opt_mode', 'weights', 'the variables to optimize: [clusters, weights, both]')
 DEFINE_string('nuql_init_style', 'quantile', 'the initialization of quantization points: [quantile, uniform]')
@@ -61,9 +58,10 @@ class NonUniformQuantLearner(AbstractLearner):
     # pylint: disable=too-many-instance-attributes
     def __init__(self, sm_writer, model_helper):
         super(NonUniformQuantLearner, self).__init__(sm_writer, model_helper)
-        if FLAGS.nuql_opt_mode != 'weights':
-            raise NotImplementedError("nuql_opt_mode '%s' (codebook gradients) is a next-tier row; "
-                                      "'weights' is built" % FLAGS.nuql_opt_mode)
+        # learner.py:254-268 tests for 'cluster' / 'both' / 'weights' (the flag's help text says 'clusters'; that
+        # spelling ends in the reference's ValueError too)
+        if FLAGS.nuql_opt_mode not in ('weights', 'cluster', 'both'):
+            raise ValueError('Unknown optimization mode')
         if FLAGS.enbl_dst:
             self.helper_dst = DistillationHelper(sm_writer, model_helper, self.mpi_comm)
         self.statistics = {}
@@ -73,8 +71,9 @@ class NonUniformQuantLearner(AbstractLearner):
         total = self.finetune_steps if nb_iters is None else nb_iters
         ex = self.sess_train
         if FLAGS.enbl_warm_start:
-            # use the latest model for warm start, THEN fit the codebooks to it (learner.py:124-129)
-            self.restore_model(FLAGS.save_path)
+            # use the latest model for warm start, THEN fit the codebooks to it (learner.py:124-129); the pre-trained
+            # checkpoint holds no codebooks (saver_train is built before the graph is quantized, :209)
+            self.restore_model(FLAGS.save_path, optional=('/clusters',))
             self.cluster_init()
         if FLAGS.enbl_multi_gpu:
             mgw.broadcast_global_variables([ex.store.P, ex.store.O])
@@ -99,19 +98,9 @@ class NonUniformQuantLearner(AbstractLearner):
         if not self.is_primary_worker():
             return
         ex = self.sess_train
-        state = ex.store.state_dict()
-        # the codebooks are variables of the reference's quantized graph (utils.py:297-347) and travel with its
-        # checkpoints; here they live in the quantizer, so they are written beside the model's variables
-        state[CLUSTERS_KEY] = ex.wq.clusters.detach().cpu().numpy().copy()
-        print('quantized model saved to ' + save_checkpoint(FLAGS.nuql_save_quant_model_path, state, ex.step_count))
-
-    def restore_for_eval(self, path):
-        if FLAGS.exec_mode != 'eval':
-            return
-        ckpt = load_checkpoint(self.restore_model(path))
-        if CLUSTERS_KEY not in ckpt or ckpt[CLUSTERS_KEY].shape != tuple(self.sess_train.wq.clusters.shape):
-            raise ValueError('checkpoint holds no codebooks for this model (%s)' % CLUSTERS_KEY)
-        self.sess_train.wq.clusters.copy_(torch.from_numpy(np.asarray(ckpt[CLUSTERS_KEY], np.float32)))
+        # the codebooks are variables of the model scope and travel with its checkpoints, as in the reference
+        print('quantized model saved to ' + save_checkpoint(FLAGS.nuql_save_quant_model_path, ex.store.state_dict(),
+                                                            ex.step_count))
 
     def train_step(self):
         ex = self.sess_train
@@ -155,9 +144,15 @@ class NonUniformQuantLearner(AbstractLearner):
                 w_bits, a_bits = BitOptimizer(len(matmul_ops), len(act_ops)).run()
                 nq.insert_quant_op_for_weights({op.name: b for op, b in zip(matmul_ops, w_bits)})
                 nq.insert_quant_op_for_activations({op.name: b for op, b in zip(act_ops, a_bits)})
+                # "Strictly speaking, clusters should be not included for regularization" (learner.py:219-220): they are
                 loss, metrics = self.calc_loss(labels, logits, self.trainable_vars)
                 if FLAGS.enbl_dst:
                     loss += self.helper_dst.calc_loss(logits, logits_dst)
+                # the variables the optimizer updates (learner.py:252-268): the codebooks ('cluster'), everything else
+                # ('weights') or all trainable variables ('both')
+                clusters = [v for v in self.trainable_vars if 'clusters' in v.name]
+                rest = [v for v in self.trainable_vars if v not in clusters]
+                frozen = {'weights': clusters, 'cluster': rest, 'both': []}[FLAGS.nuql_opt_mode]
         init_lr, bnds, decay_rates, self.finetune_steps = setup_bnds_decay_rates(self.model_name, self.dataset_name)
         self.lrn_rate = piecewise_constant(list(bnds), [init_lr * d for d in decay_rates])
         world = mgw.size() if FLAGS.enbl_multi_gpu else 1
@@ -165,9 +160,13 @@ class NonUniformQuantLearner(AbstractLearner):
         if FLAGS.enbl_dst:
             teacher = Executor(self.graph_train, images, logits_dst, self.device, train=False, seed=2)
             self.helper_dst.restore(teacher.store)
+        wq_spec = nq.weight_quant_spec()
+        if wq_spec is not None:
+            wq_spec['train_clusters'] = FLAGS.nuql_opt_mode in ('cluster', 'both')
         self.sess_train = Executor(self.graph_train, images, logits, self.device, train=True, loss=loss, labels=labels,
-                                   optimizer=dict(kind='adam'), weight_quant=nq.weight_quant_spec(),
-                                   act_quant=nq.act_quant_spec(), teacher=teacher, seed=1, grad_scale=1.0 / world)
+                                   optimizer=dict(kind='adam'), weight_quant=wq_spec,
+                                   act_quant=nq.act_quant_spec(), teacher=teacher, seed=1, grad_scale=1.0 / world,
+                                   frozen=frozen)
         if teacher is not None:
             teacher.buf[images] = self.sess_train.buf[images]
             self.sess_train.share_im2col_from(teacher)

@@ -1,7 +1,9 @@
 """Util functions for Non-Uniform Quantization — graph-editing surface of the reference
 (/root/reference/learners/nonuniform_quantization/utils.py:31-476).  Weights go through the codebook
 quantizer (pf_nuq_weight_quant), activations through the UNIFORM quantizer (utils.py:58-85)."""
-from ..uniform_quantization.utils import prefix_filter  # noqa: F401
+import numpy as np
+
+from ..uniform_quantization.utils import prefix_filter
 
 
 class NonUniformQuantization:
@@ -45,9 +47,19 @@ class NonUniformQuantization:
         return self.activation_ops
 
     def insert_quant_op_for_weights(self, w_bit_dict):
+        """Marks the ops and creates each one's codebook variable — tf.get_variable('clusters', initializer=init_c) under
+        variable_scope(prefix + '/nonuniform_quantize') inside the learner's model scope (utils.py:180, :297): a
+        TRAINABLE variable of 2^bits quantization points on [0, 1], named like the reference's so that checkpoints
+        interchange.  Its value is set by the learner's cluster_init (quantiles of the restored weights)."""
+        g = self.sess
         for op in self.matmul_ops:
+            bits = int(w_bit_dict[op.name])
             self.quantized_matmul_ops.append(op)
-            self.weight_bits.append(int(w_bit_dict[op.name]))
+            self.weight_bits.append(bits)
+            if op.type != 'DepthwiseConv2dNative' and bits <= 8:
+                name = g.scope_prefix() + prefix_filter(op.name) + '/nonuniform_quantize/clusters'
+                op.vars['clusters'] = g.get_variable(name, (2 ** bits,), lambda rng, shape: np.zeros(shape, np.float32),
+                                                     trainable=True)
 
     def insert_quant_op_for_activations(self, act_bit_dict):
         for op in self.activation_ops:
@@ -60,7 +72,7 @@ class NonUniformQuantization:
         if not self.quantized_matmul_ops:
             return None
         return dict(kind='nonuniform', ops=self.quantized_matmul_ops, bits=self.weight_bits,
-                    init_style=self.init_style)
+                    init_style=self.init_style, train_clusters=False)
 
     def act_quant_spec(self):
         if not self.quantized_activation_ops:

@@ -35,6 +35,8 @@ SIGNATURES = {
     'pf_softmax_ce_fwd_bwd': (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_f32, c_f32, c_vp, c_vp, c_vp, c_vp]),
     'pf_l2_loss': (c_i32, [c_vp, c_i64, c_f32, c_i32, c_vp, c_vp, c_vp]),
     'pf_nuq_weight_quant': (c_i32, [c_vp, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    'pf_nuq_weight_quant_ex': (c_i32, [c_vp, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'pf_nuq_cluster_grad': (c_i32, [c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'pf_im2col': (c_i32, [c_vp, c_vp, c_i32, c_vp, c_vp]),
     'pf_s2d_planes': (c_i32, [c_vp] + [c_i32] * 9 + [c_vp, c_vp, c_vp]),
     'pf_preprocess_images': (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_f32, c_f32, c_f32, c_vp, c_vp]),
@@ -93,6 +95,12 @@ SIGNATURES = {
     'pf_global_avgpool_bwd': (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     'pf_softmax_fwd': (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp]),
     'pf_softmax_bwd': (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
+    'pf_comm_nccl_version': (c_i32, [ctypes.POINTER(c_i32)]),
+    'pf_comm_unique_id': (c_i32, [c_vp]),
+    'pf_comm_init': (c_i32, [c_vp, c_i32, c_i32, ctypes.POINTER(c_vp)]),
+    'pf_comm_destroy': (c_i32, [c_vp]),
+    'pf_allreduce_flat': (c_i32, [c_vp, c_vp, c_i64, c_vp]),
+    'pf_broadcast_flat': (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp]),
     'pf_cpg_diff_l2': (c_i32, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     'pf_cpg_group_norms': (c_i32, [c_vp, c_vp, c_f32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     'pf_cpg_prox_apply': (c_i32, [c_vp, c_vp, c_f32, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
@@ -152,6 +160,6 @@ def check(status, what):
     if status == 0:
         return
     msg = load().pf_last_error().decode('utf-8', 'replace')
-    if status in (-1, -2):
+    if status in (-1, -2):       # argument errors
         raise ValueError('%s: %s' % (what, msg))
     raise RuntimeError('%s failed with status %d: %s' % (what, status, msg))

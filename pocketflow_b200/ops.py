@@ -172,6 +172,7 @@ class UniformWeightQuantizer:
         self.segs['bits'] = bits
         self.segs_dev = _upload(self.segs, self.device)
         self.grad_segs_dev = None
+        self.__dict__.pop('_grad_subsets', None)
 
     def reset_ranges(self):
         st = _stream()
@@ -195,9 +196,24 @@ class UniformWeightQuantizer:
         self.minmax()
         self.quantize()
 
-    def ste_backward_(self, grads):
-        """In-place STE chain on the gradients w.r.t. the quantized weights (a3)."""
+    def ste_backward_(self, grads, indices=None):
+        """In-place STE chain on the gradients w.r.t. the quantized weights (a3).  indices: only these tensors (the
+        gradient buckets of the data-parallel step finish at different times)."""
         _check_f32(*grads)
+        if indices is not None:
+            key = tuple(indices)
+            cache = self.__dict__.setdefault('_grad_subsets', {})
+            ent = cache.get(key)
+            if ent is None or ent[0] != [grads[i].data_ptr() for i in indices]:
+                gs = self.segs[list(indices)].copy()
+                gs['src'] = [grads[i].data_ptr() for i in indices]
+                gs['dst'] = gs['src']
+                work = flat_works([int(s['numel']) for s in gs])
+                ent = cache[key] = ([grads[i].data_ptr() for i in indices], _upload(gs, self.device),
+                                    _upload(work, self.device), len(work))
+            _lib.check(self.L.pf_uq_weight_ste_bwd(_p(ent[1]), _p(ent[2]), ent[3], _p(self.scales), self.n_buckets,
+                                                   _stream()), 'pf_uq_weight_ste_bwd')
+            return
         if self.grad_segs_dev is None or self._grad_ptrs != [g.data_ptr() for g in grads]:
             gs = self.segs.copy()
             gs['src'] = [g.data_ptr() for g in grads]
@@ -366,9 +382,13 @@ def l2_loss(v, scale, out, partial_ws, accumulate=False):
 # ----------------------------------------------------------------------------- a11 codebooks
 class CodebookWeightQuantizer:
     """Multi-tensor codebook quantizer, per-layer range —
-    NonUniformQuantization.__nonuni_quantize (learners/nonuniform_quantization/utils.py:168-194)."""
+    NonUniformQuantization.__nonuni_quantize (learners/nonuniform_quantization/utils.py:168-194).
 
-    def __init__(self, srcs, dsts, bits, keep_index=False):
+    The codebooks are either a private [tensors, 256] table (`clusters`), or — `cluster_views` — 1-D views of ONE flat
+    buffer `cluster_base` that the caller owns: the reference's trainable `clusters` variables (utils.py:297), which then
+    sit among the model's parameters (optimizer, weight decay, checkpoints, broadcast all apply to them)."""
+
+    def __init__(self, srcs, dsts, bits, keep_index=False, cluster_views=None, cluster_base=None):
         self.L = _lib.load()
         _check_f32(*srcs)
         _check_f32(*dsts)
@@ -377,7 +397,20 @@ class CodebookWeightQuantizer:
             raise ValueError('codebook bit-widths must be <= 8')
         self.srcs, self.dsts = list(srcs), list(dsts)
         self.device = self.uq.device
-        self.clusters = torch.zeros(len(srcs), 256, dtype=torch.float32, device=self.device)
+        self.cluster_views, self.cluster_base, self.cluster_off = None, None, None
+        if cluster_views is not None:
+            _check_f32(cluster_base, *cluster_views)
+            offs = []
+            for v, b in zip(cluster_views, self.uq.bits):
+                off = (v.data_ptr() - cluster_base.data_ptr()) // 4
+                if v.numel() != (1 << b) or off < 0 or off + v.numel() > cluster_base.numel():
+                    raise ValueError('codebook views must hold 2^bits floats inside cluster_base')
+                offs.append(off)
+            self.cluster_views, self.cluster_base = list(cluster_views), cluster_base
+            self.cluster_off = torch.tensor(offs, dtype=torch.int64, device=self.device)
+            self.clusters = None
+        else:
+            self.clusters = torch.zeros(len(srcs), 256, dtype=torch.float32, device=self.device)
         self.idx = None
         if keep_index:
             offs, tot = [], 0
@@ -387,11 +420,12 @@ class CodebookWeightQuantizer:
             self.idx = torch.zeros(tot, dtype=torch.uint8, device=self.device)
             self.idx_base = torch.tensor(offs, dtype=torch.int64, device=self.device)
             self.idx_offsets = offs
+        self._grad_tables = None
 
-    def quantile_init(self):
-        """clusters_j = percentile(x_n, (j+1)*100/(k+1)) (utils.py:349-366).  x -> x_n is monotone
-        non-decreasing in fp32, so the order statistic is selected on the raw weights (exact radix
-        select) and normalised afterwards with the same fp32 ops."""
+    def quantile_values(self):
+        """clusters_j = percentile(x_n, (j+1)*100/(k+1)) (utils.py:349-366), [tensors][k] as numpy.  x -> x_n is
+        monotone non-decreasing in fp32, so the order statistic is selected on the raw weights (exact radix select)
+        and normalised afterwards with the same fp32 ops."""
         self.uq.minmax()
         queries = []
         for i, s in enumerate(self.srcs):
@@ -400,22 +434,62 @@ class CodebookWeightQuantizer:
                 queries.append((i, percentile_rank_desc(s.numel(), (j + 1) * 100 / (k + 1))))
         vals = select_desc(self.srcs, queries).cpu().numpy()
         rng = self.uq.ranges()
-        c = np.zeros((len(self.srcs), 256), np.float32)
-        pos = 0
+        out, pos = [], 0
         for i in range(len(self.srcs)):
             k = 1 << self.uq.bits[i]
             mn, mx = rng[i][0][0], rng[i][1][0]
             alpha = np.float32(np.float32(mx - mn) + np.float32(1e-10))
-            c[i, :k] = ((vals[pos:pos + k] - mn).astype(np.float32) / alpha).astype(np.float32)
+            out.append(((vals[pos:pos + k] - mn).astype(np.float32) / alpha).astype(np.float32))
             pos += k
+        return out
+
+    def quantile_init(self):
+        vals = self.quantile_values()
+        if self.cluster_views is not None:
+            for v, c in zip(self.cluster_views, vals):
+                v.copy_(torch.from_numpy(c))
+            return
+        c = np.zeros((len(self.srcs), 256), np.float32)
+        for i, v in enumerate(vals):
+            c[i, :v.size] = v
         self.clusters.copy_(torch.from_numpy(c))
 
     def forward(self):
         self.uq.minmax()
-        _lib.check(self.L.pf_nuq_weight_quant(_p(self.uq.segs_dev), _p(self.uq.work_q_dev), len(self.uq.work_q),
-                                              _p(self.uq.scales), self.uq.n_buckets, _p(self.clusters),
-                                              _p(self.idx), _p(self.idx_base) if self.idx is not None else None,
-                                              _stream()), 'pf_nuq_weight_quant')
+        idx_base = _p(self.idx_base) if self.idx is not None else None
+        if self.cluster_views is not None:
+            _lib.check(self.L.pf_nuq_weight_quant_ex(_p(self.uq.segs_dev), _p(self.uq.work_q_dev), len(self.uq.work_q),
+                                                     _p(self.uq.scales), self.uq.n_buckets, _p(self.cluster_base),
+                                                     _p(self.cluster_off), _p(self.idx), idx_base, _stream()),
+                       'pf_nuq_weight_quant_ex')
+        else:
+            _lib.check(self.L.pf_nuq_weight_quant(_p(self.uq.segs_dev), _p(self.uq.work_q_dev), len(self.uq.work_q),
+                                                  _p(self.uq.scales), self.uq.n_buckets, _p(self.clusters),
+                                                  _p(self.idx), idx_base, _stream()), 'pf_nuq_weight_quant')
+
+    def cluster_grad(self, grads, grad_base):
+        """dL/dc_j = alpha * sum_{idx = j} g (learner.py:252-261 through utils.py:303-306, :433): `grads` = the gradients
+        w.r.t. the QUANTIZED tensors (one per src), results written to grad_base + the codebooks' offsets (grad_base has
+        the layout of cluster_base).  Needs keep_index and store-resident codebooks."""
+        if self.idx is None or self.cluster_off is None:
+            raise ValueError('cluster_grad needs keep_index=True and cluster_views')
+        _check_f32(grad_base, *grads)
+        ptrs = [g.data_ptr() for g in grads]
+        if self._grad_tables is None or self._grad_tables[0] != ptrs:
+            gs = self.uq.segs.copy()
+            gs['src'] = ptrs
+            gs['dst'] = ptrs
+            first = np.zeros(len(self.srcs) + 1, np.int32)
+            for w in self.uq.work_q:
+                first[int(w['seg']) + 1] += 1
+            first = np.cumsum(first).astype(np.int32)
+            self._grad_tables = (ptrs, _upload(gs, self.device), _upload(first, self.device),
+                                 torch.empty(max(len(self.uq.work_q), 1) * 256, dtype=torch.float32, device=self.device))
+        _, gsegs, first_dev, partial = self._grad_tables
+        _lib.check(self.L.pf_nuq_cluster_grad(_p(gsegs), len(self.srcs), _p(self.uq.work_q_dev), len(self.uq.work_q),
+                                              _p(first_dev), _p(self.idx), _p(self.idx_base), _p(self.uq.scales),
+                                              _p(partial), _p(grad_base), _p(self.cluster_off), _stream()),
+                   'pf_nuq_cluster_grad')
 
 
 # ----------------------------------------------------------------------------- a4 conv / a13 layers

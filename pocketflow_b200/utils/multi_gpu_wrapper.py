@@ -46,12 +46,42 @@ class MultiGpuWrapper(object):
     def local_rank(cls):
         return int(os.environ.get('LOCAL_RANK', cls.rank()))
 
+    _comm = None           # the step's own NCCL communicator behind the C ABI (pf_comm_init)
+
+    @classmethod
+    def comm(cls):
+        """The communicator pf_allreduce_flat runs on: created once per process from a unique id that rank 0 makes and
+        torch.distributed (the plumbing) hands to the other ranks.  None on CPU / gloo (host-logic tests) and when
+        PF_COMM=torch asks for torch.distributed's own all-reduce."""
+        if cls._comm is None and dist.is_initialized() and dist.get_world_size() > 1 and torch.cuda.is_available() \
+                and dist.get_backend() == 'nccl' and os.environ.get('PF_COMM', 'pf') != 'torch':
+            import ctypes
+            from .. import lib as _lib
+            L = _lib.load()
+            buf = ctypes.create_string_buffer(128)
+            if dist.get_rank() == 0:
+                _lib.check(L.pf_comm_unique_id(buf), 'pf_comm_unique_id')
+            idt = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).cuda()
+            dist.broadcast(idt, src=0)
+            buf = ctypes.create_string_buffer(bytes(idt.cpu().numpy().tobytes()), 128)
+            handle = ctypes.c_void_p()
+            _lib.check(L.pf_comm_init(buf, dist.get_world_size(), dist.get_rank(), ctypes.byref(handle)), 'pf_comm_init')
+            cls._comm = handle
+        return cls._comm
+
     @classmethod
     def allreduce_flat_(cls, flat):
-        """Sum `flat` (one contiguous fp32 buffer holding every gradient) over all ranks, in place.
+        """Sum `flat` (a contiguous fp32 range of the flat gradient buffer) over all ranks, in place, on the CURRENT
+        stream: pf_allreduce_flat (the C ABI's NCCL all-reduce) on GPUs, torch.distributed on CPU / gloo.
         The Horovod average (sum / size) is folded into the optimizer kernel's grad_scale."""
         if dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            comm = cls.comm() if flat.is_cuda else None
+            if comm is not None:
+                from .. import lib as _lib
+                _lib.check(_lib.load().pf_allreduce_flat(comm, flat.data_ptr(), flat.numel(),
+                                                         torch.cuda.current_stream().cuda_stream), 'pf_allreduce_flat')
+            else:
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM)
         return flat
 
     @classmethod

@@ -269,10 +269,9 @@ def test_nonuniform_learner_step_on_tensor_core_path():
     ex = lrn.sess_train
     assert len(ex.tc) >= 8
     state, tstate = ex.store.state_dict(), ex.teacher.store.state_dict()
-    clusters = ex.wq.clusters.cpu().numpy()
+    clusters = [state[op.vars['clusters'].name] for op in ex.wq_ops]   # codebooks are variables of the model scope
     orc = oracles(lrn)
-    for i, op in enumerate(ex.wq_ops):
-        orc.clusters[op.name] = clusters[i, :16]
+    frozen = [op.vars['clusters'].name for op in ex.wq_ops]               # 'weights' mode: not in the optimizer's var_list
     images, labels = lrn.iterator_train.next_batch()
     ex.buf[lrn.images].copy_(images)
     ex.buf[lrn.labels].copy_(labels)
@@ -280,12 +279,15 @@ def test_nonuniform_learner_step_on_tensor_core_path():
     got = ex.fetch_losses()
     for i, op in enumerate(ex.wq_ops):
         v = op.vars['kernel']
-        q_ref, _, _ = O.nonuniform_quantize(state[v.name], 4, clusters[i, :16])
+        q_ref, _, _ = O.nonuniform_quantize(state[v.name], 4, clusters[i])
         assert np.array_equal(ex.store.view(v, ex.QW).cpu().numpy(), q_ref)
-    ref, _, _ = orc.step(state, images.numpy(), labels.numpy(), dict(kind='adam', slots={}), lrn.lrn_rate(0),
-                         teacher_state=tstate)
+    ref, new_state, _ = orc.step(state, images.numpy(), labels.numpy(), dict(kind='adam', slots={}), lrn.lrn_rate(0),
+                                 teacher_state=tstate, frozen=frozen)
     for k in ('ce', 'l2', 'dst_loss', 'loss'):
         assert rel(got[k], ref[k]) <= 1e-5, (k, got[k], ref[k])
+    after = ex.store.state_dict()
+    for n in frozen:
+        assert np.array_equal(after[n], state[n])                         # frozen codebooks
 
 
 def test_mobilenet_channel_pruned_step_on_tensor_core_path():
@@ -294,6 +296,9 @@ def test_mobilenet_channel_pruned_step_on_tensor_core_path():
     lrn = make_mobilenet('chn-pruned-gpu', cpg_prune_ratio=0.5)
     ex = lrn.sess_train
     assert len(ex.tc) >= 13
+    lrn.init_from_full()
+    lrn.choose_channels(nb_iters_layer=2)                  # a short run of the selection phase: 50 % input-channel masks
+    assert abs(lrn.pr_maskable() - 0.5) < 0.1
     masks = {v.name: ex.store.view(v, ex.MASK).cpu().numpy().copy() for v in lrn.maskable_vars}
     orc = StepOracle(ex.ops, ex.logits_t, lrn.images, lrn.labels, ex.loss)
     state = ex.store.state_dict()

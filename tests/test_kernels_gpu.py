@@ -235,6 +235,42 @@ def test_codebook_quant_bit_exact(bits):
         assert np.array_equal(idx[o:o + w.size], ridx.reshape(-1).astype(np.uint8))
 
 
+@pytest.mark.parametrize('bits', [2, 4, 8])
+def test_codebook_gradient_is_the_segment_sum(bits):
+    """pf_nuq_cluster_grad (+ pf_nuq_weight_quant_ex, codebooks inside one flat parameter buffer): dL/dc_j =
+    alpha * sum_{idx=j} g against the oracle's nuq_grads (learners/nonuniform_quantization/utils.py:303-306, :433)."""
+    rng = np.random.RandomState(10 + bits)
+    shapes = [(3, 3, 16, 16), (1, 1, 64, 64), (3, 3, 5, 7), (300,), (3, 3, 128, 130)]
+    ws = [he(rng, s) for s in shapes]
+    src = [cu(w) for w in ws]
+    dst = [torch.empty_like(s) for s in src]
+    k = 1 << bits
+    base = torch.zeros(16 + len(ws) * (k + 4), dtype=torch.float32, device='cuda:0')     # codebooks at odd offsets
+    views = [base[16 + i * (k + 4):16 + i * (k + 4) + k] for i in range(len(ws))]
+    q = ops.CodebookWeightQuantizer(src, dst, bits, keep_index=True, cluster_views=views, cluster_base=base)
+    q.quantile_init()
+    q.forward()
+    gs = [rng.randn(*s).astype(np.float32) for s in shapes]
+    gdev = [cu(g) for g in gs]
+    gbase = torch.full_like(base, 7.0)
+    q.cluster_grad(gdev, gbase)
+    gb = gbase.cpu().numpy()
+    rngs = q.uq.ranges()
+    for i, (w, g) in enumerate(zip(ws, gs)):
+        rq, rc, ridx = O.nonuniform_quantize(w, bits)
+        assert np.array_equal(views[i].cpu().numpy(), rc) and np.array_equal(dst[i].cpu().numpy(), rq)
+        alpha = np.float32(np.float32(rngs[i][1][0] - rngs[i][0][0]) + np.float32(1e-10))
+        _, gc = O.nuq_grads(g, ridx, k, alpha)
+        got = gb[16 + i * (k + 4):16 + i * (k + 4) + k]
+        assert np.abs(got - gc).max() <= 2e-6 * max(np.abs(gc).max(), 1e-20) * np.sqrt(w.size), i
+    keep = np.ones(gb.size, bool)
+    for i in range(len(ws)):
+        keep[16 + i * (k + 4):16 + i * (k + 4) + k] = False
+    assert np.all(gb[keep] == 7.0)                                       # nothing written outside the codebooks
+    q.cluster_grad(gdev, gbase)
+    assert np.array_equal(gbase.cpu().numpy(), gb)                       # deterministic
+
+
 def test_against_committed_golden_vectors():
     g = np.load(os.path.join(ROOT, 'tests', 'golden', 'hotpath_v1.npz'))
     for mode, kw in (('layer', dict()), ('channel', dict(use_buckets=True, bucket_type='channel')),

