@@ -277,20 +277,22 @@ class StepOracle:
         return out
 
 
-def cpg_layer_regression(orc_full, orc_prnd, state_full, state_prnd, images, conv_full, conv_prnd):
+def cpg_layer_regression(orc_full, orc_prnd, state_full, state_prnd, images, conv_full, conv_prnd, training=True):
     """reg_loss_i = tf.nn.l2_loss(conv_i(full model) - conv_i(pruned model)) on one mini-batch and its gradient w.r.t.
     the pruned model's kernel of that layer (/root/reference/learners/channel_pruning_gpu/learner.py:339-354, :370);
     both models in training mode (forward_train), only the pruned model's BN moving statistics are updated (:283-286).
-    conv_full / conv_prnd: the two Conv2D ops (pocketflow_b200.graph).  Returns (loss, grad, new pruned-model stats)."""
+    conv_full / conv_prnd: the two Conv2D ops (pocketflow_b200.graph).  Returns (loss, grad, new pruned-model stats).
+    training=False: both networks in inference mode — the layer-wise regression of the weight-sparsification learner's
+    pruning-ratio search (learners/weight_sparsification/pr_optimizer.py:166-181 forward_eval, :298-299)."""
     x = torch.from_numpy(np.asarray(images, F32))
     pf = {k: torch.from_numpy(np.array(v, dtype=F32, copy=True)) for k, v in state_full.items()}
     pp = {k: torch.from_numpy(np.array(v, dtype=F32, copy=True)) for k, v in state_prnd.items()}
     kname = conv_prnd.vars['kernel'].name
     pp[kname].requires_grad_(True)
     with torch.no_grad():
-        out_f = orc_full.forward(pf, x, True)[conv_full.output.name]
+        out_f = orc_full.forward(pf, x, training)[conv_full.output.name]
     stats = {}
-    out_p = orc_prnd.forward(pp, x, True, stats)[conv_prnd.output.name]
+    out_p = orc_prnd.forward(pp, x, training, stats)[conv_prnd.output.name]
     loss = ((out_f - out_p) ** 2).sum() / 2
     grad, = torch.autograd.grad(loss, [pp[kname]])
     return F32(loss.item()), grad.numpy().astype(F32), {k: v.numpy().astype(F32) for k, v in stats.items()}

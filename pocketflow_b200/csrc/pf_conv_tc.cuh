@@ -79,7 +79,10 @@ __device__ __forceinline__ void epilogue_tile_t(uint32_t t_acc, uint64_t* tfull,
                                                 const float* __restrict__ extra, const float* __restrict__ bias,
                                                 int relu, int n0, int BN, int Ng, int q, int lane, uint8_t* ring,
                                                 const EpiAff& aff, float my_j, float* __restrict__ jrow,
-                                                int c_begin = 0, int c_step = 32) {
+                                                int c_begin = 0, int c_step = 32,
+                                                const float* __restrict__ aff_tab = nullptr) {
+  // aff_tab (AFF == 2, TMA-fed kernels): the tile's per-column epilogue constants e1[c] (at c) and e2[c] (at 256 + c)
+  // in shared memory, computed once per tile column range instead of being re-derived from global memory per chunk
   // c_begin / c_step: this warp handles the 32-column chunks c_begin, c_begin + c_step, ... (two warps of the same TMEM
   // lane quarter split a tile's columns between them in the TMA-fed kernels: c_step = 64)
   rowoff[lane] = my_row_off;
@@ -94,7 +97,7 @@ __device__ __forceinline__ void epilogue_tile_t(uint32_t t_acc, uint64_t* tfull,
     ro[u] = o < 0 ? -1 : (int)(o >> 2);          // row offsets are multiples of 4 elements (channel counts % 16 == 0)
     jr[u] = (AFF == 2) ? jrow[4 * u + rsub] : 0.f;
   }
-  const float a_s = (AFF && aff.a_scale) ? __ldg(aff.a_scale) : 1.f;
+  const float a_s = (AFF && aff.a_scale && !(AFF == 2 && aff_tab)) ? __ldg(aff.a_scale) : 1.f;
   auto load_extra = [&](int c0, float4 (&xv)[8]) {
     const int cv = c0 + csub;
     const bool cok = cv < BN && n0 + cv + 3 < Ng;
@@ -139,7 +142,12 @@ __device__ __forceinline__ void epilogue_tile_t(uint32_t t_acc, uint64_t* tfull,
     float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
     if (bias && cok) bb = __ldg(reinterpret_cast<const float4*>(bias + n0 + cv));
     float4 e1 = make_float4(a_s, a_s, a_s, a_s), e2 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (AFF == 2) {
+    if (AFF == 2 && aff_tab) {
+      if (cv < BN) {
+        e1 = *reinterpret_cast<const float4*>(aff_tab + cv);
+        e2 = *reinterpret_cast<const float4*>(aff_tab + 256 + cv);
+      }
+    } else if (AFF == 2) {
       float4 al, be;
       if (aff.per_channel) {
         al = cok ? __ldg(reinterpret_cast<const float4*>(aff.w_alpha + n0 + cv)) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -220,10 +228,11 @@ __device__ __forceinline__ void epilogue_tile_a(uint32_t t_acc, uint64_t* tfull,
                                                 float* __restrict__ out, const float* __restrict__ extra,
                                                 const float* __restrict__ bias, int relu, int n0, int BN, int Ng,
                                                 int q, int lane, uint8_t* ring, const EpiAff& aff, float my_j,
-                                                float* jrow, int c_begin = 0, int c_step = 32) {
-  if (extra && ring) epilogue_tile_t<2, AFF>(t_acc, tfull, tempty, parity, zero_tile, my_row_off, rowoff, stg, out, extra, bias, relu, n0, BN, Ng, q, lane, ring, aff, my_j, jrow, c_begin, c_step);
-  else if (extra) epilogue_tile_t<1, AFF>(t_acc, tfull, tempty, parity, zero_tile, my_row_off, rowoff, stg, out, extra, bias, relu, n0, BN, Ng, q, lane, nullptr, aff, my_j, jrow, c_begin, c_step);
-  else epilogue_tile_t<0, AFF>(t_acc, tfull, tempty, parity, zero_tile, my_row_off, rowoff, stg, out, nullptr, bias, relu, n0, BN, Ng, q, lane, nullptr, aff, my_j, jrow, c_begin, c_step);
+                                                float* jrow, int c_begin = 0, int c_step = 32,
+                                                const float* aff_tab = nullptr) {
+  if (extra && ring) epilogue_tile_t<2, AFF>(t_acc, tfull, tempty, parity, zero_tile, my_row_off, rowoff, stg, out, extra, bias, relu, n0, BN, Ng, q, lane, ring, aff, my_j, jrow, c_begin, c_step, aff_tab);
+  else if (extra) epilogue_tile_t<1, AFF>(t_acc, tfull, tempty, parity, zero_tile, my_row_off, rowoff, stg, out, extra, bias, relu, n0, BN, Ng, q, lane, nullptr, aff, my_j, jrow, c_begin, c_step, aff_tab);
+  else epilogue_tile_t<0, AFF>(t_acc, tfull, tempty, parity, zero_tile, my_row_off, rowoff, stg, out, nullptr, bias, relu, n0, BN, Ng, q, lane, nullptr, aff, my_j, jrow, c_begin, c_step, aff_tab);
 }
 __device__ __forceinline__ void epilogue_tile(uint32_t t_acc, uint64_t* tfull, uint64_t* tempty, uint32_t parity,
                                               bool zero_tile, long long my_row_off, long long* rowoff, float* stg,

@@ -63,7 +63,8 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   float* stage_all = reinterpret_cast<float*>(epi);
   long long* rowoff_all = reinterpret_cast<long long*>(stage_all + p.epi_warps * 32 * kStagePitch);
   float* jrow_all = reinterpret_cast<float*>(rowoff_all + p.epi_warps * 32);
-  uint8_t* ring_all = reinterpret_cast<uint8_t*>(jrow_all + p.epi_warps * 32);
+  float* aff_tab = jrow_all + p.epi_warps * 32;               // AFF == 2: e1[256], e2[256] of the current tile columns
+  uint8_t* ring_all = reinterpret_cast<uint8_t*>(aff_tab + (AFF == 2 ? 2 * 256 : 0));
 
   if (tid == 0) {
     for (int s = 0; s < kTmaMaxStages; ++s) {
@@ -154,33 +155,60 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     float* jrow = jrow_all + ew * 32;
     const float* extra = residual ? residual : (p.accumulate ? out : nullptr);
     uint32_t tcount = 0;
+    int tab_n0 = -1;
     for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++tcount) {
       const int mt = (int)fdiv((uint32_t)tile, p.d_ntiles);
       const int n0 = (tile - mt * p.n_tiles) * BN;
       const int m = mt * TM + q * 32 + lane;
       const long long off = m < p.M ? (long long)m * p.Ng : -1;
+      if (AFF == 2 && n0 != tab_n0) {
+        // per-column constants of this tile's columns, once (every epilogue warp walks the same tile sequence, so the
+        // named barrier below is reached by all of them; with one n-tile per row of tiles this runs once per CTA):
+        //   e1[c] = s_a * alpha_c / k_w ,  e2[c] = s_a * (centre * alpha_c / k_w + beta_c)
+        const int nthr = p.epi_warps * 32;
+        asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");          // readers of the previous table are done
+        const float a_s = p.aff.a_scale ? __ldg(p.aff.a_scale) : 1.f;
+        for (int c = ew * 32 + lane; c < BN; c += nthr) {
+          const bool cok = n0 + c < p.Ng;
+          const int bi = p.aff.per_channel ? n0 + c : 0;
+          const float al = cok ? __ldg(p.aff.w_alpha + bi) : 0.f, be = cok ? __ldg(p.aff.w_beta + bi) : 0.f;
+          const float sx = al * p.aff.w_rk;
+          aff_tab[c] = sx * a_s;
+          aff_tab[256 + c] = fmaf(p.aff.w_centre, sx, be) * a_s;
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
+        tab_n0 = n0;
+      }
       float my_j = 0.f;
       if (AFF == 2 && p.csum && m < p.M) {
-        // sum of the stored activation values under this row's filter window, from the per-pixel channel sums
+        // sum of the stored activation levels under this row's filter window, from the per-pixel channel sums: the
+        // (tap, segment) terms are independent loads, issued four at a time (branch-free; the terms are integers below
+        // 2^24, so the order of the additions does not change the result)
         const int img = (int)fdiv((uint32_t)m, p.d_hw);
         const int rem = m - img * p.rows_hw;
         const int y = (int)fdiv((uint32_t)rem, p.d_w), x = rem - y * p.rows_w;
         const int ow0 = p.base_w + x * p.str_w, oh0 = p.base_h + y * p.str_h;
-        for (int r = 0; r < p.R; ++r) {
-          const int ih = oh0 + r;
-          if (ih < 0 || ih >= p.src_h) continue;
-          for (int s_ = 0; s_ < p.S; ++s_) {
-            const int iw = ow0 + s_;
-            if (iw < 0 || iw >= p.src_w) continue;
-            const float* c = p.csum + ((size_t)((size_t)img * p.src_h + ih) * p.src_w + iw) * p.nseg;
-            for (int g = 0; g < p.nseg; ++g) my_j += __ldg(c + g);
-          }
+        const int total = p.R * p.S * p.nseg;
+        const float* cbase = p.csum + (size_t)img * p.src_h * p.src_w * p.nseg;
+        auto term = [&](int u) -> float {
+          if (u >= total) return 0.f;
+          const int t = u / p.nseg, g = u - t * p.nseg;
+          const int r = (int)fdiv((uint32_t)t, p.d_s), s_ = t - r * p.S;
+          const int ih = oh0 + r, iw = ow0 + s_;
+          const bool ok = (unsigned)ih < (unsigned)p.src_h && (unsigned)iw < (unsigned)p.src_w;
+          return ok ? __ldg(cbase + ((size_t)ih * p.src_w + iw) * p.nseg + g) : 0.f;
+        };
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        for (int u = 0; u < total; u += 4) {
+          const float v0 = term(u), v1 = term(u + 1), v2 = term(u + 2), v3 = term(u + 3);
+          a0 += v0; a1 += v1; a2 += v2; a3 += v3;
         }
+        my_j = (a0 + a1) + (a2 + a3);
       }
       epilogue_tile_a<AFF>(tmem_base + (tcount & 1u) * (uint32_t)p.acc_cols, &tfull_bar[tcount & 1u],
                            &tempty_bar[tcount & 1u], (tcount >> 1) & 1u, false, off, rowoff, stg, out, extra, bias, p.relu,
                            n0, BN, p.Ng, q, lane, p.ring ? ring_all + (size_t)ew * kRingDepth * kRingSlotBytes : nullptr,
-                           p.aff, my_j, jrow, 32 * half, 8 * p.epi_warps);
+                           p.aff, my_j, jrow, 32 * half, 8 * p.epi_warps, AFF == 2 ? aff_tab : nullptr);
     }
   }
   tc_fence_before();
@@ -467,7 +495,10 @@ int conv_tma_launch(int pass, const TcGeom& g, const pf_tc_act& a, const pf_tc_w
   // (three with a residual ring) stages still fit beside their staging tiles, else 4
   const int stage_max = p.na * (int)kATileBytes + p.nb * BN * 128;
   const bool has_extra = residual != nullptr || accumulate;
-  auto epi_bytes = [](int warps) { return 1024 + warps * (32 * kStagePitch * 4 + 32 * 8 + 32 * 4) + 256; };
+  const int aff_tab_bytes = aff == 2 ? 2 * 256 * 4 : 0;       // the tile's per-column epilogue constants
+  auto epi_bytes = [aff_tab_bytes](int warps) {
+    return 1024 + warps * (32 * kStagePitch * 4 + 32 * 8 + 32 * 4) + aff_tab_bytes + 256;
+  };
   // 8 epilogue warps unless their staging tiles cost a pipeline stage that 4 warps would leave (below 4 stages)
   const int st8 = (kSmemLimit - epi_bytes(kTmaEpiWarps)) / 1024 * 1024 / stage_max, st4 = (kSmemLimit - epi_bytes(4)) / 1024 * 1024 / stage_max;
   p.epi_warps = (BN >= 64 && st8 >= 2 && (st8 >= 4 || st8 == st4)) ? kTmaEpiWarps : 4;

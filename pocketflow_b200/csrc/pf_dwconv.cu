@@ -6,6 +6,8 @@
 // 2*R*S FLOP per output element against >= 8 bytes of traffic: an HBM-bound kernel (SURVEY §8 a4:
 // "depthwise is bandwidth-bound"), so: one thread per (pixel, 4 channels), 128-bit loads of the
 // R*S taps (neighbouring taps hit L1/L2), no tensor cores.
+#include <stdlib.h>
+
 #include "pf_common.cuh"
 
 namespace {
@@ -292,6 +294,204 @@ dw3x3_wgrad_partial_kernel(const float* __restrict__ x, const float* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Stride-1 3x3, ROW-BLOCKED: a thread produces RB vertically adjacent outputs of its (column, 4 channels) and streams the
+// RB + 2 input rows they share through registers — 3 (RB + 2) loads for RB outputs instead of 9 RB (RB = 4: 4.5 per
+// output), with every row read once per thread.  The 9-loads-per-output form above moved ~3.4x the tensor through
+// L2 -> SM (horizontal neighbours hit L1, the two vertical neighbours did not): 8.3 ms of MobileNet's 25 ms step against
+// 2.4 ms of HBM time (profiles/r1_bench_mobilenet_cpg50_b256_final.json).  Same accumulation order per output as the
+// kernels above (rows r ascending, columns q ascending) for fwd: bit-identical results.
+constexpr int kRB = 4;
+
+__global__ void __launch_bounds__(NT)
+dw3x3s1_fwd_rows_kernel(const float* __restrict__ x, const float* __restrict__ w, DwGeom g, float* __restrict__ y) {
+  const uint32_t C4 = (uint32_t)(g.C >> 2), PB = (uint32_t)(g.P + kRB - 1) / kRB;
+  const uint32_t total = (uint32_t)g.N * PB * g.Q * C4;
+  const uint32_t stride = gridDim.x * NT;
+  uint32_t i = blockIdx.x * NT + threadIdx.x;
+  const int c = (int)((i % C4) << 2);
+  float4 wv[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) wv[t] = __ldg(reinterpret_cast<const float4*>(w + (size_t)t * g.C + c));
+  for (; i < total; i += stride) {
+    const uint32_t pix = i / C4;
+    const uint32_t t1 = pix / (uint32_t)g.Q;
+    const int ow = (int)(pix - t1 * (uint32_t)g.Q);
+    const int n = (int)(t1 / PB);
+    const int oh0 = (int)(t1 - (uint32_t)n * PB) * kRB;
+    const int ih0 = oh0 - g.pt, iw0 = ow - g.pl;
+    const float* xn = x + (size_t)n * g.H * g.W * g.C + c;
+    float4 acc[kRB];
+#pragma unroll
+    for (int j = 0; j < kRB; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int rr = 0; rr < kRB + 2; ++rr) {
+      const int ih = ih0 + rr;
+      const bool okh = ih >= 0 && ih < g.H;
+      float4 xv[3];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int iw = iw0 + q;
+        const bool ok = okh && iw >= 0 && iw < g.W;
+        xv[q] = ok ? __ldg(reinterpret_cast<const float4*>(xn + ((size_t)ih * g.W + iw) * g.C)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < kRB; ++j) {
+        const int r = rr - j;
+        if (r >= 0 && r < 3) {
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            acc[j].x = fmaf(xv[q].x, wv[r * 3 + q].x, acc[j].x); acc[j].y = fmaf(xv[q].y, wv[r * 3 + q].y, acc[j].y);
+            acc[j].z = fmaf(xv[q].z, wv[r * 3 + q].z, acc[j].z); acc[j].w = fmaf(xv[q].w, wv[r * 3 + q].w, acc[j].w);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kRB; ++j)
+      if (oh0 + j < g.P) pf_st_stream(y + (((size_t)n * g.P + oh0 + j) * g.Q + ow) * g.C + c, acc[j]);
+  }
+}
+
+// dx(ih, iw) = sum_{r,q} dy(ih + pt - r, iw + pl - q) w[r][q]: RB input rows per thread, the RB + 2 dy rows they read
+// streamed in ascending order
+__global__ void __launch_bounds__(NT)
+dw3x3s1_dgrad_rows_kernel(const float* __restrict__ dy, const float* __restrict__ w, DwGeom g, int accumulate,
+                          float* __restrict__ dx) {
+  const uint32_t C4 = (uint32_t)(g.C >> 2), HB = (uint32_t)(g.H + kRB - 1) / kRB;
+  const uint32_t total = (uint32_t)g.N * HB * g.W * C4;
+  const uint32_t stride = gridDim.x * NT;
+  uint32_t i = blockIdx.x * NT + threadIdx.x;
+  const int c = (int)((i % C4) << 2);
+  float4 wv[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) wv[t] = __ldg(reinterpret_cast<const float4*>(w + (size_t)t * g.C + c));
+  for (; i < total; i += stride) {
+    const uint32_t pix = i / C4;
+    const uint32_t t1 = pix / (uint32_t)g.W;
+    const int iw = (int)(pix - t1 * (uint32_t)g.W);
+    const int n = (int)(t1 / HB);
+    const int ih0 = (int)(t1 - (uint32_t)n * HB) * kRB;
+    const float* dn = dy + (size_t)n * g.P * g.Q * g.C + c;
+    float4 acc[kRB];
+#pragma unroll
+    for (int j = 0; j < kRB; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int rr = 0; rr < kRB + 2; ++rr) {
+      const int oh = ih0 + g.pt - 2 + rr;
+      const bool okh = oh >= 0 && oh < g.P;
+      float4 dv[3];                                  // dv[q] = dy(oh, iw + pl - q)
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int ow = iw + g.pl - q;
+        const bool ok = okh && ow >= 0 && ow < g.Q;
+        dv[q] = ok ? __ldg(reinterpret_cast<const float4*>(dn + ((size_t)oh * g.Q + ow) * g.C)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < kRB; ++j) {
+        const int r = j + 2 - rr;                    // oh = (ih0 + j) + pt - r
+        if (r >= 0 && r < 3) {
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            acc[j].x = fmaf(dv[q].x, wv[r * 3 + q].x, acc[j].x); acc[j].y = fmaf(dv[q].y, wv[r * 3 + q].y, acc[j].y);
+            acc[j].z = fmaf(dv[q].z, wv[r * 3 + q].z, acc[j].z); acc[j].w = fmaf(dv[q].w, wv[r * 3 + q].w, acc[j].w);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kRB; ++j) {
+      if (ih0 + j >= g.H) continue;
+      float* p = dx + (((size_t)n * g.H + ih0 + j) * g.W + iw) * g.C + c;
+      float4 a = acc[j];
+      if (accumulate) {
+        const float4 o = *reinterpret_cast<const float4*>(p);
+        a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+      }
+      pf_st_stream(p, a);
+    }
+  }
+}
+
+// dw[r,q,c] = sum over outputs of x(oh + r - pt, ow + q - pl) dy(oh, ow): work item = (image, block of RB output rows,
+// column); the RB + 2 input rows are read once per item.  Items are split over blockIdx.y like the pixels above.
+__global__ void __launch_bounds__(NT)
+dw3x3s1_wgrad_rows_kernel(const float* __restrict__ x, const float* __restrict__ dy, DwGeom g, int items_per_split,
+                          float* __restrict__ part) {
+  __shared__ float sh[NT * 4];
+  const int c0 = blockIdx.x * 128;
+  const int tc = min(128, g.C - c0);
+  const int nvec = tc >> 2, nty = NT / nvec;
+  const int tx = threadIdx.x % nvec, ty = threadIdx.x / nvec;
+  const uint32_t PB = (uint32_t)(g.P + kRB - 1) / kRB;
+  const uint32_t nitems = (uint32_t)g.N * PB * g.Q;
+  const uint32_t i0 = blockIdx.y * (uint32_t)items_per_split, i1 = min(nitems, i0 + (uint32_t)items_per_split);
+  float acc[9][4];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
+  const int c = c0 + tx * 4;
+  if (ty < nty) {
+    for (uint32_t it = i0 + ty; it < i1; it += nty) {
+      const uint32_t t1 = it / (uint32_t)g.Q;
+      const int ow = (int)(it - t1 * (uint32_t)g.Q);
+      const int n = (int)(t1 / PB);
+      const int oh0 = (int)(t1 - (uint32_t)n * PB) * kRB;
+      const int ih0 = oh0 - g.pt, iw0 = ow - g.pl;
+      const float* xn = x + (size_t)n * g.H * g.W * g.C + c;
+      float4 dv[kRB];
+#pragma unroll
+      for (int j = 0; j < kRB; ++j)
+        dv[j] = (oh0 + j < g.P) ? pf_ld_stream(dy + (((size_t)n * g.P + oh0 + j) * g.Q + ow) * g.C + c)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int rr = 0; rr < kRB + 2; ++rr) {
+        const int ih = ih0 + rr;
+        const bool okh = ih >= 0 && ih < g.H;
+        float4 xv[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const int iw = iw0 + q;
+          const bool ok = okh && iw >= 0 && iw < g.W;
+          xv[q] = ok ? __ldg(reinterpret_cast<const float4*>(xn + ((size_t)ih * g.W + iw) * g.C)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < kRB; ++j) {
+          const int r = rr - j;
+          if (r >= 0 && r < 3) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+              acc[r * 3 + q][0] = fmaf(xv[q].x, dv[j].x, acc[r * 3 + q][0]); acc[r * 3 + q][1] = fmaf(xv[q].y, dv[j].y, acc[r * 3 + q][1]);
+              acc[r * 3 + q][2] = fmaf(xv[q].z, dv[j].z, acc[r * 3 + q][2]); acc[r * 3 + q][3] = fmaf(xv[q].w, dv[j].w, acc[r * 3 + q][3]);
+            }
+          }
+        }
+      }
+    }
+  }
+  for (int t = 0; t < 9; ++t) {     // combine over ty per tap, fixed order
+    __syncthreads();
+    if (ty < nty) {
+      float* a = &sh[(ty * nvec + tx) * 4];
+      a[0] = acc[t][0]; a[1] = acc[t][1]; a[2] = acc[t][2]; a[3] = acc[t][3];
+    }
+    __syncthreads();
+    for (int cc = threadIdx.x; cc < tc; cc += NT) {
+      float s = 0.f;
+      for (int y = 0; y < nty; ++y) s += sh[(y * nvec + (cc >> 2)) * 4 + (cc & 3)];
+      part[((size_t)blockIdx.y * 9 + t) * g.C + c0 + cc] = s;
+    }
+  }
+}
+
+inline bool dw_rows(const DwGeom& g) {   // the row-blocked stride-1 kernels (PF_DW_ROWS=0: the one-output-per-thread form)
+  static int on = -1;
+  if (on < 0) {
+    const char* v = getenv("PF_DW_ROWS");
+    on = !(v && v[0] == '0');
+  }
+  return on == 1 && g.sh == 1 && g.sw == 1 && g.P >= kRB && g.H >= kRB;
+}
+
 inline bool dw_is3x3(const DwGeom& g) {
   const int c4 = g.C >> 2;
   return g.R == 3 && g.S == 3 && g.sh == g.sw && (g.sh == 1 || g.sh == 2) && c4 > 0 && (NT % c4) == 0 &&
@@ -337,7 +537,10 @@ int pf_dwconv_fwd(const pf_conv_desc* d, const float* x_dev, const float* w_dev,
   if (rc) return rc;
   PF_REQUIRE(x_dev && w_dev && y_dev, "pf_dwconv_fwd: null pointer");
   const unsigned grid = dw_grid((int64_t)g.N * g.P * g.Q * (g.C >> 2));
-  if (dw_is3x3(g) && g.sh == 1) dw3x3_fwd_kernel<1><<<grid, NT, 0, (cudaStream_t)stream>>>(x_dev, w_dev, g, y_dev);
+  if (dw_is3x3(g) && dw_rows(g))
+    dw3x3s1_fwd_rows_kernel<<<dw_grid((int64_t)g.N * ((g.P + kRB - 1) / kRB) * g.Q * (g.C >> 2)), NT, 0, (cudaStream_t)stream>>>(
+        x_dev, w_dev, g, y_dev);
+  else if (dw_is3x3(g) && g.sh == 1) dw3x3_fwd_kernel<1><<<grid, NT, 0, (cudaStream_t)stream>>>(x_dev, w_dev, g, y_dev);
   else if (dw_is3x3(g)) dw3x3_fwd_kernel<2><<<grid, NT, 0, (cudaStream_t)stream>>>(x_dev, w_dev, g, y_dev);
   else dw_fwd_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(x_dev, w_dev, g, y_dev);
   PF_CHECK_LAUNCH("pf_dwconv_fwd");
@@ -351,7 +554,10 @@ int pf_dwconv_dgrad(const pf_conv_desc* d, const float* dy_dev, const float* w_d
   if (rc) return rc;
   PF_REQUIRE(dy_dev && w_dev && dx_dev, "pf_dwconv_dgrad: null pointer");
   const unsigned grid = dw_grid((int64_t)g.N * g.H * g.W * (g.C >> 2));
-  if (dw_is3x3(g) && g.sh == 1) dw3x3_dgrad_kernel<1><<<grid, NT, 0, (cudaStream_t)stream>>>(dy_dev, w_dev, g, accumulate, dx_dev);
+  if (dw_is3x3(g) && dw_rows(g))
+    dw3x3s1_dgrad_rows_kernel<<<dw_grid((int64_t)g.N * ((g.H + kRB - 1) / kRB) * g.W * (g.C >> 2)), NT, 0, (cudaStream_t)stream>>>(
+        dy_dev, w_dev, g, accumulate, dx_dev);
+  else if (dw_is3x3(g) && g.sh == 1) dw3x3_dgrad_kernel<1><<<grid, NT, 0, (cudaStream_t)stream>>>(dy_dev, w_dev, g, accumulate, dx_dev);
   else if (dw_is3x3(g)) dw3x3_dgrad_kernel<2><<<grid, NT, 0, (cudaStream_t)stream>>>(dy_dev, w_dev, g, accumulate, dx_dev);
   else dw_dgrad_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(dy_dev, w_dev, g, accumulate, dx_dev);
   PF_CHECK_LAUNCH("pf_dwconv_dgrad");
@@ -376,7 +582,12 @@ int pf_dwconv_wgrad(const pf_conv_desc* d, const float* x_dev, const float* dy_d
   const int splits = dw_splits(g, &pps);
   dim3 grid((g.C + 127) / 128, splits);
   cudaStream_t st = (cudaStream_t)stream;
-  if (dw_is3x3(g) && g.sh == 1) dw3x3_wgrad_partial_kernel<1><<<grid, NT, 0, st>>>(x_dev, dy_dev, g, pps, ws_dev);
+  if (dw_is3x3(g) && dw_rows(g)) {
+    // same number of splits, over (image, row block, column) items instead of pixels
+    const int nitems = g.N * ((g.P + kRB - 1) / kRB) * g.Q;
+    const int ips = (nitems + splits - 1) / splits;
+    dw3x3s1_wgrad_rows_kernel<<<grid, NT, 0, st>>>(x_dev, dy_dev, g, ips, ws_dev);
+  } else if (dw_is3x3(g) && g.sh == 1) dw3x3_wgrad_partial_kernel<1><<<grid, NT, 0, st>>>(x_dev, dy_dev, g, pps, ws_dev);
   else if (dw_is3x3(g)) dw3x3_wgrad_partial_kernel<2><<<grid, NT, 0, st>>>(x_dev, dy_dev, g, pps, ws_dev);
   else dw_wgrad_partial_kernel<<<grid, NT, 0, st>>>(x_dev, dy_dev, g, pps, ws_dev);
   PF_CHECK_LAUNCH("pf_dwconv_wgrad/partial");

@@ -8,6 +8,7 @@ optimizer slots live in FLAT fp32 buffers so that (a) the data-parallel gradient
 collective over one buffer and (b) the optimizer / mask / weight-decay work is a
 handful of launches instead of ~110 per step.
 """
+import contextlib
 import os
 from collections import OrderedDict
 
@@ -1082,6 +1083,20 @@ class Executor:
             # own gradients: the straight-through estimator of utils.py:303-306)
             with self.timed('weight_quant'):
                 self.wq.cluster_grad([st.view(op.vars['kernel'], self.G) for op in self.wq_ops], self.G)
+
+    @contextlib.contextmanager
+    def standalone_forward(self):
+        """forward() calls outside device_step (layer-wise regression passes): an executor that shares the first layer's
+        im2col columns with the distillation teacher normally lets the teacher's forward fill them — here it fills
+        them itself."""
+        saved = {op: im['compute'] for op, im in self.im2col.items()}
+        for im in self.im2col.values():
+            im['compute'] = True
+        try:
+            yield self
+        finally:
+            for op, c in saved.items():
+                self.im2col[op]['compute'] = c
 
     def layer_wgrad(self, op, gy, dw):
         """dW of ONE Conv2D / MatMul for an externally supplied gradient `gy` of its output, after a training-mode

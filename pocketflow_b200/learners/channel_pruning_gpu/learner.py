@@ -223,7 +223,8 @@ class ChannelPrunedGpuLearner(AbstractLearner):  # pylint: disable=too-many-inst
         op_f, op_p = self.conv_ops_full[idx_layer], self.conv_ops_prnd[idx_layer]
         self.feed(ex, self.iterator_train)
         self.sess_full.forward(training=True, upto=op_f)
-        ex.forward(training=True)
+        with ex.standalone_forward():
+            ex.forward(training=True)
         n = op_p.output.numel
         diff = sel['diff'][:n]
         ops.cpg_diff_l2(ex.buf[op_p.output].reshape(-1), self.sess_full.buf[op_f.output].reshape(-1), diff,

@@ -3,13 +3,15 @@ Zhu & Gupta gradual magnitude pruning.  Masks are rebuilt every ws_mask_update_s
 exact radix select (pf_ws_mask_build); every step the gradient is masked inside the fused
 Momentum kernel (pf_momentum_step)."""
 import os
+import re
 from timeit import default_timer as timer
 
 import numpy as np
 import torch
 
 from ... import graph as G
-from ...engine import Executor
+from ... import ops
+from ...engine import Executor, ParamStore
 from ...flags import FLAGS, DEFINE_string, DEFINE_float, DEFINE_integer
 from ...utils.multi_gpu_wrapper import MultiGpuWrapper as mgw
 from ..abstract_learner import AbstractLearner, latest_checkpoint, load_checkpoint, save_checkpoint
@@ -107,8 +109,9 @@ class WeightSparseLearner(AbstractLearner):  # pylint: disable=too-many-instance
 
     # ------------------------------------------------------------------ what the 'optimal' ratio search drives
     # (pr_optimizer.py:495-548 runs these on a second pair of graphs; here they compose calls of the training step's own
-    # executor.  Deviations, flagged: no layer-wise regression stage (`nb_iters_rg` is ignored), the short fine-tuning
-    # uses this learner's momentum optimizer at --ws_lrn_rate_ft instead of Adam, and BN runs in training mode.)
+    # executor plus a forward-only executor holding the full model.  Deviations, flagged: the short global fine-tuning
+    # uses this learner's momentum optimizer at --ws_lrn_rate_ft instead of Adam, with BN in training mode; the
+    # layer-wise regression stage follows the reference: inference-mode BN, Adam at --ws_lrn_rate_rg, masked gradients.)
     def pr_reset(self):
         """The full (pre-trained) model with every weight alive and a fresh optimizer."""
         ex = self.sess_train
@@ -127,8 +130,78 @@ class WeightSparseLearner(AbstractLearner):  # pylint: disable=too-many-instance
         self.pr_reset()
         self.sess_train.mask_builder.build([float(r) for r in prune_ratios])
 
+    def pr_core_ops(self):
+        """core_ops of __build_layer_rg_ops (pr_optimizer.py:291-296): the ops whose outputs are regressed, paired by
+        index with the maskable variables."""
+        if self.model_name.startswith('mobilenet'):
+            patterns = ['pointwise/Conv2D', 'Conv2d_1c_1x1/Conv2D']
+        else:
+            patterns = ['Conv2D', 'MatMul']
+        return [op for op in self.sess_train.ops if op.name.startswith(self.model_scope)
+                and any(re.search(pt, op.name) is not None for pt in patterns)]
+
+    def pr_regress_layers(self, nb_iters_rg):
+        """Layer-wise regression (pr_optimizer.py:283-314, :542-548): for every core op in turn, nb_iters_rg Adam steps
+        (--ws_lrn_rate_rg) on its kernel, with masked gradients, of l2_loss(out_pruned - out_full) — both networks in
+        inference mode (forward_eval), the full one holding the pre-trained weights.  Returns the losses, [layer][iteration]."""
+        ex = self.sess_train
+        core_ops = self.pr_core_ops()
+        if len(core_ops) != len(self.maskable_vars):
+            raise ValueError('%d core ops for %d maskable variables' % (len(core_ops), len(self.maskable_vars)))
+        if getattr(self, '_pr_full', None) is None:
+            variables = [v for v in self.graph_train.variables.values() if v.name.startswith(self.model_scope + '/')]
+            store = ParamStore(variables, self.device, seed=1)
+            full = Executor(self.graph_train, self.images, ex.logits_t, self.device, store=store, train=False,
+                            update_moving_stats=False)
+            full.buf[self.images] = ex.buf[self.images]
+            nmax = max(op.output.numel for op in core_ops)
+            self._pr_full = dict(ex=full, store=store, diff=torch.empty(nmax, dtype=torch.float32, device=self.device),
+                                 sc=torch.empty(nmax, dtype=torch.float32, device=self.device),
+                                 diff2=torch.empty(nmax, dtype=torch.float32, device=self.device),
+                                 loss=torch.zeros(1, dtype=torch.float32, device=self.device),
+                                 ws=torch.empty(ops.L2_PARTIALS, dtype=torch.float32, device=self.device),
+                                 hp=torch.zeros(4, dtype=torch.float32, device=self.device))
+        st = self._pr_full
+        st['store'].load_state_dict(self._pr_full_state, strict=False)
+        full, world = st['ex'], (mgw.size() if FLAGS.enbl_multi_gpu else 1)
+        losses = []
+        with ex.standalone_forward():
+            for op, var in zip(core_ops, self.maskable_vars):
+                assert op.vars['kernel'] is var, 'core ops and maskable variables are paired by index'
+                w, mask = ex.store.view(var), ex.store.view(var, ex.MASK)
+                grad = ex.store.view(var, ex.G)
+                m_slot, v_slot = torch.zeros_like(w), torch.zeros_like(w)
+                b1p, b2p = np.float32(0.9), np.float32(0.999)
+                n = op.output.numel
+                losses.append([])
+                for _ in range(nb_iters_rg):
+                    self.feed(ex, self.iterator_train)
+                    full.forward(training=False, upto=op)
+                    ex.forward(training=False, upto=op)
+                    diff = st['diff'][:n]
+                    ops.cpg_diff_l2(ex.buf[op.output].reshape(-1), full.buf[op.output].reshape(-1), diff, st['loss'], st['ws'])
+                    if op in ex.fused_add:
+                        # the conv's epilogue added the block's shortcut — out = conv + shortcut in BOTH networks — so the
+                        # difference of the conv outputs is the difference of the sums minus that of the shortcuts
+                        other, sc = ex.fused_add[op][1], st['sc'][:n]
+                        ops.cpg_diff_l2(ex.T(other).reshape(-1), full.T(other).reshape(-1), sc, st['loss'], st['ws'])
+                        ops.cpg_diff_l2(diff, sc, st['diff2'][:n], st['loss'], st['ws'])
+                        diff = st['diff2'][:n]
+                    ex.layer_wgrad(op, diff.view(op.output.shape), grad)
+                    if world > 1:
+                        mgw.allreduce_flat_(grad)
+                        grad.mul_(1.0 / world)
+                    ops.mul(grad, mask, grad)
+                    st['hp'].copy_(torch.tensor([FLAGS.ws_lrn_rate_rg, b1p, b2p, 0.0], dtype=torch.float32))
+                    ops.adam_step(w.reshape(-1), m_slot.reshape(-1), v_slot.reshape(-1), grad.reshape(-1), st['hp'])
+                    b1p, b2p = np.float32(b1p * np.float32(0.9)), np.float32(b2p * np.float32(0.999))
+                    losses[-1].append(float(st['loss'].item()))
+        return losses
+
     def pr_retrain(self, nb_iters_rg, nb_iters_ft):
         ex = self.sess_train
+        if nb_iters_rg > 0:
+            self.pr_regress_layers(nb_iters_rg)
         for _ in range(nb_iters_ft):
             self.feed(ex, self.iterator_train)
             ex.run_step(FLAGS.ws_lrn_rate_ft, self.grad_allreduce())

@@ -6,9 +6,10 @@ the maskable layers in order, maps the actor's action to a pruning ratio that ke
 (RLHelper), prunes the pre-trained model at those ratios, retrains briefly and takes the validation accuracy as the
 reward of every transition.  The device half is reached through a `tuner` object (the WeightSparseLearner):
 `pr_prune(ratios)` (restore the full model, mask it), `pr_retrain(nb_iters_rg, nb_iters_ft)`,
-`pr_evaluate() -> (loss, {metric: value})`.  The learner implements them on its own training step — WITHOUT the
-reference's layer-wise regression stage (:232-257: regressing every pruned layer's output onto the full model's needs
-paired full / pruned graphs that are not built), see the deviations listed there.  The ratios and the reward travel
+`pr_evaluate() -> (loss, {metric: value})`.  The learner implements them on its own training step, with the layer-wise
+regression stage (:283-314, :542-548: every pruned layer's output regressed onto the full model's, Adam, masked
+gradients, inference-mode BN) on a forward-only copy of the full model; see the deviations of the global fine-tuning
+listed there.  The ratios and the reward travel
 between ranks by broadcast instead of the reference's ./ws.prune.ratios and ./ws.reward files."""
 import math
 

@@ -298,7 +298,7 @@ def test_mobilenet_channel_pruned_step_on_tensor_core_path():
     assert len(ex.tc) >= 13
     lrn.init_from_full()
     lrn.choose_channels(nb_iters_layer=2)                  # a short run of the selection phase: 50 % input-channel masks
-    assert abs(lrn.pr_maskable() - 0.5) < 0.1
+    assert 0.3 < lrn.pr_maskable() < 0.5                   # head and tail layers (1/4 of the maskable weights) stay dense
     masks = {v.name: ex.store.view(v, ex.MASK).cpu().numpy().copy() for v in lrn.maskable_vars}
     orc = StepOracle(ex.ops, ex.logits_t, lrn.images, lrn.labels, ex.loss)
     state = ex.store.state_dict()

@@ -397,8 +397,12 @@ def test_ws_learner_search_hooks_compose_the_executor_calls(tmp_path):
     assert log == restore + [('build', [0.0, 0.5, 0.25])] + restore + [('build', [0.1, 0.1, 0.1])]
     del log[:]
     FLAGS.ws_lrn_rate_ft = 3e-4
+    me.pr_regress_layers = lambda n: log.append(('regress', n))
     L.pr_retrain(me, 20, 3)
-    assert log == [('feed', 'it'), ('step', 3e-4, None)] * 3                      # (no layer-wise regression stage)
+    assert log == [('regress', 20)] + [('feed', 'it'), ('step', 3e-4, None)] * 3   # layer-wise regression, then fine-tuning
+    del log[:]
+    L.pr_retrain(me, 0, 1)
+    assert log == [('feed', 'it'), ('step', 3e-4, None)]
     del log[:]
     FLAGS.ws_nb_iters_feval = 2
     assert L.pr_evaluate(me) == (1.5, {'accuracy': 0.5})

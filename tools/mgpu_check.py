@@ -51,9 +51,9 @@ def main():
     assert bk is not None and 0 < bk['split'] < bk['end'] <= ex.G.numel(), bk
     os.environ['PF_AR_BUCKETS'] = '1'
     lrn1 = UniformQuantLearner(None, R.ModelHelper())
-    del os.environ['PF_AR_BUCKETS']
     ex1 = lrn1.sess_train
-    assert ex1._bucket_plan() is None
+    assert ex1._bucket_plan() is None            # (decided once per executor, while the variable is set)
+    del os.environ['PF_AR_BUCKETS']
     ex1.store.P.copy_(P0)
     ex1.store.O.copy_(O0)
     ex1.teacher.store.P.copy_(ex.teacher.store.P)
