@@ -311,7 +311,7 @@ typedef struct pf_tc_prep_seg {
 int pf_conv2d_tc_prep_weights_multi(const pf_tc_prep_seg* segs_dev, const pf_work* work_dev, int n_work, void* stream);
 /* dw = x (*) dy on the tensor cores (MN-major operands, split-K with a fixed-order reduction).
  * Requires Cin % 16 == 0 and Cout % 64 == 0; ws_dev: pf_conv2d_tc_wgrad_workspace_bytes(d) bytes. */
-#define PF_CONV_TC_WGRAD_MAX_SPLITS 64
+#define PF_CONV_TC_WGRAD_MAX_SPLITS 148
 int pf_conv2d_tc_wgrad_supported(const pf_conv_desc* d);
 int64_t pf_conv2d_tc_wgrad_workspace_bytes(const pf_conv_desc* d);
 int pf_conv2d_tc_wgrad(const pf_conv_desc* d, const float* x_dev, const float* dy_dev, float* ws_dev,

@@ -72,7 +72,7 @@ struct EpiAff {
   float w_rk, w_centre;    // 1 / (2^bits - 1), level subtracted from the stored weight levels
 };
 
-template <int EXTRA, int AFF>
+template <int EXTRA, int AFF, int RD = kRingDepth>
 __device__ __forceinline__ void epilogue_tile_t(uint32_t t_acc, uint64_t* tfull, uint64_t* tempty, uint32_t parity,
                                                 bool zero_tile, long long my_row_off, long long* __restrict__ rowoff,
                                                 float* __restrict__ stg, float* __restrict__ out,
@@ -113,7 +113,7 @@ __device__ __forceinline__ void epilogue_tile_t(uint32_t t_acc, uint64_t* tfull,
     if (c0 < BN) {
       const int cv = c0 + csub;
       const bool cok = cv < BN && n0 + cv + 3 < Ng;
-      const uint32_t slot = ring_u32 + (uint32_t)(it & (kRingDepth - 1)) * kRingSlotBytes;
+      const uint32_t slot = ring_u32 + (uint32_t)(it & (RD - 1)) * kRingSlotBytes;
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const bool ok = cok && ro[u] >= 0;
@@ -128,7 +128,7 @@ __device__ __forceinline__ void epilogue_tile_t(uint32_t t_acc, uint64_t* tfull,
   if (EXTRA == 1) load_extra(c_begin, xa);
   if (EXTRA == 2) {
 #pragma unroll
-    for (int c = 0; c < kRingDepth; ++c) ring_issue(c_begin + c_step * c, c);
+    for (int c = 0; c < RD; ++c) ring_issue(c_begin + c_step * c, c);
   }
   mbar_wait_bounded(tfull, parity);
   tc_fence_after();
@@ -178,8 +178,8 @@ __device__ __forceinline__ void epilogue_tile_t(uint32_t t_acc, uint64_t* tfull,
       *reinterpret_cast<uint4*>(stg + lane * kStagePitch + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
     __syncwarp();
     if (EXTRA == 1 && c0 + c_step < BN) load_extra(c0 + c_step, xb);
-    if (EXTRA == 2) asm volatile("cp.async.wait_group %0;" ::"n"(kRingDepth - 1) : "memory");   // chunk c0 has landed
-    const float* slot = reinterpret_cast<const float*>(ring + (size_t)(it & (kRingDepth - 1)) * kRingSlotBytes);
+    if (EXTRA == 2) asm volatile("cp.async.wait_group %0;" ::"n"(RD - 1) : "memory");   // chunk c0 has landed
+    const float* slot = reinterpret_cast<const float*>(ring + (size_t)(it & (RD - 1)) * kRingSlotBytes);
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       float4 v[4], xr[4];
@@ -213,7 +213,7 @@ __device__ __forceinline__ void epilogue_tile_t(uint32_t t_acc, uint64_t* tfull,
 #pragma unroll
       for (int u = 0; u < 8; ++u) xa[u] = xb[u];
     }
-    if (EXTRA == 2) ring_issue(c0 + c_step * kRingDepth, it + kRingDepth);   // refill the slot just consumed
+    if (EXTRA == 2) ring_issue(c0 + c_step * RD, it + RD);   // refill the slot just consumed
   }
   if (EXTRA == 2) asm volatile("cp.async.wait_group 0;" ::: "memory");
   if (c_begin >= BN) {                           // no chunk for this warp (BN < 64): release the accumulator all the same
@@ -229,8 +229,9 @@ __device__ __forceinline__ void epilogue_tile_a(uint32_t t_acc, uint64_t* tfull,
                                                 const float* __restrict__ bias, int relu, int n0, int BN, int Ng,
                                                 int q, int lane, uint8_t* ring, const EpiAff& aff, float my_j,
                                                 float* jrow, int c_begin = 0, int c_step = 32,
-                                                const float* aff_tab = nullptr) {
-  if (extra && ring) epilogue_tile_t<2, AFF>(t_acc, tfull, tempty, parity, zero_tile, my_row_off, rowoff, stg, out, extra, bias, relu, n0, BN, Ng, q, lane, ring, aff, my_j, jrow, c_begin, c_step, aff_tab);
+                                                const float* aff_tab = nullptr, int ring_depth = kRingDepth) {
+  if (extra && ring && ring_depth == 2) epilogue_tile_t<2, AFF, 2>(t_acc, tfull, tempty, parity, zero_tile, my_row_off, rowoff, stg, out, extra, bias, relu, n0, BN, Ng, q, lane, ring, aff, my_j, jrow, c_begin, c_step, aff_tab);
+  else if (extra && ring) epilogue_tile_t<2, AFF>(t_acc, tfull, tempty, parity, zero_tile, my_row_off, rowoff, stg, out, extra, bias, relu, n0, BN, Ng, q, lane, ring, aff, my_j, jrow, c_begin, c_step, aff_tab);
   else if (extra) epilogue_tile_t<1, AFF>(t_acc, tfull, tempty, parity, zero_tile, my_row_off, rowoff, stg, out, extra, bias, relu, n0, BN, Ng, q, lane, nullptr, aff, my_j, jrow, c_begin, c_step, aff_tab);
   else epilogue_tile_t<0, AFF>(t_acc, tfull, tempty, parity, zero_tile, my_row_off, rowoff, stg, out, nullptr, bias, relu, n0, BN, Ng, q, lane, nullptr, aff, my_j, jrow, c_begin, c_step, aff_tab);
 }

@@ -30,7 +30,7 @@ struct TmaP {
   int src_h, src_w;                        // gathered tensor
   int base_w, base_h, str_w, str_h, flip;  // window origin of row (y, x): (base + x * str); flip: tap offsets mirrored
   int na, nb;                              // operand planes (na: upper bound when a_hdr decides)
-  int accumulate, relu, ring, stage_budget, epi_warps;
+  int accumulate, relu, ring, stage_budget, epi_warps;     // ring: 0 = none, else the residual ring's depth (2 or 4)
   FastDiv d_hw, d_w, d_ntiles, d_cblocks, d_s;
   EpiAff aff;
   const pf_tc_act_hdr* a_hdr;
@@ -207,8 +207,8 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       }
       epilogue_tile_a<AFF>(tmem_base + (tcount & 1u) * (uint32_t)p.acc_cols, &tfull_bar[tcount & 1u],
                            &tempty_bar[tcount & 1u], (tcount >> 1) & 1u, false, off, rowoff, stg, out, extra, bias, p.relu,
-                           n0, BN, p.Ng, q, lane, p.ring ? ring_all + (size_t)ew * kRingDepth * kRingSlotBytes : nullptr,
-                           p.aff, my_j, jrow, 32 * half, 8 * p.epi_warps, AFF == 2 ? aff_tab : nullptr);
+                           n0, BN, p.Ng, q, lane, p.ring ? ring_all + (size_t)ew * p.ring * kRingSlotBytes : nullptr,
+                           p.aff, my_j, jrow, 32 * half, 8 * p.epi_warps, AFF == 2 ? aff_tab : nullptr, p.ring);
     }
   }
   tc_fence_before();
@@ -503,18 +503,22 @@ int conv_tma_launch(int pass, const TcGeom& g, const pf_tc_act& a, const pf_tc_w
   const int st8 = (kSmemLimit - epi_bytes(kTmaEpiWarps)) / 1024 * 1024 / stage_max, st4 = (kSmemLimit - epi_bytes(4)) / 1024 * 1024 / stage_max;
   p.epi_warps = (BN >= 64 && st8 >= 2 && (st8 >= 4 || st8 == st4)) ? kTmaEpiWarps : 4;
   p.epi_warps = env_int("PF_TC_EPI_WARPS", p.epi_warps) == 4 ? 4 : p.epi_warps;
-  int ring_bytes = p.epi_warps * kRingDepth * kRingSlotBytes;
+  // the residual / accumulate operand streams through a per-warp cp.async ring of 4 (else 2) 4 KB chunks when the
+  // pipeline keeps enough stages beside it: 3, or nk + 1 for the short reductions of the 1x1 layers (a 64 -> 256 layer
+  // has ONE k-stage per tile: two stages already let the next tile's loads fly during this tile's MMAs)
   int budget = (kSmemLimit - epi_bytes(p.epi_warps)) / 1024 * 1024;
+  int ring_bytes = 0;
   p.ring = 0;
   if (has_extra && env_int("PF_TC_RING", 1) && BN >= 64) {
-    if ((budget - ring_bytes) / stage_max < 3 && p.epi_warps == kTmaEpiWarps) {       // try the ring with 4 warps
-      const int b4 = (kSmemLimit - epi_bytes(4)) / 1024 * 1024, r4 = 4 * kRingDepth * kRingSlotBytes;
-      if ((b4 - r4) / stage_max >= 3 && env_int("PF_TC_RING_PREFER", 0)) { p.epi_warps = 4; budget = b4; ring_bytes = r4; }
+    const int need = std::min(3, p.nk + 1);
+    for (int depth = kRingDepth; depth >= 2 && !p.ring; depth >>= 1) {
+      const int rb = p.epi_warps * depth * kRingSlotBytes;
+      if ((budget - rb) / stage_max >= need) {
+        p.ring = depth;
+        ring_bytes = rb;
+      }
     }
-    if ((budget - ring_bytes) / stage_max >= 3) {
-      p.ring = 1;
-      budget = (kSmemLimit - epi_bytes(p.epi_warps) - ring_bytes) / 1024 * 1024;
-    }
+    if (p.ring) budget = (kSmemLimit - epi_bytes(p.epi_warps) - ring_bytes) / 1024 * 1024;
   }
   PF_REQUIRE(budget / stage_max >= 2 || p.nk <= 1, "%s: shared-memory plan failed (BN %d)", who, BN);
   p.stage_budget = budget;

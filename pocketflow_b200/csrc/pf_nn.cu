@@ -299,6 +299,11 @@ bn_apply_kernel(const float* __restrict__ x, int64_t total, int C, const float* 
 // the stored plane values over channel segments of min(C, 128) — the rank-1 term the weight quantizer's offset needs
 // (pf_conv_tma.cu).  One warp owns whole segments (C a power of two >= 16), reduced by a fixed xor butterfly: the sums
 // are deterministic, and exact for levels.  HBM traffic: 4 B read + 2 B (levels) or 4 B (planes) written per element.
+// LEVELS_ONLY: no fp32 output wanted and the operand CAN travel as levels (host: bits <= 8) — the dequantized value is
+// then never formed (the level alone is 13 fp32 ops per element against 21; the general form ran at 3.4 TB/s on the
+// 822 MB tensors of stage 1, issue-bound).  A range that does not start at 0 (device-side condition) falls back to the
+// general path inside the same kernel.
+template <bool LEVELS_ONLY>
 __global__ void __launch_bounds__(NT)
 bn_apply_levels_kernel(const float* __restrict__ x, int64_t total, int C, int cshift, const float* __restrict__ mean,
                        const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -325,15 +330,22 @@ bn_apply_levels_kernel(const float* __restrict__ x, int64_t total, int C, int cs
   const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
   auto emit = [&](float4 v, int64_t i, bool valid) {
     float4 lv;
-    v.x = pf_fake_quant_lv(bn_act(v.x, mu.x, rs.x, ga.x, be.x, act), q_alpha, q_beta, q_k, q_ra, q_rk, lv.x);
-    v.y = pf_fake_quant_lv(bn_act(v.y, mu.y, rs.y, ga.y, be.y, act), q_alpha, q_beta, q_k, q_ra, q_rk, lv.y);
-    v.z = pf_fake_quant_lv(bn_act(v.z, mu.z, rs.z, ga.z, be.z, act), q_alpha, q_beta, q_k, q_ra, q_rk, lv.z);
-    v.w = pf_fake_quant_lv(bn_act(v.w, mu.w, rs.w, ga.w, be.w, act), q_alpha, q_beta, q_k, q_ra, q_rk, lv.w);
+    if (LEVELS_ONLY && lev) {
+      lv.x = pf_quant_level(bn_act(v.x, mu.x, rs.x, ga.x, be.x, act), q_alpha, q_beta, q_k, q_ra);
+      lv.y = pf_quant_level(bn_act(v.y, mu.y, rs.y, ga.y, be.y, act), q_alpha, q_beta, q_k, q_ra);
+      lv.z = pf_quant_level(bn_act(v.z, mu.z, rs.z, ga.z, be.z, act), q_alpha, q_beta, q_k, q_ra);
+      lv.w = pf_quant_level(bn_act(v.w, mu.w, rs.w, ga.w, be.w, act), q_alpha, q_beta, q_k, q_ra);
+    } else {
+      v.x = pf_fake_quant_lv(bn_act(v.x, mu.x, rs.x, ga.x, be.x, act), q_alpha, q_beta, q_k, q_ra, q_rk, lv.x);
+      v.y = pf_fake_quant_lv(bn_act(v.y, mu.y, rs.y, ga.y, be.y, act), q_alpha, q_beta, q_k, q_ra, q_rk, lv.y);
+      v.z = pf_fake_quant_lv(bn_act(v.z, mu.z, rs.z, ga.z, be.z, act), q_alpha, q_beta, q_k, q_ra, q_rk, lv.z);
+      v.w = pf_fake_quant_lv(bn_act(v.w, mu.w, rs.w, ga.w, be.w, act), q_alpha, q_beta, q_k, q_ra, q_rk, lv.w);
+    }
     const float4 s = lev ? lv : v;
     float part = 0.f;
     if (valid) {
       const int64_t e = i << 2;
-      if (y) pf_st_stream(y + e, v);
+      if (!LEVELS_ONLY && y) pf_st_stream(y + e, v);
       if (lev) {
         const __nv_bfloat162 a = __floats2bfloat162_rn(s.x, s.y), b = __floats2bfloat162_rn(s.z, s.w);
         *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p0) + e) =
@@ -942,9 +954,14 @@ int pf_bn_apply_quant_levels(const float* x_dev, int64_t m, int c, const float* 
   // grid: a multiple of (C/4)/gcd(C/4, NT) blocks so that every thread keeps its 4 channels (C/4 <= NT * 64 here)
   unsigned grid = chan_grid(total >> 2, c);
   PF_REQUIRE(((int64_t)grid * NT) % (c >> 2) == 0, "pf_bn_apply_quant_levels: C = %d too large for the channel-stationary grid", c);
-  bn_apply_levels_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(x_dev, total, c, cshift, mean_dev, rstd_dev, gamma_dev, beta_dev,
-                                                               act, y_dev, plane0_dev, plane1_dev, range_enc_dev, bits, hdr_dev,
-                                                               csum_dev, nseg);
+  if (y_dev == nullptr && bits <= 8)
+    bn_apply_levels_kernel<true><<<grid, NT, 0, (cudaStream_t)stream>>>(x_dev, total, c, cshift, mean_dev, rstd_dev, gamma_dev,
+                                                                       beta_dev, act, nullptr, plane0_dev, plane1_dev,
+                                                                       range_enc_dev, bits, hdr_dev, csum_dev, nseg);
+  else
+    bn_apply_levels_kernel<false><<<grid, NT, 0, (cudaStream_t)stream>>>(x_dev, total, c, cshift, mean_dev, rstd_dev, gamma_dev,
+                                                                        beta_dev, act, y_dev, plane0_dev, plane1_dev,
+                                                                        range_enc_dev, bits, hdr_dev, csum_dev, nseg);
   PF_CHECK_LAUNCH("pf_bn_apply_quant_levels");
   return PF_OK;
 }

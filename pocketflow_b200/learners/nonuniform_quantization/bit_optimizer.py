@@ -1,11 +1,13 @@
 """Bit allocation for the NonUniformQuantLearner (/root/reference/learners/nonuniform_quantization/bit_optimizer.py).
 
-Without the RL agent every layer gets the flag values (:135-142) — that is what this build provides.  The roll-out
-search is the uniform learner's loop with `nuql_*` flags upstream; it is not wired here because a new bit-width changes
-the SIZE of a layer's codebook, so every roll-out would have to re-run the quantile initialisation on the restored
-weights before fine-tuning (a device-side step that needs a GPU to validate).  The flags are declared so that the
-reference's command lines parse."""
-from ...flags import FLAGS, DEFINE_boolean, DEFINE_integer, DEFINE_string
+Without the RL agent every layer gets the flag values (:135-142).  With `--nuql_enbl_rl_agent` the search is the uniform
+learner's roll-out loop on the `nuql_*` flags (the two reference files differ in flag names, `tune_global_steps` and
+one initialisation op): the DDPG agent proposes per-layer bit-widths under the `nuql_equivalent_bits` budget, every
+roll-out restores the pre-trained weights, sets the bit-widths — a new bit-width changes the SIZE of a layer's
+codebook, so the codebooks are re-fitted to the restored weights by the quantile initialisation, as the reference's
+`cluster_init` does after its restore (:200-206) — fine-tunes and scores on the evaluation split."""
+from ...flags import DEFINE_boolean, DEFINE_integer, DEFINE_string
+from ..uniform_quantization.bit_optimizer import BitOptimizer as UniformBitOptimizer
 
 DEFINE_integer('nuql_equivalent_bits', 4, 'average number of bits per weight the RL search may spend')
 DEFINE_integer('nuql_nb_rlouts', 200, 'number of roll-outs of the RL search')
@@ -21,12 +23,5 @@ DEFINE_boolean('nuql_enbl_rl_global_tune', True, 'fine-tune all layers before a 
 DEFINE_boolean('nuql_enbl_rl_layerwise_tune', False, 'fine-tune layer by layer before a roll-out is scored')
 
 
-class BitOptimizer(object):
-    def __init__(self, nb_matmuls, nb_activations):
-        self.nb_matmuls, self.nb_activations = nb_matmuls, nb_activations
-
-    def run(self):
-        if FLAGS.nuql_enbl_rl_agent:
-            raise NotImplementedError('--nuql_enbl_rl_agent: the RL bit search is built for the uniform learner only '
-                                      '(codebooks would have to be re-initialised per roll-out)')
-        return [FLAGS.nuql_weight_bits] * self.nb_matmuls, [FLAGS.nuql_activation_bits] * self.nb_activations
+class BitOptimizer(UniformBitOptimizer):
+    PREFIX = 'nuql'

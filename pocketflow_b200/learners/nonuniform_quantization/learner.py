@@ -1,6 +1,7 @@
 """Non-Uniform Quantization Learner (/root/reference/learners/nonuniform_quantization/learner.py:33-520),
 'weights' optimisation mode: a 2^b-entry codebook per layer, quantile-initialised AFTER the weights
 are in place (learner.py:127-129), frozen; weights trained with Adam through the STE."""
+import os
 from timeit import default_timer as timer
 
 import numpy as np
@@ -10,7 +11,7 @@ from ...engine import Executor
 from ...flags import FLAGS, DEFINE_integer, DEFINE_boolean, DEFINE_string
 from ...utils.multi_gpu_wrapper import MultiGpuWrapper as mgw
 from ...utils.lrn_rate_utils import piecewise_constant
-from ..abstract_learner import AbstractLearner, save_checkpoint
+from ..abstract_learner import AbstractLearner, latest_checkpoint, load_checkpoint, save_checkpoint
 from ..distillation_helper import DistillationHelper
 from .utils import NonUniformQuantization
 from .bit_optimizer import BitOptimizer
@@ -65,7 +66,20 @@ class NonUniformQuantLearner(AbstractLearner):
         if FLAGS.enbl_dst:
             self.helper_dst = DistillationHelper(sm_writer, model_helper, self.mpi_comm)
         self.statistics = {}
+        self._rl_initial_state = None
+        if FLAGS.nuql_enbl_rl_agent and FLAGS.nuql_opt_mode != 'weights':
+            raise NotImplementedError('--nuql_enbl_rl_agent searches bit-widths in the \'weights\' optimisation mode only')
         self.__build_train()
+        if FLAGS.nuql_enbl_rl_agent:
+            # the step is compiled with the flag bit-widths; the search drives that step with per-roll-out bit-widths
+            # and leaves the best allocation in place (learner.py:95-116)
+            self.auto_barrier()
+            bit_optimizer = BitOptimizer(self.dataset_name, self.weights, self.statistics, tuner=self,
+                                         barrier_fn=self.auto_barrier)
+            self.optimal_w_bit_list, self.optimal_a_bit_list = bit_optimizer.run()
+            self.rl_restore()
+            self.rl_set_bits(self.optimal_w_bit_list, self.optimal_a_bit_list)
+            self.auto_barrier()
 
     def train(self, nb_iters=None):
         total = self.finetune_steps if nb_iters is None else nb_iters
@@ -119,6 +133,47 @@ class NonUniformQuantLearner(AbstractLearner):
             out.append(ex.fetch_losses()['loss'])
         return float(np.mean(out))
 
+    # ------------------------------------------------------------------ what the RL bit search drives
+    def rl_restore(self):
+        """Back to the pre-trained weights with a fresh optimizer (bit_optimizer.py:200-206): the latest checkpoint under
+        --save_path if there is one, else the state this learner was built with."""
+        ex = self.sess_train
+        if self._rl_initial_state is None:
+            ckpt_dir = os.path.dirname(FLAGS.save_path)
+            fn = latest_checkpoint(ckpt_dir) if os.path.isdir(ckpt_dir) else None
+            self._rl_initial_state = load_checkpoint(fn) if fn is not None else ex.store.state_dict()
+        ex.store.load_state_dict(self._rl_initial_state, strict=False)
+        ex.reset_optimizer_state()
+        if FLAGS.enbl_multi_gpu:
+            mgw.broadcast_global_variables([ex.store.P, ex.store.O])
+
+    def rl_set_bits(self, w_bits, a_bits):
+        """New bit-widths, then the codebooks re-fitted to the (restored) weights: a layer's codebook has 2^bits entries"""
+        self.sess_train.set_quant_bits(w_bits, a_bits)
+        self.cluster_init()
+
+    def rl_finetune(self, nb_steps, disp_steps):
+        for t_step in range(nb_steps):
+            self.train_step()
+            if disp_steps and (t_step + 1) % disp_steps == 0 and self.is_primary_worker():
+                r = self.sess_train.fetch_losses()
+                print('iter #%d: model_loss = %.4f | loss = %.4f | acc_top1 = %.4f'
+                      % (t_step + 1, r['model_loss'], r['loss'], r['acc_top1']))
+        self.sess_train.step_count = 0
+
+    def rl_evaluate(self):
+        """(loss, top-1, top-5) averaged over nb_smpls_eval // batch_size_eval mini-batches"""
+        ex = self.sess_train
+        rows = []
+        bs = self.iterator_train.batch_size if FLAGS.data_dir_local else FLAGS.batch_size_eval
+        for _ in range(max(1, FLAGS.nb_smpls_eval // bs)):
+            self.feed(ex, self.eval_iterator())
+            ex.forward_eval_loss()
+            r = ex.fetch_losses()
+            rows.append((r['loss'], r['acc_top1'], r['acc_top5']))
+        loss, top1, top5 = [float(v) for v in np.mean(np.array(rows, np.float64), axis=0)]
+        return loss, top1, top5
+
     def cluster_init(self):
         """ops['cluster_init'] (learner.py:127-129, 297-298): run AFTER the weights are restored."""
         self.sess_train.wq.quantile_init()
@@ -138,10 +193,14 @@ class NonUniformQuantLearner(AbstractLearner):
                     self.weights = self.weights[1:-1]
                 self.statistics['num_weights'] = [v.numel for v in self.weights]
                 nq = NonUniformQuantization(self.graph_train, FLAGS.nuql_bucket_size, FLAGS.nuql_use_buckets,
-                                            FLAGS.nuql_init_style, FLAGS.nuql_bucket_type)
+                                            FLAGS.nuql_init_style, FLAGS.nuql_bucket_type,
+                                            codebook_bits_cap=FLAGS.nuql_w_bit_max if FLAGS.nuql_enbl_rl_agent else None)
                 matmul_ops = nq.search_matmul_op(FLAGS.nuql_quantize_all_layers)
                 act_ops = nq.search_activation_op()
-                w_bits, a_bits = BitOptimizer(len(matmul_ops), len(act_ops)).run()
+                self.statistics['nb_matmuls'], self.statistics['nb_activations'] = len(matmul_ops), len(act_ops)
+                w_bits = [FLAGS.nuql_weight_bits] * len(matmul_ops)
+                a_bits = [FLAGS.nuql_activation_bits] * len(act_ops)
+                self.optimal_w_bit_list, self.optimal_a_bit_list = w_bits, a_bits
                 nq.insert_quant_op_for_weights({op.name: b for op, b in zip(matmul_ops, w_bits)})
                 nq.insert_quant_op_for_activations({op.name: b for op, b in zip(act_ops, a_bits)})
                 # "Strictly speaking, clusters should be not included for regularization" (learner.py:219-220): they are

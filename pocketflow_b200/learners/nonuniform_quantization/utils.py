@@ -8,8 +8,12 @@ from ..uniform_quantization.utils import prefix_filter
 
 class NonUniformQuantization:
     # pylint: disable=too-many-instance-attributes
-    def __init__(self, sess, bucket_size=0, use_buckets=False, init_style='quantile', bucket_type='split'):
+    def __init__(self, sess, bucket_size=0, use_buckets=False, init_style='quantile', bucket_type='split',
+                 codebook_bits_cap=None):
+        """codebook_bits_cap: size the codebook variables for this many bits (the RL bit search changes a layer's
+        bit-width at run time; its codebook then uses the first 2^bits entries)."""
         self.sess = sess
+        self.codebook_bits_cap = codebook_bits_cap
         self.use_buckets = use_buckets
         self.bucket_size = bucket_size
         self.bucket_type = bucket_type
@@ -58,7 +62,7 @@ class NonUniformQuantization:
             self.weight_bits.append(bits)
             if op.type != 'DepthwiseConv2dNative' and bits <= 8:
                 name = g.scope_prefix() + prefix_filter(op.name) + '/nonuniform_quantize/clusters'
-                op.vars['clusters'] = g.get_variable(name, (2 ** bits,), lambda rng, shape: np.zeros(shape, np.float32),
+                op.vars['clusters'] = g.get_variable(name, (2 ** max(bits, self.codebook_bits_cap or 0),), lambda rng, shape: np.zeros(shape, np.float32),
                                                      trainable=True)
 
     def insert_quant_op_for_activations(self, act_bit_dict):

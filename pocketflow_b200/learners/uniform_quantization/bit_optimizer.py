@@ -49,6 +49,10 @@ def broadcast_list(values, length, device='cpu'):
 
 class BitOptimizer(object):  # pylint: disable=too-many-instance-attributes
     """Currently only weight bits are inferred via RL; activations stay at 32 bits during the search."""
+    PREFIX = 'uql'       # the non-uniform learner's optimizer is this class on the nuql_* flags
+
+    def _f(self, name):
+        return getattr(FLAGS, '%s_%s' % (self.PREFIX, name))
 
     def __init__(self, dataset_name, weights, statistics, tuner=None, barrier_fn=None, seed=None):
         """weights: the kernels to quantize (objects with .shape); statistics: the learner's dict ('num_weights',
@@ -60,32 +64,35 @@ class BitOptimizer(object):  # pylint: disable=too-many-instance-attributes
         self.auto_barrier = barrier_fn or (lambda: None)
         self.nb_matmuls = statistics['nb_matmuls']
         self.nb_activations = statistics['nb_activations']
-        if not FLAGS.uql_enbl_rl_agent:
+        if not self._f('enbl_rl_agent'):
             return
         if tuner is None:
             raise ValueError('the RL bit search needs the learner to fine-tune and evaluate roll-outs')
-        if FLAGS.uql_enbl_rl_layerwise_tune:
-            raise NotImplementedError('layer-wise fine-tuning inside roll-outs (--uql_enbl_rl_layerwise_tune, off by '
-                                      'default in the reference) is not built; use the global fine-tuning')
+        if self._f('enbl_rl_layerwise_tune'):
+            # get_layerwise_tune_op (utils.py:136-161) minimises mean((conv(x, Q(v)) - conv(x, v))^2) over v ALONE: both terms
+            # carry v through an identity (the STE), so its gradient is zero up to the rounding of the STE chain — Adam
+            # then takes lr-sized steps along the sign of that rounding noise.  Off by default in the reference; not built.
+            raise NotImplementedError('layer-wise fine-tuning inside roll-outs (--%s_enbl_rl_layerwise_tune, off by '
+                                      'default in the reference) is not built; use the global fine-tuning' % self.PREFIX)
         self.total_num_weights = sum(statistics['num_weights'])
-        self.total_bits = self.total_num_weights * FLAGS.uql_equivalent_bits
+        self.total_bits = self.total_num_weights * self._f('equivalent_bits')
         self.w_rl_helper = RLHelper(self.total_bits, statistics['num_weights'], [tuple(w.shape) for w in weights],
-                                    random_layers=FLAGS.uql_enbl_random_layers)
+                                    random_layers=self._f('enbl_random_layers'), flag_prefix=self.PREFIX)
         self.mgw_size = int(mgw.size()) if FLAGS.enbl_multi_gpu else 1
-        self.tune_global_steps = int(FLAGS.uql_tune_global_steps / self.mgw_size)
-        self.tune_global_disp_steps = int(FLAGS.uql_tune_disp_steps / self.mgw_size)
+        self.tune_global_steps = int(self._f('tune_global_steps') / self.mgw_size)
+        self.tune_global_disp_steps = int(self._f('tune_disp_steps') / self.mgw_size)
         self.s_dims = self.w_rl_helper.s_dims
         self.a_dims = 1
-        buff_size = len(weights) * int(FLAGS.uql_nb_rlouts // 4)
-        self.agent = DdpgAgent(self.s_dims, self.a_dims, FLAGS.uql_nb_rlouts, buff_size, a_min=0.,
-                               a_max=FLAGS.uql_w_bit_max - FLAGS.uql_w_bit_min, seed=seed)
+        buff_size = len(weights) * int(self._f('nb_rlouts') // 4)
+        self.agent = DdpgAgent(self.s_dims, self.a_dims, self._f('nb_rlouts'), buff_size, a_min=0.,
+                               a_max=self._f('w_bit_max') - self._f('w_bit_min'), seed=seed)
         self.reward_list = []
 
     def run(self):
         """The bit allocation, with the RL search or without."""
-        if FLAGS.uql_enbl_rl_agent:
+        if self._f('enbl_rl_agent'):
             return self.__calc_optimal_bits()
-        return [FLAGS.uql_weight_bits] * self.nb_matmuls, [FLAGS.uql_activation_bits] * self.nb_activations
+        return [self._f('weight_bits')] * self.nb_matmuls, [self._f('activation_bits')] * self.nb_activations
 
     # ------------------------------------------------------------------ search
     def __calc_optimal_bits(self):
@@ -93,7 +100,7 @@ class BitOptimizer(object):  # pylint: disable=too-many-instance-attributes
         optimal_reward, optimal_bits = -np.inf, None
         if is_primary_worker():
             self.agent.init()
-        for idx_rlout in range(FLAGS.uql_nb_rlouts):
+        for idx_rlout in range(self._f('nb_rlouts')):
             arranged, states_n_actions = None, None
             if is_primary_worker():
                 print('starting %d-th roll-out:' % idx_rlout)
@@ -144,11 +151,11 @@ class BitOptimizer(object):  # pylint: disable=too-many-instance-attributes
     def __calc_rollout_reward(self, layer_bits, a_bits):
         """Restore -> fine-tune with these bits -> validation accuracy (top-1 on CIFAR-10, top-5 on ILSVRC-12)."""
         tuner = self.tuner
-        if FLAGS.uql_enbl_rl_global_tune:
+        if self._f('enbl_rl_global_tune'):
             tuner.rl_restore()
         tuner.rl_set_bits(layer_bits, a_bits)
         self.auto_barrier()
-        if FLAGS.uql_enbl_rl_global_tune:
+        if self._f('enbl_rl_global_tune'):
             tuner.rl_finetune(self.tune_global_steps, self.tune_global_disp_steps)
         if not is_primary_worker():
             return None

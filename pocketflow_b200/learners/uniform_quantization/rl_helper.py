@@ -14,9 +14,12 @@ from ...flags import FLAGS
 
 class RLHelper(object):
     # pylint: disable=too-many-instance-attributes
-    def __init__(self, total_bits, num_weights, var_shapes, random_layers=False):
+    def __init__(self, total_bits, num_weights, var_shapes, random_layers=False, flag_prefix='uql'):
         """total_bits: budget = sum over layers of bits x #weights; num_weights: per layer; var_shapes: kernel shapes
-        (rank 2 or 4) in layer order; random_layers: visit the layers in a fresh random order every roll-out."""
+        (rank 2 or 4) in layer order; random_layers: visit the layers in a fresh random order every roll-out;
+        flag_prefix: 'uql' / 'nuql' — the non-uniform learner's helper is the same class on its own flags
+        (learners/nonuniform_quantization/rl_helper.py is the uniform one with the flags renamed)."""
+        self.flag_prefix = flag_prefix
         self.num_weights = num_weights
         self.nb_vars = len(num_weights)
         self.total_bits = total_bits
@@ -60,7 +63,7 @@ class RLHelper(object):
         """Bit-width (array of shape (1, 1)) for layer `idx` given the actor's output in [0, w_bit_max - w_bit_min].
         All but the last visited layer: round, add the minimum, and cap at what leaves every unvisited layer its
         minimum.  The last visited layer takes the whole remainder.  Both are capped at the maximum."""
-        lo, hi = FLAGS.uql_w_bit_min, FLAGS.uql_w_bit_max
+        lo, hi = getattr(FLAGS, self.flag_prefix + '_w_bit_min'), getattr(FLAGS, self.flag_prefix + '_w_bit_max')
         n_here = self.num_weights[idx]
         spare = self.total_bits - self.w_bits_used - self.num_weights_to_quantize * lo
         assert spare >= 0, 'Not enough budget for layer {}'.format(idx)

@@ -403,8 +403,8 @@ class CodebookWeightQuantizer:
             offs = []
             for v, b in zip(cluster_views, self.uq.bits):
                 off = (v.data_ptr() - cluster_base.data_ptr()) // 4
-                if v.numel() != (1 << b) or off < 0 or off + v.numel() > cluster_base.numel():
-                    raise ValueError('codebook views must hold 2^bits floats inside cluster_base')
+                if v.numel() < (1 << b) or off < 0 or off + v.numel() > cluster_base.numel():
+                    raise ValueError('codebook views must hold at least 2^bits floats inside cluster_base')
                 offs.append(off)
             self.cluster_views, self.cluster_base = list(cluster_views), cluster_base
             self.cluster_off = torch.tensor(offs, dtype=torch.int64, device=self.device)
@@ -443,11 +443,23 @@ class CodebookWeightQuantizer:
             pos += k
         return out
 
+    def set_bits(self, bits):
+        """New bit-widths (the RL bit search): a codebook keeps its place and uses its first 2^bits entries; call
+        quantile_init() afterwards."""
+        bits = [int(b) for b in (bits if hasattr(bits, '__len__') else [bits] * len(self.srcs))]
+        if any(b < 1 or b > 8 for b in bits):
+            raise ValueError('codebook bit-widths must be in [1, 8]')
+        if self.cluster_views is not None and any(v.numel() < (1 << b) for v, b in zip(self.cluster_views, bits)):
+            raise ValueError('a codebook variable is smaller than 2^bits')
+        self.uq.set_bits(bits)
+        self._grad_tables = None
+
     def quantile_init(self):
         vals = self.quantile_values()
         if self.cluster_views is not None:
             for v, c in zip(self.cluster_views, vals):
-                v.copy_(torch.from_numpy(c))
+                v.zero_()                                   # entries past 2^bits stay 0 (no weight-decay term)
+                v[:c.size].copy_(torch.from_numpy(c))
             return
         c = np.zeros((len(self.srcs), 256), np.float32)
         for i, v in enumerate(vals):

@@ -236,6 +236,35 @@ def test_bit_optimizer_refuses_what_it_cannot_do():
         BitOptimizer('cifar_10', [], stats, tuner=_Tuner([1.0]))
 
 
+def test_nuq_bit_optimizer_is_the_same_search_on_the_nuql_flags():
+    """learners/nonuniform_quantization/bit_optimizer.py + rl_helper.py are the uniform learner's files with the flags
+    renamed: same loop, its own budget / range / roll-out count."""
+    from types import SimpleNamespace
+    import pocketflow_b200.learners.nonuniform_quantization.learner  # noqa: F401  (declares nuql_weight_bits, ...)
+    from pocketflow_b200.learners.nonuniform_quantization.bit_optimizer import BitOptimizer
+    FLAGS.nuql_weight_bits, FLAGS.nuql_activation_bits = 3, 32
+    stats = dict(nb_matmuls=2, nb_activations=1, num_weights=[10, 20])
+    assert BitOptimizer('cifar_10', [], stats).run() == ([3, 3], [32])
+    shapes = [(3, 3, 8, 16), (3, 3, 16, 16), (64, 10)]
+    nums = [int(np.prod(s)) for s in shapes]
+    FLAGS.nuql_enbl_rl_agent, FLAGS.nuql_nb_rlouts, FLAGS.nuql_equivalent_bits = True, 6, 3
+    FLAGS.nuql_w_bit_min, FLAGS.nuql_w_bit_max = 2, 5
+    FLAGS.nuql_tune_global_steps, FLAGS.nuql_tune_disp_steps = 8, 4
+    FLAGS.uql_nb_rlouts, FLAGS.uql_w_bit_max = 1, 8                       # must not be read
+    random.seed(1)
+    tuner = _Tuner([1.0, 0.3, 2.0])
+    bo = BitOptimizer('cifar_10', [SimpleNamespace(shape=s) for s in shapes],
+                      dict(nb_matmuls=3, nb_activations=2, num_weights=nums), tuner=tuner, seed=0)
+    w_bits, a_bits = bo.run()
+    assert a_bits == [32, 32] and all(2 <= b <= 5 for b in w_bits)
+    assert sum(b * n for b, n in zip(w_bits, nums)) <= 3 * sum(nums)
+    per = [tuner.calls[i:i + 4] for i in range(0, len(tuner.calls), 4)]
+    assert len(per) == 6 and all(c == ['restore', 'set_bits', ('finetune', 8, 4), 'evaluate'] for c in per)
+    FLAGS.nuql_enbl_rl_layerwise_tune = True
+    with pytest.raises(NotImplementedError, match='nuql_enbl_rl_layerwise_tune'):
+        BitOptimizer('cifar_10', [], stats, tuner=tuner)
+
+
 def test_ws_rl_helper_matches_the_executed_reference():
     import pocketflow_b200.learners.weight_sparsification.learner  # noqa: F401  (defines the ws_* flags)
     from pocketflow_b200.learners.weight_sparsification.rl_helper import RLHelper

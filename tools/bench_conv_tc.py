@@ -98,7 +98,8 @@ def main():
             xp, dyp = ops.Planes(x.numel(), dev), ops.Planes(dy.numel(), dev)
             ops.split_bf16(x, xp)
             ops.split_bf16(dy, dyp)
-            fns = dict(fwd=lambda: ops.conv2d_tc_fwd_planes(d, xp, tw, None, False, y),
+            resid = torch.randn_like(y) if os.environ.get('RESIDUAL', '0') == '1' else None   # conv3 + shortcut layers
+            fns = dict(fwd=lambda: ops.conv2d_tc_fwd_planes(d, xp, tw, None, False, y, resid),
                        dgrad=lambda: ops.conv2d_tc_dgrad_planes(d, dyp, tw, False, dx),
                        wgrad=lambda: ops.conv2d_tc_wgrad_planes(d, xp, dyp, ws, dw))
             if variant == 'levels' and ops.conv2d_tc_tma_supported(d, 0) and ops.conv2d_tc_tma_supported(d, 2):
@@ -114,7 +115,7 @@ def main():
                 wq = ops.tc_wt(wl, None, al, be, True, 8)
                 dya = ops.tc_act(dyp)
                 keep = (lv, lp, csum, hdr, wl, al, be)      # noqa: F841 — keep the device buffers alive
-                fns['fwd'] = lambda: ops.conv2d_tc_fwd_ex(d, act, wq, None, False, y)
+                fns['fwd'] = lambda: ops.conv2d_tc_fwd_ex(d, act, wq, None, False, y, resid)
                 fns['wgrad'] = lambda: ops.conv2d_tc_wgrad_ex(d, act, dya, ws, dw)
         line = '%-22s' % name
         for ps in passes:
