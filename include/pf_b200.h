@@ -459,6 +459,9 @@ int pf_bn_bwd_planes(const float* dy_dev, const float* x_dev, int64_t m, int c, 
                      void* dx_lo_dev, float* ws_dev, void* stream);
 /* out (+)= a (+ b): residual add (resnet_model.py:199,314) / gradient fan-out; b_dev may be NULL */
 int pf_add(const float* a_dev, const float* b_dev, int64_t n, int accumulate, float* out_dev, void* stream);
+/* dst[i][j] = sum_b src[b*m+i][b*n+j] (src is (g*m) x (g*n) row-major): folds the diagonal blocks of a weight gradient that
+ * the tensor cores computed from g pixels per GEMM row (convs with fewer than 64 output channels) */
+int pf_fold_diag_blocks(const float* src_dev, int g, int m, int n, float* dst_dev, void* stream);
 /* dx (+)= dy * [y > 0] (and [y < 6] for act == 2) */
 int pf_relu_bwd(const float* dy_dev, const float* y_dev, int64_t n, int act, int accumulate, float* dx_dev,
                 void* stream);

@@ -850,6 +850,18 @@ inline int bn_splits(int M, int C, int* rows_per_split) {
   return (M + rps - 1) / rps;
 }
 
+// dst[i][j] = sum_b src[b*m + i][b*n + j]: the diagonal blocks of a (g*m) x (g*n) matrix folded onto each other — the
+// weight gradient of a conv with fewer than 64 output channels, computed on the tensor cores from g pixels per GEMM row
+// (engine: the 3 -> 32 stem of MobileNet-v1)
+__global__ void __launch_bounds__(NT)
+fold_diag_blocks_kernel(const float* __restrict__ src, int g, int m, int n, float* __restrict__ dst) {
+  const int i = blockIdx.x * NT + threadIdx.x;
+  if (i >= m * n) return;
+  const int r = i / n, c = i - r * n;
+  float acc = 0.f;
+  for (int b = 0; b < g; ++b) acc += src[(size_t)(b * m + r) * (g * n) + b * n + c];
+  dst[i] = acc;
+}
 }  // namespace
 
 extern "C" {
@@ -1009,6 +1021,14 @@ int pf_bn_bwd(const float* dy_dev, const float* x_dev, int64_t m, int c, const f
   PF_REQUIRE(dx_dev != nullptr, "pf_bn_bwd: null pointer");
   return pf_bn_bwd_planes(dy_dev, x_dev, m, c, mean_dev, rstd_dev, gamma_dev, beta_dev, act, dgamma_dev, dbeta_dev,
                           dx_dev, accumulate, nullptr, nullptr, ws_dev, stream);
+}
+
+int pf_fold_diag_blocks(const float* src_dev, int g, int m, int n, float* dst_dev, void* stream) {
+  PF_REQUIRE(g >= 1 && m >= 1 && n >= 1 && (int64_t)m * n < (1ll << 30), "pf_fold_diag_blocks: bad shape");
+  PF_REQUIRE(src_dev && dst_dev, "pf_fold_diag_blocks: null pointer");
+  fold_diag_blocks_kernel<<<(m * n + NT - 1) / NT, NT, 0, (cudaStream_t)stream>>>(src_dev, g, m, n, dst_dev);
+  PF_CHECK_LAUNCH("pf_fold_diag_blocks");
+  return PF_OK;
 }
 
 int pf_add(const float* a_dev, const float* b_dev, int64_t n, int accumulate, float* out_dev, void* stream) {

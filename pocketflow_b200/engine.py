@@ -329,6 +329,18 @@ class Executor:
                     # columns directly in operand planes when every consumer is a tensor-core kernel
                     as_planes = (not self.train) or ops.conv2d_tc_wgrad_supported(d1)
                     mode = 'im2col'
+                    # fewer than 64 output channels (MobileNet's 3 -> 32 stem): the tensor-core wgrad wants Cout % 64 == 0,
+                    # so g = 64 / Cout pixels share one GEMM row — cols [pixels, kpad] and dy [pixels, k] are read as
+                    # [pixels / g, g kpad] and [pixels / g, g k]; the weight gradient is the sum of the g diagonal
+                    # kpad x k blocks of the (g kpad) x (g k) result (the exact-fp32 CUDA-core wgrad of this layer took
+                    # 4.3 of MobileNet's 23 ms: profiles/r2_ncu_launchlist_mobilenet_step_v1.txt)
+                    pair = None
+                    if self.train and not as_planes and k in (16, 32) and (kpad * (64 // k)) % 64 == 0 \
+                            and (p * q) % (64 // k) == 0:
+                        g_ = 64 // k
+                        dp = ops.conv_desc(n, 1, p * q // g_, kpad * g_, k * g_, 1, 1, 1, p * q // g_, 1, 1, 0, 0)
+                        if ops.conv2d_tc_wgrad_supported(dp):
+                            pair, as_planes = dict(g=g_, d=dp), True
                     if sh == 2 and sw == 2 and 4 * c <= 16 and os.environ.get('PF_STEM_S2D', '1') != '0':
                         # stride-2 stem: space-to-depth instead of im2col — a stride-1 conv over 16 channels that the
                         # tensor-core kernels gather themselves (no 2 GB column matrix)
@@ -345,6 +357,11 @@ class Executor:
                         self.im2col[op]['bwd_map'] = torch.from_numpy(bwd_map).to(dev)
                     if self.train:
                         self.im2col[op]['dwpad'] = torch.zeros(kpad * k, dtype=torch.float32, device=dev)
+                        if pair is not None and mode == 'im2col':
+                            pair['dw'] = torch.zeros(pair['g'] * kpad * pair['g'] * k, dtype=torch.float32, device=dev)
+                            self.im2col[op]['pair'] = pair
+                            max_ws = max(max_ws, ops.conv2d_tc_wgrad_planes_workspace_floats(pair['d']))
+                            self._stem_dy = max(getattr(self, '_stem_dy', 8), n * p * q * k)
                         if ops.conv2d_tc_wgrad_supported(d1):
                             max_ws = max(max_ws, ops.conv2d_tc_wgrad_planes_workspace_floats(d1))
                             self._stem_dy = max(getattr(self, '_stem_dy', 8), n * p * q * k)
@@ -959,7 +976,7 @@ class Executor:
                         if im['planes']:
                             gp = ops.Planes(op.output.numel, self.device, self.dy_scratch.buf)
                             ops.split_bf16(gy, gp)
-                            ops.conv2d_tc_wgrad_planes(im['d1'], im['cols'], gp, self.wgrad_ws, im['dwpad'])
+                            self._stem_wgrad_planes(im, gp)
                         elif ops.conv2d_tc_wgrad_supported(im['d1']):
                             ops.conv2d_tc_wgrad(im['d1'], im['cols'], gy, self.wgrad_ws, im['dwpad'])
                         else:
@@ -1084,6 +1101,15 @@ class Executor:
             with self.timed('weight_quant'):
                 self.wq.cluster_grad([st.view(op.vars['kernel'], self.G) for op in self.wq_ops], self.G)
 
+    def _stem_wgrad_planes(self, im, gp):
+        """weight gradient of the first layer from its column planes and the dy planes, into im['dwpad']"""
+        if 'pair' in im:
+            pr = im['pair']
+            ops.conv2d_tc_wgrad_planes(pr['d'], im['cols'], gp, self.wgrad_ws, pr['dw'])
+            ops.fold_diag_blocks(pr['dw'], pr['g'], im['kpad'], im['d1'].k, im['dwpad'])
+        else:
+            ops.conv2d_tc_wgrad_planes(im['d1'], im['cols'], gp, self.wgrad_ws, im['dwpad'])
+
     @contextlib.contextmanager
     def standalone_forward(self):
         """forward() calls outside device_step (layer-wise regression passes): an executor that shares the first layer's
@@ -1114,7 +1140,7 @@ class Executor:
                 if im['planes']:
                     gp = ops.Planes(op.output.numel, self.device, lw.buf)
                     ops.split_bf16(gy, gp)
-                    ops.conv2d_tc_wgrad_planes(im['d1'], im['cols'], gp, self.wgrad_ws, im['dwpad'])
+                    self._stem_wgrad_planes(im, gp)
                 elif ops.conv2d_tc_wgrad_supported(im['d1']):
                     ops.conv2d_tc_wgrad(im['d1'], im['cols'], gy, self.wgrad_ws, im['dwpad'])
                 else:

@@ -87,6 +87,7 @@ SIGNATURES = {
     'pf_bn_bwd_planes': (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_i32,
                                  c_vp, c_vp, c_vp, c_vp]),
     'pf_add': (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp]),
+    'pf_fold_diag_blocks': (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
     'pf_relu_bwd': (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp]),
     'pf_colsum': (c_i32, [c_vp, c_i64, c_i32, c_vp, c_vp]),
     'pf_maxpool_fwd': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp]),

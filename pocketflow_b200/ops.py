@@ -598,6 +598,10 @@ def add(a, b, out, accumulate=False):
     _lib.check(_lib.load().pf_add(_p(a), _p(b), a.numel(), int(bool(accumulate)), _p(out), _stream()), 'pf_add')
 
 
+def fold_diag_blocks(src, g, m, n, dst):
+    _lib.check(_lib.load().pf_fold_diag_blocks(_p(src), int(g), int(m), int(n), _p(dst), _stream()), 'pf_fold_diag_blocks')
+
+
 def relu_bwd(dy, y, dx, act=1, accumulate=False):
     _lib.check(_lib.load().pf_relu_bwd(_p(dy), _p(y), y.numel(), int(act), int(bool(accumulate)), _p(dx), _stream()),
                'pf_relu_bwd')

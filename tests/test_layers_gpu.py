@@ -206,7 +206,8 @@ def test_avgpool_add_relu_colsum_softmax():
 
 @pytest.mark.parametrize('cfg', [(2, 12, 12, 32, 3, 1, 1, 1), (3, 15, 15, 16, 3, 2, 0, 1), (2, 14, 14, 64, 3, 2, 0, 1),
                                  (1, 7, 7, 1024, 3, 1, 1, 1), (2, 10, 10, 64, 3, 1, 1, 1), (2, 9, 9, 32, 3, 1, 0, 0),
-                                 (3, 6, 6, 16, 3, 1, 1, 1), (2, 3, 3, 8, 3, 1, 1, 1)])
+                                 (3, 6, 6, 16, 3, 1, 1, 1), (2, 3, 3, 8, 3, 1, 1, 1), (2, 12, 12, 32, 3, 2, 1, 1), (2, 13, 13, 8, 3, 2, 1, 1),
+                                 (2, 16, 16, 16, 3, 2, 0, 1)])
 def test_depthwise_conv_fwd_dgrad_wgrad(cfg):
     n, h, w, c, k, st, p0, p1 = cfg
     g = torch.Generator().manual_seed(sum(cfg))

@@ -205,8 +205,17 @@ def test_mobilenet_channel_pruned_gpu_learner_step(monkeypatch, conv_path):
     lr = lrn.lrn_rate(0)
     ex.run_step(lr)
     got = ex.fetch_losses()
-    ref, new_state, _ = orc.step(state, images.numpy(), labels.numpy(), dict(kind='momentum', slots={}, momentum=0.9),
-                                 lr, masks=masks)
+    ref, new_state, grads = orc.step(state, images.numpy(), labels.numpy(), dict(kind='momentum', slots={}, momentum=0.9),
+                                     lr, masks=masks)
+    # the 3 -> 32 stem's weight gradient (tc path: g = 2 pixels per GEMM row on the tensor cores, diagonal blocks folded)
+    stem = ex.ops[[o.type for o in ex.ops].index('Conv2D')].vars['kernel']
+    g_dev, g_ref = ex.store.view(stem, ex.G).cpu().numpy().reshape(-1), grads[stem.name].reshape(-1)
+    cos = float(np.dot(g_dev, g_ref) / (np.linalg.norm(g_dev) * np.linalg.norm(g_ref) + 1e-30))
+    # (the deepest gradient of the net: 27 layers of ReLU6 boundaries behind it at batch 2; the kernel itself is checked
+    # against float64 in tests/test_tc_gpu.py::test_small_cout_wgrad_by_pixel_pairing)
+    assert cos >= (0.999 if conv_path == 'fp32' else 0.995) and abs(np.linalg.norm(g_dev) / np.linalg.norm(g_ref) - 1.0) <= 2e-2, cos
+    if conv_path == 'tc':
+        assert 'pair' in ex.im2col[ex.ops[[o.type for o in ex.ops].index('Conv2D')]]
     # split-bf16 operands carry 16 mantissa bits: 2e-6 per convolution, 28 of them in a row at batch 2 (measured 2e-5 on
     # the cross-entropy with half of the channels masked); the exact-fp32 path holds 1e-5
     bar = 1e-5 if conv_path == 'fp32' else 3e-5

@@ -39,7 +39,7 @@ def test_nuq_rl_bit_search_through_the_real_learner():
     import numpy as np
     from pocketflow_b200.flags import FLAGS
     from test_learners_gpu import make
-    lrn = make('non-uniform', nuql_enbl_rl_agent=True, nuql_nb_rlouts=3, nuql_tune_global_steps=2, nuql_equivalent_bits=4,
+    lrn = make('non-uniform', nuql_enbl_rl_agent=True, nuql_nb_rlouts=4, nuql_tune_global_steps=2, nuql_equivalent_bits=4,
                nuql_w_bit_min=2, nuql_w_bit_max=6, nb_smpls_eval=64, batch_size_eval=16, enbl_dst=False)
     ex = lrn.sess_train
     bits = lrn.optimal_w_bit_list

@@ -250,3 +250,31 @@ def test_space_to_depth_stem(cfg):
     ops.gather_rows(dwpad, torch.from_numpy(bwd_map).to(dev), DW, k)
     dw_ref = wd.grad.permute(2, 3, 1, 0)
     assert (DW.cpu().double() - dw_ref).abs().max().item() <= 2e-5 * dw_ref.abs().max().item()
+
+
+@pytest.mark.parametrize('cfg', [(4, 14, 14, 32, 32), (2, 8, 12, 32, 32), (3, 10, 10, 16, 16), (2, 6, 6, 48, 16)])
+def test_small_cout_wgrad_by_pixel_pairing(cfg):
+    """Weight gradient of a 1x1 conv with fewer than 64 output channels on the tensor cores (engine: the im2col'ed
+    3 -> 32 stem of MobileNet-v1): g = 64 / Cout pixels share one GEMM row, the (g Cin) x (g Cout) result's diagonal
+    blocks are folded (pf_fold_diag_blocks).  Against float64: 2e-5 of the largest entry, like every split-bf16 conv."""
+    n, p, q, cin, cout = cfg
+    g = 64 // cout
+    if (cin * g) % 64 or (p * q) % g:
+        pytest.skip('pairing does not apply')
+    gen = torch.Generator().manual_seed(sum(cfg))
+    cols = torch.randn(n * p * q, cin, generator=gen)
+    dy = torch.randn(n * p * q, cout, generator=gen)
+    ref = cols.double().t() @ dy.double()
+    dev = torch.device(DEV)
+    cp, dp = ops.Planes(cols.numel(), dev), ops.Planes(dy.numel(), dev)
+    ops.split_bf16(cols.to(DEV), cp)
+    ops.split_bf16(dy.to(DEV), dp)
+    d_pair = ops.conv_desc(n, 1, p * q // g, cin * g, cout * g, 1, 1, 1, p * q // g, 1, 1, 0, 0)
+    assert ops.conv2d_tc_wgrad_supported(d_pair)
+    ws = torch.empty(max(ops.conv2d_tc_wgrad_planes_workspace_floats(d_pair), 4), device=DEV)
+    dw_pair = torch.empty(cin * g * cout * g, device=DEV)
+    ops.conv2d_tc_wgrad_planes(d_pair, cp, dp, ws, dw_pair)
+    dw = torch.full((cin, cout), 7.0, device=DEV)
+    ops.fold_diag_blocks(dw_pair, g, cin, cout, dw)
+    err = (dw.cpu().double() - ref).abs().max().item()
+    assert err <= 2e-5 * ref.abs().max().item(), (err, ref.abs().max().item())
