@@ -406,9 +406,15 @@ bool conv_tma_eligible(int pass, const TcGeom& g) {
   return g.C % 64 == 0 && g.K % 64 == 0 && g.sh <= 8 && g.sw <= 8;
 }
 
-static int pick_bn(int Ng, int m_tiles) {
+static int pick_bn(int Ng, int m_tiles, bool has_extra, bool split_planes, int nk) {
   int BN;
-  if (Ng >= 256) {
+  if (Ng >= 256 && has_extra && (split_planes || nk >= 2)) {
+    // an epilogue that also streams a residual / accumulate operand: 128-wide tiles leave shared memory for the ring
+    // (and for 8 epilogue warps) that 256-wide stages take away.  Measured on the conv3 + shortcut layers of ResNet-50
+    // (batch 256, ms at BN 256 -> 128): split planes 64->256 0.516 -> 0.319, 128->512 0.267 -> 0.265; levels 128->512
+    // 0.299 -> 0.223, 256->1024 0.176 -> 0.133 — but levels 64->256 (one k-stage per tile) 0.354 -> 0.407: stays 256.
+    BN = 128;
+  } else if (Ng >= 256) {
     const int64_t t256 = (int64_t)m_tiles * ((Ng + 255) / 256), t128 = (int64_t)m_tiles * ((Ng + 127) / 128);
     const double c256 = (double)((t256 + PF_NUM_SMS - 1) / PF_NUM_SMS) * 1.3;   // a 256-wide tile costs ~1.3x a 128-wide one
     const double c128 = (double)((t128 + PF_NUM_SMS - 1) / PF_NUM_SMS);
@@ -459,7 +465,7 @@ int conv_tma_launch(int pass, const TcGeom& g, const pf_tc_act& a, const pf_tc_w
   p.accumulate = accumulate;
   p.relu = relu;
   const int m_tiles = (p.M + TM - 1) / TM;
-  const int BN = pick_bn(p.Ng, m_tiles);
+  const int BN = pick_bn(p.Ng, m_tiles, residual != nullptr || accumulate, a.plane1 != nullptr && a.hdr == nullptr, p.nk);
   p.BN = BN;
   p.n_tiles = (p.Ng + BN - 1) / BN;
   p.total_tiles = m_tiles * p.n_tiles;
