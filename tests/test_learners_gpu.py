@@ -26,6 +26,7 @@ def make(learner, **flags):
     import pocketflow_b200.learners.weight_sparsification.learner  # noqa: F401  (flag definitions)
     import pocketflow_b200.learners.nonuniform_quantization.learner  # noqa: F401
     import pocketflow_b200.learners.uniform_quantization.learner  # noqa: F401
+    import pocketflow_b200.learners.channel_pruning_gpu.learner  # noqa: F401
     FLAGS.resnet_size, FLAGS.batch_size, FLAGS.learner = 8, 16, learner
     for k, v in flags.items():
         setattr(FLAGS, k, v)
@@ -312,6 +313,7 @@ def test_channel_selection_phase_matches_the_oracle(monkeypatch, tmp_path, conv_
     ('weight-sparse', 'ws_save_path', dict(ws_prune_ratio=0.5, ws_prune_ratio_prtl='uniform', ws_mask_update_step=2)),
     ('uniform', 'uql_save_quant_model_path', dict(uql_weight_bits=8, uql_use_buckets=True)),
     ('non-uniform', 'nuql_save_quant_model_path', dict(nuql_weight_bits=4)),
+    ('chn-pruned-gpu', 'cpg_save_path', dict(cpg_prune_ratio=0.5, cpg_nb_iters_layer=2)),
 ])
 def test_exec_mode_eval_restores_the_saved_model(tmp_path, learner, path_flag, extra):
     """--exec_mode eval (nets/*_run.py:62-64): evaluate() restores the latest checkpoint first — a freshly built learner
