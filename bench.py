@@ -442,10 +442,22 @@ def main():
     conv_flops = (train_pi + teacher_fwd) * B
     conv_tflops = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     step_ms_eager = sum(prof.values())
-    # HBM-bound companion: the BN(+ReLU)(+activation fake-quant) apply pass, 8 B per element
-    # (fp32 conv output in, split-bf16 operand planes or fp32 out); teacher + student
-    aq_elems = sum(op.output.numel for e in ([ex] + ([ex.teacher] if ex.teacher is not None else []))
-                   for op in e.ops if op.type == 'FusedBatchNorm')
+    # HBM-bound companion: the BN(+ReLU)(+activation fake-quant) apply pass — 4 B per element read (fp32 conv output)
+    # plus what it writes: split-bf16 operand planes or fp32 (4 B), ONE bf16 plane of quantizer levels (2 B, + the
+    # per-pixel channel sums), the fp32 copy as well where another consumer needs it; teacher + student
+    aq_bytes = 0
+    for e in ([ex] + ([ex.teacher] if ex.teacher is not None else [])):
+        for op in e.ops:
+            if op.type != 'FusedBatchNorm':
+                continue
+            n_el = op.output.numel
+            lv = getattr(e, 'act_lv', {}).get(op)
+            has_planes = op in getattr(e, 'xplanes', {})
+            out_b = (2 if lv is not None else 4) if has_planes else 4
+            if has_planes and e.bn_need_f32.get(op, False):
+                out_b += 4
+            aq_bytes += n_el * (4 + out_b) + (4 * n_el // op.output.shape[-1] * lv['nseg'] if lv is not None else 0)
+    aq_elems = aq_bytes / 8.0
     aq_ms = prof.get('bn_apply', 0.0)
     conv_traffic, traffic_src = None, 'no ncu launch list of this binary under profiles/ (run tools/gpu_launchlist.sh)'
     try:
@@ -503,11 +515,13 @@ def main():
                          'peak_kind': peak_kind + ' bf16 sustained',
                          'flops_per_step': conv_flops, 'ms_per_step': conv_ms,
                          'share_of_step': conv_ms / step_ms_eager if step_ms_eager else None},
-            'roofline_hbm': {'bound': 'hbm', 'kernel': 'bn_apply_kernel (BN + ReLU + activation fake-quant -> operand planes)',
+            'roofline_hbm': {'bound': 'hbm', 'kernel': 'bn_apply_kernel / bn_apply_levels_kernel (BN + ReLU + activation fake-quant -> operand planes / levels)',
                              'achieved': (8.0 * aq_elems / (aq_ms * 1e-3) / 1e9) if aq_ms > 0 else None,
                              'peak': hbm_peak, 'unit': 'GB/s',
                              'frac': (8.0 * aq_elems / (aq_ms * 1e-3) / 1e9 / hbm_peak) if aq_ms > 0 else None,
-                             'traffic': None, 'peak_kind': peak_kind, 'bytes_per_step': 8 * aq_elems, 'ms_per_step': aq_ms},
+                             'traffic': None, 'peak_kind': peak_kind, 'bytes_per_step': int(aq_bytes), 'ms_per_step': aq_ms,
+                             'note': 'algorithmic bytes: 4 B/element read + 4 B (split planes or fp32) or 2 B (one plane of '
+                                     'quantizer levels) written'},
             'step_breakdown_ms': {k: round(v, 4) for k, v in sorted(prof.items())},
             'losses_last_step': {k: float(v) for k, v in losses.items()},
             'clocks': sampler.summary(),
