@@ -361,21 +361,21 @@ bn_apply_levels_kernel(const float* __restrict__ x, int64_t total, int C, int cs
       csum[(e >> cshift) * nseg + (int)((e & (int64_t)(C - 1)) >> 7)] = part;
     }
   };
-  // warp-uniform trip count (the segment reduction uses full-warp shuffles); two independent loads in flight
+  // warp-uniform trip count (the segment reduction uses full-warp shuffles); FOUR independent loads in flight per thread
+  // (with two, this kernel and its plane-writing sibling both read at ~2.5 TB/s: bound by the latency of the reads)
   const int64_t wbase = first - lane;
-  int64_t off = 0;
-  for (; wbase + off + stride < nvec; off += 2 * stride) {
-    const int64_t i0 = first + off, i1 = i0 + stride;
-    const bool v1 = i1 < nvec;
-    const float4 a = pf_ld_stream(x + (i0 << 2));        // wbase + off + stride < nvec  =>  i0 < nvec
-    const float4 b = v1 ? pf_ld_stream(x + (i1 << 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    emit(a, i0, true);
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t off = 0; wbase + off < nvec; off += 4 * stride) {
+    const int64_t i0 = first + off, i1 = i0 + stride, i2 = i1 + stride, i3 = i2 + stride;
+    const bool v0 = i0 < nvec, v1 = i1 < nvec, v2 = i2 < nvec, v3 = i3 < nvec;
+    const float4 a = v0 ? pf_ld_stream(x + (i0 << 2)) : zero4;
+    const float4 b = v1 ? pf_ld_stream(x + (i1 << 2)) : zero4;
+    const float4 c4 = v2 ? pf_ld_stream(x + (i2 << 2)) : zero4;
+    const float4 d = v3 ? pf_ld_stream(x + (i3 << 2)) : zero4;
+    emit(a, i0, v0);
     emit(b, i1, v1);
-  }
-  if (wbase + off < nvec) {
-    const int64_t i0 = first + off;
-    const bool v0 = i0 < nvec;
-    emit(v0 ? pf_ld_stream(x + (i0 << 2)) : make_float4(0.f, 0.f, 0.f, 0.f), i0, v0);
+    emit(c4, i2, v2);
+    emit(d, i3, v3);
   }
 }
 

@@ -56,6 +56,28 @@ def test_argument_errors_map_to_valueerror():
         lib.check(700, 'x')
 
 
+def test_comm_entry_points_bind_nccl_at_run_time_and_validate_arguments():
+    """pf_comm_* (the step's collective behind the C ABI): NCCL is bound with dlopen, not linked — the version query and
+    the unique id need no GPU; argument errors come back as status codes, never as crashes."""
+    import ctypes
+    L = lib.load()
+    v = ctypes.c_int32(0)
+    st = L.pf_comm_nccl_version(ctypes.byref(v))
+    if st != 0:
+        pytest.skip('libnccl.so.2 is not loadable here: ' + L.pf_last_error().decode())
+    assert v.value >= 20000
+    a, b = ctypes.create_string_buffer(128), ctypes.create_string_buffer(128)
+    assert L.pf_comm_unique_id(a) == 0 and L.pf_comm_unique_id(b) == 0 and a.raw != b.raw
+    assert L.pf_comm_unique_id(None) == -1
+    h = ctypes.c_void_p()
+    assert L.pf_comm_init(a, 2, 5, ctypes.byref(h)) == -1                 # rank out of range: refused before NCCL
+    assert L.pf_comm_init(None, 1, 0, ctypes.byref(h)) == -1
+    assert L.pf_allreduce_flat(None, None, 0, None) == 0                  # empty range = no-op
+    assert L.pf_allreduce_flat(None, None, 16, None) == -1                # no communicator / buffer
+    assert L.pf_broadcast_flat(None, None, 16, 0, None) == -1
+    assert L.pf_comm_destroy(None) == 0
+
+
 def test_struct_layouts_match_header():
     assert ops.UQ_SEG.itemsize == 48 and ops.UQ_SEG.fields['ncols'][1] == 32
     assert ops.WORK.itemsize == 32 and ops.WORK.fields['start'][1] == 8
