@@ -219,6 +219,68 @@ def test_multi_stream_step_is_bit_identical_to_serial(monkeypatch):
         assert torch.equal(P, results[0][0]) and torch.equal(O_, results[0][1]) and loss == results[0][2]
 
 
+def test_bucketed_gradient_exchange_covers_the_buffer_once_and_changes_nothing(monkeypatch):
+    """The data-parallel step sums the flat gradient buffer in buckets issued from inside the backward pass (SURVEY §8e;
+    engine._bucket_plan).  With a recording stand-in for the collective (world 1: the sum is the identity): every float of
+    the buffer is handed to the collective exactly once, the early bucket holds the LAST layers' kernels and goes out
+    before the backward pass has finished, and eager step, captured graph and the collective-free step agree bit for bit.
+    (The NCCL path itself — pf_allreduce_flat at world 2 / 8 — is tools/mgpu_check.py and the N > 1 bench lines.)"""
+    monkeypatch.setenv('PF_CONV_PATH', 'tc')
+    lrn = make_uq_learner(resnet_size=20, batch=32, dst=True)
+    ex = lrn.sess_train
+    lrn.iterator_train.prefill()
+    images, labels = lrn.iterator_train.next_batch()
+    ex.buf[lrn.images].copy_(images)
+    ex.buf[lrn.labels].copy_(labels)
+    P0, O0 = ex.store.P.clone(), ex.store.O.clone()
+    calls = []
+
+    def collective(flat):
+        assert flat.is_contiguous() and flat.dtype == torch.float32
+        calls.append(((flat.data_ptr() - ex.G.data_ptr()) // 4, flat.numel(), torch.cuda.current_stream().cuda_stream))
+        return flat
+
+    def rewind():
+        ex.store.P.copy_(P0)
+        ex.store.O.copy_(O0)
+        ex.reset_optimizer_state()
+
+    lr = lrn.lrn_rate(0)
+    ex.run_step(lr)                                        # no collective
+    torch.cuda.synchronize()
+    P_ref, G_ref = ex.store.P.clone(), ex.G.clone()
+    rewind()
+    ex.run_step(lr, collective)                            # eager, bucketed
+    torch.cuda.synchronize()
+    bk = ex._bucket_plan()
+    assert bk is not None and 0 < bk['split'] < bk['end'] <= ex.G.numel()
+    assert [c[:2] for c in calls][0] == (bk['split'], bk['end'] - bk['split'])          # the last layers' kernels first
+    spans = sorted(c[:2] for c in calls)
+    assert spans[0][0] == 0 and all(a[0] + a[1] == b[0] for a, b in zip(spans, spans[1:])) \
+        and spans[-1][0] + spans[-1][1] == ex.G.numel()                                  # a partition of the buffer
+    assert calls[0][2] != calls[-1][2]                                                   # on the communication stream
+    assert (bk['end'] - bk['split']) >= 0.4 * bk['end']
+    assert torch.equal(ex.store.P, P_ref) and torch.equal(ex.G, G_ref)
+    # the captured graph carries the same schedule
+    del calls[:]
+    rewind()
+    ex.capture(collective)
+    rewind()
+    ex.run_step(lr, collective)
+    torch.cuda.synchronize()
+    assert torch.equal(ex.store.P, P_ref) and torch.equal(ex.G, G_ref)
+    # PF_AR_BUCKETS=1: one call for the whole buffer after the backward pass
+    monkeypatch.setenv('PF_AR_BUCKETS', '1')
+    lrn1 = make_uq_learner(resnet_size=20, batch=32, dst=True)
+    ex1 = lrn1.sess_train
+    assert ex1._bucket_plan() is None
+    seen = []
+    ex1.buf[lrn1.images].copy_(images)
+    ex1.buf[lrn1.labels].copy_(labels)
+    ex1.run_step(lr, lambda flat: seen.append(flat.numel()))
+    assert seen == [ex1.G.numel()]
+
+
 def test_lenet_uq_step_matches_oracle():
     FLAGS.reset()
     from pocketflow_b200.nets import lenet_at_cifar10 as Lnet
