@@ -612,9 +612,10 @@ class Executor:
                 self.MASK = torch.ones(st.n_masked, dtype=torch.float32, device=dev)
                 self.BKUP = st.P[:st.n_masked].clone()
                 mv = self.maskable
+                # (the builder takes device pointers: planning-only executors on the CPU — tests — do without)
                 self.mask_builder = ops.MaskBuilder([st.view(v) for v in mv],
                                                     [st.view(v, self.BKUP) for v in mv],
-                                                    [st.view(v, self.MASK) for v in mv])
+                                                    [st.view(v, self.MASK) for v in mv]) if dev.type == 'cuda' else None
             else:
                 self.MASK = None
             if self.exact_ste and self.wq is not None and isinstance(self.wq, ops.UniformWeightQuantizer):

@@ -858,3 +858,27 @@ def test_cpg_selection_loop_feeds_what_the_reference_loop_feeds():
             if a[0] == 'prune':
                 assert abs(a[2] - b[2]) <= 1e-7 * b[2] and abs(a[3] - b[3]) <= 1e-6 * max(b[3], 1.0)
     FLAGS.reset()
+
+
+def test_codebook_gradient_kat():
+    """Hand-derived: gradient_override_map {'Mul': 'Add', 'Sign': 'Identity'} around qx = gather(c, idx) * sign(x_n + 1e-6)
+    (learners/nonuniform_quantization/utils.py:303-306) sends the upstream gradient unchanged to BOTH factors — a
+    segment sum into the codebook, the identity into x_n; the inverse scale alpha * q + beta (:433) contributes alpha.
+    w = [0, 1, 2, 4]: alpha = 4 (+1e-10), x_n = [0, .25, .5, 1]; codebook [0.2, 0.9] -> idx = [0, 0, 0, 1]
+    (|.5 - .2| = .3 < |.5 - .9| = .4); g = [1, 2, 3, 5]:  dL/dc = alpha * [1 + 2 + 3, 5] = [24, 20],  dL/dw = g."""
+    import torch
+    from oracle import pf_oracle as O
+    from oracle.step_oracle import codebook_quant
+    w = np.array([0.0, 1.0, 2.0, 4.0], np.float32)
+    c = np.array([0.2, 0.9], np.float32)
+    g = np.array([1.0, 2.0, 3.0, 5.0], np.float32)
+    q, _, idx = O.nonuniform_quantize(w, 1, c)
+    assert idx.tolist() == [0, 0, 0, 1] and np.allclose(q, [0.8, 0.8, 0.8, 3.6], rtol=1e-6)
+    gx, gc = O.nuq_grads(g, idx, 2, np.float32(4.0))
+    assert np.allclose(gc, [24.0, 20.0]) and np.allclose(gx, g)
+    wt = torch.tensor(w, requires_grad=True)
+    ct = torch.tensor(c, requires_grad=True)
+    out = codebook_quant(wt, ct)
+    assert np.allclose(out.detach().numpy(), q, rtol=1e-6)
+    out.backward(torch.tensor(g))
+    assert np.allclose(ct.grad.numpy(), [24.0, 20.0], rtol=1e-6) and np.allclose(wt.grad.numpy(), g, rtol=1e-6)

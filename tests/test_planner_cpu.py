@@ -154,3 +154,106 @@ def test_unsafe_identity_sharing_is_refused():
         for x in grad_inputs(ex, op):
             kk = ex.gkey(x)
             state[kk] = (state[kk] | {op}) if kk in state else {op}
+
+
+def test_param_store_frozen_ranges_and_checked_restores():
+    """ParamStore: frozen variables (the optimizer's var_list excludes them — the non-uniform learner's modes) form
+    their own ranges; a restore counts what it found and refuses checkpoints that match nothing / not everything."""
+    import numpy as np
+    from pocketflow_b200.engine import ParamStore
+    init = lambda rng, shape: rng.standard_normal(shape).astype(np.float32)
+    mk = lambda name, shape, trainable=True: G.Variable(name + ':0', shape, init, trainable)
+    k1, k2, c1, c2 = mk('m/conv/kernel', (3, 3, 4, 8)), mk('m/conv_1/kernel', (1, 1, 8, 8)), \
+        mk('m/conv/Conv2D/nonuniform_quantize/clusters', (16,)), mk('m/conv_1/Conv2D/nonuniform_quantize/clusters', (16,))
+    gam, mm = mk('m/bn/gamma', (8,)), mk('m/bn/moving_mean', (8,), trainable=False)
+    wd = {k1: 5e-4, k2: 5e-4, c1: 5e-4, c2: 5e-4}
+    st = ParamStore([k1, c1, gam, k2, c2, mm], torch.device('cpu'), wd, frozen=[c1, c2])
+    # kernels (wd, live) | codebooks (wd, frozen) | gamma (no wd): three ranges, the middle one skipped by the optimizer
+    assert len(st.ranges) == 3 and len(st.frozen_ranges) == 1
+    (s, e), = st.frozen_ranges
+    assert {st.offset[c1], st.offset[c2]} == {s, s + 16} and e - s == 32
+    assert all(not (s <= st.offset[v] < e) for v in (k1, k2, gam))
+    assert [r for r in st.ranges if (r[0], r[1]) == (s, e)][0][3] == 5e-4        # still weight-decayed (loss term)
+    state = st.state_dict()
+    assert set(state) == {v.name for v in (k1, k2, c1, c2, gam, mm)}
+    # checked restores
+    assert st.load_state_dict(state, strict=True) == (5, 5)
+    no_clusters = {k: v for k, v in state.items() if 'clusters' not in k}
+    with pytest.raises(ValueError):
+        st.load_state_dict(no_clusters, strict=False, require='all')
+    assert st.load_state_dict(no_clusters, strict=False, require='all', optional=('/clusters',)) == (3, 3)
+    with pytest.raises(ValueError):
+        st.load_state_dict({'other/' + k: v for k, v in state.items()}, strict=False, require='any')
+    with pytest.raises(ValueError):
+        st.load_state_dict({k1.name: np.zeros(7, np.float32)}, strict=False)      # wrong size
+    with pytest.raises(KeyError):
+        st.load_state_dict(no_clusters, strict=True)
+
+
+def test_nuq_graph_edit_creates_the_reference_cluster_variables():
+    """NonUniformQuantization.insert_quant_op_for_weights: one trainable `clusters` variable per quantized op, under
+    <model scope>/<op name without its scope>/nonuniform_quantize/ (learners/nonuniform_quantization/utils.py:180, :297),
+    2^bits entries — or 2^cap when the RL bit search may change the bit-width."""
+    FLAGS.reset()
+    import importlib
+    importlib.import_module('pocketflow_b200.learners.nonuniform_quantization.learner')
+    from pocketflow_b200.learners.nonuniform_quantization.utils import NonUniformQuantization
+    mod = importlib.import_module('pocketflow_b200.nets.resnet_at_cifar10')
+    FLAGS.resnet_size = 8
+    mh = mod.ModelHelper()
+    for cap, size in ((None, 16), (6, 64)):
+        g = G.Graph()
+        with g.as_default():
+            with G.variable_scope('data'):
+                im, _ = mh.build_dataset_train().get_next()
+            with G.variable_scope('model'):
+                mh.forward_train(im)
+                before = set(g.variables)
+                nq = NonUniformQuantization(g, 256, False, 'quantile', 'split', codebook_bits_cap=cap)
+                ops_ = nq.search_matmul_op(False)
+                nq.insert_quant_op_for_weights({o.name: 4 for o in ops_})
+        new = sorted(set(g.variables) - before)
+        assert len(new) == len(ops_) == 9
+        for o in ops_:
+            v = o.vars['clusters']
+            assert v.name == 'model/' + o.name.split('/', 1)[1] + '/nonuniform_quantize/clusters:0' and v.name in new
+            assert v.trainable and v.shape == (size,)
+        spec = nq.weight_quant_spec()
+        assert spec['kind'] == 'nonuniform' and spec['bits'] == [4] * 9 and spec['train_clusters'] is False
+    FLAGS.reset()
+
+
+def test_channel_pruned_learner_builds_the_full_and_the_pruned_model_side_by_side(tmp_path):
+    """ChannelPrunedGpuLearner's graph (learners/channel_pruning_gpu/learner.py:207-229, :347-352), on the CPU (planning
+    only): the full model under 'model', the pruned one under 'pruned_model', their Conv2D ops paired by index, the
+    maskable variables = the pruned model's Conv2D kernels (depthwise excluded), the per-layer ratios of both protocols."""
+    import importlib
+    FLAGS.reset()
+    import pocketflow_b200.datasets.ilsvrc12_dataset as D
+    importlib.reload(D)
+    M = importlib.reload(importlib.import_module('pocketflow_b200.nets.mobilenet_at_ilsvrc12'))
+    L = importlib.import_module('pocketflow_b200.learners.channel_pruning_gpu.learner')
+    FLAGS.batch_size, FLAGS.nb_classes, FLAGS.cpg_prune_ratio = 2, 1001, 0.3
+    lrn = L.ChannelPrunedGpuLearner(None, M.ModelHelper())
+    assert lrn.model_scope == 'pruned_model' and lrn.nb_layers == 15
+    assert len(lrn.conv_ops_full) == len(lrn.conv_ops_prnd) == 15
+    for f, p in zip(lrn.conv_ops_full, lrn.conv_ops_prnd):
+        assert f.name.startswith('model/') and p.name == 'pruned_' + f.name and f.output.shape == p.output.shape
+        assert 'depthwise' not in p.name
+    assert lrn.maskable_var_names == [op.vars['kernel'].name for op in lrn.conv_ops_prnd]
+    assert lrn.prune_ratios == [0.0] + [0.3] * 13 + [0.0]                  # head and tail skipped (:452-454)
+    # the training executor only holds the pruned model; the full model has its own store with the 'model/' names
+    assert all(v.name.startswith('pruned_model/') for v in lrn.sess_train.store.train_vars)
+    full_names = {v.name for v in lrn.store_full.train_vars + lrn.store_full.other_vars}
+    assert full_names == {'model/' + v.name.split('/', 1)[1]
+                          for v in lrn.sess_train.store.train_vars + lrn.sess_train.store.other_vars}
+    assert not lrn.sess_train.fused_add and lrn.channels_chosen is False
+    # 'list' protocol: one ratio per Conv2D layer from a file (:455-458)
+    ratios = [0.0, 0.5, 0.25] + [0.1] * 12
+    (tmp_path / 'r.txt').write_text(','.join(str(r) for r in ratios) + '\n')
+    FLAGS.cpg_prune_ratio_type, FLAGS.cpg_prune_ratio_file = 'list', str(tmp_path / 'r.txt')
+    assert L.ChannelPrunedGpuLearner(None, M.ModelHelper()).prune_ratios == ratios
+    FLAGS.cpg_prune_ratio_type = 'bogus'
+    with pytest.raises(ValueError):
+        L.ChannelPrunedGpuLearner(None, M.ModelHelper())
+    FLAGS.reset()
