@@ -882,3 +882,34 @@ def test_codebook_gradient_kat():
     assert np.allclose(out.detach().numpy(), q, rtol=1e-6)
     out.backward(torch.tensor(g))
     assert np.allclose(ct.grad.numpy(), [24.0, 20.0], rtol=1e-6) and np.allclose(wt.grad.numpy(), g, rtol=1e-6)
+
+
+def test_ws_layerwise_regression_is_wired_like_the_reference():
+    """The pruning-ratio search's regression stage (learners/weight_sparsification/pr_optimizer.py:283-314): the ops
+    get_ops_by_scope_n_patterns picks on this repo's graphs (golden 'ws_core_ops', from the reference's own function)
+    against WeightSparseLearner.pr_core_ops; and what __build_layer_rg_ops builds, executed from the reference source:
+    l2_loss(out_pruned - out_full), Adam at ws_lrn_rate_rg, gradient times mask."""
+    import os
+    import sys
+    from types import SimpleNamespace
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), 'golden'))
+    from graphs_for_golden import GRAPHS, build_graph
+    from pocketflow_b200.flags import FLAGS
+    from pocketflow_b200.learners.weight_sparsification.learner import WeightSparseLearner as L
+    from pocketflow_b200.learners.weight_sparsification.utils import get_maskable_vars
+    gold = _cpg_gold()
+    rg = gold['ws_layer_regression']
+    assert rg['loss'] == 'l2_loss' and rg['loss_is_pruned_minus_full'] and rg['masked_grad_matches']
+    FLAGS.reset()
+    assert rg['lrn_rate'] == FLAGS.ws_lrn_rate_rg == 3e-2
+    for e in gold['ws_core_ops']:
+        net, flags, dst = GRAPHS[e['graph']]
+        g = build_graph(net, flags, dst)
+        model_name = 'mobilenet_v1' if e['graph'].startswith('mobilenet') else 'resnet_20'
+        me = SimpleNamespace(model_name=model_name, model_scope='model', sess_train=SimpleNamespace(ops=g.ops))
+        got = L.pr_core_ops(me)
+        assert [o.name for o in got] == e['ops'], e['graph']
+        # ... and they pair, by index, with the variables the learner masks (pr_optimizer.py:303)
+        trainable = [v for v in g.variables.values() if v.name.startswith('model/') and v.trainable]
+        assert [o.vars['kernel'].name for o in got] == [v.name for v in get_maskable_vars(trainable)], e['graph']
+    FLAGS.reset()
