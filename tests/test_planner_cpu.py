@@ -257,3 +257,42 @@ def test_channel_pruned_learner_builds_the_full_and_the_pruned_model_side_by_sid
     with pytest.raises(ValueError):
         L.ChannelPrunedGpuLearner(None, M.ModelHelper())
     FLAGS.reset()
+
+
+def test_learner_restore_helpers(tmp_path, capsys):
+    """AbstractLearner.restore_model / restore_for_eval / eval_nb_iters against a CPU parameter store: the latest
+    checkpoint beside the path is loaded and counted; evaluate() only restores under --exec_mode eval (while training, the
+    executor already holds what was saved); the iteration count is the reference's ceil(nb_smpls_eval / batch_size_eval)."""
+    import numpy as np
+    from types import SimpleNamespace
+    import pocketflow_b200.datasets.cifar10_dataset  # noqa: F401  (declares nb_smpls_eval / batch_size_eval)
+    from pocketflow_b200.engine import ParamStore
+    from pocketflow_b200.learners.abstract_learner import AbstractLearner, save_checkpoint
+    FLAGS.reset()
+    init = lambda rng, shape: rng.standard_normal(shape).astype(np.float32)
+    vs = [G.Variable('model/a/kernel:0', (4, 4), init), G.Variable('model/a/bias:0', (4,), init)]
+    st = ParamStore(vs, torch.device('cpu'))
+    me = SimpleNamespace(sess_train=SimpleNamespace(store=st), iterator_train=SimpleNamespace(batch_size=32))
+    me.restore_model = lambda path, **kw: AbstractLearner.restore_model(me, path, **kw)
+    path = str(tmp_path / 'ck' / 'model.ckpt')
+    with pytest.raises(ValueError, match='no checkpoint'):
+        AbstractLearner.restore_model(me, path)
+    want = {k: v + 1.0 for k, v in st.state_dict().items()}
+    save_checkpoint(path, want, 7)
+    fn = AbstractLearner.restore_model(me, path)
+    assert fn.endswith('-7.npz') and '2 of 2 trainable variables' in capsys.readouterr().out
+    assert all(np.array_equal(st.state_dict()[k], want[k]) for k in want)
+    # restore_for_eval: a no-op while training, a restore under --exec_mode eval
+    st.P.zero_()
+    FLAGS.exec_mode = 'train'
+    AbstractLearner.restore_for_eval(me, path)
+    assert float(st.P.abs().sum()) == 0.0
+    FLAGS.exec_mode = 'eval'
+    AbstractLearner.restore_for_eval(me, path)
+    assert all(np.array_equal(st.state_dict()[k], want[k]) for k in want)
+    # iteration count
+    FLAGS.nb_smpls_eval, FLAGS.batch_size_eval, FLAGS.data_dir_local = 10000, 96, None
+    assert AbstractLearner.eval_nb_iters(me) == 105 and AbstractLearner.eval_nb_iters(me, 3) == 3
+    FLAGS.data_dir_local = '/data'                                     # real data is read at the step's batch size
+    assert AbstractLearner.eval_nb_iters(me) == 313
+    FLAGS.reset()
